@@ -1,0 +1,222 @@
+/*
+ * rtb200.h -- C ABI of the B200-native ray-tracing hot path (librtb200.so).
+ *
+ * This is the drop-in boundary for ONE path of TomClabault/RayTracerCPP: everything that sits behind
+ * `Renderer::ray_trace()` + `Renderer::post_process()` (SSAA only) and `BVH::intersect()`.
+ * The reference has no FFI of its own; the seam is the public section of `class Renderer`
+ * (tp2/projets/renderer/renderer.h:38-169) and `class BVH` (tp2/projets/bvh.h:302,307).  Each entry
+ * point below names the reference member it replaces.  A header-only C++ adapter with the reference's
+ * method names lives in `rtb200_renderer.hpp`; INTEGRATION.md shows how a maintainer swaps it in.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all host buffers are caller-owned and copied during the call;
+ *  - every function returns RT_OK (0) or a negative RtStatus; rt_last_error() gives the message;
+ *  - a handle is bound to one CUDA device and is NOT thread-safe (one caller thread, like the
+ *    reference's RenderThread, QT/mainWindowThreads.cpp:39-65);
+ *  - there is no CPU fallback: without a usable CUDA device rt_create() fails with RT_ERR_CUDA.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RtContext RtContext;
+
+typedef enum RtStatus {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,      /* bad argument / unsupported setting            */
+    RT_ERR_CUDA = -2,         /* CUDA runtime error (message in rt_last_error) */
+    RT_ERR_STATE = -3,        /* call order (e.g. render before set_triangles) */
+    RT_ERR_UNSUPPORTED = -4   /* a RenderSettings switch outside the path      */
+} RtStatus;
+
+/* Blinn-Phong material: the fields of `Material` (tp2/src/materials.h:14-38) that the path reads. */
+typedef struct RtMaterial {
+    float ambient_coeff[3];
+    float diffuse[3];
+    float specular[3];
+    float emission[3];
+    float reflection;
+    float roughness;
+    float ns;
+    float specular_threshold; /* set by MainWindow::precompute_materials, QT/mainwindow.cpp:240-249 */
+} RtMaterial;
+
+/* Shading modes: RenderSettings::ShadingMethod, tp2/projets/renderer/rendererSettings.h:8-26. */
+enum {
+    RT_SHADING = 0,
+    RT_ABS_NORMALS_SHADING = 1,
+    RT_PASTEL_NORMALS_SHADING = 2,
+    RT_BARYCENTRIC_COORDINATES_SHADING = 3,
+    RT_VISUALIZE_AO = 4
+};
+
+/* POD mirror of `RenderSettings` (tp2/projets/renderer/rendererSettings.h:6-105), same defaults via
+ * rt_default_settings().  Switches that leave the path (rasterizer, SSAO, parallax, cube-map skybox)
+ * are carried so a caller can pass its struct through; rt_render() refuses them (RT_ERR_UNSUPPORTED). */
+typedef struct RtSettings {
+    int32_t image_width;
+    int32_t image_height;
+    int32_t enable_ssaa;
+    int32_t ssaa_factor;
+    int32_t hybrid_rasterization_tracing; /* must be 0 */
+    int32_t shading_method;
+    int32_t compute_shadows;
+    int32_t max_recursion_depth;
+    int32_t enable_bvh;                   /* must be 1 */
+    int32_t bvh_max_depth;
+    int32_t bvh_leaf_object_count;
+    int32_t enable_ssao;                  /* must be 0 */
+    int32_t enable_ambient;
+    int32_t enable_diffuse;
+    int32_t enable_specular;
+    int32_t enable_emissive;
+    int32_t rough_reflections_sample_count;
+    int32_t enable_ao_mapping;
+    int32_t enable_diffuse_mapping;
+    int32_t enable_normal_mapping;
+    int32_t enable_displacement_mapping;  /* must be 0 */
+    int32_t enable_roughness_mapping;
+    int32_t enable_skysphere;
+    int32_t enable_skybox;                /* must be 0 */
+    /* Seed of the per-pixel xorshift32 streams used by rough reflections.  The reference owns one
+     * generator per OpenMP thread seeded from std::rand() (renderer.cpp:51-61), which is not
+     * reproducible; the shared stream is state(px,py) = rt_pixel_seed(py*W'+px, rng_seed). */
+    uint32_t rng_seed;
+} RtSettings;
+
+/* Texture slots: Renderer::set_{ao,diffuse,normal,roughness}_map / set_skysphere, renderer.cpp:194-201. */
+enum {
+    RT_TEX_AO = 0,
+    RT_TEX_DIFFUSE = 1,
+    RT_TEX_NORMAL = 2,
+    RT_TEX_ROUGHNESS = 3,
+    RT_TEX_SKYSPHERE = 4,
+    RT_TEX_COUNT = 5
+};
+
+/* Per-render counters (rays actually traced + what the pipeline did). */
+typedef struct RtRenderStats {
+    uint64_t primary_rays;
+    uint64_t shadow_rays;      /* depth-0 shadow rays                                       */
+    uint64_t reflection_rays;  /* closest-hit rays of reflection fans (all depths)          */
+    uint64_t reflection_shadow_rays;
+    uint64_t primary_hits;
+    uint32_t kernel_launches;  /* launches of this library's kernels during the call        */
+    float    device_ms;        /* CUDA-event time of the kernels (excludes the D2H copy)    */
+    float    trace_primary_ms; /* per-stage CUDA-event times, summed over chunks            */
+    float    shade_ms;
+    float    reflect_ms;
+    float    shadow_ms;
+    float    resolve_ms;
+} RtRenderStats;
+
+/* Flattened-tree facts, for tests and DESIGN.md (the reference tree has the same node/leaf counts). */
+typedef struct RtBvhInfo {
+    uint64_t triangles;
+    uint64_t nodes;            /* all octree cells, empty leaves included (bvh.h:153-167)   */
+    uint64_t leaves;
+    uint64_t empty_leaves;
+    uint64_t interior;
+    uint32_t max_depth_reached;
+    uint32_t max_leaf_size;
+    uint64_t child_records;    /* 64-byte slab records resident in HBM                      */
+    uint64_t device_bytes;     /* records + triangles + shading side arrays                 */
+    double   build_ms;         /* host octree build + flatten                               */
+    double   upload_ms;
+} RtBvhInfo;
+
+void rt_default_settings(RtSettings* s);
+uint32_t rt_pixel_seed(uint32_t pixel_index, uint32_t rng_seed);
+
+/* Renderer::Renderer() -- renderer.cpp:80.  `device` is a CUDA ordinal. */
+int rt_create(int device, RtContext** out);
+void rt_destroy(RtContext* ctx);
+const char* rt_last_error(const RtContext* ctx); /* ctx may be NULL for rt_create failures */
+
+/* Renderer::set_triangles(const std::vector<Triangle>&) -- renderer.cpp:137-144.
+ * xyz9: n*9 floats (a,b,c); uv6: n*6 floats (u_a,u_b,u_c,v_a,v_b,v_c) as Triangle::_tex_coords_u/_v
+ * (triangle.h:99-103) or NULL for the default (-1,-1,-1); mat: n material indices or NULL (-1).
+ * Does not build the tree: rt_build_bvh() is separate, as reconstruct_bvh_new() is in the reference. */
+int rt_set_triangles(RtContext* ctx, const float* xyz9, const float* uv6, const int32_t* mat, size_t n);
+
+/* BVH::BVH(std::vector<Triangle>*, int max_depth, int leaf_max_obj_count) -- bvh.cpp:19-43;
+ * Renderer::reconstruct_bvh_new -- renderer.cpp:243-246.  Builds the same octree as the reference's
+ * sequential insertion, flattens it, uploads it. */
+int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count);
+int rt_bvh_info(const RtContext* ctx, RtBvhInfo* out);
+
+/* Renderer::set_object_transform(const Transform&) -- renderer.cpp:214-224: re-transforms every triangle
+ * by `m` (row-major 4x4, applied as Transform::operator()(Point), mat.cpp:83-100) and rebuilds the tree.
+ * The caller composes object_transform * previous^-1 exactly as the reference does. */
+int rt_transform_triangles(RtContext* ctx, const float m[16], int max_depth, int leaf_max_obj_count);
+
+/* Renderer::set_materials / get_materials().materials -- renderer.cpp:150-152. */
+int rt_set_materials(RtContext* ctx, const RtMaterial* mats, size_t n);
+
+/* Renderer::set_*_map(const Image&) / set_skysphere -- renderer.cpp:194-201.  Texels are RGBA, row 0 first
+ * (no Y flip, QT/mainwindow.cpp:285).  f32 is the reference's `Image` storage; u8 is the on-disk form,
+ * decoded on the device as u8 * (1/255.f) exactly like read_image (image_io.cpp:115-121). */
+int rt_set_texture_f32(RtContext* ctx, int slot, const float* rgba, int width, int height);
+int rt_set_texture_u8(RtContext* ctx, int slot, const uint8_t* rgba, int width, int height);
+int rt_clear_texture(RtContext* ctx, int slot); /* Renderer::clear_*_map -- renderer.cpp:203-207 */
+
+/* Camera state: Camera::_perspective_proj_mat_inv, _camera_to_world_mat, _position
+ * (scene/camera.h:9-33; set by change_camera_fov/aspect_ratio + set_camera_transform, renderer.cpp:189-233).
+ * Matrices are row-major (Transform::m[row][col], mat.h). */
+int rt_set_camera(RtContext* ctx, const float proj_inv[16], const float cam_to_world[16], const float position[3]);
+/* Renderer::set_light_position -- renderer.cpp:191. */
+int rt_set_light(RtContext* ctx, const float position[3]);
+
+/* Renderer::ray_trace() + Renderer::post_process() -- renderer.cpp:1068-1135 (what render() times,
+ * utils/mainUtils.cpp:6-21).  argb_out: image_width*image_height ARGB32 words, row 0 = bottom row, exactly
+ * the layout of Renderer::get_image() (renderer.cpp:1086).  Host pointer; includes the D2H copy. */
+int rt_render(RtContext* ctx, const RtSettings* settings, uint32_t* argb_out, RtRenderStats* stats);
+
+/* Same frame, result left in device memory (`d_argb_out` is a device pointer on the context's device).
+ * Tile sharding for the multi-GPU path: the frame is cut into tile_size x tile_size final-resolution
+ * tiles; this call renders only tiles with (tile_index % tile_mod) == tile_rem (tile_mod = 1 -> all)
+ * and leaves the other pixels of d_argb_out untouched. */
+int rt_render_device(RtContext* ctx, const RtSettings* settings, uint32_t* d_argb_out,
+                     int tile_size, int tile_mod, int tile_rem, RtRenderStats* stats);
+
+/* Pack / unpack the tiles owned by (tile_mod, tile_rem) between the row-major frame and a tile-major
+ * staging buffer -- the operand of the framebuffer all-gather.  rt_tile_count gives how many tiles the
+ * shard owns; every tile occupies tile_size*tile_size words in the staging buffer (edge tiles padded). */
+int rt_tile_count(const RtSettings* settings, int tile_size, int tile_mod, int tile_rem);
+int rt_pack_tiles(RtContext* ctx, const RtSettings* settings, const uint32_t* d_frame, uint32_t* d_staging,
+                  int tile_size, int tile_mod, int tile_rem);
+int rt_unpack_tiles(RtContext* ctx, const RtSettings* settings, uint32_t* d_frame, const uint32_t* d_staging,
+                    int tile_size, int tile_mod, int tile_rem);
+
+/* Batched bool BVH::intersect(const Ray&, HitInfo&) const -- bvh.h:307, bvh.cpp:68-71.
+ * o3/d3: n*3 floats.  Outputs (any may be NULL): tri_id = index into the rt_set_triangles array or -1
+ * (HitInfo::triangle - triangles.data()), t/u/v = HitInfo::t,u,v (hitInfo.h:8-29; t = -1 on a miss). */
+int rt_intersect(RtContext* ctx, const float* o3, const float* d3, size_t n,
+                 int32_t* tri_id, float* t, float* u, float* v);
+
+/* Batched Renderer::is_shadowed -- renderer.cpp:340-402.  p3 = inter_point, n3 = shading normal,
+ * light = the context's light.  occluded[i] = 1 iff the reference returns true. */
+int rt_occluded(RtContext* ctx, const float* p3, const float* n3, size_t n, uint8_t* occluded);
+
+/* Primary-ray generation only (renderer.cpp:1083-1098) for the supersampled frame of `settings`:
+ * o3/d3 receive (W*f)*(H*f)*3 floats, pixel-major, row 0 = bottom row.  For parity tests. */
+int rt_generate_primary_rays(RtContext* ctx, const RtSettings* settings, float* o3, float* d3);
+
+/* Quantise + SSAA resolve only (imageUtils.h:98-152) on a host ARGB32 image; for parity tests. */
+int rt_resolve_ssaa(RtContext* ctx, const uint32_t* argb_in, int width, int height, int factor, uint32_t* argb_out);
+
+/* Device-resident throughput probes used by bench.py: trace the primary (+shadow) rays of `settings`
+ * `repeats` times without any host traffic and return the mean CUDA-event milliseconds of the dominant
+ * closest-hit kernel in *closest_ms and of the any-hit kernel in *anyhit_ms. */
+int rt_profile_trace(RtContext* ctx, const RtSettings* settings, int repeats, float* closest_ms, float* anyhit_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */
