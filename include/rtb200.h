@@ -170,6 +170,14 @@ int rt_clear_texture(RtContext* ctx, int slot); /* Renderer::clear_*_map -- rend
  * (scene/camera.h:9-33; set by change_camera_fov/aspect_ratio + set_camera_transform, renderer.cpp:189-233).
  * Matrices are row-major (Transform::m[row][col], mat.h). */
 int rt_set_camera(RtContext* ctx, const float proj_inv[16], const float cam_to_world[16], const float position[3]);
+/* Host helpers with the reference's float arithmetic, for callers that hold (fov, aspect) or a transform rather
+ * than the derived matrices: Perspective(fov, aspect, znear, zfar).inverse() (mat.cpp:307-319,378-447; the
+ * reference's Camera uses znear 0.1, zfar 1000, scene/camera.h:11) and Transform::inverse().  Row-major. */
+void rt_perspective_inverse(float fov, float aspect, float znear, float zfar, float proj_inv_out[16]);
+void rt_invert_transform(const float m[16], float out[16]);
+/* Transform::operator()(const Point&) -- mat.cpp:83-100 (e.g. Camera::_position = transform(Point(0,0,0))). */
+void rt_transform_point(const float m[16], const float p[3], float out[3]);
+
 /* Renderer::set_light_position -- renderer.cpp:191. */
 int rt_set_light(RtContext* ctx, const float position[3]);
 
@@ -210,11 +218,6 @@ int rt_generate_primary_rays(RtContext* ctx, const RtSettings* settings, float* 
 
 /* Quantise + SSAA resolve only (imageUtils.h:98-152) on a host ARGB32 image; for parity tests. */
 int rt_resolve_ssaa(RtContext* ctx, const uint32_t* argb_in, int width, int height, int factor, uint32_t* argb_out);
-
-/* Device-resident throughput probes used by bench.py: trace the primary (+shadow) rays of `settings`
- * `repeats` times without any host traffic and return the mean CUDA-event milliseconds of the dominant
- * closest-hit kernel in *closest_ms and of the any-hit kernel in *anyhit_ms. */
-int rt_profile_trace(RtContext* ctx, const RtSettings* settings, int repeats, float* closest_ms, float* anyhit_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,157 @@
+// host_common.h -- host-side helpers of the C ABI that do not touch CUDA: settings defaults and validation,
+// tile ownership.  Shared by rtb200.cu and by the single-threaded kernel emulation under tests/hostsim.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rtb200.h"
+#include "rt_math.h"
+
+namespace rtb {
+
+// Perspective(fov, aspect, znear, zfar) -- mat.cpp:307-319 with radians() of mat.cpp:13-16, row-major.
+inline M4 perspective_matrix(float fov, float aspect, float znear, float zfar)
+{
+    const float rad = ((float)3.14159265358979323846 / 180) * fov;
+    const float itan = 1 / tanf(rad * 0.5f);
+    const float id = 1 / (znear - zfar);
+    M4 p;
+    memset(&p, 0, sizeof(p));
+    p.m[0][0] = itan / aspect;
+    p.m[1][1] = itan;
+    p.m[2][2] = (zfar + znear) * id;
+    p.m[2][3] = 2.f * zfar * znear * id;
+    p.m[3][2] = -1;
+    return p;
+}
+
+// Transform::inverse() -- mat.cpp:378-447: Gauss-Jordan elimination with full pivoting, in place.  The order of
+// the float operations follows the reference so that Camera::_perspective_proj_mat_inv comes out bit-identical.
+inline M4 invert_matrix(const M4& src)
+{
+    M4 a = src;
+    int pivot_row[4], pivot_col[4], done[4] = {0, 0, 0, 0};
+    for (int step = 0; step < 4; step++) {
+        int r = 0, c = 0;
+        float largest = 0.f;
+        for (int j = 0; j < 4; j++) {
+            if (done[j] == 1) continue;
+            for (int k = 0; k < 4; k++)
+                if (done[k] == 0 && fabsf(a.m[j][k]) >= largest) { largest = fabsf(a.m[j][k]); r = j; c = k; }
+        }
+        done[c]++;
+        if (r != c)
+            for (int k = 0; k < 4; k++) { float tmp = a.m[r][k]; a.m[r][k] = a.m[c][k]; a.m[c][k] = tmp; }
+        pivot_row[step] = r;
+        pivot_col[step] = c;
+        const float inv_pivot = 1.f / a.m[c][c];
+        a.m[c][c] = 1.f;
+        for (int k = 0; k < 4; k++) a.m[c][k] *= inv_pivot;
+        for (int j = 0; j < 4; j++) {
+            if (j == c) continue;
+            const float factor = a.m[j][c];
+            a.m[j][c] = 0;
+            for (int k = 0; k < 4; k++) a.m[j][k] -= a.m[c][k] * factor;
+        }
+    }
+    for (int step = 3; step >= 0; step--)
+        if (pivot_row[step] != pivot_col[step])
+            for (int k = 0; k < 4; k++) {
+                float tmp = a.m[k][pivot_row[step]];
+                a.m[k][pivot_row[step]] = a.m[k][pivot_col[step]];
+                a.m[k][pivot_col[step]] = tmp;
+            }
+    return a;
+}
+
+constexpr int kMaxRecursionDepth = 8;             // the device stack of k_reflect is sized for this
+
+inline void default_settings(RtSettings* s)
+{
+    memset(s, 0, sizeof(*s));                     // rendererSettings.h:29-102
+    s->image_width = 1024;
+    s->image_height = 1024;
+    s->ssaa_factor = 2;
+    s->shading_method = RT_SHADING;
+    s->max_recursion_depth = 5;
+    s->enable_bvh = 1;
+    s->bvh_max_depth = 12;
+    s->bvh_leaf_object_count = 40;
+    s->enable_ambient = s->enable_diffuse = s->enable_specular = s->enable_emissive = 1;
+    s->rough_reflections_sample_count = 3;
+}
+
+// Returns RT_OK or an error code with a message in `why`.
+inline int check_settings(const RtSettings* s, std::string& why)
+{
+    char buf[256];
+    auto bad = [&](int code, const char* msg) { why = msg; return code; };
+    if (!s) return bad(RT_ERR_INVALID, "settings is NULL");
+    if (s->image_width <= 0 || s->image_height <= 0) {
+        snprintf(buf, sizeof(buf), "image size %dx%d", s->image_width, s->image_height);
+        return bad(RT_ERR_INVALID, buf);
+    }
+    if (s->enable_ssaa && s->ssaa_factor < 1) return bad(RT_ERR_INVALID, "ssaa_factor < 1");
+    if (s->hybrid_rasterization_tracing) return bad(RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing stays on the host (renderer.cpp:869-1006)");
+    if (s->enable_ssao) return bad(RT_ERR_UNSUPPORTED, "enable_ssao is a host post-process (renderer.cpp:1229-1434)");
+    if (s->enable_displacement_mapping) return bad(RT_ERR_UNSUPPORTED, "parallax mapping is outside the path (renderer.cpp:480-554)");
+    if (s->enable_skybox && !s->enable_skysphere) return bad(RT_ERR_UNSUPPORTED, "cube-map skybox is outside the path (skybox.cpp:12-51)");
+    if (!s->enable_bvh) return bad(RT_ERR_UNSUPPORTED, "enable_bvh = false (brute force) is not offered");
+    if (s->shading_method < RT_SHADING || s->shading_method > RT_VISUALIZE_AO) return bad(RT_ERR_INVALID, "shading_method out of range");
+    if (s->max_recursion_depth > kMaxRecursionDepth) return bad(RT_ERR_INVALID, "max_recursion_depth above the supported maximum (8)");
+    if (s->rough_reflections_sample_count < 0) return bad(RT_ERR_INVALID, "rough_reflections_sample_count < 0");
+    return RT_OK;
+}
+
+struct SceneFacts {
+    bool bvh_valid, camera_set;
+    uint32_t n_tris;
+    int n_mats, min_mat_index, max_mat_index;
+    int tex_format[RT_TEX_COUNT];
+};
+
+inline int check_scene_for_render(const SceneFacts& f, const RtSettings* s, std::string& why)
+{
+    auto bad = [&](int code, const char* msg) { why = msg; return code; };
+    if (!f.bvh_valid) return bad(RT_ERR_STATE, "rt_build_bvh has not been called for the current triangles");
+    if (!f.camera_set) return bad(RT_ERR_STATE, "rt_set_camera has not been called");
+    const bool rt = s->shading_method == RT_SHADING;
+    if (rt && f.n_tris > 0) {
+        // the reference asserts on a bad material index (materials.h:117); here it is an error return
+        if (f.n_mats == 0) return bad(RT_ERR_STATE, "RT_SHADING needs materials (rt_set_materials)");
+        if (f.min_mat_index < 0 || f.max_mat_index >= f.n_mats) return bad(RT_ERR_STATE, "triangle material index out of range");
+    }
+    struct { int on; int slot; const char* msg; } need[] = {
+        {(rt || s->shading_method == RT_VISUALIZE_AO) && s->enable_ao_mapping, RT_TEX_AO, "ao mapping enabled but no ao map set"},
+        {rt && s->enable_diffuse_mapping, RT_TEX_DIFFUSE, "diffuse mapping enabled but no diffuse map set"},
+        {rt && s->enable_normal_mapping, RT_TEX_NORMAL, "normal mapping enabled but no normal map set"},
+        {rt && s->enable_roughness_mapping, RT_TEX_ROUGHNESS, "roughness mapping enabled but no roughness map set"},
+        {s->enable_skysphere, RT_TEX_SKYSPHERE, "skysphere enabled but no skysphere set"},
+    };
+    for (auto& nd : need)
+        if (nd.on && f.tex_format[nd.slot] == 0) return bad(RT_ERR_STATE, nd.msg);
+    return RT_OK;
+}
+
+// Final-resolution tiles owned by shard (tile_mod, tile_rem): dealt round-robin along a row-shifted order so
+// that one shard's tiles never line up in a column (sky / geometry cost is spread over the shards).
+inline std::vector<uint32_t> owned_tiles(const RtSettings* s, int tile_size, int tile_mod, int tile_rem, int* tiles_x_out)
+{
+    int tiles_x = (s->image_width + tile_size - 1) / tile_size;
+    int tiles_y = (s->image_height + tile_size - 1) / tile_size;
+    if (tiles_x_out) *tiles_x_out = tiles_x;
+    std::vector<uint32_t> out;
+    const int pitch = (tiles_x % tile_mod == 0) ? tiles_x + 1 : tiles_x;
+    for (int i = 0; i < tiles_x * tiles_y; i++) {
+        int ty = i / tiles_x, tx = i % tiles_x;
+        if ((tx + ty * pitch) % tile_mod == tile_rem) out.push_back((uint32_t)i);
+    }
+    return out;
+}
+
+} // namespace rtb

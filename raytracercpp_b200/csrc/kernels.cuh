@@ -1,0 +1,285 @@
+// kernels.cuh -- the wavefront pipeline's __global__ kernels (sm_100a).  One frame is
+//
+//   k_primary   ray generation + closest-hit traversal, one 16x16 patch per warp fetched from an atomic counter;
+//               misses are shaded and written at once, hits are appended to the hit queue with one atomic per
+//               warp (ballot + popc), reflective hits also to the reflection queue
+//   k_reflect   (only if a material reflects) one thread per reflective hit walks its rough-reflection fan
+//   k_shade     one thread per queued hit: textures / Blinn-Phong, any-hit shadow ray, compose, quantise, store
+//   k_resolve   integer SSAA box filter of the quantised samples (imageUtils.h:98-147)
+//
+// plus the batch kernels behind rt_intersect / rt_occluded / rt_generate_primary_rays and tile pack/unpack.
+// Nothing here is a dense contraction, so no tensor-core path; the roofline that bounds these kernels is the
+// node/triangle fetch bandwidth.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "rt_device.h"
+
+namespace rtb {
+
+constexpr int kPatch = 16;           // a warp's work item is a kPatch x kPatch block of supersampled pixels
+constexpr int kPrimaryThreads = 128;
+constexpr int kQueueThreads = 128;
+
+struct ChunkCounters {               // one per chunk, zeroed before the frame
+    unsigned int next_patch;
+    unsigned int n_hits;
+    unsigned int n_refl;
+    unsigned int stack_overflow;
+    unsigned long long refl_rays;
+    unsigned long long refl_shadow_rays;
+};
+
+// Which part of the frame a launch covers: owned tiles [tile_begin, tile_end) of the shard's tile list.
+struct WorkView {
+    const uint32_t* tiles;           // indices into the tiles_x * tiles_y grid of final-resolution tiles
+    uint32_t tile_begin, tile_end;
+    int32_t tiles_x;
+    int32_t tile_px;                 // tile side in supersampled pixels (tile_size * factor)
+    int32_t patches_per_side;        // ceil(tile_px / kPatch)
+};
+
+struct QueueView {                   // hit queue (SoA) of one chunk
+    uint32_t* pix;                   // py * rw + px of the supersampled frame
+    int32_t* tri;                    // leaf-order triangle
+    float* t;
+    float* u;
+    float* v;
+    uint32_t* refl_idx;              // reflection queue: indices into the hit queue
+    float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
+    uint32_t capacity;
+};
+
+__global__ void __launch_bounds__(kPrimaryThreads)
+k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, int any_reflective)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t pps = (uint32_t)wk.patches_per_side;
+    const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&cnt->next_patch, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        const uint32_t tile = wk.tiles[wk.tile_begin + w / (pps * pps)];
+        const uint32_t pin = w % (pps * pps);
+        const int tx = (int)(tile % (uint32_t)wk.tiles_x), ty = (int)(tile / (uint32_t)wk.tiles_x);
+        const int lx0 = (int)(pin % pps) * kPatch, ly0 = (int)(pin / pps) * kPatch;
+#pragma unroll 1
+        for (int sub = 0; sub < (kPatch / 8) * (kPatch / 4); sub++) {     // 8 x 4 pixels per pass
+            const int lx = lx0 + (sub % (kPatch / 8)) * 8 + (int)(lane & 7u);
+            const int ly = ly0 + (sub / (kPatch / 8)) * 4 + (int)(lane >> 3);
+            const int px = tx * wk.tile_px + lx, py = ty * wk.tile_px + ly;
+            const bool live = lx < wk.tile_px && ly < wk.tile_px && px < fr.rw && py < fr.rh;
+            bool hit = false, reflective = false;
+            HitRec hr;
+            hr.tri = -1; hr.t = -1.0f; hr.u = 1.0f; hr.v = 0.0f;
+            if (live) {
+                V3 o, d;
+                primary_ray(fr, px, py, o, d);
+                TraceCounters tc;
+                tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
+                bool found = trace_closest(sc, o, d, hr, &tc);
+                if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
+                hit = found && hr.t > 0.1f;                               // min_t, renderer.cpp:1039-1040
+                if (!hit) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+                else if (any_reflective) {
+                    TriShade ts = load_tri_shade(sc, hr.tri);
+                    reflective = load_material(sc, ts.mat).reflection > 0.0f;
+                }
+            }
+            // warp-ballot compaction of the live hits: one atomic per warp and queue
+            const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+            if (hmask) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt->n_hits, (unsigned)__popc(hmask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t slot = base + (uint32_t)__popc(hmask & ((1u << lane) - 1u));
+                if (hit) {
+                    q.pix[slot] = (uint32_t)py * (uint32_t)fr.rw + (uint32_t)px;
+                    q.tri[slot] = hr.tri; q.t[slot] = hr.t; q.u[slot] = hr.u; q.v[slot] = hr.v;
+                }
+                const unsigned rmask = __ballot_sync(0xffffffffu, reflective);
+                if (rmask) {
+                    uint32_t rbase = 0;
+                    if (lane == 0) rbase = atomicAdd(&cnt->n_refl, (unsigned)__popc(rmask));
+                    rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                    if (reflective) q.refl_idx[rbase + (uint32_t)__popc(rmask & ((1u << lane) - 1u))] = slot;
+                }
+            }
+        }
+    }
+}
+
+RT_DEV void queue_ray(const FrameView& fr, const QueueView& q, uint32_t i, V3& o, V3& d, HitRec& hr, uint32_t& pix)
+{
+    pix = q.pix[i];
+    hr.tri = q.tri[i]; hr.t = q.t[i]; hr.u = q.u[i]; hr.v = q.v[i];
+    primary_ray(fr, (int)(pix % (uint32_t)fr.rw), (int)(pix / (uint32_t)fr.rw), o, d);
+}
+
+__global__ void __launch_bounds__(kQueueThreads)
+k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
+{
+    const uint32_t n = cnt->n_refl;
+    TraceCounters tc;
+    tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t i = q.refl_idx[r];
+        V3 o, d;
+        HitRec hr;
+        uint32_t pix;
+        queue_ray(fr, q, i, o, d, hr, pix);
+        Hit hit = complete_hit(sc, hr);
+        V3 p;
+        MatView m;
+        shade_direct(sc, fr, o, d, hit, p, m);                             // updates hit.normal (normal mapping)
+        XorShift32 rng;
+        rng.state = pixel_seed(pix, fr.s.rng_seed);
+        Col c = compute_reflection(sc, fr, d, p, hit, m, 0, rng, &tc);
+        q.refl_rgb[3 * (size_t)i + 0] = c.r;
+        q.refl_rgb[3 * (size_t)i + 1] = c.g;
+        q.refl_rgb[3 * (size_t)i + 2] = c.b;
+    }
+    // warp-aggregated tallies
+    unsigned rr = __reduce_add_sync(0xffffffffu, tc.refl_rays);
+    unsigned rs = __reduce_add_sync(0xffffffffu, tc.refl_shadow_rays);
+    unsigned ov = __reduce_or_sync(0xffffffffu, tc.stack_overflow);
+    if ((threadIdx.x & 31u) == 0) {
+        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
+        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
+        if (ov) atomicOr(&cnt->stack_overflow, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kQueueThreads)
+k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* super)
+{
+    const uint32_t n = cnt->n_hits;
+    unsigned overflow = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 o, d;
+        HitRec hr;
+        uint32_t pix;
+        queue_ray(fr, q, i, o, d, hr, pix);
+        Hit hit = complete_hit(sc, hr);
+        Col c;
+        if (fr.s.shading_method != RT_SHADING)
+            c = shade_debug(sc, fr, hit);
+        else {
+            V3 p;
+            MatView m;
+            Col direct = shade_direct(sc, fr, o, d, hit, p, m);
+            bool shadowed = false;
+            if (fr.s.compute_shadows) {
+                TraceCounters tc;
+                tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
+                shadowed = trace_occluded(sc, p, hit.normal, fr.light, &tc);
+                overflow |= tc.stack_overflow;
+            }
+            Col refl = col(0.0f);
+            if (m.reflection > 0.0f)
+                refl = col(q.refl_rgb[3 * (size_t)i], q.refl_rgb[3 * (size_t)i + 1], q.refl_rgb[3 * (size_t)i + 2]);
+            c = shade_compose(fr, m, direct, shadowed, refl);
+        }
+        super[pix] = quantise_argb(c);
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+}
+
+// ImageUtils::downscale_image_qt_ARGB32 -- imageUtils.h:98-147: per channel, sum of the factor^2 quantised samples
+// divided (integer, truncating) by factor^2.  One thread per final pixel of the owned tiles.
+__global__ void k_resolve(const uint32_t* super, uint32_t* out, WorkView wk, int tile_size, int factor, int width, int height)
+{
+    const uint32_t per_tile = (uint32_t)tile_size * (uint32_t)tile_size;
+    const uint64_t total = (uint64_t)(wk.tile_end - wk.tile_begin) * per_tile;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t tile = wk.tiles[wk.tile_begin + (uint32_t)(g / per_tile)];
+        const uint32_t in = (uint32_t)(g % per_tile);
+        const int x = (int)(tile % (uint32_t)wk.tiles_x) * tile_size + (int)(in % (uint32_t)tile_size);
+        const int y = (int)(tile / (uint32_t)wk.tiles_x) * tile_size + (int)(in / (uint32_t)tile_size);
+        if (x >= width || y >= height) continue;
+        const int rw = width * factor;
+        int ar = 0, ag = 0, ab = 0;
+        for (int i = 0; i < factor; i++) {
+            const uint32_t* row = super + (size_t)(y * factor + i) * rw + (size_t)x * factor;
+            for (int j = 0; j < factor; j++) {
+                uint32_t c = __ldg(row + j);
+                ar += (int)((c >> 16) & 0xffu);
+                ag += (int)((c >> 8) & 0xffu);
+                ab += (int)(c & 0xffu);
+            }
+        }
+        const int ff = factor * factor;
+        ar /= ff; ag /= ff; ab /= ff;
+        out[(size_t)y * width + x] = 0xff000000u | ((uint32_t)(ar & 0xff) << 16) | ((uint32_t)(ag & 0xff) << 8) | (uint32_t)(ab & 0xff);
+    }
+}
+
+// Tile pack / unpack between the row-major frame and the tile-major staging buffer of the all-gather.
+__global__ void k_pack_tiles(const uint32_t* frame, uint32_t* staging, WorkView wk, int tile_size, int width, int height, int unpack,
+                             uint32_t* frame_out)
+{
+    const uint32_t per_tile = (uint32_t)tile_size * (uint32_t)tile_size;
+    const uint64_t total = (uint64_t)(wk.tile_end - wk.tile_begin) * per_tile;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t tile = wk.tiles[wk.tile_begin + (uint32_t)(g / per_tile)];
+        const uint32_t in = (uint32_t)(g % per_tile);
+        const int x = (int)(tile % (uint32_t)wk.tiles_x) * tile_size + (int)(in % (uint32_t)tile_size);
+        const int y = (int)(tile / (uint32_t)wk.tiles_x) * tile_size + (int)(in / (uint32_t)tile_size);
+        if (x >= width || y >= height) {
+            if (!unpack) staging[g] = 0u;
+            continue;
+        }
+        if (unpack) frame_out[(size_t)y * width + x] = staging[g];
+        else staging[g] = frame[(size_t)y * width + x];
+    }
+}
+
+// Batched BVH::intersect (bvh.h:307).
+__global__ void __launch_bounds__(kQueueThreads)
+k_intersect(SceneView sc, const float* o3, const float* d3, size_t n, const int32_t* orig, int32_t* tri_id, float* t, float* u,
+            float* v, unsigned int* overflow)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]);
+        V3 d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
+        HitRec hr;
+        TraceCounters tc;
+        tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
+        bool found = trace_closest(sc, o, d, hr, &tc);
+        if (tc.stack_overflow) atomicOr(overflow, 1u);
+        if (tri_id) tri_id[i] = found ? orig[hr.tri] : -1;
+        if (t) t[i] = found ? hr.t : -1.0f;
+        if (u) u[i] = found ? hr.u : 0.0f;
+        if (v) v[i] = found ? hr.v : 0.0f;
+    }
+}
+
+// Batched Renderer::is_shadowed (renderer.cpp:340-402).
+__global__ void __launch_bounds__(kQueueThreads)
+k_occluded(SceneView sc, V3 light, const float* p3, const float* n3, size_t n, uint8_t* occluded, unsigned int* overflow)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        V3 p = v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]);
+        V3 nn = v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]);
+        TraceCounters tc;
+        tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
+        occluded[i] = trace_occluded(sc, p, nn, light, &tc) ? 1 : 0;
+        if (tc.stack_overflow) atomicOr(overflow, 1u);
+    }
+}
+
+// Primary rays only (renderer.cpp:1083-1098), pixel-major.
+__global__ void k_raygen(FrameView fr, float* o3, float* d3)
+{
+    const size_t n = (size_t)fr.rw * fr.rh;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        V3 o, d;
+        primary_ray(fr, (int)(i % (size_t)fr.rw), (int)(i / (size_t)fr.rw), o, d);
+        o3[3 * i] = o.x; o3[3 * i + 1] = o.y; o3[3 * i + 2] = o.z;
+        d3[3 * i] = d.x; d3[3 * i + 1] = d.y; d3[3 * i + 2] = d.z;
+    }
+}
+
+} // namespace rtb

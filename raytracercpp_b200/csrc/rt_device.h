@@ -1,0 +1,568 @@
+// rt_device.h -- per-ray device functions of the hot path: 7-slab octree traversal (closest hit and any hit),
+// Moeller-Trumbore, shading, texture taps, the rough-reflection fan.  Included by kernels.cu (nvcc, sm_100a).
+// The functions are plain inline code over pointer-based views so that tests/hostsim can compile the very same
+// source with g++ and run it single-threaded against the oracle before any GPU time is spent; that build lives
+// under tests/ only and is never part of librtb200.so.
+//
+// Build contract: no FMA contraction (nvcc --fmad=false / g++ -ffp-contract=off), IEEE div/sqrt.
+#pragma once
+
+#include "rt_math.h"
+#include "../../include/rtb200.h"
+
+#if defined(__CUDACC__)
+#define RT_LDG4(p) __ldg(reinterpret_cast<const float4*>(p))
+#define RT_DEV __device__ __forceinline__
+#define RT_DEV_NOINLINE __device__ __noinline__
+typedef float4 rt_f4;
+#else
+#include "scene_layout.h"
+#define RT_LDG4(p) (*(p))
+#define RT_DEV inline
+#define RT_DEV_NOINLINE inline
+typedef rtb::F4 rt_f4;
+#endif
+
+#define RT_STACK_SIZE 160              /* 7 * RT_MAX_TREE_DEPTH + root, rounded up */
+#define RT_LEAF_BIT 0x80000000u
+
+namespace rtb {
+
+#if defined(__CUDACC__)
+RT_DEV uint32_t f4_bits(float f) { return __float_as_uint(f); }
+#else
+inline uint32_t f4_bits(float f) { uint32_t u; __builtin_memcpy(&u, &f, 4); return u; }
+#endif
+
+struct TexView {
+    const void* data;   // RGBA texels, row 0 first
+    int32_t w, h;
+    int32_t format;     // 0 = none, 1 = u8 (decoded as u8 * (1/255.f)), 2 = f32
+    int32_t pad;
+};
+
+// Everything a ray needs, by value in kernel parameter space.
+struct SceneView {
+    const rt_f4* recs;      // 4 per child record (scene_layout.h)
+    const rt_f4* tris;      // 3 per triangle, leaf order
+    const rt_f4* shade;     // 2 per triangle, leaf order
+    const rt_f4* mats;      // 4 per material (RtMaterial = 16 floats)
+    int32_t n_mats;
+    uint32_t n_tris;
+    TexView tex[RT_TEX_COUNT];
+};
+
+struct FrameView {
+    M4 proj_inv;            // Camera::_perspective_proj_mat_inv
+    M4 cam_to_world;        // Camera::_camera_to_world_mat
+    V3 cam_pos;             // Camera::_position
+    V3 light;               // PointLight::_position
+    int32_t rw, rh;         // supersampled frame (renderer.cpp:116-120)
+    int32_t factor;         // ssaa factor or 1
+    RtSettings s;
+};
+
+struct HitRec {             // what a closest-hit query returns; tri is a LEAF-ORDER index
+    int32_t tri;
+    float t, u, v;
+};
+
+struct Hit {                // HitInfo, hitInfo.h:8-29 (triangle pointer -> leaf-order index)
+    int32_t tri;
+    float t, u, v;
+    int32_t mat;
+    V3 normal;
+    V3 tangent;
+};
+
+RT_DEV Hit fresh_hit()
+{
+    Hit h;
+    h.tri = -1; h.t = -1.0f; h.u = 1.0f; h.v = 0.0f; h.mat = -1;
+    h.normal = v3(0, 0, 0); h.tangent = v3(0, 0, 0);
+    return h;
+}
+
+struct TraceCounters {      // per-thread tallies, reduced by the kernels
+    uint32_t refl_rays, refl_shadow_rays, stack_overflow;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-ray constants of the slab test: denoms/numers of OctreeNode::intersect (bvh.h:216-223) with the division of
+// BoundingVolume::intersect (bvh.h:92-93) turned into a multiplication by the reciprocal.  A plane with denom == 0
+// is skipped by the reference (bvh.h:86-87); here its numer is NaN so both slab distances are NaN and the
+// NaN-dropping fminf/fmaxf leave the running interval untouched.
+struct SlabRay {
+    float inv[7];
+    float num[7];
+};
+
+RT_DEV void slab_setup(V3 o, V3 d, SlabRay& sr)
+{
+    const float s = 0.57735026f;                     // sqrt(3.f)/3, bvh.cpp:12-15 (same float)
+    float den[7];
+    den[0] = d.x; den[1] = d.y; den[2] = d.z;
+    sr.num[0] = o.x; sr.num[1] = o.y; sr.num[2] = o.z;
+    den[3] = s * d.x + s * d.y + s * d.z;      sr.num[3] = s * o.x + s * o.y + s * o.z;
+    den[4] = -s * d.x + s * d.y + s * d.z;     sr.num[4] = -s * o.x + s * o.y + s * o.z;
+    den[5] = -s * d.x + -s * d.y + s * d.z;    sr.num[5] = -s * o.x + -s * o.y + s * o.z;
+    den[6] = s * d.x + -s * d.y + s * d.z;     sr.num[6] = s * o.x + -s * o.y + s * o.z;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        if (den[i] == 0.0f) { sr.inv[i] = 0.0f; sr.num[i] = NAN; }
+        else sr.inv[i] = 1.0f / den[i];
+    }
+}
+
+// 7-slab interval of one 64-byte record.  Returns the entry distance, or +inf when the record is missed / lies
+// behind the ray / starts beyond t_limit.  (The reference has no t_far<0 / t_near>best cull, bvh.h:79-105; both
+// are pure pruning: a triangle needs t >= 0 and must beat the best hit strictly, bvh.h:241.)
+RT_DEV float slab_entry(const rt_f4& q0, const rt_f4& q1, const rt_f4& q2, const rt_f4& q3, const SlabRay& sr, float t_limit)
+{
+    float tn = -INFINITY, tf = INFINITY;
+#define RT_SLAB(i, NEAR, FAR)                                   \
+    {                                                           \
+        float a = ((NEAR) - sr.num[i]) * sr.inv[i];             \
+        float b = ((FAR) - sr.num[i]) * sr.inv[i];              \
+        tn = fmaxf(tn, fminf(a, b));                            \
+        tf = fminf(tf, fmaxf(a, b));                            \
+    }
+    RT_SLAB(0, q0.x, q1.w)
+    RT_SLAB(1, q0.y, q2.x)
+    RT_SLAB(2, q0.z, q2.y)
+    RT_SLAB(3, q0.w, q2.z)
+    RT_SLAB(4, q1.x, q2.w)
+    RT_SLAB(5, q1.y, q3.x)
+    RT_SLAB(6, q1.z, q3.y)
+#undef RT_SLAB
+    bool ok = (tn <= tf) && (tf >= 0.0f) && (tn <= t_limit);
+    return ok ? tn : INFINITY;
+}
+
+// Triangle::intersect with MOLLER_TRUMBORE 1 / BACKFACE_CULLING 1 -- triangle.cpp:25-91.  p0..p2 are the three
+// float4 of a triangle (a|n.x, b|n.y, c|n.z).  Returns true and (t,u,v) when the reference would.
+RT_DEV bool tri_test(const rt_f4& p0, const rt_f4& p1, const rt_f4& p2, V3 o, V3 md, float& t, float& u, float& v)
+{
+    V3 a = v3(p0.x, p0.y, p0.z);
+    V3 n = v3(p0.w, p1.w, p2.w);
+    float det = dot(n, md);
+    if (!(det > 0.0f)) return false;                      // Mdet <= 0 (or NaN): back-facing or parallel, :38-39
+    V3 ab = v3(p1.x, p1.y, p1.z) - a;
+    V3 ac = v3(p2.x, p2.y, p2.z) - a;
+    V3 oa = o - a;
+    V3 mdxoa = cross(md, oa);
+    det = 1.0f / det;
+    u = dot(mdxoa, ac) * det;
+    if (u < 0.0f || u > 1.0f) return false;
+    v = dot(mdxoa, -ab) * det;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    t = dot(n, oa) * det;
+    if (t < 0.0f) return false;
+    return true;
+}
+
+// Closest hit: BVH::intersect (bvh.cpp:68-71 -> bvh.h:212-287).  The reference descends children in order of slab
+// entry distance through a heap-allocated priority queue and stops when the best hit beats the next entry; the
+// result is the exact closest front-facing hit, first-found on ties.  Here: an explicit per-thread stack of
+// (entry distance, record) pairs, children of a cell pushed far-to-near so the nearest is popped first, entries
+// whose distance exceeds the best hit dropped at pop time.  Leaf triangles are visited in array order with the
+// reference's strict `<` (bvh.h:241), so ties inside a leaf resolve identically.
+//   best.tri < 0 on entry means "no hit yet" (HitInfo::t == -1).  Returns the reference's bool (a hit with t > 0).
+RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCounters* tc)
+{
+    SlabRay sr;
+    slab_setup(o, d, sr);
+    const V3 md = -d;
+    float best_t = INFINITY;
+    best.tri = -1; best.t = -1.0f; best.u = 1.0f; best.v = 0.0f;
+
+    float stack_t[RT_STACK_SIZE];
+    uint32_t stack_r[RT_STACK_SIZE];
+    int sp = 0;
+
+    {   // the root cell's own volume, bvh.h:232-233
+        const rt_f4* r = sc.recs;
+        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+        if (slab_entry(q0, q1, q2, q3, sr, best_t) == INFINITY) return false;
+        stack_t[0] = -INFINITY;
+        stack_r[0] = 0;
+        sp = 1;
+    }
+
+    while (sp > 0) {
+        --sp;
+        if (stack_t[sp] > best_t) continue;              // a closer hit was found since this cell was pushed
+        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
+        const uint32_t link = f4_bits(q3.z), meta = f4_bits(q3.w);
+        if (meta & RT_LEAF_BIT) {
+            const uint32_t cnt = meta & ~RT_LEAF_BIT;
+            const rt_f4* tp = sc.tris + 3 * (size_t)link;
+            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
+                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+                float t, u, v;
+                if (tri_test(p0, p1, p2, o, md, t, u, v) && t < best_t) {
+                    best_t = t;
+                    best.tri = (int32_t)(link + i); best.t = t; best.u = u; best.v = v;
+                }
+            }
+        } else {
+            const int base = sp;
+            const rt_f4* r = sc.recs + 4 * (size_t)link;
+            if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return best.tri >= 0 && best.t > 0.0f; }
+            for (uint32_t k = 0; k < meta; k++, r += 4) {
+                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+                float tn = slab_entry(c0, c1, c2, c3, sr, best_t);
+                if (tn == INFINITY) continue;
+                int j = sp;                                 // keep [base, sp) sorted by descending entry distance
+                while (j > base && stack_t[j - 1] < tn) {
+                    stack_t[j] = stack_t[j - 1];
+                    stack_r[j] = stack_r[j - 1];
+                    --j;
+                }
+                stack_t[j] = tn;
+                stack_r[j] = link + k;
+                ++sp;
+            }
+        }
+    }
+    return best.tri >= 0 && best.t > 0.0f;                  // leaf returns t_near > 0, bvh.h:245-247
+}
+
+// Any hit for Renderer::is_shadowed (renderer.cpp:340-402).  The reference runs a CLOSEST-hit query from
+// p + n*EPSILON towards the light and then compares |p - hitpoint|^2 with |p - light|^2.  Beyond 2e-4 from the
+// origin that predicate is monotone in t, so "some front-facing hit with t > 0 satisfies it" is the same
+// statement as "the closest one does"; the traversal can stop at the first such hit, needs no ordering, and can
+// drop cells that start beyond the light.
+RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCounters* tc)
+{
+    const V3 o = p + 1.0e-4f * n;                            // Renderer::EPSILON, renderer.h:23
+    const V3 d = normalize(light - p);
+    const float dist2 = length2(p - light);
+    const float t_limit = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
+    SlabRay sr;
+    slab_setup(o, d, sr);
+    const V3 md = -d;
+
+    uint32_t stack_r[RT_STACK_SIZE];
+    int sp = 0;
+    {
+        const rt_f4* r = sc.recs;
+        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+        if (slab_entry(q0, q1, q2, q3, sr, t_limit) == INFINITY) return false;
+        stack_r[0] = 0;
+        sp = 1;
+    }
+    while (sp > 0) {
+        --sp;
+        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
+        const uint32_t link = f4_bits(q3.z), meta = f4_bits(q3.w);
+        if (meta & RT_LEAF_BIT) {
+            const uint32_t cnt = meta & ~RT_LEAF_BIT;
+            const rt_f4* tp = sc.tris + 3 * (size_t)link;
+            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
+                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+                float t, u, v;
+                if (tri_test(p0, p1, p2, o, md, t, u, v) && t > 0.0f) {
+                    V3 q = o + t * d;                        // renderer.cpp:351
+                    if (length2(p - q) < dist2) return true; // renderer.cpp:354
+                }
+            }
+        } else {
+            const rt_f4* r = sc.recs + 4 * (size_t)link;
+            if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return false; }
+            for (uint32_t k = 0; k < meta; k++, r += 4) {
+                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+                if (slab_entry(c0, c1, c2, c3, sr, t_limit) != INFINITY) stack_r[sp++] = link + k;
+            }
+        }
+    }
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Textures: Image::texture_floor -> sample_floor -> offset (image.h:79-97,122-134): nearest texel, clamp to edge.
+RT_DEV Col tex_floor(const TexView& tx, float x, float y)
+{
+    float fu = floorf(x * (float)tx.w);
+    float fv = floorf(y * (float)tx.h);
+    int px = (int)fu, py = (int)fv;
+    if (px < 0) px = 0;
+    if (px > tx.w - 1) px = tx.w - 1;
+    if (py < 0) py = 0;
+    if (py > tx.h - 1) py = tx.h - 1;
+    size_t idx = (size_t)py * (size_t)tx.w + (size_t)px;
+    if (tx.format == 1) {
+#if defined(__CUDACC__)
+        uchar4 c = __ldg(reinterpret_cast<const uchar4*>(tx.data) + idx);
+        const float kk = 1.0f / 255.0f;                      // Color / 255 -> kk = 1 / k; kk * c (color.cpp:87-91)
+        return col((float)c.x * kk, (float)c.y * kk, (float)c.z * kk);
+#else
+        const uint8_t* c = reinterpret_cast<const uint8_t*>(tx.data) + 4 * idx;
+        const float kk = 1.0f / 255.0f;
+        return col((float)c[0] * kk, (float)c[1] * kk, (float)c[2] * kk);
+#endif
+    }
+    rt_f4 c = RT_LDG4(reinterpret_cast<const rt_f4*>(tx.data) + idx);
+    return col(c.x, c.y, c.z);
+}
+
+struct MatView {
+    Col ambient_coeff, diffuse, specular, emission;
+    float reflection, roughness, ns, specular_threshold;
+};
+
+RT_DEV MatView load_material(const SceneView& sc, int32_t index)
+{
+    const rt_f4* m = sc.mats + 4 * (size_t)index;
+    rt_f4 a = RT_LDG4(m), b = RT_LDG4(m + 1), c = RT_LDG4(m + 2), d = RT_LDG4(m + 3);
+    MatView mv;
+    mv.ambient_coeff = col(a.x, a.y, a.z);
+    mv.diffuse = col(a.w, b.x, b.y);
+    mv.specular = col(b.z, b.w, c.x);
+    mv.emission = col(c.y, c.z, c.w);
+    mv.reflection = d.x; mv.roughness = d.y; mv.ns = d.z; mv.specular_threshold = d.w;
+    return mv;
+}
+
+struct TriShade {       // shading-side triangle data
+    V3 tu, tv;          // Triangle::_tex_coords_u / _v (triangle.h:99-103)
+    int32_t mat;
+    int32_t orig;
+};
+
+RT_DEV TriShade load_tri_shade(const SceneView& sc, int32_t tri)
+{
+    const rt_f4* s = sc.shade + 2 * (size_t)tri;
+    rt_f4 a = RT_LDG4(s), b = RT_LDG4(s + 1);
+    TriShade ts;
+    ts.tu = v3(a.x, a.y, a.z);
+    ts.tv = v3(a.w, b.x, b.y);
+    ts.mat = (int32_t)f4_bits(b.z);
+    ts.orig = (int32_t)f4_bits(b.w);
+    return ts;
+}
+
+// Triangle::interpolate_texcoords -- triangle.cpp:155-160
+RT_DEV void tri_texcoords(const TriShade& ts, float u, float v, float& tex_u, float& tex_v)
+{
+    tex_u = (1 - u - v) * ts.tu.x + u * ts.tu.y + v * ts.tu.z;
+    tex_v = (1 - u - v) * ts.tv.x + u * ts.tv.y + v * ts.tv.z;
+}
+
+// Fills the HitInfo fields Triangle::intersect sets on a hit (triangle.cpp:81-88): material, normalised normal,
+// tangent (Triangle::get_tangent, triangle.cpp:134-153).
+RT_DEV Hit complete_hit(const SceneView& sc, const HitRec& hr)
+{
+    Hit h;
+    h.tri = hr.tri; h.t = hr.t; h.u = hr.u; h.v = hr.v;
+    const rt_f4* tp = sc.tris + 3 * (size_t)hr.tri;
+    rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+    V3 a = v3(p0.x, p0.y, p0.z);
+    V3 ab = v3(p1.x, p1.y, p1.z) - a;
+    V3 ac = v3(p2.x, p2.y, p2.z) - a;
+    TriShade ts = load_tri_shade(sc, hr.tri);
+    float du1 = ts.tu.y - ts.tu.x, dv1 = ts.tv.y - ts.tv.x;
+    float du2 = ts.tu.z - ts.tu.x, dv2 = ts.tv.z - ts.tv.x;
+    float f = 1.0f / (du1 * dv2 - du2 * dv1);
+    h.tangent = v3(f * (dv2 * ab.x - dv1 * ac.x), f * (dv2 * ab.y - dv1 * ac.y), f * (dv2 * ab.z - dv1 * ac.z));
+    h.mat = ts.mat;
+    h.normal = normalize(v3(p0.w, p1.w, p2.w));
+    return h;
+}
+
+RT_DEV void hit_texcoords(const SceneView& sc, const Hit& h, float u, float v, float& tu, float& tv)
+{
+    TriShade ts = load_tri_shade(sc, h.tri);            // Renderer::get_tex_coords, renderer.cpp:436-445
+    tri_texcoords(ts, u, v, tu, tv);
+}
+
+// Renderer::normal_mapping -- renderer.cpp:464-478
+RT_DEV V3 normal_mapping(const SceneView& sc, const Hit& h, float u, float v)
+{
+    float tu, tv;
+    hit_texcoords(sc, h, u, v, tu, tv);
+    V3 tg = h.tangent;
+    V3 bt = cross(tg, h.normal);
+    Col nc = tex_floor(sc.tex[RT_TEX_NORMAL], tu, tv);
+    V3 nm = 2.0f * v3(nc.r, nc.g, nc.b) - v3(1, 1, 1);
+    V3 q = normalize(nm);
+    V3 pn = v3(tg.x * q.x + bt.x * q.y + h.normal.x * q.z,      // Transform(T,B,N)(Vector), mat.cpp:69-75,103-115
+               tg.y * q.x + bt.y * q.y + h.normal.y * q.z,
+               tg.z * q.x + bt.z * q.y + h.normal.z * q.z);
+    return normalize(pn);
+}
+
+// Renderer::compute_specular -- renderer.cpp:270-280
+RT_DEV Col compute_specular(const MatView& m, V3 ray_dir, V3 n, V3 to_light)
+{
+    V3 half = normalize(to_light - ray_dir);
+    float angle = dot(half, n);
+    if (angle <= m.specular_threshold) return col(0.0f);
+    float p = powf(fmaxf(0.0f, angle), m.ns);
+    return m.specular * col(p);
+}
+
+// The part of Renderer::shade_ray_inter_point (renderer.cpp:556-617) that needs no further rays:
+// diffuse * ao * enable_diffuse + specular * enable_specular, evaluated after the normal-map update of hit.normal.
+RT_DEV Col shade_direct(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, Hit& hit, V3& p_out, MatView& m_out)
+{
+    const RtSettings& s = fr.s;
+    float u = hit.u, v = hit.v;
+    V3 p = ro + hit.t * rd;
+    V3 to_light = normalize(fr.light - p);
+    if (s.enable_normal_mapping) hit.normal = normal_mapping(sc, hit, u, v);
+    MatView m = load_material(sc, hit.mat);
+    float ao = 1.0f;
+    if (s.enable_ao_mapping) {
+        float tu, tv;
+        hit_texcoords(sc, hit, u, v, tu, tv);
+        ao = tex_floor(sc.tex[RT_TEX_AO], tu, tv).r;
+    }
+    Col diffuse;
+    if (s.enable_diffuse_mapping) {
+        float tu, tv;
+        hit_texcoords(sc, hit, u, v, tu, tv);
+        diffuse = tex_floor(sc.tex[RT_TEX_DIFFUSE], tu, tv);
+        diffuse = diffuse * col(fmaxf(0.5f, dot(hit.normal, normalize(fr.cam_pos - p))));
+    } else
+        diffuse = m.diffuse * col(fmaxf(0.0f, dot(hit.normal, to_light)));          // compute_diffuse :263-266
+    Col c = col(0.0f);
+    c = c + diffuse * ao * (s.enable_diffuse ? 1.0f : 0.0f);
+    c = c + compute_specular(m, rd, hit.normal, to_light) * (s.enable_specular ? 1.0f : 0.0f);
+    p_out = p;
+    m_out = m;
+    return c;
+}
+
+// The rest of shade_ray_inter_point once the shadow flag and the reflection colour are known (renderer.cpp:591-597,
+// 612-616) and the second clamp of trace_ray (renderer.cpp:1045-1047, idempotent).
+RT_DEV Col shade_compose(const FrameView& fr, const MatView& m, Col direct, bool shadowed, Col reflection)
+{
+    const RtSettings& s = fr.s;
+    Col c = direct;
+    if (shadowed) c = c * col(0.5f);                                                // SHADOW_INTENSITY, renderer.h:24
+    c = c + m.emission * (s.enable_emissive ? 1.0f : 0.0f);
+    if (m.reflection > 0.0f) c = c + reflection * m.reflection;
+    c = c + col(0.1f) * m.ambient_coeff * (1 - m.reflection) * (s.enable_ambient ? 1.0f : 0.0f); // AMBIENT_COLOR :18
+    return col(clamp01(c.r), clamp01(c.g), clamp01(c.b));
+}
+
+// The debug shading modes of shade_ray_inter_point (renderer.cpp:599-609, 404-434).
+RT_DEV Col shade_debug(const SceneView& sc, const FrameView& fr, const Hit& hit)
+{
+    Col c = col(0.0f);
+    int mode = fr.s.shading_method;
+    if (mode == RT_ABS_NORMALS_SHADING)
+        c = col(fabsf(hit.normal.x), fabsf(hit.normal.y), fabsf(hit.normal.z));
+    else if (mode == RT_PASTEL_NORMALS_SHADING)
+        c = (col(hit.normal.x, hit.normal.y, hit.normal.z) + col(1.0f)) * 0.5f;
+    else if (mode == RT_BARYCENTRIC_COORDINATES_SHADING)
+        c = col(1, 0, 0) * hit.u + col(0, 1, 0) * hit.v + col(0, 0, 1) * (1 - hit.u - hit.v);
+    else if (mode == RT_VISUALIZE_AO) {
+        c = col(0.9f);
+        if (fr.s.enable_ao_mapping) {
+            float tu, tv;
+            hit_texcoords(sc, hit, hit.u, hit.v, tu, tv);
+            c = c * col(tex_floor(sc.tex[RT_TEX_AO], tu, tv).r);
+        }
+    }
+    return col(clamp01(c.r), clamp01(c.g), clamp01(c.b));
+}
+
+// Miss shader of trace_ray -- renderer.cpp:1052-1065 (skysphere or BACKGROUND_COLOR; the cube-map skybox is
+// outside the path).  The reference mixes float libm calls with double constants; so does this.
+RT_DEV Col shade_miss(const SceneView& sc, const FrameView& fr, V3 rd)
+{
+    if (fr.s.enable_skysphere) {
+        float u = (float)(0.5 + (double)atan2f(-rd.z, -rd.x) / (2 * 3.14159265358979323846));
+        float v = (float)(0.5 + (double)asinf(-rd.y) / 3.14159265358979323846);
+        return tex_floor(sc.tex[RT_TEX_SKYSPHERE], u, v);
+    }
+    return col(135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f);                  // renderer.cpp:19
+}
+
+RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, Hit& final_hit,
+                                       int depth, XorShift32& rng, TraceCounters* tc);
+
+// Renderer::compute_reflection -- renderer.cpp:283-338.  One thread walks the whole fan in order: the reference's
+// random stream (3 draws per rough sample, consumed also by nested fans that are cut off by the recursion limit)
+// and its reflection_hit_info (declared OUTSIDE the sample loop, :286, so sample k is shaded with the closest hit
+// seen by samples 1..k) are both sequential by construction.  Returns colour already multiplied by
+// material.reflection once (:337); the caller multiplies again (:595).
+RT_DEV Col compute_reflection(const SceneView& sc, const FrameView& fr, V3 rd, V3 p, const Hit& hit, const MatView& m,
+                             int depth, XorShift32& rng, TraceCounters* tc)
+{
+    const RtSettings& s = fr.s;
+    Hit rh = fresh_hit();
+    V3 n = hit.normal;
+    V3 origin = p + 0.01f * n;
+    V3 mirror = rd - (2 * dot(rd, n)) * n;
+    int samples = 0;
+    Col total = col(0.0f);
+    for (int i = 0; i < s.rough_reflections_sample_count; i++) {
+        float roughness;
+        if (s.enable_roughness_mapping) {
+            float tu, tv;
+            hit_texcoords(sc, hit, hit.u, hit.v, tu, tv);
+            roughness = tex_floor(sc.tex[RT_TEX_ROUGHNESS], tu, tv).r;
+        } else
+            roughness = m.roughness;
+        if (roughness > 0) {
+            // Vector(rand, rand, rand), renderer.cpp:313: the compiled reference (g++) evaluates right to left.
+            float rz = rng.bilateral();
+            float ry = rng.bilateral();
+            float rx = rng.bilateral();
+            V3 r = normalize(v3(rx, ry, rz));
+            if (dot(r, hit.normal) < 0) r = -r;
+            V3 dir = roughness * r + (1 - roughness) * mirror;
+            total = total + trace_ray_secondary(sc, fr, origin, dir, rh, depth + 1, rng, tc);
+            samples++;
+        } else {
+            total = total + trace_ray_secondary(sc, fr, origin, mirror, rh, depth + 1, rng, tc);
+            samples = 1;
+            break;
+        }
+    }
+    return total / col((float)samples) * col(m.reflection);
+}
+
+// Renderer::trace_ray for depth >= 1 (renderer.cpp:1008-1066) with shade_ray_inter_point inlined; recursion as in
+// the reference, bounded by max_recursion_depth (the C ABI caps it so the device stack can be sized).
+RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, Hit& final_hit, int depth,
+                        XorShift32& rng, TraceCounters* tc)
+{
+    if (depth > fr.s.max_recursion_depth) return col(0.0f);
+    if (tc) tc->refl_rays++;
+    HitRec hr;
+    if (trace_closest(sc, ro, rd, hr, tc)) {
+        if (hr.t < final_hit.t || final_hit.t == -1.0f) final_hit = complete_hit(sc, hr);
+    }
+    if (final_hit.t > 0.1f) {                                                        // min_t, renderer.cpp:1039
+        if (fr.s.shading_method != RT_SHADING) return shade_debug(sc, fr, final_hit);
+        V3 p;
+        MatView m;
+        Col direct = shade_direct(sc, fr, ro, rd, final_hit, p, m);
+        bool shadowed = false;
+        if (fr.s.compute_shadows) {
+            if (tc) tc->refl_shadow_rays++;
+            shadowed = trace_occluded(sc, p, final_hit.normal, fr.light, tc);
+        }
+        Col refl = col(0.0f);
+        if (m.reflection > 0.0f) refl = compute_reflection(sc, fr, rd, p, final_hit, m, depth, rng, tc);
+        return shade_compose(fr, m, direct, shadowed, refl);
+    }
+    return shade_miss(sc, fr, rd);
+}
+
+// Primary ray of pixel (px, py) of the supersampled frame -- renderer.cpp:1083-1098.
+RT_DEV void primary_ray(const FrameView& fr, int px, int py, V3& o, V3& d)
+{
+    float yw = ((float)py + 0.5f) / (float)fr.rh * 2 - 1;
+    float xw = ((float)px + 0.5f) / (float)fr.rw * 2 - 1;
+    V3 vs = xform_point(fr.proj_inv, v3(xw, yw, -1));
+    V3 ws = xform_point(fr.cam_to_world, vs);
+    o = fr.cam_pos;
+    d = normalize(ws - fr.cam_pos);
+}
+
+} // namespace rtb

@@ -1,0 +1,747 @@
+// rtb200.cu -- implementation of the C ABI in include/rtb200.h: context, HBM-resident scene, wavefront driver.
+// There is no CPU path: every entry point that computes launches the kernels of kernels.cuh on the context's device.
+#include "../../include/rtb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "scene_layout.h"
+#include "host_common.h"
+
+using namespace rtb;
+
+namespace {
+
+constexpr uint64_t kChunkPixels = 1ull << 25;     // supersampled pixels per wavefront chunk (bounds queue memory)
+constexpr int kMaxChunks = 256;
+
+thread_local std::string g_create_error;
+
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Texture {
+    void* d = nullptr;
+    int w = 0, h = 0, format = 0;
+};
+
+enum Stage { ST_PRIMARY = 0, ST_REFLECT, ST_SHADE, ST_RESOLVE, ST_COUNT };
+
+struct TimedLaunch {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+} // namespace
+
+struct RtContext {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    // host copy of the caller's triangles (set_object_transform re-transforms and rebuilds, renderer.cpp:214-224)
+    std::vector<float> xyz9, uv6;
+    std::vector<int32_t> mat;
+    bool has_uv = false, has_mat = false;
+    int32_t max_mat_index = -1, min_mat_index = 0;
+
+    bool bvh_valid = false;
+    RtBvhInfo info{};
+    DevBuf<float4> d_recs, d_tris, d_shade, d_mats;
+    DevBuf<int32_t> d_orig;
+    uint32_t n_tris = 0;
+    int n_mats = 0;
+    bool any_reflective = false;
+    Texture tex[RT_TEX_COUNT];
+
+    M4 proj_inv{}, cam_to_world{};
+    V3 cam_pos{0, 0, 0};
+    V3 light{3, 3, 2};                            // PointLight default, scene/light.h:8
+    bool camera_set = false;
+
+    // per-frame work buffers
+    DevBuf<uint32_t> d_super, d_frame, d_tiles, q_pix, q_refl_idx;
+    DevBuf<int32_t> q_tri;
+    DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
+    DevBuf<ChunkCounters> d_counters;
+    DevBuf<unsigned int> d_flag;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    std::vector<TimedLaunch> timed;
+    size_t stack_limit_set = 0;
+
+    // batch query staging
+    DevBuf<float> b_a, b_b, b_t, b_u, b_v;
+    DevBuf<int32_t> b_id;
+    DevBuf<uint8_t> b_occ;
+};
+
+namespace {
+
+int fail(RtContext* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define RT_CUDA(ctx, expr)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));   \
+    } while (0)
+
+int bind(RtContext* ctx)
+{
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return RT_OK;
+}
+
+cudaEvent_t next_event(RtContext* ctx)
+{
+    if (ctx->events_used == ctx->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->event_pool.push_back(e);
+    }
+    return ctx->event_pool[ctx->events_used++];
+}
+
+struct ScopedTimer {
+    RtContext* ctx;
+    TimedLaunch tl;
+    ScopedTimer(RtContext* c, int stage) : ctx(c)
+    {
+        tl.stage = stage;
+        tl.a = next_event(c);
+        tl.b = next_event(c);
+        cudaEventRecord(tl.a, c->stream);
+    }
+    ~ScopedTimer()
+    {
+        cudaEventRecord(tl.b, ctx->stream);
+        ctx->timed.push_back(tl);
+    }
+};
+
+SceneView scene_view(const RtContext* ctx)
+{
+    SceneView sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.recs = ctx->d_recs.p;
+    sc.tris = ctx->d_tris.p;
+    sc.shade = ctx->d_shade.p;
+    sc.mats = ctx->d_mats.p;
+    sc.n_mats = ctx->n_mats;
+    sc.n_tris = ctx->n_tris;
+    for (int i = 0; i < RT_TEX_COUNT; i++) {
+        sc.tex[i].data = ctx->tex[i].d;
+        sc.tex[i].w = ctx->tex[i].w;
+        sc.tex[i].h = ctx->tex[i].h;
+        sc.tex[i].format = ctx->tex[i].format;
+    }
+    return sc;
+}
+
+int validate_settings(RtContext* ctx, const RtSettings* s)
+{
+    std::string why;
+    int r = check_settings(s, why);
+    return r ? fail(ctx, r, "%s", why.c_str()) : RT_OK;
+}
+
+int validate_scene_for_render(RtContext* ctx, const RtSettings* s)
+{
+    SceneFacts f;
+    f.bvh_valid = ctx->bvh_valid; f.camera_set = ctx->camera_set; f.n_tris = ctx->n_tris; f.n_mats = ctx->n_mats;
+    f.min_mat_index = ctx->min_mat_index; f.max_mat_index = ctx->max_mat_index;
+    for (int i = 0; i < RT_TEX_COUNT; i++) f.tex_format[i] = ctx->tex[i].format;
+    std::string why;
+    int r = check_scene_for_render(f, s, why);
+    return r ? fail(ctx, r, "%s", why.c_str()) : RT_OK;
+}
+
+FrameView frame_view(const RtContext* ctx, const RtSettings* s)
+{
+    FrameView fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.proj_inv = ctx->proj_inv;
+    fr.cam_to_world = ctx->cam_to_world;
+    fr.cam_pos = ctx->cam_pos;
+    fr.light = ctx->light;
+    fr.factor = s->enable_ssaa ? s->ssaa_factor : 1;                                // renderer.cpp:116-120
+    fr.rw = s->image_width * fr.factor;
+    fr.rh = s->image_height * fr.factor;
+    fr.s = *s;
+    return fr;
+}
+
+int check_tile_args(RtContext* ctx, int tile_size, int tile_mod, int tile_rem)
+{
+    if (tile_size <= 0 || tile_mod <= 0 || tile_rem < 0 || tile_rem >= tile_mod)
+        return fail(ctx, RT_ERR_INVALID, "tile_size %d tile_mod %d tile_rem %d", tile_size, tile_mod, tile_rem);
+    return RT_OK;
+}
+
+int grid_for(const RtContext* ctx, const void* kernel, int threads)
+{
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (per_sm < 1) per_sm = 1;
+    return ctx->sm_count * per_sm;                 // persistent grid: a whole number of CTAs per SM
+}
+
+int ensure_stack(RtContext* ctx, const RtSettings* s)
+{
+    // k_reflect recurses (trace_ray_secondary); every level holds two traversal stacks.
+    size_t want = 4096 + (size_t)(std::max(0, s->max_recursion_depth) + 2) * 3072;
+    if (want > ctx->stack_limit_set) {
+        RT_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, want));
+        ctx->stack_limit_set = want;
+    }
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void rt_default_settings(RtSettings* s)
+{
+    if (s) default_settings(s);
+}
+
+uint32_t rt_pixel_seed(uint32_t pixel_index, uint32_t rng_seed) { return pixel_seed(pixel_index, rng_seed); }
+
+void rt_perspective_inverse(float fov, float aspect, float znear, float zfar, float proj_inv_out[16])
+{
+    M4 inv = invert_matrix(perspective_matrix(fov, aspect, znear, zfar));
+    memcpy(proj_inv_out, inv.m, sizeof(inv.m));
+}
+
+void rt_invert_transform(const float m[16], float out[16])
+{
+    M4 a;
+    memcpy(a.m, m, sizeof(a.m));
+    M4 inv = invert_matrix(a);
+    memcpy(out, inv.m, sizeof(inv.m));
+}
+
+void rt_transform_point(const float m[16], const float p[3], float out[3])
+{
+    M4 a;
+    memcpy(a.m, m, sizeof(a.m));
+    V3 q = xform_point(a, v3(p[0], p[1], p[2]));
+    out[0] = q.x; out[1] = q.y; out[2] = q.z;
+}
+
+int rt_create(int device, RtContext** out)
+{
+    if (!out) return fail(nullptr, RT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RT_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, RT_ERR_INVALID, "device %d of %d", device, count);
+    RtContext* ctx = new RtContext();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RT_ERR_CUDA, "device init: %s", cudaGetErrorString(e));
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    // identity camera looking down -z, like a default-constructed Camera (scene/camera.h:11,29-30)
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) ctx->cam_to_world.m[i][j] = ctx->proj_inv.m[i][j] = (i == j) ? 1.0f : 0.0f;
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(RtContext* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release();
+    for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
+    ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_pix.release(); ctx->q_refl_idx.release();
+    ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release();
+    ctx->d_counters.release(); ctx->d_flag.release();
+    ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rt_last_error(const RtContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rt_set_triangles(RtContext* ctx, const float* xyz9, const float* uv6, const int32_t* mat, size_t n)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (n && !xyz9) return fail(ctx, RT_ERR_INVALID, "xyz9 is NULL");
+    if (n > 0x7fffffffu / 3) return fail(ctx, RT_ERR_INVALID, "too many triangles");
+    ctx->xyz9.assign(xyz9, xyz9 + 9 * n);
+    ctx->has_uv = uv6 != nullptr;
+    ctx->has_mat = mat != nullptr;
+    if (uv6) ctx->uv6.assign(uv6, uv6 + 6 * n); else ctx->uv6.clear();
+    if (mat) ctx->mat.assign(mat, mat + n); else ctx->mat.clear();
+    ctx->min_mat_index = n ? (mat ? *std::min_element(mat, mat + n) : -1) : 0;
+    ctx->max_mat_index = n ? (mat ? *std::max_element(mat, mat + n) : -1) : -1;
+    ctx->bvh_valid = false;
+    return RT_OK;
+}
+
+int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (max_depth < 0 || max_depth > RT_MAX_TREE_DEPTH) return fail(ctx, RT_ERR_INVALID, "max_depth %d outside [0,%d]", max_depth, RT_MAX_TREE_DEPTH);
+    if (leaf_max_obj_count < 0) return fail(ctx, RT_ERR_INVALID, "leaf_max_obj_count %d", leaf_max_obj_count);
+    const size_t n = ctx->xyz9.size() / 9;
+    double t0 = now_ms();
+    FlatScene flat;
+    build_flat_scene(ctx->xyz9.data(), ctx->has_uv ? ctx->uv6.data() : nullptr, ctx->has_mat ? ctx->mat.data() : nullptr, n,
+                     max_depth, leaf_max_obj_count, flat);
+    double t1 = now_ms();
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, ctx->d_recs.ensure(flat.recs.size()));
+    RT_CUDA(ctx, ctx->d_tris.ensure(flat.tris.size()));
+    RT_CUDA(ctx, ctx->d_shade.ensure(flat.shade.size()));
+    RT_CUDA(ctx, ctx->d_orig.ensure(flat.orig.size()));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_recs.p, flat.recs.data(), flat.recs.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris.p, flat.tris.data(), flat.tris.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_shade.p, flat.shade.data(), flat.shade.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_orig.p, flat.orig.data(), flat.orig.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double t2 = now_ms();
+    ctx->n_tris = (uint32_t)n;
+    RtBvhInfo& bi = ctx->info;
+    bi.triangles = n;
+    bi.nodes = flat.nodes; bi.leaves = flat.leaves; bi.empty_leaves = flat.empty_leaves; bi.interior = flat.interior;
+    bi.max_depth_reached = flat.max_depth_reached; bi.max_leaf_size = flat.max_leaf_size;
+    bi.child_records = flat.n_records;
+    bi.device_bytes = (flat.recs.size() + flat.tris.size() + flat.shade.size()) * sizeof(F4) + flat.orig.size() * sizeof(int32_t);
+    bi.build_ms = t1 - t0;
+    bi.upload_ms = t2 - t1;
+    ctx->bvh_valid = true;
+    return RT_OK;
+}
+
+int rt_bvh_info(const RtContext* ctx, RtBvhInfo* out)
+{
+    if (!ctx || !out) return RT_ERR_INVALID;
+    if (!ctx->bvh_valid) return RT_ERR_STATE;
+    *out = ctx->info;
+    return RT_OK;
+}
+
+int rt_transform_triangles(RtContext* ctx, const float m[16], int max_depth, int leaf_max_obj_count)
+{
+    if (!ctx || !m) return RT_ERR_INVALID;
+    M4 t;
+    memcpy(t.m, m, sizeof(t.m));
+    const size_t n = ctx->xyz9.size() / 3;
+    for (size_t i = 0; i < n; i++) {                                               // Transform::operator()(Triangle), mat.cpp:133-140
+        V3 p = xform_point(t, v3(ctx->xyz9[3 * i], ctx->xyz9[3 * i + 1], ctx->xyz9[3 * i + 2]));
+        ctx->xyz9[3 * i] = p.x; ctx->xyz9[3 * i + 1] = p.y; ctx->xyz9[3 * i + 2] = p.z;
+    }
+    ctx->bvh_valid = false;
+    return rt_build_bvh(ctx, max_depth, leaf_max_obj_count);
+}
+
+int rt_set_materials(RtContext* ctx, const RtMaterial* mats, size_t n)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (n && !mats) return fail(ctx, RT_ERR_INVALID, "mats is NULL");
+    static_assert(sizeof(RtMaterial) == 64, "RtMaterial is read as 4 float4");
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, ctx->d_mats.ensure(4 * n));
+    if (n) RT_CUDA(ctx, cudaMemcpy(ctx->d_mats.p, mats, n * sizeof(RtMaterial), cudaMemcpyHostToDevice));
+    ctx->n_mats = (int)n;
+    ctx->any_reflective = false;
+    for (size_t i = 0; i < n; i++)
+        if (mats[i].reflection > 0.0f) ctx->any_reflective = true;
+    return RT_OK;
+}
+
+static int set_texture(RtContext* ctx, int slot, const void* data, int width, int height, int format)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (slot < 0 || slot >= RT_TEX_COUNT) return fail(ctx, RT_ERR_INVALID, "texture slot %d", slot);
+    if (!data || width <= 0 || height <= 0) return fail(ctx, RT_ERR_INVALID, "texture %dx%d", width, height);
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    Texture& t = ctx->tex[slot];
+    if (t.d) cudaFree(t.d);
+    t = Texture();
+    size_t bytes = (size_t)width * height * (format == 1 ? 4 : 16);
+    RT_CUDA(ctx, cudaMalloc(&t.d, bytes));
+    RT_CUDA(ctx, cudaMemcpy(t.d, data, bytes, cudaMemcpyHostToDevice));
+    t.w = width; t.h = height; t.format = format;
+    return RT_OK;
+}
+
+int rt_set_texture_f32(RtContext* ctx, int slot, const float* rgba, int width, int height) { return set_texture(ctx, slot, rgba, width, height, 2); }
+int rt_set_texture_u8(RtContext* ctx, int slot, const uint8_t* rgba, int width, int height) { return set_texture(ctx, slot, rgba, width, height, 1); }
+
+int rt_clear_texture(RtContext* ctx, int slot)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (slot < 0 || slot >= RT_TEX_COUNT) return fail(ctx, RT_ERR_INVALID, "texture slot %d", slot);
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->tex[slot].d) cudaFree(ctx->tex[slot].d);
+    ctx->tex[slot] = Texture();
+    return RT_OK;
+}
+
+int rt_set_camera(RtContext* ctx, const float proj_inv[16], const float cam_to_world[16], const float position[3])
+{
+    if (!ctx || !proj_inv || !cam_to_world || !position) return RT_ERR_INVALID;
+    memcpy(ctx->proj_inv.m, proj_inv, 64);
+    memcpy(ctx->cam_to_world.m, cam_to_world, 64);
+    ctx->cam_pos = v3(position[0], position[1], position[2]);
+    ctx->camera_set = true;
+    return RT_OK;
+}
+
+int rt_set_light(RtContext* ctx, const float position[3])
+{
+    if (!ctx || !position) return RT_ERR_INVALID;
+    ctx->light = v3(position[0], position[1], position[2]);
+    return RT_OK;
+}
+
+int rt_tile_count(const RtSettings* s, int tile_size, int tile_mod, int tile_rem)
+{
+    if (!s || tile_size <= 0 || tile_mod <= 0 || tile_rem < 0 || tile_rem >= tile_mod) return RT_ERR_INVALID;
+    return (int)owned_tiles(s, tile_size, tile_mod, tile_rem, nullptr).size();
+}
+
+int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, int tile_size, int tile_mod, int tile_rem,
+                     RtRenderStats* stats)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (int r = validate_settings(ctx, s)) return r;
+    if (int r = validate_scene_for_render(ctx, s)) return r;
+    if (int r = check_tile_args(ctx, tile_size, tile_mod, tile_rem)) return r;
+    if (!d_argb_out) return fail(ctx, RT_ERR_INVALID, "d_argb_out is NULL");
+
+    const FrameView fr = frame_view(ctx, s);
+    const SceneView sc = scene_view(ctx);
+    const bool resolve = fr.factor > 1;
+    const bool reflect = ctx->any_reflective && s->shading_method == RT_SHADING;
+    if (reflect) if (int r = ensure_stack(ctx, s)) return r;
+
+    int tiles_x = 0;
+    std::vector<uint32_t> tiles = owned_tiles(s, tile_size, tile_mod, tile_rem, &tiles_x);
+    WorkView wk;
+    wk.tiles_x = tiles_x;
+    wk.tile_px = tile_size * fr.factor;
+    wk.patches_per_side = (wk.tile_px + kPatch - 1) / kPatch;
+    const uint64_t px_per_tile = (uint64_t)wk.patches_per_side * wk.patches_per_side * kPatch * kPatch;
+    uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, kChunkPixels / px_per_tile);
+    if ((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk > (size_t)kMaxChunks)
+        tiles_per_chunk = (uint32_t)((tiles.size() + kMaxChunks - 1) / kMaxChunks);
+    const uint32_t n_chunks = (uint32_t)((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk);
+    const size_t qcap = (size_t)std::min<uint64_t>((uint64_t)tiles_per_chunk, tiles.size()) * px_per_tile;
+
+    RT_CUDA(ctx, ctx->d_tiles.ensure(tiles.size()));
+    RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
+    RT_CUDA(ctx, ctx->q_pix.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
+    RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
+    if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); }
+    uint32_t* super = d_argb_out;
+    if (resolve) {
+        RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
+        super = ctx->d_super.p;
+    }
+    wk.tiles = ctx->d_tiles.p;
+    QueueView q;
+    q.pix = ctx->q_pix.p; q.tri = ctx->q_tri.p; q.t = ctx->q_t.p; q.u = ctx->q_u.p; q.v = ctx->q_v.p;
+    q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.capacity = (uint32_t)qcap;
+
+    cudaStream_t st = ctx->stream;
+    ctx->events_used = 0;
+    ctx->timed.clear();
+    uint32_t launches = 0;
+    cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
+    RT_CUDA(ctx, cudaEventRecord(ev_begin, st));
+    if (!tiles.empty())
+        RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
+
+    static int grid_primary = 0, grid_reflect = 0, grid_shade = 0;
+    if (!grid_primary) {
+        grid_primary = grid_for(ctx, (const void*)k_primary, kPrimaryThreads);
+        grid_reflect = grid_for(ctx, (const void*)k_reflect, kQueueThreads);
+        grid_shade = grid_for(ctx, (const void*)k_shade, kQueueThreads);
+    }
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        wk.tile_begin = c * tiles_per_chunk;
+        wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
+        ChunkCounters* cnt = ctx->d_counters.p + c;
+        {
+            ScopedTimer tm(ctx, ST_PRIMARY);
+            k_primary<<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0);
+            launches++;
+        }
+        if (reflect) {
+            ScopedTimer tm(ctx, ST_REFLECT);
+            k_reflect<<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, q, cnt);
+            launches++;
+        }
+        {
+            ScopedTimer tm(ctx, ST_SHADE);
+            k_shade<<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super);
+            launches++;
+        }
+    }
+    if (resolve && !tiles.empty()) {
+        wk.tile_begin = 0;
+        wk.tile_end = (uint32_t)tiles.size();
+        ScopedTimer tm(ctx, ST_RESOLVE);
+        k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(super, d_argb_out, wk, tile_size, fr.factor, s->image_width, s->image_height);
+        launches++;
+    }
+    RT_CUDA(ctx, cudaEventRecord(ev_end, st));
+    RT_CUDA(ctx, cudaGetLastError());
+
+    std::vector<ChunkCounters> host_cnt(std::max<uint32_t>(n_chunks, 1));
+    RT_CUDA(ctx, cudaMemcpyAsync(host_cnt.data(), ctx->d_counters.p, sizeof(ChunkCounters) * host_cnt.size(), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+
+    RtRenderStats rs;
+    memset(&rs, 0, sizeof(rs));
+    bool overflow = false;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        rs.primary_hits += host_cnt[c].n_hits;
+        rs.reflection_rays += host_cnt[c].refl_rays;
+        rs.reflection_shadow_rays += host_cnt[c].refl_shadow_rays;
+        overflow |= host_cnt[c].stack_overflow != 0;
+    }
+    // primary rays = supersampled pixels of the owned tiles that lie inside the frame
+    for (uint32_t tile : tiles) {
+        int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+        int w = std::min(tile_size, s->image_width - tx * tile_size), h = std::min(tile_size, s->image_height - ty * tile_size);
+        rs.primary_rays += (uint64_t)w * h * fr.factor * fr.factor;
+    }
+    rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
+    rs.kernel_launches = launches;
+    cudaEventElapsedTime(&rs.device_ms, ev_begin, ev_end);
+    for (const TimedLaunch& tl : ctx->timed) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, tl.a, tl.b);
+        if (tl.stage == ST_PRIMARY) rs.trace_primary_ms += ms;
+        else if (tl.stage == ST_REFLECT) rs.reflect_ms += ms;
+        else if (tl.stage == ST_SHADE) rs.shade_ms += ms;
+        else rs.resolve_ms += ms;
+    }
+    if (stats) *stats = rs;
+    if (overflow) return fail(ctx, RT_ERR_STATE, "traversal stack overflow (tree deeper than RT_MAX_TREE_DEPTH)");
+    return RT_OK;
+}
+
+int rt_render(RtContext* ctx, const RtSettings* s, uint32_t* argb_out, RtRenderStats* stats)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (int r = validate_settings(ctx, s)) return r;
+    if (!argb_out) return fail(ctx, RT_ERR_INVALID, "argb_out is NULL");
+    const size_t n = (size_t)s->image_width * s->image_height;
+    RT_CUDA(ctx, ctx->d_frame.ensure(n));
+    int r = rt_render_device(ctx, s, ctx->d_frame.p, 64, 1, 0, stats);
+    if (r) return r;
+    RT_CUDA(ctx, cudaMemcpyAsync(argb_out, ctx->d_frame.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+static int pack_unpack(RtContext* ctx, const RtSettings* s, const uint32_t* d_frame_in, uint32_t* d_frame_out, uint32_t* d_staging,
+                       int tile_size, int tile_mod, int tile_rem, int unpack)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (int r = validate_settings(ctx, s)) return r;
+    if (int r = check_tile_args(ctx, tile_size, tile_mod, tile_rem)) return r;
+    int tiles_x = 0;
+    std::vector<uint32_t> tiles = owned_tiles(s, tile_size, tile_mod, tile_rem, &tiles_x);
+    if (tiles.empty()) return RT_OK;
+    // the tile list of another shard may be needed while d_tiles holds ours: use a scratch allocation
+    uint32_t* d_list = nullptr;
+    RT_CUDA(ctx, cudaMallocAsync((void**)&d_list, tiles.size() * sizeof(uint32_t), ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d_list, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    WorkView wk;
+    memset(&wk, 0, sizeof(wk));
+    wk.tiles = d_list;
+    wk.tile_begin = 0;
+    wk.tile_end = (uint32_t)tiles.size();
+    wk.tiles_x = tiles_x;
+    k_pack_tiles<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_frame_in, d_staging, wk, tile_size, s->image_width, s->image_height, unpack, d_frame_out);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaFreeAsync(d_list, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_pack_tiles(RtContext* ctx, const RtSettings* s, const uint32_t* d_frame, uint32_t* d_staging, int tile_size, int tile_mod, int tile_rem)
+{
+    return pack_unpack(ctx, s, d_frame, nullptr, d_staging, tile_size, tile_mod, tile_rem, 0);
+}
+
+int rt_unpack_tiles(RtContext* ctx, const RtSettings* s, uint32_t* d_frame, const uint32_t* d_staging, int tile_size, int tile_mod, int tile_rem)
+{
+    return pack_unpack(ctx, s, nullptr, d_frame, const_cast<uint32_t*>(d_staging), tile_size, tile_mod, tile_rem, 1);
+}
+
+int rt_intersect(RtContext* ctx, const float* o3, const float* d3, size_t n, int32_t* tri_id, float* t, float* u, float* v)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (!ctx->bvh_valid) return fail(ctx, RT_ERR_STATE, "rt_build_bvh has not been called for the current triangles");
+    if (n == 0) return RT_OK;
+    if (!o3 || !d3) return fail(ctx, RT_ERR_INVALID, "ray arrays are NULL");
+    cudaStream_t st = ctx->stream;
+    RT_CUDA(ctx, ctx->b_a.ensure(3 * n)); RT_CUDA(ctx, ctx->b_b.ensure(3 * n));
+    RT_CUDA(ctx, ctx->b_id.ensure(n)); RT_CUDA(ctx, ctx->b_t.ensure(n)); RT_CUDA(ctx, ctx->b_u.ensure(n)); RT_CUDA(ctx, ctx->b_v.ensure(n));
+    RT_CUDA(ctx, ctx->d_flag.ensure(1));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_a.p, o3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_b.p, d3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(unsigned int), st));
+    static int grid = 0;
+    if (!grid) grid = grid_for(ctx, (const void*)k_intersect, kQueueThreads);
+    int blocks = (int)std::min<size_t>((size_t)grid, (n + kQueueThreads - 1) / kQueueThreads);
+    k_intersect<<<blocks, kQueueThreads, 0, st>>>(scene_view(ctx), ctx->b_a.p, ctx->b_b.p, n, ctx->d_orig.p, ctx->b_id.p, ctx->b_t.p, ctx->b_u.p,
+                                                 ctx->b_v.p, ctx->d_flag.p);
+    RT_CUDA(ctx, cudaGetLastError());
+    unsigned int flag = 0;
+    if (tri_id) RT_CUDA(ctx, cudaMemcpyAsync(tri_id, ctx->b_id.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (t) RT_CUDA(ctx, cudaMemcpyAsync(t, ctx->b_t.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (u) RT_CUDA(ctx, cudaMemcpyAsync(u, ctx->b_u.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (v) RT_CUDA(ctx, cudaMemcpyAsync(v, ctx->b_v.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    if (flag) return fail(ctx, RT_ERR_STATE, "traversal stack overflow");
+    return RT_OK;
+}
+
+int rt_occluded(RtContext* ctx, const float* p3, const float* n3, size_t n, uint8_t* occluded)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (!ctx->bvh_valid) return fail(ctx, RT_ERR_STATE, "rt_build_bvh has not been called for the current triangles");
+    if (n == 0) return RT_OK;
+    if (!p3 || !n3 || !occluded) return fail(ctx, RT_ERR_INVALID, "arrays are NULL");
+    cudaStream_t st = ctx->stream;
+    RT_CUDA(ctx, ctx->b_a.ensure(3 * n)); RT_CUDA(ctx, ctx->b_b.ensure(3 * n)); RT_CUDA(ctx, ctx->b_occ.ensure(n));
+    RT_CUDA(ctx, ctx->d_flag.ensure(1));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_a.p, p3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_b.p, n3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(unsigned int), st));
+    static int grid = 0;
+    if (!grid) grid = grid_for(ctx, (const void*)k_occluded, kQueueThreads);
+    int blocks = (int)std::min<size_t>((size_t)grid, (n + kQueueThreads - 1) / kQueueThreads);
+    k_occluded<<<blocks, kQueueThreads, 0, st>>>(scene_view(ctx), ctx->light, ctx->b_a.p, ctx->b_b.p, n, ctx->b_occ.p, ctx->d_flag.p);
+    RT_CUDA(ctx, cudaGetLastError());
+    unsigned int flag = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(occluded, ctx->b_occ.p, n, cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    if (flag) return fail(ctx, RT_ERR_STATE, "traversal stack overflow");
+    return RT_OK;
+}
+
+int rt_generate_primary_rays(RtContext* ctx, const RtSettings* s, float* o3, float* d3)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (int r = validate_settings(ctx, s)) return r;
+    if (!ctx->camera_set) return fail(ctx, RT_ERR_STATE, "rt_set_camera has not been called");
+    if (!o3 || !d3) return fail(ctx, RT_ERR_INVALID, "arrays are NULL");
+    FrameView fr = frame_view(ctx, s);
+    size_t n = (size_t)fr.rw * fr.rh;
+    RT_CUDA(ctx, ctx->b_a.ensure(3 * n)); RT_CUDA(ctx, ctx->b_b.ensure(3 * n));
+    k_raygen<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(fr, ctx->b_a.p, ctx->b_b.p);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpyAsync(o3, ctx->b_a.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(d3, ctx->b_b.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_resolve_ssaa(RtContext* ctx, const uint32_t* argb_in, int width, int height, int factor, uint32_t* argb_out)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (!argb_in || !argb_out || factor < 1 || width <= 0 || height <= 0) return fail(ctx, RT_ERR_INVALID, "bad resolve arguments");
+    if (width % factor || height % factor) return fail(ctx, RT_ERR_INVALID, "image size not divisible by the factor (imageUtils.h:100-112)");
+    const int w = width / factor, h = height / factor;
+    RtSettings s;
+    rt_default_settings(&s);
+    s.image_width = w; s.image_height = h;
+    const int tile = 64;
+    int tiles_x = 0;
+    std::vector<uint32_t> tiles = owned_tiles(&s, tile, 1, 0, &tiles_x);
+    RT_CUDA(ctx, ctx->d_super.ensure((size_t)width * height));
+    RT_CUDA(ctx, ctx->d_frame.ensure((size_t)w * h));
+    RT_CUDA(ctx, ctx->d_tiles.ensure(tiles.size()));
+    cudaStream_t st = ctx->stream;
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_super.p, argb_in, (size_t)width * height * 4, cudaMemcpyHostToDevice, st));
+    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, st));
+    WorkView wk;
+    memset(&wk, 0, sizeof(wk));
+    wk.tiles = ctx->d_tiles.p; wk.tile_begin = 0; wk.tile_end = (uint32_t)tiles.size(); wk.tiles_x = tiles_x;
+    k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_super.p, ctx->d_frame.p, wk, tile, factor, w, h);
+    RT_CUDA(ctx, cudaGetLastError());
+    RT_CUDA(ctx, cudaMemcpyAsync(argb_out, ctx->d_frame.p, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,57 @@
+// scene_layout.h -- the flattened, HBM-resident form of the reference's pointer octree (bvh.h:108-289).
+//
+// Reference layout (per node, 176 B + heap): 8 child pointers, std::vector<Triangle*>, AABB, 7 near + 7 far floats.
+// B200 layout (SoA, read with 128-bit loads):
+//
+//   recs[]  : one 64-byte "child record" per NON-EMPTY octree cell = 4 x float4
+//               q0 = near[0..3]      q1 = near[4..6], far[0]      q2 = far[1..4]
+//               q3 = far[5], far[6], bits(link), bits(meta)
+//             meta bit 31 = leaf; low bits = triangle count (leaf) or number of child records (interior, 1..8)
+//             link        = first triangle (leaf) or first child record (interior)
+//             The (<= 8) records of one interior cell are contiguous and start on a 128-byte boundary, so a cell
+//             is 1..4 full cache lines.  Record 0 is the root cell itself.  Cells are laid out depth-first, so a
+//             subtree is one contiguous span.  Empty cells (the reference allocates all 8 children, bvh.h:159-166)
+//             have near=+inf/far=-inf, can never pass the slab test (bvh.h:101) and are dropped.
+//             Bounds are widened by RT_SLAB_PAD_ULPS ulps: the slab test multiplies by a reciprocal where the
+//             reference divides (bvh.h:92-93), so the widening keeps it conservative; it can only add visits.
+//   tris[]  : 48 bytes per triangle in LEAF order = 3 x float4: (a.xyz, n.x) (b.xyz, n.y) (c.xyz, n.z) with
+//             n = cross(b-a, c-a), the un-normalised normal the reference caches (triangle.cpp:9-10).
+//   shade[] : 32 bytes per triangle in leaf order, read by shading only = 2 x float4:
+//             (u_a, u_b, u_c, v_a) (v_b, v_c, bits(material), bits(original index))
+#pragma once
+
+#include <stdint.h>
+#include <vector>
+
+#include "rt_math.h"
+
+#define RT_SLAB_PAD_ULPS 4
+#define RT_MAX_TREE_DEPTH 20
+#define RT_META_LEAF 0x80000000u
+
+namespace rtb {
+
+struct alignas(16) F4 {
+    float x, y, z, w;
+};
+
+struct FlatScene {
+    std::vector<F4> recs;        // 4 per record
+    std::vector<F4> tris;        // 3 per triangle, leaf order
+    std::vector<F4> shade;       // 2 per triangle, leaf order
+    std::vector<int32_t> orig;   // leaf order -> index in the caller's array
+    // statistics of the (reference-shaped) octree
+    uint64_t nodes = 0, leaves = 0, empty_leaves = 0, interior = 0;
+    uint32_t max_depth_reached = 0, max_leaf_size = 0;
+    uint64_t n_records = 0;
+};
+
+// Builds the reference's octree (same cells, same leaf contents in the same order as sequential insertion,
+// bvh.cpp:19-66 / bvh.h:141-210) top-down and flattens it.  uv6 / mat may be null (defaults of triangle.h:48).
+void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, size_t n, int max_depth,
+                      int leaf_max, FlatScene& out);
+
+inline uint32_t f2u(float f) { uint32_t u; __builtin_memcpy(&u, &f, 4); return u; }
+inline float u2f(uint32_t u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
+
+} // namespace rtb

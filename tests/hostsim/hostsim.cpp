@@ -1,0 +1,429 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY (tests/hostsim/librtb200_hostsim.so).
+//
+// Compiles the per-ray source of the CUDA kernels (raytracercpp_b200/csrc/rt_device.h) with g++ and drives it
+// through the SAME C ABI as librtb200.so, so that the kernel logic (traversal, shading, reflection fan, queues,
+// tiles, resolve) can be checked against the oracle in this GPU-less container before GPU minutes are spent.
+// It is NOT a product path: the package never loads it, `raytracercpp_b200.load_library()` only ever opens
+// librtb200.so, and rt_create() of the real library fails without a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#include "../../raytracercpp_b200/csrc/rt_device.h"
+#include "../../raytracercpp_b200/csrc/host_common.h"
+#include "../../raytracercpp_b200/csrc/scene_layout.h"
+
+using namespace rtb;
+
+struct HostTexture {
+    std::vector<uint8_t> bytes;
+    int w = 0, h = 0, format = 0;
+};
+
+struct RtContext {
+    std::string error;
+    std::vector<float> xyz9, uv6;
+    std::vector<int32_t> mat;
+    bool has_uv = false, has_mat = false;
+    int min_mat = 0, max_mat = -1;
+    bool bvh_valid = false, camera_set = false;
+    FlatScene flat;
+    RtBvhInfo info{};
+    std::vector<F4> mats;
+    int n_mats = 0;
+    bool any_reflective = false;
+    HostTexture tex[RT_TEX_COUNT];
+    M4 proj_inv{}, cam_to_world{};
+    V3 cam_pos{0, 0, 0}, light{3, 3, 2};
+};
+
+static int fail(RtContext* c, int code, const std::string& msg)
+{
+    if (c) c->error = msg;
+    return code;
+}
+
+static SceneView scene_view(const RtContext* c)
+{
+    SceneView sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.recs = c->flat.recs.data();
+    sc.tris = c->flat.tris.data();
+    sc.shade = c->flat.shade.data();
+    sc.mats = c->mats.data();
+    sc.n_mats = c->n_mats;
+    sc.n_tris = (uint32_t)(c->xyz9.size() / 9);
+    for (int i = 0; i < RT_TEX_COUNT; i++) {
+        sc.tex[i].data = c->tex[i].bytes.data();
+        sc.tex[i].w = c->tex[i].w;
+        sc.tex[i].h = c->tex[i].h;
+        sc.tex[i].format = c->tex[i].format;
+    }
+    return sc;
+}
+
+static FrameView frame_view(const RtContext* c, const RtSettings* s)
+{
+    FrameView fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.proj_inv = c->proj_inv;
+    fr.cam_to_world = c->cam_to_world;
+    fr.cam_pos = c->cam_pos;
+    fr.light = c->light;
+    fr.factor = s->enable_ssaa ? s->ssaa_factor : 1;
+    fr.rw = s->image_width * fr.factor;
+    fr.rh = s->image_height * fr.factor;
+    fr.s = *s;
+    return fr;
+}
+
+extern "C" {
+
+void rt_default_settings(RtSettings* s) { if (s) default_settings(s); }
+uint32_t rt_pixel_seed(uint32_t pixel_index, uint32_t rng_seed) { return pixel_seed(pixel_index, rng_seed); }
+
+void rt_perspective_inverse(float fov, float aspect, float znear, float zfar, float proj_inv_out[16])
+{
+    M4 inv = invert_matrix(perspective_matrix(fov, aspect, znear, zfar));
+    memcpy(proj_inv_out, inv.m, sizeof(inv.m));
+}
+
+void rt_invert_transform(const float m[16], float out[16])
+{
+    M4 a;
+    memcpy(a.m, m, sizeof(a.m));
+    M4 inv = invert_matrix(a);
+    memcpy(out, inv.m, sizeof(inv.m));
+}
+
+void rt_transform_point(const float m[16], const float p[3], float out[3])
+{
+    M4 a;
+    memcpy(a.m, m, sizeof(a.m));
+    V3 q = xform_point(a, v3(p[0], p[1], p[2]));
+    out[0] = q.x; out[1] = q.y; out[2] = q.z;
+}
+
+int rt_create(int, RtContext** out)
+{
+    RtContext* c = new RtContext();
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) c->cam_to_world.m[i][j] = c->proj_inv.m[i][j] = (i == j) ? 1.0f : 0.0f;
+    *out = c;
+    return RT_OK;
+}
+void rt_destroy(RtContext* c) { delete c; }
+const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""; }
+
+int rt_set_triangles(RtContext* c, const float* xyz9, const float* uv6, const int32_t* mat, size_t n)
+{
+    c->xyz9.assign(xyz9, xyz9 + 9 * n);
+    c->has_uv = uv6 != nullptr;
+    c->has_mat = mat != nullptr;
+    if (uv6) c->uv6.assign(uv6, uv6 + 6 * n); else c->uv6.clear();
+    if (mat) c->mat.assign(mat, mat + n); else c->mat.clear();
+    c->min_mat = n ? (mat ? *std::min_element(mat, mat + n) : -1) : 0;
+    c->max_mat = n ? (mat ? *std::max_element(mat, mat + n) : -1) : -1;
+    c->bvh_valid = false;
+    return RT_OK;
+}
+
+int rt_build_bvh(RtContext* c, int max_depth, int leaf_max)
+{
+    if (max_depth < 0 || max_depth > RT_MAX_TREE_DEPTH) return fail(c, RT_ERR_INVALID, "max_depth");
+    if (leaf_max < 0) return fail(c, RT_ERR_INVALID, "leaf_max");
+    size_t n = c->xyz9.size() / 9;
+    build_flat_scene(c->xyz9.data(), c->has_uv ? c->uv6.data() : nullptr, c->has_mat ? c->mat.data() : nullptr, n, max_depth, leaf_max, c->flat);
+    RtBvhInfo& bi = c->info;
+    memset(&bi, 0, sizeof(bi));
+    bi.triangles = n;
+    bi.nodes = c->flat.nodes; bi.leaves = c->flat.leaves; bi.empty_leaves = c->flat.empty_leaves; bi.interior = c->flat.interior;
+    bi.max_depth_reached = c->flat.max_depth_reached; bi.max_leaf_size = c->flat.max_leaf_size;
+    bi.child_records = c->flat.n_records;
+    bi.device_bytes = (c->flat.recs.size() + c->flat.tris.size() + c->flat.shade.size()) * sizeof(F4) + c->flat.orig.size() * 4;
+    c->bvh_valid = true;
+    return RT_OK;
+}
+
+int rt_bvh_info(const RtContext* c, RtBvhInfo* out)
+{
+    if (!c->bvh_valid) return RT_ERR_STATE;
+    *out = c->info;
+    return RT_OK;
+}
+
+int rt_transform_triangles(RtContext* c, const float m[16], int max_depth, int leaf_max)
+{
+    M4 t;
+    memcpy(t.m, m, sizeof(t.m));
+    for (size_t i = 0; i < c->xyz9.size() / 3; i++) {
+        V3 p = xform_point(t, v3(c->xyz9[3 * i], c->xyz9[3 * i + 1], c->xyz9[3 * i + 2]));
+        c->xyz9[3 * i] = p.x; c->xyz9[3 * i + 1] = p.y; c->xyz9[3 * i + 2] = p.z;
+    }
+    return rt_build_bvh(c, max_depth, leaf_max);
+}
+
+int rt_set_materials(RtContext* c, const RtMaterial* mats, size_t n)
+{
+    c->mats.resize(4 * n);
+    if (n) memcpy(c->mats.data(), mats, n * sizeof(RtMaterial));
+    c->n_mats = (int)n;
+    c->any_reflective = false;
+    for (size_t i = 0; i < n; i++) if (mats[i].reflection > 0.0f) c->any_reflective = true;
+    return RT_OK;
+}
+
+static int set_tex(RtContext* c, int slot, const void* data, int w, int h, int format)
+{
+    if (slot < 0 || slot >= RT_TEX_COUNT || !data || w <= 0 || h <= 0) return fail(c, RT_ERR_INVALID, "texture");
+    size_t bytes = (size_t)w * h * (format == 1 ? 4 : 16);
+    c->tex[slot].bytes.resize(bytes + 16);
+    // keep the texel array 16-byte aligned for the F4 view
+    memcpy(c->tex[slot].bytes.data(), data, bytes);
+    c->tex[slot].w = w; c->tex[slot].h = h; c->tex[slot].format = format;
+    return RT_OK;
+}
+int rt_set_texture_f32(RtContext* c, int slot, const float* rgba, int w, int h) { return set_tex(c, slot, rgba, w, h, 2); }
+int rt_set_texture_u8(RtContext* c, int slot, const uint8_t* rgba, int w, int h) { return set_tex(c, slot, rgba, w, h, 1); }
+int rt_clear_texture(RtContext* c, int slot)
+{
+    if (slot < 0 || slot >= RT_TEX_COUNT) return fail(c, RT_ERR_INVALID, "texture slot");
+    c->tex[slot] = HostTexture();
+    return RT_OK;
+}
+
+int rt_set_camera(RtContext* c, const float proj_inv[16], const float cam_to_world[16], const float position[3])
+{
+    memcpy(c->proj_inv.m, proj_inv, 64);
+    memcpy(c->cam_to_world.m, cam_to_world, 64);
+    c->cam_pos = v3(position[0], position[1], position[2]);
+    c->camera_set = true;
+    return RT_OK;
+}
+int rt_set_light(RtContext* c, const float p[3]) { c->light = v3(p[0], p[1], p[2]); return RT_OK; }
+
+int rt_tile_count(const RtSettings* s, int tile_size, int tile_mod, int tile_rem)
+{
+    if (!s || tile_size <= 0 || tile_mod <= 0 || tile_rem < 0 || tile_rem >= tile_mod) return RT_ERR_INVALID;
+    return (int)owned_tiles(s, tile_size, tile_mod, tile_rem, nullptr).size();
+}
+
+// Same stage order as the CUDA driver (k_primary -> k_reflect -> k_shade -> k_resolve), one loop per kernel.
+int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_size, int tile_mod, int tile_rem, RtRenderStats* stats)
+{
+    std::string why;
+    if (int r = check_settings(s, why)) return fail(c, r, why);
+    SceneFacts f;
+    f.bvh_valid = c->bvh_valid; f.camera_set = c->camera_set; f.n_tris = (uint32_t)(c->xyz9.size() / 9); f.n_mats = c->n_mats;
+    f.min_mat_index = c->min_mat; f.max_mat_index = c->max_mat;
+    for (int i = 0; i < RT_TEX_COUNT; i++) f.tex_format[i] = c->tex[i].format;
+    if (int r = check_scene_for_render(f, s, why)) return fail(c, r, why);
+    if (tile_size <= 0 || tile_mod <= 0 || tile_rem < 0 || tile_rem >= tile_mod) return fail(c, RT_ERR_INVALID, "tile args");
+
+    const FrameView fr = frame_view(c, s);
+    const SceneView sc = scene_view(c);
+    const bool reflect = c->any_reflective && s->shading_method == RT_SHADING;
+    int tiles_x = 0;
+    std::vector<uint32_t> tiles = owned_tiles(s, tile_size, tile_mod, tile_rem, &tiles_x);
+    const int tile_px = tile_size * fr.factor;
+    std::vector<uint32_t> super_store;
+    uint32_t* super = out;
+    if (fr.factor > 1) {
+        super_store.assign((size_t)fr.rw * fr.rh, 0);
+        super = super_store.data();
+    }
+    RtRenderStats rs;
+    memset(&rs, 0, sizeof(rs));
+
+    // k_primary
+    struct QEntry { uint32_t pix; HitRec hr; };
+    std::vector<QEntry> queue;
+    std::vector<uint32_t> refl_idx;
+    for (uint32_t tile : tiles) {
+        int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+        for (int ly = 0; ly < tile_px; ly++)
+            for (int lx = 0; lx < tile_px; lx++) {
+                int px = tx * tile_px + lx, py = ty * tile_px + ly;
+                if (px >= fr.rw || py >= fr.rh) continue;
+                rs.primary_rays++;
+                V3 o, d;
+                primary_ray(fr, px, py, o, d);
+                HitRec hr;
+                TraceCounters tc{0, 0, 0};
+                bool found = trace_closest(sc, o, d, hr, &tc);
+                if (tc.stack_overflow) return fail(c, RT_ERR_STATE, "traversal stack overflow");
+                bool hit = found && hr.t > 0.1f;
+                if (!hit) { super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d)); continue; }
+                if (reflect) {
+                    TriShade ts = load_tri_shade(sc, hr.tri);
+                    if (load_material(sc, ts.mat).reflection > 0.0f) refl_idx.push_back((uint32_t)queue.size());
+                }
+                queue.push_back(QEntry{(uint32_t)py * (uint32_t)fr.rw + (uint32_t)px, hr});
+            }
+    }
+    rs.primary_hits = queue.size();
+    // k_reflect
+    std::vector<Col> refl_rgb(queue.size(), col(0.0f));
+    uint64_t refl_rays = 0, refl_shadow = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : refl_rays, refl_shadow)
+    for (long long r = 0; r < (long long)refl_idx.size(); r++) {
+        const QEntry& e = queue[refl_idx[r]];
+        V3 o, d;
+        primary_ray(fr, (int)(e.pix % (uint32_t)fr.rw), (int)(e.pix / (uint32_t)fr.rw), o, d);
+        Hit hit = complete_hit(sc, e.hr);
+        V3 p;
+        MatView m;
+        shade_direct(sc, fr, o, d, hit, p, m);
+        XorShift32 rng;
+        rng.state = pixel_seed(e.pix, fr.s.rng_seed);
+        TraceCounters tc{0, 0, 0};
+        refl_rgb[refl_idx[r]] = compute_reflection(sc, fr, d, p, hit, m, 0, rng, &tc);
+        refl_rays += tc.refl_rays;
+        refl_shadow += tc.refl_shadow_rays;
+    }
+    rs.reflection_rays = refl_rays;
+    rs.reflection_shadow_rays = refl_shadow;
+    // k_shade
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long i = 0; i < (long long)queue.size(); i++) {
+        const QEntry& e = queue[i];
+        V3 o, d;
+        primary_ray(fr, (int)(e.pix % (uint32_t)fr.rw), (int)(e.pix / (uint32_t)fr.rw), o, d);
+        Hit hit = complete_hit(sc, e.hr);
+        Col cc;
+        if (fr.s.shading_method != RT_SHADING) cc = shade_debug(sc, fr, hit);
+        else {
+            V3 p;
+            MatView m;
+            Col direct = shade_direct(sc, fr, o, d, hit, p, m);
+            bool shadowed = false;
+            if (fr.s.compute_shadows) shadowed = trace_occluded(sc, p, hit.normal, fr.light, nullptr);
+            Col refl = m.reflection > 0.0f ? refl_rgb[i] : col(0.0f);
+            cc = shade_compose(fr, m, direct, shadowed, refl);
+        }
+        super[e.pix] = quantise_argb(cc);
+    }
+    rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
+    // k_resolve
+    if (fr.factor > 1) {
+        const int ff = fr.factor * fr.factor;
+        for (uint32_t tile : tiles) {
+            int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+            for (int iy = 0; iy < tile_size; iy++)
+                for (int ix = 0; ix < tile_size; ix++) {
+                    int x = tx * tile_size + ix, y = ty * tile_size + iy;
+                    if (x >= s->image_width || y >= s->image_height) continue;
+                    int ar = 0, ag = 0, ab = 0;
+                    for (int i = 0; i < fr.factor; i++)
+                        for (int j = 0; j < fr.factor; j++) {
+                            uint32_t cpx = super[(size_t)(y * fr.factor + i) * fr.rw + (size_t)x * fr.factor + j];
+                            ar += (cpx >> 16) & 0xff; ag += (cpx >> 8) & 0xff; ab += cpx & 0xff;
+                        }
+                    ar /= ff; ag /= ff; ab /= ff;
+                    out[(size_t)y * s->image_width + x] = 0xff000000u | ((uint32_t)(ar & 0xff) << 16) | ((uint32_t)(ag & 0xff) << 8) | (uint32_t)(ab & 0xff);
+                }
+        }
+    }
+    rs.kernel_launches = 0;
+    if (stats) *stats = rs;
+    return RT_OK;
+}
+
+int rt_render(RtContext* c, const RtSettings* s, uint32_t* argb_out, RtRenderStats* stats)
+{
+    return rt_render_device(c, s, argb_out, 64, 1, 0, stats);
+}
+
+static void tile_copy(const RtSettings* s, const uint32_t* frame_in, uint32_t* frame_out, uint32_t* staging, int tile_size, int mod, int rem, int unpack)
+{
+    int tiles_x = 0;
+    std::vector<uint32_t> tiles = owned_tiles(s, tile_size, mod, rem, &tiles_x);
+    size_t g = 0;
+    for (uint32_t tile : tiles) {
+        int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+        for (int iy = 0; iy < tile_size; iy++)
+            for (int ix = 0; ix < tile_size; ix++, g++) {
+                int x = tx * tile_size + ix, y = ty * tile_size + iy;
+                if (x >= s->image_width || y >= s->image_height) { if (!unpack) staging[g] = 0; continue; }
+                if (unpack) frame_out[(size_t)y * s->image_width + x] = staging[g];
+                else staging[g] = frame_in[(size_t)y * s->image_width + x];
+            }
+    }
+}
+
+int rt_pack_tiles(RtContext*, const RtSettings* s, const uint32_t* frame, uint32_t* staging, int tile_size, int mod, int rem)
+{
+    tile_copy(s, frame, nullptr, staging, tile_size, mod, rem, 0);
+    return RT_OK;
+}
+int rt_unpack_tiles(RtContext*, const RtSettings* s, uint32_t* frame, const uint32_t* staging, int tile_size, int mod, int rem)
+{
+    tile_copy(s, nullptr, frame, const_cast<uint32_t*>(staging), tile_size, mod, rem, 1);
+    return RT_OK;
+}
+
+int rt_intersect(RtContext* c, const float* o3, const float* d3, size_t n, int32_t* tri_id, float* t, float* u, float* v)
+{
+    if (!c->bvh_valid) return fail(c, RT_ERR_STATE, "rt_build_bvh has not been called for the current triangles");
+    const SceneView sc = scene_view(c);
+    int overflow = 0;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < (long long)n; i++) {
+        HitRec hr;
+        TraceCounters tc{0, 0, 0};
+        bool found = trace_closest(sc, v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]), hr, &tc);
+        if (tc.stack_overflow) overflow = 1;
+        if (tri_id) tri_id[i] = found ? c->flat.orig[hr.tri] : -1;
+        if (t) t[i] = found ? hr.t : -1.0f;
+        if (u) u[i] = found ? hr.u : 0.0f;
+        if (v) v[i] = found ? hr.v : 0.0f;
+    }
+    return overflow ? fail(c, RT_ERR_STATE, "traversal stack overflow") : RT_OK;
+}
+
+int rt_occluded(RtContext* c, const float* p3, const float* n3, size_t n, uint8_t* occluded)
+{
+    if (!c->bvh_valid) return fail(c, RT_ERR_STATE, "rt_build_bvh has not been called for the current triangles");
+    const SceneView sc = scene_view(c);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < (long long)n; i++)
+        occluded[i] = trace_occluded(sc, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]), c->light, nullptr) ? 1 : 0;
+    return RT_OK;
+}
+
+int rt_generate_primary_rays(RtContext* c, const RtSettings* s, float* o3, float* d3)
+{
+    std::string why;
+    if (int r = check_settings(s, why)) return fail(c, r, why);
+    FrameView fr = frame_view(c, s);
+    for (size_t i = 0; i < (size_t)fr.rw * fr.rh; i++) {
+        V3 o, d;
+        primary_ray(fr, (int)(i % (size_t)fr.rw), (int)(i / (size_t)fr.rw), o, d);
+        o3[3 * i] = o.x; o3[3 * i + 1] = o.y; o3[3 * i + 2] = o.z;
+        d3[3 * i] = d.x; d3[3 * i + 1] = d.y; d3[3 * i + 2] = d.z;
+    }
+    return RT_OK;
+}
+
+int rt_resolve_ssaa(RtContext* c, const uint32_t* in, int width, int height, int factor, uint32_t* out)
+{
+    if (factor < 1 || width % factor || height % factor) return fail(c, RT_ERR_INVALID, "image size not divisible by the factor");
+    int w = width / factor, h = height / factor, ff = factor * factor;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int ar = 0, ag = 0, ab = 0;
+            for (int i = 0; i < factor; i++)
+                for (int j = 0; j < factor; j++) {
+                    uint32_t cpx = in[(size_t)(y * factor + i) * width + (size_t)x * factor + j];
+                    ar += (cpx >> 16) & 0xff; ag += (cpx >> 8) & 0xff; ab += cpx & 0xff;
+                }
+            ar /= ff; ag /= ff; ab /= ff;
+            out[(size_t)y * w + x] = 0xff000000u | ((uint32_t)(ar & 0xff) << 16) | ((uint32_t)(ag & 0xff) << 8) | (uint32_t)(ab & 0xff);
+        }
+    return RT_OK;
+}
+
+} // extern "C"
