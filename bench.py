@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s (primary + shadow) of the ray-tracing hot path on BASELINE.json's headline configuration:
+synthetic 10 M-triangle displaced sphere, 3840x2160, 16 spp (ssaa_factor 4), one point light with hard shadows,
+screen-tile sharded over N GPUs (strong scaling: the frame is fixed, the tiles are dealt over the ranks).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU tracer (oracle/_ref) on the host cores
+
+A step is one full frame.  `value` = rays of the whole frame / device time (CUDA events on the launching stream, scene
+and all buffers resident in HBM, max over ranks); `e2e` = the same frame through the public call with a HOST
+framebuffer (camera/settings in, 33 MB ARGB32 out, copies inside the timed region).  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (triangles, width, height, ssaa, bvh_max_depth, bvh_leaf_object_count)
+    "cfg4_sphere10M_4k_16spp": (10_000_000, 3840, 2160, 4, 12, 40),
+    "sphere1M_1080p_4spp": (1_000_000, 1920, 1080, 2, 12, 40),         # for quick local checks only
+}
+FOV, LIGHT = 80.0, (3.0, 3.0, 2.0)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_scene(name):
+    from raytracercpp_b200 import scenes
+    from raytracercpp_b200.renderer import precompute_materials
+    tris, w, h, f, depth, leaf = WORKLOADS[name]
+    xyz9, uv6, mat = scenes.displaced_sphere(*scenes.sphere_grid_for(tris))
+    mats = precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
+    kw = dict(image_width=w, image_height=h, enable_ssaa=int(f > 1), ssaa_factor=f, compute_shadows=1, bvh_max_depth=depth,
+              bvh_leaf_object_count=leaf)
+    return dict(xyz9=xyz9, uv6=uv6, mat=mat, mats=mats, kw=kw, name=name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def reference_sample(scene, row_step, threads=0, renderer=None, tracer=None):
+    """Times the compiled reference (oracle/_ref/libref.so, or the oracle port if that was never built) on every
+    `row_step`-th row of the supersampled frame, driving the reference's public trace_ray per pixel exactly as its
+    ray_trace() loop does.  Returns (renderer, rays, ms, kind, cores)."""
+    from oracle import bindings
+    if tracer is None:
+        kind = "reference" if bindings.available("ref") else "port"
+        tracer = bindings.CpuTracer("ref" if kind == "reference" else "oracle")
+    kind = "reference" if tracer.kind == "ref" else "port"
+    if renderer is None:
+        s = bindings.default_settings(**scene["kw"])
+        renderer = tracer.renderer()
+        renderer.configure(s, FOV)
+        t0 = time.time()
+        renderer.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
+        log(f"[reference] BVH::BVH over {len(scene['xyz9'])} triangles: {time.time() - t0:.1f} s")
+        renderer.set_materials(scene["mats"])
+        renderer.set_light(LIGHT)
+    rw, rh = renderer._super_dims()
+    _, ms = renderer.trace_rows(row_begin=row_step // 2, row_end=rh, row_step=row_step, reseed=False, threads=threads, want_image=False)
+    rows = len(range(row_step // 2, rh, row_step))
+    if kind == "reference":
+        hits = renderer.last_hit_count()
+    else:
+        hits = renderer.count_rows(row_begin=row_step // 2, row_end=rh, row_step=row_step)["shadow_rays"]
+    rays = rows * rw + hits
+    return renderer, tracer, rays, ms, kind, tracer.max_threads() if threads <= 0 else threads
+
+
+def run_reference(args, scene):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import bindings
+    if not (bindings.available("ref") or bindings.available("oracle")):
+        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libref.so nor oracle/liboracle.so is built"}))
+        return
+    kw = scene["kw"]
+    rh = kw["image_height"] * kw["ssaa_factor"]
+    # calibrate on a sparse sample, then size the per-step sample so that W + K steps take about two minutes
+    renderer, tracer, rays, ms, kind, cores = reference_sample(scene, row_step=max(rh // 16, 1))
+    per_ray_ms = ms / max(rays, 1)
+    budget_ms = 120_000.0 / (args.steps + args.warmup)
+    total_rays_est = rays * max(rh // 16, 1)
+    row_step = int(max(1, np.ceil(total_rays_est * per_ray_ms / budget_ms)))
+    log(f"[reference] calibration {ms:.0f} ms for {rays} rays -> row_step {row_step}")
+    times, nrays = [], 0
+    for i in range(args.warmup + args.steps):
+        _, _, rays, ms, _, _ = reference_sample(scene, row_step, renderer=renderer, tracer=tracer)
+        if i >= args.warmup:
+            times.append(ms)
+            nrays = rays
+    ms_step = float(np.mean(times))
+    value = nrays / ms_step / 1e3
+    sample = f"every {row_step}th row of the {kw['image_width'] * kw['ssaa_factor']}x{rh} supersampled frame ({nrays} rays per step)"
+    out = {
+        "impl": "reference", "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(scene, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(scene, n_gpus):
+    kw = scene["kw"]
+    return {"workload": scene["name"], "triangles": int(len(scene["xyz9"])), "image": f"{kw['image_width']}x{kw['image_height']}",
+            "spp": kw["ssaa_factor"] ** 2, "primary_rays": kw["image_width"] * kw["image_height"] * kw["ssaa_factor"] ** 2,
+            "shadows": "1 point light, hard", "bvh": f"octree max_depth {kw['bvh_max_depth']} leaf {kw['bvh_leaf_object_count']} (reference GUI defaults)",
+            "fov": FOV, "parallelism": f"screen tiles 64x64 round-robin over {n_gpus} GPU(s), scene replicated",
+            "l2": "scene (~0.9 GB) and sample buffer (0.5 GB) exceed the 126 MB L2; no flush between steps"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args, scene):
+    import torch
+    import torch.distributed as dist
+    from raytracercpp_b200 import api
+    from raytracercpp_b200.distributed import ShardedFrame
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = api.load_library()
+    ctx = api.Context(local, lib)
+    kw = scene["kw"]
+    s = api.default_settings(lib, **kw)
+    t0 = time.time()
+    ctx.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
+    info = ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
+    if rank == 0:
+        log(f"[ours] octree build {info['build_ms']:.0f} ms + upload {info['upload_ms']:.0f} ms, {info['child_records']} records, "
+            f"{info['device_bytes'] / 1e6:.0f} MB resident, max leaf {info['max_leaf_size']}")
+    ctx.set_materials(scene["mats"])
+    ctx.set_light(LIGHT)
+    f = kw["ssaa_factor"]
+    aspect = float(np.float32(kw["image_width"] * f) / np.float32(kw["image_height"] * f))
+    proj_inv = ctx.perspective_inverse(FOV, aspect)
+    cam = np.eye(4, dtype=np.float32)
+    ctx.set_camera(proj_inv, cam, (0, 0, 0))
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    frame = ShardedFrame(ctx, s, rank, world)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # --- work of the traversal (instrumented instantiations, outside every timed region)
+    ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
+    with torch.cuda.stream(stream):
+        work = frame.render()
+    ctx.set_option(api.RT_OPT_COUNT_WORK, 0)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            frame.render()
+            frame.gather()
+        sync_all()
+        sampler = ClockSampler(local)
+        sampler.start()
+        stage = {"k_primary": 0.0, "k_shade": 0.0, "k_reflect": 0.0, "k_resolve": 0.0}
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        rays_rank = 0
+        ev0.record(stream)
+        for _ in range(args.steps):
+            st = frame.render()
+            frame.gather()
+            stage["k_primary"] += st.trace_primary_ms; stage["k_shade"] += st.shade_ms
+            stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms
+            launches += st.kernel_launches + (world if world > 1 else 0)       # + pack and (world - 1) unpack kernels
+            rays_rank = st.total_rays
+        ev1.record(stream)
+        sync_all()
+        clocks = sampler.stop()
+        dev_ms = ev0.elapsed_time(ev1)
+
+        # --- end to end: host framebuffer, copies inside the timed region
+        host = torch.empty((kw["image_height"], kw["image_width"]), dtype=torch.int32).pin_memory()
+        for _ in range(min(args.warmup, 2)):
+            frame.render(); frame.gather(); host.copy_(frame.frame, non_blocking=True); stream.synchronize()
+        sync_all()
+        t_e2e = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.set_camera(proj_inv, cam, (0, 0, 0))                             # the step's inputs: camera + settings (kernel arguments)
+            frame.render()
+            frame.gather()
+            host.copy_(frame.frame, non_blocking=True)
+            stream.synchronize()
+        e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    dev_ms = reduce(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_ms = reduce(e2e_ms, dist.ReduceOp.MAX if world > 1 else None)
+    rays_total = reduce(float(rays_rank), dist.ReduceOp.SUM if world > 1 else None)
+    ms_step = dev_ms / args.steps
+    value = rays_total / ms_step / 1e3
+
+    if rank == 0:
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if peaks_file.exists():
+            peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        dom = max(("k_primary", "k_shade", "k_reflect"), key=lambda k: stage[k])
+        vt = {"k_primary": (work.primary_volume_tests, work.primary_triangle_tests), "k_shade": (work.shadow_volume_tests, work.shadow_triangle_tests),
+              "k_reflect": (work.reflection_volume_tests, work.reflection_triangle_tests)}[dom]
+        dom_bytes = 56 * vt[0] + 36 * vt[1]                                       # per launch (one launch per step and chunk set)
+        dom_ms = stage[dom] / args.steps
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_step": dom_ms,
+                    "definition": "56 B per 7-slab volume test + 36 B per triangle test performed by the kernel's traversal (rank 0's tiles), counted by the instrumented instantiation",
+                    "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
+        out = {
+            "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(scene, world), "rays_per_step": int(rays_total), "clocks": clocks,
+            "e2e": {"value": rays_total / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 2 * 64 + 12 + 12 + 100, "d2h_bytes_per_step": int(host.numel() * 4)},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "bvh": {k: info[k] for k in ("nodes", "interior", "leaves", "empty_leaves", "max_leaf_size", "child_records", "device_bytes", "build_ms", "upload_ms")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                _, _, rays, ms, kind, cores = reference_sample(scene, row_step=args.cpu_row_step)
+                out["cpu_baseline"] = {"value": rays / ms / 1e3, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                                       "sample": f"every {args.cpu_row_step}th row of the supersampled frame, {rays} rays in {ms / 1e3:.1f} s"}
+            except Exception as e:  # the checker is optional for the GPU number, never the other way round
+                out["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4_sphere10M_4k_16spp", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-row-step", type=int, default=48, help="cpu_baseline sample: every n-th supersampled row")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference" and int(os.environ.get("RANK", 0)) != 0:
+        return
+    t0 = time.time()
+    scene = make_scene(args.workload)
+    log(f"[{args.impl}] scene {args.workload}: {len(scene['xyz9'])} triangles generated in {time.time() - t0:.1f} s")
+    if args.impl == "reference":
+        run_reference(args, scene)
+    else:
+        run_ours(args, scene)
+
+
+if __name__ == "__main__":
+    main()

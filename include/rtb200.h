@@ -114,6 +114,12 @@ typedef struct RtRenderStats {
     float    reflect_ms;
     float    shadow_ms;
     float    resolve_ms;
+    /* Filled only when RT_OPT_COUNT_WORK is on (instrumented kernel instantiations, never the timed ones):
+     * 7-slab volume tests and ray/triangle tests the traversal performed, per ray class -- the V and T of
+     * the bytes-per-ray metric 56*V + 36*T.  Reflection = fan rays and their shadow rays. */
+    uint64_t primary_volume_tests, primary_triangle_tests;
+    uint64_t shadow_volume_tests, shadow_triangle_tests;
+    uint64_t reflection_volume_tests, reflection_triangle_tests;
 } RtRenderStats;
 
 /* Flattened-tree facts, for tests and DESIGN.md (the reference tree has the same node/leaf counts). */
@@ -138,6 +144,16 @@ uint32_t rt_pixel_seed(uint32_t pixel_index, uint32_t rng_seed);
 int rt_create(int device, RtContext** out);
 void rt_destroy(RtContext* ctx);
 const char* rt_last_error(const RtContext* ctx); /* ctx may be NULL for rt_create failures */
+
+/* Library knobs (no reference counterpart). */
+enum {
+    RT_OPT_COUNT_WORK = 0,    /* 1: run the instrumented kernels and fill the *_tests counters of RtRenderStats */
+    RT_OPT_CHUNK_PIXELS = 1   /* supersampled pixels per wavefront chunk (bounds ray-queue memory)             */
+};
+int rt_set_option(RtContext* ctx, int option, int64_t value);
+/* Run all of the context's work on the caller's CUDA stream (a cudaStream_t; NULL = back to the context's own
+ * non-blocking stream), so a host that already orders work on a stream -- or times it with events -- can do so. */
+int rt_set_stream(RtContext* ctx, void* cuda_stream);
 
 /* Renderer::set_triangles(const std::vector<Triangle>&) -- renderer.cpp:137-144.
  * xyz9: n*9 floats (a,b,c); uv6: n*6 floats (u_a,u_b,u_c,v_a,v_b,v_c) as Triangle::_tex_coords_u/_v

@@ -1,0 +1,192 @@
+// rtb200_renderer.hpp -- header-only C++ adapter: the method names of the reference's `Renderer`
+// (tp2/projets/renderer/renderer.h:38-169) for the ray-tracing path, forwarding to the C ABI of rtb200.h.
+//
+// It is duck-typed on the reference's own value types so that it compiles inside the reference tree without
+// dragging those headers in here (nothing is copied from them):
+//   TriangleT   : ._a ._b ._c (.x .y .z), ._tex_coords_u ._tex_coords_v (.x .y .z), ._materialIndex   (triangle.h:93-103)
+//   MaterialsT  : .materials = std::vector<MaterialT>; MaterialT: .ambient_coeff .diffuse .specular .emission (.r .g .b),
+//                 .reflection .roughness .ns .specular_threshold                                       (materials.h:14-38)
+//   ImageT      : .width() .height() .data() -> const float* RGBA                                      (image.h:99-118)
+//   TransformT  : .m[4][4] row-major                                                                   (mat.h)
+//   PointT      : .x .y .z
+// Members of the reference class that belong to the rasterizer, SSAO, analytic shapes, parallax mapping or the
+// cube-map skybox are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rtb200.h"
+
+namespace rtb200 {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+class Renderer {
+public:
+    explicit Renderer(int device = 0)
+    {
+        if (int rc = rt_create(device, &_ctx)) throw Error(rc, rt_last_error(nullptr));
+        rt_default_settings(&_settings);
+        for (int i = 0; i < 16; i++) _camera_to_world[i] = _previous_object_transform[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+        change_render_size(_settings.image_width, _settings.image_height);
+    }
+    ~Renderer() { rt_destroy(_ctx); }
+    Renderer(const Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
+
+    RtSettings& render_settings() { return _settings; }                                  // renderer.cpp:111-114
+
+    void get_render_width_height(const RtSettings& s, int& w, int& h) const              // renderer.cpp:116-120
+    {
+        w = s.enable_ssaa ? s.image_width * s.ssaa_factor : s.image_width;
+        h = s.enable_ssaa ? s.image_height * s.ssaa_factor : s.image_height;
+    }
+
+    template <class TriangleT>
+    void set_triangles(const std::vector<TriangleT>& tris)                              // renderer.cpp:137-144
+    {
+        std::vector<float> xyz9(tris.size() * 9), uv6(tris.size() * 6);
+        std::vector<int32_t> mat(tris.size());
+        for (size_t i = 0; i < tris.size(); i++) {
+            const TriangleT& t = tris[i];
+            float* p = &xyz9[9 * i];
+            p[0] = t._a.x; p[1] = t._a.y; p[2] = t._a.z; p[3] = t._b.x; p[4] = t._b.y; p[5] = t._b.z; p[6] = t._c.x; p[7] = t._c.y; p[8] = t._c.z;
+            float* q = &uv6[6 * i];
+            q[0] = t._tex_coords_u.x; q[1] = t._tex_coords_u.y; q[2] = t._tex_coords_u.z;
+            q[3] = t._tex_coords_v.x; q[4] = t._tex_coords_v.y; q[5] = t._tex_coords_v.z;
+            mat[i] = t._materialIndex;
+        }
+        check(rt_set_triangles(_ctx, xyz9.data(), uv6.data(), mat.data(), tris.size()));
+        reconstruct_bvh_new();
+    }
+
+    void reconstruct_bvh_new() { check(rt_build_bvh(_ctx, _settings.bvh_max_depth, _settings.bvh_leaf_object_count)); }  // :243-246
+
+    template <class MaterialsT>
+    void set_materials(const MaterialsT& ms)                                             // renderer.cpp:150-152
+    {
+        std::vector<RtMaterial> out(ms.materials.size());
+        for (size_t i = 0; i < out.size(); i++) {
+            const auto& m = ms.materials[i];
+            RtMaterial& o = out[i];
+            o.ambient_coeff[0] = m.ambient_coeff.r; o.ambient_coeff[1] = m.ambient_coeff.g; o.ambient_coeff[2] = m.ambient_coeff.b;
+            o.diffuse[0] = m.diffuse.r; o.diffuse[1] = m.diffuse.g; o.diffuse[2] = m.diffuse.b;
+            o.specular[0] = m.specular.r; o.specular[1] = m.specular.g; o.specular[2] = m.specular.b;
+            o.emission[0] = m.emission.r; o.emission[1] = m.emission.g; o.emission[2] = m.emission.b;
+            o.reflection = m.reflection; o.roughness = m.roughness; o.ns = m.ns; o.specular_threshold = m.specular_threshold;
+        }
+        check(rt_set_materials(_ctx, out.data(), out.size()));
+    }
+
+    template <class ImageT> void set_ao_map(const ImageT& im) { set_map(RT_TEX_AO, im); }                // renderer.cpp:194-201
+    template <class ImageT> void set_diffuse_map(const ImageT& im) { set_map(RT_TEX_DIFFUSE, im); }
+    template <class ImageT> void set_normal_map(const ImageT& im) { set_map(RT_TEX_NORMAL, im); }
+    template <class ImageT> void set_roughness_map(const ImageT& im) { set_map(RT_TEX_ROUGHNESS, im); }
+    template <class ImageT> void set_skysphere(const ImageT& im) { set_map(RT_TEX_SKYSPHERE, im); }
+    void clear_ao_map() { check(rt_clear_texture(_ctx, RT_TEX_AO)); }                                     // renderer.cpp:203-207
+    void clear_diffuse_map() { check(rt_clear_texture(_ctx, RT_TEX_DIFFUSE)); }
+    void clear_normal_map() { check(rt_clear_texture(_ctx, RT_TEX_NORMAL)); }
+    void clear_roughness_map() { check(rt_clear_texture(_ctx, RT_TEX_ROUGHNESS)); }
+
+    void change_camera_fov(float fov) { _fov = fov; push_camera(); }                                      // renderer.cpp:189
+    void change_camera_aspect_ratio(float aspect) { _aspect = aspect; push_camera(); }                    // renderer.cpp:190
+    template <class PointT> void set_light_position(const PointT& p)                                      // renderer.cpp:191
+    {
+        float l[3] = {p.x, p.y, p.z};
+        check(rt_set_light(_ctx, l));
+    }
+    template <class TransformT> void set_camera_transform(const TransformT& t)                            // renderer.cpp:226-233
+    {
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) _camera_to_world[4 * r + c] = t.m[r][c];
+        const float origin[3] = {0, 0, 0};
+        rt_transform_point(_camera_to_world, origin, _position);
+        push_camera();
+    }
+    void reset_previous_transform()                                                                        // renderer.cpp:212
+    {
+        for (int i = 0; i < 16; i++) _previous_object_transform[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    }
+    template <class TransformT> void set_object_transform(const TransformT& t)                            // renderer.cpp:214-224
+    {
+        float prev_inv[16], now[16], composed[16];
+        rt_invert_transform(_previous_object_transform, prev_inv);
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) now[4 * r + c] = t.m[r][c];
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) {
+                float acc = 0;
+                for (int k = 0; k < 4; k++) acc += now[4 * r + k] * prev_inv[4 * k + c];
+                composed[4 * r + c] = acc;
+            }
+        check(rt_transform_triangles(_ctx, composed, _settings.bvh_max_depth, _settings.bvh_leaf_object_count));
+        for (int i = 0; i < 16; i++) _previous_object_transform[i] = now[i];
+    }
+
+    void change_render_size(int width, int height)                                                         // renderer.cpp:250-261
+    {
+        _settings.image_width = width;
+        _settings.image_height = height;
+        int rw, rh;
+        get_render_width_height(_settings, rw, rh);
+        _aspect = (float)rw / rh;
+        push_camera();
+    }
+
+    // Renderer::ray_trace() (renderer.cpp:1068-1116); the SSAA resolve of post_process() happens in the same call.
+    void ray_trace()
+    {
+        int rw, rh;
+        get_render_width_height(_settings, rw, rh);
+        _aspect = (float)rw / rh;
+        push_camera();
+        _image.resize((size_t)_settings.image_width * _settings.image_height);
+        check(rt_render(_ctx, &_settings, _image.data(), &_stats));
+    }
+    void post_process()                                                                                    // renderer.cpp:1118-1124
+    {
+        if (_settings.enable_ssao) throw Error(RT_ERR_UNSUPPORTED, "SSAO stays on the host");
+    }
+
+    // Renderer::get_image(): ARGB32, row 0 = bottom row (renderer.cpp:1086); copy_to() fills a QImage-like object.
+    const std::vector<uint32_t>& get_image() const { return _image; }
+    template <class QImageT> void copy_to(QImageT& img) const
+    {
+        for (int y = 0; y < _settings.image_height; y++)
+            for (int x = 0; x < _settings.image_width; x++) img.setPixel(x, y, _image[(size_t)y * _settings.image_width + x]);
+    }
+    const RtRenderStats& last_stats() const { return _stats; }
+    RtContext* context() { return _ctx; }
+
+    // bool BVH::intersect(const Ray&, HitInfo&) const (bvh.h:307), batched.
+    void intersect(const float* o3, const float* d3, size_t n, int32_t* tri_id, float* t, float* u, float* v)
+    {
+        check(rt_intersect(_ctx, o3, d3, n, tri_id, t, u, v));
+    }
+
+private:
+    void check(int rc) { if (rc != RT_OK) throw Error(rc, rt_last_error(_ctx)); }
+    template <class ImageT> void set_map(int slot, const ImageT& im) { check(rt_set_texture_f32(_ctx, slot, im.data(), im.width(), im.height())); }
+    void push_camera()
+    {
+        float proj_inv[16];
+        rt_perspective_inverse(_fov, _aspect, 0.1f, 1000.0f, proj_inv);                                    // Camera(), scene/camera.h:11
+        check(rt_set_camera(_ctx, proj_inv, _camera_to_world, _position));
+    }
+
+    RtContext* _ctx = nullptr;
+    RtSettings _settings;
+    RtRenderStats _stats{};
+    std::vector<uint32_t> _image;
+    float _fov = 45.0f, _aspect = 1.0f;
+    float _camera_to_world[16], _previous_object_transform[16];
+    float _position[3] = {0, 0, 0};
+};
+
+} // namespace rtb200

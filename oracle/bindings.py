@@ -146,6 +146,7 @@ class CpuTracer:
         f("downscale").argtypes = [UP, C.c_int, C.c_int, C.c_int, UP]
         f("omp_max_threads").restype = C.c_int
         if kind != "oracle":
+            f("last_hit_count").restype = C.c_longlong
             f("load_obj").restype = C.c_int
             f("load_obj").argtypes = [C.c_char_p, FP, FP, FP, IP, C.POINTER(RtMaterial), C.c_int, IP]
         else:
@@ -326,6 +327,10 @@ class CpuRenderer:
         ms = self.tr._fn("renderer_trace_rows")(self.h, _ptr(self.cam_to_world, C.c_float), _ptr(out, C.c_uint32),
                                                 row_begin, row_end, row_step, int(reseed), threads)
         return out, ms
+
+    def last_hit_count(self) -> int:
+        """Compiled reference only: primary hits of the last trace_rows() call."""
+        return int(self.tr._fn("last_hit_count")())
 
     def count_rows(self, row_begin=0, row_end=None, row_step=1, threads=0):
         """Oracle only: ray / test counters for the same pixel loop (see oracle.h OrcCounters)."""

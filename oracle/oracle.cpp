@@ -87,15 +87,6 @@ V3 xform_point(const M4& t, V3 p)
     return v3(xt * w, yt * w, zt * w);
 }
 
-// Transform::operator()(const Vector&) -- mat.cpp:103-115
-V3 xform_vector(const M4& t, V3 v)
-{
-    float x = v.x, y = v.y, z = v.z;
-    return v3(t.m[0][0] * x + t.m[0][1] * y + t.m[0][2] * z,
-              t.m[1][0] * x + t.m[1][1] * y + t.m[1][2] * z,
-              t.m[2][0] * x + t.m[2][1] * y + t.m[2][2] * z);
-}
-
 // Perspective() -- mat.cpp:307-319 ; radians() -- mat.cpp:13-16
 M4 perspective(float fov, float aspect, float znear, float zfar)
 {

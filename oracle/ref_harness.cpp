@@ -87,6 +87,8 @@ struct RefRenderer {
     float fov = 45.0f;
 };
 
+long long g_last_hits = 0;
+
 uint32_t pixel_seed(uint32_t pixel_index, uint32_t rng_seed)
 {
     // must equal rt_pixel_seed() of the product (include/rtb200.h)
@@ -342,8 +344,9 @@ double ref_renderer_trace_rows(void* handle, const float cam_to_world[16], uint3
     Point cam_pos = c2w(Point(0, 0, 0));
     if (threads <= 0) threads = omp_get_max_threads();
     if ((int)Renderer::_xorshift_generators.size() < threads) Renderer::_xorshift_generators.resize(threads);
+    long long hits = 0;
     auto t0 = std::chrono::steady_clock::now();
-#pragma omp parallel for schedule(dynamic) num_threads(threads)
+#pragma omp parallel for schedule(dynamic) num_threads(threads) reduction(+ : hits)
     for (int py = row_begin; py < row_end; py += row_step) {
         float y_world = ((float)py + 0.5f) / rh * 2 - 1;
         for (int px = 0; px < rw; px++) {
@@ -357,12 +360,18 @@ double ref_renderer_trace_rows(void* handle, const float cam_to_world[16], uint3
             bool found = false;
             HitInfo hit;
             Color c = h->renderer.trace_ray(ray, hit, 0, found);
+            if (found) hits++;
             if (argb_super) argb_super[(size_t)py * rw + px] = ImageUtils::gkit_color_to_Qt_ARGB32_uint(c);
         }
     }
     auto t1 = std::chrono::steady_clock::now();
+    g_last_hits = hits;
     return std::chrono::duration<double, std::milli>(t1 - t0).count();
 }
+
+// Primary rays of the last ref_renderer_trace_rows call whose trace_ray reported intersection_found
+// (= shadow rays traced when compute_shadows is on and no material reflects).
+long long ref_last_hit_count() { return g_last_hits; }
 
 // ImageUtils::downscale_image_qt_ARGB32 (imageUtils.h:98-147) on a caller image.
 void ref_downscale(const uint32_t* in, int w, int hgt, int factor, uint32_t* out)

@@ -18,6 +18,7 @@ LIB_PATH = PKG / "librtb200.so"
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 RT_SHADING, RT_ABS_NORMALS_SHADING, RT_PASTEL_NORMALS_SHADING, RT_BARYCENTRIC_COORDINATES_SHADING, RT_VISUALIZE_AO = range(5)
 RT_TEX_AO, RT_TEX_DIFFUSE, RT_TEX_NORMAL, RT_TEX_ROUGHNESS, RT_TEX_SKYSPHERE = range(5)
+RT_OPT_COUNT_WORK, RT_OPT_CHUNK_PIXELS = 0, 1
 
 
 class RtError(RuntimeError):
@@ -55,7 +56,10 @@ class RtRenderStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("reflection_rays", C.c_uint64),
                 ("reflection_shadow_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("kernel_launches", C.c_uint32),
                 ("device_ms", C.c_float), ("trace_primary_ms", C.c_float), ("shade_ms", C.c_float),
-                ("reflect_ms", C.c_float), ("shadow_ms", C.c_float), ("resolve_ms", C.c_float)]
+                ("reflect_ms", C.c_float), ("shadow_ms", C.c_float), ("resolve_ms", C.c_float),
+                ("primary_volume_tests", C.c_uint64), ("primary_triangle_tests", C.c_uint64),
+                ("shadow_volume_tests", C.c_uint64), ("shadow_triangle_tests", C.c_uint64),
+                ("reflection_volume_tests", C.c_uint64), ("reflection_triangle_tests", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,6 +67,13 @@ class RtRenderStats(C.Structure):
     @property
     def total_rays(self) -> int:
         return self.primary_rays + self.shadow_rays + self.reflection_rays + self.reflection_shadow_rays
+
+    @property
+    def work_bytes(self) -> int:
+        """56 B per 7-slab volume test + 36 B per triangle test (needs RT_OPT_COUNT_WORK)."""
+        v = self.primary_volume_tests + self.shadow_volume_tests + self.reflection_volume_tests
+        t = self.primary_triangle_tests + self.shadow_triangle_tests + self.reflection_triangle_tests
+        return 56 * v + 36 * t
 
 
 class RtBvhInfo(C.Structure):
@@ -84,6 +95,8 @@ ABI = {
     "rt_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rt_destroy": (None, [C.c_void_p]),
     "rt_last_error": (C.c_char_p, [C.c_void_p]),
+    "rt_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "rt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_set_triangles": (C.c_int, [C.c_void_p, FP, FP, IP, C.c_size_t]),
     "rt_build_bvh": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rt_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(RtBvhInfo)]),
@@ -188,6 +201,12 @@ class Context:
     def _check(self, rc: int):
         if rc != RT_OK:
             raise RtError(rc, (self.lib.rt_last_error(self.h) or b"").decode())
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.rt_set_option(self.h, option, value))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.rt_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
 
     # ---- scene ------------------------------------------------------------------------------------------
     def set_triangles(self, xyz9, uv6=None, mat=None):

@@ -28,7 +28,24 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int stack_overflow;
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
+    // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
+    unsigned long long primary_vol, primary_tri, shadow_vol, shadow_tri, refl_vol, refl_tri;
 };
+
+RT_DEV void flush_work(TraceCounters& tc, unsigned long long* vol, unsigned long long* tri)
+{
+    // warp-aggregated: one atomic pair per warp
+    unsigned long long v = tc.vol_tests, t = tc.tri_tests;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (v) atomicAdd(vol, v);
+        if (t) atomicAdd(tri, t);
+    }
+}
 
 // Which part of the frame a launch covers: owned tiles [tile_begin, tile_end) of the shard's tile list.
 struct WorkView {
@@ -50,12 +67,14 @@ struct QueueView {                   // hit queue (SoA) of one chunk
     uint32_t capacity;
 };
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryThreads)
 k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, int any_reflective)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t pps = (uint32_t)wk.patches_per_side;
     const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps;
+    TraceCounters tc = zero_counters();
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(&cnt->next_patch, 1u);
@@ -77,10 +96,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
             if (live) {
                 V3 o, d;
                 primary_ray(fr, px, py, o, d);
-                TraceCounters tc;
-                tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
-                bool found = trace_closest(sc, o, d, hr, &tc);
-                if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
+                bool found = trace_closest<COUNT>(sc, o, d, hr, &tc);
                 hit = found && hr.t > 0.1f;                               // min_t, renderer.cpp:1039-1040
                 if (!hit) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
                 else if (any_reflective) {
@@ -109,6 +125,8 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
             }
         }
     }
+    if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
 }
 
 RT_DEV void queue_ray(const FrameView& fr, const QueueView& q, uint32_t i, V3& o, V3& d, HitRec& hr, uint32_t& pix)
@@ -118,12 +136,12 @@ RT_DEV void queue_ray(const FrameView& fr, const QueueView& q, uint32_t i, V3& o
     primary_ray(fr, (int)(pix % (uint32_t)fr.rw), (int)(pix / (uint32_t)fr.rw), o, d);
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
 k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
 {
     const uint32_t n = cnt->n_refl;
-    TraceCounters tc;
-    tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
+    TraceCounters tc = zero_counters();
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         const uint32_t i = q.refl_idx[r];
         V3 o, d;
@@ -136,7 +154,7 @@ k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
         shade_direct(sc, fr, o, d, hit, p, m);                             // updates hit.normal (normal mapping)
         XorShift32 rng;
         rng.state = pixel_seed(pix, fr.s.rng_seed);
-        Col c = compute_reflection(sc, fr, d, p, hit, m, 0, rng, &tc);
+        Col c = compute_reflection<COUNT>(sc, fr, d, p, hit, m, 0, rng, &tc);
         q.refl_rgb[3 * (size_t)i + 0] = c.r;
         q.refl_rgb[3 * (size_t)i + 1] = c.g;
         q.refl_rgb[3 * (size_t)i + 2] = c.b;
@@ -150,13 +168,15 @@ k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
         if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
         if (ov) atomicOr(&cnt->stack_overflow, 1u);
     }
+    if (COUNT) flush_work(tc, &cnt->refl_vol, &cnt->refl_tri);
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
 k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* super)
 {
     const uint32_t n = cnt->n_hits;
-    unsigned overflow = 0;
+    TraceCounters tc = zero_counters();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         V3 o, d;
         HitRec hr;
@@ -171,12 +191,7 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
             MatView m;
             Col direct = shade_direct(sc, fr, o, d, hit, p, m);
             bool shadowed = false;
-            if (fr.s.compute_shadows) {
-                TraceCounters tc;
-                tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
-                shadowed = trace_occluded(sc, p, hit.normal, fr.light, &tc);
-                overflow |= tc.stack_overflow;
-            }
+            if (fr.s.compute_shadows) shadowed = trace_occluded<COUNT>(sc, p, hit.normal, fr.light, &tc);
             Col refl = col(0.0f);
             if (m.reflection > 0.0f)
                 refl = col(q.refl_rgb[3 * (size_t)i], q.refl_rgb[3 * (size_t)i + 1], q.refl_rgb[3 * (size_t)i + 2]);
@@ -184,7 +199,8 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
         }
         super[pix] = quantise_argb(c);
     }
-    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
 }
 
 // ImageUtils::downscale_image_qt_ARGB32 -- imageUtils.h:98-147: per channel, sum of the factor^2 quantised samples
@@ -245,9 +261,8 @@ k_intersect(SceneView sc, const float* o3, const float* d3, size_t n, const int3
         V3 o = v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]);
         V3 d = v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]);
         HitRec hr;
-        TraceCounters tc;
-        tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
-        bool found = trace_closest(sc, o, d, hr, &tc);
+        TraceCounters tc = zero_counters();
+        bool found = trace_closest<false>(sc, o, d, hr, &tc);
         if (tc.stack_overflow) atomicOr(overflow, 1u);
         if (tri_id) tri_id[i] = found ? orig[hr.tri] : -1;
         if (t) t[i] = found ? hr.t : -1.0f;
@@ -263,9 +278,8 @@ k_occluded(SceneView sc, V3 light, const float* p3, const float* n3, size_t n, u
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         V3 p = v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]);
         V3 nn = v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]);
-        TraceCounters tc;
-        tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0;
-        occluded[i] = trace_occluded(sc, p, nn, light, &tc) ? 1 : 0;
+        TraceCounters tc = zero_counters();
+        occluded[i] = trace_occluded<false>(sc, p, nn, light, &tc) ? 1 : 0;
         if (tc.stack_overflow) atomicOr(overflow, 1u);
     }
 }

@@ -85,7 +85,17 @@ RT_DEV Hit fresh_hit()
 
 struct TraceCounters {      // per-thread tallies, reduced by the kernels
     uint32_t refl_rays, refl_shadow_rays, stack_overflow;
+    // work actually done by the traversal (only maintained by the COUNT instantiations): 7-slab volume tests and
+    // ray/triangle tests, the V and T of the bytes-per-ray metric (56 V + 36 T)
+    unsigned long long vol_tests, tri_tests;
 };
+
+RT_DEV TraceCounters zero_counters()
+{
+    TraceCounters tc;
+    tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0; tc.vol_tests = 0; tc.tri_tests = 0;
+    return tc;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Per-ray constants of the slab test: denoms/numers of OctreeNode::intersect (bvh.h:216-223) with the division of
@@ -168,6 +178,7 @@ RT_DEV bool tri_test(const rt_f4& p0, const rt_f4& p1, const rt_f4& p2, V3 o, V3
 // whose distance exceeds the best hit dropped at pop time.  Leaf triangles are visited in array order with the
 // reference's strict `<` (bvh.h:241), so ties inside a leaf resolve identically.
 //   best.tri < 0 on entry means "no hit yet" (HitInfo::t == -1).  Returns the reference's bool (a hit with t > 0).
+template <bool COUNT>
 RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCounters* tc)
 {
     SlabRay sr;
@@ -183,6 +194,7 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
     {   // the root cell's own volume, bvh.h:232-233
         const rt_f4* r = sc.recs;
         rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+        if (COUNT) tc->vol_tests++;
         if (slab_entry(q0, q1, q2, q3, sr, best_t) == INFINITY) return false;
         stack_t[0] = -INFINITY;
         stack_r[0] = 0;
@@ -197,6 +209,7 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
         if (meta & RT_LEAF_BIT) {
             const uint32_t cnt = meta & ~RT_LEAF_BIT;
             const rt_f4* tp = sc.tris + 3 * (size_t)link;
+            if (COUNT) tc->tri_tests += cnt;
             for (uint32_t i = 0; i < cnt; i++, tp += 3) {
                 rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
                 float t, u, v;
@@ -209,6 +222,7 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
             const int base = sp;
             const rt_f4* r = sc.recs + 4 * (size_t)link;
             if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return best.tri >= 0 && best.t > 0.0f; }
+            if (COUNT) tc->vol_tests += meta;
             for (uint32_t k = 0; k < meta; k++, r += 4) {
                 rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
                 float tn = slab_entry(c0, c1, c2, c3, sr, best_t);
@@ -233,6 +247,7 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
 // origin that predicate is monotone in t, so "some front-facing hit with t > 0 satisfies it" is the same
 // statement as "the closest one does"; the traversal can stop at the first such hit, needs no ordering, and can
 // drop cells that start beyond the light.
+template <bool COUNT>
 RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCounters* tc)
 {
     const V3 o = p + 1.0e-4f * n;                            // Renderer::EPSILON, renderer.h:23
@@ -248,6 +263,7 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
     {
         const rt_f4* r = sc.recs;
         rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+        if (COUNT) tc->vol_tests++;
         if (slab_entry(q0, q1, q2, q3, sr, t_limit) == INFINITY) return false;
         stack_r[0] = 0;
         sp = 1;
@@ -262,6 +278,7 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
             for (uint32_t i = 0; i < cnt; i++, tp += 3) {
                 rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
                 float t, u, v;
+                if (COUNT) tc->tri_tests++;
                 if (tri_test(p0, p1, p2, o, md, t, u, v) && t > 0.0f) {
                     V3 q = o + t * d;                        // renderer.cpp:351
                     if (length2(p - q) < dist2) return true; // renderer.cpp:354
@@ -270,6 +287,7 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
         } else {
             const rt_f4* r = sc.recs + 4 * (size_t)link;
             if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return false; }
+            if (COUNT) tc->vol_tests += meta;
             for (uint32_t k = 0; k < meta; k++, r += 4) {
                 rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
                 if (slab_entry(c0, c1, c2, c3, sr, t_limit) != INFINITY) stack_r[sp++] = link + k;
@@ -481,6 +499,7 @@ RT_DEV Col shade_miss(const SceneView& sc, const FrameView& fr, V3 rd)
     return col(135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f);                  // renderer.cpp:19
 }
 
+template <bool COUNT>
 RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, Hit& final_hit,
                                        int depth, XorShift32& rng, TraceCounters* tc);
 
@@ -489,6 +508,7 @@ RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr
 // and its reflection_hit_info (declared OUTSIDE the sample loop, :286, so sample k is shaded with the closest hit
 // seen by samples 1..k) are both sequential by construction.  Returns colour already multiplied by
 // material.reflection once (:337); the caller multiplies again (:595).
+template <bool COUNT>
 RT_DEV Col compute_reflection(const SceneView& sc, const FrameView& fr, V3 rd, V3 p, const Hit& hit, const MatView& m,
                              int depth, XorShift32& rng, TraceCounters* tc)
 {
@@ -515,10 +535,10 @@ RT_DEV Col compute_reflection(const SceneView& sc, const FrameView& fr, V3 rd, V
             V3 r = normalize(v3(rx, ry, rz));
             if (dot(r, hit.normal) < 0) r = -r;
             V3 dir = roughness * r + (1 - roughness) * mirror;
-            total = total + trace_ray_secondary(sc, fr, origin, dir, rh, depth + 1, rng, tc);
+            total = total + trace_ray_secondary<COUNT>(sc, fr, origin, dir, rh, depth + 1, rng, tc);
             samples++;
         } else {
-            total = total + trace_ray_secondary(sc, fr, origin, mirror, rh, depth + 1, rng, tc);
+            total = total + trace_ray_secondary<COUNT>(sc, fr, origin, mirror, rh, depth + 1, rng, tc);
             samples = 1;
             break;
         }
@@ -528,13 +548,14 @@ RT_DEV Col compute_reflection(const SceneView& sc, const FrameView& fr, V3 rd, V
 
 // Renderer::trace_ray for depth >= 1 (renderer.cpp:1008-1066) with shade_ray_inter_point inlined; recursion as in
 // the reference, bounded by max_recursion_depth (the C ABI caps it so the device stack can be sized).
+template <bool COUNT>
 RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, Hit& final_hit, int depth,
-                        XorShift32& rng, TraceCounters* tc)
+                                       XorShift32& rng, TraceCounters* tc)
 {
     if (depth > fr.s.max_recursion_depth) return col(0.0f);
     if (tc) tc->refl_rays++;
     HitRec hr;
-    if (trace_closest(sc, ro, rd, hr, tc)) {
+    if (trace_closest<COUNT>(sc, ro, rd, hr, tc)) {
         if (hr.t < final_hit.t || final_hit.t == -1.0f) final_hit = complete_hit(sc, hr);
     }
     if (final_hit.t > 0.1f) {                                                        // min_t, renderer.cpp:1039
@@ -545,10 +566,10 @@ RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr
         bool shadowed = false;
         if (fr.s.compute_shadows) {
             if (tc) tc->refl_shadow_rays++;
-            shadowed = trace_occluded(sc, p, final_hit.normal, fr.light, tc);
+            shadowed = trace_occluded<COUNT>(sc, p, final_hit.normal, fr.light, tc);
         }
         Col refl = col(0.0f);
-        if (m.reflection > 0.0f) refl = compute_reflection(sc, fr, rd, p, final_hit, m, depth, rng, tc);
+        if (m.reflection > 0.0f) refl = compute_reflection<COUNT>(sc, fr, rd, p, final_hit, m, depth, rng, tc);
         return shade_compose(fr, m, direct, shadowed, refl);
     }
     return shade_miss(sc, fr, rd);

@@ -70,7 +70,8 @@ struct TimedLaunch {
 struct RtContext {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream in use
+    cudaStream_t own_stream = nullptr;   // created by rt_create
     std::string error;
 
     // host copy of the caller's triangles (set_object_transform re-transforms and rebuilds, renderer.cpp:214-224)
@@ -103,6 +104,8 @@ struct RtContext {
     size_t events_used = 0;
     std::vector<TimedLaunch> timed;
     size_t stack_limit_set = 0;
+    bool opt_count_work = false;
+    uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
     DevBuf<float> b_a, b_b, b_t, b_u, b_v;
@@ -291,6 +294,7 @@ int rt_create(int device, RtContext** out)
         delete ctx;
         return fail(nullptr, RT_ERR_CUDA, "device init: %s", cudaGetErrorString(e));
     }
+    ctx->own_stream = ctx->stream;
     ctx->sm_count = prop.multiProcessorCount;
     // identity camera looking down -z, like a default-constructed Camera (scene/camera.h:11,29-30)
     for (int i = 0; i < 4; i++)
@@ -311,11 +315,33 @@ void rt_destroy(RtContext* ctx)
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
 const char* rt_last_error(const RtContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rt_set_option(RtContext* ctx, int option, int64_t value)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    switch (option) {
+    case RT_OPT_COUNT_WORK: ctx->opt_count_work = value != 0; return RT_OK;
+    case RT_OPT_CHUNK_PIXELS:
+        if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
+        ctx->opt_chunk_pixels = (uint64_t)value;
+        return RT_OK;
+    default: return fail(ctx, RT_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+int rt_set_stream(RtContext* ctx, void* cuda_stream)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RT_OK;
+}
 
 int rt_set_triangles(RtContext* ctx, const float* xyz9, const float* uv6, const int32_t* mat, size_t n)
 {
@@ -486,7 +512,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     wk.tile_px = tile_size * fr.factor;
     wk.patches_per_side = (wk.tile_px + kPatch - 1) / kPatch;
     const uint64_t px_per_tile = (uint64_t)wk.patches_per_side * wk.patches_per_side * kPatch * kPatch;
-    uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, kChunkPixels / px_per_tile);
+    uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, ctx->opt_chunk_pixels / px_per_tile);
     if ((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk > (size_t)kMaxChunks)
         tiles_per_chunk = (uint32_t)((tiles.size() + kMaxChunks - 1) / kMaxChunks);
     const uint32_t n_chunks = (uint32_t)((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk);
@@ -517,29 +543,34 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
 
-    static int grid_primary = 0, grid_reflect = 0, grid_shade = 0;
-    if (!grid_primary) {
-        grid_primary = grid_for(ctx, (const void*)k_primary, kPrimaryThreads);
-        grid_reflect = grid_for(ctx, (const void*)k_reflect, kQueueThreads);
-        grid_shade = grid_for(ctx, (const void*)k_shade, kQueueThreads);
+    const bool count = ctx->opt_count_work;
+    static int grids[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (!grids[count][0]) {
+        grids[count][0] = grid_for(ctx, count ? (const void*)k_primary<true> : (const void*)k_primary<false>, kPrimaryThreads);
+        grids[count][1] = grid_for(ctx, count ? (const void*)k_reflect<true> : (const void*)k_reflect<false>, kQueueThreads);
+        grids[count][2] = grid_for(ctx, count ? (const void*)k_shade<true> : (const void*)k_shade<false>, kQueueThreads);
     }
+    const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
         ChunkCounters* cnt = ctx->d_counters.p + c;
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
-            k_primary<<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0);
+            if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0);
+            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0);
             launches++;
         }
         if (reflect) {
             ScopedTimer tm(ctx, ST_REFLECT);
-            k_reflect<<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, q, cnt);
+            if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, q, cnt);
+            else k_reflect<false><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, q, cnt);
             launches++;
         }
         {
             ScopedTimer tm(ctx, ST_SHADE);
-            k_shade<<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super);
+            if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super);
+            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super);
             launches++;
         }
     }
@@ -564,6 +595,9 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         rs.primary_hits += host_cnt[c].n_hits;
         rs.reflection_rays += host_cnt[c].refl_rays;
         rs.reflection_shadow_rays += host_cnt[c].refl_shadow_rays;
+        rs.primary_volume_tests += host_cnt[c].primary_vol; rs.primary_triangle_tests += host_cnt[c].primary_tri;
+        rs.shadow_volume_tests += host_cnt[c].shadow_vol; rs.shadow_triangle_tests += host_cnt[c].shadow_tri;
+        rs.reflection_volume_tests += host_cnt[c].refl_vol; rs.reflection_triangle_tests += host_cnt[c].refl_tri;
         overflow |= host_cnt[c].stack_overflow != 0;
     }
     // primary rays = supersampled pixels of the owned tiles that lie inside the frame

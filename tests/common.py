@@ -1,0 +1,118 @@
+"""Helpers shared by the parity tests: scene set-up on either side and image comparison."""
+from __future__ import annotations
+
+import numpy as np
+
+import raytracercpp_b200 as rt
+from raytracercpp_b200 import api, scenes
+from raytracercpp_b200.renderer import precompute_materials
+from oracle import bindings as ob
+
+LIGHT = (3.0, 3.0, 2.0)
+FOV = 80.0
+
+
+def channels(argb):
+    argb = np.asarray(argb)
+    return np.stack([(argb >> 16) & 255, (argb >> 8) & 255, argb & 255], -1).astype(np.int32)
+
+
+def image_error(a, b):
+    """(mean, max) absolute per-channel difference in 8-bit units."""
+    d = np.abs(channels(a) - channels(b))
+    return float(d.mean()), int(d.max())
+
+
+def assert_image_close(a, b, mean_tol=1.0, max_tol=4, what=""):
+    """north_star tolerance: final RGB within 1/255 mean and 4/255 max per channel."""
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    mean, mx = image_error(a, b)
+    assert mean <= mean_tol and mx <= max_tol, f"{what}: mean {mean:.4f} max {mx} (tolerance {mean_tol}/{max_tol})"
+
+
+def config_table(mats):
+    """The reduced-size cfg1/cfg2/cfg3 set-ups of tests/golden/make_golden.py (must stay in sync with it)."""
+    tex2 = {0: scenes.noise_texture((128, 128), 2), 1: scenes.noise_texture((128, 128), 1, "rgb"),
+            2: scenes.normal_map_texture((128, 128), 4), 3: scenes.noise_texture((128, 128), 3)}
+    mats3 = [dict(m) for m in mats]
+    mats3[0].update(reflection=0.9, roughness=0.0, specular=(0.2, 0.2, 0.2), diffuse=(0.5, 0.5, 0.5))
+    mats3[1].update(reflection=0.5, roughness=0.4)
+    mats3 = precompute_materials(mats3)
+    tex3 = {3: tex2[3], 4: scenes.sky_texture((128, 256))}
+    return {
+        "cfg1": (dict(image_width=320, image_height=180, compute_shadows=1), mats, {}),
+        "cfg2": (dict(image_width=160, image_height=90, compute_shadows=1, enable_ssaa=1, ssaa_factor=2, enable_ao_mapping=1,
+                      enable_diffuse_mapping=1, enable_normal_mapping=1), mats, tex2),
+        "cfg3": (dict(image_width=240, image_height=135, compute_shadows=1, rough_reflections_sample_count=16, max_recursion_depth=1,
+                      enable_roughness_mapping=1, enable_skysphere=1, rng_seed=7), mats3, tex3),
+        "cfg3_mirror5": (dict(image_width=160, image_height=90, compute_shadows=1, max_recursion_depth=5, enable_skysphere=1), mats3, tex3),
+    }
+
+
+def oracle_renderer(tracer, scene, kw, mats, tex, fov=FOV, light=LIGHT, cam=None):
+    s = ob.default_settings(**kw)
+    r = tracer.renderer()
+    r.configure(s, fov)
+    r.set_triangles(scene["xyz9"], scene.get("uv6"), scene.get("mat"))
+    r.set_materials(mats)
+    r.set_light(light)
+    if cam is not None:
+        r.set_camera_transform(cam)
+    for slot, img in tex.items():
+        r.set_texture(slot, img)
+    return r
+
+
+def oracle_image(tracer, scene, kw, mats, tex, **k):
+    r = oracle_renderer(tracer, scene, kw, mats, tex, **k)
+    if tracer.kind == "oracle":
+        return r.render()[0]
+    sup, _ = r.trace_rows()            # compiled reference: seeded pixel loop, then its own downscale
+    s = r.settings
+    f = s.ssaa_factor if s.enable_ssaa else 1
+    return tracer.downscale(sup, f) if f > 1 else sup
+
+
+def product_renderer(lib, scene, kw, mats, tex, fov=FOV, light=LIGHT, cam=None, device=0):
+    r = rt.Renderer(device, lib)
+    s = r.render_settings()
+    for k, v in kw.items():
+        setattr(s, k, int(v))
+    r.change_render_size(s.image_width, s.image_height)
+    r.change_camera_fov(fov)
+    if cam is not None:
+        r.set_camera_transform(cam)
+    r.set_triangles(scene["xyz9"], scene.get("uv6"), scene.get("mat"))
+    r.set_materials(mats)
+    r.set_light_position(light)
+    for slot, img in tex.items():
+        r.ctx.set_texture(slot, img)
+    return r
+
+
+def product_image(lib, scene, kw, mats, tex, **k):
+    r = product_renderer(lib, scene, kw, mats, tex, **k)
+    r.ray_trace()
+    r.post_process()
+    img, stats = r.get_image(), r.last_stats()
+    r.close()
+    return img, stats
+
+
+def random_rays(n, seed, box_lo, box_hi):
+    """Half camera-like rays from the origin, half incoherent un-normalised rays from inside the box."""
+    rng = np.random.default_rng(seed)
+    h = n // 2
+    o1 = np.zeros((h, 3), np.float32)
+    d1 = rng.normal(size=(h, 3)).astype(np.float32)
+    d1[:, 2] = -np.abs(d1[:, 2]) * 3
+    d1 /= np.linalg.norm(d1, axis=1, keepdims=True).astype(np.float32)
+    o2 = rng.uniform(box_lo, box_hi, size=(n - h, 3)).astype(np.float32)
+    d2 = rng.normal(size=(n - h, 3)).astype(np.float32)
+    return np.concatenate([o1, o2]), np.concatenate([d1, d2])
+
+
+def triangle_soup(n, seed, size=0.2, center=(0, 0, -4), spread=1.5):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-spread, spread, size=(n, 1, 3)) + np.asarray(center)
+    return (c + rng.normal(scale=size, size=(n, 3, 3))).reshape(n, 9).astype(np.float32)

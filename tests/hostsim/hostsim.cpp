@@ -118,6 +118,10 @@ int rt_create(int, RtContext** out)
 void rt_destroy(RtContext* c) { delete c; }
 const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""; }
 
+int rt_set_option(RtContext* c, int option, int64_t) { return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option"); }
+
+int rt_set_stream(RtContext*, void*) { return RT_OK; }
+
 int rt_set_triangles(RtContext* c, const float* xyz9, const float* uv6, const int32_t* mat, size_t n)
 {
     c->xyz9.assign(xyz9, xyz9 + 9 * n);
@@ -252,8 +256,9 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
                 V3 o, d;
                 primary_ray(fr, px, py, o, d);
                 HitRec hr;
-                TraceCounters tc{0, 0, 0};
-                bool found = trace_closest(sc, o, d, hr, &tc);
+                TraceCounters tc = zero_counters();
+                bool found = trace_closest<true>(sc, o, d, hr, &tc);
+                rs.primary_volume_tests += tc.vol_tests; rs.primary_triangle_tests += tc.tri_tests;
                 if (tc.stack_overflow) return fail(c, RT_ERR_STATE, "traversal stack overflow");
                 bool hit = found && hr.t > 0.1f;
                 if (!hit) { super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d)); continue; }
@@ -267,8 +272,8 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
     rs.primary_hits = queue.size();
     // k_reflect
     std::vector<Col> refl_rgb(queue.size(), col(0.0f));
-    uint64_t refl_rays = 0, refl_shadow = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : refl_rays, refl_shadow)
+    uint64_t refl_rays = 0, refl_shadow = 0, rv = 0, rtt = 0, sv = 0, stt = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : refl_rays, refl_shadow, rv, rtt)
     for (long long r = 0; r < (long long)refl_idx.size(); r++) {
         const QEntry& e = queue[refl_idx[r]];
         V3 o, d;
@@ -279,15 +284,17 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
         shade_direct(sc, fr, o, d, hit, p, m);
         XorShift32 rng;
         rng.state = pixel_seed(e.pix, fr.s.rng_seed);
-        TraceCounters tc{0, 0, 0};
-        refl_rgb[refl_idx[r]] = compute_reflection(sc, fr, d, p, hit, m, 0, rng, &tc);
+        TraceCounters tc = zero_counters();
+        refl_rgb[refl_idx[r]] = compute_reflection<true>(sc, fr, d, p, hit, m, 0, rng, &tc);
         refl_rays += tc.refl_rays;
         refl_shadow += tc.refl_shadow_rays;
+        rv += tc.vol_tests; rtt += tc.tri_tests;
     }
+    rs.reflection_volume_tests = rv; rs.reflection_triangle_tests = rtt;
     rs.reflection_rays = refl_rays;
     rs.reflection_shadow_rays = refl_shadow;
     // k_shade
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : sv, stt)
     for (long long i = 0; i < (long long)queue.size(); i++) {
         const QEntry& e = queue[i];
         V3 o, d;
@@ -300,13 +307,16 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
             MatView m;
             Col direct = shade_direct(sc, fr, o, d, hit, p, m);
             bool shadowed = false;
-            if (fr.s.compute_shadows) shadowed = trace_occluded(sc, p, hit.normal, fr.light, nullptr);
+            TraceCounters tc = zero_counters();
+            if (fr.s.compute_shadows) shadowed = trace_occluded<true>(sc, p, hit.normal, fr.light, &tc);
+            sv += tc.vol_tests; stt += tc.tri_tests;
             Col refl = m.reflection > 0.0f ? refl_rgb[i] : col(0.0f);
             cc = shade_compose(fr, m, direct, shadowed, refl);
         }
         super[e.pix] = quantise_argb(cc);
     }
     rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
+    rs.shadow_volume_tests = sv; rs.shadow_triangle_tests = stt;
     // k_resolve
     if (fr.factor > 1) {
         const int ff = fr.factor * fr.factor;
@@ -373,8 +383,8 @@ int rt_intersect(RtContext* c, const float* o3, const float* d3, size_t n, int32
 #pragma omp parallel for schedule(dynamic, 256)
     for (long long i = 0; i < (long long)n; i++) {
         HitRec hr;
-        TraceCounters tc{0, 0, 0};
-        bool found = trace_closest(sc, v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]), hr, &tc);
+        TraceCounters tc = zero_counters();
+        bool found = trace_closest<false>(sc, v3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), v3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]), hr, &tc);
         if (tc.stack_overflow) overflow = 1;
         if (tri_id) tri_id[i] = found ? c->flat.orig[hr.tri] : -1;
         if (t) t[i] = found ? hr.t : -1.0f;
@@ -390,7 +400,7 @@ int rt_occluded(RtContext* c, const float* p3, const float* n3, size_t n, uint8_
     const SceneView sc = scene_view(c);
 #pragma omp parallel for schedule(dynamic, 256)
     for (long long i = 0; i < (long long)n; i++)
-        occluded[i] = trace_occluded(sc, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]), c->light, nullptr) ? 1 : 0;
+        occluded[i] = trace_occluded<false>(sc, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]), c->light, nullptr) ? 1 : 0;
     return RT_OK;
 }
 

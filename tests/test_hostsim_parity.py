@@ -1,0 +1,216 @@
+"""CPU-side parity of the KERNEL SOURCE: raytracercpp_b200/csrc/rt_device.h + octree_build.cpp compiled for the
+host (tests/hostsim) and driven through the same C ABI and the same Python mirror as the CUDA library, against the
+oracle.  Host libm == the oracle's libm, so everything here is bit-exact; the GPU run of the same assertions
+(test_gpu_parity.py) relaxes only what CUDA's powf/atan2f/asinf can change."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import raytracercpp_b200 as rt
+from raytracercpp_b200 import api
+from tests import common
+
+
+@pytest.mark.parametrize("params", [(12, 40), (10, 8), (3, 2), (0, 5)])
+def test_flattened_tree_and_closest_hit(hostsim_lib, oracle, robot, golden_rays, params):
+    ctx = api.Context(0, hostsim_lib)
+    ctx.set_triangles(robot["xyz9"], robot["uv6"], robot["mat"])
+    info = ctx.build_bvh(*params)
+    ob = oracle.bvh(robot["xyz9"], *params)
+    st = ob.stats()
+    for k in ("nodes", "leaves", "empty_leaves", "interior", "max_depth_reached", "max_leaf_size"):
+        assert info[k] == st[k], k
+    assert info["child_records"] >= st["nodes"] - st["empty_leaves"]
+    o, d = golden_rays["o"], golden_rays["d"]
+    got, want = ctx.intersect(o, d), ob.intersect(o, d)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    tag = f"_{params[0]}_{params[1]}"
+    if "tri" + tag in golden_rays:                       # and straight against the reference's own vectors
+        assert np.array_equal(got[0], golden_rays["tri" + tag]) and np.array_equal(got[1], golden_rays["t" + tag])
+
+
+def test_edge_cases(hostsim_lib, oracle):
+    ctx = api.Context(0, hostsim_lib)
+    o, d = common.random_rays(2000, 1, (-1, -1, -5), (1, 1, -3))
+    # empty scene
+    ctx.set_triangles(np.zeros((0, 9), np.float32))
+    ctx.build_bvh(12, 40)
+    assert (ctx.intersect(o, d)[0] == -1).all()
+    # one triangle, back-face culled from behind
+    one = np.float32([[-1, -1, -4, 1, -1, -4, 0, 1, -4]])
+    ctx.set_triangles(one)
+    ctx.build_bvh(12, 40)
+    tri, t, u, v = ctx.intersect([[0, 0, 0], [0, 0, -8]], [[0, 0, -1], [0, 0, 1]])
+    assert list(tri) == [0, -1] and t[0] == 4.0
+    # many coincident triangles: the cell can never split below the depth limit; ties keep the first (bvh.h:241)
+    same = np.repeat(one, 100, 0)
+    ctx.set_triangles(same)
+    info = ctx.build_bvh(5, 8)
+    ob = oracle.bvh(same, 5, 8)
+    assert info["max_leaf_size"] == ob.stats()["max_leaf_size"] == 100 and info["max_depth_reached"] == 5
+    a, b = ctx.intersect(o, d), ob.intersect(o, d)
+    assert np.array_equal(a[0], b[0]) and set(np.unique(a[0])) <= {-1, 0}
+    # ragged soup incl. degenerate (zero-area) triangles and rays with zero direction components
+    soup = common.triangle_soup(3000, 8)
+    soup[::50, 3:9] = np.tile(soup[::50, 0:3], 2)
+    ctx.set_triangles(soup)
+    ctx.build_bvh(8, 4)
+    ob = oracle.bvh(soup, 8, 4)
+    d2 = d.copy()
+    d2[::3, 0] = 0
+    d2[::5, 1] = 0
+    d2[::7] = [0, 0, -1]
+    for g, w in zip(ctx.intersect(o, d2), ob.intersect(o, d2)):
+        assert np.array_equal(g, w)
+    with pytest.raises(api.RtError):
+        ctx.build_bvh(64, 8)
+
+
+def test_call_order_and_unsupported_switches(hostsim_lib, robot):
+    r = rt.Renderer(0, hostsim_lib)
+    s = r.render_settings()
+    s.image_width, s.image_height = 32, 32
+    with pytest.raises(api.RtError) as e:
+        r.ray_trace()                                     # no triangles / BVH yet
+    assert e.value.code == api.RT_ERR_STATE
+    r.set_triangles(robot["xyz9"], robot["uv6"], robot["mat"])
+    with pytest.raises(api.RtError):
+        r.ray_trace()                                     # RT_SHADING without materials (reference: assert, materials.h:117)
+    r.set_materials(robot["materials"])
+    r.ray_trace()
+    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping", "enable_skybox"):
+        setattr(s, field, 1)
+        with pytest.raises(api.RtError) as e:
+            r.ray_trace()
+        assert e.value.code == api.RT_ERR_UNSUPPORTED
+        setattr(s, field, 0)
+    s.enable_ao_mapping = 1
+    with pytest.raises(api.RtError):
+        r.ray_trace()                                     # mapping enabled, no map
+    s.enable_ao_mapping = 0
+    s.max_recursion_depth = 99
+    with pytest.raises(api.RtError):
+        r.ray_trace()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5"])
+def test_frames_bit_exact(hostsim_lib, oracle, robot, golden_images, name):
+    kw, mats, tex = common.config_table(robot["materials"])[name]
+    img, stats = common.product_image(hostsim_lib, robot, kw, mats, tex)
+    assert np.array_equal(img, common.oracle_image(oracle, robot, kw, mats, tex))
+    assert np.array_equal(img, golden_images[name + "_strict"])
+    f = kw.get("ssaa_factor", 1) if kw.get("enable_ssaa") else 1
+    assert stats.primary_rays == kw["image_width"] * kw["image_height"] * f * f
+    assert stats.shadow_rays == stats.primary_hits > 0
+    r = common.oracle_renderer(oracle, robot, kw, mats, tex)
+    cnt = r.count_rows()
+    for k in ("primary_rays", "shadow_rays", "reflection_rays", "reflection_shadow_rays", "primary_hits"):
+        assert getattr(stats, k) == cnt[k], k
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+def test_debug_shading_modes(hostsim_lib, oracle, robot, mode):
+    kw = dict(image_width=96, image_height=54, shading_method=mode, enable_ao_mapping=1)
+    tex = {0: common.scenes.noise_texture((64, 64), 2)}
+    img, _ = common.product_image(hostsim_lib, robot, kw, robot["materials"], tex)
+    assert np.array_equal(img, common.oracle_image(oracle, robot, kw, robot["materials"], tex))
+
+
+def test_moved_camera_light_and_f32_textures(hostsim_lib, oracle, robot):
+    kw, mats, tex = common.config_table(robot["materials"])["cfg2"]
+    tex = {k: (v.astype(np.float32) * np.float32(1 / 255.0)) for k, v in tex.items()}     # Image storage of the reference
+    c, s = np.cos(0.4), np.sin(0.4)
+    cam = np.float32([[c, 0, s, 1.0], [0, 1, 0, -0.5], [-s, 0, c, 0.5], [0, 0, 0, 1]])
+    a, _ = common.product_image(hostsim_lib, robot, kw, mats, tex, cam=cam, light=(-2, 4, 1), fov=55.0)
+    b = common.oracle_image(oracle, robot, kw, mats, tex, cam=cam, light=(-2, 4, 1), fov=55.0)
+    assert np.array_equal(a, b)
+
+
+def test_occlusion_matches_is_shadowed(hostsim_lib, oracle, robot):
+    """rt_occluded == the shadow flag the oracle's is_shadowed produces for the same points (via two renders:
+    shadows off vs on differ exactly where the point is shadowed and the direct term is non-zero)."""
+    ctx = api.Context(0, hostsim_lib)
+    ctx.set_triangles(robot["xyz9"], robot["uv6"], robot["mat"])
+    ctx.build_bvh(12, 40)
+    ctx.set_light(common.LIGHT)
+    o, d = common.random_rays(30000, 5, (-1, -1, -5), (1, 1, -3))
+    o[:] = 0
+    tri, t, u, v = ctx.intersect(o, d)
+    hit = tri >= 0
+    p = (o + d * t[:, None])[hit]
+    xyz = robot["xyz9"][tri[hit]]
+    n = np.cross(xyz[:, 3:6] - xyz[:, 0:3], xyz[:, 6:9] - xyz[:, 0:3])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    occ = ctx.occluded(p, n)
+    # brute force with the oracle: closest hit of the shadow ray, then the reference's distance predicate
+    so = (p + n.astype(np.float32) * np.float32(1e-4)).astype(np.float32)
+    sd = (np.float32(common.LIGHT) - p)
+    sd = (sd / np.linalg.norm(sd, axis=1, keepdims=True)).astype(np.float32)
+    bt, bt_t, _, _ = oracle.bvh(robot["xyz9"], 12, 40).intersect(so, sd)
+    q = so + sd * bt_t[:, None]
+    want = (bt >= 0) & (((p - q) ** 2).sum(1) < ((p - np.float32(common.LIGHT)) ** 2).sum(1))
+    assert (occ == want).mean() >= 0.9995           # numpy's normalisation differs from the kernel's in the last ulp
+    assert want.sum() > 100
+
+
+def test_primary_rays_and_resolve(hostsim_lib, oracle, golden_images):
+    ctx = api.Context(0, hostsim_lib)
+    s = api.default_settings(hostsim_lib, image_width=64, image_height=36, enable_ssaa=1, ssaa_factor=2)
+    ctx.set_camera(golden_images["proj_inv_80_16x9"], np.eye(4), (0, 0, 0))
+    o, d = ctx.generate_primary_rays(s)
+    assert o.shape == (128 * 72, 3) and np.allclose(np.linalg.norm(d, axis=1), 1, atol=1e-6)
+    assert d[0, 0] < 0 and d[0, 1] < 0 and d[-1, 0] > 0 and d[-1, 1] > 0       # row 0 = bottom row (renderer.cpp:1086)
+    for f in (2, 3, 4):
+        assert np.array_equal(ctx.resolve_ssaa(golden_images["resolve_in"], f), golden_images[f"resolve_out_{f}"])
+    with pytest.raises(api.RtError):
+        ctx.resolve_ssaa(golden_images["resolve_in"], 5)                          # imageUtils.h:100-112
+
+
+@pytest.mark.parametrize("mod", [2, 3, 8])
+def test_tile_shards_tile_the_frame(hostsim_lib, robot, mod):
+    kw, mats, tex = common.config_table(robot["materials"])["cfg2"]
+    r = common.product_renderer(hostsim_lib, robot, kw, mats, tex)
+    r.ray_trace()
+    full = r.get_image().copy()
+    s = r.render_settings()
+    frame = np.zeros_like(full)
+    total = 0
+    for rem in range(mod):
+        shard = np.full_like(full, 0xdeadbeef)
+        st = r.ctx.render_device(s, shard.ctypes.data, 16, mod, rem)
+        total += st.primary_rays
+        n = r.ctx.tile_count(s, 16, mod, rem)
+        staging = np.zeros(n * 16 * 16, np.uint32)
+        r.ctx.pack_tiles(s, shard.ctypes.data, staging.ctypes.data, 16, mod, rem)
+        r.ctx.unpack_tiles(s, frame.ctypes.data, staging.ctypes.data, 16, mod, rem)
+    assert np.array_equal(frame, full)
+    assert total == full.size * 4
+
+
+def test_object_transform_rebuilds(hostsim_lib, oracle, robot):
+    """Renderer::set_object_transform (renderer.cpp:214-224) == re-creating the triangles at the new placement."""
+    kw = dict(image_width=96, image_height=54, compute_shadows=1)
+    r = common.product_renderer(hostsim_lib, robot, kw, robot["materials"], {})
+    m = np.eye(4, dtype=np.float32)
+    m[0, 3], m[2, 3] = 0.5, -1.0
+    r.set_object_transform(m)
+    r.ray_trace()
+    moved = dict(robot)
+    pts = robot["xyz9"].reshape(-1, 3)
+    moved["xyz9"] = (pts + np.float32([0.5, 0, -1.0])).astype(np.float32).reshape(-1, 9)
+    assert np.array_equal(r.get_image(), common.oracle_image(oracle, moved, kw, robot["materials"], {}))
+
+
+def test_cpp_adapter_compiles_against_the_abi(hostsim_lib, tmp_path):
+    """include/rtb200_renderer.hpp (reference method names over the C ABI), linked against the host emulation here;
+    the GPU run links the same example against librtb200.so (test_gpu_parity.py)."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "adapter_example"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(root / "include"), str(root / "tests" / "adapter_example.cpp"), "-o", str(exe),
+                    "-L", str(root / "tests" / "hostsim"), "-lrtb200_hostsim", f"-Wl,-rpath,{root / 'tests' / 'hostsim'}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "adapter ok" in out

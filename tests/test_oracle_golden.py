@@ -1,0 +1,52 @@
+"""The oracle (oracle/oracle.cpp) against the golden vectors cut from the compiled reference (tests/golden/)."""
+import numpy as np
+import pytest
+
+from tests import common
+
+
+@pytest.mark.parametrize("params", [(12, 40), (10, 8)])
+def test_bvh_intersect_matches_reference_vectors(oracle, robot, golden_rays, params):
+    depth, leaf = params
+    tag = f"_{depth}_{leaf}"
+    bvh = oracle.bvh(robot["xyz9"], depth, leaf)
+    st = bvh.stats()
+    assert [st[k] for k in ("nodes", "leaves", "empty_leaves", "interior", "max_depth_reached", "max_leaf_size")] == list(golden_rays["stats" + tag])
+    tri, t, u, v = bvh.intersect(golden_rays["o"], golden_rays["d"])
+    # bit-exact against the reference built without FMA contraction
+    assert np.array_equal(tri, golden_rays["tri" + tag])
+    assert np.array_equal(t, golden_rays["t" + tag]) and np.array_equal(u, golden_rays["u" + tag]) and np.array_equal(v, golden_rays["v" + tag])
+    # and >= 99.9 % identical triangle ids against the reference built with its own flags (-mfma, contraction on)
+    assert (tri == golden_rays["tri_fma" + tag]).mean() >= 0.999
+    assert (tri >= 0).sum() > 1000
+
+
+def test_reference_kats(oracle, golden_images):
+    """tp2/projets/tests.cpp:97-112: four rays that must miss (back face, outside, two grazing) + two hits."""
+    g = golden_images
+    for i in range(len(g["kat_tris"])):
+        hit, t, u, v = oracle.triangle_intersect(g["kat_tris"][i], g["kat_o"][i], g["kat_d"][i])
+        assert hit == bool(g["kat_hit"][i])
+        if hit:
+            assert np.array_equal(np.float32([t, u, v]), g["kat_tuv"][i])
+    assert list(g["kat_hit"][:4]) == [False] * 4
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5"])
+def test_images_match_reference(oracle, robot, golden_images, name):
+    kw, mats, tex = common.config_table(robot["materials"])[name]
+    img = common.oracle_image(oracle, robot, kw, mats, tex)
+    assert np.array_equal(img, golden_images[name + "_strict"])          # bit-exact vs the no-contraction build
+    common.assert_image_close(img, golden_images[name + "_fma"], what=name + " vs reference flags")
+
+
+def test_camera_matrices_and_inverse(oracle, golden_images):
+    p, pi = oracle.camera_matrices(80.0, 16.0 / 9.0)
+    assert np.array_equal(p, golden_images["proj_80_16x9"]) and np.array_equal(pi, golden_images["proj_inv_80_16x9"])
+    assert np.array_equal(oracle.camera_matrices(45.0, 1.0)[1], golden_images["proj_inv_45_1"])
+    assert np.array_equal(oracle.transform_inverse(golden_images["inv_in"]), golden_images["inv_out"])
+
+
+@pytest.mark.parametrize("factor", [2, 3, 4])
+def test_ssaa_resolve(oracle, golden_images, factor):
+    assert np.array_equal(oracle.downscale(golden_images["resolve_in"], factor), golden_images[f"resolve_out_{factor}"])
