@@ -64,6 +64,7 @@ struct QueueView {                   // hit queue (SoA) of one chunk
     float* v;
     uint32_t* refl_idx;              // reflection queue: indices into the hit queue
     float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
+    unsigned long long* refl_cnt;    // 3 words per hit-queue entry, written by k_reflect: rays | shadow rays << 32, V, T
     uint32_t capacity;
 };
 
@@ -140,10 +141,13 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
 k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
 {
+    // Tallies of a fan go to a per-entry record that k_shade sums up: the threads of a warp sit at different
+    // recursion depths here, so no warp-level reduction is attempted in this kernel.
     const uint32_t n = cnt->n_refl;
-    TraceCounters tc = zero_counters();
+    unsigned overflow = 0;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         const uint32_t i = q.refl_idx[r];
+        TraceCounters tc = zero_counters();
         V3 o, d;
         HitRec hr;
         uint32_t pix;
@@ -158,17 +162,12 @@ k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
         q.refl_rgb[3 * (size_t)i + 0] = c.r;
         q.refl_rgb[3 * (size_t)i + 1] = c.g;
         q.refl_rgb[3 * (size_t)i + 2] = c.b;
+        q.refl_cnt[3 * (size_t)i + 0] = (unsigned long long)tc.refl_rays | ((unsigned long long)tc.refl_shadow_rays << 32);
+        q.refl_cnt[3 * (size_t)i + 1] = tc.vol_tests;
+        q.refl_cnt[3 * (size_t)i + 2] = tc.tri_tests;
+        overflow |= tc.stack_overflow;
     }
-    // warp-aggregated tallies
-    unsigned rr = __reduce_add_sync(0xffffffffu, tc.refl_rays);
-    unsigned rs = __reduce_add_sync(0xffffffffu, tc.refl_shadow_rays);
-    unsigned ov = __reduce_or_sync(0xffffffffu, tc.stack_overflow);
-    if ((threadIdx.x & 31u) == 0) {
-        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
-        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
-        if (ov) atomicOr(&cnt->stack_overflow, 1u);
-    }
-    if (COUNT) flush_work(tc, &cnt->refl_vol, &cnt->refl_tri);
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
 }
 
 template <bool COUNT>
@@ -177,6 +176,7 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
 {
     const uint32_t n = cnt->n_hits;
     TraceCounters tc = zero_counters();
+    TraceCounters fan = zero_counters();                      // sums of the per-entry records of k_reflect
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         V3 o, d;
         HitRec hr;
@@ -193,14 +193,25 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
             bool shadowed = false;
             if (fr.s.compute_shadows) shadowed = trace_occluded<COUNT>(sc, p, hit.normal, fr.light, &tc);
             Col refl = col(0.0f);
-            if (m.reflection > 0.0f)
+            if (m.reflection > 0.0f) {
                 refl = col(q.refl_rgb[3 * (size_t)i], q.refl_rgb[3 * (size_t)i + 1], q.refl_rgb[3 * (size_t)i + 2]);
+                const unsigned long long packed = q.refl_cnt[3 * (size_t)i];
+                fan.refl_rays += (uint32_t)packed;
+                fan.refl_shadow_rays += (uint32_t)(packed >> 32);
+                if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)i + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)i + 2]; }
+            }
             c = shade_compose(fr, m, direct, shadowed, refl);
         }
         super[pix] = quantise_argb(c);
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
+    if ((threadIdx.x & 31u) == 0) {
+        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
+        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
+    }
+    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
 }
 
 // ImageUtils::downscale_image_qt_ARGB32 -- imageUtils.h:98-147: per channel, sum of the factor^2 quantised samples

@@ -98,6 +98,7 @@ struct RtContext {
     DevBuf<uint32_t> d_super, d_frame, d_tiles, q_pix, q_refl_idx;
     DevBuf<int32_t> q_tri;
     DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
+    DevBuf<unsigned long long> q_refl_cnt;
     DevBuf<ChunkCounters> d_counters;
     DevBuf<unsigned int> d_flag;
     std::vector<cudaEvent_t> event_pool;
@@ -311,7 +312,7 @@ void rt_destroy(RtContext* ctx)
     ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_pix.release(); ctx->q_refl_idx.release();
-    ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release();
+    ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -522,7 +523,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
     RT_CUDA(ctx, ctx->q_pix.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
     RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
-    if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); }
+    if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, ctx->q_refl_cnt.ensure(3 * qcap)); }
     uint32_t* super = d_argb_out;
     if (resolve) {
         RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
@@ -531,7 +532,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     wk.tiles = ctx->d_tiles.p;
     QueueView q;
     q.pix = ctx->q_pix.p; q.tri = ctx->q_tri.p; q.t = ctx->q_t.p; q.u = ctx->q_u.p; q.v = ctx->q_v.p;
-    q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.capacity = (uint32_t)qcap;
+    q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
 
     cudaStream_t st = ctx->stream;
     ctx->events_used = 0;

@@ -218,6 +218,23 @@ def test_object_transform_and_counters(cuda_lib, oracle, robot):
     r.close()
 
 
+def test_work_counters_equal_the_host_emulation(cuda_lib, hostsim_lib, robot):
+    """The V/T tallies of the instrumented kernels == the same source run serially on the host (cfg1 + a fan config)."""
+    for name in ("cfg1", "cfg3"):
+        kw, mats, tex = common.config_table(robot["materials"])[name]
+        r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+        r.ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
+        r.ray_trace()
+        a = r.last_stats().as_dict()
+        r.close()
+        _, b = common.product_image(hostsim_lib, robot, kw, mats, tex)
+        b = b.as_dict()
+        for k in ("primary_volume_tests", "primary_triangle_tests", "shadow_volume_tests", "shadow_triangle_tests",
+                  "reflection_volume_tests", "reflection_triangle_tests", "reflection_rays", "reflection_shadow_rays"):
+            assert a[k] == b[k], (name, k, a[k], b[k])
+        assert a["primary_volume_tests"] > 0
+
+
 def test_cpp_adapter_example(cuda_lib, tmp_path):
     """include/rtb200_renderer.hpp (the reference's method names over the C ABI) compiles and renders."""
     exe = tmp_path / "adapter_example"
