@@ -183,6 +183,8 @@ def run_ours(args, scene):
     kw = scene["kw"]
     s = api.default_settings(lib, **kw)
     t0 = time.time()
+    if args.leaf_split is not None:
+        ctx.set_option(api.RT_OPT_LEAF_SPLIT, args.leaf_split)
     ctx.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
     info = ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
     if rank == 0:
@@ -285,6 +287,8 @@ def run_ours(args, scene):
             "e2e": {"value": rays_total / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * 64 + 12 + 12 + 100, "d2h_bytes_per_step": int(host.numel() * 4)},
             "gpu_launches": int(launches), "roofline": roofline,
+            "work": {k: getattr(work, k) for k in ("primary_volume_tests", "primary_triangle_tests", "shadow_volume_tests", "shadow_triangle_tests",
+                                                   "primary_hits")},
             "bvh": {k: info[k] for k in ("nodes", "interior", "leaves", "empty_leaves", "max_leaf_size", "child_records", "device_bytes", "build_ms", "upload_ms")},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -309,6 +313,7 @@ def main():
     ap.add_argument("--workload", default="cfg4_sphere10M_4k_16spp", choices=list(WORKLOADS))
     ap.add_argument("--cpu-row-step", type=int, default=48, help="cpu_baseline sample: every n-th supersampled row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--leaf-split", type=int, default=None, help="RT_OPT_LEAF_SPLIT override (experiments); default = library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference" and int(os.environ.get("RANK", 0)) != 0:

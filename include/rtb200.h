@@ -148,7 +148,11 @@ const char* rt_last_error(const RtContext* ctx); /* ctx may be NULL for rt_creat
 /* Library knobs (no reference counterpart). */
 enum {
     RT_OPT_COUNT_WORK = 0,    /* 1: run the instrumented kernels and fill the *_tests counters of RtRenderStats */
-    RT_OPT_CHUNK_PIXELS = 1   /* supersampled pixels per wavefront chunk (bounds ray-queue memory)             */
+    RT_OPT_CHUNK_PIXELS = 1,  /* supersampled pixels per wavefront chunk (bounds ray-queue memory)             */
+    RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 4): when flattening, octree leaves with more than n triangles get a
+                                 device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
+                                 reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.
+                                 Results do not depend on it (tests/test_gpu_parity.py)                               */
 };
 int rt_set_option(RtContext* ctx, int option, int64_t value);
 /* Run all of the context's work on the caller's CUDA stream (a cudaStream_t; NULL = back to the context's own

@@ -1,6 +1,6 @@
 // kernels.cuh -- the wavefront pipeline's __global__ kernels (sm_100a).  One frame is
 //
-//   k_primary   ray generation + closest-hit traversal, one 16x16 patch per warp fetched from an atomic counter;
+//   k_primary   ray generation + closest-hit traversal, one 8x8 patch per warp fetched from an atomic counter;
 //               misses are shaded and written at once, hits are appended to the hit queue with one atomic per
 //               warp (ballot + popc), reflective hits also to the reflection queue
 //   k_reflect   (only if a material reflects) one thread per reflective hit walks its rough-reflection fan
@@ -17,7 +17,7 @@
 
 namespace rtb {
 
-constexpr int kPatch = 16;           // a warp's work item is a kPatch x kPatch block of supersampled pixels
+constexpr int kPatch = 8;            // a warp's work item is a kPatch x kPatch block of supersampled pixels (2 passes of 8x4)
 constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
 

@@ -50,6 +50,7 @@ struct Builder {
     const float* xyz9;
     size_t n;
     int max_depth, leaf_max;
+    int leaf_split = 0;          // > 0: reference leaves with more triangles than this are refined (emit_group)
     std::vector<V3> centroid;
     std::vector<uint32_t> perm, scratch;
     std::vector<uint8_t> oct;
@@ -196,49 +197,131 @@ struct Builder {
         return (uint32_t)recs;
     }
 
-    void emit(int32_t cell, uint32_t rec, const float* uv6, const int32_t* mat)
+    void write_record(uint32_t rec, const float* nr_in, const float* fr_in, uint32_t link, uint32_t meta)
     {
-        const Cell c = cells[cell];
         float nr[PLANES], fr[PLANES];
-        for (int i = 0; i < PLANES; i++) { nr[i] = pad_down(c.nr[i]); fr[i] = pad_up(c.fr[i]); }
-        uint32_t link, meta;
-        if (c.leaf) {
-            link = (uint32_t)(out->tris.size() / 3);
-            meta = RT_META_LEAF | c.count;
-            for (uint32_t i = c.begin; i < c.begin + c.count; i++) {
-                uint32_t t = perm[i];
-                V3 a = vert(t, 0), b = vert(t, 1), cc = vert(t, 2);
-                V3 nrm = cross(b - a, cc - a);                                       // triangle.cpp:9-10
-                out->tris.push_back(F4{a.x, a.y, a.z, nrm.x});
-                out->tris.push_back(F4{b.x, b.y, b.z, nrm.y});
-                out->tris.push_back(F4{cc.x, cc.y, cc.z, nrm.z});
-                float u[6] = {-1, -1, -1, -1, -1, -1};                               // triangle.h:48
-                if (uv6) memcpy(u, uv6 + 6 * (size_t)t, sizeof(u));
-                int32_t m = mat ? mat[t] : -1;
-                out->shade.push_back(F4{u[0], u[1], u[2], u[3]});
-                out->shade.push_back(F4{u[4], u[5], u2f((uint32_t)m), u2f(t)});
-                out->orig.push_back((int32_t)t);
-            }
-        } else {
-            int kids[8], k = 0;
-            for (int o = 0; o < 8; o++)
-                if (c.child[o] >= 0) kids[k++] = c.child[o];
-            link = alloc_block((uint32_t)k);
-            meta = (uint32_t)k;
-            for (int j = 0; j < k; j++) emit(kids[j], link + (uint32_t)j, uv6, mat);
-        }
+        for (int i = 0; i < PLANES; i++) { nr[i] = pad_down(nr_in[i]); fr[i] = pad_up(fr_in[i]); }
         F4* q = &out->recs[(size_t)rec * 4];
         q[0] = F4{nr[0], nr[1], nr[2], nr[3]};
         q[1] = F4{nr[4], nr[5], nr[6], fr[0]};
         q[2] = F4{fr[1], fr[2], fr[3], fr[4]};
         q[3] = F4{fr[5], fr[6], u2f(link), u2f(meta)};
     }
+
+    // Appends triangles `ids` (sorted ascending = the reference's order inside a leaf) as one leaf; returns link.
+    uint32_t append_leaf(const uint32_t* ids, uint32_t count, const float* uv6, const int32_t* mat)
+    {
+        const uint32_t link = (uint32_t)(out->tris.size() / 3);
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t t = ids[i];
+            V3 a = vert(t, 0), b = vert(t, 1), cc = vert(t, 2);
+            V3 nrm = cross(b - a, cc - a);                                           // triangle.cpp:9-10
+            out->tris.push_back(F4{a.x, a.y, a.z, nrm.x});
+            out->tris.push_back(F4{b.x, b.y, b.z, nrm.y});
+            out->tris.push_back(F4{cc.x, cc.y, cc.z, nrm.z});
+            float u[6] = {-1, -1, -1, -1, -1, -1};                                   // triangle.h:48
+            if (uv6) memcpy(u, uv6 + 6 * (size_t)t, sizeof(u));
+            int32_t m = mat ? mat[t] : -1;
+            out->shade.push_back(F4{u[0], u[1], u[2], u[3]});
+            out->shade.push_back(F4{u[4], u[5], u2f((uint32_t)m), u2f(t)});
+            out->orig.push_back((int32_t)t);
+        }
+        return link;
+    }
+
+    void group_volume(const uint32_t* ids, uint32_t count, float* nr, float* fr) const
+    {
+        for (int i = 0; i < PLANES; i++) { nr[i] = INFINITY; fr[i] = -INFINITY; }
+        for (uint32_t i = 0; i < count; i++)
+            for (int k = 0; k < 3; k++) {
+                V3 p = vert(ids[i], k);
+                for (int pl = 0; pl < PLANES; pl++) {
+                    float d = dot(kPlanes.n[pl], p);
+                    nr[pl] = std::min(nr[pl], d);
+                    fr[pl] = std::max(fr[pl], d);
+                }
+            }
+    }
+
+    // B200-side refinement of an oversized reference leaf (not part of the reference tree): the triangles of the
+    // leaf are split into up to 8 groups by three rounds of median cuts of their bbox centroids (each cut along the
+    // axis of largest centroid extent of the group being cut), recursively, until a group holds <= leaf_split
+    // triangles.  Every group gets its own 7-slab volume.  Closest-hit results cannot change: the groups partition the
+    // leaf, volumes bound their triangles, and ties on t are resolved by original index in the kernel
+    // (the reference keeps the first triangle of the leaf in array order, bvh.h:241).
+    void emit_group(uint32_t* ids, uint32_t count, uint32_t rec, const float* nr, const float* fr, const float* uv6, const int32_t* mat)
+    {
+        if (count <= (uint32_t)leaf_split) {
+            std::sort(ids, ids + count);
+            write_record(rec, nr, fr, append_leaf(ids, count, uv6, mat), RT_META_LEAF | count);
+            return;
+        }
+        struct Range { uint32_t b, e; };
+        Range groups[8];
+        int ng = 1;
+        groups[0] = Range{0, count};
+        for (int round = 0; round < 3; round++) {
+            Range next[8];
+            int nn = 0;
+            for (int g = 0; g < ng; g++) {
+                Range r = groups[g];
+                if (r.e - r.b <= (uint32_t)leaf_split) { next[nn++] = r; continue; }
+                V3 lo = v3(INFINITY, INFINITY, INFINITY), hi = v3(-INFINITY, -INFINITY, -INFINITY);
+                for (uint32_t i = r.b; i < r.e; i++) {
+                    V3 c = centroid[ids[i]];
+                    lo = v3(std::min(lo.x, c.x), std::min(lo.y, c.y), std::min(lo.z, c.z));
+                    hi = v3(std::max(hi.x, c.x), std::max(hi.y, c.y), std::max(hi.z, c.z));
+                }
+                V3 ext = hi - lo;
+                int axis = (ext.x >= ext.y && ext.x >= ext.z) ? 0 : (ext.y >= ext.z ? 1 : 2);
+                uint32_t mid = r.b + (r.e - r.b) / 2;
+                std::nth_element(ids + r.b, ids + mid, ids + r.e, [&](uint32_t a, uint32_t b) {
+                    float ca = (&centroid[a].x)[axis], cb = (&centroid[b].x)[axis];
+                    return ca < cb || (ca == cb && a < b);
+                });
+                next[nn++] = Range{r.b, mid};
+                next[nn++] = Range{mid, r.e};
+            }
+            ng = nn;
+            for (int g = 0; g < ng; g++) groups[g] = next[g];
+        }
+        const uint32_t first = alloc_block((uint32_t)ng);
+        write_record(rec, nr, fr, first, (uint32_t)ng);
+        for (int g = 0; g < ng; g++) {
+            float gn[PLANES], gf[PLANES];
+            group_volume(ids + groups[g].b, groups[g].e - groups[g].b, gn, gf);
+            emit_group(ids + groups[g].b, groups[g].e - groups[g].b, first + (uint32_t)g, gn, gf, uv6, mat);
+        }
+    }
+
+    void emit(int32_t cell, uint32_t rec, const float* uv6, const int32_t* mat)
+    {
+        const Cell c = cells[cell];
+        if (c.leaf) {
+            if (leaf_split > 0 && c.count > (uint32_t)leaf_split) {
+                std::vector<uint32_t> ids(perm.begin() + c.begin, perm.begin() + c.begin + c.count);
+                emit_group(ids.data(), c.count, rec, c.nr, c.fr, uv6, mat);
+            } else
+                write_record(rec, c.nr, c.fr, append_leaf(&perm[c.begin], c.count, uv6, mat), RT_META_LEAF | c.count);
+            return;
+        }
+        int kids[8], k = 0;
+        for (int o = 0; o < 8; o++)
+            if (c.child[o] >= 0) kids[k++] = c.child[o];
+        if (k == 1 && leaf_split > 0) {       // a cell with one non-empty child has that child's volume: skip the level
+            emit(kids[0], rec, uv6, mat);
+            return;
+        }
+        const uint32_t first = alloc_block((uint32_t)k);
+        write_record(rec, c.nr, c.fr, first, (uint32_t)k);
+        for (int j = 0; j < k; j++) emit(kids[j], first + (uint32_t)j, uv6, mat);
+    }
 };
 
 } // namespace
 
 void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, size_t n, int max_depth,
-                      int leaf_max, FlatScene& out)
+                      int leaf_max, int leaf_split, FlatScene& out)
 {
     out = FlatScene();
     Builder b;
@@ -246,6 +329,7 @@ void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, s
     b.n = n;
     b.max_depth = max_depth;
     b.leaf_max = leaf_max;
+    b.leaf_split = leaf_split;
     b.out = &out;
     b.centroid.resize(n);
     b.perm.resize(n);

@@ -14,12 +14,14 @@
 #define RT_LDG4(p) __ldg(reinterpret_cast<const float4*>(p))
 #define RT_DEV __device__ __forceinline__
 #define RT_DEV_NOINLINE __device__ __noinline__
+#define RT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
 typedef float4 rt_f4;
 #else
 #include "scene_layout.h"
 #define RT_LDG4(p) (*(p))
 #define RT_DEV inline
 #define RT_DEV_NOINLINE inline
+#define RT_FMA(a, b, c) fmaf((a), (b), (c))
 typedef rtb::F4 rt_f4;
 #endif
 
@@ -47,6 +49,7 @@ struct SceneView {
     const rt_f4* tris;      // 3 per triangle, leaf order
     const rt_f4* shade;     // 2 per triangle, leaf order
     const rt_f4* mats;      // 4 per material (RtMaterial = 16 floats)
+    const int32_t* orig;    // leaf order -> index in the caller's array (tie-break + reported ids)
     int32_t n_mats;
     uint32_t n_tris;
     TexView tex[RT_TEX_COUNT];
@@ -98,55 +101,69 @@ RT_DEV TraceCounters zero_counters()
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Per-ray constants of the slab test: denoms/numers of OctreeNode::intersect (bvh.h:216-223) with the division of
-// BoundingVolume::intersect (bvh.h:92-93) turned into a multiplication by the reciprocal.  A plane with denom == 0
-// is skipped by the reference (bvh.h:86-87); here its numer is NaN so both slab distances are NaN and the
-// NaN-dropping fminf/fmaxf leave the running interval untouched.
+// Per-ray constants of the slab test.  The reference computes, per plane i, denom = N_i.d and numer = N_i.o
+// (bvh.h:216-223) and then (d_near - numer) / denom, (d_far - numer) / denom (bvh.h:92-93).  Here the two quotients
+// are one fused multiply-add each: bound * inv_i - c_i with inv_i = 1/denom_i and c_i = numer_i * inv_i.  That form
+// is NOT bit-identical to the reference's (it does not have to be: slab distances only prune and order, they never
+// reach a result) and it can cancel when |c_i| is large, so the interval is widened by `slack` = 2^-22 * max_i |c_i|
+// on top of the ulp padding of the stored bounds (scene_layout.h): the test can only accept more than the exact one.
+// A plane with denom == 0 is skipped by the reference (bvh.h:86-87); here its c is NaN so both distances are NaN and
+// the NaN-dropping fminf / fmaxf leave the running interval untouched.
 struct SlabRay {
     float inv[7];
-    float num[7];
+    float c[7];
+    float slack;
 };
 
 RT_DEV void slab_setup(V3 o, V3 d, SlabRay& sr)
 {
     const float s = 0.57735026f;                     // sqrt(3.f)/3, bvh.cpp:12-15 (same float)
-    float den[7];
+    float den[7], num[7];
     den[0] = d.x; den[1] = d.y; den[2] = d.z;
-    sr.num[0] = o.x; sr.num[1] = o.y; sr.num[2] = o.z;
-    den[3] = s * d.x + s * d.y + s * d.z;      sr.num[3] = s * o.x + s * o.y + s * o.z;
-    den[4] = -s * d.x + s * d.y + s * d.z;     sr.num[4] = -s * o.x + s * o.y + s * o.z;
-    den[5] = -s * d.x + -s * d.y + s * d.z;    sr.num[5] = -s * o.x + -s * o.y + s * o.z;
-    den[6] = s * d.x + -s * d.y + s * d.z;     sr.num[6] = s * o.x + -s * o.y + s * o.z;
+    num[0] = o.x; num[1] = o.y; num[2] = o.z;
+    den[3] = s * d.x + s * d.y + s * d.z;      num[3] = s * o.x + s * o.y + s * o.z;
+    den[4] = -s * d.x + s * d.y + s * d.z;     num[4] = -s * o.x + s * o.y + s * o.z;
+    den[5] = -s * d.x + -s * d.y + s * d.z;    num[5] = -s * o.x + -s * o.y + s * o.z;
+    den[6] = s * d.x + -s * d.y + s * d.z;     num[6] = s * o.x + -s * o.y + s * o.z;
+    float cmax = 0.0f;
 #pragma unroll
     for (int i = 0; i < 7; i++) {
-        if (den[i] == 0.0f) { sr.inv[i] = 0.0f; sr.num[i] = NAN; }
-        else sr.inv[i] = 1.0f / den[i];
+        if (den[i] == 0.0f) { sr.inv[i] = 0.0f; sr.c[i] = NAN; }
+        else {
+            sr.inv[i] = 1.0f / den[i];
+            sr.c[i] = num[i] * sr.inv[i];
+            cmax = fmaxf(cmax, fabsf(sr.c[i]));
+        }
     }
+    sr.slack = cmax * 2.3841858e-7f;                 // 2^-22
 }
 
 // 7-slab interval of one 64-byte record.  Returns the entry distance, or +inf when the record is missed / lies
 // behind the ray / starts beyond t_limit.  (The reference has no t_far<0 / t_near>best cull, bvh.h:79-105; both
-// are pure pruning: a triangle needs t >= 0 and must beat the best hit strictly, bvh.h:241.)
+// are pure pruning: a triangle needs t >= 0 and must beat the best hit strictly, bvh.h:241.)  The three axis slabs
+// are tested first: most children of a visited cell are already missed there.
 RT_DEV float slab_entry(const rt_f4& q0, const rt_f4& q1, const rt_f4& q2, const rt_f4& q3, const SlabRay& sr, float t_limit)
 {
     float tn = -INFINITY, tf = INFINITY;
 #define RT_SLAB(i, NEAR, FAR)                                   \
     {                                                           \
-        float a = ((NEAR) - sr.num[i]) * sr.inv[i];             \
-        float b = ((FAR) - sr.num[i]) * sr.inv[i];              \
+        float a = RT_FMA((NEAR), sr.inv[i], -sr.c[i]);          \
+        float b = RT_FMA((FAR), sr.inv[i], -sr.c[i]);           \
         tn = fmaxf(tn, fminf(a, b));                            \
         tf = fminf(tf, fmaxf(a, b));                            \
     }
     RT_SLAB(0, q0.x, q1.w)
     RT_SLAB(1, q0.y, q2.x)
     RT_SLAB(2, q0.z, q2.y)
+    const float lim = fminf(t_limit, tf) + 2.0f * sr.slack;
+    if (!(tn <= lim) || tf + sr.slack < 0.0f) return INFINITY;
     RT_SLAB(3, q0.w, q2.z)
     RT_SLAB(4, q1.x, q2.w)
     RT_SLAB(5, q1.y, q3.x)
     RT_SLAB(6, q1.z, q3.y)
 #undef RT_SLAB
-    bool ok = (tn <= tf) && (tf >= 0.0f) && (tn <= t_limit);
-    return ok ? tn : INFINITY;
+    bool ok = (tn <= tf + 2.0f * sr.slack) && (tf + sr.slack >= 0.0f) && (tn - sr.slack <= t_limit);
+    return ok ? tn - sr.slack : INFINITY;
 }
 
 // Triangle::intersect with MOLLER_TRUMBORE 1 / BACKFACE_CULLING 1 -- triangle.cpp:25-91.  p0..p2 are the three
@@ -173,11 +190,13 @@ RT_DEV bool tri_test(const rt_f4& p0, const rt_f4& p1, const rt_f4& p2, V3 o, V3
 
 // Closest hit: BVH::intersect (bvh.cpp:68-71 -> bvh.h:212-287).  The reference descends children in order of slab
 // entry distance through a heap-allocated priority queue and stops when the best hit beats the next entry; the
-// result is the exact closest front-facing hit, first-found on ties.  Here: an explicit per-thread stack of
-// (entry distance, record) pairs, children of a cell pushed far-to-near so the nearest is popped first, entries
-// whose distance exceeds the best hit dropped at pop time.  Leaf triangles are visited in array order with the
-// reference's strict `<` (bvh.h:241), so ties inside a leaf resolve identically.
-//   best.tri < 0 on entry means "no hit yet" (HitInfo::t == -1).  Returns the reference's bool (a hit with t > 0).
+// result is the exact closest front-facing hit, first-found on ties.  Here: "while-while" traversal -- an inner loop
+// walks interior cells (nearest hit child stays in registers, the others go far-to-near onto an explicit per-thread
+// stack of (entry distance, record) pairs), an outer step tests the triangles of the leaf that loop ended on, so the
+// lanes of a warp run the two phases together instead of interleaving them.  Entries whose distance exceeds the best
+// hit are dropped at pop time.  Leaf triangles are visited in array order with the reference's strict `<`
+// (bvh.h:241); a tie on t goes to the lower original index, which is the same rule inside a leaf.
+//   Returns the reference's bool (a hit with t > 0); best.tri is a LEAF-ORDER index or -1.
 template <bool COUNT>
 RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCounters* tc)
 {
@@ -190,43 +209,36 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
     float stack_t[RT_STACK_SIZE];
     uint32_t stack_r[RT_STACK_SIZE];
     int sp = 0;
-
+    uint32_t link, meta;
+    bool have;
     {   // the root cell's own volume, bvh.h:232-233
         const rt_f4* r = sc.recs;
         rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
         if (COUNT) tc->vol_tests++;
         if (slab_entry(q0, q1, q2, q3, sr, best_t) == INFINITY) return false;
-        stack_t[0] = -INFINITY;
-        stack_r[0] = 0;
-        sp = 1;
+        link = f4_bits(q3.z); meta = f4_bits(q3.w);
+        have = true;
     }
-
-    while (sp > 0) {
-        --sp;
-        if (stack_t[sp] > best_t) continue;              // a closer hit was found since this cell was pushed
-        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
-        const uint32_t link = f4_bits(q3.z), meta = f4_bits(q3.w);
-        if (meta & RT_LEAF_BIT) {
-            const uint32_t cnt = meta & ~RT_LEAF_BIT;
-            const rt_f4* tp = sc.tris + 3 * (size_t)link;
-            if (COUNT) tc->tri_tests += cnt;
-            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
-                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-                float t, u, v;
-                if (tri_test(p0, p1, p2, o, md, t, u, v) && t < best_t) {
-                    best_t = t;
-                    best.tri = (int32_t)(link + i); best.t = t; best.u = u; best.v = v;
-                }
-            }
-        } else {
-            const int base = sp;
+    for (;;) {
+        // ---- phase 1: interior cells
+        while (have && !(meta & RT_LEAF_BIT)) {
             const rt_f4* r = sc.recs + 4 * (size_t)link;
             if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return best.tri >= 0 && best.t > 0.0f; }
             if (COUNT) tc->vol_tests += meta;
+            const int base = sp;
+            float near_t = INFINITY;
+            uint32_t near_rec = 0, near_link = 0, near_meta = 0;
             for (uint32_t k = 0; k < meta; k++, r += 4) {
                 rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
                 float tn = slab_entry(c0, c1, c2, c3, sr, best_t);
                 if (tn == INFINITY) continue;
+                uint32_t rec = link + k;
+                if (tn < near_t) {                          // new nearest child: the previous one goes to the stack
+                    float pt = near_t; uint32_t pr = near_rec;
+                    near_t = tn; near_rec = rec; near_link = f4_bits(c3.z); near_meta = f4_bits(c3.w);
+                    tn = pt; rec = pr;
+                    if (tn == INFINITY) continue;
+                }
                 int j = sp;                                 // keep [base, sp) sorted by descending entry distance
                 while (j > base && stack_t[j - 1] < tn) {
                     stack_t[j] = stack_t[j - 1];
@@ -234,10 +246,48 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
                     --j;
                 }
                 stack_t[j] = tn;
-                stack_r[j] = link + k;
+                stack_r[j] = rec;
                 ++sp;
             }
+            if (near_t != INFINITY) { link = near_link; meta = near_meta; }
+            else {
+                have = false;
+                while (sp > 0) {
+                    --sp;
+                    if (stack_t[sp] > best_t) continue;     // a closer hit was found since this cell was pushed
+                    const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
+                    link = f4_bits(q3.z); meta = f4_bits(q3.w);
+                    have = true;
+                    break;
+                }
+            }
         }
+        if (!have) break;
+        // ---- phase 2: the triangles of one leaf
+        {
+            const uint32_t cnt = meta & ~RT_LEAF_BIT;
+            const rt_f4* tp = sc.tris + 3 * (size_t)link;
+            if (COUNT) tc->tri_tests += cnt;
+            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
+                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+                float t, u, v;
+                if (tri_test(p0, p1, p2, o, md, t, u, v) &&
+                    (t < best_t || (t == best_t && sc.orig[link + i] < sc.orig[best.tri]))) {
+                    best_t = t;
+                    best.tri = (int32_t)(link + i); best.t = t; best.u = u; best.v = v;
+                }
+            }
+        }
+        have = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_t[sp] > best_t) continue;
+            const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
+            link = f4_bits(q3.z); meta = f4_bits(q3.w);
+            have = true;
+            break;
+        }
+        if (!have) break;
     }
     return best.tri >= 0 && best.t > 0.0f;                  // leaf returns t_near > 0, bvh.h:245-247
 }
@@ -246,7 +296,7 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
 // p + n*EPSILON towards the light and then compares |p - hitpoint|^2 with |p - light|^2.  Beyond 2e-4 from the
 // origin that predicate is monotone in t, so "some front-facing hit with t > 0 satisfies it" is the same
 // statement as "the closest one does"; the traversal can stop at the first such hit, needs no ordering, and can
-// drop cells that start beyond the light.
+// drop cells that start beyond the light.  Same while-while shape as trace_closest.
 template <bool COUNT>
 RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCounters* tc)
 {
@@ -260,19 +310,38 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
 
     uint32_t stack_r[RT_STACK_SIZE];
     int sp = 0;
+    uint32_t link, meta;
+    bool have;
     {
         const rt_f4* r = sc.recs;
         rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
         if (COUNT) tc->vol_tests++;
         if (slab_entry(q0, q1, q2, q3, sr, t_limit) == INFINITY) return false;
-        stack_r[0] = 0;
-        sp = 1;
+        link = f4_bits(q3.z); meta = f4_bits(q3.w);
+        have = true;
     }
-    while (sp > 0) {
-        --sp;
-        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
-        const uint32_t link = f4_bits(q3.z), meta = f4_bits(q3.w);
-        if (meta & RT_LEAF_BIT) {
+    for (;;) {
+        while (have && !(meta & RT_LEAF_BIT)) {
+            const rt_f4* r = sc.recs + 4 * (size_t)link;
+            if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return false; }
+            if (COUNT) tc->vol_tests += meta;
+            bool got = false;
+            uint32_t nl = 0, nm = 0;
+            for (uint32_t k = 0; k < meta; k++, r += 4) {
+                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+                if (slab_entry(c0, c1, c2, c3, sr, t_limit) == INFINITY) continue;
+                if (got) stack_r[sp++] = link + k;          // first hit child stays in registers
+                else { got = true; nl = f4_bits(c3.z); nm = f4_bits(c3.w); }
+            }
+            if (got) { link = nl; meta = nm; }
+            else if (sp > 0) {
+                const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[--sp] + 3);
+                link = f4_bits(q3.z); meta = f4_bits(q3.w);
+            } else
+                have = false;
+        }
+        if (!have) break;
+        {
             const uint32_t cnt = meta & ~RT_LEAF_BIT;
             const rt_f4* tp = sc.tris + 3 * (size_t)link;
             for (uint32_t i = 0; i < cnt; i++, tp += 3) {
@@ -284,15 +353,12 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
                     if (length2(p - q) < dist2) return true; // renderer.cpp:354
                 }
             }
-        } else {
-            const rt_f4* r = sc.recs + 4 * (size_t)link;
-            if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return false; }
-            if (COUNT) tc->vol_tests += meta;
-            for (uint32_t k = 0; k < meta; k++, r += 4) {
-                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-                if (slab_entry(c0, c1, c2, c3, sr, t_limit) != INFINITY) stack_r[sp++] = link + k;
-            }
         }
+        if (sp > 0) {
+            const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[--sp] + 3);
+            link = f4_bits(q3.z); meta = f4_bits(q3.w);
+        } else
+            break;
     }
     return false;
 }

@@ -106,6 +106,7 @@ struct RtContext {
     std::vector<TimedLaunch> timed;
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
+    int opt_leaf_split = 4;
     uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
@@ -175,6 +176,7 @@ SceneView scene_view(const RtContext* ctx)
     sc.tris = ctx->d_tris.p;
     sc.shade = ctx->d_shade.p;
     sc.mats = ctx->d_mats.p;
+    sc.orig = ctx->d_orig.p;
     sc.n_mats = ctx->n_mats;
     sc.n_tris = ctx->n_tris;
     for (int i = 0; i < RT_TEX_COUNT; i++) {
@@ -327,6 +329,11 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
     if (!ctx) return RT_ERR_INVALID;
     switch (option) {
     case RT_OPT_COUNT_WORK: ctx->opt_count_work = value != 0; return RT_OK;
+    case RT_OPT_LEAF_SPLIT:
+        if (value < 0 || value > 1024) return fail(ctx, RT_ERR_INVALID, "leaf split %lld", (long long)value);
+        ctx->opt_leaf_split = (int)value;
+        ctx->bvh_valid = false;                          // takes effect at the next rt_build_bvh
+        return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -370,7 +377,7 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     double t0 = now_ms();
     FlatScene flat;
     build_flat_scene(ctx->xyz9.data(), ctx->has_uv ? ctx->uv6.data() : nullptr, ctx->has_mat ? ctx->mat.data() : nullptr, n,
-                     max_depth, leaf_max_obj_count, flat);
+                     max_depth, leaf_max_obj_count, ctx->opt_leaf_split, flat);
     double t1 = now_ms();
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RT_CUDA(ctx, ctx->d_recs.ensure(flat.recs.size()));

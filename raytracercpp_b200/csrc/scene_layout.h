@@ -48,8 +48,12 @@ struct FlatScene {
 
 // Builds the reference's octree (same cells, same leaf contents in the same order as sequential insertion,
 // bvh.cpp:19-66 / bvh.h:141-210) top-down and flattens it.  uv6 / mat may be null (defaults of triangle.h:48).
+// leaf_split > 0 additionally refines, on the B200 side only, every reference leaf that holds more than leaf_split
+// triangles into a small median-split hierarchy of groups of <= leaf_split triangles (octree_build.cpp:emit_group) and
+// skips levels with a single non-empty child; leaf_split = 0 keeps exactly the reference's cells and leaves.  The
+// statistics below always describe the reference-shaped octree.
 void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, size_t n, int max_depth,
-                      int leaf_max, FlatScene& out);
+                      int leaf_max, int leaf_split, FlatScene& out);
 
 inline uint32_t f2u(float f) { uint32_t u; __builtin_memcpy(&u, &f, 4); return u; }
 inline float u2f(uint32_t u) { float f; __builtin_memcpy(&f, &u, 4); return f; }

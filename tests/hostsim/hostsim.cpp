@@ -38,6 +38,7 @@ struct RtContext {
     HostTexture tex[RT_TEX_COUNT];
     M4 proj_inv{}, cam_to_world{};
     V3 cam_pos{0, 0, 0}, light{3, 3, 2};
+    int leaf_split = 4;
 };
 
 static int fail(RtContext* c, int code, const std::string& msg)
@@ -54,6 +55,7 @@ static SceneView scene_view(const RtContext* c)
     sc.tris = c->flat.tris.data();
     sc.shade = c->flat.shade.data();
     sc.mats = c->mats.data();
+    sc.orig = c->flat.orig.data();
     sc.n_mats = c->n_mats;
     sc.n_tris = (uint32_t)(c->xyz9.size() / 9);
     for (int i = 0; i < RT_TEX_COUNT; i++) {
@@ -118,7 +120,11 @@ int rt_create(int, RtContext** out)
 void rt_destroy(RtContext* c) { delete c; }
 const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""; }
 
-int rt_set_option(RtContext* c, int option, int64_t) { return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option"); }
+int rt_set_option(RtContext* c, int option, int64_t value)
+{
+    if (option == RT_OPT_LEAF_SPLIT) { c->leaf_split = (int)value; c->bvh_valid = false; return RT_OK; }
+    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
+}
 
 int rt_set_stream(RtContext*, void*) { return RT_OK; }
 
@@ -140,7 +146,7 @@ int rt_build_bvh(RtContext* c, int max_depth, int leaf_max)
     if (max_depth < 0 || max_depth > RT_MAX_TREE_DEPTH) return fail(c, RT_ERR_INVALID, "max_depth");
     if (leaf_max < 0) return fail(c, RT_ERR_INVALID, "leaf_max");
     size_t n = c->xyz9.size() / 9;
-    build_flat_scene(c->xyz9.data(), c->has_uv ? c->uv6.data() : nullptr, c->has_mat ? c->mat.data() : nullptr, n, max_depth, leaf_max, c->flat);
+    build_flat_scene(c->xyz9.data(), c->has_uv ? c->uv6.data() : nullptr, c->has_mat ? c->mat.data() : nullptr, n, max_depth, leaf_max, c->leaf_split, c->flat);
     RtBvhInfo& bi = c->info;
     memset(&bi, 0, sizeof(bi));
     bi.triangles = n;

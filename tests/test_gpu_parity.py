@@ -305,3 +305,29 @@ def test_full_size_properties(cuda_lib, oracle, big_sphere):
     common.assert_image_close(big[rows], sup[rows], what="10M-triangle band vs oracle")
     assert (big[rows] == sup[rows]).mean() >= 0.999
     r.close()
+
+
+@pytest.mark.parametrize("split", [0, 1, 3, 16])
+def test_leaf_refinement_never_changes_a_result(cuda_lib, oracle, robot, golden_rays, split):
+    """RT_OPT_LEAF_SPLIT only reshapes the device-side hierarchy below the reference's leaves: ids, t, u, v and frames
+    stay bit-identical, including with the reference's own leaves (split = 0)."""
+    ctx = api.Context(0, cuda_lib)
+    ctx.set_option(api.RT_OPT_LEAF_SPLIT, split)
+    ctx.set_triangles(robot["xyz9"], robot["uv6"], robot["mat"])
+    info = ctx.build_bvh(12, 40)
+    assert info["nodes"] == 585 and info["max_leaf_size"] == 40          # statistics always describe the reference tree
+    got = ctx.intersect(golden_rays["o"], golden_rays["d"])
+    assert np.array_equal(got[0], golden_rays["tri_12_40"]) and np.array_equal(got[1], golden_rays["t_12_40"])
+    same = np.repeat(np.float32([[-1, -1, -4, 1, -1, -4, 0, 1, -4]]), 100, 0)
+    ctx.set_triangles(same)
+    ctx.build_bvh(5, 8)
+    o, d = common.random_rays(2000, 1, (-1, -1, -5), (1, 1, -3))
+    assert set(np.unique(ctx.intersect(o, d)[0])) <= {-1, 0}            # a tie goes to the lowest index, bvh.h:241
+    ctx.close()
+    kw, mats, tex = common.config_table(robot["materials"])["cfg3"]
+    r = common.product_renderer(cuda_lib, robot, dict(kw, image_width=96, image_height=54), mats, tex)
+    r.ctx.set_option(api.RT_OPT_LEAF_SPLIT, split)
+    r.reconstruct_bvh_new()
+    r.ray_trace()
+    common.assert_image_close(r.get_image(), common.oracle_image(oracle, robot, dict(kw, image_width=96, image_height=54), mats, tex), what="split")
+    r.close()
