@@ -185,6 +185,9 @@ def run_ours(args, scene):
     t0 = time.time()
     if args.leaf_split is not None:
         ctx.set_option(api.RT_OPT_LEAF_SPLIT, args.leaf_split)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(int(k), int(v))
     ctx.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
     info = ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
     if rank == 0:
@@ -313,6 +316,7 @@ def main():
     ap.add_argument("--workload", default="cfg4_sphere10M_4k_16spp", choices=list(WORKLOADS))
     ap.add_argument("--cpu-row-step", type=int, default=48, help="cpu_baseline sample: every n-th supersampled row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option override id=value (experiments), e.g. --opt 3=4")
     ap.add_argument("--leaf-split", type=int, default=None, help="RT_OPT_LEAF_SPLIT override (experiments); default = library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

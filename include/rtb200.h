@@ -149,7 +149,9 @@ const char* rt_last_error(const RtContext* ctx); /* ctx may be NULL for rt_creat
 enum {
     RT_OPT_COUNT_WORK = 0,    /* 1: run the instrumented kernels and fill the *_tests counters of RtRenderStats */
     RT_OPT_CHUNK_PIXELS = 1,  /* supersampled pixels per wavefront chunk (bounds ray-queue memory)             */
-    RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 4): when flattening, octree leaves with more than n triangles get a
+    RT_OPT_REFILL_PRIMARY = 3,/* a warp of k_primary / k_shade fetches new rays once this many of its 32 lanes are idle  */
+    RT_OPT_REFILL_SHADE = 4,  /* (defaults 8 and 12)                                                                   */
+    RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.
                                  Results do not depend on it (tests/test_gpu_parity.py)                               */

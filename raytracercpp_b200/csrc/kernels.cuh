@@ -1,8 +1,8 @@
 // kernels.cuh -- the wavefront pipeline's __global__ kernels (sm_100a).  One frame is
 //
-//   k_primary   ray generation + closest-hit traversal, one 8x8 patch per warp fetched from an atomic counter;
-//               misses are shaded and written at once, hits are appended to the hit queue with one atomic per
-//               warp (ballot + popc), reflective hits also to the reflection queue
+//   k_primary   ray generation + closest-hit traversal by persistent warps whose idle lanes are refilled from an
+//               atomic ray counter; misses are shaded and written at once, hits are appended to the hit queue with
+//               one atomic per warp (ballot + popc), reflective hits also to the reflection queue
 //   k_reflect   (only if a material reflects) one thread per reflective hit walks its rough-reflection fan
 //   k_shade     one thread per queued hit: textures / Blinn-Phong, any-hit shadow ray, compose, quantise, store
 //   k_resolve   integer SSAA box filter of the quantised samples (imageUtils.h:98-147)
@@ -22,10 +22,12 @@ constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
 
 struct ChunkCounters {               // one per chunk, zeroed before the frame
-    unsigned int next_patch;
+    unsigned int next_patch;         // next ray slot of k_primary
+    unsigned int next_shade;         // next hit-queue entry of k_shade
     unsigned int n_hits;
     unsigned int n_refl;
     unsigned int stack_overflow;
+    unsigned int pad0, pad1, pad2;
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
@@ -68,61 +70,97 @@ struct QueueView {                   // hit queue (SoA) of one chunk
     uint32_t capacity;
 };
 
+// Refill thresholds of the persistent kernels: a warp fetches new rays when at least this many of its lanes are idle
+// (and always when all are).  Low = lanes never idle long but the per-ray set-up code runs with few lanes; high = the
+// opposite.  Set through rt_set_option for experiments.
+struct Tuning {
+    int32_t primary_refill;
+    int32_t shade_refill;
+};
+
+// Ray generation + closest hit.  Persistent warps; every lane owns one ray at a time and steps it through the
+// traversal state machine (rt_device.h); lanes whose ray has ended are refilled from an atomic ray counter with the
+// next rays in patch order (tile -> 8x8 patch -> 8x4 half -> pixel), so a warp starts on 32 adjacent pixels and stays
+// on nearby ones.  Misses are shaded and stored at once; hits are appended to the hit queue by warp-ballot
+// compaction (one atomic per warp and iteration), reflective hits also to the reflection queue.
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryThreads)
-k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, int any_reflective)
+k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, int any_reflective, Tuning tune)
 {
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t pps = (uint32_t)wk.patches_per_side;
-    const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps;
+    const uint32_t per_tile = pps * pps * (uint32_t)(kPatch * kPatch);
+    const uint32_t total = (wk.tile_end - wk.tile_begin) * per_tile;      // ray slots of the chunk (edge slots may be empty)
     TraceCounters tc = zero_counters();
+    ClosestState S;
+    ClosestStack K;
+    S.have = false;
+    bool alive = false, exhausted = false;
+    int px = 0, py = 0;
+    V3 dir = v3(0, 0, 0);
     for (;;) {
-        uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(&cnt->next_patch, 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= total) break;
-        const uint32_t tile = wk.tiles[wk.tile_begin + w / (pps * pps)];
-        const uint32_t pin = w % (pps * pps);
-        const int tx = (int)(tile % (uint32_t)wk.tiles_x), ty = (int)(tile / (uint32_t)wk.tiles_x);
-        const int lx0 = (int)(pin % pps) * kPatch, ly0 = (int)(pin / pps) * kPatch;
-#pragma unroll 1
-        for (int sub = 0; sub < (kPatch / 8) * (kPatch / 4); sub++) {     // 8 x 4 pixels per pass
-            const int lx = lx0 + (sub % (kPatch / 8)) * 8 + (int)(lane & 7u);
-            const int ly = ly0 + (sub / (kPatch / 8)) * 4 + (int)(lane >> 3);
-            const int px = tx * wk.tile_px + lx, py = ty * wk.tile_px + ly;
-            const bool live = lx < wk.tile_px && ly < wk.tile_px && px < fr.rw && py < fr.rh;
-            bool hit = false, reflective = false;
-            HitRec hr;
-            hr.tri = -1; hr.t = -1.0f; hr.u = 1.0f; hr.v = 0.0f;
-            if (live) {
-                V3 o, d;
-                primary_ray(fr, px, py, o, d);
-                bool found = trace_closest<COUNT>(sc, o, d, hr, &tc);
-                hit = found && hr.t > 0.1f;                               // min_t, renderer.cpp:1039-1040
-                if (!hit) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
-                else if (any_reflective) {
-                    TriShade ts = load_tri_shade(sc, hr.tri);
-                    reflective = load_material(sc, ts.mat).reflection > 0.0f;
+        // ---- refill the idle lanes
+        const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        const int n_idle = __popc(idle);
+        if (!exhausted && (n_idle >= tune.primary_refill || n_idle == 32)) {
+            uint32_t base = 0;
+            const int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(&cnt->next_patch, (unsigned)n_idle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (uint32_t)n_idle >= total) exhausted = true;
+            const uint32_t r = base + (uint32_t)__popc(idle & lt_mask);
+            if (!alive && r < total) {
+                const uint32_t tile = wk.tiles[wk.tile_begin + r / per_tile];
+                const uint32_t in_tile = r % per_tile;
+                const uint32_t patch = in_tile / (uint32_t)(kPatch * kPatch), in_patch = in_tile % (uint32_t)(kPatch * kPatch);
+                const int lx = (int)(patch % pps) * kPatch + (int)(in_patch & 7u);
+                const int ly = (int)(patch / pps) * kPatch + (int)(in_patch >> 3);
+                px = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px + lx;
+                py = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px + ly;
+                if (lx < wk.tile_px && ly < wk.tile_px && px < fr.rw && py < fr.rh) {
+                    V3 o;
+                    primary_ray(fr, px, py, o, dir);
+                    closest_begin<COUNT>(sc, o, dir, S, &tc);
+                    alive = true;
                 }
             }
-            // warp-ballot compaction of the live hits: one atomic per warp and queue
-            const unsigned hmask = __ballot_sync(0xffffffffu, hit);
-            if (hmask) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&cnt->n_hits, (unsigned)__popc(hmask));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const uint32_t slot = base + (uint32_t)__popc(hmask & ((1u << lane) - 1u));
-                if (hit) {
-                    q.pix[slot] = (uint32_t)py * (uint32_t)fr.rw + (uint32_t)px;
-                    q.tri[slot] = hr.tri; q.t[slot] = hr.t; q.u[slot] = hr.u; q.v[slot] = hr.v;
-                }
-                const unsigned rmask = __ballot_sync(0xffffffffu, reflective);
-                if (rmask) {
-                    uint32_t rbase = 0;
-                    if (lane == 0) rbase = atomicAdd(&cnt->n_refl, (unsigned)__popc(rmask));
-                    rbase = __shfl_sync(0xffffffffu, rbase, 0);
-                    if (reflective) q.refl_idx[rbase + (uint32_t)__popc(rmask & ((1u << lane) - 1u))] = slot;
-                }
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- one interior step, then one leaf step, for the lanes that are there
+        if (alive && S.have && !(S.meta & RT_LEAF_BIT)) closest_interior_step<COUNT>(sc, S, K, &tc);
+        if (alive && S.have && (S.meta & RT_LEAF_BIT)) closest_leaf_step<COUNT>(sc, S, K, &tc);
+        // ---- rays that ended this iteration
+        const bool done = alive && !S.have;
+        bool hit = false, reflective = false;
+        if (done) {
+            alive = false;
+            hit = closest_found(S) && S.best.t > 0.1f;                     // min_t, renderer.cpp:1039-1040
+            if (!hit) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, dir));
+            else if (any_reflective) {
+                TriShade ts = load_tri_shade(sc, S.best.tri);
+                reflective = load_material(sc, ts.mat).reflection > 0.0f;
+            }
+        }
+        const unsigned hmask = __ballot_sync(0xffffffffu, hit);
+        if (hmask) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cnt->n_hits, (unsigned)__popc(hmask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t slot = base + (uint32_t)__popc(hmask & lt_mask);
+            if (hit) {
+                q.pix[slot] = (uint32_t)py * (uint32_t)fr.rw + (uint32_t)px;
+                q.tri[slot] = S.best.tri; q.t[slot] = S.best.t; q.u[slot] = S.best.u; q.v[slot] = S.best.v;
+            }
+            const unsigned rmask = __ballot_sync(0xffffffffu, reflective);
+            if (rmask) {
+                uint32_t rbase = 0;
+                if (lane == 0) rbase = atomicAdd(&cnt->n_refl, (unsigned)__popc(rmask));
+                rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                if (reflective) q.refl_idx[rbase + (uint32_t)__popc(rmask & lt_mask)] = slot;
             }
         }
     }
@@ -170,39 +208,76 @@ k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
 }
 
+// Shade + hard shadow + compose + quantise for the queued hits.  Same persistent / refill scheme as k_primary over
+// the hit queue: a refilled lane shades its hit (textures, Blinn-Phong) and starts the any-hit state machine of its
+// shadow ray; when that ends the lane composes the pixel (with the fan colour k_reflect left, if the material
+// reflects) and stores it.
 template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
-k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* super)
+k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t n = cnt->n_hits;
     TraceCounters tc = zero_counters();
     TraceCounters fan = zero_counters();                      // sums of the per-entry records of k_reflect
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        V3 o, d;
-        HitRec hr;
-        uint32_t pix;
-        queue_ray(fr, q, i, o, d, hr, pix);
-        Hit hit = complete_hit(sc, hr);
-        Col c;
-        if (fr.s.shading_method != RT_SHADING)
-            c = shade_debug(sc, fr, hit);
-        else {
-            V3 p;
-            MatView m;
-            Col direct = shade_direct(sc, fr, o, d, hit, p, m);
-            bool shadowed = false;
-            if (fr.s.compute_shadows) shadowed = trace_occluded<COUNT>(sc, p, hit.normal, fr.light, &tc);
+    AnyState S;
+    AnyStack K;
+    S.have = false;
+    S.occluded = false;
+    bool alive = false, exhausted = false;
+    uint32_t entry = 0, pix = 0;
+    int32_t mat = 0;
+    Col direct = col(0.0f);
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        const int n_idle = __popc(idle);
+        if (!exhausted && (n_idle >= tune.shade_refill || n_idle == 32)) {
+            uint32_t base = 0;
+            const int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(&cnt->next_shade, (unsigned)n_idle);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + (uint32_t)n_idle >= n) exhausted = true;
+            const uint32_t r = base + (uint32_t)__popc(idle & lt_mask);
+            if (!alive && r < n) {
+                entry = r;
+                V3 o, d;
+                HitRec hr;
+                queue_ray(fr, q, entry, o, d, hr, pix);
+                Hit hit = complete_hit(sc, hr);
+                if (fr.s.shading_method != RT_SHADING)
+                    super[pix] = quantise_argb(shade_debug(sc, fr, hit));
+                else {
+                    V3 p;
+                    MatView m;
+                    direct = shade_direct(sc, fr, o, d, hit, p, m);
+                    mat = hit.mat;
+                    S.occluded = false;
+                    S.have = false;
+                    if (fr.s.compute_shadows) any_begin<COUNT>(sc, p, hit.normal, fr.light, S, &tc);
+                    alive = true;                             // ends at once when there is no shadow ray to trace
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        if (alive && S.have && !(S.meta & RT_LEAF_BIT)) any_interior_step<COUNT>(sc, S, K, &tc);
+        if (alive && S.have && (S.meta & RT_LEAF_BIT)) any_leaf_step<COUNT>(sc, S, K, &tc);
+        if (alive && !S.have) {
+            alive = false;
+            const MatView m = load_material(sc, mat);
             Col refl = col(0.0f);
             if (m.reflection > 0.0f) {
-                refl = col(q.refl_rgb[3 * (size_t)i], q.refl_rgb[3 * (size_t)i + 1], q.refl_rgb[3 * (size_t)i + 2]);
-                const unsigned long long packed = q.refl_cnt[3 * (size_t)i];
+                refl = col(q.refl_rgb[3 * (size_t)entry], q.refl_rgb[3 * (size_t)entry + 1], q.refl_rgb[3 * (size_t)entry + 2]);
+                const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
                 fan.refl_rays += (uint32_t)packed;
                 fan.refl_shadow_rays += (uint32_t)(packed >> 32);
-                if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)i + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)i + 2]; }
+                if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
             }
-            c = shade_compose(fr, m, direct, shadowed, refl);
+            super[pix] = quantise_argb(shade_compose(fr, m, direct, S.occluded, refl));
         }
-        super[pix] = quantise_argb(c);
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);

@@ -188,179 +188,227 @@ RT_DEV bool tri_test(const rt_f4& p0, const rt_f4& p1, const rt_f4& p2, V3 o, V3
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Traversal as a resumable state machine.  One step = one interior cell (test its <= 8 child records) or one leaf
+// (test its triangles).  The run-to-completion functions below loop over the steps; the persistent kernels interleave
+// the steps of 32 rays and REFILL the lanes whose ray has terminated (kernels.cuh), which is what keeps the warp full
+// when neighbouring rays do very different amounts of work (shadow rays: 6/32 lanes active without it, measured).
+//
 // Closest hit: BVH::intersect (bvh.cpp:68-71 -> bvh.h:212-287).  The reference descends children in order of slab
 // entry distance through a heap-allocated priority queue and stops when the best hit beats the next entry; the
-// result is the exact closest front-facing hit, first-found on ties.  Here: "while-while" traversal -- an inner loop
-// walks interior cells (nearest hit child stays in registers, the others go far-to-near onto an explicit per-thread
-// stack of (entry distance, record) pairs), an outer step tests the triangles of the leaf that loop ended on, so the
-// lanes of a warp run the two phases together instead of interleaving them.  Entries whose distance exceeds the best
-// hit are dropped at pop time.  Leaf triangles are visited in array order with the reference's strict `<`
-// (bvh.h:241); a tie on t goes to the lower original index, which is the same rule inside a leaf.
-//   Returns the reference's bool (a hit with t > 0); best.tri is a LEAF-ORDER index or -1.
+// result is the exact closest front-facing hit, first-found on ties.  Here the nearest hit child stays in registers,
+// the others go far-to-near onto an explicit per-thread stack of (entry distance, record) pairs, and entries whose
+// distance exceeds the best hit are dropped at pop time.  Leaf triangles are visited in array order with the
+// reference's strict `<` (bvh.h:241); a tie on t goes to the lower original index (the same rule inside a leaf).
+struct ClosestState {
+    SlabRay sr;
+    V3 o, md;                       // origin, -direction
+    float best_t;
+    HitRec best;                    // best.tri: LEAF-ORDER index or -1
+    uint32_t link, meta;            // current cell
+    int sp;
+    bool have;                      // false = traversal finished
+};
+
+// The per-thread traversal stack lives apart from the scalar state so that the state stays in registers.
+struct ClosestStack {
+    float t[RT_STACK_SIZE];
+    uint32_t r[RT_STACK_SIZE];
+};
+
+RT_DEV void closest_pop(const SceneView& sc, ClosestState& S, const ClosestStack& K)
+{
+    S.have = false;
+    while (S.sp > 0) {
+        --S.sp;
+        if (K.t[S.sp] > S.best_t) continue;                 // a closer hit was found since this cell was pushed
+        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)K.r[S.sp] + 3);
+        S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
+        S.have = true;
+        break;
+    }
+}
+
+template <bool COUNT>
+RT_DEV void closest_begin(const SceneView& sc, V3 o, V3 d, ClosestState& S, TraceCounters* tc)
+{
+    slab_setup(o, d, S.sr);
+    S.o = o; S.md = -d;
+    S.best_t = INFINITY;
+    S.best.tri = -1; S.best.t = -1.0f; S.best.u = 1.0f; S.best.v = 0.0f;
+    S.sp = 0;
+    const rt_f4* r = sc.recs;                                // the root cell's own volume, bvh.h:232-233
+    rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+    if (COUNT) tc->vol_tests++;
+    S.have = slab_entry(q0, q1, q2, q3, S.sr, S.best_t) != INFINITY;
+    S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
+}
+
+template <bool COUNT>
+RT_DEV void closest_interior_step(const SceneView& sc, ClosestState& S, ClosestStack& K, TraceCounters* tc)
+{
+    const uint32_t link = S.link, meta = S.meta;
+    const rt_f4* r = sc.recs + 4 * (size_t)link;
+    if (S.sp + (int)meta > RT_STACK_SIZE) { tc->stack_overflow = 1; S.have = false; return; }
+    if (COUNT) tc->vol_tests += meta;
+    const int base = S.sp;
+    float near_t = INFINITY;
+    uint32_t near_rec = 0, near_link = 0, near_meta = 0;
+    for (uint32_t k = 0; k < meta; k++, r += 4) {
+        rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+        float tn = slab_entry(c0, c1, c2, c3, S.sr, S.best_t);
+        if (tn == INFINITY) continue;
+        uint32_t rec = link + k;
+        if (tn < near_t) {                                  // new nearest child: the previous one goes to the stack
+            float pt = near_t; uint32_t pr = near_rec;
+            near_t = tn; near_rec = rec; near_link = f4_bits(c3.z); near_meta = f4_bits(c3.w);
+            tn = pt; rec = pr;
+            if (tn == INFINITY) continue;
+        }
+        int j = S.sp;                                       // keep [base, sp) sorted by descending entry distance
+        while (j > base && K.t[j - 1] < tn) {
+            K.t[j] = K.t[j - 1];
+            K.r[j] = K.r[j - 1];
+            --j;
+        }
+        K.t[j] = tn;
+        K.r[j] = rec;
+        ++S.sp;
+    }
+    if (near_t != INFINITY) { S.link = near_link; S.meta = near_meta; }
+    else closest_pop(sc, S, K);
+}
+
+template <bool COUNT>
+RT_DEV void closest_leaf_step(const SceneView& sc, ClosestState& S, const ClosestStack& K, TraceCounters* tc)
+{
+    const uint32_t link = S.link, cnt = S.meta & ~RT_LEAF_BIT;
+    const rt_f4* tp = sc.tris + 3 * (size_t)link;
+    if (COUNT) tc->tri_tests += cnt;
+    for (uint32_t i = 0; i < cnt; i++, tp += 3) {
+        rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+        float t, u, v;
+        if (tri_test(p0, p1, p2, S.o, S.md, t, u, v) &&
+            (t < S.best_t || (t == S.best_t && sc.orig[link + i] < sc.orig[S.best.tri]))) {
+            S.best_t = t;
+            S.best.tri = (int32_t)(link + i); S.best.t = t; S.best.u = u; S.best.v = v;
+        }
+    }
+    closest_pop(sc, S, K);
+}
+
+// Returns the reference's bool (a hit with t > 0: the leaf returns t_near > 0, bvh.h:245-247).
+RT_DEV bool closest_found(const ClosestState& S) { return S.best.tri >= 0 && S.best.t > 0.0f; }
+
 template <bool COUNT>
 RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCounters* tc)
 {
-    SlabRay sr;
-    slab_setup(o, d, sr);
-    const V3 md = -d;
-    float best_t = INFINITY;
-    best.tri = -1; best.t = -1.0f; best.u = 1.0f; best.v = 0.0f;
-
-    float stack_t[RT_STACK_SIZE];
-    uint32_t stack_r[RT_STACK_SIZE];
-    int sp = 0;
-    uint32_t link, meta;
-    bool have;
-    {   // the root cell's own volume, bvh.h:232-233
-        const rt_f4* r = sc.recs;
-        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
-        if (COUNT) tc->vol_tests++;
-        if (slab_entry(q0, q1, q2, q3, sr, best_t) == INFINITY) return false;
-        link = f4_bits(q3.z); meta = f4_bits(q3.w);
-        have = true;
+    ClosestState S;
+    ClosestStack K;
+    closest_begin<COUNT>(sc, o, d, S, tc);
+    while (S.have) {
+        while (S.have && !(S.meta & RT_LEAF_BIT)) closest_interior_step<COUNT>(sc, S, K, tc);
+        if (S.have) closest_leaf_step<COUNT>(sc, S, K, tc);
     }
-    for (;;) {
-        // ---- phase 1: interior cells
-        while (have && !(meta & RT_LEAF_BIT)) {
-            const rt_f4* r = sc.recs + 4 * (size_t)link;
-            if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return best.tri >= 0 && best.t > 0.0f; }
-            if (COUNT) tc->vol_tests += meta;
-            const int base = sp;
-            float near_t = INFINITY;
-            uint32_t near_rec = 0, near_link = 0, near_meta = 0;
-            for (uint32_t k = 0; k < meta; k++, r += 4) {
-                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-                float tn = slab_entry(c0, c1, c2, c3, sr, best_t);
-                if (tn == INFINITY) continue;
-                uint32_t rec = link + k;
-                if (tn < near_t) {                          // new nearest child: the previous one goes to the stack
-                    float pt = near_t; uint32_t pr = near_rec;
-                    near_t = tn; near_rec = rec; near_link = f4_bits(c3.z); near_meta = f4_bits(c3.w);
-                    tn = pt; rec = pr;
-                    if (tn == INFINITY) continue;
-                }
-                int j = sp;                                 // keep [base, sp) sorted by descending entry distance
-                while (j > base && stack_t[j - 1] < tn) {
-                    stack_t[j] = stack_t[j - 1];
-                    stack_r[j] = stack_r[j - 1];
-                    --j;
-                }
-                stack_t[j] = tn;
-                stack_r[j] = rec;
-                ++sp;
-            }
-            if (near_t != INFINITY) { link = near_link; meta = near_meta; }
-            else {
-                have = false;
-                while (sp > 0) {
-                    --sp;
-                    if (stack_t[sp] > best_t) continue;     // a closer hit was found since this cell was pushed
-                    const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
-                    link = f4_bits(q3.z); meta = f4_bits(q3.w);
-                    have = true;
-                    break;
-                }
-            }
-        }
-        if (!have) break;
-        // ---- phase 2: the triangles of one leaf
-        {
-            const uint32_t cnt = meta & ~RT_LEAF_BIT;
-            const rt_f4* tp = sc.tris + 3 * (size_t)link;
-            if (COUNT) tc->tri_tests += cnt;
-            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
-                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-                float t, u, v;
-                if (tri_test(p0, p1, p2, o, md, t, u, v) &&
-                    (t < best_t || (t == best_t && sc.orig[link + i] < sc.orig[best.tri]))) {
-                    best_t = t;
-                    best.tri = (int32_t)(link + i); best.t = t; best.u = u; best.v = v;
-                }
-            }
-        }
-        have = false;
-        while (sp > 0) {
-            --sp;
-            if (stack_t[sp] > best_t) continue;
-            const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[sp] + 3);
-            link = f4_bits(q3.z); meta = f4_bits(q3.w);
-            have = true;
-            break;
-        }
-        if (!have) break;
-    }
-    return best.tri >= 0 && best.t > 0.0f;                  // leaf returns t_near > 0, bvh.h:245-247
+    best = S.best;
+    return closest_found(S);
 }
 
 // Any hit for Renderer::is_shadowed (renderer.cpp:340-402).  The reference runs a CLOSEST-hit query from
 // p + n*EPSILON towards the light and then compares |p - hitpoint|^2 with |p - light|^2.  Beyond 2e-4 from the
 // origin that predicate is monotone in t, so "some front-facing hit with t > 0 satisfies it" is the same
 // statement as "the closest one does"; the traversal can stop at the first such hit, needs no ordering, and can
-// drop cells that start beyond the light.  Same while-while shape as trace_closest.
+// drop cells that start beyond the light.
+struct AnyState {
+    SlabRay sr;
+    V3 o, d, p;
+    float dist2, t_limit;
+    uint32_t link, meta;
+    int sp;
+    bool have, occluded;
+};
+
+struct AnyStack {
+    uint32_t r[RT_STACK_SIZE];
+};
+
+RT_DEV void any_pop(const SceneView& sc, AnyState& S, const AnyStack& K)
+{
+    if (S.sp > 0) {
+        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)K.r[--S.sp] + 3);
+        S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
+    } else
+        S.have = false;
+}
+
+template <bool COUNT>
+RT_DEV void any_begin(const SceneView& sc, V3 p, V3 n, V3 light, AnyState& S, TraceCounters* tc)
+{
+    S.p = p;
+    S.o = p + 1.0e-4f * n;                                   // Renderer::EPSILON, renderer.h:23
+    S.d = normalize(light - p);
+    S.dist2 = length2(p - light);
+    S.t_limit = (sqrtf(S.dist2) + 4.0e-4f) * 1.0001f;
+    slab_setup(S.o, S.d, S.sr);
+    S.sp = 0;
+    S.occluded = false;
+    const rt_f4* r = sc.recs;
+    rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+    if (COUNT) tc->vol_tests++;
+    S.have = slab_entry(q0, q1, q2, q3, S.sr, S.t_limit) != INFINITY;
+    S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
+}
+
+template <bool COUNT>
+RT_DEV void any_interior_step(const SceneView& sc, AnyState& S, AnyStack& K, TraceCounters* tc)
+{
+    const uint32_t link = S.link, meta = S.meta;
+    const rt_f4* r = sc.recs + 4 * (size_t)link;
+    if (S.sp + (int)meta > RT_STACK_SIZE) { tc->stack_overflow = 1; S.have = false; return; }
+    if (COUNT) tc->vol_tests += meta;
+    bool got = false;
+    for (uint32_t k = 0; k < meta; k++, r += 4) {
+        rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+        if (slab_entry(c0, c1, c2, c3, S.sr, S.t_limit) == INFINITY) continue;
+        if (got) K.r[S.sp++] = link + k;                    // the first hit child stays in registers
+        else { got = true; S.link = f4_bits(c3.z); S.meta = f4_bits(c3.w); }
+    }
+    if (!got) any_pop(sc, S, K);
+}
+
+template <bool COUNT>
+RT_DEV void any_leaf_step(const SceneView& sc, AnyState& S, const AnyStack& K, TraceCounters* tc)
+{
+    const uint32_t cnt = S.meta & ~RT_LEAF_BIT;
+    const rt_f4* tp = sc.tris + 3 * (size_t)S.link;
+    const V3 md = -S.d;
+    for (uint32_t i = 0; i < cnt; i++, tp += 3) {
+        rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+        float t, u, v;
+        if (COUNT) tc->tri_tests++;
+        if (tri_test(p0, p1, p2, S.o, md, t, u, v) && t > 0.0f) {
+            V3 q = S.o + t * S.d;                            // renderer.cpp:351
+            if (length2(S.p - q) < S.dist2) {                // renderer.cpp:354
+                S.occluded = true;
+                S.have = false;
+                return;
+            }
+        }
+    }
+    any_pop(sc, S, K);
+}
+
 template <bool COUNT>
 RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCounters* tc)
 {
-    const V3 o = p + 1.0e-4f * n;                            // Renderer::EPSILON, renderer.h:23
-    const V3 d = normalize(light - p);
-    const float dist2 = length2(p - light);
-    const float t_limit = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
-    SlabRay sr;
-    slab_setup(o, d, sr);
-    const V3 md = -d;
-
-    uint32_t stack_r[RT_STACK_SIZE];
-    int sp = 0;
-    uint32_t link, meta;
-    bool have;
-    {
-        const rt_f4* r = sc.recs;
-        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
-        if (COUNT) tc->vol_tests++;
-        if (slab_entry(q0, q1, q2, q3, sr, t_limit) == INFINITY) return false;
-        link = f4_bits(q3.z); meta = f4_bits(q3.w);
-        have = true;
+    AnyState S;
+    AnyStack K;
+    any_begin<COUNT>(sc, p, n, light, S, tc);
+    while (S.have) {
+        while (S.have && !(S.meta & RT_LEAF_BIT)) any_interior_step<COUNT>(sc, S, K, tc);
+        if (S.have) any_leaf_step<COUNT>(sc, S, K, tc);
     }
-    for (;;) {
-        while (have && !(meta & RT_LEAF_BIT)) {
-            const rt_f4* r = sc.recs + 4 * (size_t)link;
-            if (sp + (int)meta > RT_STACK_SIZE) { if (tc) tc->stack_overflow = 1; return false; }
-            if (COUNT) tc->vol_tests += meta;
-            bool got = false;
-            uint32_t nl = 0, nm = 0;
-            for (uint32_t k = 0; k < meta; k++, r += 4) {
-                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-                if (slab_entry(c0, c1, c2, c3, sr, t_limit) == INFINITY) continue;
-                if (got) stack_r[sp++] = link + k;          // first hit child stays in registers
-                else { got = true; nl = f4_bits(c3.z); nm = f4_bits(c3.w); }
-            }
-            if (got) { link = nl; meta = nm; }
-            else if (sp > 0) {
-                const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[--sp] + 3);
-                link = f4_bits(q3.z); meta = f4_bits(q3.w);
-            } else
-                have = false;
-        }
-        if (!have) break;
-        {
-            const uint32_t cnt = meta & ~RT_LEAF_BIT;
-            const rt_f4* tp = sc.tris + 3 * (size_t)link;
-            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
-                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-                float t, u, v;
-                if (COUNT) tc->tri_tests++;
-                if (tri_test(p0, p1, p2, o, md, t, u, v) && t > 0.0f) {
-                    V3 q = o + t * d;                        // renderer.cpp:351
-                    if (length2(p - q) < dist2) return true; // renderer.cpp:354
-                }
-            }
-        }
-        if (sp > 0) {
-            const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)stack_r[--sp] + 3);
-            link = f4_bits(q3.z); meta = f4_bits(q3.w);
-        } else
-            break;
-    }
-    return false;
+    return S.occluded;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -106,7 +106,8 @@ struct RtContext {
     std::vector<TimedLaunch> timed;
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
-    int opt_leaf_split = 4;
+    int opt_leaf_split = 8;
+    Tuning tune{8, 12};
     uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
@@ -333,6 +334,11 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         if (value < 0 || value > 1024) return fail(ctx, RT_ERR_INVALID, "leaf split %lld", (long long)value);
         ctx->opt_leaf_split = (int)value;
         ctx->bvh_valid = false;                          // takes effect at the next rt_build_bvh
+        return RT_OK;
+    case RT_OPT_REFILL_PRIMARY:
+    case RT_OPT_REFILL_SHADE:
+        if (value < 1 || value > 32) return fail(ctx, RT_ERR_INVALID, "refill threshold %lld outside [1,32]", (long long)value);
+        (option == RT_OPT_REFILL_PRIMARY ? ctx->tune.primary_refill : ctx->tune.shade_refill) = (int32_t)value;
         return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
@@ -565,8 +571,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         ChunkCounters* cnt = ctx->d_counters.p + c;
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
-            if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0);
-            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0);
+            if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0, ctx->tune);
+            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0, ctx->tune);
             launches++;
         }
         if (reflect) {
@@ -577,8 +583,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         }
         {
             ScopedTimer tm(ctx, ST_SHADE);
-            if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super);
-            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super);
+            if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super, ctx->tune);
+            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super, ctx->tune);
             launches++;
         }
     }

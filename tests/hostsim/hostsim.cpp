@@ -38,7 +38,7 @@ struct RtContext {
     HostTexture tex[RT_TEX_COUNT];
     M4 proj_inv{}, cam_to_world{};
     V3 cam_pos{0, 0, 0}, light{3, 3, 2};
-    int leaf_split = 4;
+    int leaf_split = 8;
 };
 
 static int fail(RtContext* c, int code, const std::string& msg)
@@ -123,7 +123,7 @@ const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""
 int rt_set_option(RtContext* c, int option, int64_t value)
 {
     if (option == RT_OPT_LEAF_SPLIT) { c->leaf_split = (int)value; c->bvh_valid = false; return RT_OK; }
-    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
+    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
 }
 
 int rt_set_stream(RtContext*, void*) { return RT_OK; }
@@ -406,7 +406,7 @@ int rt_occluded(RtContext* c, const float* p3, const float* n3, size_t n, uint8_
     const SceneView sc = scene_view(c);
 #pragma omp parallel for schedule(dynamic, 256)
     for (long long i = 0; i < (long long)n; i++)
-        occluded[i] = trace_occluded<false>(sc, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]), c->light, nullptr) ? 1 : 0;
+        { TraceCounters tcs = zero_counters(); occluded[i] = trace_occluded<false>(sc, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]), c->light, &tcs) ? 1 : 0; }
     return RT_OK;
 }
 
