@@ -20,6 +20,7 @@ namespace rtb {
 constexpr int kPatch = 8;            // a warp's work item is a kPatch x kPatch block of supersampled pixels (2 passes of 8x4)
 constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
+constexpr int kStepsPerCheck = 4;    // single-test steps between two refill / completion checks of a persistent warp
 
 struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int next_patch;         // next ray slot of k_primary
@@ -95,7 +96,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
     TraceCounters tc = zero_counters();
     ClosestState S;
     ClosestStack K;
-    S.have = false;
+    S.mode = RT_MODE_DONE;
     bool alive = false, exhausted = false;
     int px = 0, py = 0;
     V3 dir = v3(0, 0, 0);
@@ -130,11 +131,14 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
             if (exhausted) break;
             continue;
         }
-        // ---- one interior step, then one leaf step, for the lanes that are there
-        if (alive && S.have && !(S.meta & RT_LEAF_BIT)) closest_interior_step<COUNT>(sc, S, K, &tc);
-        if (alive && S.have && (S.meta & RT_LEAF_BIT)) closest_leaf_step<COUNT>(sc, S, K, &tc);
-        // ---- rays that ended this iteration
-        const bool done = alive && !S.have;
+        // ---- a few single-test steps: slab tests for the lanes inside a cell, triangle tests for those inside a leaf
+#pragma unroll 1
+        for (int it = 0; it < kStepsPerCheck; it++) {
+            if (alive && S.mode == RT_MODE_CHILDREN) closest_child_step<COUNT>(sc, S, K, &tc);
+            if (alive && S.mode == RT_MODE_TRIANGLES) closest_triangle_step<COUNT>(sc, S, K, &tc);
+        }
+        // ---- rays that have ended
+        const bool done = alive && S.mode == RT_MODE_DONE;
         bool hit = false, reflective = false;
         if (done) {
             alive = false;
@@ -223,7 +227,7 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
     TraceCounters fan = zero_counters();                      // sums of the per-entry records of k_reflect
     AnyState S;
     AnyStack K;
-    S.have = false;
+    S.mode = RT_MODE_DONE;
     S.occluded = false;
     bool alive = false, exhausted = false;
     uint32_t entry = 0, pix = 0;
@@ -253,7 +257,7 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
                     direct = shade_direct(sc, fr, o, d, hit, p, m);
                     mat = hit.mat;
                     S.occluded = false;
-                    S.have = false;
+                    S.mode = RT_MODE_DONE;
                     if (fr.s.compute_shadows) any_begin<COUNT>(sc, p, hit.normal, fr.light, S, &tc);
                     alive = true;                             // ends at once when there is no shadow ray to trace
                 }
@@ -263,9 +267,12 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
             if (exhausted) break;
             continue;
         }
-        if (alive && S.have && !(S.meta & RT_LEAF_BIT)) any_interior_step<COUNT>(sc, S, K, &tc);
-        if (alive && S.have && (S.meta & RT_LEAF_BIT)) any_leaf_step<COUNT>(sc, S, K, &tc);
-        if (alive && !S.have) {
+#pragma unroll 1
+        for (int it = 0; it < kStepsPerCheck; it++) {
+            if (alive && S.mode == RT_MODE_CHILDREN) any_child_step<COUNT>(sc, S, K, &tc);
+            if (alive && S.mode == RT_MODE_TRIANGLES) any_triangle_step<COUNT>(sc, S, K, &tc);
+        }
+        if (alive && S.mode == RT_MODE_DONE) {
             alive = false;
             const MatView m = load_material(sc, mat);
             Col refl = col(0.0f);

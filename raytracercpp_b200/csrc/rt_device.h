@@ -189,25 +189,30 @@ RT_DEV bool tri_test(const rt_f4& p0, const rt_f4& p1, const rt_f4& p2, V3 o, V3
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Traversal as a resumable state machine.  One step = one interior cell (test its <= 8 child records) or one leaf
-// (test its triangles).  The run-to-completion functions below loop over the steps; the persistent kernels interleave
-// the steps of 32 rays and REFILL the lanes whose ray has terminated (kernels.cuh), which is what keeps the warp full
-// when neighbouring rays do very different amounts of work (shadow rays: 6/32 lanes active without it, measured).
+// Traversal as a resumable state machine with ONE TEST PER STEP: a step is either one 7-slab test of one child
+// record (mode 1) or one ray/triangle test (mode 2).  The run-to-completion functions below loop over the steps; the
+// persistent kernels (kernels.cuh) interleave the steps of 32 rays, so every lane of a warp does the same amount of
+// work per iteration whatever the arity of its cell or the size of its leaf, and lanes whose ray has ended are
+// refilled.  (Measured on B200, shadow rays of the 10 M-triangle scene: a cell-per-step loop kept 6 of 32 lanes busy.)
 //
 // Closest hit: BVH::intersect (bvh.cpp:68-71 -> bvh.h:212-287).  The reference descends children in order of slab
 // entry distance through a heap-allocated priority queue and stops when the best hit beats the next entry; the
-// result is the exact closest front-facing hit, first-found on ties.  Here the nearest hit child stays in registers,
-// the others go far-to-near onto an explicit per-thread stack of (entry distance, record) pairs, and entries whose
+// result is the exact closest front-facing hit, first-found on ties.  Here the hit children of a cell go far-to-near
+// onto an explicit per-thread stack of (entry distance, record) pairs, the nearest is popped first, and entries whose
 // distance exceeds the best hit are dropped at pop time.  Leaf triangles are visited in array order with the
 // reference's strict `<` (bvh.h:241); a tie on t goes to the lower original index (the same rule inside a leaf).
+#define RT_MODE_DONE 0u
+#define RT_MODE_CHILDREN 1u
+#define RT_MODE_TRIANGLES 2u
+
 struct ClosestState {
     SlabRay sr;
     V3 o, md;                       // origin, -direction
     float best_t;
     HitRec best;                    // best.tri: LEAF-ORDER index or -1
-    uint32_t link, meta;            // current cell
-    int sp;
-    bool have;                      // false = traversal finished
+    uint32_t mode;                  // RT_MODE_*
+    uint32_t next, left;            // next child record / triangle to test and how many remain in the range
+    int sp, base;                   // stack top; first entry pushed by the current cell
 };
 
 // The per-thread traversal stack lives apart from the scalar state so that the state stays in registers.
@@ -216,15 +221,24 @@ struct ClosestStack {
     uint32_t r[RT_STACK_SIZE];
 };
 
+RT_DEV void closest_enter(ClosestState& S, uint32_t link, uint32_t meta)
+{
+    S.next = link;
+    S.base = S.sp;
+    if (meta & RT_LEAF_BIT) { S.mode = RT_MODE_TRIANGLES; S.left = meta & ~RT_LEAF_BIT; }
+    else { S.mode = RT_MODE_CHILDREN; S.left = meta; }
+}
+
 RT_DEV void closest_pop(const SceneView& sc, ClosestState& S, const ClosestStack& K)
 {
-    S.have = false;
+    S.mode = RT_MODE_DONE;
     while (S.sp > 0) {
         --S.sp;
         if (K.t[S.sp] > S.best_t) continue;                 // a closer hit was found since this cell was pushed
         const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)K.r[S.sp] + 3);
-        S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
-        S.have = true;
+        const uint32_t meta = f4_bits(q3.w);
+        if ((meta & ~RT_LEAF_BIT) == 0u) continue;          // empty scene root
+        closest_enter(S, f4_bits(q3.z), meta);
         break;
     }
 }
@@ -237,64 +251,51 @@ RT_DEV void closest_begin(const SceneView& sc, V3 o, V3 d, ClosestState& S, Trac
     S.best_t = INFINITY;
     S.best.tri = -1; S.best.t = -1.0f; S.best.u = 1.0f; S.best.v = 0.0f;
     S.sp = 0;
+    S.mode = RT_MODE_DONE;
     const rt_f4* r = sc.recs;                                // the root cell's own volume, bvh.h:232-233
     rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
     if (COUNT) tc->vol_tests++;
-    S.have = slab_entry(q0, q1, q2, q3, S.sr, S.best_t) != INFINITY;
-    S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
+    const uint32_t meta = f4_bits(q3.w);
+    if (slab_entry(q0, q1, q2, q3, S.sr, S.best_t) != INFINITY && (meta & ~RT_LEAF_BIT) != 0u) closest_enter(S, f4_bits(q3.z), meta);
 }
 
 template <bool COUNT>
-RT_DEV void closest_interior_step(const SceneView& sc, ClosestState& S, ClosestStack& K, TraceCounters* tc)
+RT_DEV void closest_child_step(const SceneView& sc, ClosestState& S, ClosestStack& K, TraceCounters* tc)
 {
-    const uint32_t link = S.link, meta = S.meta;
-    const rt_f4* r = sc.recs + 4 * (size_t)link;
-    if (S.sp + (int)meta > RT_STACK_SIZE) { tc->stack_overflow = 1; S.have = false; return; }
-    if (COUNT) tc->vol_tests += meta;
-    const int base = S.sp;
-    float near_t = INFINITY;
-    uint32_t near_rec = 0, near_link = 0, near_meta = 0;
-    for (uint32_t k = 0; k < meta; k++, r += 4) {
-        rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-        float tn = slab_entry(c0, c1, c2, c3, S.sr, S.best_t);
-        if (tn == INFINITY) continue;
-        uint32_t rec = link + k;
-        if (tn < near_t) {                                  // new nearest child: the previous one goes to the stack
-            float pt = near_t; uint32_t pr = near_rec;
-            near_t = tn; near_rec = rec; near_link = f4_bits(c3.z); near_meta = f4_bits(c3.w);
-            tn = pt; rec = pr;
-            if (tn == INFINITY) continue;
-        }
+    const rt_f4* r = sc.recs + 4 * (size_t)S.next;
+    rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+    if (COUNT) tc->vol_tests++;
+    const float tn = slab_entry(c0, c1, c2, c3, S.sr, S.best_t);
+    if (tn != INFINITY) {
+        if (S.sp >= RT_STACK_SIZE) { tc->stack_overflow = 1; S.mode = RT_MODE_DONE; return; }
         int j = S.sp;                                       // keep [base, sp) sorted by descending entry distance
-        while (j > base && K.t[j - 1] < tn) {
+        while (j > S.base && K.t[j - 1] < tn) {
             K.t[j] = K.t[j - 1];
             K.r[j] = K.r[j - 1];
             --j;
         }
         K.t[j] = tn;
-        K.r[j] = rec;
+        K.r[j] = S.next;
         ++S.sp;
     }
-    if (near_t != INFINITY) { S.link = near_link; S.meta = near_meta; }
-    else closest_pop(sc, S, K);
+    ++S.next;
+    if (--S.left == 0u) closest_pop(sc, S, K);
 }
 
 template <bool COUNT>
-RT_DEV void closest_leaf_step(const SceneView& sc, ClosestState& S, const ClosestStack& K, TraceCounters* tc)
+RT_DEV void closest_triangle_step(const SceneView& sc, ClosestState& S, const ClosestStack& K, TraceCounters* tc)
 {
-    const uint32_t link = S.link, cnt = S.meta & ~RT_LEAF_BIT;
-    const rt_f4* tp = sc.tris + 3 * (size_t)link;
-    if (COUNT) tc->tri_tests += cnt;
-    for (uint32_t i = 0; i < cnt; i++, tp += 3) {
-        rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-        float t, u, v;
-        if (tri_test(p0, p1, p2, S.o, S.md, t, u, v) &&
-            (t < S.best_t || (t == S.best_t && sc.orig[link + i] < sc.orig[S.best.tri]))) {
-            S.best_t = t;
-            S.best.tri = (int32_t)(link + i); S.best.t = t; S.best.u = u; S.best.v = v;
-        }
+    const rt_f4* tp = sc.tris + 3 * (size_t)S.next;
+    rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+    if (COUNT) tc->tri_tests++;
+    float t, u, v;
+    if (tri_test(p0, p1, p2, S.o, S.md, t, u, v) &&
+        (t < S.best_t || (t == S.best_t && sc.orig[S.next] < sc.orig[S.best.tri]))) {
+        S.best_t = t;
+        S.best.tri = (int32_t)S.next; S.best.t = t; S.best.u = u; S.best.v = v;
     }
-    closest_pop(sc, S, K);
+    ++S.next;
+    if (--S.left == 0u) closest_pop(sc, S, K);
 }
 
 // Returns the reference's bool (a hit with t > 0: the leaf returns t_near > 0, bvh.h:245-247).
@@ -306,9 +307,9 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
     ClosestState S;
     ClosestStack K;
     closest_begin<COUNT>(sc, o, d, S, tc);
-    while (S.have) {
-        while (S.have && !(S.meta & RT_LEAF_BIT)) closest_interior_step<COUNT>(sc, S, K, tc);
-        if (S.have) closest_leaf_step<COUNT>(sc, S, K, tc);
+    while (S.mode != RT_MODE_DONE) {
+        if (S.mode == RT_MODE_CHILDREN) closest_child_step<COUNT>(sc, S, K, tc);
+        else closest_triangle_step<COUNT>(sc, S, K, tc);
     }
     best = S.best;
     return closest_found(S);
@@ -323,22 +324,32 @@ struct AnyState {
     SlabRay sr;
     V3 o, d, p;
     float dist2, t_limit;
-    uint32_t link, meta;
+    uint32_t mode, next, left;
     int sp;
-    bool have, occluded;
+    bool occluded;
 };
 
 struct AnyStack {
     uint32_t r[RT_STACK_SIZE];
 };
 
+RT_DEV void any_enter(AnyState& S, uint32_t link, uint32_t meta)
+{
+    S.next = link;
+    if (meta & RT_LEAF_BIT) { S.mode = RT_MODE_TRIANGLES; S.left = meta & ~RT_LEAF_BIT; }
+    else { S.mode = RT_MODE_CHILDREN; S.left = meta; }
+}
+
 RT_DEV void any_pop(const SceneView& sc, AnyState& S, const AnyStack& K)
 {
-    if (S.sp > 0) {
+    S.mode = RT_MODE_DONE;
+    while (S.sp > 0) {
         const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)K.r[--S.sp] + 3);
-        S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
-    } else
-        S.have = false;
+        const uint32_t meta = f4_bits(q3.w);
+        if ((meta & ~RT_LEAF_BIT) == 0u) continue;
+        any_enter(S, f4_bits(q3.z), meta);
+        break;
+    }
 }
 
 template <bool COUNT>
@@ -352,50 +363,45 @@ RT_DEV void any_begin(const SceneView& sc, V3 p, V3 n, V3 light, AnyState& S, Tr
     slab_setup(S.o, S.d, S.sr);
     S.sp = 0;
     S.occluded = false;
+    S.mode = RT_MODE_DONE;
     const rt_f4* r = sc.recs;
     rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
     if (COUNT) tc->vol_tests++;
-    S.have = slab_entry(q0, q1, q2, q3, S.sr, S.t_limit) != INFINITY;
-    S.link = f4_bits(q3.z); S.meta = f4_bits(q3.w);
+    const uint32_t meta = f4_bits(q3.w);
+    if (slab_entry(q0, q1, q2, q3, S.sr, S.t_limit) != INFINITY && (meta & ~RT_LEAF_BIT) != 0u) any_enter(S, f4_bits(q3.z), meta);
 }
 
 template <bool COUNT>
-RT_DEV void any_interior_step(const SceneView& sc, AnyState& S, AnyStack& K, TraceCounters* tc)
+RT_DEV void any_child_step(const SceneView& sc, AnyState& S, AnyStack& K, TraceCounters* tc)
 {
-    const uint32_t link = S.link, meta = S.meta;
-    const rt_f4* r = sc.recs + 4 * (size_t)link;
-    if (S.sp + (int)meta > RT_STACK_SIZE) { tc->stack_overflow = 1; S.have = false; return; }
-    if (COUNT) tc->vol_tests += meta;
-    bool got = false;
-    for (uint32_t k = 0; k < meta; k++, r += 4) {
-        rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-        if (slab_entry(c0, c1, c2, c3, S.sr, S.t_limit) == INFINITY) continue;
-        if (got) K.r[S.sp++] = link + k;                    // the first hit child stays in registers
-        else { got = true; S.link = f4_bits(c3.z); S.meta = f4_bits(c3.w); }
+    const rt_f4* r = sc.recs + 4 * (size_t)S.next;
+    rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+    if (COUNT) tc->vol_tests++;
+    if (slab_entry(c0, c1, c2, c3, S.sr, S.t_limit) != INFINITY) {
+        if (S.sp >= RT_STACK_SIZE) { tc->stack_overflow = 1; S.mode = RT_MODE_DONE; return; }
+        K.r[S.sp++] = S.next;
     }
-    if (!got) any_pop(sc, S, K);
+    ++S.next;
+    if (--S.left == 0u) any_pop(sc, S, K);
 }
 
 template <bool COUNT>
-RT_DEV void any_leaf_step(const SceneView& sc, AnyState& S, const AnyStack& K, TraceCounters* tc)
+RT_DEV void any_triangle_step(const SceneView& sc, AnyState& S, const AnyStack& K, TraceCounters* tc)
 {
-    const uint32_t cnt = S.meta & ~RT_LEAF_BIT;
-    const rt_f4* tp = sc.tris + 3 * (size_t)S.link;
-    const V3 md = -S.d;
-    for (uint32_t i = 0; i < cnt; i++, tp += 3) {
-        rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-        float t, u, v;
-        if (COUNT) tc->tri_tests++;
-        if (tri_test(p0, p1, p2, S.o, md, t, u, v) && t > 0.0f) {
-            V3 q = S.o + t * S.d;                            // renderer.cpp:351
-            if (length2(S.p - q) < S.dist2) {                // renderer.cpp:354
-                S.occluded = true;
-                S.have = false;
-                return;
-            }
+    const rt_f4* tp = sc.tris + 3 * (size_t)S.next;
+    rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+    if (COUNT) tc->tri_tests++;
+    float t, u, v;
+    if (tri_test(p0, p1, p2, S.o, -S.d, t, u, v) && t > 0.0f) {
+        V3 q = S.o + t * S.d;                                // renderer.cpp:351
+        if (length2(S.p - q) < S.dist2) {                    // renderer.cpp:354
+            S.occluded = true;
+            S.mode = RT_MODE_DONE;
+            return;
         }
     }
-    any_pop(sc, S, K);
+    ++S.next;
+    if (--S.left == 0u) any_pop(sc, S, K);
 }
 
 template <bool COUNT>
@@ -404,9 +410,9 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
     AnyState S;
     AnyStack K;
     any_begin<COUNT>(sc, p, n, light, S, tc);
-    while (S.have) {
-        while (S.have && !(S.meta & RT_LEAF_BIT)) any_interior_step<COUNT>(sc, S, K, tc);
-        if (S.have) any_leaf_step<COUNT>(sc, S, K, tc);
+    while (S.mode != RT_MODE_DONE) {
+        if (S.mode == RT_MODE_CHILDREN) any_child_step<COUNT>(sc, S, K, tc);
+        else any_triangle_step<COUNT>(sc, S, K, tc);
     }
     return S.occluded;
 }
