@@ -223,7 +223,7 @@ def run_ours(args, scene):
         sync_all()
         sampler = ClockSampler(local)
         sampler.start()
-        stage = {"k_primary": 0.0, "k_shade": 0.0, "k_reflect": 0.0, "k_resolve": 0.0}
+        stage = {"k_primary": 0.0, "k_compact": 0.0, "k_shade": 0.0, "k_reflect": 0.0, "k_resolve": 0.0}
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
         rays_rank = 0
@@ -232,7 +232,7 @@ def run_ours(args, scene):
             st = frame.render()
             frame.gather()
             stage["k_primary"] += st.trace_primary_ms; stage["k_shade"] += st.shade_ms
-            stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms
+            stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms; stage["k_compact"] += st.compact_ms
             launches += st.kernel_launches + (world if world > 1 else 0)       # + pack and (world - 1) unpack kernels
             rays_rank = st.total_rays
         ev1.record(stream)

@@ -112,7 +112,7 @@ typedef struct RtRenderStats {
     float    trace_primary_ms; /* per-stage CUDA-event times, summed over chunks            */
     float    shade_ms;
     float    reflect_ms;
-    float    shadow_ms;
+    float    compact_ms;       /* ordered compaction of the hit records into the ray queues */
     float    resolve_ms;
     /* Filled only when RT_OPT_COUNT_WORK is on (instrumented kernel instantiations, never the timed ones):
      * 7-slab volume tests and ray/triangle tests the traversal performed, per ray class -- the V and T of

@@ -56,7 +56,7 @@ class RtRenderStats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("reflection_rays", C.c_uint64),
                 ("reflection_shadow_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("kernel_launches", C.c_uint32),
                 ("device_ms", C.c_float), ("trace_primary_ms", C.c_float), ("shade_ms", C.c_float),
-                ("reflect_ms", C.c_float), ("shadow_ms", C.c_float), ("resolve_ms", C.c_float),
+                ("reflect_ms", C.c_float), ("compact_ms", C.c_float), ("resolve_ms", C.c_float),
                 ("primary_volume_tests", C.c_uint64), ("primary_triangle_tests", C.c_uint64),
                 ("shadow_volume_tests", C.c_uint64), ("shadow_triangle_tests", C.c_uint64),
                 ("reflection_volume_tests", C.c_uint64), ("reflection_triangle_tests", C.c_uint64)]

@@ -3,6 +3,8 @@
 //   k_primary   ray generation + closest-hit traversal by persistent warps whose idle lanes are refilled from an
 //               atomic ray counter; misses are shaded and written at once, hits are appended to the hit queue with
 //               one atomic per warp (ballot + popc), reflective hits also to the reflection queue
+//   k_compact   turns the per-ray-slot hit records into the hit queue, block by block in slot order, so that 32
+//               consecutive queue entries are 32 neighbouring pixels (coherent shadow rays); also the reflection queue
 //   k_reflect   (only if a material reflects) one thread per reflective hit walks its rough-reflection fan
 //   k_shade     one thread per queued hit: textures / Blinn-Phong, any-hit shadow ray, compose, quantise, store
 //   k_resolve   integer SSAA box filter of the quantised samples (imageUtils.h:98-147)
@@ -59,17 +61,36 @@ struct WorkView {
     int32_t patches_per_side;        // ceil(tile_px / kPatch)
 };
 
-struct QueueView {                   // hit queue (SoA) of one chunk
-    uint32_t* pix;                   // py * rw + px of the supersampled frame
-    int32_t* tri;                    // leaf-order triangle
-    float* t;
-    float* u;
-    float* v;
+struct QueueView {
+    // dense, one per ray slot of the chunk (slot = position in patch order, see slot_pixel)
+    int32_t* slot_tri;               // leaf-order triangle of the closest hit, -1 = miss / no ray
+    float* slot_t;                   // valid where slot_tri >= 0
+    float* slot_u;
+    float* slot_v;
+    // compacted by k_compact
+    uint32_t* hit_slot;              // hit queue: ray slots of the hits
     uint32_t* refl_idx;              // reflection queue: indices into the hit queue
     float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
     unsigned long long* refl_cnt;    // 3 words per hit-queue entry, written by k_reflect: rays | shadow rays << 32, V, T
     uint32_t capacity;
 };
+
+// Ray slot -> pixel of the supersampled frame.  Slots enumerate the chunk's tiles, inside a tile its 8x8 patches
+// row-major, inside a patch its pixels row-major, so 32 consecutive slots are an 8x4 pixel block.  Returns false for
+// slots that hang over the tile or frame edge.
+RT_DEV bool slot_pixel(const WorkView& wk, const FrameView& fr, uint32_t slot, int& px, int& py)
+{
+    const uint32_t pps = (uint32_t)wk.patches_per_side;
+    const uint32_t per_tile = pps * pps * (uint32_t)(kPatch * kPatch);
+    const uint32_t tile = wk.tiles[wk.tile_begin + slot / per_tile];
+    const uint32_t in_tile = slot % per_tile;
+    const uint32_t patch = in_tile / (uint32_t)(kPatch * kPatch), in_patch = in_tile % (uint32_t)(kPatch * kPatch);
+    const int lx = (int)(patch % pps) * kPatch + (int)(in_patch & 7u);
+    const int ly = (int)(patch / pps) * kPatch + (int)(in_patch >> 3);
+    px = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px + lx;
+    py = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px + ly;
+    return lx < wk.tile_px && ly < wk.tile_px && px < fr.rw && py < fr.rh;
+}
 
 // Refill thresholds of the persistent kernels: a warp fetches new rays when at least this many of its lanes are idle
 // (and always when all are).  Low = lanes never idle long but the per-ray set-up code runs with few lanes; high = the
@@ -80,25 +101,24 @@ struct Tuning {
 };
 
 // Ray generation + closest hit.  Persistent warps; every lane owns one ray at a time and steps it through the
-// traversal state machine (rt_device.h); lanes whose ray has ended are refilled from an atomic ray counter with the
-// next rays in patch order (tile -> 8x8 patch -> 8x4 half -> pixel), so a warp starts on 32 adjacent pixels and stays
-// on nearby ones.  Misses are shaded and stored at once; hits are appended to the hit queue by warp-ballot
-// compaction (one atomic per warp and iteration), reflective hits also to the reflection queue.
+// traversal state machine (rt_device.h); lanes whose ray has ended are refilled from an atomic ray-slot counter with
+// the next slots in patch order, so a warp starts on 32 adjacent pixels and stays on nearby ones.  Misses are shaded
+// and stored at once; the hit record of every slot goes to the dense slot arrays (k_compact makes the queue).
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryThreads)
-k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, int any_reflective, Tuning tune)
+k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t pps = (uint32_t)wk.patches_per_side;
-    const uint32_t per_tile = pps * pps * (uint32_t)(kPatch * kPatch);
-    const uint32_t total = (wk.tile_end - wk.tile_begin) * per_tile;      // ray slots of the chunk (edge slots may be empty)
+    const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);   // ray slots of the chunk
     TraceCounters tc = zero_counters();
     ClosestState S;
     ClosestStack K;
     S.mode = RT_MODE_DONE;
     bool alive = false, exhausted = false;
     int px = 0, py = 0;
+    uint32_t slot = 0;
     V3 dir = v3(0, 0, 0);
     for (;;) {
         // ---- refill the idle lanes
@@ -112,19 +132,14 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
             if (base + (uint32_t)n_idle >= total) exhausted = true;
             const uint32_t r = base + (uint32_t)__popc(idle & lt_mask);
             if (!alive && r < total) {
-                const uint32_t tile = wk.tiles[wk.tile_begin + r / per_tile];
-                const uint32_t in_tile = r % per_tile;
-                const uint32_t patch = in_tile / (uint32_t)(kPatch * kPatch), in_patch = in_tile % (uint32_t)(kPatch * kPatch);
-                const int lx = (int)(patch % pps) * kPatch + (int)(in_patch & 7u);
-                const int ly = (int)(patch / pps) * kPatch + (int)(in_patch >> 3);
-                px = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px + lx;
-                py = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px + ly;
-                if (lx < wk.tile_px && ly < wk.tile_px && px < fr.rw && py < fr.rh) {
+                slot = r;
+                if (slot_pixel(wk, fr, slot, px, py)) {
                     V3 o;
                     primary_ray(fr, px, py, o, dir);
                     closest_begin<COUNT>(sc, o, dir, S, &tc);
                     alive = true;
-                }
+                } else
+                    q.slot_tri[slot] = -1;
             }
         }
         if (__ballot_sync(0xffffffffu, alive) == 0u) {
@@ -138,33 +153,14 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
             if (alive && S.mode == RT_MODE_TRIANGLES) closest_triangle_step<COUNT>(sc, S, K, &tc);
         }
         // ---- rays that have ended
-        const bool done = alive && S.mode == RT_MODE_DONE;
-        bool hit = false, reflective = false;
-        if (done) {
+        if (alive && S.mode == RT_MODE_DONE) {
             alive = false;
-            hit = closest_found(S) && S.best.t > 0.1f;                     // min_t, renderer.cpp:1039-1040
-            if (!hit) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, dir));
-            else if (any_reflective) {
-                TriShade ts = load_tri_shade(sc, S.best.tri);
-                reflective = load_material(sc, ts.mat).reflection > 0.0f;
-            }
-        }
-        const unsigned hmask = __ballot_sync(0xffffffffu, hit);
-        if (hmask) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&cnt->n_hits, (unsigned)__popc(hmask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t slot = base + (uint32_t)__popc(hmask & lt_mask);
+            const bool hit = closest_found(S) && S.best.t > 0.1f;          // min_t, renderer.cpp:1039-1040
             if (hit) {
-                q.pix[slot] = (uint32_t)py * (uint32_t)fr.rw + (uint32_t)px;
-                q.tri[slot] = S.best.tri; q.t[slot] = S.best.t; q.u[slot] = S.best.u; q.v[slot] = S.best.v;
-            }
-            const unsigned rmask = __ballot_sync(0xffffffffu, reflective);
-            if (rmask) {
-                uint32_t rbase = 0;
-                if (lane == 0) rbase = atomicAdd(&cnt->n_refl, (unsigned)__popc(rmask));
-                rbase = __shfl_sync(0xffffffffu, rbase, 0);
-                if (reflective) q.refl_idx[rbase + (uint32_t)__popc(rmask & lt_mask)] = slot;
+                q.slot_tri[slot] = S.best.tri; q.slot_t[slot] = S.best.t; q.slot_u[slot] = S.best.u; q.slot_v[slot] = S.best.v;
+            } else {
+                q.slot_tri[slot] = -1;
+                super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, dir));
             }
         }
     }
@@ -172,16 +168,80 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
     if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
 }
 
-RT_DEV void queue_ray(const FrameView& fr, const QueueView& q, uint32_t i, V3& o, V3& d, HitRec& hr, uint32_t& pix)
+// Ordered stream compaction of the slot records into the hit queue.  A block owns kCompactSlots consecutive slots:
+// every thread counts the hits among its kCompactPerThread consecutive slots, a block-wide exclusive scan places them,
+// ONE atomic per block reserves the block's span of the queue.  Inside a span the entries keep slot order, so a warp
+// of k_shade / k_reflect that takes 32 consecutive entries gets neighbouring pixels.
+constexpr int kCompactThreads = 256;
+constexpr int kCompactPerThread = 8;
+constexpr int kCompactSlots = kCompactThreads * kCompactPerThread;
+
+__global__ void __launch_bounds__(kCompactThreads)
+k_compact(SceneView sc, QueueView q, ChunkCounters* cnt, uint32_t total, int any_reflective)
 {
-    pix = q.pix[i];
-    hr.tri = q.tri[i]; hr.t = q.t[i]; hr.u = q.u[i]; hr.v = q.v[i];
-    primary_ray(fr, (int)(pix % (uint32_t)fr.rw), (int)(pix / (uint32_t)fr.rw), o, d);
+    __shared__ uint32_t warp_hits[kCompactThreads / 32], warp_refl[kCompactThreads / 32];
+    __shared__ uint32_t span_hits, span_refl;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_blocks = (total + kCompactSlots - 1) / kCompactSlots;
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint32_t first = blk * kCompactSlots + threadIdx.x * kCompactPerThread;
+        uint32_t hits = 0, refl = 0;                         // bit j: slot first + j is a hit / a reflective hit
+#pragma unroll
+        for (int j = 0; j < kCompactPerThread; j++) {
+            const uint32_t slot = first + (uint32_t)j;
+            if (slot < total) {
+                const int32_t tri = q.slot_tri[slot];
+                if (tri >= 0) {
+                    hits |= 1u << j;
+                    if (any_reflective && load_material(sc, load_tri_shade(sc, tri).mat).reflection > 0.0f) refl |= 1u << j;
+                }
+            }
+        }
+        // exclusive scan of the per-thread counts over the block
+        uint32_t ch = (uint32_t)__popc(hits), cr = (uint32_t)__popc(refl);
+        uint32_t ih = ch, ir = cr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, ih, o), b = __shfl_up_sync(0xffffffffu, ir, o);
+            if ((int)lane >= o) { ih += a; ir += b; }
+        }
+        if (lane == 31) { warp_hits[warp] = ih; warp_refl[warp] = ir; }
+        __syncthreads();
+        uint32_t oh = ih - ch, orf = ir - cr;
+        for (unsigned w = 0; w < warp; w++) { oh += warp_hits[w]; orf += warp_refl[w]; }
+        if (threadIdx.x == kCompactThreads - 1) {
+            const uint32_t th = oh + ch, tr = orf + cr;
+            span_hits = th ? atomicAdd(&cnt->n_hits, th) : 0u;
+            span_refl = tr ? atomicAdd(&cnt->n_refl, tr) : 0u;
+        }
+        __syncthreads();
+        uint32_t ph = span_hits + oh, pr = span_refl + orf;
+#pragma unroll
+        for (int j = 0; j < kCompactPerThread; j++) {
+            if (hits & (1u << j)) {
+                q.hit_slot[ph] = first + (uint32_t)j;
+                if (refl & (1u << j)) q.refl_idx[pr++] = ph;
+                ph++;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The primary ray and hit record of hit-queue entry i.
+RT_DEV void queue_ray(const FrameView& fr, const WorkView& wk, const QueueView& q, uint32_t i, V3& o, V3& d, HitRec& hr, uint32_t& pix)
+{
+    const uint32_t slot = q.hit_slot[i];
+    int px, py;
+    slot_pixel(wk, fr, slot, px, py);
+    pix = (uint32_t)py * (uint32_t)fr.rw + (uint32_t)px;
+    hr.tri = q.slot_tri[slot]; hr.t = q.slot_t[slot]; hr.u = q.slot_u[slot]; hr.v = q.slot_v[slot];
+    primary_ray(fr, px, py, o, d);
 }
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
-k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
+k_reflect(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt)
 {
     // Tallies of a fan go to a per-entry record that k_shade sums up: the threads of a warp sit at different
     // recursion depths here, so no warp-level reduction is attempted in this kernel.
@@ -193,7 +253,7 @@ k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
         V3 o, d;
         HitRec hr;
         uint32_t pix;
-        queue_ray(fr, q, i, o, d, hr, pix);
+        queue_ray(fr, wk, q, i, o, d, hr, pix);
         Hit hit = complete_hit(sc, hr);
         V3 p;
         MatView m;
@@ -218,7 +278,7 @@ k_reflect(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt)
 // reflects) and stores it.
 template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
-k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
+k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -247,7 +307,7 @@ k_shade(SceneView sc, FrameView fr, QueueView q, ChunkCounters* cnt, uint32_t* s
                 entry = r;
                 V3 o, d;
                 HitRec hr;
-                queue_ray(fr, q, entry, o, d, hr, pix);
+                queue_ray(fr, wk, q, entry, o, d, hr, pix);
                 Hit hit = complete_hit(sc, hr);
                 if (fr.s.shading_method != RT_SHADING)
                     super[pix] = quantise_argb(shade_debug(sc, fr, hit));

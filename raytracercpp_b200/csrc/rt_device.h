@@ -340,16 +340,18 @@ RT_DEV void any_enter(AnyState& S, uint32_t link, uint32_t meta)
     else { S.mode = RT_MODE_CHILDREN; S.left = meta; }
 }
 
-RT_DEV void any_pop(const SceneView& sc, AnyState& S, const AnyStack& K)
+// Stack entries of the any-hit traversal are RANGES of sibling records that have not been tested yet
+// (first record << 4 | count - 1): a hit child is entered at once and its remaining siblings wait on the stack, so
+// they are never tested when an occluder turns up first.
+RT_DEV void any_pop(AnyState& S, const AnyStack& K)
 {
-    S.mode = RT_MODE_DONE;
-    while (S.sp > 0) {
-        const rt_f4 q3 = RT_LDG4(sc.recs + 4 * (size_t)K.r[--S.sp] + 3);
-        const uint32_t meta = f4_bits(q3.w);
-        if ((meta & ~RT_LEAF_BIT) == 0u) continue;
-        any_enter(S, f4_bits(q3.z), meta);
-        break;
-    }
+    if (S.sp > 0) {
+        const uint32_t e = K.r[--S.sp];
+        S.next = e >> 4;
+        S.left = (e & 15u) + 1u;
+        S.mode = RT_MODE_CHILDREN;
+    } else
+        S.mode = RT_MODE_DONE;
 }
 
 template <bool COUNT>
@@ -377,12 +379,17 @@ RT_DEV void any_child_step(const SceneView& sc, AnyState& S, AnyStack& K, TraceC
     const rt_f4* r = sc.recs + 4 * (size_t)S.next;
     rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
     if (COUNT) tc->vol_tests++;
-    if (slab_entry(c0, c1, c2, c3, S.sr, S.t_limit) != INFINITY) {
-        if (S.sp >= RT_STACK_SIZE) { tc->stack_overflow = 1; S.mode = RT_MODE_DONE; return; }
-        K.r[S.sp++] = S.next;
-    }
+    const bool hit = slab_entry(c0, c1, c2, c3, S.sr, S.t_limit) != INFINITY;
     ++S.next;
-    if (--S.left == 0u) any_pop(sc, S, K);
+    --S.left;
+    if (hit) {
+        if (S.left > 0u) {
+            if (S.sp >= RT_STACK_SIZE) { tc->stack_overflow = 1; S.mode = RT_MODE_DONE; return; }
+            K.r[S.sp++] = (S.next << 4) | (S.left - 1u);     // the untested siblings
+        }
+        any_enter(S, f4_bits(c3.z), f4_bits(c3.w));
+    } else if (S.left == 0u)
+        any_pop(S, K);
 }
 
 template <bool COUNT>
@@ -401,7 +408,7 @@ RT_DEV void any_triangle_step(const SceneView& sc, AnyState& S, const AnyStack& 
         }
     }
     ++S.next;
-    if (--S.left == 0u) any_pop(sc, S, K);
+    if (--S.left == 0u) any_pop(S, K);
 }
 
 template <bool COUNT>

@@ -58,7 +58,7 @@ struct Texture {
     int w = 0, h = 0, format = 0;
 };
 
-enum Stage { ST_PRIMARY = 0, ST_REFLECT, ST_SHADE, ST_RESOLVE, ST_COUNT };
+enum Stage { ST_PRIMARY = 0, ST_COMPACT, ST_REFLECT, ST_SHADE, ST_RESOLVE, ST_COUNT };
 
 struct TimedLaunch {
     int stage;
@@ -95,7 +95,7 @@ struct RtContext {
     bool camera_set = false;
 
     // per-frame work buffers
-    DevBuf<uint32_t> d_super, d_frame, d_tiles, q_pix, q_refl_idx;
+    DevBuf<uint32_t> d_super, d_frame, d_tiles, q_hit_slot, q_refl_idx;
     DevBuf<int32_t> q_tri;
     DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
     DevBuf<unsigned long long> q_refl_cnt;
@@ -314,7 +314,7 @@ void rt_destroy(RtContext* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
-    ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_pix.release(); ctx->q_refl_idx.release();
+    ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_hit_slot.release(); ctx->q_refl_idx.release();
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
@@ -404,6 +404,7 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     bi.nodes = flat.nodes; bi.leaves = flat.leaves; bi.empty_leaves = flat.empty_leaves; bi.interior = flat.interior;
     bi.max_depth_reached = flat.max_depth_reached; bi.max_leaf_size = flat.max_leaf_size;
     bi.child_records = flat.n_records;
+    if (flat.n_records >= (1ull << 28)) return fail(ctx, RT_ERR_INVALID, "scene needs %llu child records (limit 2^28)", (unsigned long long)flat.n_records);
     bi.device_bytes = (flat.recs.size() + flat.tris.size() + flat.shade.size()) * sizeof(F4) + flat.orig.size() * sizeof(int32_t);
     bi.build_ms = t1 - t0;
     bi.upload_ms = t2 - t1;
@@ -534,7 +535,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     RT_CUDA(ctx, ctx->d_tiles.ensure(tiles.size()));
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
-    RT_CUDA(ctx, ctx->q_pix.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
+    RT_CUDA(ctx, ctx->q_hit_slot.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
     RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
     if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, ctx->q_refl_cnt.ensure(3 * qcap)); }
     uint32_t* super = d_argb_out;
@@ -544,7 +545,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     }
     wk.tiles = ctx->d_tiles.p;
     QueueView q;
-    q.pix = ctx->q_pix.p; q.tri = ctx->q_tri.p; q.t = ctx->q_t.p; q.u = ctx->q_u.p; q.v = ctx->q_v.p;
+    q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
     q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
 
     cudaStream_t st = ctx->stream;
@@ -571,20 +572,27 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         ChunkCounters* cnt = ctx->d_counters.p + c;
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
-            if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0, ctx->tune);
-            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, reflect ? 1 : 0, ctx->tune);
+            if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            launches++;
+        }
+        {
+            ScopedTimer tm(ctx, ST_COMPACT);
+            const uint32_t slots = (wk.tile_end - wk.tile_begin) * (uint32_t)px_per_tile;
+            const uint32_t blocks = std::min<uint32_t>((slots + kCompactSlots - 1) / kCompactSlots, (uint32_t)ctx->sm_count * 8u);
+            k_compact<<<blocks, kCompactThreads, 0, st>>>(sc, q, cnt, slots, reflect ? 1 : 0);
             launches++;
         }
         if (reflect) {
             ScopedTimer tm(ctx, ST_REFLECT);
-            if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, q, cnt);
-            else k_reflect<false><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, q, cnt);
+            if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
+            else k_reflect<false><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
             launches++;
         }
         {
             ScopedTimer tm(ctx, ST_SHADE);
-            if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super, ctx->tune);
-            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, q, cnt, super, ctx->tune);
+            if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
         }
     }
@@ -627,6 +635,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         float ms = 0;
         cudaEventElapsedTime(&ms, tl.a, tl.b);
         if (tl.stage == ST_PRIMARY) rs.trace_primary_ms += ms;
+        else if (tl.stage == ST_COMPACT) rs.compact_ms += ms;
         else if (tl.stage == ST_REFLECT) rs.reflect_ms += ms;
         else if (tl.stage == ST_SHADE) rs.shade_ms += ms;
         else rs.resolve_ms += ms;
