@@ -98,7 +98,23 @@ RT_DEV bool slot_pixel(const WorkView& wk, const FrameView& fr, uint32_t slot, i
 struct Tuning {
     int32_t primary_refill;
     int32_t shade_refill;
+    int32_t tri_batch;        // run the triangle phase once this many lanes wait for it (or nothing else can run)
+    int32_t diag;             // diagonal-slab policy of slab_entry (0 always, 1 leaf records only, 2 never)
 };
+
+// One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
+// lane that sits in a leaf tests one triangle.  Triangle tests are postponed until `tri_batch` lanes want one.
+template <bool ANY, bool COUNT>
+RT_DEV void warp_step(const SceneView& sc, RayState& S, RayStack& K, TraceCounters* tc, bool alive, const Tuning& tune)
+{
+    const unsigned want_c = __ballot_sync(0xffffffffu, alive && S.mode == RT_MODE_CHILDREN);
+    const unsigned want_t = __ballot_sync(0xffffffffu, alive && S.mode == RT_MODE_TRIANGLES);
+    if (want_c != 0u && __popc(want_t) < tune.tri_batch) {
+        if (alive && S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc, tune.diag);
+    } else if (want_t != 0u) {
+        if (alive && S.mode == RT_MODE_TRIANGLES) ray_triangle_step<ANY, COUNT>(sc, S, K, tc);
+    }
+}
 
 // Ray generation + closest hit.  Persistent warps; every lane owns one ray at a time and steps it through the
 // traversal state machine (rt_device.h); lanes whose ray has ended are refilled from an atomic ray-slot counter with
@@ -113,8 +129,8 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
     const uint32_t pps = (uint32_t)wk.patches_per_side;
     const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);   // ray slots of the chunk
     TraceCounters tc = zero_counters();
-    ClosestState S;
-    ClosestStack K;
+    RayState S;
+    RayStack K;
     S.mode = RT_MODE_DONE;
     bool alive = false, exhausted = false;
     int px = 0, py = 0;
@@ -148,10 +164,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
         }
         // ---- a few single-test steps: slab tests for the lanes inside a cell, triangle tests for those inside a leaf
 #pragma unroll 1
-        for (int it = 0; it < kStepsPerCheck; it++) {
-            if (alive && S.mode == RT_MODE_CHILDREN) closest_child_step<COUNT>(sc, S, K, &tc);
-            if (alive && S.mode == RT_MODE_TRIANGLES) closest_triangle_step<COUNT>(sc, S, K, &tc);
-        }
+        for (int it = 0; it < kStepsPerCheck; it++) warp_step<false, COUNT>(sc, S, K, &tc, alive, tune);
         // ---- rays that have ended
         if (alive && S.mode == RT_MODE_DONE) {
             alive = false;
@@ -285,8 +298,8 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
     const uint32_t n = cnt->n_hits;
     TraceCounters tc = zero_counters();
     TraceCounters fan = zero_counters();                      // sums of the per-entry records of k_reflect
-    AnyState S;
-    AnyStack K;
+    RayState S;
+    RayStack K;
     S.mode = RT_MODE_DONE;
     S.occluded = false;
     bool alive = false, exhausted = false;
@@ -328,10 +341,7 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
             continue;
         }
 #pragma unroll 1
-        for (int it = 0; it < kStepsPerCheck; it++) {
-            if (alive && S.mode == RT_MODE_CHILDREN) any_child_step<COUNT>(sc, S, K, &tc);
-            if (alive && S.mode == RT_MODE_TRIANGLES) any_triangle_step<COUNT>(sc, S, K, &tc);
-        }
+        for (int it = 0; it < kStepsPerCheck; it++) warp_step<true, COUNT>(sc, S, K, &tc, alive, tune);
         if (alive && S.mode == RT_MODE_DONE) {
             alive = false;
             const MatView m = load_material(sc, mat);

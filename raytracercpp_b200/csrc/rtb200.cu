@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -107,7 +108,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{8, 12};
+    Tuning tune{16, 16, 8, 0};
     uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
@@ -339,6 +340,14 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
     case RT_OPT_REFILL_SHADE:
         if (value < 1 || value > 32) return fail(ctx, RT_ERR_INVALID, "refill threshold %lld outside [1,32]", (long long)value);
         (option == RT_OPT_REFILL_PRIMARY ? ctx->tune.primary_refill : ctx->tune.shade_refill) = (int32_t)value;
+        return RT_OK;
+    case RT_OPT_TRI_BATCH:
+        if (value < 1 || value > 32) return fail(ctx, RT_ERR_INVALID, "triangle batch %lld outside [1,32]", (long long)value);
+        ctx->tune.tri_batch = (int32_t)value;
+        return RT_OK;
+    case RT_OPT_DIAGONAL_SLABS:
+        if (value < 0 || value > 2) return fail(ctx, RT_ERR_INVALID, "diagonal slab policy %lld outside [0,2]", (long long)value);
+        ctx->tune.diag = (int32_t)value;
         return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
@@ -631,9 +640,11 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
     rs.kernel_launches = launches;
     cudaEventElapsedTime(&rs.device_ms, ev_begin, ev_end);
+    static const bool trace = getenv("RTB200_TRACE") != nullptr;       // per-launch CUDA-event times on stderr
     for (const TimedLaunch& tl : ctx->timed) {
         float ms = 0;
         cudaEventElapsedTime(&ms, tl.a, tl.b);
+        if (trace) fprintf(stderr, "[rtb200] %s %.3f ms\n", tl.stage == ST_PRIMARY ? "k_primary" : tl.stage == ST_COMPACT ? "k_compact" : tl.stage == ST_REFLECT ? "k_reflect" : tl.stage == ST_SHADE ? "k_shade" : "k_resolve", ms);
         if (tl.stage == ST_PRIMARY) rs.trace_primary_ms += ms;
         else if (tl.stage == ST_COMPACT) rs.compact_ms += ms;
         else if (tl.stage == ST_REFLECT) rs.reflect_ms += ms;
