@@ -152,8 +152,9 @@ enum {
     RT_OPT_REFILL_PRIMARY = 3,/* a warp of k_primary / k_shade fetches new rays once this many of its 32 lanes are idle  */
     RT_OPT_REFILL_SHADE = 4,  /* (default 16)                                                                          */
     RT_OPT_TRI_BATCH = 5,     /* a warp runs a round of triangle tests once this many lanes wait for one (default 8)   */
-    RT_OPT_DIAGONAL_SLABS = 6,/* 0 (default): every child test clips against all 7 slabs; 1: the 4 diagonal slabs only
-                                 for leaf records; 2: axis slabs only.  Pure pruning: results never depend on it       */
+    RT_OPT_PACKETS = 6,       /* 1 (default): primary and shadow rays are traced as 32-ray packets (one traversal per
+                                 warp); 0: every lane runs its own traversal state machine with lane refill.  Results do
+                                 not depend on it                                                                       */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.

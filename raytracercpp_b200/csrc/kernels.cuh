@@ -99,7 +99,7 @@ struct Tuning {
     int32_t primary_refill;
     int32_t shade_refill;
     int32_t tri_batch;        // run the triangle phase once this many lanes wait for it (or nothing else can run)
-    int32_t diag;             // diagonal-slab policy of slab_entry (0 always, 1 leaf records only, 2 never)
+    int32_t packets;          // 1: primary and shadow rays are traced as 32-ray packets (k_primary_packet / k_shade_packet)
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -110,7 +110,7 @@ RT_DEV void warp_step(const SceneView& sc, RayState& S, RayStack& K, TraceCounte
     const unsigned want_c = __ballot_sync(0xffffffffu, alive && S.mode == RT_MODE_CHILDREN);
     const unsigned want_t = __ballot_sync(0xffffffffu, alive && S.mode == RT_MODE_TRIANGLES);
     if (want_c != 0u && __popc(want_t) < tune.tri_batch) {
-        if (alive && S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc, tune.diag);
+        if (alive && S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc);
     } else if (want_t != 0u) {
         if (alive && S.mode == RT_MODE_TRIANGLES) ray_triangle_step<ANY, COUNT>(sc, S, K, tc);
     }
@@ -178,6 +178,145 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
         }
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 32-ray packets.  Primary rays of an 8x4 pixel block (2x1 final pixels at 16 spp) and the shadow rays of 32 neighbouring
+// hits walk almost the same cells, so the warp traverses ONCE for all of them: one shared stack per warp (shared
+// memory), every lane tests the same record / triangle for its own ray, a cell is entered if ANY lane hits it (ballot),
+// ordered by the smallest entry distance of the warp (shuffle-min), and dropped at pop time when no lane can still beat
+// its own best hit there.  Control flow is warp-uniform: no divergence inside the tests, one broadcast fetch per record.
+// Per ray the result is the same exact closest hit (or occlusion flag): a lane only ever sees extra candidates.
+// Incoherent rays (reflection fans, arbitrary batches) keep the per-ray state machine above.
+struct PacketStack {
+    float t[RT_STACK_SIZE];
+    uint32_t link[RT_STACK_SIZE];
+    uint32_t meta[RT_STACK_SIZE];
+};
+
+RT_DEV float warp_min(float x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
+// occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
+template <bool ANY, bool COUNT>
+RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o, V3 d, float t_max, V3 p, float dist2,
+                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    SlabRay sr;
+    slab_setup(o, d, sr);
+    const V3 md = -d;
+    best.tri = -1; best.t = -1.0f; best.u = 1.0f; best.v = 0.0f;
+    occluded = false;
+    uint32_t link, meta;
+    {
+        const rt_f4* r = sc.recs;
+        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+        if (COUNT && active) tc.vol_tests++;
+        const float tn = active ? slab_entry(q0, q1, q2, q3, sr, t_max) : INFINITY;
+        link = f4_bits(q3.z); meta = f4_bits(q3.w);
+        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return;
+    }
+    int sp = 0;
+    for (;;) {
+        if (!(meta & RT_LEAF_BIT)) {
+            // ---- one cell: every lane tests every child record for its own ray
+            const int base = sp;
+            const rt_f4* r = sc.recs + 4 * (size_t)link;
+            for (uint32_t k = 0; k < meta; k++, r += 4) {
+                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+                if (COUNT && active) tc.vol_tests++;
+                const float tn = active ? slab_entry(c0, c1, c2, c3, sr, t_max) : INFINITY;
+                if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
+                const float tmin = warp_min(tn);
+                if (sp >= RT_STACK_SIZE) { overflow = 1u; return; }
+                if (lane == 0) {                             // keep [base, sp) sorted by descending entry distance
+                    int j = sp;
+                    while (j > base && K.t[j - 1] < tmin) {
+                        K.t[j] = K.t[j - 1]; K.link[j] = K.link[j - 1]; K.meta[j] = K.meta[j - 1];
+                        --j;
+                    }
+                    K.t[j] = tmin; K.link[j] = f4_bits(c3.z); K.meta[j] = f4_bits(c3.w);
+                }
+                ++sp;
+            }
+            __syncwarp();
+        } else {
+            // ---- one leaf: every lane tests every triangle for its own ray
+            const uint32_t cnt = meta & ~RT_LEAF_BIT;
+            const rt_f4* tp = sc.tris + 3 * (size_t)link;
+            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
+                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+                if (COUNT && active) tc.tri_tests++;
+                float t, u, v;
+                if (active && tri_test(p0, p1, p2, o, md, t, u, v)) {
+                    if (ANY) {
+                        if (t > 0.0f) {
+                            V3 q = o + t * d;                    // renderer.cpp:351
+                            if (length2(p - q) < dist2) { occluded = true; active = false; }   // renderer.cpp:354
+                        }
+                    } else if (t < t_max || (t == t_max && sc.orig[link + i] < sc.orig[best.tri])) {
+                        t_max = t;
+                        best.tri = (int32_t)(link + i); best.t = t; best.u = u; best.v = v;
+                    }
+                }
+            }
+            if (ANY && __ballot_sync(0xffffffffu, active) == 0u) return;     // every ray of the packet is occluded
+        }
+        // ---- next cell: nearest first; skip entries no lane can still use
+        bool got = false;
+        while (sp > 0) {
+            --sp;
+            const float et = K.t[sp];
+            if (__ballot_sync(0xffffffffu, active && et <= t_max) == 0u) continue;
+            link = K.link[sp]; meta = K.meta[sp];
+            got = true;
+            break;
+        }
+        if (!got) return;
+    }
+}
+
+// Packet version of k_primary: a warp takes 32 consecutive ray slots (an 8x4 pixel block) per fetch.
+template <bool COUNT>
+__global__ void __launch_bounds__(kPrimaryThreads)
+k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+{
+    __shared__ PacketStack stacks[kPrimaryThreads / 32];
+    PacketStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t pps = (uint32_t)wk.patches_per_side;
+    const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);
+    TraceCounters tc = zero_counters();
+    unsigned overflow = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt->next_patch, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= total) break;
+        const uint32_t slot = base + lane;
+        int px = 0, py = 0;
+        const bool active = slot < total && slot_pixel(wk, fr, slot, px, py);
+        V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
+        if (active) primary_ray(fr, px, py, o, d);
+        HitRec best;
+        bool occ;
+        packet_trace<false, COUNT>(sc, K, active, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow);
+        __syncwarp();
+        if (slot < total) {
+            const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
+            q.slot_tri[slot] = hit ? best.tri : -1;
+            if (hit) { q.slot_t[slot] = best.t; q.slot_u[slot] = best.u; q.slot_v[slot] = best.v; }
+            else if (active) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+        }
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
 }
 
@@ -357,6 +496,81 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
         }
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
+    if ((threadIdx.x & 31u) == 0) {
+        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
+        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
+    }
+    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
+}
+
+// Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
+// them, traces their 32 shadow rays as one packet, composes and stores.
+template <bool COUNT>
+__global__ void __launch_bounds__(kQueueThreads)
+k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+{
+    __shared__ PacketStack stacks[kQueueThreads / 32];
+    PacketStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = cnt->n_hits;
+    TraceCounters tc = zero_counters();
+    TraceCounters fan = zero_counters();
+    unsigned overflow = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t entry = base + lane;
+        const bool valid = entry < n;
+        uint32_t pix = 0;
+        Col direct = col(0.0f), debug = col(0.0f);
+        int32_t mat = 0;
+        V3 p = v3(0, 0, 0), nrm = v3(0, 0, 1);
+        bool rt = false;
+        if (valid) {
+            V3 o, d;
+            HitRec hr;
+            queue_ray(fr, wk, q, entry, o, d, hr, pix);
+            Hit hit = complete_hit(sc, hr);
+            if (fr.s.shading_method != RT_SHADING) debug = shade_debug(sc, fr, hit);
+            else {
+                MatView m;
+                direct = shade_direct(sc, fr, o, d, hit, p, m);
+                mat = hit.mat;
+                nrm = hit.normal;
+                rt = true;
+            }
+        }
+        bool occluded = false;
+        if (fr.s.compute_shadows && fr.s.shading_method == RT_SHADING) {
+            const bool active = valid && rt;
+            const V3 so = p + 1.0e-4f * nrm;                                   // Renderer::EPSILON, renderer.h:23
+            const V3 sd = active ? normalize(fr.light - p) : v3(0, 0, 1);
+            const float dist2 = length2(p - fr.light);
+            HitRec unused;
+            packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded, tc, overflow);
+            __syncwarp();
+        }
+        if (valid) {
+            if (!rt) super[pix] = quantise_argb(debug);
+            else {
+                const MatView m = load_material(sc, mat);
+                Col refl = col(0.0f);
+                if (m.reflection > 0.0f) {
+                    refl = col(q.refl_rgb[3 * (size_t)entry], q.refl_rgb[3 * (size_t)entry + 1], q.refl_rgb[3 * (size_t)entry + 2]);
+                    const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
+                    fan.refl_rays += (uint32_t)packed;
+                    fan.refl_shadow_rays += (uint32_t)(packed >> 32);
+                    if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
+                }
+                super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
+            }
+        }
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
     const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
     if ((threadIdx.x & 31u) == 0) {

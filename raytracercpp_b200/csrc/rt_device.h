@@ -142,8 +142,9 @@ RT_DEV void slab_setup(V3 o, V3 d, SlabRay& sr)
 // behind the ray / starts beyond t_limit.  (The reference has no t_far<0 / t_near>best cull, bvh.h:79-105; both
 // are pure pruning: a triangle needs t >= 0 and must beat the best hit strictly, bvh.h:241.)  The three axis slabs
 // are tested first: most children of a visited cell are already missed there (measured on the 10 M-triangle scene:
-// 65 % of the child tests end at the axis slabs, and 97 % of those that pass them also pass the diagonal ones).
-RT_DEV float slab_entry(const rt_f4& q0, const rt_f4& q1, const rt_f4& q2, const rt_f4& q3, const SlabRay& sr, float t_limit, int diag)
+// 65 % of the child tests end at the axis slabs).  The diagonal slabs are not optional: skipping them on interior
+// records made the shadow pass 12x slower.
+RT_DEV float slab_entry(const rt_f4& q0, const rt_f4& q1, const rt_f4& q2, const rt_f4& q3, const SlabRay& sr, float t_limit)
 {
     float tn = -INFINITY, tf = INFINITY;
 #define RT_SLAB(i, NEAR, FAR)                                   \
@@ -158,9 +159,6 @@ RT_DEV float slab_entry(const rt_f4& q0, const rt_f4& q1, const rt_f4& q2, const
     RT_SLAB(2, q0.z, q2.y)
     const float lim = fminf(t_limit, tf) + 2.0f * sr.slack;
     if (!(tn <= lim) || tf + sr.slack < 0.0f) return INFINITY;
-    // `diag` (a tuning knob, results never depend on it): 0 = always clip against the four diagonal slabs too,
-    // 1 = only for leaf records (where a false positive costs triangle tests), 2 = never (axis slabs only).
-    if (diag == 2 || (diag == 1 && !(f4_bits(q3.w) & RT_LEAF_BIT))) return tn - sr.slack;
     RT_SLAB(3, q0.w, q2.z)
     RT_SLAB(4, q1.x, q2.w)
     RT_SLAB(5, q1.y, q3.x)
@@ -256,7 +254,7 @@ RT_DEV void ray_pop(RayState& S, const RayStack& K)
     }
 }
 
-// Root cell (bvh.h:232-233) + per-ray constants.  `diag`: see slab_entry.
+// Root cell (bvh.h:232-233) + per-ray constants.
 template <bool COUNT>
 RT_DEV void ray_begin(const SceneView& sc, V3 o, V3 d, float t_max, RayState& S, TraceCounters* tc)
 {
@@ -271,7 +269,7 @@ RT_DEV void ray_begin(const SceneView& sc, V3 o, V3 d, float t_max, RayState& S,
     rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
     if (COUNT) tc->vol_tests++;
     const uint32_t meta = f4_bits(q3.w);
-    if (slab_entry(q0, q1, q2, q3, S.sr, S.t_max, 0) != INFINITY && (meta & ~RT_LEAF_BIT) != 0u) ray_enter(S, f4_bits(q3.z), meta);
+    if (slab_entry(q0, q1, q2, q3, S.sr, S.t_max) != INFINITY && (meta & ~RT_LEAF_BIT) != 0u) ray_enter(S, f4_bits(q3.z), meta);
 }
 
 template <bool COUNT>
@@ -292,12 +290,12 @@ RT_DEV void any_begin(const SceneView& sc, V3 p, V3 n, V3 light, RayState& S, Tr
 }
 
 template <bool COUNT>
-RT_DEV void ray_child_step(const SceneView& sc, RayState& S, RayStack& K, TraceCounters* tc, int diag)
+RT_DEV void ray_child_step(const SceneView& sc, RayState& S, RayStack& K, TraceCounters* tc)
 {
     const rt_f4* r = sc.recs + 4 * (size_t)S.next;
     rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
     if (COUNT) tc->vol_tests++;
-    const float tn = slab_entry(c0, c1, c2, c3, S.sr, S.t_max, diag);
+    const float tn = slab_entry(c0, c1, c2, c3, S.sr, S.t_max);
     if (tn != INFINITY) {
         if (S.sp >= RT_STACK_SIZE) { tc->stack_overflow = 1; S.mode = RT_MODE_DONE; return; }
         int j = S.sp;                                       // keep [base, sp) sorted by descending entry distance
@@ -352,7 +350,7 @@ RT_DEV bool trace_closest(const SceneView& sc, V3 o, V3 d, HitRec& best, TraceCo
     RayStack K;
     closest_begin<COUNT>(sc, o, d, S, tc);
     while (S.mode != RT_MODE_DONE) {
-        if (S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc, 0);
+        if (S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc);
         else ray_triangle_step<false, COUNT>(sc, S, K, tc);
     }
     best = S.best;
@@ -366,7 +364,7 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
     RayStack K;
     any_begin<COUNT>(sc, p, n, light, S, tc);
     while (S.mode != RT_MODE_DONE) {
-        if (S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc, 0);
+        if (S.mode == RT_MODE_CHILDREN) ray_child_step<COUNT>(sc, S, K, tc);
         else ray_triangle_step<true, COUNT>(sc, S, K, tc);
     }
     return S.occluded;

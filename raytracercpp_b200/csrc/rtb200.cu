@@ -108,7 +108,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 0};
+    Tuning tune{16, 16, 8, 1};
     uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
@@ -345,9 +345,8 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         if (value < 1 || value > 32) return fail(ctx, RT_ERR_INVALID, "triangle batch %lld outside [1,32]", (long long)value);
         ctx->tune.tri_batch = (int32_t)value;
         return RT_OK;
-    case RT_OPT_DIAGONAL_SLABS:
-        if (value < 0 || value > 2) return fail(ctx, RT_ERR_INVALID, "diagonal slab policy %lld outside [0,2]", (long long)value);
-        ctx->tune.diag = (int32_t)value;
+    case RT_OPT_PACKETS:
+        ctx->tune.packets = value != 0;
         return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
@@ -568,20 +567,26 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
 
     const bool count = ctx->opt_count_work;
-    static int grids[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    static int grids[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
     if (!grids[count][0]) {
+        grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
+        grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
         grids[count][0] = grid_for(ctx, count ? (const void*)k_primary<true> : (const void*)k_primary<false>, kPrimaryThreads);
         grids[count][1] = grid_for(ctx, count ? (const void*)k_reflect<true> : (const void*)k_reflect<false>, kQueueThreads);
         grids[count][2] = grid_for(ctx, count ? (const void*)k_shade<true> : (const void*)k_shade<false>, kQueueThreads);
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
+    const int grid_pp = grids[count][3], grid_sp = grids[count][4];
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
         ChunkCounters* cnt = ctx->d_counters.p + c;
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
-            if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            if (ctx->tune.packets) {
+                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+            } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
         }
@@ -600,7 +605,10 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         }
         {
             ScopedTimer tm(ctx, ST_SHADE);
-            if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            if (ctx->tune.packets) {
+                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+            } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
         }

@@ -224,6 +224,7 @@ def test_work_counters_equal_the_host_emulation(cuda_lib, hostsim_lib, robot):
         kw, mats, tex = common.config_table(robot["materials"])[name]
         r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
         r.ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
+        r.ctx.set_option(api.RT_OPT_PACKETS, 0)            # per-ray scheduling does exactly the host emulation's tests
         r.ray_trace()
         a = r.last_stats().as_dict()
         r.close()
@@ -233,6 +234,24 @@ def test_work_counters_equal_the_host_emulation(cuda_lib, hostsim_lib, robot):
                   "reflection_volume_tests", "reflection_triangle_tests", "reflection_rays", "reflection_shadow_rays"):
             assert a[k] == b[k], (name, k, a[k], b[k])
         assert a["primary_volume_tests"] > 0
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_packet_and_single_ray_kernels_agree(cuda_lib, oracle, robot, name):
+    """RT_OPT_PACKETS only changes how primary / shadow rays are scheduled (32-ray packets vs one state machine per
+    lane): frames and ray counts are identical, and both equal the oracle's."""
+    kw, mats, tex = common.config_table(robot["materials"])[name]
+    out = []
+    for packets in (1, 0):
+        r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+        r.ctx.set_option(api.RT_OPT_PACKETS, packets)
+        r.ray_trace()
+        out.append((r.get_image().copy(), r.last_stats().as_dict()))
+        r.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
+        assert out[0][1][k] == out[1][1][k]
+    common.assert_image_close(out[0][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name)
 
 
 def test_cpp_adapter_example(cuda_lib, tmp_path):
