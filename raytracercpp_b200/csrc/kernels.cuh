@@ -190,6 +190,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
 // Per ray the result is the same exact closest hit (or occlusion flag): a lane only ever sees extra candidates.
 // Incoherent rays (reflection fans, arbitrary batches) keep the per-ray state machine above.
 struct PacketStack {
+    float4 stage[32];               // the cell (<= 8 records) or leaf chunk (<= 10 triangles) being tested, 512 bytes
     float t[RT_STACK_SIZE];
     uint32_t link[RT_STACK_SIZE];
     uint32_t meta[RT_STACK_SIZE];
@@ -226,11 +227,14 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
     int sp = 0;
     for (;;) {
         if (!(meta & RT_LEAF_BIT)) {
-            // ---- one cell: every lane tests every child record for its own ray
+            // ---- one cell: the warp fetches the cell's records with ONE coalesced 128-bit load per lane and stages
+            // them in shared memory (one memory latency per cell instead of one per child); then every lane tests every
+            // child record (broadcast LDS) for its own ray
             const int base = sp;
-            const rt_f4* r = sc.recs + 4 * (size_t)link;
-            for (uint32_t k = 0; k < meta; k++, r += 4) {
-                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+            if (lane < 4u * meta) K.stage[lane] = RT_LDG4(sc.recs + 4 * (size_t)link + lane);
+            __syncwarp();
+            for (uint32_t k = 0; k < meta; k++) {
+                const float4 c0 = K.stage[4 * k], c1 = K.stage[4 * k + 1], c2 = K.stage[4 * k + 2], c3 = K.stage[4 * k + 3];
                 if (COUNT && active) tc.vol_tests++;
                 const float tn = active ? slab_entry(c0, c1, c2, c3, sr, t_max) : INFINITY;
                 if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
@@ -248,24 +252,30 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
             }
             __syncwarp();
         } else {
-            // ---- one leaf: every lane tests every triangle for its own ray
+            // ---- one leaf: triangles staged the same way, 10 per round; every lane tests every triangle for its own ray
             const uint32_t cnt = meta & ~RT_LEAF_BIT;
-            const rt_f4* tp = sc.tris + 3 * (size_t)link;
-            for (uint32_t i = 0; i < cnt; i++, tp += 3) {
-                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-                if (COUNT && active) tc.tri_tests++;
-                float t, u, v;
-                if (active && tri_test(p0, p1, p2, o, md, t, u, v)) {
-                    if (ANY) {
-                        if (t > 0.0f) {
-                            V3 q = o + t * d;                    // renderer.cpp:351
-                            if (length2(p - q) < dist2) { occluded = true; active = false; }   // renderer.cpp:354
+            for (uint32_t first = 0; first < cnt; first += 10u) {
+                const uint32_t m = min(10u, cnt - first);
+                if (lane < 3u * m) K.stage[lane] = RT_LDG4(sc.tris + 3 * (size_t)(link + first) + lane);
+                __syncwarp();
+                for (uint32_t i = 0; i < m; i++) {
+                    const float4 p0 = K.stage[3 * i], p1 = K.stage[3 * i + 1], p2 = K.stage[3 * i + 2];
+                    if (COUNT && active) tc.tri_tests++;
+                    float t, u, v;
+                    if (active && tri_test(p0, p1, p2, o, md, t, u, v)) {
+                        const uint32_t tri = link + first + i;
+                        if (ANY) {
+                            if (t > 0.0f) {
+                                V3 q = o + t * d;                // renderer.cpp:351
+                                if (length2(p - q) < dist2) { occluded = true; active = false; }   // renderer.cpp:354
+                            }
+                        } else if (t < t_max || (t == t_max && sc.orig[tri] < sc.orig[best.tri])) {
+                            t_max = t;
+                            best.tri = (int32_t)tri; best.t = t; best.u = u; best.v = v;
                         }
-                    } else if (t < t_max || (t == t_max && sc.orig[link + i] < sc.orig[best.tri])) {
-                        t_max = t;
-                        best.tri = (int32_t)(link + i); best.t = t; best.u = u; best.v = v;
                     }
                 }
+                __syncwarp();
             }
             if (ANY && __ballot_sync(0xffffffffu, active) == 0u) return;     // every ray of the packet is occluded
         }
