@@ -248,6 +248,12 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
                     }
                     K.t[j] = tmin; K.link[j] = f4_bits(c3.z); K.meta[j] = f4_bits(c3.w);
                 }
+                // the pushed cell will be fetched when it is popped: start moving its first lines towards L1 now
+                if (lane < 2u) {
+                    const uint32_t cl = f4_bits(c3.z), cm = f4_bits(c3.w);
+                    const char* a = (cm & RT_LEAF_BIT) ? (const char*)(sc.tris + 3 * (size_t)cl) : (const char*)(sc.recs + 4 * (size_t)cl);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 256 * lane));
+                }
                 ++sp;
             }
             __syncwarp();
@@ -518,7 +524,7 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
 // Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
 // them, traces their 32 shadow rays as one packet, composes and stores.
 template <bool COUNT>
-__global__ void __launch_bounds__(kQueueThreads)
+__global__ void __launch_bounds__(kQueueThreads, 6)
 k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
 {
     __shared__ PacketStack stacks[kQueueThreads / 32];
