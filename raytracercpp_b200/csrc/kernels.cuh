@@ -30,8 +30,7 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int n_hits;
     unsigned int n_refl;
     unsigned int stack_overflow;
-    unsigned int slow_packets;       // diagnostics (RTB200_TRACE): shadow packets that were finished ray by ray
-    unsigned int pad1, pad2;
+    unsigned int pad0, pad1, pad2;
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
@@ -101,7 +100,6 @@ struct Tuning {
     int32_t shade_refill;
     int32_t tri_batch;        // run the triangle phase once this many lanes wait for it (or nothing else can run)
     int32_t packets;          // 1: primary and shadow rays are traced as 32-ray packets (k_primary_packet / k_shade_packet)
-    int32_t packet_rounds;    // a packet that needs more cell/leaf rounds than this is finished ray by ray (incoherent packet)
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -207,12 +205,9 @@ RT_DEV float warp_min(float x)
 
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
 // occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
-// Returns false when the packet used up `max_rounds` cell/leaf rounds without finishing: its rays do not share their
-// cells (grazing shadow rays along the terminator: 8000 rounds measured against a typical 50), and the caller finishes
-// the rays that are still active one by one with the per-ray state machine, which only visits each ray's own cells.
 template <bool ANY, bool COUNT>
-RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o, V3 d, float t_max, V3 p, float dist2,
-                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds)
+RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o, V3 d, float t_max, V3 p, float dist2,
+                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow)
 {
     const unsigned lane = threadIdx.x & 31u;
     SlabRay sr;
@@ -227,11 +222,10 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
         if (COUNT && active) tc.vol_tests++;
         const float tn = active ? slab_entry(q0, q1, q2, q3, sr, t_max) : INFINITY;
         link = f4_bits(q3.z); meta = f4_bits(q3.w);
-        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return true;
+        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return;
     }
     int sp = 0;
-    for (int round = 0;; round++) {
-        if (round >= max_rounds) return false;
+    for (;;) {
         if (!(meta & RT_LEAF_BIT)) {
             // ---- one cell: the warp fetches the cell's records with ONE coalesced 128-bit load per lane and stages
             // them in shared memory (one memory latency per cell instead of one per child); then every lane tests every
@@ -245,7 +239,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
                 const float tn = active ? slab_entry(c0, c1, c2, c3, sr, t_max) : INFINITY;
                 if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
                 const float tmin = warp_min(tn);
-                if (sp >= RT_STACK_SIZE) { overflow = 1u; return true; }
+                if (sp >= RT_STACK_SIZE) { overflow = 1u; return; }
                 if (lane == 0) {                             // keep [base, sp) sorted by descending entry distance
                     int j = sp;
                     while (j > base && K.t[j - 1] < tmin) {
@@ -289,7 +283,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
                 }
                 __syncwarp();
             }
-            if (ANY && __ballot_sync(0xffffffffu, active) == 0u) return true;   // every ray of the packet is occluded
+            if (ANY && __ballot_sync(0xffffffffu, active) == 0u) return;     // every ray of the packet is occluded
         }
         // ---- next cell: nearest first; skip entries no lane can still use
         bool got = false;
@@ -301,14 +295,14 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
             got = true;
             break;
         }
-        if (!got) return true;
+        if (!got) return;
     }
 }
 
 // Packet version of k_primary: a warp takes 32 consecutive ray slots (an 8x4 pixel block) per fetch.
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryThreads)
-k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
+k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
 {
     __shared__ PacketStack stacks[kPrimaryThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
@@ -329,10 +323,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
         if (active) primary_ray(fr, px, py, o, d);
         HitRec best;
         bool occ;
-        if (!packet_trace<false, COUNT>(sc, K, active, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.packet_rounds)) {
-            if (active) trace_closest<COUNT>(sc, o, d, best, &tc);             // incoherent packet: ray by ray
-            overflow |= tc.stack_overflow;
-        }
+        packet_trace<false, COUNT>(sc, K, active, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow);
         __syncwarp();
         if (slot < total) {
             const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
@@ -534,7 +525,7 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
 // them, traces their 32 shadow rays as one packet, composes and stores.
 template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads, 6)
-k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
+k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
 {
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
@@ -542,7 +533,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
     const uint32_t n = cnt->n_hits;
     TraceCounters tc = zero_counters();
     TraceCounters fan = zero_counters();
-    unsigned overflow = 0, slow_packets = 0;
+    unsigned overflow = 0;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
@@ -576,12 +567,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
             const V3 sd = active ? normalize(fr.light - p) : v3(0, 0, 1);
             const float dist2 = length2(p - fr.light);
             HitRec unused;
-            if (!packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded, tc, overflow,
-                                           tune.packet_rounds)) {
-                if (active && !occluded) occluded = trace_occluded<COUNT>(sc, p, nrm, fr.light, &tc);   // incoherent packet: ray by ray
-                overflow |= tc.stack_overflow;
-                ++slow_packets;
-            }
+            packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded, tc, overflow);
             __syncwarp();
         }
         if (valid) {
@@ -601,7 +587,6 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         }
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (lane == 0 && slow_packets) atomicAdd(&cnt->slow_packets, slow_packets);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
     const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
     if ((threadIdx.x & 31u) == 0) {

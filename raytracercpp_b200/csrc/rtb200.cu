@@ -108,7 +108,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, 384};
+    Tuning tune{16, 16, 8, 1};
     uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
@@ -348,10 +348,6 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
     case RT_OPT_PACKETS:
         ctx->tune.packets = value != 0;
         return RT_OK;
-    case RT_OPT_PACKET_ROUNDS:
-        if (value < 1 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet round budget %lld", (long long)value);
-        ctx->tune.packet_rounds = (int32_t)value;
-        return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -588,8 +584,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
             if (ctx->tune.packets) {
-                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
             } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
@@ -610,8 +606,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         {
             ScopedTimer tm(ctx, ST_SHADE);
             if (ctx->tune.packets) {
-                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
             } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
@@ -642,7 +638,6 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         rs.shadow_volume_tests += host_cnt[c].shadow_vol; rs.shadow_triangle_tests += host_cnt[c].shadow_tri;
         rs.reflection_volume_tests += host_cnt[c].refl_vol; rs.reflection_triangle_tests += host_cnt[c].refl_tri;
         overflow |= host_cnt[c].stack_overflow != 0;
-        if (getenv("RTB200_TRACE")) fprintf(stderr, "[rtb200] chunk %u: %u hits, %u shadow packets finished ray by ray\n", c, host_cnt[c].n_hits, host_cnt[c].slow_packets);
     }
     // primary rays = supersampled pixels of the owned tiles that lie inside the frame
     for (uint32_t tile : tiles) {

@@ -242,16 +242,15 @@ def test_packet_and_single_ray_kernels_agree(cuda_lib, oracle, robot, name):
     lane): frames and ray counts are identical, and both equal the oracle's."""
     kw, mats, tex = common.config_table(robot["materials"])[name]
     out = []
-    for packets, rounds in ((1, 384), (0, 384), (1, 3)):      # rounds = 3: nearly every packet falls back to ray-by-ray
+    for packets in (1, 0):
         r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
         r.ctx.set_option(api.RT_OPT_PACKETS, packets)
-        r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, rounds)
         r.ray_trace()
         out.append((r.get_image().copy(), r.last_stats().as_dict()))
         r.close()
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][0], out[2][0])
+    assert np.array_equal(out[0][0], out[1][0])
     for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
-        assert out[0][1][k] == out[1][1][k] == out[2][1][k]
+        assert out[0][1][k] == out[1][1][k]
     common.assert_image_close(out[0][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name)
 
 
