@@ -178,7 +178,7 @@ def run_ours(args, scene):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = api.load_library()
+    lib = api.load_library(args.lib)
     ctx = api.Context(local, lib)
     kw = scene["kw"]
     s = api.default_settings(lib, **kw)
@@ -189,6 +189,32 @@ def run_ours(args, scene):
         k, v = kv.split("=")
         ctx.set_option(int(k), int(v))
     ctx.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
+    ref_work = None
+    if not args.no_ref_work:
+        # Work of the REFERENCE-SHAPED traversal: the reference's own cells and leaves
+        # (RT_OPT_LEAF_SPLIT 0), one ordered early-exit traversal per ray (RT_OPT_PACKETS 0), instrumented kernels.
+        # Outside every timed region; the product tree is built afterwards.
+        ctx.set_option(api.RT_OPT_LEAF_SPLIT, 0)
+        ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
+        ctx.set_materials(scene["mats"])
+        ctx.set_light(LIGHT)
+        f0 = kw["ssaa_factor"]
+        ctx.set_camera(ctx.perspective_inverse(FOV, float(np.float32(kw["image_width"] * f0) / np.float32(kw["image_height"] * f0))),
+                       np.eye(4, dtype=np.float32), (0, 0, 0))
+        ctx.set_option(api.RT_OPT_PACKETS, 0)
+        ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
+        ref_frame = ShardedFrame(ctx, s, rank, world)
+        ref_work = ref_frame.render().as_dict()
+        del ref_frame
+        ctx.set_option(api.RT_OPT_COUNT_WORK, 0)
+        ctx.set_option(api.RT_OPT_PACKETS, 1)
+        ctx.set_option(api.RT_OPT_LEAF_SPLIT, args.leaf_split if args.leaf_split is not None else 8)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            ctx.set_option(int(k), int(v))
+        if rank == 0:
+            log(f"[ours] reference-shaped traversal: {ref_work['primary_volume_tests']} + {ref_work['shadow_volume_tests']} volume tests, "
+                f"{ref_work['primary_triangle_tests']} + {ref_work['shadow_triangle_tests']} triangle tests (primary + shadow)")
     info = ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
     if rank == 0:
         log(f"[ours] octree build {info['build_ms']:.0f} ms + upload {info['upload_ms']:.0f} ms, {info['child_records']} records, "
@@ -261,6 +287,13 @@ def run_ours(args, scene):
         dist.all_reduce(t, op=op)
         return float(t.item())
 
+    mine = torch.tensor([stage[k] / args.steps for k in ("k_primary", "k_compact", "k_shade", "k_reflect", "k_resolve")] + [dev_ms / args.steps],
+                        dtype=torch.float64, device="cuda")
+    per_rank = [mine.tolist()]
+    if world > 1:
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(x, 3) for x in t.tolist()] for t in allr]
     dev_ms = reduce(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
     e2e_ms = reduce(e2e_ms, dist.ReduceOp.MAX if world > 1 else None)
     rays_total = reduce(float(rays_rank), dist.ReduceOp.SUM if world > 1 else None)
@@ -273,15 +306,26 @@ def run_ours(args, scene):
         if peaks_file.exists():
             peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         dom = max(("k_primary", "k_shade", "k_reflect"), key=lambda k: stage[k])
-        vt = {"k_primary": (work.primary_volume_tests, work.primary_triangle_tests), "k_shade": (work.shadow_volume_tests, work.shadow_triangle_tests),
-              "k_reflect": (work.reflection_volume_tests, work.reflection_triangle_tests)}[dom]
-        dom_bytes = 56 * vt[0] + 36 * vt[1]                                       # per launch (one launch per step and chunk set)
+        keys = {"k_primary": ("primary_volume_tests", "primary_triangle_tests"), "k_shade": ("shadow_volume_tests", "shadow_triangle_tests"),
+                "k_reflect": ("reflection_volume_tests", "reflection_triangle_tests")}[dom]
+        own = work.as_dict()
+        src = ref_work if ref_work is not None else own
+        dom_bytes = 56 * src[keys[0]] + 36 * src[keys[1]]                         # per launch set (one per step)
+        own_bytes = 56 * own[keys[0]] + 36 * own[keys[1]]
         dom_ms = stage[dom] / args.steps
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"                                   # dram bytes per launch from the committed ncu --set full capture
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(scene["name"], {}).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_step": dom_ms,
-                    "definition": "56 B per 7-slab volume test + 36 B per triangle test performed by the kernel's traversal (rank 0's tiles), counted by the instrumented instantiation",
+                    "definition": ("56 B per 7-slab volume test + 36 B per triangle test of the REFERENCE-SHAPED traversal of the kernel's rays (rank 0's tiles): "
+                                   "the reference's own octree cells and leaves, one ordered early-exit traversal per ray, counted on the GPU by the "
+                                   "instrumented single-ray kernels (SURVEY.md 8(d))") if ref_work is not None else
+                                  "56 B per volume test + 36 B per triangle test performed by the kernel's own traversal (rank 0's tiles)",
+                    "kernel_traversal_bytes_per_launch": own_bytes,
                     "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
         out = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -292,6 +336,9 @@ def run_ours(args, scene):
             "gpu_launches": int(launches), "roofline": roofline,
             "work": {k: getattr(work, k) for k in ("primary_volume_tests", "primary_triangle_tests", "shadow_volume_tests", "shadow_triangle_tests",
                                                    "primary_hits")},
+            "reference_work": None if ref_work is None else {k: ref_work[k] for k in ("primary_volume_tests", "primary_triangle_tests",
+                                                                                      "shadow_volume_tests", "shadow_triangle_tests")},
+            "per_rank_stage_ms": per_rank,
             "bvh": {k: info[k] for k in ("nodes", "interior", "leaves", "empty_leaves", "max_leaf_size", "child_records", "device_bytes", "build_ms", "upload_ms")},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -316,7 +363,9 @@ def main():
     ap.add_argument("--workload", default="cfg4_sphere10M_4k_16spp", choices=list(WORKLOADS))
     ap.add_argument("--cpu-row-step", type=int, default=48, help="cpu_baseline sample: every n-th supersampled row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-work", action="store_true", help="skip the reference-shaped work count (roofline then uses the kernel's own tests)")
     ap.add_argument("--opt", action="append", default=[], help="library option override id=value (experiments), e.g. --opt 3=4")
+    ap.add_argument("--lib", default=None, help="another build of librtb200 (kernel A/B experiments)")
     ap.add_argument("--leaf-split", type=int, default=None, help="RT_OPT_LEAF_SPLIT override (experiments); default = library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -19,6 +19,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_UNSUPPORTED = 0, -1, -2
 RT_SHADING, RT_ABS_NORMALS_SHADING, RT_PASTEL_NORMALS_SHADING, RT_BARYCENTRIC_COORDINATES_SHADING, RT_VISUALIZE_AO = range(5)
 RT_TEX_AO, RT_TEX_DIFFUSE, RT_TEX_NORMAL, RT_TEX_ROUGHNESS, RT_TEX_SKYSPHERE = range(5)
 RT_OPT_COUNT_WORK, RT_OPT_CHUNK_PIXELS, RT_OPT_LEAF_SPLIT, RT_OPT_REFILL_PRIMARY, RT_OPT_REFILL_SHADE, RT_OPT_TRI_BATCH, RT_OPT_PACKETS = 0, 1, 2, 3, 4, 5, 6
+RT_OPT_PACKET_ROUNDS, RT_OPT_SHADE_REVERSE = 7, 8
 
 
 class RtError(RuntimeError):
@@ -133,9 +134,12 @@ def bind(lib: C.CDLL) -> C.CDLL:
 _LIB = None
 
 
-def load_library() -> C.CDLL:
-    """Opens raytracercpp_b200/librtb200.so (CUDA, sm_100a).  Raises if it has not been built."""
+def load_library(path=None) -> C.CDLL:
+    """Opens raytracercpp_b200/librtb200.so (CUDA, sm_100a).  Raises if it has not been built.  `path` names another
+    build of the same sources (kernel A/B experiments: python -m raytracercpp_b200.build --out ... -D...)."""
     global _LIB
+    if path is not None:
+        return bind(C.CDLL(str(path)))
     if _LIB is None:
         if not LIB_PATH.exists():
             raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -m raytracercpp_b200.build` (needs nvcc). "

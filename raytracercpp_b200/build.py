@@ -43,10 +43,10 @@ def up_to_date() -> bool:
     return all(p.stat().st_mtime <= t for p in SOURCES + HEADERS + [Path(__file__)])
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> Path:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, extra=(), out: Path | None = None) -> Path:
+    if out is None and not force and up_to_date():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
+    cmd = [nvcc(), *NVCC_FLAGS, *extra, "-o", str(out or LIB), *map(str, SOURCES)]
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,9 +54,12 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> Path:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode:
         raise RuntimeError("nvcc failed")
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else ())
-    print(LIB)
+    # extra -D... arguments and --out <file> build a variant of the same sources next to the product library
+    argv = sys.argv[1:]
+    out = Path(argv[argv.index("--out") + 1]) if "--out" in argv else None
+    extra = [a for a in argv if a.startswith("-D")] + (["-Xptxas", "-v"] if "--ptxas" in argv else [])
+    print(build(force="--force" in argv, verbose=True, extra=extra, out=out))

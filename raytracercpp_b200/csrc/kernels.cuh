@@ -22,7 +22,10 @@ namespace rtb {
 constexpr int kPatch = 8;            // a warp's work item is a kPatch x kPatch block of supersampled pixels (2 passes of 8x4)
 constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
-constexpr int kStepsPerCheck = 4;    // single-test steps between two refill / completion checks of a persistent warp
+constexpr int kStepsPerCheck = 4;
+#ifndef RTB_SHADE_MINB
+#define RTB_SHADE_MINB 6   /* resident CTAs per SM the compiler must allow for k_shade_packet (register bound) */
+#endif    // single-test steps between two refill / completion checks of a persistent warp
 
 struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int next_patch;         // next ray slot of k_primary
@@ -30,12 +33,35 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int n_hits;
     unsigned int n_refl;
     unsigned int stack_overflow;
-    unsigned int pad0, pad1, pad2;
+    unsigned int n_tail;             // hit-queue entries whose shadow packet ran out of rounds (k_shade_tail finishes them)
+    unsigned int next_tail;
+    unsigned int pad2;
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
     unsigned long long primary_vol, primary_tri, shadow_vol, shadow_tri, refl_vol, refl_tri;
+    // COUNT instantiations of the packet kernels only: cell/leaf rounds per packet, [0] primary, [1] shadow
+    unsigned int rounds_hist[2][16]; // bucket b: packets with 2^b <= rounds < 2^(b+1) (bucket 0 also holds 0 rounds)
+    unsigned int max_rounds[2];
+    unsigned long long max_packet_ns[2], sum_packet_ns[2];
 };
+
+RT_DEV unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// one lane per warp: tallies of one traced packet (diagnostics of the COUNT instantiations)
+RT_DEV void note_packet(ChunkCounters* cnt, int which, unsigned rounds, unsigned long long ns)
+{
+    const int b = rounds ? min(31 - __clz(rounds), 15) : 0;
+    atomicAdd(&cnt->rounds_hist[which][b], 1u);
+    atomicMax(&cnt->max_rounds[which], rounds);
+    atomicMax(&cnt->max_packet_ns[which], ns);
+    atomicAdd(&cnt->sum_packet_ns[which], ns);
+}
 
 RT_DEV void flush_work(TraceCounters& tc, unsigned long long* vol, unsigned long long* tri)
 {
@@ -69,6 +95,7 @@ struct QueueView {
     float* slot_v;
     // compacted by k_compact
     uint32_t* hit_slot;              // hit queue: ray slots of the hits
+    uint32_t* tail;                  // tail queue: hit-queue entries left to k_shade_tail
     uint32_t* refl_idx;              // reflection queue: indices into the hit queue
     float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
     unsigned long long* refl_cnt;    // 3 words per hit-queue entry, written by k_reflect: rays | shadow rays << 32, V, T
@@ -100,6 +127,8 @@ struct Tuning {
     int32_t shade_refill;
     int32_t tri_batch;        // run the triangle phase once this many lanes wait for it (or nothing else can run)
     int32_t packets;          // 1: primary and shadow rays are traced as 32-ray packets (k_primary_packet / k_shade_packet)
+    int32_t packet_rounds;    // a shadow packet that needs more cell/leaf rounds than this hands its rays to k_shade_tail (0: never)
+    int32_t shade_reverse;    // 1: k_shade_packet walks the hit queue back to front (experiments)
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -205,9 +234,14 @@ RT_DEV float warp_min(float x)
 
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
 // occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
+// Returns false when the packet used up `max_rounds` cell/leaf rounds without finishing (max_rounds 0: no limit); the
+// lanes whose `active` is still set then have no result yet.  A packet's rounds are one dependent chain (pop -> fetch
+// -> test -> push), about 1.4 us each, so a packet that needs thousands of them (measured: one shadow packet through
+// the pole of the 10 M-triangle sphere, 8 000 rounds = 11 ms of a 17 ms kernel) is better finished by warps that each
+// take ONE of its rays and spread the ray's tests over their lanes (coop_occluded).
 template <bool ANY, bool COUNT>
-RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o, V3 d, float t_max, V3 p, float dist2,
-                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow)
+RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
+                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds)
 {
     const unsigned lane = threadIdx.x & 31u;
     SlabRay sr;
@@ -222,10 +256,12 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
         if (COUNT && active) tc.vol_tests++;
         const float tn = active ? slab_entry(q0, q1, q2, q3, sr, t_max) : INFINITY;
         link = f4_bits(q3.z); meta = f4_bits(q3.w);
-        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return;
+        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return true;
     }
     int sp = 0;
     for (;;) {
+        if (max_rounds > 0 && (int)rounds >= max_rounds) return false;
+        ++rounds;
         if (!(meta & RT_LEAF_BIT)) {
             // ---- one cell: the warp fetches the cell's records with ONE coalesced 128-bit load per lane and stages
             // them in shared memory (one memory latency per cell instead of one per child); then every lane tests every
@@ -239,7 +275,7 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
                 const float tn = active ? slab_entry(c0, c1, c2, c3, sr, t_max) : INFINITY;
                 if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
                 const float tmin = warp_min(tn);
-                if (sp >= RT_STACK_SIZE) { overflow = 1u; return; }
+                if (sp >= RT_STACK_SIZE) { overflow = 1u; return true; }
                 if (lane == 0) {                             // keep [base, sp) sorted by descending entry distance
                     int j = sp;
                     while (j > base && K.t[j - 1] < tmin) {
@@ -247,12 +283,6 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
                         --j;
                     }
                     K.t[j] = tmin; K.link[j] = f4_bits(c3.z); K.meta[j] = f4_bits(c3.w);
-                }
-                // the pushed cell will be fetched when it is popped: start moving its first lines towards L1 now
-                if (lane < 2u) {
-                    const uint32_t cl = f4_bits(c3.z), cm = f4_bits(c3.w);
-                    const char* a = (cm & RT_LEAF_BIT) ? (const char*)(sc.tris + 3 * (size_t)cl) : (const char*)(sc.recs + 4 * (size_t)cl);
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 256 * lane));
                 }
                 ++sp;
             }
@@ -283,7 +313,7 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
                 }
                 __syncwarp();
             }
-            if (ANY && __ballot_sync(0xffffffffu, active) == 0u) return;     // every ray of the packet is occluded
+            if (ANY && __ballot_sync(0xffffffffu, active) == 0u) return true;   // every ray of the packet is occluded
         }
         // ---- next cell: nearest first; skip entries no lane can still use
         bool got = false;
@@ -295,14 +325,100 @@ RT_DEV void packet_trace(const SceneView& sc, PacketStack& K, bool active, V3 o,
             got = true;
             break;
         }
-        if (!got) return;
+        if (!got) return true;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One ray, one warp: Renderer::is_shadowed (renderer.cpp:340-402) with the ray's tests spread over the lanes.  Any-hit
+// needs no order, so the warp pops up to FOUR stack entries per round and gives each eight lanes: a lane tests one child
+// record of a cell or one triangle of a leaf (a leaf with more than eight triangles goes back on the stack minus the
+// eight being tested).  Children that are hit are pushed with one ballot + prefix count.  Same predicate and the same
+// conservative slab test as the packet and single-ray paths, so the same answer; only the schedule differs.
+constexpr int kCoopStack = 1024;
+
+struct CoopStack {
+    uint32_t link[kCoopStack];
+    uint32_t meta[kCoopStack];
+};
+
+template <bool COUNT>
+RT_DEV bool coop_occluded(const SceneView& sc, CoopStack& K, V3 p, V3 n, V3 light, TraceCounters& tc, unsigned& overflow)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const V3 o = p + 1.0e-4f * n;                                // Renderer::EPSILON, renderer.h:23
+    const V3 d = normalize(light - p);
+    const float dist2 = length2(p - light);
+    const float t_max = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
+    SlabRay sr;
+    slab_setup(o, d, sr);
+    const V3 md = -d;
+    int sp = 0;
+    {
+        const rt_f4* r = sc.recs;
+        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
+        if (COUNT && lane == 0) tc.vol_tests++;
+        const uint32_t meta = f4_bits(q3.w);
+        if (slab_entry(q0, q1, q2, q3, sr, t_max) == INFINITY || (meta & ~RT_LEAF_BIT) == 0u) return false;
+        if (lane == 0) { K.link[0] = f4_bits(q3.z); K.meta[0] = meta; }
+        sp = 1;
+        __syncwarp();
+    }
+    const int slot = (int)(lane >> 3), sub = (int)(lane & 7u);
+    while (sp > 0) {
+        const int take = min(sp, 4);
+        const bool have = slot < take;
+        uint32_t link = 0, meta = 0;
+        if (have) { link = K.link[sp - 1 - slot]; meta = K.meta[sp - 1 - slot]; }
+        __syncwarp();
+        sp -= take;
+        const bool leaf = (meta & RT_LEAF_BIT) != 0u;
+        const uint32_t cnt = meta & ~RT_LEAF_BIT;
+        // a long leaf: the rest of it goes back on the stack
+        const bool rem = have && leaf && cnt > 8u && sub == 0;
+        const unsigned rm = __ballot_sync(0xffffffffu, rem);
+        if (rem) {
+            const int pos = sp + __popc(rm & lt_mask);
+            K.link[pos] = link + 8u; K.meta[pos] = RT_LEAF_BIT | (cnt - 8u);
+        }
+        sp += __popc(rm);
+        bool push = false, occ = false;
+        uint32_t cl = 0, cm = 0;
+        if (have && (uint32_t)sub < min(cnt, 8u)) {
+            if (!leaf) {
+                const rt_f4* r = sc.recs + 4 * (size_t)(link + (uint32_t)sub);
+                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
+                if (COUNT) tc.vol_tests++;
+                if (slab_entry(c0, c1, c2, c3, sr, t_max) != INFINITY) { push = true; cl = f4_bits(c3.z); cm = f4_bits(c3.w); }
+            } else {
+                const rt_f4* tp = sc.tris + 3 * (size_t)(link + (uint32_t)sub);
+                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
+                if (COUNT) tc.tri_tests++;
+                float t, u, v;
+                if (tri_test(p0, p1, p2, o, md, t, u, v) && t > 0.0f) {
+                    V3 q = o + t * d;                            // renderer.cpp:351
+                    occ = length2(p - q) < dist2;                // renderer.cpp:354
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, occ) != 0u) return true;
+        const unsigned pm = __ballot_sync(0xffffffffu, push);
+        if (sp + __popc(pm) > kCoopStack) { overflow = 1u; return false; }
+        if (push) {
+            const int pos = sp + __popc(pm & lt_mask);
+            K.link[pos] = cl; K.meta[pos] = cm;
+        }
+        sp += __popc(pm);
+        __syncwarp();
+    }
+    return false;
 }
 
 // Packet version of k_primary: a warp takes 32 consecutive ray slots (an 8x4 pixel block) per fetch.
 template <bool COUNT>
 __global__ void __launch_bounds__(kPrimaryThreads)
-k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     __shared__ PacketStack stacks[kPrimaryThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
@@ -322,9 +438,12 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
         if (active) primary_ray(fr, px, py, o, d);
         HitRec best;
-        bool occ;
-        packet_trace<false, COUNT>(sc, K, active, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow);
+        bool occ, live = active;
+        unsigned rounds = 0;
+        const unsigned long long t0 = COUNT ? global_ns() : 0ull;
+        packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
         __syncwarp();
+        if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
         if (slot < total) {
             const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
             q.slot_tri[slot] = hit ? best.tri : -1;
@@ -524,8 +643,8 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
 // Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
 // them, traces their 32 shadow rays as one packet, composes and stores.
 template <bool COUNT>
-__global__ void __launch_bounds__(kQueueThreads, 6)
-k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+__global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
+k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
@@ -539,6 +658,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
+        if (tune.shade_reverse) base = ((n - 1u) / 32u) * 32u - base;
         const uint32_t entry = base + lane;
         const bool valid = entry < n;
         uint32_t pix = 0;
@@ -560,17 +680,30 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
                 rt = true;
             }
         }
-        bool occluded = false;
+        bool occluded = false, deferred = false;
         if (fr.s.compute_shadows && fr.s.shading_method == RT_SHADING) {
-            const bool active = valid && rt;
+            bool active = valid && rt;
             const V3 so = p + 1.0e-4f * nrm;                                   // Renderer::EPSILON, renderer.h:23
             const V3 sd = active ? normalize(fr.light - p) : v3(0, 0, 1);
             const float dist2 = length2(p - fr.light);
             HitRec unused;
-            packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded, tc, overflow);
+            unsigned rounds = 0;
+            const unsigned long long t0 = COUNT ? global_ns() : 0ull;
+            const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded,
+                                                            tc, overflow, tune.packet_rounds, rounds);
             __syncwarp();
+            if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
+            if (!finished) {
+                // out of rounds: the rays without an answer go to the tail queue (one atomic per warp)
+                deferred = active;
+                const unsigned dm = __ballot_sync(0xffffffffu, deferred);
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&cnt->n_tail, (unsigned)__popc(dm));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (deferred) q.tail[at + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = entry;
+            }
         }
-        if (valid) {
+        if (valid && !deferred) {
             if (!rt) super[pix] = quantise_argb(debug);
             else {
                 const MatView m = load_material(sc, mat);
@@ -584,6 +717,56 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
                 }
                 super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
             }
+        }
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
+    if ((threadIdx.x & 31u) == 0) {
+        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
+        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
+    }
+    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
+}
+
+// Finishes the hits whose shadow packet ran out of rounds: one warp per hit.  Every lane recomputes the (cheap) direct
+// shading of the hit, the warp answers the shadow query together (coop_occluded), lane 0 composes and stores.
+template <bool COUNT>
+__global__ void __launch_bounds__(kQueueThreads)
+k_shade_tail(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+{
+    __shared__ CoopStack stacks[kQueueThreads / 32];
+    CoopStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = cnt->n_tail;
+    TraceCounters tc = zero_counters();
+    TraceCounters fan = zero_counters();
+    unsigned overflow = 0;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&cnt->next_tail, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const uint32_t entry = q.tail[i];
+        V3 o, d, p;
+        HitRec hr;
+        uint32_t pix;
+        queue_ray(fr, wk, q, entry, o, d, hr, pix);
+        Hit hit = complete_hit(sc, hr);
+        MatView m;
+        const Col direct = shade_direct(sc, fr, o, d, hit, p, m);
+        const bool occluded = coop_occluded<COUNT>(sc, K, p, hit.normal, fr.light, tc, overflow);
+        __syncwarp();
+        if (lane == 0) {
+            Col refl = col(0.0f);
+            if (m.reflection > 0.0f) {
+                refl = col(q.refl_rgb[3 * (size_t)entry], q.refl_rgb[3 * (size_t)entry + 1], q.refl_rgb[3 * (size_t)entry + 2]);
+                const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
+                fan.refl_rays += (uint32_t)packed;
+                fan.refl_shadow_rays += (uint32_t)(packed >> 32);
+                if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
+            }
+            super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
         }
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);

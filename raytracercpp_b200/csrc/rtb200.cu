@@ -22,7 +22,7 @@ using namespace rtb;
 
 namespace {
 
-constexpr uint64_t kChunkPixels = 1ull << 25;     // supersampled pixels per wavefront chunk (bounds queue memory)
+constexpr uint64_t kChunkPixels = 1ull << 28;     // supersampled pixels per wavefront chunk (bounds queue memory: 20 B per pixel)
 constexpr int kMaxChunks = 256;
 
 thread_local std::string g_create_error;
@@ -96,7 +96,7 @@ struct RtContext {
     bool camera_set = false;
 
     // per-frame work buffers
-    DevBuf<uint32_t> d_super, d_frame, d_tiles, q_hit_slot, q_refl_idx;
+    DevBuf<uint32_t> d_super, d_frame, d_tiles, q_hit_slot, q_refl_idx, q_tail;
     DevBuf<int32_t> q_tri;
     DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
     DevBuf<unsigned long long> q_refl_cnt;
@@ -108,7 +108,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1};
+    Tuning tune{16, 16, 8, 1, 512, 0};
     uint64_t opt_chunk_pixels = kChunkPixels;
 
     // batch query staging
@@ -315,7 +315,7 @@ void rt_destroy(RtContext* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
-    ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_hit_slot.release(); ctx->q_refl_idx.release();
+    ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_tail.release();
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
@@ -348,6 +348,11 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
     case RT_OPT_PACKETS:
         ctx->tune.packets = value != 0;
         return RT_OK;
+    case RT_OPT_PACKET_ROUNDS:
+        if (value < 0 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet rounds %lld", (long long)value);
+        ctx->tune.packet_rounds = (int32_t)value;
+        return RT_OK;
+    case RT_OPT_SHADE_REVERSE: ctx->tune.shade_reverse = value != 0; return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -543,6 +548,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     RT_CUDA(ctx, ctx->d_tiles.ensure(tiles.size()));
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
+    const bool tail = ctx->tune.packets && ctx->tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
+    if (tail) RT_CUDA(ctx, ctx->q_tail.ensure(qcap));
     RT_CUDA(ctx, ctx->q_hit_slot.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
     RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
     if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, ctx->q_refl_cnt.ensure(3 * qcap)); }
@@ -554,6 +561,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     wk.tiles = ctx->d_tiles.p;
     QueueView q;
     q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
+    q.tail = ctx->q_tail.p;
     q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
 
     cudaStream_t st = ctx->stream;
@@ -567,16 +575,17 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
 
     const bool count = ctx->opt_count_work;
-    static int grids[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    static int grids[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
     if (!grids[count][0]) {
         grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
         grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
+        grids[count][5] = grid_for(ctx, count ? (const void*)k_shade_tail<true> : (const void*)k_shade_tail<false>, kQueueThreads);
         grids[count][0] = grid_for(ctx, count ? (const void*)k_primary<true> : (const void*)k_primary<false>, kPrimaryThreads);
         grids[count][1] = grid_for(ctx, count ? (const void*)k_reflect<true> : (const void*)k_reflect<false>, kQueueThreads);
         grids[count][2] = grid_for(ctx, count ? (const void*)k_shade<true> : (const void*)k_shade<false>, kQueueThreads);
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
-    const int grid_pp = grids[count][3], grid_sp = grids[count][4];
+    const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_tail = grids[count][5];
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
@@ -584,8 +593,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
             if (ctx->tune.packets) {
-                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
-                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
@@ -606,11 +615,16 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         {
             ScopedTimer tm(ctx, ST_SHADE);
             if (ctx->tune.packets) {
-                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
-                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
+            if (tail) {
+                if (count) k_shade_tail<true><<<grid_tail, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                else k_shade_tail<false><<<grid_tail, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                launches++;
+            }
         }
     }
     if (resolve && !tiles.empty()) {
@@ -658,6 +672,24 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         else if (tl.stage == ST_REFLECT) rs.reflect_ms += ms;
         else if (tl.stage == ST_SHADE) rs.shade_ms += ms;
         else rs.resolve_ms += ms;
+    }
+    if (trace && count && ctx->tune.packets) {
+        for (int w = 0; w < 2; w++) {
+            unsigned hist[16] = {0}, mx = 0;
+            unsigned long long mns = 0, sns = 0, packets = 0;
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                for (int b = 0; b < 16; b++) hist[b] += host_cnt[c].rounds_hist[w][b];
+                mx = std::max(mx, host_cnt[c].max_rounds[w]);
+                mns = std::max(mns, host_cnt[c].max_packet_ns[w]);
+                sns += host_cnt[c].sum_packet_ns[w];
+            }
+            for (int b = 0; b < 16; b++) packets += hist[b];
+            if (w) { unsigned long long nt = 0; for (uint32_t c = 0; c < n_chunks; c++) nt += host_cnt[c].n_tail; fprintf(stderr, "[rtb200] tail queue %llu rays\n", nt); }
+            fprintf(stderr, "[rtb200] %s packets %llu  max rounds %u  max packet %.3f ms  mean packet %.1f us  log2(rounds) histogram:",
+                    w ? "shadow" : "primary", packets, mx, mns * 1e-6, packets ? sns * 1e-3 / packets : 0.0);
+            for (int b = 0; b < 16; b++) fprintf(stderr, " %u", hist[b]);
+            fprintf(stderr, "\n");
+        }
     }
     if (stats) *stats = rs;
     if (overflow) return fail(ctx, RT_ERR_STATE, "traversal stack overflow (tree deeper than RT_MAX_TREE_DEPTH)");

@@ -254,6 +254,27 @@ def test_packet_and_single_ray_kernels_agree(cuda_lib, oracle, robot, name):
     common.assert_image_close(out[0][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_round_budget_and_tail_kernel_never_change_a_frame(cuda_lib, oracle, robot, name):
+    """RT_OPT_PACKET_ROUNDS hands the unanswered rays of long shadow packets to the one-ray-per-warp tail kernel
+    (k_shade_tail / coop_occluded).  With a budget of 1, 3 or 20 rounds nearly every shadow ray takes that route: the
+    frames must equal the unlimited-packet frame bit for bit, and the oracle's within the image tolerance."""
+    kw, mats, tex = common.config_table(robot["materials"])[name]
+    frames = {}
+    for rounds in (0, 1, 3, 20):
+        r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+        r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, rounds)
+        r.ray_trace()
+        frames[rounds] = (r.get_image().copy(), r.last_stats().as_dict())
+        r.close()
+    for rounds in (1, 3, 20):
+        assert np.array_equal(frames[rounds][0], frames[0][0]), rounds
+        for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
+            assert frames[rounds][1][k] == frames[0][1][k]
+        assert frames[rounds][1]["kernel_launches"] == frames[0][1]["kernel_launches"] + 1
+    common.assert_image_close(frames[1][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through the tail kernel")
+
+
 def test_cpp_adapter_example(cuda_lib, tmp_path):
     """include/rtb200_renderer.hpp (the reference's method names over the C ABI) compiles and renders."""
     exe = tmp_path / "adapter_example"
