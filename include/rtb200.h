@@ -157,7 +157,8 @@ enum {
                                  not depend on it                                                                       */
     RT_OPT_PACKET_ROUNDS = 7, /* a shadow packet that needs more cell/leaf rounds than this (default 512; 0 = no limit) hands
                                  its unanswered rays to the one-ray-per-warp tail kernel.  Results do not depend on it  */
-    RT_OPT_SHADE_REVERSE = 8, /* 1: shadow packets walk the hit queue back to front (scheduling experiment)            */
+    RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
+                                 written as misses without tracing.  Results do not depend on it                        */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.

@@ -22,6 +22,10 @@ namespace rtb {
 constexpr int kPatch = 8;            // a warp's work item is a kPatch x kPatch block of supersampled pixels (2 passes of 8x4)
 constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
+#ifndef RTB_FETCH
+#define RTB_FETCH 1
+#endif
+constexpr int kPrimaryFetch = RTB_FETCH;     // 32-ray packets a warp of k_primary_packet takes per atomic
 constexpr int kStepsPerCheck = 4;
 #ifndef RTB_SHADE_MINB
 #define RTB_SHADE_MINB 6   /* resident CTAs per SM the compiler must allow for k_shade_packet (register bound) */
@@ -85,6 +89,9 @@ struct WorkView {
     int32_t tiles_x;
     int32_t tile_px;                 // tile side in supersampled pixels (tile_size * factor)
     int32_t patches_per_side;        // ceil(tile_px / kPatch)
+    // Supersampled pixels outside [cull_x0, cull_x1] x [cull_y0, cull_y1] cannot hit the scene: the rectangle is the
+    // screen-space bound of the root cell's box (host side, rt_render_device).  The whole frame when no bound exists.
+    int32_t cull_x0, cull_y0, cull_x1, cull_y1;
 };
 
 struct QueueView {
@@ -128,7 +135,6 @@ struct Tuning {
     int32_t tri_batch;        // run the triangle phase once this many lanes wait for it (or nothing else can run)
     int32_t packets;          // 1: primary and shadow rays are traced as 32-ray packets (k_primary_packet / k_shade_packet)
     int32_t packet_rounds;    // a shadow packet that needs more cell/leaf rounds than this hands its rays to k_shade_tail (0: never)
-    int32_t shade_reverse;    // 1: k_shade_packet walks the hit queue back to front (experiments)
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -225,11 +231,48 @@ struct PacketStack {
     uint32_t meta[RT_STACK_SIZE];
 };
 
+// Minimum over the warp (no NaNs on this path): floats map to unsigned keys that sort the same way, so ONE redux.sync
+// replaces five dependent shuffle + min steps.
 RT_DEV float warp_min(float x)
 {
+#ifdef RTB_OLD_WARPMIN
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
     return x;
+#endif
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+    const uint32_t m = __reduce_min_sync(0xffffffffu, key);
+    return __uint_as_float(m ^ ((m & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+
+// slab_entry (rt_device.h) for packets, with a warp-uniform exit between the axis slabs and the diagonal slabs: the
+// rays of a packet mostly agree, so when NO lane survives the three axis slabs the record is dropped without the
+// divergent region a per-lane early return costs.  Same arithmetic, same conservative acceptance.
+RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4& q2, const float4& q3, const SlabRay& sr, float t_limit,
+                               bool active)
+{
+    float tn = -INFINITY, tf = INFINITY;
+#define RT_SLAB(i, NEAR, FAR)                                   \
+    {                                                           \
+        float a = RT_FMA((NEAR), sr.inv[i], -sr.c[i]);          \
+        float b = RT_FMA((FAR), sr.inv[i], -sr.c[i]);           \
+        tn = fmaxf(tn, fminf(a, b));                            \
+        tf = fminf(tf, fmaxf(a, b));                            \
+    }
+    RT_SLAB(0, q0.x, q1.w)
+    RT_SLAB(1, q0.y, q2.x)
+    RT_SLAB(2, q0.z, q2.y)
+    const float lim = fminf(t_limit, tf) + 2.0f * sr.slack;
+    const bool pass = active && (tn <= lim) && !(tf + sr.slack < 0.0f);
+    if (__ballot_sync(0xffffffffu, pass) == 0u) return INFINITY;
+    RT_SLAB(3, q0.w, q2.z)
+    RT_SLAB(4, q1.x, q2.w)
+    RT_SLAB(5, q1.y, q3.x)
+    RT_SLAB(6, q1.z, q3.y)
+#undef RT_SLAB
+    const bool ok = pass && (tn <= tf + 2.0f * sr.slack) && (tf + sr.slack >= 0.0f) && (tn - sr.slack <= t_limit);
+    return ok ? tn - sr.slack : INFINITY;
 }
 
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
@@ -272,7 +315,11 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
             for (uint32_t k = 0; k < meta; k++) {
                 const float4 c0 = K.stage[4 * k], c1 = K.stage[4 * k + 1], c2 = K.stage[4 * k + 2], c3 = K.stage[4 * k + 3];
                 if (COUNT && active) tc.vol_tests++;
+#ifdef RTB_OLD_SLAB
                 const float tn = active ? slab_entry(c0, c1, c2, c3, sr, t_max) : INFINITY;
+#else
+                const float tn = slab_entry_packet(c0, c1, c2, c3, sr, t_max, active);
+#endif
                 if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
                 const float tmin = warp_min(tn);
                 if (sp >= RT_STACK_SIZE) { overflow = 1u; return true; }
@@ -416,8 +463,13 @@ RT_DEV bool coop_occluded(const SceneView& sc, CoopStack& K, V3 p, V3 n, V3 ligh
 }
 
 // Packet version of k_primary: a warp takes 32 consecutive ray slots (an 8x4 pixel block) per fetch.
+#ifdef RTB_PRIMARY_MINB
+#define RTB_PRIMARY_BOUNDS __launch_bounds__(kPrimaryThreads, RTB_PRIMARY_MINB)
+#else
+#define RTB_PRIMARY_BOUNDS __launch_bounds__(kPrimaryThreads)
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(kPrimaryThreads)
+__global__ void RTB_PRIMARY_BOUNDS
 k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     __shared__ PacketStack stacks[kPrimaryThreads / 32];
@@ -427,28 +479,48 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
     const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);
     TraceCounters tc = zero_counters();
     unsigned overflow = 0;
+    // Work fetch: kPrimaryFetch packets per atomic, and the atomic for the NEXT batch is issued before the current
+    // batch is traced, so its round trip (11 % of the stall samples when it was waited for) is hidden.
+    uint32_t nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&cnt->next_patch, 32u * kPrimaryFetch);
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&cnt->next_patch, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= total) break;
-        const uint32_t slot = base + lane;
-        int px = 0, py = 0;
-        const bool active = slot < total && slot_pixel(wk, fr, slot, px, py);
-        V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
-        if (active) primary_ray(fr, px, py, o, d);
-        HitRec best;
-        bool occ, live = active;
-        unsigned rounds = 0;
-        const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-        packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
-        __syncwarp();
-        if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
-        if (slot < total) {
-            const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
-            q.slot_tri[slot] = hit ? best.tri : -1;
-            if (hit) { q.slot_t[slot] = best.t; q.slot_u[slot] = best.u; q.slot_v[slot] = best.v; }
-            else if (active) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+        const uint32_t first = __shfl_sync(0xffffffffu, nxt, 0);
+        if (first >= total) break;
+        if (lane == 0) nxt = atomicAdd(&cnt->next_patch, 32u * kPrimaryFetch);
+#pragma unroll 1
+        for (uint32_t b = 0; b < (uint32_t)kPrimaryFetch; b++) {
+            const uint32_t base = first + 32u * b;
+            if (base >= total) break;
+            const uint32_t slot = base + lane;
+            int px = 0, py = 0;
+            const bool active = slot < total && slot_pixel(wk, fr, slot, px, py);
+            V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
+            // a block that lies outside the screen-space bound of the scene misses without a ray being set up
+            const bool inside = active && px >= wk.cull_x0 && px <= wk.cull_x1 && py >= wk.cull_y0 && py <= wk.cull_y1;
+            if (__ballot_sync(0xffffffffu, inside) == 0u) {
+                if (slot < total) {
+                    q.slot_tri[slot] = -1;
+                    if (active) {
+                        if (fr.s.enable_skysphere) primary_ray(fr, px, py, o, d);
+                        super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+                    }
+                }
+                continue;
+            }
+            if (active) primary_ray(fr, px, py, o, d);
+            HitRec best;
+            bool occ, live = active;
+            unsigned rounds = 0;
+            const unsigned long long t0 = COUNT ? global_ns() : 0ull;
+            packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
+            __syncwarp();
+            if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
+            if (slot < total) {
+                const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
+                q.slot_tri[slot] = hit ? best.tri : -1;
+                if (hit) { q.slot_t[slot] = best.t; q.slot_u[slot] = best.u; q.slot_v[slot] = best.v; }
+                else if (active) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+            }
         }
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
@@ -658,7 +730,6 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
-        if (tune.shade_reverse) base = ((n - 1u) / 32u) * 32u - base;
         const uint32_t entry = base + lane;
         const bool valid = entry < n;
         uint32_t pix = 0;

@@ -108,8 +108,10 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, 512, 0};
+    Tuning tune{16, 16, 8, 1, 512};
     uint64_t opt_chunk_pixels = kChunkPixels;
+    bool opt_screen_cull = true;
+    float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
     DevBuf<float> b_a, b_b, b_t, b_u, b_v;
@@ -238,6 +240,74 @@ int grid_for(const RtContext* ctx, const void* kernel, int threads)
     return ctx->sm_count * per_sm;                 // persistent grid: a whole number of CTAs per SM
 }
 
+// Screen-space bound of the scene for the supersampled frame: every primary ray that can hit the root cell's box goes
+// through a pixel of [x0,x1] x [y0,y1].  The eight corners of the box are taken to camera space (inverse of
+// camera_to_world) and through the projection (inverse of proj_inv) in double precision; two pixels of margin cover
+// the float arithmetic of primary_ray.  No bound (whole frame) when a corner is not safely in front of the camera, when
+// the ray origin is not the projection centre (rt_set_camera accepts any position), or when a matrix is singular.
+bool invert4(const double a[16], double out[16])
+{
+    double m[4][8];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) { m[i][j] = a[4 * i + j]; m[i][4 + j] = i == j ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; c++) {
+        int piv = c;
+        for (int r = c + 1; r < 4; r++) if (std::fabs(m[r][c]) > std::fabs(m[piv][c])) piv = r;
+        if (std::fabs(m[piv][c]) < 1e-300) return false;
+        if (piv != c) for (int j = 0; j < 8; j++) std::swap(m[piv][j], m[c][j]);
+        const double d = 1.0 / m[c][c];
+        for (int j = 0; j < 8; j++) m[c][j] *= d;
+        for (int r = 0; r < 4; r++) {
+            if (r == c) continue;
+            const double f = m[r][c];
+            if (f != 0.0) for (int j = 0; j < 8; j++) m[r][j] -= f * m[c][j];
+        }
+    }
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[4 * i + j] = m[i][4 + j];
+    return true;
+}
+
+void screen_cull_rect(const RtContext* ctx, const FrameView& fr, WorkView& wk)
+{
+    wk.cull_x0 = 0; wk.cull_y0 = 0; wk.cull_x1 = fr.rw - 1; wk.cull_y1 = fr.rh - 1;
+    if (!ctx->opt_screen_cull) return;
+    if (ctx->n_tris == 0 || !(ctx->root_lo[0] <= ctx->root_hi[0])) { wk.cull_x0 = 1; wk.cull_x1 = 0; return; }   // nothing to hit
+    double c2w[16], pinv[16], w2c[16], proj[16];
+    for (int i = 0; i < 16; i++) { c2w[i] = (&ctx->cam_to_world.m[0][0])[i]; pinv[i] = (&ctx->proj_inv.m[0][0])[i]; }
+    if (!invert4(c2w, w2c) || !invert4(pinv, proj)) return;
+    // the ray origin must be the projection centre: camera_to_world * (0,0,0)
+    const double w0 = c2w[15];
+    if (!(std::fabs(w0) > 1e-12)) return;
+    const double centre[3] = {c2w[3] / w0, c2w[7] / w0, c2w[11] / w0};
+    const double pos[3] = {ctx->cam_pos.x, ctx->cam_pos.y, ctx->cam_pos.z};
+    double scale = 1.0;
+    for (int k = 0; k < 3; k++) scale = std::max(scale, std::fabs(centre[k]));
+    for (int k = 0; k < 3; k++) if (std::fabs(centre[k] - pos[k]) > 1e-5 * scale) return;
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int corner = 0; corner < 8; corner++) {
+        const double p[4] = {corner & 1 ? ctx->root_hi[0] : ctx->root_lo[0], corner & 2 ? ctx->root_hi[1] : ctx->root_lo[1],
+                             corner & 4 ? ctx->root_hi[2] : ctx->root_lo[2], 1.0};
+        double v[4], c[4];
+        for (int i = 0; i < 4; i++) v[i] = w2c[4 * i] * p[0] + w2c[4 * i + 1] * p[1] + w2c[4 * i + 2] * p[2] + w2c[4 * i + 3] * p[3];
+        if (!(std::fabs(v[3]) > 1e-12)) return;
+        for (int i = 0; i < 3; i++) v[i] /= v[3];
+        v[3] = 1.0;
+        for (int i = 0; i < 4; i++) c[i] = proj[4 * i] * v[0] + proj[4 * i + 1] * v[1] + proj[4 * i + 2] * v[2] + proj[4 * i + 3] * v[3];
+        // in front of the camera with margin: clip w is the view depth of a perspective projection
+        if (!(c[3] > 1e-3 * (1.0 + std::fabs(v[2])))) return;
+        const double nx = c[0] / c[3], ny = c[1] / c[3];
+        if (!std::isfinite(nx) || !std::isfinite(ny)) return;
+        xmin = std::min(xmin, nx); xmax = std::max(xmax, nx); ymin = std::min(ymin, ny); ymax = std::max(ymax, ny);
+    }
+    // the projection must map depth monotonically for "in front" to mean what it says: check with the near-plane point
+    // that primary_ray uses (NDC z = -1 -> a view-space point with negative z for the reference's Perspective)
+    const double px0 = (xmin + 1.0) * 0.5 * fr.rw, px1 = (xmax + 1.0) * 0.5 * fr.rw;
+    const double py0 = (ymin + 1.0) * 0.5 * fr.rh, py1 = (ymax + 1.0) * 0.5 * fr.rh;
+    const double lim = 1e9;
+    wk.cull_x0 = (int32_t)std::max(-lim, std::floor(px0) - 2.0); wk.cull_x1 = (int32_t)std::min(lim, std::ceil(px1) + 2.0);
+    wk.cull_y0 = (int32_t)std::max(-lim, std::floor(py0) - 2.0); wk.cull_y1 = (int32_t)std::min(lim, std::ceil(py1) + 2.0);
+}
+
 int ensure_stack(RtContext* ctx, const RtSettings* s)
 {
     // k_reflect recurses (trace_ray_secondary); every level holds two traversal stacks.
@@ -352,7 +422,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         if (value < 0 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet rounds %lld", (long long)value);
         ctx->tune.packet_rounds = (int32_t)value;
         return RT_OK;
-    case RT_OPT_SHADE_REVERSE: ctx->tune.shade_reverse = value != 0; return RT_OK;
+    case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -412,6 +482,11 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double t2 = now_ms();
     ctx->n_tris = (uint32_t)n;
+    {
+        const F4 *q0 = &flat.recs[0], *q1 = &flat.recs[1], *q2 = &flat.recs[2];
+        ctx->root_lo[0] = q0->x; ctx->root_lo[1] = q0->y; ctx->root_lo[2] = q0->z;
+        ctx->root_hi[0] = q1->w; ctx->root_hi[1] = q2->x; ctx->root_hi[2] = q2->y;
+    }
     RtBvhInfo& bi = ctx->info;
     bi.triangles = n;
     bi.nodes = flat.nodes; bi.leaves = flat.leaves; bi.empty_leaves = flat.empty_leaves; bi.interior = flat.interior;
@@ -535,10 +610,11 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     int tiles_x = 0;
     std::vector<uint32_t> tiles = owned_tiles(s, tile_size, tile_mod, tile_rem, &tiles_x);
-    WorkView wk;
+    WorkView wk = {};
     wk.tiles_x = tiles_x;
     wk.tile_px = tile_size * fr.factor;
     wk.patches_per_side = (wk.tile_px + kPatch - 1) / kPatch;
+    screen_cull_rect(ctx, fr, wk);
     const uint64_t px_per_tile = (uint64_t)wk.patches_per_side * wk.patches_per_side * kPatch * kPatch;
     uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, ctx->opt_chunk_pixels / px_per_tile);
     if ((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk > (size_t)kMaxChunks)
@@ -725,7 +801,7 @@ static int pack_unpack(RtContext* ctx, const RtSettings* s, const uint32_t* d_fr
     uint32_t* d_list = nullptr;
     RT_CUDA(ctx, cudaMallocAsync((void**)&d_list, tiles.size() * sizeof(uint32_t), ctx->stream));
     RT_CUDA(ctx, cudaMemcpyAsync(d_list, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    WorkView wk;
+    WorkView wk = {};
     memset(&wk, 0, sizeof(wk));
     wk.tiles = d_list;
     wk.tile_begin = 0;
@@ -842,7 +918,7 @@ int rt_resolve_ssaa(RtContext* ctx, const uint32_t* argb_in, int width, int heig
     cudaStream_t st = ctx->stream;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_super.p, argb_in, (size_t)width * height * 4, cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, st));
-    WorkView wk;
+    WorkView wk = {};
     memset(&wk, 0, sizeof(wk));
     wk.tiles = ctx->d_tiles.p; wk.tile_begin = 0; wk.tile_end = (uint32_t)tiles.size(); wk.tiles_x = tiles_x;
     k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_super.p, ctx->d_frame.p, wk, tile, factor, w, h);

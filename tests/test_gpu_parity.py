@@ -275,6 +275,34 @@ def test_round_budget_and_tail_kernel_never_change_a_frame(cuda_lib, oracle, rob
     common.assert_image_close(frames[1][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through the tail kernel")
 
 
+def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
+    """RT_OPT_SCREEN_CULL writes the primary packets outside the screen-space bound of the root box as misses without
+    tracing them.  Cameras in front of, beside, inside and behind the scene, with and without a skysphere: the frame
+    equals the one traced without the cull bit for bit, and the oracle's within tolerance."""
+    table = common.config_table(robot["materials"])
+    c, s = np.cos(0.9), np.sin(0.9)
+    cams = [None,
+            np.float32([[c, 0, s, 1.5], [0, 1, 0, -0.5], [-s, 0, c, -1.0], [0, 0, 0, 1]]),       # from the side, scene partly off-screen
+            np.float32([[1, 0, 0, 0.0], [0, 1, 0, -1.5], [0, 0, 1, -3.9], [0, 0, 0, 1]]),        # inside the scene's box
+            np.float32([[-1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, -1, 2.0], [0, 0, 0, 1]]),        # looking away: nothing on screen
+            np.float32([[1, 0, 0, 3.0], [0, 1, 0, 2.0], [0, 0, 1, 4.0], [0, 0, 0, 1]])]          # far away: a small bound
+    for name in ("cfg1", "cfg3"):
+        kw, mats, tex = table[name]
+        kw = dict(kw, image_width=160, image_height=90)
+        for i, cam in enumerate(cams):
+            frames = []
+            for cull in (1, 0):
+                r = common.product_renderer(cuda_lib, robot, kw, mats, tex, cam=cam)
+                r.ctx.set_option(api.RT_OPT_SCREEN_CULL, cull)
+                r.ray_trace()
+                frames.append((r.get_image().copy(), r.last_stats().as_dict()))
+                r.close()
+            assert np.array_equal(frames[0][0], frames[1][0]), (name, i)
+            for k in ("primary_rays", "primary_hits", "shadow_rays", "reflection_rays"):
+                assert frames[0][1][k] == frames[1][1][k], (name, i, k)
+            common.assert_image_close(frames[0][0], common.oracle_image(oracle, robot, kw, mats, tex, cam=cam), what=f"{name} camera {i}")
+
+
 def test_cpp_adapter_example(cuda_lib, tmp_path):
     """include/rtb200_renderer.hpp (the reference's method names over the C ABI) compiles and renders."""
     exe = tmp_path / "adapter_example"
