@@ -147,7 +147,7 @@ def run_reference(args, scene):
     out = {
         "impl": "reference", "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(scene, args.gpus),
+        "data": "synthetic", "config": workload_config(scene, args.gpus, args.tile),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,12 +155,12 @@ def run_reference(args, scene):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(scene, n_gpus):
+def workload_config(scene, n_gpus, tile=64):
     kw = scene["kw"]
     return {"workload": scene["name"], "triangles": int(len(scene["xyz9"])), "image": f"{kw['image_width']}x{kw['image_height']}",
             "spp": kw["ssaa_factor"] ** 2, "primary_rays": kw["image_width"] * kw["image_height"] * kw["ssaa_factor"] ** 2,
             "shadows": "1 point light, hard", "bvh": f"octree max_depth {kw['bvh_max_depth']} leaf {kw['bvh_leaf_object_count']} (reference GUI defaults)",
-            "fov": FOV, "parallelism": f"screen tiles 64x64 round-robin over {n_gpus} GPU(s), scene replicated",
+            "fov": FOV, "parallelism": f"screen tiles {tile}x{tile} round-robin over {n_gpus} GPU(s), scene replicated",
             "l2": "scene (~0.9 GB) and sample buffer (0.5 GB) exceed the 126 MB L2; no flush between steps"}
 
 
@@ -203,7 +203,7 @@ def run_ours(args, scene):
                        np.eye(4, dtype=np.float32), (0, 0, 0))
         ctx.set_option(api.RT_OPT_PACKETS, 0)
         ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
-        ref_frame = ShardedFrame(ctx, s, rank, world)
+        ref_frame = ShardedFrame(ctx, s, rank, world, tile_size=args.tile)
         ref_work = ref_frame.render().as_dict()
         del ref_frame
         ctx.set_option(api.RT_OPT_COUNT_WORK, 0)
@@ -228,7 +228,7 @@ def run_ours(args, scene):
     ctx.set_camera(proj_inv, cam, (0, 0, 0))
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    frame = ShardedFrame(ctx, s, rank, world)
+    frame = ShardedFrame(ctx, s, rank, world, tile_size=args.tile)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -259,7 +259,7 @@ def run_ours(args, scene):
             frame.gather()
             stage["k_primary"] += st.trace_primary_ms; stage["k_shade"] += st.shade_ms
             stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms; stage["k_compact"] += st.compact_ms
-            launches += st.kernel_launches + (world if world > 1 else 0)       # + pack and (world - 1) unpack kernels
+            launches += st.kernel_launches + (2 if world > 1 else 0)           # + the pack and unpack kernels of the gather
             rays_rank = st.total_rays
         ev1.record(stream)
         sync_all()
@@ -269,14 +269,18 @@ def run_ours(args, scene):
         # --- end to end: host framebuffer, copies inside the timed region
         host = torch.empty((kw["image_height"], kw["image_width"]), dtype=torch.int32).pin_memory()
         for _ in range(min(args.warmup, 2)):
-            frame.render(); frame.gather(); host.copy_(frame.frame, non_blocking=True); stream.synchronize()
+            frame.render(); frame.gather()
+            if rank == 0:
+                host.copy_(frame.frame, non_blocking=True)
+            stream.synchronize()
         sync_all()
         t_e2e = time.perf_counter()
         for _ in range(args.steps):
             ctx.set_camera(proj_inv, cam, (0, 0, 0))                             # the step's inputs: camera + settings (kernel arguments)
             frame.render()
             frame.gather()
-            host.copy_(frame.frame, non_blocking=True)
+            if rank == 0:                                                        # the caller's host framebuffer lives with rank 0
+                host.copy_(frame.frame, non_blocking=True)
             stream.synchronize()
         e2e_ms = (time.perf_counter() - t_e2e) * 1e3
 
@@ -330,7 +334,7 @@ def run_ours(args, scene):
         out = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(scene, world), "rays_per_step": int(rays_total), "clocks": clocks,
+            "config": workload_config(scene, world, args.tile), "rays_per_step": int(rays_total), "clocks": clocks,
             "e2e": {"value": rays_total / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * 64 + 12 + 12 + 100, "d2h_bytes_per_step": int(host.numel() * 4)},
             "gpu_launches": int(launches), "roofline": roofline,
@@ -365,6 +369,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-work", action="store_true", help="skip the reference-shaped work count (roofline then uses the kernel's own tests)")
     ap.add_argument("--opt", action="append", default=[], help="library option override id=value (experiments), e.g. --opt 3=4")
+    ap.add_argument("--tile", type=int, default=64, help="side of the screen tiles dealt over the ranks (final-resolution pixels)")
     ap.add_argument("--lib", default=None, help="another build of librtb200 (kernel A/B experiments)")
     ap.add_argument("--leaf-split", type=int, default=None, help="RT_OPT_LEAF_SPLIT override (experiments); default = library default")
     args = ap.parse_args()

@@ -159,6 +159,9 @@ enum {
                                  its unanswered rays to the one-ray-per-warp tail kernel.  Results do not depend on it  */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
+    RT_OPT_COST_ORDER = 9,    /* 1 (default 0): a frame walks its tiles in descending order of the SM cycles their packets took in
+                                 the previous frame rendered with the same tile list, so that long packets start first;
+                                 the first frame uses the list's own order.  Results do not depend on it                */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.
@@ -231,6 +234,12 @@ int rt_pack_tiles(RtContext* ctx, const RtSettings* settings, const uint32_t* d_
                   int tile_size, int tile_mod, int tile_rem);
 int rt_unpack_tiles(RtContext* ctx, const RtSettings* settings, uint32_t* d_frame, const uint32_t* d_staging,
                     int tile_size, int tile_mod, int tile_rem);
+
+/* The receiving side of the all-gather in one launch: d_gathered holds the staging buffers of all tile_mod shards
+ * back to back, each max_r(rt_tile_count(r)) * tile_size^2 words; the tiles of every shard but self_rem are
+ * written into d_frame (self_rem = -1: all shards).  Stream-ordered like rt_pack_tiles (no host synchronisation). */
+int rt_unpack_gathered(RtContext* ctx, const RtSettings* settings, uint32_t* d_frame, const uint32_t* d_gathered,
+                       int tile_size, int tile_mod, int self_rem);
 
 /* Batched bool BVH::intersect(const Ray&, HitInfo&) const -- bvh.h:307, bvh.cpp:68-71.
  * o3/d3: n*3 floats.  Outputs (any may be NULL): tri_id = index into the rt_set_triangles array or -1

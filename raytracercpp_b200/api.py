@@ -19,7 +19,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_UNSUPPORTED = 0, -1, -2
 RT_SHADING, RT_ABS_NORMALS_SHADING, RT_PASTEL_NORMALS_SHADING, RT_BARYCENTRIC_COORDINATES_SHADING, RT_VISUALIZE_AO = range(5)
 RT_TEX_AO, RT_TEX_DIFFUSE, RT_TEX_NORMAL, RT_TEX_ROUGHNESS, RT_TEX_SKYSPHERE = range(5)
 RT_OPT_COUNT_WORK, RT_OPT_CHUNK_PIXELS, RT_OPT_LEAF_SPLIT, RT_OPT_REFILL_PRIMARY, RT_OPT_REFILL_SHADE, RT_OPT_TRI_BATCH, RT_OPT_PACKETS = 0, 1, 2, 3, 4, 5, 6
-RT_OPT_PACKET_ROUNDS, RT_OPT_SCREEN_CULL = 7, 8
+RT_OPT_PACKET_ROUNDS, RT_OPT_SCREEN_CULL, RT_OPT_COST_ORDER = 7, 8, 9
 
 
 class RtError(RuntimeError):
@@ -116,6 +116,7 @@ ABI = {
     "rt_tile_count": (C.c_int, [C.POINTER(RtSettings), C.c_int, C.c_int, C.c_int]),
     "rt_pack_tiles": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rt_unpack_tiles": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "rt_unpack_gathered": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rt_intersect": (C.c_int, [C.c_void_p, FP, FP, C.c_size_t, IP, FP, FP, FP]),
     "rt_occluded": (C.c_int, [C.c_void_p, FP, FP, C.c_size_t, BP]),
     "rt_generate_primary_rays": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), FP, FP]),
@@ -295,6 +296,9 @@ class Context:
 
     def pack_tiles(self, settings, d_frame: int, d_staging: int, tile_size, tile_mod, tile_rem):
         self._check(self.lib.rt_pack_tiles(self.h, C.byref(settings), C.c_void_p(d_frame), C.c_void_p(d_staging), tile_size, tile_mod, tile_rem))
+
+    def unpack_gathered(self, settings, d_frame: int, d_gathered: int, tile_size, tile_mod, self_rem):
+        self._check(self.lib.rt_unpack_gathered(self.h, C.byref(settings), C.c_void_p(d_frame), C.c_void_p(d_gathered), tile_size, tile_mod, self_rem))
 
     def unpack_tiles(self, settings, d_frame: int, d_staging: int, tile_size, tile_mod, tile_rem):
         self._check(self.lib.rt_unpack_tiles(self.h, C.byref(settings), C.c_void_p(d_frame), C.c_void_p(d_staging), tile_size, tile_mod, tile_rem))

@@ -39,7 +39,7 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int stack_overflow;
     unsigned int n_tail;             // hit-queue entries whose shadow packet ran out of rounds (k_shade_tail finishes them)
     unsigned int next_tail;
-    unsigned int pad2;
+    unsigned int cont_used;          // entries of the continuation buffer handed out
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
@@ -92,7 +92,18 @@ struct WorkView {
     // Supersampled pixels outside [cull_x0, cull_x1] x [cull_y0, cull_y1] cannot hit the scene: the rectangle is the
     // screen-space bound of the root cell's box (host side, rt_render_device).  The whole frame when no bound exists.
     int32_t cull_x0, cull_y0, cull_x1, cull_y1;
+    // Per position in `tiles` (may be null): SM cycles spent by the packets of the tile, accumulated with one atomic per
+    // traced packet; the host orders the next frame's tiles by it (rt_render_device).
+    unsigned long long* tile_cost;
 };
+
+RT_DEV void note_tile_cost(const WorkView& wk, uint32_t slot, long long t0)
+{
+    if (wk.tile_cost && (threadIdx.x & 31u) == 0) {
+        const uint32_t pps = (uint32_t)wk.patches_per_side;
+        atomicAdd(&wk.tile_cost[wk.tile_begin + slot / (pps * pps * (uint32_t)(kPatch * kPatch))], (unsigned long long)(clock64() - t0));
+    }
+}
 
 struct QueueView {
     // dense, one per ray slot of the chunk (slot = position in patch order, see slot_pixel)
@@ -102,7 +113,12 @@ struct QueueView {
     float* slot_v;
     // compacted by k_compact
     uint32_t* hit_slot;              // hit queue: ray slots of the hits
-    uint32_t* tail;                  // tail queue: hit-queue entries left to k_shade_tail
+    uint32_t* tail;                  // tail queue: hit-queue entries left to k_shade_tail ...
+    uint32_t* tail_off;              // ... and where in cont_* the unvisited cells of the entry's packet start / how many
+    uint32_t* tail_cnt;
+    uint32_t* cont_link;             // continuation buffer: the stacks of the packets that ran out of rounds
+    uint32_t* cont_meta;
+    uint32_t cont_capacity;
     uint32_t* refl_idx;              // reflection queue: indices into the hit queue
     float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
     unsigned long long* refl_cnt;    // 3 words per hit-queue entry, written by k_reflect: rays | shadow rays << 32, V, T
@@ -225,6 +241,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
 // Per ray the result is the same exact closest hit (or occlusion flag): a lane only ever sees extra candidates.
 // Incoherent rays (reflection fans, arbitrary batches) keep the per-ray state machine above.
 struct PacketStack {
+    int saved;                      // entries [0, saved) are the unvisited cells of a packet that ran out of rounds
     float4 stage[32];               // the cell (<= 8 records) or leaf chunk (<= 10 triangles) being tested, 512 bytes
     float t[RT_STACK_SIZE];
     uint32_t link[RT_STACK_SIZE];
@@ -278,10 +295,12 @@ RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4&
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
 // occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
 // Returns false when the packet used up `max_rounds` cell/leaf rounds without finishing (max_rounds 0: no limit); the
-// lanes whose `active` is still set then have no result yet.  A packet's rounds are one dependent chain (pop -> fetch
-// -> test -> push), about 1.4 us each, so a packet that needs thousands of them (measured: one shadow packet through
-// the pole of the 10 M-triangle sphere, 8 000 rounds = 11 ms of a 17 ms kernel) is better finished by warps that each
-// take ONE of its rays and spread the ray's tests over their lanes (coop_occluded).
+// lanes whose `active` is still set then have no result yet, and K.link/meta[0, K.saved) are the cells the packet has
+// not visited (for each of those lanes a superset of the cells it still has to visit).  A packet's rounds are one
+// dependent chain (pop -> fetch -> test -> push), 1-2 us each, so a packet that needs thousands of them (measured: one
+// shadow packet through the pole of the 10 M-triangle sphere, 8 000 rounds = 11 ms of a 17 ms kernel) is better
+// finished by warps that each take ONE of its rays, start from those cells, and spread the ray's tests over their
+// lanes (coop_occluded).
 template <bool ANY, bool COUNT>
 RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
                          HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds)
@@ -303,7 +322,11 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
     }
     int sp = 0;
     for (;;) {
-        if (max_rounds > 0 && (int)rounds >= max_rounds) return false;
+        if (max_rounds > 0 && (int)rounds >= max_rounds && sp < RT_STACK_SIZE) {
+            if (lane == 0) { K.t[sp] = 0.0f; K.link[sp] = link; K.meta[sp] = meta; K.saved = sp + 1; }
+            __syncwarp();
+            return false;
+        }
         ++rounds;
         if (!(meta & RT_LEAF_BIT)) {
             // ---- one cell: the warp fetches the cell's records with ONE coalesced 128-bit load per lane and stages
@@ -389,8 +412,10 @@ struct CoopStack {
     uint32_t meta[kCoopStack];
 };
 
+// The traversal starts from `n_start` cells at cont_link/cont_meta (the unvisited cells of the ray's packet).
 template <bool COUNT>
-RT_DEV bool coop_occluded(const SceneView& sc, CoopStack& K, V3 p, V3 n, V3 light, TraceCounters& tc, unsigned& overflow)
+RT_DEV bool coop_occluded(const SceneView& sc, CoopStack& K, V3 p, V3 n, V3 light, const uint32_t* cont_link, const uint32_t* cont_meta,
+                          uint32_t n_start, TraceCounters& tc, unsigned& overflow)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -401,17 +426,9 @@ RT_DEV bool coop_occluded(const SceneView& sc, CoopStack& K, V3 p, V3 n, V3 ligh
     SlabRay sr;
     slab_setup(o, d, sr);
     const V3 md = -d;
-    int sp = 0;
-    {
-        const rt_f4* r = sc.recs;
-        rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
-        if (COUNT && lane == 0) tc.vol_tests++;
-        const uint32_t meta = f4_bits(q3.w);
-        if (slab_entry(q0, q1, q2, q3, sr, t_max) == INFINITY || (meta & ~RT_LEAF_BIT) == 0u) return false;
-        if (lane == 0) { K.link[0] = f4_bits(q3.z); K.meta[0] = meta; }
-        sp = 1;
-        __syncwarp();
-    }
+    int sp = (int)n_start;
+    for (uint32_t i = lane; i < n_start; i += 32u) { K.link[i] = cont_link[i]; K.meta[i] = cont_meta[i]; }
+    __syncwarp();
     const int slot = (int)(lane >> 3), sub = (int)(lane & 7u);
     while (sp > 0) {
         const int take = min(sp, 4);
@@ -507,6 +524,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
                 }
                 continue;
             }
+            const long long c0 = clock64();
             if (active) primary_ray(fr, px, py, o, d);
             HitRec best;
             bool occ, live = active;
@@ -514,6 +532,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
             packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
             __syncwarp();
+            note_tile_cost(wk, base, c0);
             if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
             if (slot < total) {
                 const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
@@ -730,6 +749,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
+        const long long c0 = clock64();
         const uint32_t entry = base + lane;
         const bool valid = entry < n;
         uint32_t pix = 0;
@@ -765,13 +785,32 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
             if (!finished) {
-                // out of rounds: the rays without an answer go to the tail queue (one atomic per warp)
-                deferred = active;
-                const unsigned dm = __ballot_sync(0xffffffffu, deferred);
-                uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(&cnt->n_tail, (unsigned)__popc(dm));
+                // Out of rounds: the packet's unvisited cells go to the continuation buffer and the rays without an
+                // answer to the tail queue (two atomics per warp).  No room left there: finish the packet here.
+                const uint32_t n_cont = (uint32_t)K.saved;
+                const unsigned dm = __ballot_sync(0xffffffffu, active);
+                uint32_t off = 0, at = 0;
+                if (lane == 0) {
+                    off = atomicAdd(&cnt->cont_used, n_cont);
+                    if (off + n_cont <= q.cont_capacity) at = atomicAdd(&cnt->n_tail, (unsigned)__popc(dm));
+                }
+                off = __shfl_sync(0xffffffffu, off, 0);
                 at = __shfl_sync(0xffffffffu, at, 0);
-                if (deferred) q.tail[at + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = entry;
+                if (off + n_cont <= q.cont_capacity) {
+                    for (uint32_t i = lane; i < n_cont; i += 32u) { q.cont_link[off + i] = K.link[i]; q.cont_meta[off + i] = K.meta[i]; }
+                    deferred = active;
+                    if (deferred) {
+                        const uint32_t at_me = at + (uint32_t)__popc(dm & ((1u << lane) - 1u));
+                        q.tail[at_me] = entry; q.tail_off[at_me] = off; q.tail_cnt[at_me] = n_cont;
+                    }
+                    __syncwarp();
+                } else {
+                    const bool before = occluded;
+                    packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded, tc, overflow, 0,
+                                              rounds);
+                    occluded = occluded || before;
+                    __syncwarp();
+                }
             }
         }
         if (valid && !deferred) {
@@ -789,6 +828,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
                 super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
             }
         }
+        if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[base], c0);
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
@@ -819,6 +859,7 @@ k_shade_tail(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
         const uint32_t entry = q.tail[i];
+        const long long c0 = clock64();
         V3 o, d, p;
         HitRec hr;
         uint32_t pix;
@@ -826,7 +867,8 @@ k_shade_tail(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters
         Hit hit = complete_hit(sc, hr);
         MatView m;
         const Col direct = shade_direct(sc, fr, o, d, hit, p, m);
-        const bool occluded = coop_occluded<COUNT>(sc, K, p, hit.normal, fr.light, tc, overflow);
+        const uint32_t off = q.tail_off[i];
+        const bool occluded = coop_occluded<COUNT>(sc, K, p, hit.normal, fr.light, q.cont_link + off, q.cont_meta + off, q.tail_cnt[i], tc, overflow);
         __syncwarp();
         if (lane == 0) {
             Col refl = col(0.0f);
@@ -839,6 +881,7 @@ k_shade_tail(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters
             }
             super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
         }
+        if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[entry], c0);
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
@@ -896,6 +939,26 @@ __global__ void k_pack_tiles(const uint32_t* frame, uint32_t* staging, WorkView 
         }
         if (unpack) frame_out[(size_t)y * width + x] = staging[g];
         else staging[g] = frame[(size_t)y * width + x];
+    }
+}
+
+// The other half of the gather in ONE launch: `gathered` holds the staging buffers of all `mod` shards back to back
+// (per_shard tiles each, padded), `lists` their tile indices (0xffffffff = padding).  Tiles of shard `self` are skipped
+// (they are already in the frame).
+__global__ void k_unpack_gathered(const uint32_t* gathered, uint32_t* frame, const uint32_t* lists, uint32_t per_shard, int mod, int self,
+                                  int tiles_x, int tile_size, int width, int height)
+{
+    const uint32_t per_tile = (uint32_t)tile_size * (uint32_t)tile_size;
+    const uint64_t total = (uint64_t)per_shard * (uint64_t)mod * per_tile;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t slot = (uint32_t)(g / per_tile);                  // = shard * per_shard + tile position
+        if ((int)(slot / per_shard) == self) continue;
+        const uint32_t tile = lists[slot];
+        if (tile == 0xffffffffu) continue;
+        const uint32_t in = (uint32_t)(g % per_tile);
+        const int x = (int)(tile % (uint32_t)tiles_x) * tile_size + (int)(in % (uint32_t)tile_size);
+        const int y = (int)(tile / (uint32_t)tiles_x) * tile_size + (int)(in / (uint32_t)tile_size);
+        if (x < width && y < height) frame[(size_t)y * width + x] = gathered[g];
     }
 }
 

@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -66,6 +68,21 @@ struct TimedLaunch {
     cudaEvent_t a, b;
 };
 
+// Device copy of a shard's tile list (owned_tiles), uploaded once per (frame size, tile size, shard) and kept.
+struct TileList {
+    uint32_t* d = nullptr;
+    uint32_t count = 0;
+    int tiles_x = 0;
+    std::vector<uint32_t> host;
+    // cost-ordered rendering (RT_OPT_COST_ORDER): SM cycles the packets of each tile took in the last frame rendered with
+    // this list; the next frame walks the tiles in descending order of it so that the long packets start first
+    std::vector<float> cost;             // by position in `host`; empty until a frame has been rendered
+    std::vector<uint32_t> order;         // positions in `host`, the order the last frame used
+    uint32_t* d_sorted = nullptr;        // host[order[i]]
+    unsigned long long* d_cost = nullptr; // per position in d_sorted, accumulated by the kernels
+};
+typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile_size, tile_mod, tile_rem (-1: all shards, padded)
+
 } // namespace
 
 struct RtContext {
@@ -96,7 +113,8 @@ struct RtContext {
     bool camera_set = false;
 
     // per-frame work buffers
-    DevBuf<uint32_t> d_super, d_frame, d_tiles, q_hit_slot, q_refl_idx, q_tail;
+    DevBuf<uint32_t> d_super, d_frame, q_hit_slot, q_refl_idx, q_tail, q_tail_off, q_tail_cnt, q_cont_link, q_cont_meta;
+    std::map<TileKey, TileList> tile_lists;
     DevBuf<int32_t> q_tri;
     DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
     DevBuf<unsigned long long> q_refl_cnt;
@@ -111,6 +129,7 @@ struct RtContext {
     Tuning tune{16, 16, 8, 1, 512};
     uint64_t opt_chunk_pixels = kChunkPixels;
     bool opt_screen_cull = true;
+    bool opt_cost_order = false;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -308,6 +327,38 @@ void screen_cull_rect(const RtContext* ctx, const FrameView& fr, WorkView& wk)
     wk.cull_y0 = (int32_t)std::max(-lim, std::floor(py0) - 2.0); wk.cull_y1 = (int32_t)std::min(lim, std::ceil(py1) + 2.0);
 }
 
+// The shard's tile list on the device (cached).  tile_rem = -1: the lists of ALL tile_mod shards, each padded with
+// 0xffffffff to the longest one (the layout of the gathered staging buffer).
+int get_tile_list(RtContext* ctx, const RtSettings* s, int tile_size, int tile_mod, int tile_rem, TileList** out)
+{
+    const TileKey key(s->image_width, s->image_height, tile_size, tile_mod, tile_rem);
+    auto it = ctx->tile_lists.find(key);
+    if (it == ctx->tile_lists.end()) {
+        if (ctx->tile_lists.size() > 64) {                         // a caller cycling through frame sizes: start over
+            RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_sorted); cudaFree(kv.second.d_cost); }
+            ctx->tile_lists.clear();
+        }
+        TileList tl;
+        if (tile_rem >= 0) tl.host = owned_tiles(s, tile_size, tile_mod, tile_rem, &tl.tiles_x);
+        else {
+            std::vector<std::vector<uint32_t>> per(tile_mod);
+            size_t longest = 0;
+            for (int r = 0; r < tile_mod; r++) { per[r] = owned_tiles(s, tile_size, tile_mod, r, &tl.tiles_x); longest = std::max(longest, per[r].size()); }
+            tl.host.assign(longest * tile_mod, 0xffffffffu);
+            for (int r = 0; r < tile_mod; r++) std::copy(per[r].begin(), per[r].end(), tl.host.begin() + (size_t)r * longest);
+        }
+        tl.count = (uint32_t)tl.host.size();
+        if (tl.count) {
+            RT_CUDA(ctx, cudaMalloc((void**)&tl.d, tl.host.size() * sizeof(uint32_t)));
+            RT_CUDA(ctx, cudaMemcpy(tl.d, tl.host.data(), tl.host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        it = ctx->tile_lists.emplace(key, std::move(tl)).first;
+    }
+    *out = &it->second;
+    return RT_OK;
+}
+
 int ensure_stack(RtContext* ctx, const RtSettings* s)
 {
     // k_reflect recurses (trace_ray_secondary); every level holds two traversal stacks.
@@ -385,7 +436,9 @@ void rt_destroy(RtContext* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
-    ctx->d_super.release(); ctx->d_frame.release(); ctx->d_tiles.release(); ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_tail.release();
+    ctx->d_super.release(); ctx->d_frame.release();
+    for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_sorted); cudaFree(kv.second.d_cost); }
+    ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_tail.release(); ctx->q_tail_off.release(); ctx->q_tail_cnt.release(); ctx->q_cont_link.release(); ctx->q_cont_meta.release();
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
@@ -423,6 +476,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->tune.packet_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
+    case RT_OPT_COST_ORDER: ctx->opt_cost_order = value != 0; return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -608,8 +662,24 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     const bool reflect = ctx->any_reflective && s->shading_method == RT_SHADING;
     if (reflect) if (int r = ensure_stack(ctx, s)) return r;
 
-    int tiles_x = 0;
-    std::vector<uint32_t> tiles = owned_tiles(s, tile_size, tile_mod, tile_rem, &tiles_x);
+    TileList* tl = nullptr;
+    if (int r = get_tile_list(ctx, s, tile_size, tile_mod, tile_rem, &tl)) return r;
+    // the tiles in the order this frame walks them: descending cost of the previous frame (same list, any order gives
+    // the same frame), or the list's own order when there is no history
+    const bool cost_order = ctx->opt_cost_order && tl->count > 1;
+    std::vector<uint32_t> tiles = tl->host;
+    if (cost_order) {
+        if (!tl->d_sorted) {
+            RT_CUDA(ctx, cudaMalloc((void**)&tl->d_sorted, tl->count * sizeof(uint32_t)));
+            RT_CUDA(ctx, cudaMalloc((void**)&tl->d_cost, tl->count * sizeof(unsigned long long)));
+        }
+        tl->order.resize(tl->count);
+        for (uint32_t i = 0; i < tl->count; i++) tl->order[i] = i;
+        if (tl->cost.size() == tl->count)
+            std::stable_sort(tl->order.begin(), tl->order.end(), [&](uint32_t a, uint32_t b) { return tl->cost[a] > tl->cost[b]; });
+        for (uint32_t i = 0; i < tl->count; i++) tiles[i] = tl->host[tl->order[i]];
+    }
+    const int tiles_x = tl->tiles_x;
     WorkView wk = {};
     wk.tiles_x = tiles_x;
     wk.tile_px = tile_size * fr.factor;
@@ -622,10 +692,15 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     const uint32_t n_chunks = (uint32_t)((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk);
     const size_t qcap = (size_t)std::min<uint64_t>((uint64_t)tiles_per_chunk, tiles.size()) * px_per_tile;
 
-    RT_CUDA(ctx, ctx->d_tiles.ensure(tiles.size()));
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
     const bool tail = ctx->tune.packets && ctx->tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
-    if (tail) RT_CUDA(ctx, ctx->q_tail.ensure(qcap));
+    // continuation buffer: the stacks (<= RT_STACK_SIZE cells each) of the shadow packets that run out of rounds; a packet
+    // that finds it full is finished in place
+    const size_t cont_cap = tail ? std::min<size_t>(std::max<size_t>(qcap / 4, (size_t)1 << 16), (size_t)1 << 25) : 0;
+    if (tail) {
+        RT_CUDA(ctx, ctx->q_tail.ensure(qcap)); RT_CUDA(ctx, ctx->q_tail_off.ensure(qcap)); RT_CUDA(ctx, ctx->q_tail_cnt.ensure(qcap));
+        RT_CUDA(ctx, ctx->q_cont_link.ensure(cont_cap)); RT_CUDA(ctx, ctx->q_cont_meta.ensure(cont_cap));
+    }
     RT_CUDA(ctx, ctx->q_hit_slot.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
     RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
     if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, ctx->q_refl_cnt.ensure(3 * qcap)); }
@@ -634,10 +709,12 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
         super = ctx->d_super.p;
     }
-    wk.tiles = ctx->d_tiles.p;
+    wk.tiles = cost_order ? tl->d_sorted : tl->d;
+    wk.tile_cost = cost_order ? tl->d_cost : nullptr;
     QueueView q;
     q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
-    q.tail = ctx->q_tail.p;
+    q.tail = ctx->q_tail.p; q.tail_off = ctx->q_tail_off.p; q.tail_cnt = ctx->q_tail_cnt.p;
+    q.cont_link = ctx->q_cont_link.p; q.cont_meta = ctx->q_cont_meta.p; q.cont_capacity = (uint32_t)cont_cap;
     q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
 
     cudaStream_t st = ctx->stream;
@@ -646,9 +723,11 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     uint32_t launches = 0;
     cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
     RT_CUDA(ctx, cudaEventRecord(ev_begin, st));
-    if (!tiles.empty())
-        RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
+    if (cost_order) {
+        RT_CUDA(ctx, cudaMemcpyAsync(tl->d_sorted, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemsetAsync(tl->d_cost, 0, tl->count * sizeof(unsigned long long), st));
+    }
 
     const bool count = ctx->opt_count_work;
     static int grids[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
@@ -715,8 +794,14 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     std::vector<ChunkCounters> host_cnt(std::max<uint32_t>(n_chunks, 1));
     RT_CUDA(ctx, cudaMemcpyAsync(host_cnt.data(), ctx->d_counters.p, sizeof(ChunkCounters) * host_cnt.size(), cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned long long> host_cost(cost_order ? tl->count : 0);
+    if (cost_order) RT_CUDA(ctx, cudaMemcpyAsync(host_cost.data(), tl->d_cost, tl->count * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RT_CUDA(ctx, cudaStreamSynchronize(st));
 
+    if (cost_order && ctx->tune.packets) {
+        tl->cost.assign(tl->count, 0.0f);
+        for (uint32_t i = 0; i < tl->count; i++) tl->cost[tl->order[i]] = (float)host_cost[i];
+    }
     RtRenderStats rs;
     memset(&rs, 0, sizeof(rs));
     bool overflow = false;
@@ -794,24 +879,17 @@ static int pack_unpack(RtContext* ctx, const RtSettings* s, const uint32_t* d_fr
     if (int r = bind(ctx)) return r;
     if (int r = validate_settings(ctx, s)) return r;
     if (int r = check_tile_args(ctx, tile_size, tile_mod, tile_rem)) return r;
-    int tiles_x = 0;
-    std::vector<uint32_t> tiles = owned_tiles(s, tile_size, tile_mod, tile_rem, &tiles_x);
-    if (tiles.empty()) return RT_OK;
-    // the tile list of another shard may be needed while d_tiles holds ours: use a scratch allocation
-    uint32_t* d_list = nullptr;
-    RT_CUDA(ctx, cudaMallocAsync((void**)&d_list, tiles.size() * sizeof(uint32_t), ctx->stream));
-    RT_CUDA(ctx, cudaMemcpyAsync(d_list, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    TileList* tl = nullptr;
+    if (int r = get_tile_list(ctx, s, tile_size, tile_mod, tile_rem, &tl)) return r;
+    if (tl->count == 0) return RT_OK;
     WorkView wk = {};
-    memset(&wk, 0, sizeof(wk));
-    wk.tiles = d_list;
+    wk.tiles = tl->d;
     wk.tile_begin = 0;
-    wk.tile_end = (uint32_t)tiles.size();
-    wk.tiles_x = tiles_x;
+    wk.tile_end = tl->count;
+    wk.tiles_x = tl->tiles_x;
     k_pack_tiles<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_frame_in, d_staging, wk, tile_size, s->image_width, s->image_height, unpack, d_frame_out);
     RT_CUDA(ctx, cudaGetLastError());
-    RT_CUDA(ctx, cudaFreeAsync(d_list, ctx->stream));
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
+    return RT_OK;                                                  // stream-ordered: no host synchronisation
 }
 
 int rt_pack_tiles(RtContext* ctx, const RtSettings* s, const uint32_t* d_frame, uint32_t* d_staging, int tile_size, int tile_mod, int tile_rem)
@@ -822,6 +900,22 @@ int rt_pack_tiles(RtContext* ctx, const RtSettings* s, const uint32_t* d_frame, 
 int rt_unpack_tiles(RtContext* ctx, const RtSettings* s, uint32_t* d_frame, const uint32_t* d_staging, int tile_size, int tile_mod, int tile_rem)
 {
     return pack_unpack(ctx, s, nullptr, d_frame, const_cast<uint32_t*>(d_staging), tile_size, tile_mod, tile_rem, 1);
+}
+
+int rt_unpack_gathered(RtContext* ctx, const RtSettings* s, uint32_t* d_frame, const uint32_t* d_gathered, int tile_size, int tile_mod, int self_rem)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (int r = validate_settings(ctx, s)) return r;
+    if (int r = check_tile_args(ctx, tile_size, tile_mod, self_rem < 0 ? 0 : self_rem)) return r;
+    if (!d_frame || !d_gathered) return fail(ctx, RT_ERR_INVALID, "NULL buffer");
+    TileList* tl = nullptr;
+    if (int r = get_tile_list(ctx, s, tile_size, tile_mod, -1, &tl)) return r;
+    if (tl->count == 0) return RT_OK;
+    k_unpack_gathered<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_gathered, d_frame, tl->d, tl->count / (uint32_t)tile_mod, tile_mod, self_rem, tl->tiles_x,
+                                                                  tile_size, s->image_width, s->image_height);
+    RT_CUDA(ctx, cudaGetLastError());
+    return RT_OK;
 }
 
 int rt_intersect(RtContext* ctx, const float* o3, const float* d3, size_t n, int32_t* tri_id, float* t, float* u, float* v)
@@ -910,17 +1004,14 @@ int rt_resolve_ssaa(RtContext* ctx, const uint32_t* argb_in, int width, int heig
     rt_default_settings(&s);
     s.image_width = w; s.image_height = h;
     const int tile = 64;
-    int tiles_x = 0;
-    std::vector<uint32_t> tiles = owned_tiles(&s, tile, 1, 0, &tiles_x);
+    TileList* tl = nullptr;
+    if (int r = get_tile_list(ctx, &s, tile, 1, 0, &tl)) return r;
     RT_CUDA(ctx, ctx->d_super.ensure((size_t)width * height));
     RT_CUDA(ctx, ctx->d_frame.ensure((size_t)w * h));
-    RT_CUDA(ctx, ctx->d_tiles.ensure(tiles.size()));
     cudaStream_t st = ctx->stream;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_super.p, argb_in, (size_t)width * height * 4, cudaMemcpyHostToDevice, st));
-    RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, st));
     WorkView wk = {};
-    memset(&wk, 0, sizeof(wk));
-    wk.tiles = ctx->d_tiles.p; wk.tile_begin = 0; wk.tile_end = (uint32_t)tiles.size(); wk.tiles_x = tiles_x;
+    wk.tiles = tl->d; wk.tile_begin = 0; wk.tile_end = tl->count; wk.tiles_x = tl->tiles_x;
     k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_super.p, ctx->d_frame.p, wk, tile, factor, w, h);
     RT_CUDA(ctx, cudaGetLastError());
     RT_CUDA(ctx, cudaMemcpyAsync(argb_out, ctx->d_frame.p, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));

@@ -3,7 +3,7 @@
 Every pixel's ray tree is independent, so the path shards with no data-path exchange: the scene is replicated on
 every GPU, the frame is cut into `tile_size`^2 final-resolution tiles dealt round-robin over the ranks
 (rtb::owned_tiles), each rank traces, shades and RESOLVES its own tiles, and the only collective is the gather of
-the final ARGB32 tiles: pack (kernel) -> all_gather over NCCL/NVLink -> unpack (kernel).  One process per GPU,
+the final ARGB32 tiles: pack (kernel) -> all_gather over NCCL/NVLink -> unpack (one kernel for all peers).  One process per GPU,
 `torch.distributed` is the plumbing; the tensors are only device memory handed to the C ABI as raw pointers.
 
 With backend "gloo" and CPU tensors the same code runs against the host kernel emulation in the CPU tests.
@@ -40,8 +40,6 @@ class ShardedFrame:
             return self.frame
         self.ctx.pack_tiles(self.s, self.frame.data_ptr(), self.staging.data_ptr(), self.tile, self.world, self.rank)
         dist.all_gather_into_tensor(self.gathered, self.staging)
-        esz = self.gathered.element_size()
-        for r in range(self.world):
-            if r != self.rank:
-                self.ctx.unpack_tiles(self.s, self.frame.data_ptr(), self.gathered.data_ptr() + r * self.slot * esz, self.tile, self.world, r)
+        # one launch scatters the peers' tiles; pack, collective and unpack are stream-ordered, no host synchronisation
+        self.ctx.unpack_gathered(self.s, self.frame.data_ptr(), self.gathered.data_ptr(), self.tile, self.world, self.rank)
         return self.frame

@@ -123,7 +123,7 @@ const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""
 int rt_set_option(RtContext* c, int option, int64_t value)
 {
     if (option == RT_OPT_LEAF_SPLIT) { c->leaf_split = (int)value; c->bvh_valid = false; return RT_OK; }
-    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
+    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_COST_ORDER) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
 }
 
 int rt_set_stream(RtContext*, void*) { return RT_OK; }
@@ -378,6 +378,16 @@ int rt_pack_tiles(RtContext*, const RtSettings* s, const uint32_t* frame, uint32
 int rt_unpack_tiles(RtContext*, const RtSettings* s, uint32_t* frame, const uint32_t* staging, int tile_size, int mod, int rem)
 {
     tile_copy(s, nullptr, frame, const_cast<uint32_t*>(staging), tile_size, mod, rem, 1);
+    return RT_OK;
+}
+
+int rt_unpack_gathered(RtContext*, const RtSettings* s, uint32_t* frame, const uint32_t* gathered, int tile_size, int mod, int self_rem)
+{
+    size_t longest = 0;
+    for (int r = 0; r < mod; r++) longest = std::max(longest, owned_tiles(s, tile_size, mod, r, nullptr).size());
+    for (int r = 0; r < mod; r++)
+        if (r != self_rem)
+            tile_copy(s, nullptr, frame, const_cast<uint32_t*>(gathered) + (size_t)r * longest * tile_size * tile_size, tile_size, mod, r, 1);
     return RT_OK;
 }
 

@@ -193,6 +193,26 @@ def test_tile_shards_tile_the_frame(cuda_lib, robot, mod):
         r.ctx.unpack_tiles(s, frame.data_ptr(), staging.data_ptr(), 16, mod, rem)
     torch.cuda.synchronize()
     assert np.array_equal(frame.cpu().numpy().view(np.uint32), full)
+    # the same through the single-launch receiving side of the all-gather (rt_unpack_gathered)
+    slot = max(r.ctx.tile_count(s, 16, mod, rem) for rem in range(mod)) * 256
+    gathered = torch.zeros(mod * slot, dtype=torch.int32, device="cuda")
+    shard = torch.from_numpy(full.view(np.int32)).cuda()
+    for rem in range(mod):
+        r.ctx.pack_tiles(s, shard.data_ptr(), gathered.data_ptr() + rem * slot * 4, 16, mod, rem)
+    again = torch.full(full.shape, 0x5a5a5a5a, dtype=torch.int32, device="cuda")
+    r.ctx.unpack_gathered(s, again.data_ptr(), gathered.data_ptr(), 16, mod, 1)
+    torch.cuda.synchronize()
+    got = again.cpu().numpy().view(np.uint32)
+    mine = np.zeros(full.shape, bool)
+    ty, tx = np.divmod(np.arange(full.size).reshape(full.shape), full.shape[1])
+    own = torch.zeros(full.shape, dtype=torch.int32, device="cuda")
+    stg = torch.zeros(slot, dtype=torch.int32, device="cuda")
+    ones = torch.ones(full.shape, dtype=torch.int32, device="cuda")
+    r.ctx.pack_tiles(s, ones.data_ptr(), stg.data_ptr(), 16, mod, 1)
+    r.ctx.unpack_tiles(s, own.data_ptr(), stg.data_ptr(), 16, mod, 1)
+    torch.cuda.synchronize()
+    mine = own.cpu().numpy() == 1                                 # pixels of shard 1: left untouched by self_rem = 1
+    assert np.array_equal(got[~mine], full[~mine]) and (got[mine] == 0x5a5a5a5a).all() and mine.any()
     r.close()
 
 
@@ -301,6 +321,34 @@ def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
             for k in ("primary_rays", "primary_hits", "shadow_rays", "reflection_rays"):
                 assert frames[0][1][k] == frames[1][1][k], (name, i, k)
             common.assert_image_close(frames[0][0], common.oracle_image(oracle, robot, kw, mats, tex, cam=cam), what=f"{name} camera {i}")
+
+
+def test_cost_ordered_tiles_never_change_a_frame(cuda_lib, robot):
+    """RT_OPT_COST_ORDER re-orders the tiles of frame n+1 by what their packets cost in frame n: consecutive frames of
+    the same context (first without history, then re-ordered) and the frame of a context that never re-orders are
+    bit-identical, with the same ray counts; also for a 3-shard split."""
+    import torch
+    kw, mats, tex = common.config_table(robot["materials"])["cfg2"]
+    ref = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+    ref.ctx.set_option(api.RT_OPT_COST_ORDER, 0)
+    ref.ray_trace()
+    want, want_stats = ref.get_image().copy(), ref.last_stats().as_dict()
+    ref.close()
+    r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+    r.ctx.set_option(api.RT_OPT_COST_ORDER, 1)
+    for frame_no in range(3):
+        r.ray_trace()
+        assert np.array_equal(r.get_image(), want), frame_no
+        for k in ("primary_rays", "shadow_rays", "primary_hits"):
+            assert r.last_stats().as_dict()[k] == want_stats[k]
+    s = r.render_settings()
+    for frame_no in range(2):
+        frame = torch.zeros(want.shape, dtype=torch.int32, device="cuda")
+        for rem in range(3):
+            r.ctx.render_device(s, frame.data_ptr(), 16, 3, rem)
+        torch.cuda.synchronize()
+        assert np.array_equal(frame.cpu().numpy().view(np.uint32), want)
+    r.close()
 
 
 def test_cpp_adapter_example(cuda_lib, tmp_path):
