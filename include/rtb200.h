@@ -155,8 +155,10 @@ enum {
     RT_OPT_PACKETS = 6,       /* 1 (default): primary and shadow rays are traced as 32-ray packets (one traversal per
                                  warp); 0: every lane runs its own traversal state machine with lane refill.  Results do
                                  not depend on it                                                                       */
-    RT_OPT_PACKET_ROUNDS = 7, /* a shadow packet that needs more cell/leaf rounds than this (default 512; 0 = no limit) hands
-                                 its unanswered rays to the one-ray-per-warp tail kernel.  Results do not depend on it  */
+    RT_OPT_PACKET_ROUNDS = 7, /* a shadow packet that needs more cell/leaf rounds than this (default 256; 0 = no limit) is
+                                 split: each cell it has not visited becomes a work item another warp traces for the same
+                                 32 rays (up to 3 item passes, the last without a limit).  Results do not depend on it   */
+    RT_OPT_ITEM_ROUNDS = 10,  /* round limit of a work item in all item passes but the last (default 64)                */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
     RT_OPT_COST_ORDER = 9,    /* 1 (default 0): a frame walks its tiles in descending order of the SM cycles their packets took in

@@ -27,6 +27,7 @@ constexpr int kQueueThreads = 128;
 #endif
 constexpr int kPrimaryFetch = RTB_FETCH;     // 32-ray packets a warp of k_primary_packet takes per atomic
 constexpr int kStepsPerCheck = 4;
+constexpr int kItemPasses = 3;      // launches of k_shade_items after k_shade_packet; the last one has no round budget
 #ifndef RTB_SHADE_MINB
 #define RTB_SHADE_MINB 6   /* resident CTAs per SM the compiler must allow for k_shade_packet (register bound) */
 #endif    // single-test steps between two refill / completion checks of a persistent warp
@@ -37,9 +38,9 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int n_hits;
     unsigned int n_refl;
     unsigned int stack_overflow;
-    unsigned int n_tail;             // hit-queue entries whose shadow packet ran out of rounds (k_shade_tail finishes them)
-    unsigned int next_tail;
-    unsigned int cont_used;          // entries of the continuation buffer handed out
+    unsigned int n_split;            // shadow packets that ran out of rounds and were split into work items
+    unsigned int items_n[kItemPasses];    // work items written for item pass p (each: one unvisited cell of a split packet)
+    unsigned int items_next[kItemPasses]; // next item of pass p to take
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
@@ -113,12 +114,12 @@ struct QueueView {
     float* slot_v;
     // compacted by k_compact
     uint32_t* hit_slot;              // hit queue: ray slots of the hits
-    uint32_t* tail;                  // tail queue: hit-queue entries left to k_shade_tail ...
-    uint32_t* tail_off;              // ... and where in cont_* the unvisited cells of the entry's packet start / how many
-    uint32_t* tail_cnt;
-    uint32_t* cont_link;             // continuation buffer: the stacks of the packets that ran out of rounds
-    uint32_t* cont_meta;
-    uint32_t cont_capacity;
+    // split shadow packets (k_shade_packet -> k_shade_items -> k_shade_finish)
+    uint32_t* split_base;            // first hit-queue entry of the packet
+    uint32_t* split_active;          // lanes that had no answer when the packet was split
+    uint32_t* split_occ;             // lanes found occluded since (atomicOr by the items)
+    uint4* items;                    // kItemPasses regions of item_capacity: (split index, link, meta, -)
+    uint32_t split_capacity, item_capacity;
     uint32_t* refl_idx;              // reflection queue: indices into the hit queue
     float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
     unsigned long long* refl_cnt;    // 3 words per hit-queue entry, written by k_reflect: rays | shadow rays << 32, V, T
@@ -150,7 +151,8 @@ struct Tuning {
     int32_t shade_refill;
     int32_t tri_batch;        // run the triangle phase once this many lanes wait for it (or nothing else can run)
     int32_t packets;          // 1: primary and shadow rays are traced as 32-ray packets (k_primary_packet / k_shade_packet)
-    int32_t packet_rounds;    // a shadow packet that needs more cell/leaf rounds than this hands its rays to k_shade_tail (0: never)
+    int32_t packet_rounds;    // a shadow packet that needs more cell/leaf rounds than this is split into work items (0: never)
+    int32_t item_rounds;      // the same for the items of all passes but the last
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -294,16 +296,17 @@ RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4&
 
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
 // occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
+// The traversal starts at the root cell, or (start_meta != 0) at the cell / leaf (start_link, start_meta).
 // Returns false when the packet used up `max_rounds` cell/leaf rounds without finishing (max_rounds 0: no limit); the
 // lanes whose `active` is still set then have no result yet, and K.link/meta[0, K.saved) are the cells the packet has
-// not visited (for each of those lanes a superset of the cells it still has to visit).  A packet's rounds are one
-// dependent chain (pop -> fetch -> test -> push), 1-2 us each, so a packet that needs thousands of them (measured: one
-// shadow packet through the pole of the 10 M-triangle sphere, 8 000 rounds = 11 ms of a 17 ms kernel) is better
-// finished by warps that each take ONE of its rays, start from those cells, and spread the ray's tests over their
-// lanes (coop_occluded).
+// not visited.  A packet's rounds are one dependent chain (pop -> fetch -> test -> push), 1-2 us each, so a packet that
+// needs thousands of them (measured: one shadow packet through the pole of the 10 M-triangle sphere, 8 000 rounds =
+// 11 ms of a 17 ms kernel) is SPLIT: each unvisited cell becomes a work item that another warp traces for the same 32
+// rays (k_shade_items), and the answers are merged (any-hit: OR).
 template <bool ANY, bool COUNT>
 RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
-                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds)
+                         HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds,
+                         uint32_t start_link = 0u, uint32_t start_meta = 0u)
 {
     const unsigned lane = threadIdx.x & 31u;
     SlabRay sr;
@@ -311,8 +314,8 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
     const V3 md = -d;
     best.tri = -1; best.t = -1.0f; best.u = 1.0f; best.v = 0.0f;
     occluded = false;
-    uint32_t link, meta;
-    {
+    uint32_t link = start_link, meta = start_meta;
+    if (start_meta == 0u) {
         const rt_f4* r = sc.recs;
         rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
         if (COUNT && active) tc.vol_tests++;
@@ -397,86 +400,6 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
         }
         if (!got) return true;
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// One ray, one warp: Renderer::is_shadowed (renderer.cpp:340-402) with the ray's tests spread over the lanes.  Any-hit
-// needs no order, so the warp pops up to FOUR stack entries per round and gives each eight lanes: a lane tests one child
-// record of a cell or one triangle of a leaf (a leaf with more than eight triangles goes back on the stack minus the
-// eight being tested).  Children that are hit are pushed with one ballot + prefix count.  Same predicate and the same
-// conservative slab test as the packet and single-ray paths, so the same answer; only the schedule differs.
-constexpr int kCoopStack = 1024;
-
-struct CoopStack {
-    uint32_t link[kCoopStack];
-    uint32_t meta[kCoopStack];
-};
-
-// The traversal starts from `n_start` cells at cont_link/cont_meta (the unvisited cells of the ray's packet).
-template <bool COUNT>
-RT_DEV bool coop_occluded(const SceneView& sc, CoopStack& K, V3 p, V3 n, V3 light, const uint32_t* cont_link, const uint32_t* cont_meta,
-                          uint32_t n_start, TraceCounters& tc, unsigned& overflow)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const V3 o = p + 1.0e-4f * n;                                // Renderer::EPSILON, renderer.h:23
-    const V3 d = normalize(light - p);
-    const float dist2 = length2(p - light);
-    const float t_max = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
-    SlabRay sr;
-    slab_setup(o, d, sr);
-    const V3 md = -d;
-    int sp = (int)n_start;
-    for (uint32_t i = lane; i < n_start; i += 32u) { K.link[i] = cont_link[i]; K.meta[i] = cont_meta[i]; }
-    __syncwarp();
-    const int slot = (int)(lane >> 3), sub = (int)(lane & 7u);
-    while (sp > 0) {
-        const int take = min(sp, 4);
-        const bool have = slot < take;
-        uint32_t link = 0, meta = 0;
-        if (have) { link = K.link[sp - 1 - slot]; meta = K.meta[sp - 1 - slot]; }
-        __syncwarp();
-        sp -= take;
-        const bool leaf = (meta & RT_LEAF_BIT) != 0u;
-        const uint32_t cnt = meta & ~RT_LEAF_BIT;
-        // a long leaf: the rest of it goes back on the stack
-        const bool rem = have && leaf && cnt > 8u && sub == 0;
-        const unsigned rm = __ballot_sync(0xffffffffu, rem);
-        if (rem) {
-            const int pos = sp + __popc(rm & lt_mask);
-            K.link[pos] = link + 8u; K.meta[pos] = RT_LEAF_BIT | (cnt - 8u);
-        }
-        sp += __popc(rm);
-        bool push = false, occ = false;
-        uint32_t cl = 0, cm = 0;
-        if (have && (uint32_t)sub < min(cnt, 8u)) {
-            if (!leaf) {
-                const rt_f4* r = sc.recs + 4 * (size_t)(link + (uint32_t)sub);
-                rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-                if (COUNT) tc.vol_tests++;
-                if (slab_entry(c0, c1, c2, c3, sr, t_max) != INFINITY) { push = true; cl = f4_bits(c3.z); cm = f4_bits(c3.w); }
-            } else {
-                const rt_f4* tp = sc.tris + 3 * (size_t)(link + (uint32_t)sub);
-                rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-                if (COUNT) tc.tri_tests++;
-                float t, u, v;
-                if (tri_test(p0, p1, p2, o, md, t, u, v) && t > 0.0f) {
-                    V3 q = o + t * d;                            // renderer.cpp:351
-                    occ = length2(p - q) < dist2;                // renderer.cpp:354
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, occ) != 0u) return true;
-        const unsigned pm = __ballot_sync(0xffffffffu, push);
-        if (sp + __popc(pm) > kCoopStack) { overflow = 1u; return false; }
-        if (push) {
-            const int pos = sp + __popc(pm & lt_mask);
-            K.link[pos] = cl; K.meta[pos] = cm;
-        }
-        sp += __popc(pm);
-        __syncwarp();
-    }
-    return false;
 }
 
 // Packet version of k_primary: a warp takes 32 consecutive ray slots (an 8x4 pixel block) per fetch.
@@ -731,8 +654,84 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
     if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
 }
 
+// What a lane of the shading kernels knows about its hit-queue entry before the shadow ray is traced.
+struct ShadeLane {
+    uint32_t pix;
+    int32_t mat;
+    Col direct;             // diffuse * ao + specular (shade_direct), or the debug colour when !rt
+    V3 p, nrm;              // shaded point and (normal-mapped) shading normal: the shadow ray starts at p + nrm * EPSILON
+    bool rt;                // RT_SHADING (false: one of the debug shading modes, no further rays)
+};
+
+RT_DEV ShadeLane shade_prepare(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, uint32_t entry)
+{
+    ShadeLane L;
+    V3 o, d;
+    HitRec hr;
+    queue_ray(fr, wk, q, entry, o, d, hr, L.pix);
+    Hit hit = complete_hit(sc, hr);
+    L.mat = hit.mat;
+    L.rt = fr.s.shading_method == RT_SHADING;
+    if (!L.rt) { L.direct = shade_debug(sc, fr, hit); L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1); }
+    else {
+        MatView m;
+        L.direct = shade_direct(sc, fr, o, d, hit, L.p, m);
+        L.nrm = hit.normal;
+    }
+    return L;
+}
+
+template <bool COUNT>
+RT_DEV void shade_store(const SceneView& sc, const FrameView& fr, const QueueView& q, uint32_t entry, const ShadeLane& L, bool occluded,
+                        TraceCounters& fan, uint32_t* super)
+{
+    if (!L.rt) { super[L.pix] = quantise_argb(L.direct); return; }
+    const MatView m = load_material(sc, L.mat);
+    Col refl = col(0.0f);
+    if (m.reflection > 0.0f) {
+        refl = col(q.refl_rgb[3 * (size_t)entry], q.refl_rgb[3 * (size_t)entry + 1], q.refl_rgb[3 * (size_t)entry + 2]);
+        const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
+        fan.refl_rays += (uint32_t)packed;
+        fan.refl_shadow_rays += (uint32_t)(packed >> 32);
+        if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
+    }
+    super[L.pix] = quantise_argb(shade_compose(fr, m, L.direct, occluded, refl));
+}
+
+template <bool COUNT>
+RT_DEV void shade_epilogue(ChunkCounters* cnt, TraceCounters& tc, TraceCounters& fan, unsigned overflow)
+{
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
+    if ((threadIdx.x & 31u) == 0) {
+        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
+        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
+    }
+    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
+}
+
+// A packet (or item) that ran out of rounds: every unvisited cell K.link/meta[0, K.saved) becomes one work item of item
+// pass `pass` for split record `sidx`.  Returns false when the item region is full (the caller then finishes in place);
+// the slots it was handed are still filled (with null items) so that the region never holds garbage.
+RT_DEV bool emit_items(const QueueView& q, ChunkCounters* cnt, const PacketStack& K, int pass, uint32_t sidx)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = (uint32_t)K.saved;
+    uint32_t at = 0;
+    if (lane == 0) at = atomicAdd(&cnt->items_n[pass], n);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    const bool ok = at + n <= q.item_capacity;
+    uint4* region = q.items + (size_t)pass * q.item_capacity;
+    for (uint32_t i = lane; i < n && at + i < q.item_capacity; i += 32u)
+        region[at + i] = ok ? make_uint4(sidx, K.link[i], K.meta[i], 0u) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+    __syncwarp();
+    return ok;
+}
+
 // Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
-// them, traces their 32 shadow rays as one packet, composes and stores.
+// them, traces their 32 shadow rays as one packet, composes and stores.  A packet that runs out of rounds
+// (RT_OPT_PACKET_ROUNDS) stores the pixels it has an answer for and is split into work items for the rest.
 template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
 k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
@@ -752,145 +751,122 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         const long long c0 = clock64();
         const uint32_t entry = base + lane;
         const bool valid = entry < n;
-        uint32_t pix = 0;
-        Col direct = col(0.0f), debug = col(0.0f);
-        int32_t mat = 0;
-        V3 p = v3(0, 0, 0), nrm = v3(0, 0, 1);
-        bool rt = false;
-        if (valid) {
-            V3 o, d;
-            HitRec hr;
-            queue_ray(fr, wk, q, entry, o, d, hr, pix);
-            Hit hit = complete_hit(sc, hr);
-            if (fr.s.shading_method != RT_SHADING) debug = shade_debug(sc, fr, hit);
-            else {
-                MatView m;
-                direct = shade_direct(sc, fr, o, d, hit, p, m);
-                mat = hit.mat;
-                nrm = hit.normal;
-                rt = true;
-            }
-        }
+        ShadeLane L;
+        L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
+        if (valid) L = shade_prepare(sc, fr, wk, q, entry);
         bool occluded = false, deferred = false;
         if (fr.s.compute_shadows && fr.s.shading_method == RT_SHADING) {
-            bool active = valid && rt;
-            const V3 so = p + 1.0e-4f * nrm;                                   // Renderer::EPSILON, renderer.h:23
-            const V3 sd = active ? normalize(fr.light - p) : v3(0, 0, 1);
-            const float dist2 = length2(p - fr.light);
+            bool active = valid && L.rt;
+            const V3 so = L.p + 1.0e-4f * L.nrm;                               // Renderer::EPSILON, renderer.h:23
+            const V3 sd = active ? normalize(fr.light - L.p) : v3(0, 0, 1);
+            const float dist2 = length2(L.p - fr.light);
+            const float t_lim = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
             HitRec unused;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded,
-                                                            tc, overflow, tune.packet_rounds, rounds);
+            const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
+                                                            tune.packet_rounds, rounds);
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
             if (!finished) {
-                // Out of rounds: the packet's unvisited cells go to the continuation buffer and the rays without an
-                // answer to the tail queue (two atomics per warp).  No room left there: finish the packet here.
-                const uint32_t n_cont = (uint32_t)K.saved;
                 const unsigned dm = __ballot_sync(0xffffffffu, active);
-                uint32_t off = 0, at = 0;
-                if (lane == 0) {
-                    off = atomicAdd(&cnt->cont_used, n_cont);
-                    if (off + n_cont <= q.cont_capacity) at = atomicAdd(&cnt->n_tail, (unsigned)__popc(dm));
-                }
-                off = __shfl_sync(0xffffffffu, off, 0);
-                at = __shfl_sync(0xffffffffu, at, 0);
-                if (off + n_cont <= q.cont_capacity) {
-                    for (uint32_t i = lane; i < n_cont; i += 32u) { q.cont_link[off + i] = K.link[i]; q.cont_meta[off + i] = K.meta[i]; }
-                    deferred = active;
-                    if (deferred) {
-                        const uint32_t at_me = at + (uint32_t)__popc(dm & ((1u << lane) - 1u));
-                        q.tail[at_me] = entry; q.tail_off[at_me] = off; q.tail_cnt[at_me] = n_cont;
-                    }
-                    __syncwarp();
+                uint32_t sidx = 0;
+                if (lane == 0) sidx = atomicAdd(&cnt->n_split, 1u);
+                sidx = __shfl_sync(0xffffffffu, sidx, 0);
+                if (sidx < q.split_capacity && emit_items(q, cnt, K, 0, sidx)) {
+                    if (lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = dm; q.split_occ[sidx] = 0u; }
+                    deferred = active;                                         // k_shade_finish stores these pixels
                 } else {
-                    const bool before = occluded;
-                    packet_trace<true, COUNT>(sc, K, active, so, sd, (sqrtf(dist2) + 4.0e-4f) * 1.0001f, p, dist2, unused, occluded, tc, overflow, 0,
-                                              rounds);
+                    if (sidx < q.split_capacity && lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = 0u; q.split_occ[sidx] = 0u; }
+                    const bool before = occluded;                              // no room: finish here, from the root
+                    packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds);
                     occluded = occluded || before;
                     __syncwarp();
                 }
             }
         }
-        if (valid && !deferred) {
-            if (!rt) super[pix] = quantise_argb(debug);
-            else {
-                const MatView m = load_material(sc, mat);
-                Col refl = col(0.0f);
-                if (m.reflection > 0.0f) {
-                    refl = col(q.refl_rgb[3 * (size_t)entry], q.refl_rgb[3 * (size_t)entry + 1], q.refl_rgb[3 * (size_t)entry + 2]);
-                    const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
-                    fan.refl_rays += (uint32_t)packed;
-                    fan.refl_shadow_rays += (uint32_t)(packed >> 32);
-                    if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
-                }
-                super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
-            }
+        if (valid && !deferred) shade_store<COUNT>(sc, fr, q, entry, L, occluded, fan, super);
+        if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[base], c0);
+    }
+    shade_epilogue<COUNT>(cnt, tc, fan, overflow);
+}
+
+// Item pass `pass` (0 .. kItemPasses-1): a warp takes one work item = one unvisited cell of a split packet, rebuilds the
+// packet's 32 shadow rays, traces them from that cell and ORs the newly occluded lanes into the split record.  An item
+// that runs out of rounds itself is split again into the next pass's region; the last pass has no budget.
+template <bool COUNT>
+__global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
+k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, Tuning tune, int pass)
+{
+    __shared__ PacketStack stacks[kQueueThreads / 32];
+    PacketStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_hits = cnt->n_hits;
+    const uint32_t n = min(cnt->items_n[pass], q.item_capacity);
+    const uint4* region = q.items + (size_t)pass * q.item_capacity;
+    const int budget = pass + 1 < kItemPasses ? tune.item_rounds : 0;
+    TraceCounters tc = zero_counters();
+    unsigned overflow = 0;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&cnt->items_next[pass], 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const uint4 item = region[i];
+        const uint32_t sidx = item.x;
+        if (sidx == 0xffffffffu) continue;
+        const uint32_t base = q.split_base[sidx];
+        const uint32_t live = q.split_active[sidx] & ~*((volatile uint32_t*)&q.split_occ[sidx]);
+        const uint32_t entry = base + lane;
+        bool active = entry < n_hits && ((live >> lane) & 1u) != 0u;
+        if (__ballot_sync(0xffffffffu, active) == 0u) continue;                // every ray has been answered meanwhile
+        const long long c0 = clock64();
+        ShadeLane L;
+        L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
+        if (active) L = shade_prepare(sc, fr, wk, q, entry);
+        const V3 so = L.p + 1.0e-4f * L.nrm;
+        const V3 sd = active ? normalize(fr.light - L.p) : v3(0, 0, 1);
+        const float dist2 = length2(L.p - fr.light);
+        const float t_lim = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
+        HitRec unused;
+        bool occluded = false;
+        unsigned rounds = 0;
+        bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
+                                                  item.y, item.z);
+        __syncwarp();
+        if (!finished && !emit_items(q, cnt, K, pass + 1, sidx)) {
+            const bool before = occluded;                                      // no room: finish the item here
+            packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z);
+            occluded = occluded || before;
+            __syncwarp();
         }
+        const unsigned om = __ballot_sync(0xffffffffu, occluded);
+        if (om != 0u && lane == 0) atomicOr(&q.split_occ[sidx], om);
         if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[base], c0);
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
-    const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
-    if ((threadIdx.x & 31u) == 0) {
-        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
-        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
-    }
-    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
 }
 
-// Finishes the hits whose shadow packet ran out of rounds: one warp per hit.  Every lane recomputes the (cheap) direct
-// shading of the hit, the warp answers the shadow query together (coop_occluded), lane 0 composes and stores.
+// After the item passes: composes and stores the pixels of the split packets' unanswered lanes with the merged answers.
 template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
-k_shade_tail(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+k_shade_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
 {
-    __shared__ CoopStack stacks[kQueueThreads / 32];
-    CoopStack& K = stacks[threadIdx.x >> 5];
     const unsigned lane = threadIdx.x & 31u;
-    const uint32_t n = cnt->n_tail;
+    const uint32_t n_hits = cnt->n_hits;
+    const uint32_t n = min(cnt->n_split, q.split_capacity);
     TraceCounters tc = zero_counters();
     TraceCounters fan = zero_counters();
-    unsigned overflow = 0;
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(&cnt->next_tail, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= n) break;
-        const uint32_t entry = q.tail[i];
-        const long long c0 = clock64();
-        V3 o, d, p;
-        HitRec hr;
-        uint32_t pix;
-        queue_ray(fr, wk, q, entry, o, d, hr, pix);
-        Hit hit = complete_hit(sc, hr);
-        MatView m;
-        const Col direct = shade_direct(sc, fr, o, d, hit, p, m);
-        const uint32_t off = q.tail_off[i];
-        const bool occluded = coop_occluded<COUNT>(sc, K, p, hit.normal, fr.light, q.cont_link + off, q.cont_meta + off, q.tail_cnt[i], tc, overflow);
-        __syncwarp();
-        if (lane == 0) {
-            Col refl = col(0.0f);
-            if (m.reflection > 0.0f) {
-                refl = col(q.refl_rgb[3 * (size_t)entry], q.refl_rgb[3 * (size_t)entry + 1], q.refl_rgb[3 * (size_t)entry + 2]);
-                const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
-                fan.refl_rays += (uint32_t)packed;
-                fan.refl_shadow_rays += (uint32_t)(packed >> 32);
-                if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
-            }
-            super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sidx < n; sidx += warps) {
+        const uint32_t entry = q.split_base[sidx] + lane;
+        if (entry < n_hits && ((q.split_active[sidx] >> lane) & 1u) != 0u) {
+            const ShadeLane L = shade_prepare(sc, fr, wk, q, entry);
+            shade_store<COUNT>(sc, fr, q, entry, L, ((q.split_occ[sidx] >> lane) & 1u) != 0u, fan, super);
         }
-        if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[entry], c0);
     }
-    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
-    const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
-    if ((threadIdx.x & 31u) == 0) {
-        if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
-        if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
-    }
-    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
+    shade_epilogue<COUNT>(cnt, tc, fan, 0u);
 }
 
 // ImageUtils::downscale_image_qt_ARGB32 -- imageUtils.h:98-147: per channel, sum of the factor^2 quantised samples

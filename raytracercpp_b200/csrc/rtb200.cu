@@ -113,7 +113,8 @@ struct RtContext {
     bool camera_set = false;
 
     // per-frame work buffers
-    DevBuf<uint32_t> d_super, d_frame, q_hit_slot, q_refl_idx, q_tail, q_tail_off, q_tail_cnt, q_cont_link, q_cont_meta;
+    DevBuf<uint32_t> d_super, d_frame, q_hit_slot, q_refl_idx, q_split_base, q_split_active, q_split_occ;
+    DevBuf<uint4> q_items;
     std::map<TileKey, TileList> tile_lists;
     DevBuf<int32_t> q_tri;
     DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
@@ -126,7 +127,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, 512};
+    Tuning tune{16, 16, 8, 1, 256, 64};
     uint64_t opt_chunk_pixels = kChunkPixels;
     bool opt_screen_cull = true;
     bool opt_cost_order = false;
@@ -438,7 +439,7 @@ void rt_destroy(RtContext* ctx)
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_sorted); cudaFree(kv.second.d_cost); }
-    ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_tail.release(); ctx->q_tail_off.release(); ctx->q_tail_cnt.release(); ctx->q_cont_link.release(); ctx->q_cont_meta.release();
+    ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_split_base.release(); ctx->q_split_active.release(); ctx->q_split_occ.release(); ctx->q_items.release();
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
@@ -474,6 +475,10 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
     case RT_OPT_PACKET_ROUNDS:
         if (value < 0 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet rounds %lld", (long long)value);
         ctx->tune.packet_rounds = (int32_t)value;
+        return RT_OK;
+    case RT_OPT_ITEM_ROUNDS:
+        if (value < 1 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "item rounds %lld", (long long)value);
+        ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
     case RT_OPT_COST_ORDER: ctx->opt_cost_order = value != 0; return RT_OK;
@@ -694,12 +699,13 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
     const bool tail = ctx->tune.packets && ctx->tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
-    // continuation buffer: the stacks (<= RT_STACK_SIZE cells each) of the shadow packets that run out of rounds; a packet
-    // that finds it full is finished in place
-    const size_t cont_cap = tail ? std::min<size_t>(std::max<size_t>(qcap / 4, (size_t)1 << 16), (size_t)1 << 25) : 0;
+    // split records and work items of the shadow packets that run out of rounds; a packet that finds them full is
+    // finished in place
+    const size_t split_cap = tail ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
+    const size_t item_cap = tail ? std::min<size_t>(std::max<size_t>(qcap / 4, (size_t)1 << 14), (size_t)1 << 21) : 0;
     if (tail) {
-        RT_CUDA(ctx, ctx->q_tail.ensure(qcap)); RT_CUDA(ctx, ctx->q_tail_off.ensure(qcap)); RT_CUDA(ctx, ctx->q_tail_cnt.ensure(qcap));
-        RT_CUDA(ctx, ctx->q_cont_link.ensure(cont_cap)); RT_CUDA(ctx, ctx->q_cont_meta.ensure(cont_cap));
+        RT_CUDA(ctx, ctx->q_split_base.ensure(split_cap)); RT_CUDA(ctx, ctx->q_split_active.ensure(split_cap)); RT_CUDA(ctx, ctx->q_split_occ.ensure(split_cap));
+        RT_CUDA(ctx, ctx->q_items.ensure(item_cap * kItemPasses));
     }
     RT_CUDA(ctx, ctx->q_hit_slot.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
     RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
@@ -713,8 +719,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     wk.tile_cost = cost_order ? tl->d_cost : nullptr;
     QueueView q;
     q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
-    q.tail = ctx->q_tail.p; q.tail_off = ctx->q_tail_off.p; q.tail_cnt = ctx->q_tail_cnt.p;
-    q.cont_link = ctx->q_cont_link.p; q.cont_meta = ctx->q_cont_meta.p; q.cont_capacity = (uint32_t)cont_cap;
+    q.split_base = ctx->q_split_base.p; q.split_active = ctx->q_split_active.p; q.split_occ = ctx->q_split_occ.p;
+    q.items = ctx->q_items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
     q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
 
     cudaStream_t st = ctx->stream;
@@ -730,17 +736,18 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     }
 
     const bool count = ctx->opt_count_work;
-    static int grids[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    static int grids[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
     if (!grids[count][0]) {
         grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
         grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
-        grids[count][5] = grid_for(ctx, count ? (const void*)k_shade_tail<true> : (const void*)k_shade_tail<false>, kQueueThreads);
+        grids[count][5] = grid_for(ctx, count ? (const void*)k_shade_items<true> : (const void*)k_shade_items<false>, kQueueThreads);
+        grids[count][6] = grid_for(ctx, count ? (const void*)k_shade_finish<true> : (const void*)k_shade_finish<false>, kQueueThreads);
         grids[count][0] = grid_for(ctx, count ? (const void*)k_primary<true> : (const void*)k_primary<false>, kPrimaryThreads);
         grids[count][1] = grid_for(ctx, count ? (const void*)k_reflect<true> : (const void*)k_reflect<false>, kQueueThreads);
         grids[count][2] = grid_for(ctx, count ? (const void*)k_shade<true> : (const void*)k_shade<false>, kQueueThreads);
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
-    const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_tail = grids[count][5];
+    const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_items = grids[count][5], grid_finish = grids[count][6];
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
@@ -776,9 +783,13 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
             else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
             launches++;
             if (tail) {
-                if (count) k_shade_tail<true><<<grid_tail, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
-                else k_shade_tail<false><<<grid_tail, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
-                launches++;
+                for (int pass = 0; pass < kItemPasses; pass++) {
+                    if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, ctx->tune, pass);
+                    else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, ctx->tune, pass);
+                }
+                if (count) k_shade_finish<true><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                else k_shade_finish<false><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                launches += kItemPasses + 1;
             }
         }
     }
@@ -845,7 +856,13 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
                 sns += host_cnt[c].sum_packet_ns[w];
             }
             for (int b = 0; b < 16; b++) packets += hist[b];
-            if (w) { unsigned long long nt = 0; for (uint32_t c = 0; c < n_chunks; c++) nt += host_cnt[c].n_tail; fprintf(stderr, "[rtb200] tail queue %llu rays\n", nt); }
+            if (w) {
+                unsigned long long ns = 0, ni[kItemPasses] = {0};
+                for (uint32_t c = 0; c < n_chunks; c++) { ns += host_cnt[c].n_split; for (int p = 0; p < kItemPasses; p++) ni[p] += host_cnt[c].items_n[p]; }
+                fprintf(stderr, "[rtb200] split shadow packets %llu, work items per pass:", ns);
+                for (int p = 0; p < kItemPasses; p++) fprintf(stderr, " %llu", ni[p]);
+                fprintf(stderr, "\n");
+            }
             fprintf(stderr, "[rtb200] %s packets %llu  max rounds %u  max packet %.3f ms  mean packet %.1f us  log2(rounds) histogram:",
                     w ? "shadow" : "primary", packets, mx, mns * 1e-6, packets ? sns * 1e-3 / packets : 0.0);
             for (int b = 0; b < 16; b++) fprintf(stderr, " %u", hist[b]);

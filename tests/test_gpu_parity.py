@@ -275,24 +275,29 @@ def test_packet_and_single_ray_kernels_agree(cuda_lib, oracle, robot, name):
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
-def test_round_budget_and_tail_kernel_never_change_a_frame(cuda_lib, oracle, robot, name):
-    """RT_OPT_PACKET_ROUNDS hands the unanswered rays of long shadow packets to the one-ray-per-warp tail kernel
-    (k_shade_tail / coop_occluded).  With a budget of 1, 3 or 20 rounds nearly every shadow ray takes that route: the
-    frames must equal the unlimited-packet frame bit for bit, and the oracle's within the image tolerance."""
+def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name):
+    """RT_OPT_PACKET_ROUNDS / RT_OPT_ITEM_ROUNDS split shadow packets that run out of rounds into work items (one per
+    unvisited cell) that other warps trace for the same rays; answers are merged and the pixels stored by k_shade_finish.
+    With budgets of 1..20 rounds nearly every packet is split, items are split again, and on the larger frames the item
+    regions overflow (finish-in-place path): the frames must equal the unlimited-packet frame bit for bit."""
     kw, mats, tex = common.config_table(robot["materials"])[name]
     frames = {}
-    for rounds in (0, 1, 3, 20):
+    for rounds, item_rounds in ((0, 64), (1, 1), (3, 2), (20, 5), (2, 64)):
         r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
         r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, rounds)
+        r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, item_rounds)
         r.ray_trace()
-        frames[rounds] = (r.get_image().copy(), r.last_stats().as_dict())
+        frames[(rounds, item_rounds)] = (r.get_image().copy(), r.last_stats().as_dict())
         r.close()
-    for rounds in (1, 3, 20):
-        assert np.array_equal(frames[rounds][0], frames[0][0]), rounds
+    base = frames[(0, 64)]
+    for key, (img, st) in frames.items():
+        if key == (0, 64):
+            continue
+        assert np.array_equal(img, base[0]), key
         for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
-            assert frames[rounds][1][k] == frames[0][1][k]
-        assert frames[rounds][1]["kernel_launches"] == frames[0][1]["kernel_launches"] + 1
-    common.assert_image_close(frames[1][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through the tail kernel")
+            assert st[k] == base[1][k]
+        assert st["kernel_launches"] == base[1]["kernel_launches"] + 4      # 3 item passes + k_shade_finish
+    common.assert_image_close(frames[(1, 1)][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through split packets")
 
 
 def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
