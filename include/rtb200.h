@@ -158,12 +158,13 @@ enum {
     RT_OPT_PACKET_ROUNDS = 7, /* a shadow packet that needs more cell/leaf rounds than this (default 256; 0 = no limit) is
                                  split: each cell it has not visited becomes a work item another warp traces for the same
                                  32 rays (up to 3 item passes, the last without a limit).  Results do not depend on it   */
+    RT_OPT_PRIMARY_ROUNDS = 11,/* the same limit for primary (closest-hit) packets; their items merge the closest hit with a
+                                 64-bit atomicMin on (t, original index).  n > 0: always; 0: never; n < 0 (default -256):
+                                 |n| rounds, but only for launches short enough for one long packet to show (fewer than
+                                 256 packets per resident warp, e.g. one of 8 tile shards of a 4K 16-spp frame)          */
     RT_OPT_ITEM_ROUNDS = 10,  /* round limit of a work item in all item passes but the last (default 64)                */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
-    RT_OPT_COST_ORDER = 9,    /* 1 (default 0): a frame walks its tiles in descending order of the SM cycles their packets took in
-                                 the previous frame rendered with the same tile list, so that long packets start first;
-                                 the first frame uses the list's own order.  Results do not depend on it                */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.

@@ -29,7 +29,7 @@ constexpr int kPrimaryFetch = RTB_FETCH;     // 32-ray packets a warp of k_prima
 constexpr int kStepsPerCheck = 4;
 constexpr int kItemPasses = 3;      // launches of k_shade_items after k_shade_packet; the last one has no round budget
 #ifndef RTB_SHADE_MINB
-#define RTB_SHADE_MINB 6   /* resident CTAs per SM the compiler must allow for k_shade_packet (register bound) */
+#define RTB_SHADE_MINB 7   /* measured on cfg4: 7 CTAs/SM 8.9 ms, 6: 9.4, 8: 9.6 */
 #endif    // single-test steps between two refill / completion checks of a persistent warp
 
 struct ChunkCounters {               // one per chunk, zeroed before the frame
@@ -41,6 +41,7 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int n_split;            // shadow packets that ran out of rounds and were split into work items
     unsigned int items_n[kItemPasses];    // work items written for item pass p (each: one unvisited cell of a split packet)
     unsigned int items_next[kItemPasses]; // next item of pass p to take
+    unsigned int p_split, p_items_n[kItemPasses], p_items_next[kItemPasses];   // the same for split PRIMARY packets
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
@@ -93,18 +94,7 @@ struct WorkView {
     // Supersampled pixels outside [cull_x0, cull_x1] x [cull_y0, cull_y1] cannot hit the scene: the rectangle is the
     // screen-space bound of the root cell's box (host side, rt_render_device).  The whole frame when no bound exists.
     int32_t cull_x0, cull_y0, cull_x1, cull_y1;
-    // Per position in `tiles` (may be null): SM cycles spent by the packets of the tile, accumulated with one atomic per
-    // traced packet; the host orders the next frame's tiles by it (rt_render_device).
-    unsigned long long* tile_cost;
 };
-
-RT_DEV void note_tile_cost(const WorkView& wk, uint32_t slot, long long t0)
-{
-    if (wk.tile_cost && (threadIdx.x & 31u) == 0) {
-        const uint32_t pps = (uint32_t)wk.patches_per_side;
-        atomicAdd(&wk.tile_cost[wk.tile_begin + slot / (pps * pps * (uint32_t)(kPatch * kPatch))], (unsigned long long)(clock64() - t0));
-    }
-}
 
 struct QueueView {
     // dense, one per ray slot of the chunk (slot = position in patch order, see slot_pixel)
@@ -120,6 +110,9 @@ struct QueueView {
     uint32_t* split_occ;             // lanes found occluded since (atomicOr by the items)
     uint4* items;                    // kItemPasses regions of item_capacity: (split index, link, meta, -)
     uint32_t split_capacity, item_capacity;
+    // split primary packets (k_primary_packet -> k_primary_items -> k_primary_finish); item regions are shared with the
+    // shadow packets (the two never run at the same time), split_base / split_active too
+    unsigned long long* split_best;  // 32 per split record: bits(t) << 32 | original triangle index of the closest hit so far (atomicMin)
     uint32_t* refl_idx;              // reflection queue: indices into the hit queue
     float* refl_rgb;                 // 3 floats per hit-queue entry, written by k_reflect
     unsigned long long* refl_cnt;    // 3 words per hit-queue entry, written by k_reflect: rays | shadow rays << 32, V, T
@@ -153,6 +146,7 @@ struct Tuning {
     int32_t packets;          // 1: primary and shadow rays are traced as 32-ray packets (k_primary_packet / k_shade_packet)
     int32_t packet_rounds;    // a shadow packet that needs more cell/leaf rounds than this is split into work items (0: never)
     int32_t item_rounds;      // the same for the items of all passes but the last
+    int32_t primary_rounds;   // round budget of a primary packet (0: never split)
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -306,7 +300,7 @@ RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4&
 template <bool ANY, bool COUNT>
 RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
                          HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds,
-                         uint32_t start_link = 0u, uint32_t start_meta = 0u)
+                         uint32_t start_link = 0u, uint32_t start_meta = 0u, int32_t best_orig = 0x7fffffff)
 {
     const unsigned lane = threadIdx.x & 31u;
     SlabRay sr;
@@ -378,8 +372,11 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
                                 V3 q = o + t * d;                // renderer.cpp:351
                                 if (length2(p - q) < dist2) { occluded = true; active = false; }   // renderer.cpp:354
                             }
-                        } else if (t < t_max || (t == t_max && sc.orig[tri] < sc.orig[best.tri])) {
+                        } else if (t < t_max || (t == t_max && sc.orig[tri] < best_orig)) {
+                            // closest so far; a tie on t goes to the lower original index.  best_orig starts at
+                            // INT_MAX (root) or at the index of the hit other parts of a split packet have found
                             t_max = t;
+                            best_orig = sc.orig[tri];
                             best.tri = (int32_t)tri; best.t = t; best.u = u; best.v = v;
                         }
                     }
@@ -402,12 +399,34 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
     }
 }
 
+// A packet (or item) that ran out of rounds: every unvisited cell K.link/meta[0, K.saved) becomes one work item of item
+// pass `pass` for split record `sidx`.  Returns false when the item region is full (the caller then finishes in place);
+// the slots it was handed are still filled (with null items) so that the region never holds garbage.
+RT_DEV bool emit_items(const QueueView& q, unsigned int* items_n, const PacketStack& K, int pass, uint32_t sidx)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = (uint32_t)K.saved;
+    uint32_t at = 0;
+    if (lane == 0) at = atomicAdd(&items_n[pass], n);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    const bool ok = at + n <= q.item_capacity;
+    uint4* region = q.items + (size_t)pass * q.item_capacity;
+    for (uint32_t i = lane; i < n && at + i < q.item_capacity; i += 32u)
+        region[at + i] = ok ? make_uint4(sidx, K.link[i], K.meta[i], 0u) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+    __syncwarp();
+    return ok;
+}
+
+// Closest hit of a split primary packet, merged over its work items with atomicMin: t >= 0, so the bits of t order like
+// t; a tie on t goes to the lower original index -- the rule of packet_trace.
+RT_DEV unsigned long long closest_key(float t, int32_t orig) { return ((unsigned long long)__float_as_uint(t) << 32) | (uint32_t)orig; }
+constexpr unsigned long long kNoHitKey = ~0ull;
+
 // Packet version of k_primary: a warp takes 32 consecutive ray slots (an 8x4 pixel block) per fetch.
-#ifdef RTB_PRIMARY_MINB
-#define RTB_PRIMARY_BOUNDS __launch_bounds__(kPrimaryThreads, RTB_PRIMARY_MINB)
-#else
-#define RTB_PRIMARY_BOUNDS __launch_bounds__(kPrimaryThreads)
+#ifndef RTB_PRIMARY_MINB
+#define RTB_PRIMARY_MINB 8   /* measured on cfg4: 8 CTAs/SM (64 registers, some spills) 7.5 ms, 7: 7.6, 6 (80, none): 8.0, 5: 8.6 -- latency-bound */
 #endif
+#define RTB_PRIMARY_BOUNDS __launch_bounds__(kPrimaryThreads, RTB_PRIMARY_MINB)
 template <bool COUNT>
 __global__ void RTB_PRIMARY_BOUNDS
 k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
@@ -447,16 +466,30 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
                 }
                 continue;
             }
-            const long long c0 = clock64();
             if (active) primary_ray(fr, px, py, o, d);
             HitRec best;
             bool occ, live = active;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
+            const bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds);
             __syncwarp();
-            note_tile_cost(wk, base, c0);
             if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
+            if (!finished) {
+                // out of rounds: the closest hits so far go to a split record, every unvisited cell becomes a work item
+                const unsigned am = __ballot_sync(0xffffffffu, active);
+                uint32_t sidx = 0;
+                if (lane == 0) sidx = atomicAdd(&cnt->p_split, 1u);
+                sidx = __shfl_sync(0xffffffffu, sidx, 0);
+                if (sidx < q.split_capacity && emit_items(q, cnt->p_items_n, K, 0, sidx)) {
+                    if (lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = am; }
+                    q.split_best[(size_t)sidx * 32u + lane] = (active && best.tri >= 0) ? closest_key(best.t, sc.orig[best.tri]) : kNoHitKey;
+                    continue;                                                  // k_primary_finish writes these slots
+                }
+                if (sidx < q.split_capacity && lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = 0u; }
+                live = active;                                                 // no room: trace it here, from the root
+                packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
+                __syncwarp();
+            }
             if (slot < total) {
                 const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
                 q.slot_tri[slot] = hit ? best.tri : -1;
@@ -467,6 +500,99 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
+}
+
+// Item pass of the split primary packets: a warp takes one unvisited cell of a split packet, rebuilds the packet's 32
+// primary rays, starts every lane at the closest hit the record holds so far (cells beyond it are pruned), traces from
+// that cell and merges what it finds with atomicMin.  An item that runs out of rounds is split again.
+template <bool COUNT>
+__global__ void RTB_PRIMARY_BOUNDS
+k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, Tuning tune, int pass)
+{
+    __shared__ PacketStack stacks[kPrimaryThreads / 32];
+    PacketStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = min(cnt->p_items_n[pass], q.item_capacity);
+    const uint4* region = q.items + (size_t)pass * q.item_capacity;
+    const int budget = pass + 1 < kItemPasses ? tune.item_rounds : 0;
+    TraceCounters tc = zero_counters();
+    unsigned overflow = 0;
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&cnt->p_items_next[pass], 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const uint4 item = region[i];
+        const uint32_t sidx = item.x;
+        if (sidx == 0xffffffffu) continue;
+        const uint32_t base = q.split_base[sidx];
+        const uint32_t slot = base + lane;
+        const bool active = ((q.split_active[sidx] >> lane) & 1u) != 0u;
+        int px = 0, py = 0;
+        V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
+        if (active) { slot_pixel(wk, fr, slot, px, py); primary_ray(fr, px, py, o, d); }
+        unsigned long long* mine = q.split_best + (size_t)sidx * 32u + lane;
+        const unsigned long long seen = *((volatile unsigned long long*)mine);
+        const float t_start = seen == kNoHitKey ? INFINITY : __uint_as_float((uint32_t)(seen >> 32));
+        const int32_t orig_start = seen == kNoHitKey ? 0x7fffffff : (int32_t)(uint32_t)seen;
+        HitRec best;
+        bool occ, live = active;
+        unsigned rounds = 0;
+        bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start);
+        __syncwarp();
+        if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
+        if (!finished && !emit_items(q, cnt->p_items_n, K, pass + 1, sidx)) {
+            // no room: finish the item here (from its cell again, now pruned by what it has just found)
+            const unsigned long long now = *((volatile unsigned long long*)mine);
+            const float t2 = now == kNoHitKey ? INFINITY : __uint_as_float((uint32_t)(now >> 32));
+            const int32_t o2 = now == kNoHitKey ? 0x7fffffff : (int32_t)(uint32_t)now;
+            live = active;
+            packet_trace<false, COUNT>(sc, K, live, o, d, t2, o, 0.0f, best, occ, tc, overflow, 0, rounds, item.y, item.z, o2);
+            __syncwarp();
+            if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
+        }
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
+}
+
+// After the item passes: the slot records (or miss colours) of the split primary packets.  The merged key names the
+// triangle by its original index; one more ray/triangle test of that triangle reproduces t, u, v bit for bit.
+__global__ void __launch_bounds__(kPrimaryThreads)
+k_primary_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = min(cnt->p_split, q.split_capacity);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sidx < n; sidx += warps) {
+        const uint32_t am = q.split_active[sidx];
+        if (am == 0u) continue;                                                // traced in place after all
+        const uint32_t slot = q.split_base[sidx] + lane;
+        const unsigned long long key = q.split_best[(size_t)sidx * 32u + lane];
+        if ((am >> lane) & 1u) {
+            int px = 0, py = 0;
+            V3 o, d;
+            slot_pixel(wk, fr, slot, px, py);
+            primary_ray(fr, px, py, o, d);
+            bool hit = false;
+            if (key != kNoHitKey) {
+                const uint32_t tri = (uint32_t)sc.leaf_of[(uint32_t)key];
+                const rt_f4* tp = sc.tris + 3 * (size_t)tri;
+                float t, u, v;
+                if (tri_test(RT_LDG4(tp), RT_LDG4(tp + 1), RT_LDG4(tp + 2), o, -d, t, u, v) && t > 0.1f) {   // min_t, renderer.cpp:1039
+                    hit = true;
+                    q.slot_tri[slot] = (int32_t)tri; q.slot_t[slot] = t; q.slot_u[slot] = u; q.slot_v[slot] = v;
+                }
+            }
+            if (!hit) {
+                q.slot_tri[slot] = -1;
+                super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+            }
+        } else {
+            const uint32_t pps = (uint32_t)wk.patches_per_side;
+            if (slot < (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch)) q.slot_tri[slot] = -1;   // slot without a ray
+        }
+    }
 }
 
 // Ordered stream compaction of the slot records into the hit queue.  A block owns kCompactSlots consecutive slots:
@@ -711,24 +837,6 @@ RT_DEV void shade_epilogue(ChunkCounters* cnt, TraceCounters& tc, TraceCounters&
     if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
 }
 
-// A packet (or item) that ran out of rounds: every unvisited cell K.link/meta[0, K.saved) becomes one work item of item
-// pass `pass` for split record `sidx`.  Returns false when the item region is full (the caller then finishes in place);
-// the slots it was handed are still filled (with null items) so that the region never holds garbage.
-RT_DEV bool emit_items(const QueueView& q, ChunkCounters* cnt, const PacketStack& K, int pass, uint32_t sidx)
-{
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t n = (uint32_t)K.saved;
-    uint32_t at = 0;
-    if (lane == 0) at = atomicAdd(&cnt->items_n[pass], n);
-    at = __shfl_sync(0xffffffffu, at, 0);
-    const bool ok = at + n <= q.item_capacity;
-    uint4* region = q.items + (size_t)pass * q.item_capacity;
-    for (uint32_t i = lane; i < n && at + i < q.item_capacity; i += 32u)
-        region[at + i] = ok ? make_uint4(sidx, K.link[i], K.meta[i], 0u) : make_uint4(0xffffffffu, 0u, 0u, 0u);
-    __syncwarp();
-    return ok;
-}
-
 // Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
 // them, traces their 32 shadow rays as one packet, composes and stores.  A packet that runs out of rounds
 // (RT_OPT_PACKET_ROUNDS) stores the pixels it has an answer for and is split into work items for the rest.
@@ -748,7 +856,6 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
-        const long long c0 = clock64();
         const uint32_t entry = base + lane;
         const bool valid = entry < n;
         ShadeLane L;
@@ -773,7 +880,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
                 uint32_t sidx = 0;
                 if (lane == 0) sidx = atomicAdd(&cnt->n_split, 1u);
                 sidx = __shfl_sync(0xffffffffu, sidx, 0);
-                if (sidx < q.split_capacity && emit_items(q, cnt, K, 0, sidx)) {
+                if (sidx < q.split_capacity && emit_items(q, cnt->items_n, K, 0, sidx)) {
                     if (lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = dm; q.split_occ[sidx] = 0u; }
                     deferred = active;                                         // k_shade_finish stores these pixels
                 } else {
@@ -786,7 +893,6 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
             }
         }
         if (valid && !deferred) shade_store<COUNT>(sc, fr, q, entry, L, occluded, fan, super);
-        if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[base], c0);
     }
     shade_epilogue<COUNT>(cnt, tc, fan, overflow);
 }
@@ -820,7 +926,6 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         const uint32_t entry = base + lane;
         bool active = entry < n_hits && ((live >> lane) & 1u) != 0u;
         if (__ballot_sync(0xffffffffu, active) == 0u) continue;                // every ray has been answered meanwhile
-        const long long c0 = clock64();
         ShadeLane L;
         L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
         if (active) L = shade_prepare(sc, fr, wk, q, entry);
@@ -834,7 +939,7 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
                                                   item.y, item.z);
         __syncwarp();
-        if (!finished && !emit_items(q, cnt, K, pass + 1, sidx)) {
+        if (!finished && !emit_items(q, cnt->items_n, K, pass + 1, sidx)) {
             const bool before = occluded;                                      // no room: finish the item here
             packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z);
             occluded = occluded || before;
@@ -842,7 +947,6 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         }
         const unsigned om = __ballot_sync(0xffffffffu, occluded);
         if (om != 0u && lane == 0) atomicOr(&q.split_occ[sidx], om);
-        if (wk.tile_cost) note_tile_cost(wk, q.hit_slot[base], c0);
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
     if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);

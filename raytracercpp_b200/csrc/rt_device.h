@@ -50,6 +50,7 @@ struct SceneView {
     const rt_f4* shade;     // 2 per triangle, leaf order
     const rt_f4* mats;      // 4 per material (RtMaterial = 16 floats)
     const int32_t* orig;    // leaf order -> index in the caller's array (tie-break + reported ids)
+    const int32_t* leaf_of; // the inverse: index in the caller's array -> leaf order (split primary packets)
     int32_t n_mats;
     uint32_t n_tris;
     TexView tex[RT_TEX_COUNT];

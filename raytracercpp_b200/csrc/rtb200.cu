@@ -74,12 +74,6 @@ struct TileList {
     uint32_t count = 0;
     int tiles_x = 0;
     std::vector<uint32_t> host;
-    // cost-ordered rendering (RT_OPT_COST_ORDER): SM cycles the packets of each tile took in the last frame rendered with
-    // this list; the next frame walks the tiles in descending order of it so that the long packets start first
-    std::vector<float> cost;             // by position in `host`; empty until a frame has been rendered
-    std::vector<uint32_t> order;         // positions in `host`, the order the last frame used
-    uint32_t* d_sorted = nullptr;        // host[order[i]]
-    unsigned long long* d_cost = nullptr; // per position in d_sorted, accumulated by the kernels
 };
 typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile_size, tile_mod, tile_rem (-1: all shards, padded)
 
@@ -101,7 +95,7 @@ struct RtContext {
     bool bvh_valid = false;
     RtBvhInfo info{};
     DevBuf<float4> d_recs, d_tris, d_shade, d_mats;
-    DevBuf<int32_t> d_orig;
+    DevBuf<int32_t> d_orig, d_leaf_of;
     uint32_t n_tris = 0;
     int n_mats = 0;
     bool any_reflective = false;
@@ -114,6 +108,7 @@ struct RtContext {
 
     // per-frame work buffers
     DevBuf<uint32_t> d_super, d_frame, q_hit_slot, q_refl_idx, q_split_base, q_split_active, q_split_occ;
+    DevBuf<unsigned long long> q_split_best;
     DevBuf<uint4> q_items;
     std::map<TileKey, TileList> tile_lists;
     DevBuf<int32_t> q_tri;
@@ -127,10 +122,9 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, 256, 64};
+    Tuning tune{16, 16, 8, 1, 256, 64, -256};
     uint64_t opt_chunk_pixels = kChunkPixels;
     bool opt_screen_cull = true;
-    bool opt_cost_order = false;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -201,6 +195,7 @@ SceneView scene_view(const RtContext* ctx)
     sc.shade = ctx->d_shade.p;
     sc.mats = ctx->d_mats.p;
     sc.orig = ctx->d_orig.p;
+    sc.leaf_of = ctx->d_leaf_of.p;
     sc.n_mats = ctx->n_mats;
     sc.n_tris = ctx->n_tris;
     for (int i = 0; i < RT_TEX_COUNT; i++) {
@@ -337,7 +332,7 @@ int get_tile_list(RtContext* ctx, const RtSettings* s, int tile_size, int tile_m
     if (it == ctx->tile_lists.end()) {
         if (ctx->tile_lists.size() > 64) {                         // a caller cycling through frame sizes: start over
             RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_sorted); cudaFree(kv.second.d_cost); }
+            for (auto& kv : ctx->tile_lists) cudaFree(kv.second.d);
             ctx->tile_lists.clear();
         }
         TileList tl;
@@ -435,11 +430,11 @@ void rt_destroy(RtContext* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release();
+    ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release();
-    for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_sorted); cudaFree(kv.second.d_cost); }
-    ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_split_base.release(); ctx->q_split_active.release(); ctx->q_split_occ.release(); ctx->q_items.release();
+    for (auto& kv : ctx->tile_lists) cudaFree(kv.second.d);
+    ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_split_base.release(); ctx->q_split_active.release(); ctx->q_split_occ.release(); ctx->q_items.release(); ctx->q_split_best.release();
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
@@ -476,12 +471,15 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         if (value < 0 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet rounds %lld", (long long)value);
         ctx->tune.packet_rounds = (int32_t)value;
         return RT_OK;
+    case RT_OPT_PRIMARY_ROUNDS:
+        if (value < -(1 << 30) || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "primary rounds %lld", (long long)value);
+        ctx->tune.primary_rounds = (int32_t)value;
+        return RT_OK;
     case RT_OPT_ITEM_ROUNDS:
         if (value < 1 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "item rounds %lld", (long long)value);
         ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
-    case RT_OPT_COST_ORDER: ctx->opt_cost_order = value != 0; return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -532,11 +530,15 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     RT_CUDA(ctx, ctx->d_tris.ensure(flat.tris.size()));
     RT_CUDA(ctx, ctx->d_shade.ensure(flat.shade.size()));
     RT_CUDA(ctx, ctx->d_orig.ensure(flat.orig.size()));
+    RT_CUDA(ctx, ctx->d_leaf_of.ensure(flat.orig.size()));
+    std::vector<int32_t> leaf_of(flat.orig.size());
+    for (size_t i = 0; i < flat.orig.size(); i++) leaf_of[(size_t)flat.orig[i]] = (int32_t)i;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_recs.p, flat.recs.data(), flat.recs.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
     if (n) {
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris.p, flat.tris.data(), flat.tris.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_shade.p, flat.shade.data(), flat.shade.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_orig.p, flat.orig.data(), flat.orig.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_leaf_of.p, leaf_of.data(), leaf_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double t2 = now_ms();
@@ -669,21 +671,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     TileList* tl = nullptr;
     if (int r = get_tile_list(ctx, s, tile_size, tile_mod, tile_rem, &tl)) return r;
-    // the tiles in the order this frame walks them: descending cost of the previous frame (same list, any order gives
-    // the same frame), or the list's own order when there is no history
-    const bool cost_order = ctx->opt_cost_order && tl->count > 1;
-    std::vector<uint32_t> tiles = tl->host;
-    if (cost_order) {
-        if (!tl->d_sorted) {
-            RT_CUDA(ctx, cudaMalloc((void**)&tl->d_sorted, tl->count * sizeof(uint32_t)));
-            RT_CUDA(ctx, cudaMalloc((void**)&tl->d_cost, tl->count * sizeof(unsigned long long)));
-        }
-        tl->order.resize(tl->count);
-        for (uint32_t i = 0; i < tl->count; i++) tl->order[i] = i;
-        if (tl->cost.size() == tl->count)
-            std::stable_sort(tl->order.begin(), tl->order.end(), [&](uint32_t a, uint32_t b) { return tl->cost[a] > tl->cost[b]; });
-        for (uint32_t i = 0; i < tl->count; i++) tiles[i] = tl->host[tl->order[i]];
-    }
+    const std::vector<uint32_t>& tiles = tl->host;
     const int tiles_x = tl->tiles_x;
     WorkView wk = {};
     wk.tiles_x = tiles_x;
@@ -699,14 +687,25 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
     const bool tail = ctx->tune.packets && ctx->tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
-    // split records and work items of the shadow packets that run out of rounds; a packet that finds them full is
-    // finished in place
-    const size_t split_cap = tail ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
-    const size_t item_cap = tail ? std::min<size_t>(std::max<size_t>(qcap / 4, (size_t)1 << 14), (size_t)1 << 21) : 0;
-    if (tail) {
+    // Primary packets are split only when the launch is short enough for one long packet to show: fewer than 256 packets
+    // per resident warp (a whole 4K 16-spp frame on one GPU has ~1000 and hides its stragglers; an eighth of it does not).
+    // RT_OPT_PRIMARY_ROUNDS < 0 selects this rule with |value| rounds, > 0 forces splitting, 0 turns it off.
+    bool psplit = ctx->tune.packets && ctx->tune.primary_rounds != 0;
+    if (psplit && ctx->tune.primary_rounds < 0) {
+        const int pw = grid_for(ctx, (const void*)k_primary_packet<false>, kPrimaryThreads) * (kPrimaryThreads / 32);
+        psplit = (uint64_t)tiles.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
+    }
+    Tuning tune = ctx->tune;
+    tune.primary_rounds = psplit ? std::abs(ctx->tune.primary_rounds) : 0;
+    // split records and work items of the packets that run out of rounds; a packet that finds them full is finished in
+    // place.  Primary and shadow packets never run at the same time and share the storage.
+    const size_t split_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
+    const size_t item_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 4, (size_t)1 << 14), (size_t)1 << 21) : 0;
+    if (tail || psplit) {
         RT_CUDA(ctx, ctx->q_split_base.ensure(split_cap)); RT_CUDA(ctx, ctx->q_split_active.ensure(split_cap)); RT_CUDA(ctx, ctx->q_split_occ.ensure(split_cap));
         RT_CUDA(ctx, ctx->q_items.ensure(item_cap * kItemPasses));
     }
+    if (psplit) RT_CUDA(ctx, ctx->q_split_best.ensure(split_cap * 32));
     RT_CUDA(ctx, ctx->q_hit_slot.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
     RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
     if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, ctx->q_refl_cnt.ensure(3 * qcap)); }
@@ -715,11 +714,11 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
         super = ctx->d_super.p;
     }
-    wk.tiles = cost_order ? tl->d_sorted : tl->d;
-    wk.tile_cost = cost_order ? tl->d_cost : nullptr;
+    wk.tiles = tl->d;
     QueueView q;
     q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
     q.split_base = ctx->q_split_base.p; q.split_active = ctx->q_split_active.p; q.split_occ = ctx->q_split_occ.p;
+    q.split_best = ctx->q_split_best.p;
     q.items = ctx->q_items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
     q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
 
@@ -730,36 +729,42 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
     RT_CUDA(ctx, cudaEventRecord(ev_begin, st));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
-    if (cost_order) {
-        RT_CUDA(ctx, cudaMemcpyAsync(tl->d_sorted, tiles.data(), tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        RT_CUDA(ctx, cudaMemsetAsync(tl->d_cost, 0, tl->count * sizeof(unsigned long long), st));
-    }
 
     const bool count = ctx->opt_count_work;
-    static int grids[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
+    static int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
     if (!grids[count][0]) {
         grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
         grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
         grids[count][5] = grid_for(ctx, count ? (const void*)k_shade_items<true> : (const void*)k_shade_items<false>, kQueueThreads);
+        grids[count][7] = grid_for(ctx, count ? (const void*)k_primary_items<true> : (const void*)k_primary_items<false>, kPrimaryThreads);
+        grids[count][8] = grid_for(ctx, (const void*)k_primary_finish, kPrimaryThreads);
         grids[count][6] = grid_for(ctx, count ? (const void*)k_shade_finish<true> : (const void*)k_shade_finish<false>, kQueueThreads);
         grids[count][0] = grid_for(ctx, count ? (const void*)k_primary<true> : (const void*)k_primary<false>, kPrimaryThreads);
         grids[count][1] = grid_for(ctx, count ? (const void*)k_reflect<true> : (const void*)k_reflect<false>, kQueueThreads);
         grids[count][2] = grid_for(ctx, count ? (const void*)k_shade<true> : (const void*)k_shade<false>, kQueueThreads);
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
-    const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_items = grids[count][5], grid_finish = grids[count][6];
+    const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_items = grids[count][5], grid_finish = grids[count][6], grid_pitems = grids[count][7], grid_pfinish = grids[count][8];
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
         ChunkCounters* cnt = ctx->d_counters.p + c;
         {
             ScopedTimer tm(ctx, ST_PRIMARY);
-            if (ctx->tune.packets) {
-                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-            } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            if (tune.packets) {
+                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+            } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+            else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             launches++;
+            if (psplit) {
+                for (int pass = 0; pass < kItemPasses; pass++) {
+                    if (count) k_primary_items<true><<<grid_pitems, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
+                    else k_primary_items<false><<<grid_pitems, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
+                }
+                k_primary_finish<<<grid_pfinish, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                launches += kItemPasses + 1;
+            }
         }
         {
             ScopedTimer tm(ctx, ST_COMPACT);
@@ -776,16 +781,16 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         }
         {
             ScopedTimer tm(ctx, ST_SHADE);
-            if (ctx->tune.packets) {
-                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-            } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
-            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, ctx->tune);
+            if (tune.packets) {
+                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+            } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             launches++;
             if (tail) {
                 for (int pass = 0; pass < kItemPasses; pass++) {
-                    if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, ctx->tune, pass);
-                    else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, ctx->tune, pass);
+                    if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
+                    else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                 }
                 if (count) k_shade_finish<true><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
                 else k_shade_finish<false><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
@@ -805,14 +810,8 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     std::vector<ChunkCounters> host_cnt(std::max<uint32_t>(n_chunks, 1));
     RT_CUDA(ctx, cudaMemcpyAsync(host_cnt.data(), ctx->d_counters.p, sizeof(ChunkCounters) * host_cnt.size(), cudaMemcpyDeviceToHost, st));
-    std::vector<unsigned long long> host_cost(cost_order ? tl->count : 0);
-    if (cost_order) RT_CUDA(ctx, cudaMemcpyAsync(host_cost.data(), tl->d_cost, tl->count * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RT_CUDA(ctx, cudaStreamSynchronize(st));
 
-    if (cost_order && ctx->tune.packets) {
-        tl->cost.assign(tl->count, 0.0f);
-        for (uint32_t i = 0; i < tl->count; i++) tl->cost[tl->order[i]] = (float)host_cost[i];
-    }
     RtRenderStats rs;
     memset(&rs, 0, sizeof(rs));
     bool overflow = false;
@@ -860,6 +859,11 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
                 unsigned long long ns = 0, ni[kItemPasses] = {0};
                 for (uint32_t c = 0; c < n_chunks; c++) { ns += host_cnt[c].n_split; for (int p = 0; p < kItemPasses; p++) ni[p] += host_cnt[c].items_n[p]; }
                 fprintf(stderr, "[rtb200] split shadow packets %llu, work items per pass:", ns);
+                for (int p = 0; p < kItemPasses; p++) fprintf(stderr, " %llu", ni[p]);
+                ns = 0;
+                for (int p = 0; p < kItemPasses; p++) ni[p] = 0;
+                for (uint32_t c = 0; c < n_chunks; c++) { ns += host_cnt[c].p_split; for (int p = 0; p < kItemPasses; p++) ni[p] += host_cnt[c].p_items_n[p]; }
+                fprintf(stderr, "\n[rtb200] split primary packets %llu, work items per pass:", ns);
                 for (int p = 0; p < kItemPasses; p++) fprintf(stderr, " %llu", ni[p]);
                 fprintf(stderr, "\n");
             }

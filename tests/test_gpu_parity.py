@@ -285,6 +285,7 @@ def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name
     for rounds, item_rounds in ((0, 64), (1, 1), (3, 2), (20, 5), (2, 64)):
         r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
         r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, rounds)
+        r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, rounds)                 # primary packets: closest hit merged with atomicMin
         r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, item_rounds)
         r.ray_trace()
         frames[(rounds, item_rounds)] = (r.get_image().copy(), r.last_stats().as_dict())
@@ -296,8 +297,32 @@ def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name
         assert np.array_equal(img, base[0]), key
         for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
             assert st[k] == base[1][k]
-        assert st["kernel_launches"] == base[1]["kernel_launches"] + 4      # 3 item passes + k_shade_finish
+        assert st["kernel_launches"] == base[1]["kernel_launches"] + 8      # (3 item passes + finish) for primary and for shadow packets
     common.assert_image_close(frames[(1, 1)][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through split packets")
+
+
+def test_split_primary_packets_keep_ids_and_ties(cuda_lib, oracle):
+    """Split primary packets on a scene made of 60 coincident copies of a few triangles (every hit is a tie on t between
+    copies in different leaves' order): the merged closest hit must be the lowest original index, as without splitting."""
+    tri = common.triangle_soup(40, 3, size=0.6, center=(0, 0, -4), spread=0.8)
+    soup = np.tile(tri, (60, 1)).astype(np.float32)
+    # copy k of every triangle has material k, in a random order of the copies: which copy wins a tie is visible
+    perm = np.random.default_rng(5).permutation(60)
+    mats = rt.precompute_materials([dict(scenes.DEFAULT_SPHERE_MATERIAL, diffuse=(k / 60.0, 1 - k / 60.0, 0.5)) for k in range(60)])
+    scene = dict(xyz9=soup, uv6=None, mat=np.repeat(perm, 40).astype(np.int32))
+    kw = dict(image_width=128, image_height=72, compute_shadows=0)
+    out = []
+    for rounds in (0, 1, 2):
+        r = common.product_renderer(cuda_lib, scene, kw, mats, {})
+        r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, rounds)
+        r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, 1)
+        r.ray_trace()
+        out.append((r.get_image().copy(), r.last_stats().primary_hits))
+        r.close()
+    assert out[0][1] > 200
+    for img, hits in out[1:]:
+        assert np.array_equal(img, out[0][0]) and hits == out[0][1]
+    common.assert_image_close(out[1][0], common.oracle_image(oracle, scene, kw, mats, {}), what="split primary packets, coincident triangles")
 
 
 def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
@@ -326,34 +351,6 @@ def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
             for k in ("primary_rays", "primary_hits", "shadow_rays", "reflection_rays"):
                 assert frames[0][1][k] == frames[1][1][k], (name, i, k)
             common.assert_image_close(frames[0][0], common.oracle_image(oracle, robot, kw, mats, tex, cam=cam), what=f"{name} camera {i}")
-
-
-def test_cost_ordered_tiles_never_change_a_frame(cuda_lib, robot):
-    """RT_OPT_COST_ORDER re-orders the tiles of frame n+1 by what their packets cost in frame n: consecutive frames of
-    the same context (first without history, then re-ordered) and the frame of a context that never re-orders are
-    bit-identical, with the same ray counts; also for a 3-shard split."""
-    import torch
-    kw, mats, tex = common.config_table(robot["materials"])["cfg2"]
-    ref = common.product_renderer(cuda_lib, robot, kw, mats, tex)
-    ref.ctx.set_option(api.RT_OPT_COST_ORDER, 0)
-    ref.ray_trace()
-    want, want_stats = ref.get_image().copy(), ref.last_stats().as_dict()
-    ref.close()
-    r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
-    r.ctx.set_option(api.RT_OPT_COST_ORDER, 1)
-    for frame_no in range(3):
-        r.ray_trace()
-        assert np.array_equal(r.get_image(), want), frame_no
-        for k in ("primary_rays", "shadow_rays", "primary_hits"):
-            assert r.last_stats().as_dict()[k] == want_stats[k]
-    s = r.render_settings()
-    for frame_no in range(2):
-        frame = torch.zeros(want.shape, dtype=torch.int32, device="cuda")
-        for rem in range(3):
-            r.ctx.render_device(s, frame.data_ptr(), 16, 3, rem)
-        torch.cuda.synchronize()
-        assert np.array_equal(frame.cpu().numpy().view(np.uint32), want)
-    r.close()
 
 
 def test_cpp_adapter_example(cuda_lib, tmp_path):
