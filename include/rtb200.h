@@ -157,7 +157,7 @@ enum {
                                  not depend on it                                                                       */
     RT_OPT_PACKET_ROUNDS = 7, /* a shadow packet that needs more cell/leaf rounds than this (default 256; 0 = no limit) is
                                  split: each cell it has not visited becomes a work item another warp traces for the same
-                                 32 rays (up to 3 item passes, the last without a limit).  Results do not depend on it   */
+                                 32 rays (up to 6 item passes, the last without a limit).  Results do not depend on it   */
     RT_OPT_PRIMARY_ROUNDS = 11,/* the same limit for primary (closest-hit) packets; their items merge the closest hit with a
                                  64-bit atomicMin on (t, original index).  n > 0: always; 0: never; n < 0 (default -256):
                                  |n| rounds, but only for launches short enough for one long packet to show (fewer than

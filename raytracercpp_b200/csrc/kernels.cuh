@@ -27,7 +27,10 @@ constexpr int kQueueThreads = 128;
 #endif
 constexpr int kPrimaryFetch = RTB_FETCH;     // 32-ray packets a warp of k_primary_packet takes per atomic
 constexpr int kStepsPerCheck = 4;
-constexpr int kItemPasses = 3;      // launches of k_shade_items after k_shade_packet; the last one has no round budget
+#ifndef RTB_ITEM_PASSES
+#define RTB_ITEM_PASSES 6
+#endif
+constexpr int kItemPasses = RTB_ITEM_PASSES;      // launches of k_shade_items after k_shade_packet; the last one has no round budget
 #ifndef RTB_SHADE_MINB
 #define RTB_SHADE_MINB 7   /* measured on cfg4: 7 CTAs/SM 8.9 ms, 6: 9.4, 8: 9.6 */
 #endif    // single-test steps between two refill / completion checks of a persistent warp

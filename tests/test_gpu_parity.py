@@ -297,7 +297,7 @@ def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name
         assert np.array_equal(img, base[0]), key
         for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
             assert st[k] == base[1][k]
-        assert st["kernel_launches"] == base[1]["kernel_launches"] + 8      # (3 item passes + finish) for primary and for shadow packets
+        assert st["kernel_launches"] == base[1]["kernel_launches"] + 14     # (6 item passes + finish) for primary and for shadow packets
     common.assert_image_close(frames[(1, 1)][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through split packets")
 
 
