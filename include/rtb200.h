@@ -155,14 +155,15 @@ enum {
     RT_OPT_PACKETS = 6,       /* 1 (default): primary and shadow rays are traced as 32-ray packets (one traversal per
                                  warp); 0: every lane runs its own traversal state machine with lane refill.  Results do
                                  not depend on it                                                                       */
-    RT_OPT_PACKET_ROUNDS = 7, /* a shadow packet that needs more cell/leaf rounds than this (default 256; 0 = no limit) is
-                                 split: each cell it has not visited becomes a work item another warp traces for the same
-                                 32 rays (up to 6 item passes, the last without a limit).  Results do not depend on it   */
-    RT_OPT_PRIMARY_ROUNDS = 11,/* the same limit for primary (closest-hit) packets; their items merge the closest hit with a
-                                 64-bit atomicMin on (t, original index).  n > 0: always; 0: never; n < 0 (default -256):
-                                 |n| rounds, but only for launches short enough for one long packet to show (fewer than
-                                 256 packets per resident warp, e.g. one of 8 tile shards of a 4K 16-spp frame)          */
-    RT_OPT_ITEM_ROUNDS = 10,  /* round limit of a work item in all item passes but the last (default 64)                */
+    /* Round budgets of the 32-ray packets.  A packet that needs more cell/leaf rounds than its budget is SPLIT: each cell
+       it has not visited becomes a work item that another warp traces for the same 32 rays (items can be split again, 6
+       generations deep, the last without a limit); answers are merged (shadow: OR, primary: 64-bit atomicMin on
+       (t, original index)).  n > 0: n rounds; 0: never split; n < 0 (the defaults): |n| rounds for a long launch, |n| / 2
+       for a short one (fewer than 256 packets per resident warp, e.g. one of 8 tile shards of a 4K 16-spp frame), where
+       one long packet shows in the launch time.  Results do not depend on any of them. */
+    RT_OPT_PACKET_ROUNDS = 7, /* shadow packets (default -256)                                                           */
+    RT_OPT_PRIMARY_ROUNDS = 11,/* primary packets (default -256; negative additionally means: not split in long launches) */
+    RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -64; 0 is invalid)                 */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a

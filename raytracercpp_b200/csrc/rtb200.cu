@@ -122,7 +122,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, 256, 64, -256};
+    Tuning tune{16, 16, 8, 1, -256, -64, -256};
     uint64_t opt_chunk_pixels = kChunkPixels;
     bool opt_screen_cull = true;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
@@ -468,7 +468,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->tune.packets = value != 0;
         return RT_OK;
     case RT_OPT_PACKET_ROUNDS:
-        if (value < 0 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet rounds %lld", (long long)value);
+        if (value < -(1 << 30) || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "packet rounds %lld", (long long)value);
         ctx->tune.packet_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_PRIMARY_ROUNDS:
@@ -476,7 +476,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->tune.primary_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_ITEM_ROUNDS:
-        if (value < 1 || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "item rounds %lld", (long long)value);
+        if (value == 0 || value < -(1 << 30) || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "item rounds %lld", (long long)value);
         ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
@@ -686,17 +686,19 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     const size_t qcap = (size_t)std::min<uint64_t>((uint64_t)tiles_per_chunk, tiles.size()) * px_per_tile;
 
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
-    const bool tail = ctx->tune.packets && ctx->tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
-    // Primary packets are split only when the launch is short enough for one long packet to show: fewer than 256 packets
-    // per resident warp (a whole 4K 16-spp frame on one GPU has ~1000 and hides its stragglers; an eighth of it does not).
-    // RT_OPT_PRIMARY_ROUNDS < 0 selects this rule with |value| rounds, > 0 forces splitting, 0 turns it off.
-    bool psplit = ctx->tune.packets && ctx->tune.primary_rounds != 0;
-    if (psplit && ctx->tune.primary_rounds < 0) {
-        const int pw = grid_for(ctx, (const void*)k_primary_packet<false>, kPrimaryThreads) * (kPrimaryThreads / 32);
-        psplit = (uint64_t)tiles.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
-    }
+    // Round budgets.  A launch is SHORT when it has fewer than 256 packets per resident warp: one long packet then shows in
+    // the launch time (a whole 4K 16-spp frame on one GPU has ~1000 and hides its stragglers; one of 8 tile shards does
+    // not).  Positive option values are taken as they are; negative ones (the defaults) mean: |n| rounds for a long launch
+    // and |n| / 2 for a short one -- and for primary packets: no splitting at all in a long launch.
+    const int pw = grid_for(ctx, (const void*)k_primary_packet<false>, kPrimaryThreads) * (kPrimaryThreads / 32);
+    const bool short_launch = (uint64_t)tiles.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
+    auto budget = [&](int32_t v) { return v >= 0 ? v : (short_launch ? std::max(1, -v / 2) : -v); };
     Tuning tune = ctx->tune;
-    tune.primary_rounds = psplit ? std::abs(ctx->tune.primary_rounds) : 0;
+    tune.packet_rounds = budget(ctx->tune.packet_rounds);
+    tune.item_rounds = budget(ctx->tune.item_rounds);
+    tune.primary_rounds = ctx->tune.primary_rounds >= 0 ? ctx->tune.primary_rounds : (short_launch ? std::max(1, -ctx->tune.primary_rounds / 2) : 0);
+    const bool tail = tune.packets && tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
+    const bool psplit = tune.packets && tune.primary_rounds > 0;
     // split records and work items of the packets that run out of rounds; a packet that finds them full is finished in
     // place.  Primary and shadow packets never run at the same time and share the storage.
     const size_t split_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
