@@ -976,6 +976,29 @@ k_shade_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
     shade_epilogue<COUNT>(cnt, tc, fan, 0u);
 }
 
+// The tiles that lie outside the screen-space bound of the scene (WorkView::cull_*): every sample is a miss
+// (renderer.cpp:1052-1065).  One thread per supersampled pixel, rows of a tile are contiguous in the sample buffer.
+__global__ void k_fill_miss(SceneView sc, FrameView fr, WorkView wk, uint32_t* super)
+{
+    const uint32_t per_tile = (uint32_t)wk.tile_px * (uint32_t)wk.tile_px;
+    const uint64_t total = (uint64_t)(wk.tile_end - wk.tile_begin) * per_tile;
+    const uint32_t background = quantise_argb(shade_miss(sc, fr, v3(0, 0, 1)));
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t tile = wk.tiles[wk.tile_begin + (uint32_t)(g / per_tile)];
+        const uint32_t in = (uint32_t)(g % per_tile);
+        const int px = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px + (int)(in % (uint32_t)wk.tile_px);
+        const int py = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px + (int)(in / (uint32_t)wk.tile_px);
+        if (px >= fr.rw || py >= fr.rh) continue;
+        uint32_t c = background;
+        if (fr.s.enable_skysphere) {
+            V3 o, d;
+            primary_ray(fr, px, py, o, d);
+            c = quantise_argb(shade_miss(sc, fr, d));
+        }
+        super[(size_t)py * fr.rw + px] = c;
+    }
+}
+
 // ImageUtils::downscale_image_qt_ARGB32 -- imageUtils.h:98-147: per channel, sum of the factor^2 quantised samples
 // divided (integer, truncating) by factor^2.  One thread per final pixel of the owned tiles.
 __global__ void k_resolve(const uint32_t* super, uint32_t* out, WorkView wk, int tile_size, int factor, int width, int height)

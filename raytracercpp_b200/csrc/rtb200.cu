@@ -74,6 +74,14 @@ struct TileList {
     uint32_t count = 0;
     int tiles_x = 0;
     std::vector<uint32_t> host;
+    // the list split by the screen-space bound of the scene (rt_render_device): tiles that can contain a hit are traced,
+    // the others only get the miss colour.  Re-uploaded when the bound changes.
+    uint32_t* d_split = nullptr;         // traced tiles first, then the others; `count` entries
+    std::vector<uint32_t> split_host;
+    uint32_t n_traced = 0;
+    int32_t split_rect[4] = {0, 0, -1, -1};
+    int32_t split_tile_px = 0;
+    bool split_valid = false;
 };
 typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile_size, tile_mod, tile_rem (-1: all shards, padded)
 
@@ -332,7 +340,7 @@ int get_tile_list(RtContext* ctx, const RtSettings* s, int tile_size, int tile_m
     if (it == ctx->tile_lists.end()) {
         if (ctx->tile_lists.size() > 64) {                         // a caller cycling through frame sizes: start over
             RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            for (auto& kv : ctx->tile_lists) cudaFree(kv.second.d);
+            for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
             ctx->tile_lists.clear();
         }
         TileList tl;
@@ -433,7 +441,7 @@ void rt_destroy(RtContext* ctx)
     ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release();
-    for (auto& kv : ctx->tile_lists) cudaFree(kv.second.d);
+    for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
     ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_split_base.release(); ctx->q_split_active.release(); ctx->q_split_occ.release(); ctx->q_items.release(); ctx->q_split_best.release();
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
@@ -671,13 +679,38 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
 
     TileList* tl = nullptr;
     if (int r = get_tile_list(ctx, s, tile_size, tile_mod, tile_rem, &tl)) return r;
-    const std::vector<uint32_t>& tiles = tl->host;
+    const std::vector<uint32_t>& owned = tl->host;
     const int tiles_x = tl->tiles_x;
     WorkView wk = {};
     wk.tiles_x = tiles_x;
     wk.tile_px = tile_size * fr.factor;
     wk.patches_per_side = (wk.tile_px + kPatch - 1) / kPatch;
     screen_cull_rect(ctx, fr, wk);
+    // Tiles outside the screen-space bound of the scene cannot contain a hit: they get no ray slots, no queue entries and
+    // no traversal, only the miss colour (k_fill_miss).  The wavefront below runs over the other tiles.
+    const bool classify = ctx->opt_screen_cull && ctx->tune.packets && tl->count > 0;
+    if (classify) {
+        const int32_t rect[4] = {wk.cull_x0, wk.cull_y0, wk.cull_x1, wk.cull_y1};
+        if (!tl->split_valid || memcmp(rect, tl->split_rect, sizeof(rect)) != 0 || tl->split_tile_px != wk.tile_px) {
+            std::vector<uint32_t> in, out;
+            for (uint32_t tile : owned) {
+                const int x0 = (int)(tile % (uint32_t)tiles_x) * wk.tile_px, y0 = (int)(tile / (uint32_t)tiles_x) * wk.tile_px;
+                const bool hit = !(x0 + wk.tile_px - 1 < rect[0] || x0 > rect[2] || y0 + wk.tile_px - 1 < rect[1] || y0 > rect[3]);
+                (hit ? in : out).push_back(tile);
+            }
+            tl->n_traced = (uint32_t)in.size();
+            tl->split_host = in;
+            tl->split_host.insert(tl->split_host.end(), out.begin(), out.end());
+            if (!tl->d_split) RT_CUDA(ctx, cudaMalloc((void**)&tl->d_split, tl->count * sizeof(uint32_t)));
+            RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                  // the previous frame may still read the old split
+            RT_CUDA(ctx, cudaMemcpy(tl->d_split, tl->split_host.data(), tl->count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            memcpy(tl->split_rect, rect, sizeof(rect));
+            tl->split_tile_px = wk.tile_px;
+            tl->split_valid = true;
+        }
+    }
+    const uint32_t n_traced = classify ? tl->n_traced : tl->count;
+    const std::vector<uint32_t> tiles(classify ? tl->split_host.begin() : owned.begin(), (classify ? tl->split_host.begin() : owned.begin()) + n_traced);
     const uint64_t px_per_tile = (uint64_t)wk.patches_per_side * wk.patches_per_side * kPatch * kPatch;
     uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, ctx->opt_chunk_pixels / px_per_tile);
     if ((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk > (size_t)kMaxChunks)
@@ -691,7 +724,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     // not).  Positive option values are taken as they are; negative ones (the defaults) mean: |n| rounds for a long launch
     // and |n| / 2 for a short one -- and for primary packets: no splitting at all in a long launch.
     const int pw = grid_for(ctx, (const void*)k_primary_packet<false>, kPrimaryThreads) * (kPrimaryThreads / 32);
-    const bool short_launch = (uint64_t)tiles.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
+    const bool short_launch = (uint64_t)owned.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
     auto budget = [&](int32_t v) { return v >= 0 ? v : (short_launch ? std::max(1, -v / 2) : -v); };
     Tuning tune = ctx->tune;
     tune.packet_rounds = budget(ctx->tune.packet_rounds);
@@ -716,7 +749,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
         super = ctx->d_super.p;
     }
-    wk.tiles = tl->d;
+    wk.tiles = classify ? tl->d_split : tl->d;
     QueueView q;
     q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
     q.split_base = ctx->q_split_base.p; q.split_active = ctx->q_split_active.p; q.split_occ = ctx->q_split_occ.p;
@@ -800,9 +833,17 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
             }
         }
     }
-    if (resolve && !tiles.empty()) {
+    if (classify && n_traced < tl->count) {
+        // the tiles that cannot contain a hit: miss colour only
+        wk.tile_begin = n_traced;
+        wk.tile_end = tl->count;
+        ScopedTimer tm(ctx, ST_PRIMARY);
+        k_fill_miss<<<ctx->sm_count * 8, 256, 0, st>>>(sc, fr, wk, super);
+        launches++;
+    }
+    if (resolve && !owned.empty()) {
         wk.tile_begin = 0;
-        wk.tile_end = (uint32_t)tiles.size();
+        wk.tile_end = tl->count;                                               // all owned tiles, traced or not
         ScopedTimer tm(ctx, ST_RESOLVE);
         k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(super, d_argb_out, wk, tile_size, fr.factor, s->image_width, s->image_height);
         launches++;
@@ -827,7 +868,7 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         overflow |= host_cnt[c].stack_overflow != 0;
     }
     // primary rays = supersampled pixels of the owned tiles that lie inside the frame
-    for (uint32_t tile : tiles) {
+    for (uint32_t tile : owned) {
         int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
         int w = std::min(tile_size, s->image_width - tx * tile_size), h = std::min(tile_size, s->image_height - ty * tile_size);
         rs.primary_rays += (uint64_t)w * h * fr.factor * fr.factor;
