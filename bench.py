@@ -244,8 +244,7 @@ def run_ours(args, scene):
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            frame.render()
-            frame.gather()
+            frame.render_and_gather()
         sync_all()
         sampler = ClockSampler(local)
         sampler.start()
@@ -255,8 +254,7 @@ def run_ours(args, scene):
         rays_rank = 0
         ev0.record(stream)
         for _ in range(args.steps):
-            st = frame.render()
-            frame.gather()
+            st = frame.render_and_gather()
             stage["k_primary"] += st.trace_primary_ms; stage["k_shade"] += st.shade_ms
             stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms; stage["k_compact"] += st.compact_ms
             launches += st.kernel_launches + (2 if world > 1 else 0)           # + the pack and unpack kernels of the gather
@@ -269,7 +267,7 @@ def run_ours(args, scene):
         # --- end to end: host framebuffer, copies inside the timed region
         host = torch.empty((kw["image_height"], kw["image_width"]), dtype=torch.int32).pin_memory()
         for _ in range(min(args.warmup, 2)):
-            frame.render(); frame.gather()
+            frame.render_and_gather()
             if rank == 0:
                 host.copy_(frame.frame, non_blocking=True)
             stream.synchronize()
@@ -277,12 +275,28 @@ def run_ours(args, scene):
         t_e2e = time.perf_counter()
         for _ in range(args.steps):
             ctx.set_camera(proj_inv, cam, (0, 0, 0))                             # the step's inputs: camera + settings (kernel arguments)
-            frame.render()
+            frame.ctx.render_device_begin(s, frame.frame.data_ptr(), frame.tile, world, rank)
             frame.gather()
             if rank == 0:                                                        # the caller's host framebuffer lives with rank 0
                 host.copy_(frame.frame, non_blocking=True)
-            stream.synchronize()
+            frame.ctx.render_device_end()                                        # waits for the stream: frame, gather and copy
         e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+
+    # --- the gathered frame of the sharded run must be the 1-GPU frame (rank 0 renders every tile once more, untimed)
+    frame_check = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            frame.render_and_gather()
+            stream.synchronize()
+            gathered = frame.frame.clone()
+            if rank == 0:
+                whole = ShardedFrame(ctx, s, 0, 1, tile_size=args.tile)
+                whole.render()
+                stream.synchronize()
+                same = bool(torch.equal(whole.frame, gathered))
+                frame_check = "identical to the 1-GPU frame" if same else "DIFFERS from the 1-GPU frame"
+                if not same:
+                    raise SystemExit("bench.py: the gathered frame differs from the 1-GPU frame")
 
     def reduce(x, op):
         if world == 1:
@@ -342,7 +356,7 @@ def run_ours(args, scene):
                                                    "primary_hits")},
             "reference_work": None if ref_work is None else {k: ref_work[k] for k in ("primary_volume_tests", "primary_triangle_tests",
                                                                                       "shadow_volume_tests", "shadow_triangle_tests")},
-            "per_rank_stage_ms": per_rank,
+            "per_rank_stage_ms": per_rank, "frame_check": frame_check,
             "bvh": {k: info[k] for k in ("nodes", "interior", "leaves", "empty_leaves", "max_leaf_size", "child_records", "device_bytes", "build_ms", "upload_ms")},
         }
         if world == 1 and not args.no_cpu_baseline:

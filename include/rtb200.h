@@ -230,6 +230,13 @@ int rt_render(RtContext* ctx, const RtSettings* settings, uint32_t* argb_out, Rt
 int rt_render_device(RtContext* ctx, const RtSettings* settings, uint32_t* d_argb_out,
                      int tile_size, int tile_mod, int tile_rem, RtRenderStats* stats);
 
+/* The same call in two halves, for hosts that put more work (pack, a collective, unpack, a copy) on the context's stream
+ * behind the frame without a host synchronisation in between: _begin enqueues every kernel of the frame and returns;
+ * _end waits for the stream, fills `stats` (may be NULL) and reports device-side errors.  One frame at a time. */
+int rt_render_device_begin(RtContext* ctx, const RtSettings* settings, uint32_t* d_argb_out,
+                           int tile_size, int tile_mod, int tile_rem);
+int rt_render_device_end(RtContext* ctx, RtRenderStats* stats);
+
 /* Pack / unpack the tiles owned by (tile_mod, tile_rem) between the row-major frame and a tile-major
  * staging buffer -- the operand of the framebuffer all-gather.  rt_tile_count gives how many tiles the
  * shard owns; every tile occupies tile_size*tile_size words in the staging buffer (edge tiles padded). */

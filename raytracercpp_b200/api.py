@@ -113,6 +113,8 @@ ABI = {
     "rt_set_light": (C.c_int, [C.c_void_p, FP]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), UP, C.POINTER(RtRenderStats)]),
     "rt_render_device": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(RtRenderStats)]),
+    "rt_render_device_begin": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "rt_render_device_end": (C.c_int, [C.c_void_p, C.POINTER(RtRenderStats)]),
     "rt_tile_count": (C.c_int, [C.POINTER(RtSettings), C.c_int, C.c_int, C.c_int]),
     "rt_pack_tiles": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "rt_unpack_tiles": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -286,6 +288,15 @@ class Context:
     def render_device(self, settings: RtSettings, d_ptr: int, tile_size=64, tile_mod=1, tile_rem=0):
         stats = RtRenderStats()
         self._check(self.lib.rt_render_device(self.h, C.byref(settings), C.c_void_p(d_ptr), tile_size, tile_mod, tile_rem, C.byref(stats)))
+        return stats
+
+    def render_device_begin(self, settings: RtSettings, d_ptr: int, tile_size=64, tile_mod=1, tile_rem=0):
+        """Enqueues the frame and returns; render_device_end() waits for it and returns the stats."""
+        self._check(self.lib.rt_render_device_begin(self.h, C.byref(settings), C.c_void_p(d_ptr), tile_size, tile_mod, tile_rem))
+
+    def render_device_end(self) -> RtRenderStats:
+        stats = RtRenderStats()
+        self._check(self.lib.rt_render_device_end(self.h, C.byref(stats)))
         return stats
 
     def tile_count(self, settings, tile_size, tile_mod, tile_rem) -> int:

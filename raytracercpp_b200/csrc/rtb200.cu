@@ -87,6 +87,16 @@ typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile
 
 } // namespace
 
+struct Pending {                          // a frame that has been enqueued (rt_render_device_begin) and not yet ended
+    bool active = false;
+    ChunkCounters* host_cnt = nullptr;    // pinned, so that the read-back really is asynchronous
+    size_t host_cap = 0;
+    uint32_t n_chunks = 0, launches = 0;
+    bool count = false, shadow = false;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    uint64_t primary_rays = 0;
+};
+
 struct RtContext {
     int device = 0;
     int sm_count = 0;
@@ -132,6 +142,7 @@ struct RtContext {
     int opt_leaf_split = 8;
     Tuning tune{16, 16, 8, 1, -256, -64, -256};
     uint64_t opt_chunk_pixels = kChunkPixels;
+    Pending pending;
     bool opt_screen_cull = true;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
@@ -446,6 +457,7 @@ void rt_destroy(RtContext* ctx)
     ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
+    if (ctx->pending.host_cnt) cudaFreeHost(ctx->pending.host_cnt);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -661,10 +673,10 @@ int rt_tile_count(const RtSettings* s, int tile_size, int tile_mod, int tile_rem
     return (int)owned_tiles(s, tile_size, tile_mod, tile_rem, nullptr).size();
 }
 
-int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, int tile_size, int tile_mod, int tile_rem,
-                     RtRenderStats* stats)
+int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, int tile_size, int tile_mod, int tile_rem)
 {
     if (!ctx) return RT_ERR_INVALID;
+    if (ctx->pending.active) return fail(ctx, RT_ERR_STATE, "rt_render_device_begin: the previous frame has not been ended (rt_render_device_end)");
     if (int r = bind(ctx)) return r;
     if (int r = validate_settings(ctx, s)) return r;
     if (int r = validate_scene_for_render(ctx, s)) return r;
@@ -851,9 +863,43 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     RT_CUDA(ctx, cudaEventRecord(ev_end, st));
     RT_CUDA(ctx, cudaGetLastError());
 
-    std::vector<ChunkCounters> host_cnt(std::max<uint32_t>(n_chunks, 1));
-    RT_CUDA(ctx, cudaMemcpyAsync(host_cnt.data(), ctx->d_counters.p, sizeof(ChunkCounters) * host_cnt.size(), cudaMemcpyDeviceToHost, st));
-    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    // everything is enqueued; the counters come back with the same stream order and are read by rt_render_device_end
+    Pending& pd = ctx->pending;
+    const size_t n_cnt = std::max<uint32_t>(n_chunks, 1);
+    if (n_cnt > pd.host_cap) {
+        if (pd.host_cnt) cudaFreeHost(pd.host_cnt);
+        pd.host_cnt = nullptr; pd.host_cap = 0;
+        RT_CUDA(ctx, cudaHostAlloc((void**)&pd.host_cnt, n_cnt * sizeof(ChunkCounters), cudaHostAllocDefault));
+        pd.host_cap = n_cnt;
+    }
+    RT_CUDA(ctx, cudaMemcpyAsync(pd.host_cnt, ctx->d_counters.p, sizeof(ChunkCounters) * n_cnt, cudaMemcpyDeviceToHost, st));
+    pd.n_chunks = n_chunks;
+    pd.launches = launches;
+    pd.count = count;
+    pd.ev_begin = ev_begin; pd.ev_end = ev_end;
+    pd.shadow = s->shading_method == RT_SHADING && s->compute_shadows;
+    pd.primary_rays = 0;                                  // supersampled pixels of the owned tiles that lie inside the frame
+    for (uint32_t tile : owned) {
+        int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
+        int w = std::min(tile_size, s->image_width - tx * tile_size), h = std::min(tile_size, s->image_height - ty * tile_size);
+        pd.primary_rays += (uint64_t)w * h * fr.factor * fr.factor;
+    }
+    pd.active = true;
+    return RT_OK;
+}
+
+int rt_render_device_end(RtContext* ctx, RtRenderStats* stats)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    Pending& pd = ctx->pending;
+    if (!pd.active) return fail(ctx, RT_ERR_STATE, "rt_render_device_end without rt_render_device_begin");
+    pd.active = false;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const ChunkCounters* host_cnt = pd.host_cnt;
+    const uint32_t n_chunks = pd.n_chunks;
+    const bool count = pd.count;
+    const cudaEvent_t ev_begin = pd.ev_begin, ev_end = pd.ev_end;
 
     RtRenderStats rs;
     memset(&rs, 0, sizeof(rs));
@@ -867,14 +913,9 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
         rs.reflection_volume_tests += host_cnt[c].refl_vol; rs.reflection_triangle_tests += host_cnt[c].refl_tri;
         overflow |= host_cnt[c].stack_overflow != 0;
     }
-    // primary rays = supersampled pixels of the owned tiles that lie inside the frame
-    for (uint32_t tile : owned) {
-        int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
-        int w = std::min(tile_size, s->image_width - tx * tile_size), h = std::min(tile_size, s->image_height - ty * tile_size);
-        rs.primary_rays += (uint64_t)w * h * fr.factor * fr.factor;
-    }
-    rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
-    rs.kernel_launches = launches;
+    rs.primary_rays = pd.primary_rays;
+    rs.shadow_rays = pd.shadow ? rs.primary_hits : 0;
+    rs.kernel_launches = pd.launches;
     cudaEventElapsedTime(&rs.device_ms, ev_begin, ev_end);
     static const bool trace = getenv("RTB200_TRACE") != nullptr;       // per-launch CUDA-event times on stderr
     for (const TimedLaunch& tl : ctx->timed) {
@@ -919,6 +960,13 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     if (stats) *stats = rs;
     if (overflow) return fail(ctx, RT_ERR_STATE, "traversal stack overflow (tree deeper than RT_MAX_TREE_DEPTH)");
     return RT_OK;
+}
+
+int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, int tile_size, int tile_mod, int tile_rem,
+                     RtRenderStats* stats)
+{
+    if (int r = rt_render_device_begin(ctx, s, d_argb_out, tile_size, tile_mod, tile_rem)) return r;
+    return rt_render_device_end(ctx, stats);
 }
 
 int rt_render(RtContext* ctx, const RtSettings* s, uint32_t* argb_out, RtRenderStats* stats)

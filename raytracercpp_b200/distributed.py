@@ -34,6 +34,13 @@ class ShardedFrame:
         """Trace + shade + resolve this rank's tiles into self.frame."""
         return self.ctx.render_device(self.s, self.frame.data_ptr(), self.tile, self.world, self.rank)
 
+    def render_and_gather(self) -> api.RtRenderStats:
+        """One frame, all ranks end up with all of it: the frame's kernels, pack, all-gather and unpack are enqueued back
+        to back on the context's stream; the host waits once, at the end."""
+        self.ctx.render_device_begin(self.s, self.frame.data_ptr(), self.tile, self.world, self.rank)
+        self.gather()
+        return self.ctx.render_device_end()
+
     def gather(self):
         """All ranks end up with the complete frame."""
         if self.world == 1:

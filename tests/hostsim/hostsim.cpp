@@ -348,6 +348,18 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
     return RT_OK;
 }
 
+// the host emulation has no stream: _begin renders, _end hands the stats back
+static thread_local RtRenderStats g_pending_stats;
+int rt_render_device_begin(RtContext* c, const RtSettings* s, uint32_t* out, int tile_size, int tile_mod, int tile_rem)
+{
+    return rt_render_device(c, s, out, tile_size, tile_mod, tile_rem, &g_pending_stats);
+}
+int rt_render_device_end(RtContext*, RtRenderStats* stats)
+{
+    if (stats) *stats = g_pending_stats;
+    return RT_OK;
+}
+
 int rt_render(RtContext* c, const RtSettings* s, uint32_t* argb_out, RtRenderStats* stats)
 {
     return rt_render_device(c, s, argb_out, 64, 1, 0, stats);

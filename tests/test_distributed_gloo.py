@@ -40,6 +40,9 @@ def _worker(rank, world, port, out_dir):
     frame = ShardedFrame(r.ctx, r.render_settings(), rank, world, tile_size=16, device=torch.device("cpu"))
     stats = frame.render()
     full = frame.gather().numpy().view(np.uint32).copy()
+    frame.frame.zero_()
+    stats2 = frame.render_and_gather()                       # the begin / gather / end form used by bench.py
+    assert np.array_equal(frame.frame.numpy().view(np.uint32), full) and stats2.primary_hits == stats.primary_hits
     np.save(Path(out_dir) / f"frame_{rank}.npy", full)
     np.save(Path(out_dir) / f"rays_{rank}.npy", np.array([stats.primary_rays, stats.primary_hits]))
     if rank == 0:
