@@ -344,6 +344,11 @@ def run_ours(args, scene):
                                    "instrumented single-ray kernels (SURVEY.md 8(d))") if ref_work is not None else
                                   "56 B per volume test + 36 B per triangle test performed by the kernel's own traversal (rank 0's tiles)",
                     "kernel_traversal_bytes_per_launch": own_bytes,
+                    "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if (traffic and dom_ms > 0) else None,
+                    "note": ("frac > 1 is real: the device tree refines the reference's leaves (7.7x fewer triangle tests) and 32 rays share each "
+                             "fetch, so the kernel ends sooner than the reference-shaped traversal could stream its bytes from HBM; physical DRAM "
+                             "traffic (`traffic`, ncu) is ~0.2 % of the algorithmic bytes (L2 hit rate 86 %) and the kernel is issue-bound "
+                             "(79 % issue-active, ALU pipe 68 %), see DESIGN.md section 5"),
                     "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
         out = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -379,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4_sphere10M_4k_16spp", choices=list(WORKLOADS))
-    ap.add_argument("--cpu-row-step", type=int, default=48, help="cpu_baseline sample: every n-th supersampled row")
+    ap.add_argument("--cpu-row-step", type=int, default=6, help="cpu_baseline sample: every n-th supersampled row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-work", action="store_true", help="skip the reference-shaped work count (roofline then uses the kernel's own tests)")
     ap.add_argument("--opt", action="append", default=[], help="library option override id=value (experiments), e.g. --opt 3=4")

@@ -980,22 +980,38 @@ k_shade_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
 // (renderer.cpp:1052-1065).  One thread per supersampled pixel, rows of a tile are contiguous in the sample buffer.
 __global__ void k_fill_miss(SceneView sc, FrameView fr, WorkView wk, uint32_t* super)
 {
-    const uint32_t per_tile = (uint32_t)wk.tile_px * (uint32_t)wk.tile_px;
-    const uint64_t total = (uint64_t)(wk.tile_end - wk.tile_begin) * per_tile;
+    const uint32_t n_tiles = wk.tile_end - wk.tile_begin;
     const uint32_t background = quantise_argb(shade_miss(sc, fr, v3(0, 0, 1)));
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t tile = wk.tiles[wk.tile_begin + (uint32_t)(g / per_tile)];
-        const uint32_t in = (uint32_t)(g % per_tile);
-        const int px = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px + (int)(in % (uint32_t)wk.tile_px);
-        const int py = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px + (int)(in / (uint32_t)wk.tile_px);
-        if (px >= fr.rw || py >= fr.rh) continue;
-        uint32_t c = background;
-        if (fr.s.enable_skysphere) {
-            V3 o, d;
-            primary_ray(fr, px, py, o, d);
-            c = quantise_argb(shade_miss(sc, fr, d));
+    if (!fr.s.enable_skysphere && (wk.tile_px & 3) == 0 && (fr.rw & 3) == 0 && (reinterpret_cast<uintptr_t>(super) & 15u) == 0) {
+        // constant colour, rows of a tile are whole 16-byte groups: one 128-bit store per thread and step
+        const uint32_t groups_per_row = (uint32_t)wk.tile_px >> 2;
+        const uint32_t per_tile = groups_per_row * (uint32_t)wk.tile_px;
+        const uint4 c4 = make_uint4(background, background, background, background);
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t tile = wk.tiles[wk.tile_begin + t];
+            const int x0 = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px, y0 = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px;
+            for (uint32_t g = threadIdx.x; g < per_tile; g += blockDim.x) {
+                const int px = x0 + (int)((g % groups_per_row) << 2), py = y0 + (int)(g / groups_per_row);
+                if (px < fr.rw && py < fr.rh) *reinterpret_cast<uint4*>(super + (size_t)py * fr.rw + px) = c4;
+            }
         }
-        super[(size_t)py * fr.rw + px] = c;
+        return;
+    }
+    const uint32_t per_tile = (uint32_t)wk.tile_px * (uint32_t)wk.tile_px;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t tile = wk.tiles[wk.tile_begin + t];
+        const int x0 = (int)(tile % (uint32_t)wk.tiles_x) * wk.tile_px, y0 = (int)(tile / (uint32_t)wk.tiles_x) * wk.tile_px;
+        for (uint32_t g = threadIdx.x; g < per_tile; g += blockDim.x) {
+            const int px = x0 + (int)(g % (uint32_t)wk.tile_px), py = y0 + (int)(g / (uint32_t)wk.tile_px);
+            if (px >= fr.rw || py >= fr.rh) continue;
+            uint32_t c = background;
+            if (fr.s.enable_skysphere) {
+                V3 o, d;
+                primary_ray(fr, px, py, o, d);
+                c = quantise_argb(shade_miss(sc, fr, d));
+            }
+            super[(size_t)py * fr.rw + px] = c;
+        }
     }
 }
 
