@@ -31,6 +31,7 @@ WORKLOADS = {
     # name: (triangles, width, height, ssaa, bvh_max_depth, bvh_leaf_object_count)
     "cfg4_sphere10M_4k_16spp": (10_000_000, 3840, 2160, 4, 12, 40),
     "sphere1M_1080p_4spp": (1_000_000, 1920, 1080, 2, 12, 40),         # for quick local checks only
+    "cfg5_hair1M_4k": (1_000_000, 3840, 2160, 1, 12, 40),              # BASELINE.json configs[4]: ~1 M thin strand triangles, 4K, shadows
 }
 FOV, LIGHT = 80.0, (3.0, 3.0, 2.0)
 
@@ -43,7 +44,10 @@ def make_scene(name):
     from raytracercpp_b200 import scenes
     from raytracercpp_b200.renderer import precompute_materials
     tris, w, h, f, depth, leaf = WORKLOADS[name]
-    xyz9, uv6, mat = scenes.displaced_sphere(*scenes.sphere_grid_for(tris))
+    if "hair" in name:
+        xyz9, uv6, mat = scenes.hair_ball(n_strands=tris // 64, segments=16)
+    else:
+        xyz9, uv6, mat = scenes.displaced_sphere(*scenes.sphere_grid_for(tris))
     mats = precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
     kw = dict(image_width=w, image_height=h, enable_ssaa=int(f > 1), ssaa_factor=f, compute_shadows=1, bvh_max_depth=depth,
               bvh_leaf_object_count=leaf)

@@ -353,6 +353,37 @@ def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
             common.assert_image_close(frames[0][0], common.oracle_image(oracle, robot, kw, mats, tex, cam=cam), what=f"{name} camera {i}")
 
 
+def test_hair_scene_vs_oracle(cuda_lib, oracle):
+    """BASELINE.json configs[4] at reduced size (the oracle must finish in seconds): 256 000 thin double-sided strand
+    triangles -- a deep tree and incoherent packets, many of them split -- with hard shadows, 4 spp; the frame against the
+    oracle, closest hits of a ray batch bit-exact, and the frame unchanged by the scheduling knobs."""
+    xyz9, uv6, mat = scenes.hair_ball(n_strands=4000, segments=16, width=4.0e-3)
+    scene = dict(xyz9=xyz9, uv6=uv6, mat=mat)
+    mats = rt.precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
+    kw = dict(image_width=320, image_height=180, enable_ssaa=1, ssaa_factor=2, compute_shadows=1)
+    r = common.product_renderer(cuda_lib, scene, kw, mats, {})
+    assert r.bvh_info["triangles"] == 256000
+    r.ray_trace()
+    img, st = r.get_image().copy(), r.last_stats().as_dict()
+    want = common.oracle_image(oracle, scene, kw, mats, {})
+    common.assert_image_close(img, want, what="hair scene")
+    assert (img == want).mean() >= 0.999 and st["primary_hits"] > 20000 and st["shadow_rays"] == st["primary_hits"]
+    o, d = common.random_rays(20000, 23, (-1, -1, -4), (1, 1, -2))
+    got, ref = r.ctx.intersect(o, d), oracle.bvh(xyz9, 12, 40).intersect(o, d)
+    for g, w in zip(got, ref):
+        assert np.array_equal(g, w)
+    for opts in ({api.RT_OPT_PACKETS: 0}, {api.RT_OPT_PACKET_ROUNDS: 8, api.RT_OPT_PRIMARY_ROUNDS: 8, api.RT_OPT_ITEM_ROUNDS: 4},
+                 {api.RT_OPT_SCREEN_CULL: 0}):
+        for k, v in opts.items():
+            r.ctx.set_option(k, v)
+        r.ray_trace()
+        assert np.array_equal(r.get_image(), img), opts
+        r.ctx.set_option(api.RT_OPT_PACKETS, 1)
+        r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -64)
+        r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1)
+    r.close()
+
+
 def test_cpp_adapter_example(cuda_lib, tmp_path):
     """include/rtb200_renderer.hpp (the reference's method names over the C ABI) compiles and renders."""
     exe = tmp_path / "adapter_example"

@@ -240,3 +240,15 @@ def test_leaf_refinement_never_changes_a_result(hostsim_lib, oracle, robot, gold
     r.ray_trace()
     common.assert_image_close(r.get_image(), common.oracle_image(oracle, robot, dict(kw, image_width=96, image_height=54), mats, tex), what="split")
     r.close()
+
+
+def test_hair_scene_frame_bit_exact(hostsim_lib, oracle):
+    """BASELINE.json configs[4] at reduced size: thin double-sided Bezier strands (deep tree, incoherent rays), hard shadows."""
+    from raytracercpp_b200 import scenes
+    xyz9, uv6, mat = scenes.hair_ball(n_strands=600, segments=8, width=0.02)
+    scene = dict(xyz9=xyz9, uv6=uv6, mat=mat)
+    mats = rt.precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
+    kw = dict(image_width=96, image_height=54, compute_shadows=1, bvh_max_depth=12, bvh_leaf_object_count=40)
+    img, stats = common.product_image(hostsim_lib, scene, kw, mats, {})
+    assert np.array_equal(img, common.oracle_image(oracle, scene, kw, mats, {}))
+    assert stats.primary_hits > 300 and stats.shadow_rays == stats.primary_hits
