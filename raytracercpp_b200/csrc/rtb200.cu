@@ -143,6 +143,7 @@ struct RtContext {
     Tuning tune{16, 16, 8, 1, -256, -64, -256};
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
+    int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
     bool opt_screen_cull = true;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
@@ -778,7 +779,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
 
     const bool count = ctx->opt_count_work;
-    static int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    int (&grids)[2][9] = ctx->grids;                                           // per context: its device's occupancy
     if (!grids[count][0]) {
         grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
         grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
