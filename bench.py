@@ -259,14 +259,27 @@ def run_ours(args, scene):
         ev0.record(stream)
         for _ in range(args.steps):
             st = frame.render_and_gather()
-            stage["k_primary"] += st.trace_primary_ms; stage["k_shade"] += st.shade_ms
-            stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms; stage["k_compact"] += st.compact_ms
             launches += st.kernel_launches + (2 if world > 1 else 0)           # + the pack and unpack kernels of the gather
             rays_rank = st.total_rays
         ev1.record(stream)
         sync_all()
-        clocks = sampler.stop()
         dev_ms = ev0.elapsed_time(ev1)
+        # Per-kernel durations for the roofline: the SAME K frames once more, still inside the clock sampling, with the two
+        # chunk lanes turned off (RT_OPT_LANES 0) -- with two lanes the kernels of the two chunks overlap on purpose and a
+        # CUDA-event pair around one of them also measures the time it waits for SMs.
+        ctx.set_option(api.RT_OPT_LANES, 0)
+        serial0, serial1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        frame.render_and_gather()
+        serial0.record(stream)
+        for _ in range(args.steps):
+            st = frame.render_and_gather()
+            stage["k_primary"] += st.trace_primary_ms; stage["k_shade"] += st.shade_ms
+            stage["k_reflect"] += st.reflect_ms; stage["k_resolve"] += st.resolve_ms; stage["k_compact"] += st.compact_ms
+        serial1.record(stream)
+        sync_all()
+        serial_ms = serial0.elapsed_time(serial1) / args.steps
+        ctx.set_option(api.RT_OPT_LANES, 0 if "9=0" in args.opt else 1)
+        clocks = sampler.stop()
 
         # --- end to end: host framebuffer, copies inside the timed region
         host = torch.empty((kw["image_height"], kw["image_width"]), dtype=torch.int32).pin_memory()
@@ -353,7 +366,9 @@ def run_ours(args, scene):
                              "fetch, so the kernel ends sooner than the reference-shaped traversal could stream its bytes from HBM; physical DRAM "
                              "traffic (`traffic`, ncu) is ~0.2 % of the algorithmic bytes (L2 hit rate 86 %) and the kernel is issue-bound "
                              "(79 % issue-active, ALU pipe 68 %), see DESIGN.md section 5"),
-                    "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
+                    "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+                    "stage_timing": "K more frames with RT_OPT_LANES 0 (the chunks' kernels back to back on one stream; with the two lanes of "
+                                    "the timed run they overlap on purpose), %.3f ms per frame that way" % serial_ms}
         out = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -166,6 +166,9 @@ enum {
     RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -64; 0 is invalid)                 */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
+    RT_OPT_LANES = 9,         /* 1 (default): two wavefront chunks are in flight at a time on two streams, so one chunk's
+                                 kernels fill the SMs the other's leave idle while their longest packets finish; the
+                                 per-stage times of RtRenderStats then overlap.  Results do not depend on it           */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.

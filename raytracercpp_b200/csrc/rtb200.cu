@@ -87,6 +87,22 @@ typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile
 
 } // namespace
 
+constexpr int kLanes = 2;
+
+// The per-frame work buffers of ONE wavefront chunk in flight.
+struct QueueSet {
+    DevBuf<uint32_t> hit_slot, refl_idx, split_base, split_active, split_occ;
+    DevBuf<unsigned long long> split_best, refl_cnt;
+    DevBuf<uint4> items;
+    DevBuf<int32_t> tri;
+    DevBuf<float> t, u, v, refl_rgb;
+    void release()
+    {
+        hit_slot.release(); refl_idx.release(); split_base.release(); split_active.release(); split_occ.release(); split_best.release();
+        refl_cnt.release(); items.release(); tri.release(); t.release(); u.release(); v.release(); refl_rgb.release();
+    }
+};
+
 struct Pending {                          // a frame that has been enqueued (rt_render_device_begin) and not yet ended
     bool active = false;
     ChunkCounters* host_cnt = nullptr;    // pinned, so that the read-back really is asynchronous
@@ -125,13 +141,11 @@ struct RtContext {
     bool camera_set = false;
 
     // per-frame work buffers
-    DevBuf<uint32_t> d_super, d_frame, q_hit_slot, q_refl_idx, q_split_base, q_split_active, q_split_occ;
-    DevBuf<unsigned long long> q_split_best;
-    DevBuf<uint4> q_items;
+    DevBuf<uint32_t> d_super, d_frame;
     std::map<TileKey, TileList> tile_lists;
-    DevBuf<int32_t> q_tri;
-    DevBuf<float> q_t, q_u, q_v, q_refl_rgb;
-    DevBuf<unsigned long long> q_refl_cnt;
+    QueueSet qs[kLanes];                 // ray queues of the wavefront chunks in flight (one per lane, see rt_render_device_begin)
+    cudaStream_t lane_stream = nullptr;  // the second lane's stream (created on first use)
+    cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
     DevBuf<ChunkCounters> d_counters;
     DevBuf<unsigned int> d_flag;
     std::vector<cudaEvent_t> event_pool;
@@ -145,6 +159,7 @@ struct RtContext {
     Pending pending;
     int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
     bool opt_screen_cull = true;
+    bool opt_lanes = true;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -192,16 +207,17 @@ cudaEvent_t next_event(RtContext* ctx)
 struct ScopedTimer {
     RtContext* ctx;
     TimedLaunch tl;
-    ScopedTimer(RtContext* c, int stage) : ctx(c)
+    cudaStream_t stream;
+    ScopedTimer(RtContext* c, int stage, cudaStream_t st = nullptr) : ctx(c), stream(st ? st : c->stream)
     {
         tl.stage = stage;
         tl.a = next_event(c);
         tl.b = next_event(c);
-        cudaEventRecord(tl.a, c->stream);
+        cudaEventRecord(tl.a, stream);
     }
     ~ScopedTimer()
     {
-        cudaEventRecord(tl.b, ctx->stream);
+        cudaEventRecord(tl.b, stream);
         ctx->timed.push_back(tl);
     }
 };
@@ -375,6 +391,8 @@ int get_tile_list(RtContext* ctx, const RtSettings* s, int tile_size, int tile_m
     return RT_OK;
 }
 
+bool tune_packets_hint(const RtContext* ctx) { return ctx->tune.packets != 0; }
+
 int ensure_stack(RtContext* ctx, const RtSettings* s)
 {
     // k_reflect recurses (trace_ray_secondary); every level holds two traversal stacks.
@@ -454,8 +472,10 @@ void rt_destroy(RtContext* ctx)
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
-    ctx->q_hit_slot.release(); ctx->q_refl_idx.release(); ctx->q_split_base.release(); ctx->q_split_active.release(); ctx->q_split_occ.release(); ctx->q_items.release(); ctx->q_split_best.release();
-    ctx->q_tri.release(); ctx->q_t.release(); ctx->q_u.release(); ctx->q_v.release(); ctx->q_refl_rgb.release(); ctx->q_refl_cnt.release();
+    for (auto& qs : ctx->qs) qs.release();
+    if (ctx->lane_stream) cudaStreamDestroy(ctx->lane_stream);
+    if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+    if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
     if (ctx->pending.host_cnt) cudaFreeHost(ctx->pending.host_cnt);
@@ -501,6 +521,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
+    case RT_OPT_LANES: ctx->opt_lanes = value != 0; return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
@@ -728,6 +749,12 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, ctx->opt_chunk_pixels / px_per_tile);
     if ((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk > (size_t)kMaxChunks)
         tiles_per_chunk = (uint32_t)((tiles.size() + kMaxChunks - 1) / kMaxChunks);
+    // Two chunks are in flight at a time, each on its own stream ("lane") with its own queues: the persistent kernels of
+    // one chunk fill the SMs that the other chunk's kernels leave idle while their last, longest packets finish (within
+    // one stream a kernel cannot start before the previous one has ended completely).  A frame that fits one chunk is cut
+    // in two for that purpose.
+    const int n_lanes = (ctx->opt_lanes && tune_packets_hint(ctx) && tiles.size() >= 2) ? kLanes : 1;
+    if (n_lanes > 1 && tiles.size() <= tiles_per_chunk) tiles_per_chunk = (uint32_t)((tiles.size() + 1) / 2);
     const uint32_t n_chunks = (uint32_t)((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk);
     const size_t qcap = (size_t)std::min<uint64_t>((uint64_t)tiles_per_chunk, tiles.size()) * px_per_tile;
 
@@ -749,28 +776,41 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     // place.  Primary and shadow packets never run at the same time and share the storage.
     const size_t split_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
     const size_t item_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 4, (size_t)1 << 14), (size_t)1 << 21) : 0;
-    if (tail || psplit) {
-        RT_CUDA(ctx, ctx->q_split_base.ensure(split_cap)); RT_CUDA(ctx, ctx->q_split_active.ensure(split_cap)); RT_CUDA(ctx, ctx->q_split_occ.ensure(split_cap));
-        RT_CUDA(ctx, ctx->q_items.ensure(item_cap * kItemPasses));
+    for (int l = 0; l < n_lanes; l++) {
+        QueueSet& Q = ctx->qs[l];
+        if (tail || psplit) {
+            RT_CUDA(ctx, Q.split_base.ensure(split_cap)); RT_CUDA(ctx, Q.split_active.ensure(split_cap)); RT_CUDA(ctx, Q.split_occ.ensure(split_cap));
+            RT_CUDA(ctx, Q.items.ensure(item_cap * kItemPasses));
+        }
+        if (psplit) RT_CUDA(ctx, Q.split_best.ensure(split_cap * 32));
+        RT_CUDA(ctx, Q.hit_slot.ensure(qcap)); RT_CUDA(ctx, Q.tri.ensure(qcap)); RT_CUDA(ctx, Q.t.ensure(qcap));
+        RT_CUDA(ctx, Q.u.ensure(qcap)); RT_CUDA(ctx, Q.v.ensure(qcap));
+        if (reflect) { RT_CUDA(ctx, Q.refl_idx.ensure(qcap)); RT_CUDA(ctx, Q.refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, Q.refl_cnt.ensure(3 * qcap)); }
     }
-    if (psplit) RT_CUDA(ctx, ctx->q_split_best.ensure(split_cap * 32));
-    RT_CUDA(ctx, ctx->q_hit_slot.ensure(qcap)); RT_CUDA(ctx, ctx->q_tri.ensure(qcap)); RT_CUDA(ctx, ctx->q_t.ensure(qcap));
-    RT_CUDA(ctx, ctx->q_u.ensure(qcap)); RT_CUDA(ctx, ctx->q_v.ensure(qcap));
-    if (reflect) { RT_CUDA(ctx, ctx->q_refl_idx.ensure(qcap)); RT_CUDA(ctx, ctx->q_refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, ctx->q_refl_cnt.ensure(3 * qcap)); }
     uint32_t* super = d_argb_out;
     if (resolve) {
         RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
         super = ctx->d_super.p;
     }
     wk.tiles = classify ? tl->d_split : tl->d;
-    QueueView q;
-    q.hit_slot = ctx->q_hit_slot.p; q.slot_tri = ctx->q_tri.p; q.slot_t = ctx->q_t.p; q.slot_u = ctx->q_u.p; q.slot_v = ctx->q_v.p;
-    q.split_base = ctx->q_split_base.p; q.split_active = ctx->q_split_active.p; q.split_occ = ctx->q_split_occ.p;
-    q.split_best = ctx->q_split_best.p;
-    q.items = ctx->q_items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
-    q.refl_idx = ctx->q_refl_idx.p; q.refl_rgb = ctx->q_refl_rgb.p; q.refl_cnt = ctx->q_refl_cnt.p; q.capacity = (uint32_t)qcap;
+    QueueView qv[kLanes];
+    for (int l = 0; l < n_lanes; l++) {
+        QueueSet& Q = ctx->qs[l];
+        QueueView& q = qv[l];
+        q.hit_slot = Q.hit_slot.p; q.slot_tri = Q.tri.p; q.slot_t = Q.t.p; q.slot_u = Q.u.p; q.slot_v = Q.v.p;
+        q.split_base = Q.split_base.p; q.split_active = Q.split_active.p; q.split_occ = Q.split_occ.p;
+        q.split_best = Q.split_best.p;
+        q.items = Q.items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
+        q.refl_idx = Q.refl_idx.p; q.refl_rgb = Q.refl_rgb.p; q.refl_cnt = Q.refl_cnt.p; q.capacity = (uint32_t)qcap;
+    }
+    if (n_lanes > 1 && !ctx->lane_stream) {
+        RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join, cudaEventDisableTiming));
+    }
 
-    cudaStream_t st = ctx->stream;
+    const cudaStream_t main_stream = ctx->stream;
+    cudaStream_t st = main_stream;
     ctx->events_used = 0;
     ctx->timed.clear();
     uint32_t launches = 0;
@@ -793,12 +833,19 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
     const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_items = grids[count][5], grid_finish = grids[count][6], grid_pitems = grids[count][7], grid_pfinish = grids[count][8];
+    if (n_lanes > 1) {                                                         // the second lane starts after everything enqueued so far
+        RT_CUDA(ctx, cudaEventRecord(ctx->lane_fork, main_stream));
+        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream, ctx->lane_fork, 0));
+    }
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
         ChunkCounters* cnt = ctx->d_counters.p + c;
+        const int lane = (int)(c % (uint32_t)n_lanes);
+        st = lane ? ctx->lane_stream : main_stream;
+        const QueueView& q = qv[lane];
         {
-            ScopedTimer tm(ctx, ST_PRIMARY);
+            ScopedTimer tm(ctx, ST_PRIMARY, st);
             if (tune.packets) {
                 if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
                 else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
@@ -815,20 +862,20 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             }
         }
         {
-            ScopedTimer tm(ctx, ST_COMPACT);
+            ScopedTimer tm(ctx, ST_COMPACT, st);
             const uint32_t slots = (wk.tile_end - wk.tile_begin) * (uint32_t)px_per_tile;
             const uint32_t blocks = std::min<uint32_t>((slots + kCompactSlots - 1) / kCompactSlots, (uint32_t)ctx->sm_count * 8u);
             k_compact<<<blocks, kCompactThreads, 0, st>>>(sc, q, cnt, slots, reflect ? 1 : 0);
             launches++;
         }
         if (reflect) {
-            ScopedTimer tm(ctx, ST_REFLECT);
+            ScopedTimer tm(ctx, ST_REFLECT, st);
             if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
             else k_reflect<false><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
             launches++;
         }
         {
-            ScopedTimer tm(ctx, ST_SHADE);
+            ScopedTimer tm(ctx, ST_SHADE, st);
             if (tune.packets) {
                 if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
                 else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
@@ -845,6 +892,11 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
                 launches += kItemPasses + 1;
             }
         }
+    }
+    st = main_stream;
+    if (n_lanes > 1) {                                                         // the frame continues when both lanes are done
+        RT_CUDA(ctx, cudaEventRecord(ctx->lane_join, ctx->lane_stream));
+        RT_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->lane_join, 0));
     }
     if (classify && n_traced < tl->count) {
         // the tiles that cannot contain a hit: miss colour only
