@@ -57,7 +57,7 @@ enum {
 };
 
 /* POD mirror of `RenderSettings` (tp2/projets/renderer/rendererSettings.h:6-105), same defaults via
- * rt_default_settings().  Switches that leave the path (rasterizer, SSAO, parallax, cube-map skybox)
+ * rt_default_settings().  Switches that leave the path (rasterizer, SSAO, parallax mapping)
  * are carried so a caller can pass its struct through; rt_render() refuses them (RT_ERR_UNSUPPORTED). */
 typedef struct RtSettings {
     int32_t image_width;
@@ -83,21 +83,29 @@ typedef struct RtSettings {
     int32_t enable_displacement_mapping;  /* must be 0 */
     int32_t enable_roughness_mapping;
     int32_t enable_skysphere;
-    int32_t enable_skybox;                /* must be 0 */
+    int32_t enable_skybox;                /* cube-map miss shader (Skybox::sample, skybox.cpp:12-51); the skysphere wins */
     /* Seed of the per-pixel xorshift32 streams used by rough reflections.  The reference owns one
      * generator per OpenMP thread seeded from std::rand() (renderer.cpp:51-61), which is not
      * reproducible; the shared stream is state(px,py) = rt_pixel_seed(py*W'+px, rng_seed). */
     uint32_t rng_seed;
 } RtSettings;
 
-/* Texture slots: Renderer::set_{ao,diffuse,normal,roughness}_map / set_skysphere, renderer.cpp:194-201. */
+/* Texture slots: Renderer::set_{ao,diffuse,normal,roughness}_map / set_skysphere / set_skybox, renderer.cpp:194-201.
+ * The six faces of the cube-map skybox are six slots, in the order of Skybox::Skybox(const Image faces[6])
+ * (renderer/skybox.h:13-17): right, left, top, bottom, back, front. */
 enum {
     RT_TEX_AO = 0,
     RT_TEX_DIFFUSE = 1,
     RT_TEX_NORMAL = 2,
     RT_TEX_ROUGHNESS = 3,
     RT_TEX_SKYSPHERE = 4,
-    RT_TEX_COUNT = 5
+    RT_TEX_SKYBOX_RIGHT = 5,
+    RT_TEX_SKYBOX_LEFT = 6,
+    RT_TEX_SKYBOX_TOP = 7,
+    RT_TEX_SKYBOX_BOTTOM = 8,
+    RT_TEX_SKYBOX_BACK = 9,
+    RT_TEX_SKYBOX_FRONT = 10,
+    RT_TEX_COUNT = 11
 };
 
 /* Per-render counters (rays actually traced + what the pipeline did). */

@@ -9,8 +9,8 @@
 //   ImageT      : .width() .height() .data() -> const float* RGBA                                      (image.h:99-118)
 //   TransformT  : .m[4][4] row-major                                                                   (mat.h)
 //   PointT      : .x .y .z
-// Members of the reference class that belong to the rasterizer, SSAO, analytic shapes, parallax mapping or the
-// cube-map skybox are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
+// Members of the reference class that belong to the rasterizer, SSAO, analytic shapes or parallax mapping
+// are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
 #pragma once
 
 #include <cstdint>
@@ -89,6 +89,12 @@ public:
     template <class ImageT> void set_normal_map(const ImageT& im) { set_map(RT_TEX_NORMAL, im); }
     template <class ImageT> void set_roughness_map(const ImageT& im) { set_map(RT_TEX_ROUGHNESS, im); }
     template <class ImageT> void set_skysphere(const ImageT& im) { set_map(RT_TEX_SKYSPHERE, im); }
+    // Renderer::set_skybox(const Skybox&) -- renderer.cpp:199.  Skybox keeps its faces private (skybox.h:21), so the
+    // adapter takes what Skybox's constructor takes: Image faces[6] = right, left, top, bottom, back, front.
+    template <class ImageT> void set_skybox(const ImageT (&faces)[6])
+    {
+        for (int i = 0; i < 6; i++) set_map(RT_TEX_SKYBOX_RIGHT + i, faces[i]);
+    }
     void clear_ao_map() { check(rt_clear_texture(_ctx, RT_TEX_AO)); }                                     // renderer.cpp:203-207
     void clear_diffuse_map() { check(rt_clear_texture(_ctx, RT_TEX_DIFFUSE)); }
     void clear_normal_map() { check(rt_clear_texture(_ctx, RT_TEX_NORMAL)); }

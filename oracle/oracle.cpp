@@ -503,6 +503,16 @@ struct Tex {
         float v = std::floor(y * h);
         return texel((int)u, (int)v);
     }
+    Col texture_bilinear(float xn, float yn) const                                  // image.h:66-77,89-92
+    {
+        float x = xn * w, y = yn * h;
+        float u = x - std::floor(x);
+        float v = y - std::floor(y);
+        int ix = x;
+        int iy = y;
+        return cadd(cadd(cadd(cscale(texel(ix, iy), (1 - u) * (1 - v)), cscale(texel(ix + 1, iy), u * (1 - v))),
+                         cscale(texel(ix, iy + 1), (1 - u) * v)), cscale(texel(ix + 1, iy + 1), u * v));
+    }
 };
 
 // xorshift.h:37-65
@@ -700,7 +710,36 @@ struct Renderer {
         return c;
     }
 
-    // Renderer::trace_ray -- renderer.cpp:1008-1066 (BVH branch; analytic shapes and cube-map skybox are outside the path)
+    // Skybox::sample -- renderer/skybox.cpp:12-51 (faces: right, left, top, bottom, back, front)
+    Col skybox_sample(V3 direction) const
+    {
+        V3 direction2 = v3(direction.x, direction.y, -direction.z);
+        V3 dir_abs = v3(std::abs(direction2.x), std::abs(direction2.y), std::abs(direction2.z));
+        int face_index;
+        float norm_factor;
+        float u, v;
+        if (dir_abs.z >= dir_abs.x && dir_abs.z >= dir_abs.y) {
+            face_index = direction2.z < 0.0 ? 4.0 : 5.0;
+            norm_factor = 0.5 / dir_abs.z;
+            u = direction2.z < 0.0 ? -direction2.x : direction2.x;
+            v = -direction2.y;
+        } else if (dir_abs.y >= dir_abs.x) {
+            face_index = direction2.y < 0.0 ? 3.0 : 2.0;
+            norm_factor = 0.5 / dir_abs.y;
+            u = direction2.x;
+            v = direction2.y < 0.0 ? -direction2.z : direction2.z;
+        } else {
+            face_index = direction2.x < 0.0 ? 1.0 : 0.0;
+            norm_factor = 0.5 / dir_abs.x;
+            u = direction2.x < 0.0 ? direction2.z : -direction2.z;
+            v = -direction2.y;
+        }
+        u = u * norm_factor + 0.5;
+        v = v * norm_factor + 0.5;
+        return tex[RT_TEX_SKYBOX_RIGHT + face_index].texture_bilinear(u, v);
+    }
+
+    // Renderer::trace_ray -- renderer.cpp:1008-1066 (BVH branch; analytic shapes are outside the path)
     Col trace_ray(const RayT& ray, Hit& final_hit, int depth, bool& found, XorShift& rng, RenderCounters* rc, bool secondary) const
     {
         Hit local;
@@ -727,6 +766,7 @@ struct Renderer {
             float v = 0.5 + std::asin(-ray.d.y) / M_PI;
             return tex[RT_TEX_SKYSPHERE].texture_floor(u, v);
         }
+        if (s.enable_skybox) return skybox_sample(ray.d);                            // :1061-1062
         return Col{135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f};               // BACKGROUND_COLOR :19
     }
 

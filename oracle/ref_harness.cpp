@@ -85,6 +85,7 @@ struct RefRenderer {
     Renderer renderer;
     RtSettings settings;
     float fov = 45.0f;
+    Image skybox_faces[6];      // right, left, top, bottom, back, front (skybox.h:13-17); handed over as one Skybox
 };
 
 long long g_last_hits = 0;
@@ -263,6 +264,12 @@ void ref_renderer_set_texture_f32(void* handle, int slot, const float* rgba, int
     case RT_TEX_NORMAL: h->renderer.set_normal_map(img); break;
     case RT_TEX_ROUGHNESS: h->renderer.set_roughness_map(img); break;
     case RT_TEX_SKYSPHERE: h->renderer.set_skysphere(img); break;
+    default:
+        if (slot >= RT_TEX_SKYBOX_RIGHT && slot <= RT_TEX_SKYBOX_FRONT) {
+            h->skybox_faces[slot - RT_TEX_SKYBOX_RIGHT] = img;
+            h->renderer.set_skybox(Skybox(h->skybox_faces));
+        }
+        break;
     }
 }
 

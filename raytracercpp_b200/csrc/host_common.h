@@ -100,7 +100,6 @@ inline int check_settings(const RtSettings* s, std::string& why)
     if (s->hybrid_rasterization_tracing) return bad(RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing stays on the host (renderer.cpp:869-1006)");
     if (s->enable_ssao) return bad(RT_ERR_UNSUPPORTED, "enable_ssao is a host post-process (renderer.cpp:1229-1434)");
     if (s->enable_displacement_mapping) return bad(RT_ERR_UNSUPPORTED, "parallax mapping is outside the path (renderer.cpp:480-554)");
-    if (s->enable_skybox && !s->enable_skysphere) return bad(RT_ERR_UNSUPPORTED, "cube-map skybox is outside the path (skybox.cpp:12-51)");
     if (!s->enable_bvh) return bad(RT_ERR_UNSUPPORTED, "enable_bvh = false (brute force) is not offered");
     if (s->shading_method < RT_SHADING || s->shading_method > RT_VISUALIZE_AO) return bad(RT_ERR_INVALID, "shading_method out of range");
     if (s->max_recursion_depth > kMaxRecursionDepth) return bad(RT_ERR_INVALID, "max_recursion_depth above the supported maximum (8)");
@@ -132,6 +131,12 @@ inline int check_scene_for_render(const SceneFacts& f, const RtSettings* s, std:
         {rt && s->enable_normal_mapping, RT_TEX_NORMAL, "normal mapping enabled but no normal map set"},
         {rt && s->enable_roughness_mapping, RT_TEX_ROUGHNESS, "roughness mapping enabled but no roughness map set"},
         {s->enable_skysphere, RT_TEX_SKYSPHERE, "skysphere enabled but no skysphere set"},
+        {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_RIGHT, "skybox enabled but its right face is not set"},
+        {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_LEFT, "skybox enabled but its left face is not set"},
+        {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_TOP, "skybox enabled but its top face is not set"},
+        {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_BOTTOM, "skybox enabled but its bottom face is not set"},
+        {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_BACK, "skybox enabled but its back face is not set"},
+        {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_FRONT, "skybox enabled but its front face is not set"},
     };
     for (auto& nd : need)
         if (nd.on && f.tex_format[nd.slot] == 0) return bad(RT_ERR_STATE, nd.msg);

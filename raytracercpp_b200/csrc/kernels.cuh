@@ -463,7 +463,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
                 if (slot < total) {
                     q.slot_tri[slot] = -1;
                     if (active) {
-                        if (fr.s.enable_skysphere) primary_ray(fr, px, py, o, d);
+                        if (miss_needs_ray(fr)) primary_ray(fr, px, py, o, d);
                         super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
                     }
                 }
@@ -982,7 +982,7 @@ __global__ void k_fill_miss(SceneView sc, FrameView fr, WorkView wk, uint32_t* s
 {
     const uint32_t n_tiles = wk.tile_end - wk.tile_begin;
     const uint32_t background = quantise_argb(shade_miss(sc, fr, v3(0, 0, 1)));
-    if (!fr.s.enable_skysphere && (wk.tile_px & 3) == 0 && (fr.rw & 3) == 0 && (reinterpret_cast<uintptr_t>(super) & 15u) == 0) {
+    if (!miss_needs_ray(fr) && (wk.tile_px & 3) == 0 && (fr.rw & 3) == 0 && (reinterpret_cast<uintptr_t>(super) & 15u) == 0) {
         // constant colour, rows of a tile are whole 16-byte groups: one 128-bit store per thread and step
         const uint32_t groups_per_row = (uint32_t)wk.tile_px >> 2;
         const uint32_t per_tile = groups_per_row * (uint32_t)wk.tile_px;
@@ -1005,7 +1005,7 @@ __global__ void k_fill_miss(SceneView sc, FrameView fr, WorkView wk, uint32_t* s
             const int px = x0 + (int)(g % (uint32_t)wk.tile_px), py = y0 + (int)(g / (uint32_t)wk.tile_px);
             if (px >= fr.rw || py >= fr.rh) continue;
             uint32_t c = background;
-            if (fr.s.enable_skysphere) {
+            if (miss_needs_ray(fr)) {
                 V3 o, d;
                 primary_ray(fr, px, py, o, d);
                 c = quantise_argb(shade_miss(sc, fr, d));

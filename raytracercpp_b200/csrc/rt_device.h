@@ -373,11 +373,9 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
 
 // ------------------------------------------------------------------------------------------------------------
 // Textures: Image::texture_floor -> sample_floor -> offset (image.h:79-97,122-134): nearest texel, clamp to edge.
-RT_DEV Col tex_floor(const TexView& tx, float x, float y)
+// Image::operator()(int, int) -> offset (image.h:40-49,122-134): the texel with clamp-to-edge addressing.
+RT_DEV Col tex_texel(const TexView& tx, int px, int py)
 {
-    float fu = floorf(x * (float)tx.w);
-    float fv = floorf(y * (float)tx.h);
-    int px = (int)fu, py = (int)fv;
     if (px < 0) px = 0;
     if (px > tx.w - 1) px = tx.w - 1;
     if (py < 0) py = 0;
@@ -396,6 +394,25 @@ RT_DEV Col tex_floor(const TexView& tx, float x, float y)
     }
     rt_f4 c = RT_LDG4(reinterpret_cast<const rt_f4*>(tx.data) + idx);
     return col(c.x, c.y, c.z);
+}
+
+RT_DEV Col tex_floor(const TexView& tx, float x, float y)
+{
+    float fu = floorf(x * (float)tx.w);
+    float fv = floorf(y * (float)tx.h);
+    return tex_texel(tx, (int)fu, (int)fv);
+}
+
+// Image::texture_bilinear -> sample_bilinear (image.h:66-77,89-92): weights from the fractional part, texel indices by
+// truncation, the four products summed left to right.
+RT_DEV Col tex_bilinear(const TexView& tx, float x, float y)
+{
+    float sx = x * (float)tx.w, sy = y * (float)tx.h;
+    float u = sx - floorf(sx);
+    float v = sy - floorf(sy);
+    int ix = (int)sx, iy = (int)sy;
+    return tex_texel(tx, ix, iy) * ((1 - u) * (1 - v)) + tex_texel(tx, ix + 1, iy) * (u * (1 - v)) + tex_texel(tx, ix, iy + 1) * ((1 - u) * v) +
+           tex_texel(tx, ix + 1, iy + 1) * (u * v);
 }
 
 struct MatView {
@@ -561,8 +578,38 @@ RT_DEV Col shade_debug(const SceneView& sc, const FrameView& fr, const Hit& hit)
     return col(clamp01(c.r), clamp01(c.g), clamp01(c.b));
 }
 
-// Miss shader of trace_ray -- renderer.cpp:1052-1065 (skysphere or BACKGROUND_COLOR; the cube-map skybox is
-// outside the path).  The reference mixes float libm calls with double constants; so does this.
+// Skybox::sample -- renderer/skybox.cpp:12-51: the face the direction (z flipped) points at, the face coordinates, one
+// bilinear tap.  The reference's `0.5` literals are doubles: norm_factor = float(0.5 / double(|axis|)) and
+// u = float(double(u * norm_factor) + 0.5); so here.
+RT_DEV Col skybox_sample(const SceneView& sc, V3 dir)
+{
+    const V3 d2 = v3(dir.x, dir.y, -dir.z);
+    const V3 a = v3(fabsf(d2.x), fabsf(d2.y), fabsf(d2.z));
+    int face;
+    float nf, u, v;
+    if (a.z >= a.x && a.z >= a.y) {
+        face = d2.z < 0.0f ? 4 : 5;
+        nf = (float)(0.5 / (double)a.z);
+        u = d2.z < 0.0f ? -d2.x : d2.x;
+        v = -d2.y;
+    } else if (a.y >= a.x) {
+        face = d2.y < 0.0f ? 3 : 2;
+        nf = (float)(0.5 / (double)a.y);
+        u = d2.x;
+        v = d2.y < 0.0f ? -d2.z : d2.z;
+    } else {
+        face = d2.x < 0.0f ? 1 : 0;
+        nf = (float)(0.5 / (double)a.x);
+        u = d2.x < 0.0f ? d2.z : -d2.z;
+        v = -d2.y;
+    }
+    u = (float)((double)(u * nf) + 0.5);
+    v = (float)((double)(v * nf) + 0.5);
+    return tex_bilinear(sc.tex[RT_TEX_SKYBOX_RIGHT + face], u, v);
+}
+
+// Miss shader of trace_ray -- renderer.cpp:1052-1065: skysphere, else cube-map skybox, else BACKGROUND_COLOR.  The
+// reference mixes float libm calls with double constants; so does this.
 RT_DEV Col shade_miss(const SceneView& sc, const FrameView& fr, V3 rd)
 {
     if (fr.s.enable_skysphere) {
@@ -570,8 +617,12 @@ RT_DEV Col shade_miss(const SceneView& sc, const FrameView& fr, V3 rd)
         float v = (float)(0.5 + (double)asinf(-rd.y) / 3.14159265358979323846);
         return tex_floor(sc.tex[RT_TEX_SKYSPHERE], u, v);
     }
+    if (fr.s.enable_skybox) return skybox_sample(sc, rd);                           // renderer.cpp:1061-1062
     return col(135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f);                  // renderer.cpp:19
 }
+
+// Does the miss colour depend on the ray (else it is the constant background)?
+RT_DEV bool miss_needs_ray(const FrameView& fr) { return fr.s.enable_skysphere || fr.s.enable_skybox; }
 
 template <bool COUNT>
 RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, Hit& final_hit,

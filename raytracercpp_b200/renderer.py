@@ -104,6 +104,13 @@ class Renderer:
     def set_normal_map(self, image): self.ctx.set_texture(api.RT_TEX_NORMAL, image)
     def set_roughness_map(self, image): self.ctx.set_texture(api.RT_TEX_ROUGHNESS, image)
     def set_skysphere(self, image): self.ctx.set_texture(api.RT_TEX_SKYSPHERE, image)
+
+    def set_skybox(self, faces):
+        """Renderer::set_skybox(Skybox(faces)) -- renderer.cpp:199; faces: right, left, top, bottom, back, front (skybox.h:13-17)."""
+        assert len(faces) == 6
+        for i, image in enumerate(faces):
+            self.ctx.set_texture(api.RT_TEX_SKYBOX_RIGHT + i, image)
+
     def clear_ao_map(self): self.ctx.clear_texture(api.RT_TEX_AO)
     def clear_diffuse_map(self): self.ctx.clear_texture(api.RT_TEX_DIFFUSE)
     def clear_normal_map(self): self.ctx.clear_texture(api.RT_TEX_NORMAL)

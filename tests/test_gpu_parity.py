@@ -83,7 +83,7 @@ def test_edge_cases(cuda_lib, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
 def test_frames_vs_oracle_and_reference(cuda_lib, oracle, robot, golden_images, name):
     kw, mats, tex = common.config_table(robot["materials"])[name]
     img, stats = common.product_image(cuda_lib, robot, kw, mats, tex)
@@ -166,7 +166,7 @@ def test_primary_rays_resolve_and_call_order(cuda_lib, golden_images, robot):
         r.ray_trace()                                          # RT_SHADING without materials
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping", "enable_skybox"):
+    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping"):
         setattr(st, field, 1)
         with pytest.raises(api.RtError) as e:
             r.ray_trace()
@@ -336,7 +336,7 @@ def test_screen_cull_never_changes_a_frame(cuda_lib, oracle, robot):
             np.float32([[1, 0, 0, 0.0], [0, 1, 0, -1.5], [0, 0, 1, -3.9], [0, 0, 0, 1]]),        # inside the scene's box
             np.float32([[-1, 0, 0, 0.0], [0, 1, 0, 0.0], [0, 0, -1, 2.0], [0, 0, 0, 1]]),        # looking away: nothing on screen
             np.float32([[1, 0, 0, 3.0], [0, 1, 0, 2.0], [0, 0, 1, 4.0], [0, 0, 0, 1]])]          # far away: a small bound
-    for name in ("cfg1", "cfg3"):
+    for name in ("cfg1", "cfg3", "cfg3_skybox"):
         kw, mats, tex = table[name]
         kw = dict(kw, image_width=160, image_height=90)
         for i, cam in enumerate(cams):

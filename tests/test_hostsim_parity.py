@@ -80,7 +80,7 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
         r.ray_trace()                                     # RT_SHADING without materials (reference: assert, materials.h:117)
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping", "enable_skybox"):
+    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping"):
         setattr(s, field, 1)
         with pytest.raises(api.RtError) as e:
             r.ray_trace()
@@ -90,12 +90,16 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
     with pytest.raises(api.RtError):
         r.ray_trace()                                     # mapping enabled, no map
     s.enable_ao_mapping = 0
+    s.enable_skybox = 1
+    with pytest.raises(api.RtError):
+        r.ray_trace()                                     # skybox enabled, faces missing
+    s.enable_skybox = 0
     s.max_recursion_depth = 99
     with pytest.raises(api.RtError):
         r.ray_trace()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
 def test_frames_bit_exact(hostsim_lib, oracle, robot, golden_images, name):
     kw, mats, tex = common.config_table(robot["materials"])[name]
     img, stats = common.product_image(hostsim_lib, robot, kw, mats, tex)
@@ -252,3 +256,21 @@ def test_hair_scene_frame_bit_exact(hostsim_lib, oracle):
     img, stats = common.product_image(hostsim_lib, scene, kw, mats, {})
     assert np.array_equal(img, common.oracle_image(oracle, scene, kw, mats, {}))
     assert stats.primary_hits > 300 and stats.shadow_rays == stats.primary_hits
+
+
+def test_skybox_faces_from_every_side(hostsim_lib, oracle, robot):
+    """Skybox::sample (skybox.cpp:12-51) through all six faces: cameras turned left, right, up, down and backwards."""
+    kw, mats, tex = common.config_table(robot["materials"])["cfg3_skybox"]
+    kw = dict(kw, image_width=96, image_height=54)
+    def rot(yaw, pitch):
+        cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+        ry = np.float32([[cy, 0, sy, 0], [0, 1, 0, 0], [-sy, 0, cy, 0], [0, 0, 0, 1]])
+        rx = np.float32([[1, 0, 0, 0], [0, cp, -sp, 0], [0, sp, cp, 0], [0, 0, 0, 1]])
+        return (ry @ rx).astype(np.float32)
+    seen = set()
+    for yaw, pitch in ((1.6, 0.0), (-1.6, 0.0), (0.3, 1.3), (0.3, -1.3), (3.1, 0.2)):
+        cam = rot(yaw, pitch)
+        img, _ = common.product_image(hostsim_lib, robot, kw, mats, tex, cam=cam)
+        assert np.array_equal(img, common.oracle_image(oracle, robot, kw, mats, tex, cam=cam)), (yaw, pitch)
+        seen.add(int(img[27, 48]))
+    assert len(seen) >= 4                                  # the views really differ
