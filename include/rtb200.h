@@ -57,7 +57,7 @@ enum {
 };
 
 /* POD mirror of `RenderSettings` (tp2/projets/renderer/rendererSettings.h:6-105), same defaults via
- * rt_default_settings().  Switches that leave the path (rasterizer, SSAO, parallax mapping)
+ * rt_default_settings().  Switches that leave the path (rasterizer, SSAO)
  * are carried so a caller can pass its struct through; rt_render() refuses them (RT_ERR_UNSUPPORTED). */
 typedef struct RtSettings {
     int32_t image_width;
@@ -80,7 +80,7 @@ typedef struct RtSettings {
     int32_t enable_ao_mapping;
     int32_t enable_diffuse_mapping;
     int32_t enable_normal_mapping;
-    int32_t enable_displacement_mapping;  /* must be 0 */
+    int32_t enable_displacement_mapping;  /* parallax occlusion mapping, renderer.cpp:518-554,567-568 */
     int32_t enable_roughness_mapping;
     int32_t enable_skysphere;
     int32_t enable_skybox;                /* cube-map miss shader (Skybox::sample, skybox.cpp:12-51); the skysphere wins */
@@ -88,6 +88,9 @@ typedef struct RtSettings {
      * generator per OpenMP thread seeded from std::rand() (renderer.cpp:51-61), which is not
      * reproducible; the shared stream is state(px,py) = rt_pixel_seed(py*W'+px, rng_seed). */
     uint32_t rng_seed;
+    /* RenderSettings::displacement_mapping_strength / parallax_mapping_steps, rendererSettings.h:94-95 (0.02, 32). */
+    float displacement_mapping_strength;
+    int32_t parallax_mapping_steps;
 } RtSettings;
 
 /* Texture slots: Renderer::set_{ao,diffuse,normal,roughness}_map / set_skysphere / set_skybox, renderer.cpp:194-201.
@@ -105,7 +108,8 @@ enum {
     RT_TEX_SKYBOX_BOTTOM = 8,
     RT_TEX_SKYBOX_BACK = 9,
     RT_TEX_SKYBOX_FRONT = 10,
-    RT_TEX_COUNT = 11
+    RT_TEX_DISPLACEMENT = 11, /* Renderer::set_displacement_map: the depth map of parallax occlusion mapping (.r) */
+    RT_TEX_COUNT = 12
 };
 
 /* Per-render counters (rays actually traced + what the pipeline did). */

@@ -9,8 +9,7 @@
 //   ImageT      : .width() .height() .data() -> const float* RGBA                                      (image.h:99-118)
 //   TransformT  : .m[4][4] row-major                                                                   (mat.h)
 //   PointT      : .x .y .z
-// Members of the reference class that belong to the rasterizer, SSAO, analytic shapes or parallax mapping
-// are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
+// Members of the reference class that belong to the rasterizer, SSAO or analytic shapes are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
 #pragma once
 
 #include <cstdint>
@@ -88,6 +87,7 @@ public:
     template <class ImageT> void set_diffuse_map(const ImageT& im) { set_map(RT_TEX_DIFFUSE, im); }
     template <class ImageT> void set_normal_map(const ImageT& im) { set_map(RT_TEX_NORMAL, im); }
     template <class ImageT> void set_roughness_map(const ImageT& im) { set_map(RT_TEX_ROUGHNESS, im); }
+    template <class ImageT> void set_displacement_map(const ImageT& im) { set_map(RT_TEX_DISPLACEMENT, im); }
     template <class ImageT> void set_skysphere(const ImageT& im) { set_map(RT_TEX_SKYSPHERE, im); }
     // Renderer::set_skybox(const Skybox&) -- renderer.cpp:199.  Skybox keeps its faces private (skybox.h:21), so the
     // adapter takes what Skybox's constructor takes: Image faces[6] = right, left, top, bottom, back, front.
@@ -99,6 +99,7 @@ public:
     void clear_diffuse_map() { check(rt_clear_texture(_ctx, RT_TEX_DIFFUSE)); }
     void clear_normal_map() { check(rt_clear_texture(_ctx, RT_TEX_NORMAL)); }
     void clear_roughness_map() { check(rt_clear_texture(_ctx, RT_TEX_ROUGHNESS)); }
+    void clear_displacement_map() { check(rt_clear_texture(_ctx, RT_TEX_DISPLACEMENT)); }
 
     void change_camera_fov(float fov) { _fov = fov; push_camera(); }                                      // renderer.cpp:189
     void change_camera_aspect_ratio(float aspect) { _aspect = aspect; push_camera(); }                    // renderer.cpp:190

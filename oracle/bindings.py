@@ -44,7 +44,8 @@ SETTINGS_FIELDS = [
 
 
 class RtSettings(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32)]
+    _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32), ("displacement_mapping_strength", C.c_float),
+                                                              ("parallax_mapping_steps", C.c_int32)]
 
 
 def default_settings(**kw) -> RtSettings:
@@ -63,10 +64,12 @@ def default_settings(**kw) -> RtSettings:
     s.enable_ambient = s.enable_diffuse = s.enable_specular = s.enable_emissive = 1
     s.rough_reflections_sample_count = 3
     s.rng_seed = 0
+    s.displacement_mapping_strength = 0.02
+    s.parallax_mapping_steps = 32
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
-        setattr(s, k, int(v))
+        setattr(s, k, float(v) if k == "displacement_mapping_strength" else int(v))
     return s
 
 

@@ -657,6 +657,36 @@ struct Renderer {
         return cmul(cdiv(total, col((float)samples)), col(m.reflection));
     }
 
+    // Renderer::parallax_occlusion_mapping -- renderer.cpp:518-554
+    void parallax_occlusion_mapping(const Hit& hit, float u, float v, V3 view_dir, float& new_u, float& new_v) const
+    {
+        const Tex& dm = tex[RT_TEX_DISPLACEMENT];
+        float tex_coord_u, tex_coord_v;
+        tex_coords(hit, u, v, tex_coord_u, tex_coord_v);
+        float current_depth;
+        float depth_step = 1.0f / s.parallax_mapping_steps;
+        float sampled_depth = dm.texture_floor(tex_coord_u, tex_coord_v).r;
+        V3 search_direction = scale(s.displacement_mapping_strength, neg(view_dir));
+        float delta_u = search_direction.x / s.parallax_mapping_steps;
+        float delta_v = search_direction.y / s.parallax_mapping_steps;
+        current_depth = 0.0f;
+        new_u = tex_coord_u;
+        new_v = tex_coord_v;
+        while (current_depth < sampled_depth) {
+            new_u += delta_u;
+            new_v += delta_v;
+            sampled_depth = dm.texture_floor(new_u, new_v).r;
+            current_depth += depth_step;
+        }
+        float previous_u_coord = new_u - delta_u;
+        float previous_v_coord = new_v - delta_v;
+        float after_depth = sampled_depth - current_depth;
+        float before_depth = dm.texture_floor(previous_u_coord, previous_v_coord).r - (current_depth - depth_step);
+        float interpolation_weight = after_depth / (after_depth - before_depth);
+        new_u = (1 - interpolation_weight) * new_u + interpolation_weight * previous_u_coord;
+        new_v = (1 - interpolation_weight) * new_v + interpolation_weight * previous_v_coord;
+    }
+
     // Renderer::shade_ray_inter_point -- renderer.cpp:556-617
     Col shade(const RayT& ray, Hit& hit, int depth, XorShift& rng, RenderCounters* rc, bool secondary) const
     {
@@ -664,6 +694,7 @@ struct Renderer {
         if (s.shading_method == RT_SHADING) {
             float u = hit.u, v = hit.v;
             V3 p = add(ray.o, scale(hit.t, ray.d));
+            if (s.enable_displacement_mapping) parallax_occlusion_mapping(hit, hit.u, hit.v, normalize(sub(cam_pos, p)), u, v);   // :567-568
             V3 to_light = normalize(sub(light, p));
             if (s.enable_normal_mapping) hit.normal = normal_mapping(hit, u, v);
             RtMaterial m = mats[hit.mat];

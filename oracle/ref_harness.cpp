@@ -73,6 +73,8 @@ void apply_settings(RenderSettings& rs, const RtSettings& s)
     rs.enable_roughness_mapping = s.enable_roughness_mapping != 0;
     rs.enable_skysphere = s.enable_skysphere != 0;
     rs.enable_skybox = s.enable_skybox != 0;
+    rs.displacement_mapping_strength = s.displacement_mapping_strength;
+    rs.parallax_mapping_steps = s.parallax_mapping_steps;
 }
 
 struct RefBvh {
@@ -264,6 +266,7 @@ void ref_renderer_set_texture_f32(void* handle, int slot, const float* rgba, int
     case RT_TEX_NORMAL: h->renderer.set_normal_map(img); break;
     case RT_TEX_ROUGHNESS: h->renderer.set_roughness_map(img); break;
     case RT_TEX_SKYSPHERE: h->renderer.set_skysphere(img); break;
+    case RT_TEX_DISPLACEMENT: h->renderer.set_displacement_map(img); break;
     default:
         if (slot >= RT_TEX_SKYBOX_RIGHT && slot <= RT_TEX_SKYBOX_FRONT) {
             h->skybox_faces[slot - RT_TEX_SKYBOX_RIGHT] = img;

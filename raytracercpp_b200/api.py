@@ -19,6 +19,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_UNSUPPORTED = 0, -1, -2
 RT_SHADING, RT_ABS_NORMALS_SHADING, RT_PASTEL_NORMALS_SHADING, RT_BARYCENTRIC_COORDINATES_SHADING, RT_VISUALIZE_AO = range(5)
 RT_TEX_AO, RT_TEX_DIFFUSE, RT_TEX_NORMAL, RT_TEX_ROUGHNESS, RT_TEX_SKYSPHERE = range(5)
 RT_TEX_SKYBOX_RIGHT, RT_TEX_SKYBOX_LEFT, RT_TEX_SKYBOX_TOP, RT_TEX_SKYBOX_BOTTOM, RT_TEX_SKYBOX_BACK, RT_TEX_SKYBOX_FRONT = range(5, 11)
+RT_TEX_DISPLACEMENT = 11
 RT_OPT_COUNT_WORK, RT_OPT_CHUNK_PIXELS, RT_OPT_LEAF_SPLIT, RT_OPT_REFILL_PRIMARY, RT_OPT_REFILL_SHADE, RT_OPT_TRI_BATCH, RT_OPT_PACKETS = 0, 1, 2, 3, 4, 5, 6
 RT_OPT_PACKET_ROUNDS, RT_OPT_SCREEN_CULL, RT_OPT_LANES, RT_OPT_ITEM_ROUNDS, RT_OPT_PRIMARY_ROUNDS = 7, 8, 9, 10, 11
 
@@ -46,7 +47,8 @@ SETTINGS_FIELDS = [
 
 
 class RtSettings(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32)]
+    _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32), ("displacement_mapping_strength", C.c_float),
+                                                              ("parallax_mapping_steps", C.c_int32)]
 
     def copy(self) -> "RtSettings":
         out = RtSettings()
@@ -159,7 +161,7 @@ def default_settings(lib=None, **kw) -> RtSettings:
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
-        setattr(s, k, int(v))
+        setattr(s, k, float(v) if k == "displacement_mapping_strength" else int(v))
     return s
 
 

@@ -84,6 +84,8 @@ inline void default_settings(RtSettings* s)
     s->bvh_leaf_object_count = 40;
     s->enable_ambient = s->enable_diffuse = s->enable_specular = s->enable_emissive = 1;
     s->rough_reflections_sample_count = 3;
+    s->displacement_mapping_strength = 0.02f;
+    s->parallax_mapping_steps = 32;
 }
 
 // Returns RT_OK or an error code with a message in `why`.
@@ -99,7 +101,7 @@ inline int check_settings(const RtSettings* s, std::string& why)
     if (s->enable_ssaa && s->ssaa_factor < 1) return bad(RT_ERR_INVALID, "ssaa_factor < 1");
     if (s->hybrid_rasterization_tracing) return bad(RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing stays on the host (renderer.cpp:869-1006)");
     if (s->enable_ssao) return bad(RT_ERR_UNSUPPORTED, "enable_ssao is a host post-process (renderer.cpp:1229-1434)");
-    if (s->enable_displacement_mapping) return bad(RT_ERR_UNSUPPORTED, "parallax mapping is outside the path (renderer.cpp:480-554)");
+    if (s->enable_displacement_mapping && s->parallax_mapping_steps < 1) return bad(RT_ERR_INVALID, "parallax_mapping_steps < 1");
     if (!s->enable_bvh) return bad(RT_ERR_UNSUPPORTED, "enable_bvh = false (brute force) is not offered");
     if (s->shading_method < RT_SHADING || s->shading_method > RT_VISUALIZE_AO) return bad(RT_ERR_INVALID, "shading_method out of range");
     if (s->max_recursion_depth > kMaxRecursionDepth) return bad(RT_ERR_INVALID, "max_recursion_depth above the supported maximum (8)");
@@ -130,6 +132,7 @@ inline int check_scene_for_render(const SceneFacts& f, const RtSettings* s, std:
         {rt && s->enable_diffuse_mapping, RT_TEX_DIFFUSE, "diffuse mapping enabled but no diffuse map set"},
         {rt && s->enable_normal_mapping, RT_TEX_NORMAL, "normal mapping enabled but no normal map set"},
         {rt && s->enable_roughness_mapping, RT_TEX_ROUGHNESS, "roughness mapping enabled but no roughness map set"},
+        {rt && s->enable_displacement_mapping, RT_TEX_DISPLACEMENT, "displacement mapping enabled but no displacement map set"},
         {s->enable_skysphere, RT_TEX_SKYSPHERE, "skysphere enabled but no skysphere set"},
         {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_RIGHT, "skybox enabled but its right face is not set"},
         {s->enable_skybox && !s->enable_skysphere, RT_TEX_SKYBOX_LEFT, "skybox enabled but its left face is not set"},

@@ -373,6 +373,18 @@ RT_DEV bool trace_occluded(const SceneView& sc, V3 p, V3 n, V3 light, TraceCount
 
 // ------------------------------------------------------------------------------------------------------------
 // Textures: Image::texture_floor -> sample_floor -> offset (image.h:79-97,122-134): nearest texel, clamp to edge.
+// float -> int as the reference's host does it (x86 cvttss2si): truncation, and INT_MIN for NaN and for values outside
+// the int range -- where CUDA's conversion would saturate (NaN -> 0, +big -> INT_MAX).  Texture coordinates can get
+// there (parallax interpolation weight with a zero denominator); the clamp that follows then picks the same texel.
+RT_DEV int f2i_x86(float x)
+{
+#if defined(__CUDACC__)
+    return (x >= -2147483648.0f && x < 2147483648.0f) ? (int)x : (int)0x80000000;
+#else
+    return (int)x;
+#endif
+}
+
 // Image::operator()(int, int) -> offset (image.h:40-49,122-134): the texel with clamp-to-edge addressing.
 RT_DEV Col tex_texel(const TexView& tx, int px, int py)
 {
@@ -400,7 +412,7 @@ RT_DEV Col tex_floor(const TexView& tx, float x, float y)
 {
     float fu = floorf(x * (float)tx.w);
     float fv = floorf(y * (float)tx.h);
-    return tex_texel(tx, (int)fu, (int)fv);
+    return tex_texel(tx, f2i_x86(fu), f2i_x86(fv));
 }
 
 // Image::texture_bilinear -> sample_bilinear (image.h:66-77,89-92): weights from the fractional part, texel indices by
@@ -410,7 +422,7 @@ RT_DEV Col tex_bilinear(const TexView& tx, float x, float y)
     float sx = x * (float)tx.w, sy = y * (float)tx.h;
     float u = sx - floorf(sx);
     float v = sy - floorf(sy);
-    int ix = (int)sx, iy = (int)sy;
+    int ix = f2i_x86(sx), iy = f2i_x86(sy);
     return tex_texel(tx, ix, iy) * ((1 - u) * (1 - v)) + tex_texel(tx, ix + 1, iy) * (u * (1 - v)) + tex_texel(tx, ix, iy + 1) * ((1 - u) * v) +
            tex_texel(tx, ix + 1, iy + 1) * (u * v);
 }
@@ -501,6 +513,40 @@ RT_DEV V3 normal_mapping(const SceneView& sc, const Hit& h, float u, float v)
     return normalize(pn);
 }
 
+// Renderer::parallax_occlusion_mapping -- renderer.cpp:518-554.  Marches the displacement map along the view
+// direction's (x, y) in `parallax_mapping_steps` layers, then interpolates between the last two layers.  As in the
+// reference, (new_u, new_v) are TEXTURE coordinates that the caller nevertheless hands to the mapping functions as if
+// they were barycentrics (renderer.cpp:567-585); parity keeps that.
+RT_DEV void parallax_occlusion_mapping(const SceneView& sc, const FrameView& fr, const Hit& h, float u, float v, V3 view_dir, float& new_u,
+                                       float& new_v)
+{
+    const TexView& dm = sc.tex[RT_TEX_DISPLACEMENT];
+    float tu, tv;
+    hit_texcoords(sc, h, u, v, tu, tv);
+    float current_depth;
+    float depth_step = 1.0f / fr.s.parallax_mapping_steps;
+    float sampled_depth = tex_floor(dm, tu, tv).r;
+    V3 search_direction = fr.s.displacement_mapping_strength * (-view_dir);       // -view_dir * strength (Vector * float, vec.cpp:98-101)
+    float delta_u = search_direction.x / fr.s.parallax_mapping_steps;
+    float delta_v = search_direction.y / fr.s.parallax_mapping_steps;
+    current_depth = 0.0f;
+    new_u = tu;
+    new_v = tv;
+    while (current_depth < sampled_depth) {
+        new_u += delta_u;
+        new_v += delta_v;
+        sampled_depth = tex_floor(dm, new_u, new_v).r;
+        current_depth += depth_step;
+    }
+    float previous_u = new_u - delta_u;
+    float previous_v = new_v - delta_v;
+    float after_depth = sampled_depth - current_depth;
+    float before_depth = tex_floor(dm, previous_u, previous_v).r - (current_depth - depth_step);
+    float w = after_depth / (after_depth - before_depth);
+    new_u = (1 - w) * new_u + w * previous_u;
+    new_v = (1 - w) * new_v + w * previous_v;
+}
+
 // Renderer::compute_specular -- renderer.cpp:270-280
 RT_DEV Col compute_specular(const MatView& m, V3 ray_dir, V3 n, V3 to_light)
 {
@@ -518,6 +564,7 @@ RT_DEV Col shade_direct(const SceneView& sc, const FrameView& fr, V3 ro, V3 rd, 
     const RtSettings& s = fr.s;
     float u = hit.u, v = hit.v;
     V3 p = ro + hit.t * rd;
+    if (s.enable_displacement_mapping) parallax_occlusion_mapping(sc, fr, hit, hit.u, hit.v, normalize(fr.cam_pos - p), u, v);
     V3 to_light = normalize(fr.light - p);
     if (s.enable_normal_mapping) hit.normal = normal_mapping(sc, hit, u, v);
     MatView m = load_material(sc, hit.mat);

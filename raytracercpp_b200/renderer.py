@@ -103,6 +103,7 @@ class Renderer:
     def set_diffuse_map(self, image): self.ctx.set_texture(api.RT_TEX_DIFFUSE, image)
     def set_normal_map(self, image): self.ctx.set_texture(api.RT_TEX_NORMAL, image)
     def set_roughness_map(self, image): self.ctx.set_texture(api.RT_TEX_ROUGHNESS, image)
+    def set_displacement_map(self, image): self.ctx.set_texture(api.RT_TEX_DISPLACEMENT, image)
     def set_skysphere(self, image): self.ctx.set_texture(api.RT_TEX_SKYSPHERE, image)
 
     def set_skybox(self, faces):
@@ -115,6 +116,7 @@ class Renderer:
     def clear_diffuse_map(self): self.ctx.clear_texture(api.RT_TEX_DIFFUSE)
     def clear_normal_map(self): self.ctx.clear_texture(api.RT_TEX_NORMAL)
     def clear_roughness_map(self): self.ctx.clear_texture(api.RT_TEX_ROUGHNESS)
+    def clear_displacement_map(self): self.ctx.clear_texture(api.RT_TEX_DISPLACEMENT)
 
     # -- camera / light -------------------------------------------------------------------------------------------
     def change_camera_fov(self, fov: float):

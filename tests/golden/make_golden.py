@@ -66,6 +66,10 @@ def configs(mats):
         "cfg3": (dict(image_width=240, image_height=135, compute_shadows=1, rough_reflections_sample_count=16, max_recursion_depth=1,
                       enable_roughness_mapping=1, enable_skysphere=1, rng_seed=7), mats3, tex3),
         "cfg3_mirror5": (dict(image_width=160, image_height=90, compute_shadows=1, max_recursion_depth=5, enable_skysphere=1), mats3, tex3),
+        # parallax occlusion mapping on top of cfg2's maps (renderer.cpp:518-554)
+        "cfg2_pom": (dict(image_width=160, image_height=90, compute_shadows=1, enable_ao_mapping=1, enable_diffuse_mapping=1, enable_normal_mapping=1,
+                          enable_displacement_mapping=1, displacement_mapping_strength=0.05, parallax_mapping_steps=16), mats,
+                     {**tex2, 11: scenes.noise_texture((96, 96), 9)}),
         # the GUI's default miss shader (QT/mainwindow.cpp:45-46): cube-map skybox, seen directly and in mirror reflections
         "cfg3_skybox": (dict(image_width=200, image_height=112, compute_shadows=1, max_recursion_depth=2, enable_skybox=1), mats3,
                        {5 + i: scenes.noise_texture((48 + 8 * i, 40 + 4 * i), 20 + i, "rgb") for i in range(6)}),

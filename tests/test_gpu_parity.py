@@ -83,7 +83,7 @@ def test_edge_cases(cuda_lib, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_pom", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
 def test_frames_vs_oracle_and_reference(cuda_lib, oracle, robot, golden_images, name):
     kw, mats, tex = common.config_table(robot["materials"])[name]
     img, stats = common.product_image(cuda_lib, robot, kw, mats, tex)
@@ -166,7 +166,7 @@ def test_primary_rays_resolve_and_call_order(cuda_lib, golden_images, robot):
         r.ray_trace()                                          # RT_SHADING without materials
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping"):
+    for field in ("enable_ssao", "hybrid_rasterization_tracing"):
         setattr(st, field, 1)
         with pytest.raises(api.RtError) as e:
             r.ray_trace()

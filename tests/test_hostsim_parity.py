@@ -80,7 +80,7 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
         r.ray_trace()                                     # RT_SHADING without materials (reference: assert, materials.h:117)
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao", "hybrid_rasterization_tracing", "enable_displacement_mapping"):
+    for field in ("enable_ssao", "hybrid_rasterization_tracing"):
         setattr(s, field, 1)
         with pytest.raises(api.RtError) as e:
             r.ray_trace()
@@ -99,7 +99,7 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
         r.ray_trace()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_pom", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
 def test_frames_bit_exact(hostsim_lib, oracle, robot, golden_images, name):
     kw, mats, tex = common.config_table(robot["materials"])[name]
     img, stats = common.product_image(hostsim_lib, robot, kw, mats, tex)
