@@ -40,6 +40,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Exactly ONE line may reach stdout: the JSON.  Libraries write there too (NCCL prints its version banner on stdout), so
+# file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a private copy of the real stdout.
+_JSON_OUT = None
+
+
+def claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def make_scene(name):
     from raytracercpp_b200 import scenes
     from raytracercpp_b200.renderer import precompute_materials
@@ -128,7 +147,7 @@ def run_reference(args, scene):
         return
     from oracle import bindings
     if not (bindings.available("ref") or bindings.available("oracle")):
-        print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref/libref.so nor oracle/liboracle.so is built"}))
+        emit({"impl": "reference", "unavailable": "neither oracle/_ref/libref.so nor oracle/liboracle.so is built"})
         return
     kw = scene["kw"]
     rh = kw["image_height"] * kw["ssaa_factor"]
@@ -156,7 +175,7 @@ def run_reference(args, scene):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(scene, n_gpus, tile=64):
@@ -390,7 +409,7 @@ def run_ours(args, scene):
                                        "sample": f"every {args.cpu_row_step}th row of the supersampled frame, {rays} rays in {ms / 1e3:.1f} s"}
             except Exception as e:  # the checker is optional for the GPU number, never the other way round
                 out["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -412,6 +431,7 @@ def main():
     ap.add_argument("--lib", default=None, help="another build of librtb200 (kernel A/B experiments)")
     ap.add_argument("--leaf-split", type=int, default=None, help="RT_OPT_LEAF_SPLIT override (experiments); default = library default")
     args = ap.parse_args()
+    claim_stdout()
     if args.tile is None:
         args.tile = 64 if int(os.environ.get("WORLD_SIZE", 1)) == 1 else 32
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -22,18 +22,13 @@ namespace rtb {
 constexpr int kPatch = 8;            // a warp's work item is a kPatch x kPatch block of supersampled pixels (2 passes of 8x4)
 constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
-#ifndef RTB_FETCH
-#define RTB_FETCH 1
-#endif
-constexpr int kPrimaryFetch = RTB_FETCH;     // 32-ray packets a warp of k_primary_packet takes per atomic
-constexpr int kStepsPerCheck = 4;
-#ifndef RTB_ITEM_PASSES
-#define RTB_ITEM_PASSES 6
-#endif
-constexpr int kItemPasses = RTB_ITEM_PASSES;      // launches of k_shade_items after k_shade_packet; the last one has no round budget
+constexpr int kPrimaryFetch = 1;     // 32-ray packets a warp of k_primary_packet takes per atomic (4: -4 %, coarser load balance)
+constexpr int kStepsPerCheck = 4;    // single-test steps between two refill / completion checks of a persistent single-ray warp
+constexpr int kItemPasses = 6;       // generations of work items of a split packet = launches of k_*_items; the last has no round
+                                     // budget (3 left a straggler in the unlimited pass: k_shade 8.9 ms against 8.0 with 6; 10: same)
 #ifndef RTB_SHADE_MINB
-#define RTB_SHADE_MINB 7   /* measured on cfg4: 7 CTAs/SM 8.9 ms, 6: 9.4, 8: 9.6 */
-#endif    // single-test steps between two refill / completion checks of a persistent warp
+#define RTB_SHADE_MINB 7   /* resident CTAs per SM the compiler must allow for k_shade_packet; measured on cfg4: 7 -> 8.9 ms, 6: 9.4, 8: 9.6 */
+#endif
 
 struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int next_patch;         // next ray slot of k_primary
@@ -251,11 +246,6 @@ struct PacketStack {
 // replaces five dependent shuffle + min steps.
 RT_DEV float warp_min(float x)
 {
-#ifdef RTB_OLD_WARPMIN
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
-#endif
     const uint32_t b = __float_as_uint(x);
     const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
     const uint32_t m = __reduce_min_sync(0xffffffffu, key);
@@ -338,11 +328,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
             for (uint32_t k = 0; k < meta; k++) {
                 const float4 c0 = K.stage[4 * k], c1 = K.stage[4 * k + 1], c2 = K.stage[4 * k + 2], c3 = K.stage[4 * k + 3];
                 if (COUNT && active) tc.vol_tests++;
-#ifdef RTB_OLD_SLAB
-                const float tn = active ? slab_entry(c0, c1, c2, c3, sr, t_max) : INFINITY;
-#else
                 const float tn = slab_entry_packet(c0, c1, c2, c3, sr, t_max, active);
-#endif
                 if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
                 const float tmin = warp_min(tn);
                 if (sp >= RT_STACK_SIZE) { overflow = 1u; return true; }
