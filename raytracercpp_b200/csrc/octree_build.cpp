@@ -14,7 +14,10 @@
 #include "scene_layout.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <omp.h>
 
@@ -43,7 +46,20 @@ struct Cell {
     int32_t child[8];     // index into cells, -1 = empty cell
     uint32_t begin, count; // leaf: range in the permutation array
     bool leaf;
+    int32_t job;          // >= 0: the subtree below this cell is built and flattened by that job (see build_flat_scene)
     float nr[PLANES], fr[PLANES];
+};
+
+// A subtree handed to one thread: it builds the subtree's cells and flattens them into buffers of its own.  Local record
+// 0 is the subtree's root record, 1 is padding (so that local and final record indices have the same parity), the
+// children blocks start at 2.
+struct Job {
+    V3 lo, hi;
+    int depth;
+    uint32_t b, e;
+    FlatScene flat;
+    float nr[PLANES], fr[PLANES];
+    size_t rec_base = 0, tri_base = 0;     // where the job's records [2..) and triangles go in the final arrays
 };
 
 struct Builder {
@@ -51,11 +67,18 @@ struct Builder {
     size_t n;
     int max_depth, leaf_max;
     int leaf_split = 0;          // > 0: reference leaves with more triangles than this are refined (emit_group)
-    std::vector<V3> centroid;
-    std::vector<uint32_t> perm, scratch;
-    std::vector<uint8_t> oct;
+    // shared by the top-level builder and the jobs; a job only touches its own range [b, e) of perm / scratch / oct
+    const V3* centroid = nullptr;
+    uint32_t* perm = nullptr;
+    uint32_t* scratch = nullptr;
+    uint8_t* oct = nullptr;
     std::vector<Cell> cells;
     FlatScene* out;
+    // top-level builder only: subtrees of at most job_size triangles become jobs; rec slots waiting for a job's root record
+    uint32_t job_size = 0;
+    bool in_parallel = false;    // a job runs inside the parallel loop: its partitions are single-threaded
+    std::vector<Job>* jobs = nullptr;
+    std::vector<std::pair<uint32_t, int32_t>> job_slots;
 
     V3 vert(uint32_t tri, int k) const
     {
@@ -67,7 +90,7 @@ struct Builder {
     void partition(uint32_t b, uint32_t e, V3 mid, uint32_t offs[9])
     {
         const uint32_t len = e - b;
-        const int T = len > (1u << 18) ? omp_get_max_threads() : 1;
+        const int T = (!in_parallel && len > (1u << 16)) ? omp_get_max_threads() : 1;
         std::vector<uint32_t> counts((size_t)T * 8, 0);
         const uint32_t chunk = (len + T - 1) / T;
 #pragma omp parallel num_threads(T) if (T > 1)
@@ -121,6 +144,14 @@ struct Builder {
             c.begin = b;
             c.count = e - b;
             c.leaf = true;
+            c.job = -1;
+        }
+        if (jobs && e - b <= job_size) {                 // small enough: another thread builds and flattens this subtree
+            cells[self].job = (int32_t)jobs->size();
+            jobs->emplace_back();
+            Job& j = jobs->back();
+            j.lo = lo; j.hi = hi; j.depth = depth; j.b = b; j.e = e;
+            return self;
         }
         out->nodes++;
         const bool split = (size_t)(e - b) > (size_t)leaf_max && depth != max_depth; // bvh.h:171-177
@@ -178,16 +209,25 @@ struct Builder {
         return self;
     }
 
-    static float pad_down(float f)
+    // f moved by `ulps` representable floats towards -inf / +inf: nextafterf applied `ulps` times, done on the bits
+    // (floats ordered as sign-magnitude integers); 56 calls per record made the libm loop the slowest part of flattening.
+    static float pad(float f, int ulps)
     {
-        for (int i = 0; i < RT_SLAB_PAD_ULPS; i++) f = nextafterf(f, -INFINITY);
-        return f;
+        if (f != f) return f;
+        int32_t i;
+        memcpy(&i, &f, 4);
+        int64_t ord = i >= 0 ? (int64_t)i : -(int64_t)(i & 0x7fffffff);     // one zero, as nextafterf walks: -min, 0, +min
+        ord += ulps;
+        const int64_t inf = 0x7f800000;
+        if (ord >= inf) return INFINITY;
+        if (ord <= -inf) return -INFINITY;
+        uint32_t o = ord > 0 ? (uint32_t)ord : ord < 0 ? (0x80000000u | (uint32_t)(-ord)) : ((uint32_t)i & 0x80000000u);   // zero keeps the sign it came from
+        float r;
+        memcpy(&r, &o, 4);
+        return r;
     }
-    static float pad_up(float f)
-    {
-        for (int i = 0; i < RT_SLAB_PAD_ULPS; i++) f = nextafterf(f, INFINITY);
-        return f;
-    }
+    static float pad_down(float f) { return pad(f, -RT_SLAB_PAD_ULPS); }
+    static float pad_up(float f) { return pad(f, RT_SLAB_PAD_ULPS); }
 
     uint32_t alloc_block(uint32_t k)
     {
@@ -297,9 +337,13 @@ struct Builder {
     void emit(int32_t cell, uint32_t rec, const float* uv6, const int32_t* mat)
     {
         const Cell c = cells[cell];
+        if (c.job >= 0) {                              // the job's root record goes here once the job's place is known
+            job_slots.emplace_back(rec, c.job);
+            return;
+        }
         if (c.leaf) {
             if (leaf_split > 0 && c.count > (uint32_t)leaf_split) {
-                std::vector<uint32_t> ids(perm.begin() + c.begin, perm.begin() + c.begin + c.count);
+                std::vector<uint32_t> ids(perm + c.begin, perm + c.begin + c.count);
                 emit_group(ids.data(), c.count, rec, c.nr, c.fr, uv6, mat);
             } else
                 write_record(rec, c.nr, c.fr, append_leaf(&perm[c.begin], c.count, uv6, mat), RT_META_LEAF | c.count);
@@ -316,6 +360,25 @@ struct Builder {
         write_record(rec, c.nr, c.fr, first, (uint32_t)k);
         for (int j = 0; j < k; j++) emit(kids[j], first + (uint32_t)j, uv6, mat);
     }
+
+    // Top-level builder, after the jobs have run: the slab extents of the cells above them (bvh.h:147-149).
+    void refit(int32_t cell)
+    {
+        Cell& c = cells[cell];
+        if (c.job >= 0) {
+            const Job& j = (*jobs)[c.job];
+            for (int pl = 0; pl < PLANES; pl++) { c.nr[pl] = j.nr[pl]; c.fr[pl] = j.fr[pl]; }
+            return;
+        }
+        if (c.leaf) return;
+        for (int pl = 0; pl < PLANES; pl++) { c.nr[pl] = INFINITY; c.fr[pl] = -INFINITY; }
+        for (int o = 0; o < 8; o++) {
+            if (c.child[o] < 0) continue;
+            refit(c.child[o]);
+            const Cell& k = cells[c.child[o]];
+            for (int pl = 0; pl < PLANES; pl++) { c.nr[pl] = std::min(c.nr[pl], k.nr[pl]); c.fr[pl] = std::max(c.fr[pl], k.fr[pl]); }
+        }
+    }
 };
 
 } // namespace
@@ -324,6 +387,9 @@ void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, s
                       int leaf_max, int leaf_split, FlatScene& out)
 {
     out = FlatScene();
+    std::vector<V3> centroid(n);
+    std::vector<uint32_t> perm(n), scratch(n);
+    std::vector<uint8_t> oct(n);
     Builder b;
     b.xyz9 = xyz9;
     b.n = n;
@@ -331,10 +397,10 @@ void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, s
     b.leaf_max = leaf_max;
     b.leaf_split = leaf_split;
     b.out = &out;
-    b.centroid.resize(n);
-    b.perm.resize(n);
-    b.scratch.resize(n);
-    b.oct.resize(n);
+    b.centroid = centroid.data();
+    b.perm = perm.data();
+    b.scratch = scratch.data();
+    b.oct = oct.data();
     // root cell = bounds of all vertices (bvh.cpp:25-36); centroids as Triangle::bbox_centroid (triangle.cpp:162-165)
     V3 lo = v3(INFINITY, INFINITY, INFINITY), hi = v3(-INFINITY, -INFINITY, -INFINITY);
 #pragma omp parallel
@@ -346,8 +412,8 @@ void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, s
             V3 mn = v3(std::min(a.x, std::min(bb.x, c.x)), std::min(a.y, std::min(bb.y, c.y)), std::min(a.z, std::min(bb.z, c.z)));
             V3 mx = v3(std::max(a.x, std::max(bb.x, c.x)), std::max(a.y, std::max(bb.y, c.y)), std::max(a.z, std::max(bb.z, c.z)));
             float kk = 1.f / 2;                                                     // Point operator/ (vec.cpp:52-56)
-            b.centroid[i] = kk * (mn + mx);
-            b.perm[i] = (uint32_t)i;
+            centroid[i] = kk * (mn + mx);
+            perm[i] = (uint32_t)i;
             tlo = v3(std::min(tlo.x, mn.x), std::min(tlo.y, mn.y), std::min(tlo.z, mn.z));
             thi = v3(std::max(thi.x, mx.x), std::max(thi.y, mx.y), std::max(thi.z, mx.z));
         }
@@ -357,14 +423,91 @@ void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, s
             hi = v3(std::max(hi.x, thi.x), std::max(hi.y, thi.y), std::max(hi.z, thi.z));
         }
     }
-    b.cells.reserve(n / 2 + 16);
-    out.tris.reserve(n * 3);
-    out.shade.reserve(n * 2);
-    out.orig.reserve(n);
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+
+    // Stage A (this thread; the 8-way partitions of big cells are parallel inside): the top of the tree, down to subtrees
+    // of at most job_size triangles.  Stage B: those subtrees, one thread each, cells AND flattening, into buffers of
+    // their own.  Stage C: the top is flattened, the jobs' buffers are appended behind it and their links relocated.
+    // The tree is the same as a sequential build's; only the order of the record blocks in memory depends on job_size.
+    std::vector<Job> jobs;
+    const int threads = std::max(1, omp_get_max_threads());
+    b.jobs = &jobs;
+    b.job_size = (uint32_t)std::max<size_t>(4096, n / ((size_t)threads * 8));
     int32_t root = b.build(lo, hi, 0, 0, (uint32_t)n);
+    const double t1 = now();
+
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ji = 0; ji < (long long)jobs.size(); ji++) {
+        Job& j = jobs[ji];
+        Builder jb;
+        jb.xyz9 = xyz9; jb.n = n; jb.max_depth = max_depth; jb.leaf_max = leaf_max; jb.leaf_split = leaf_split;
+        jb.centroid = centroid.data(); jb.perm = perm.data(); jb.scratch = scratch.data(); jb.oct = oct.data();
+        jb.out = &j.flat;
+        jb.in_parallel = true;
+        const size_t cnt = j.e - j.b;
+        jb.cells.reserve(cnt / 8 + 16);
+        j.flat.tris.reserve(cnt * 3); j.flat.shade.reserve(cnt * 2); j.flat.orig.reserve(cnt);
+        int32_t jr = jb.build(j.lo, j.hi, j.depth, j.b, j.e);
+        for (int pl = 0; pl < PLANES; pl++) { j.nr[pl] = jb.cells[jr].nr[pl]; j.fr[pl] = jb.cells[jr].fr[pl]; }
+        j.flat.recs.assign(8, F4{0, 0, 0, 0});                                      // record 0 = the subtree's root, record 1 = padding
+        jb.emit(jr, 0, uv6, mat);
+    }
+    const double t2 = now();
+
+    // statistics of the whole (reference-shaped) tree
+    for (const Job& j : jobs) {
+        out.nodes += j.flat.nodes; out.leaves += j.flat.leaves; out.empty_leaves += j.flat.empty_leaves; out.interior += j.flat.interior;
+        out.max_depth_reached = std::max(out.max_depth_reached, j.flat.max_depth_reached);
+        out.max_leaf_size = std::max(out.max_leaf_size, j.flat.max_leaf_size);
+    }
+    b.refit(root);
     out.recs.assign(4, F4{0, 0, 0, 0}); // record 0 = the root cell
     b.emit(root, 0, uv6, mat);
+    // places of the jobs behind the top-level records (block starts stay 128-byte aligned: even record indices)
+    size_t n_recs = out.recs.size() / 4, n_tris = out.tris.size() / 3;
+    for (Job& j : jobs) {
+        if (n_recs & 1) n_recs++;
+        j.rec_base = n_recs;
+        j.tri_base = n_tris;
+        n_recs += j.flat.recs.size() / 4 - 2;
+        n_tris += j.flat.tris.size() / 3;
+    }
+    out.recs.resize(n_recs * 4, F4{0, 0, 0, 0});
+    out.tris.resize(n_tris * 3);
+    out.shade.resize(n_tris * 2);
+    out.orig.resize(n_tris);
+    auto relocate = [](F4 q3, const Job& j) {           // link of a record: first triangle (leaf) or first child record
+        uint32_t link = f2u(q3.z);
+        const uint32_t meta = f2u(q3.w);
+        link = (meta & RT_META_LEAF) ? link + (uint32_t)j.tri_base : (uint32_t)(j.rec_base + (link - 2));
+        q3.z = u2f(link);
+        return q3;
+    };
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ji = 0; ji < (long long)jobs.size(); ji++) {
+        const Job& j = jobs[ji];
+        const size_t nr = j.flat.recs.size() / 4 - 2, nt = j.flat.tris.size() / 3;
+        for (size_t r = 0; r < nr; r++) {
+            const F4* src = &j.flat.recs[(r + 2) * 4];
+            F4* dst = &out.recs[(j.rec_base + r) * 4];
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = relocate(src[3], j);
+        }
+        if (nt) {
+            memcpy(&out.tris[j.tri_base * 3], j.flat.tris.data(), nt * 3 * sizeof(F4));
+            memcpy(&out.shade[j.tri_base * 2], j.flat.shade.data(), nt * 2 * sizeof(F4));
+            memcpy(&out.orig[j.tri_base], j.flat.orig.data(), nt * sizeof(int32_t));
+        }
+    }
+    for (const auto& slot : b.job_slots) {              // the jobs' root records, in the blocks of the cells above them
+        const Job& j = jobs[slot.second];
+        const F4* src = &j.flat.recs[0];
+        F4* dst = &out.recs[(size_t)slot.first * 4];
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = relocate(src[3], j);
+    }
     out.n_records = out.recs.size() / 4;
+    if (getenv("RTB200_TRACE"))
+        fprintf(stderr, "[rtb200] octree: top %.0f ms, %zu jobs %.0f ms, assemble %.0f ms\n", t1 - t0, jobs.size(), t2 - t1, now() - t2);
 }
 
 } // namespace rtb

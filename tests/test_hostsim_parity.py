@@ -274,3 +274,27 @@ def test_skybox_faces_from_every_side(hostsim_lib, oracle, robot):
         assert np.array_equal(img, common.oracle_image(oracle, robot, kw, mats, tex, cam=cam)), (yaw, pitch)
         seen.add(int(img[27, 48]))
     assert len(seen) >= 4                                  # the views really differ
+
+
+@pytest.mark.parametrize("split", [8, 0])
+def test_parallel_build_of_a_large_mesh(hostsim_lib, oracle, split):
+    """octree_build.cpp hands subtrees to threads (jobs) that build and flatten them into buffers of their own; the top
+    of the tree and the relocation of the jobs' links are assembled afterwards.  A 300 000-triangle mesh makes ~100 jobs:
+    the tree statistics and the closest hit of 30 000 rays must equal the oracle's (= the reference's sequential
+    insertion), with and without the device-side leaf refinement."""
+    from raytracercpp_b200 import scenes
+    xyz9, uv6, mat = scenes.displaced_sphere(*scenes.sphere_grid_for(300_000))
+    ctx = api.Context(0, hostsim_lib)
+    ctx.set_option(api.RT_OPT_LEAF_SPLIT, split)
+    ctx.set_triangles(xyz9, uv6, mat)
+    info = ctx.build_bvh(12, 40)
+    ob = oracle.bvh(xyz9, 12, 40)
+    st = ob.stats()
+    for k in ("nodes", "leaves", "empty_leaves", "interior", "max_depth_reached", "max_leaf_size"):
+        assert info[k] == st[k], k
+    o, d = common.random_rays(30000, 9, (-1.2, -1.2, -4.2), (1.2, 1.2, -1.8))
+    got, want = ctx.intersect(o, d), ob.intersect(o, d)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert (want[0] >= 0).sum() > 5000
+    ctx.close()
