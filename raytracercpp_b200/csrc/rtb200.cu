@@ -616,8 +616,9 @@ int rt_transform_triangles(RtContext* ctx, const float m[16], int max_depth, int
     if (!ctx || !m) return RT_ERR_INVALID;
     M4 t;
     memcpy(t.m, m, sizeof(t.m));
-    const size_t n = ctx->xyz9.size() / 3;
-    for (size_t i = 0; i < n; i++) {                                               // Transform::operator()(Triangle), mat.cpp:133-140
+    const long long n = (long long)(ctx->xyz9.size() / 3);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; i++) {                                            // Transform::operator()(Triangle), mat.cpp:133-140
         V3 p = xform_point(t, v3(ctx->xyz9[3 * i], ctx->xyz9[3 * i + 1], ctx->xyz9[3 * i + 2]));
         ctx->xyz9[3 * i] = p.x; ctx->xyz9[3 * i + 1] = p.y; ctx->xyz9[3 * i + 2] = p.z;
     }
