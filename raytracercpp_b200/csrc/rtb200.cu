@@ -573,8 +573,9 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     RT_CUDA(ctx, ctx->d_shade.ensure(flat.shade.size()));
     RT_CUDA(ctx, ctx->d_orig.ensure(flat.orig.size()));
     RT_CUDA(ctx, ctx->d_leaf_of.ensure(flat.orig.size()));
-    std::vector<int32_t> leaf_of(flat.orig.size());
-    for (size_t i = 0; i < flat.orig.size(); i++) leaf_of[(size_t)flat.orig[i]] = (int32_t)i;
+    RawVector<int32_t> leaf_of(flat.orig.size());
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)flat.orig.size(); i++) leaf_of[(size_t)flat.orig[i]] = (int32_t)i;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_recs.p, flat.recs.data(), flat.recs.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
     if (n) {
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris.p, flat.tris.data(), flat.tris.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));

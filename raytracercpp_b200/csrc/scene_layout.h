@@ -21,6 +21,9 @@
 #pragma once
 
 #include <stdint.h>
+#include <memory>
+#include <new>
+#include <utility>
 #include <vector>
 
 #include "rt_math.h"
@@ -35,11 +38,21 @@ struct alignas(16) F4 {
     float x, y, z, w;
 };
 
+// std::allocator whose value-less construct() leaves trivial types uninitialised: resize(n) of a gigabyte array does not
+// write it once on one thread before the parallel copy fills it.
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { typedef DefaultInitAllocator<U> other; };
+    template <class U> void construct(U* p) { ::new ((void*)p) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVector = std::vector<T, DefaultInitAllocator<T>>;
+
 struct FlatScene {
-    std::vector<F4> recs;        // 4 per record
-    std::vector<F4> tris;        // 3 per triangle, leaf order
-    std::vector<F4> shade;       // 2 per triangle, leaf order
-    std::vector<int32_t> orig;   // leaf order -> index in the caller's array
+    RawVector<F4> recs;          // 4 per record
+    RawVector<F4> tris;          // 3 per triangle, leaf order
+    RawVector<F4> shade;         // 2 per triangle, leaf order
+    RawVector<int32_t> orig;     // leaf order -> index in the caller's array
     // statistics of the (reference-shaped) octree
     uint64_t nodes = 0, leaves = 0, empty_leaves = 0, interior = 0;
     uint32_t max_depth_reached = 0, max_leaf_size = 0;
