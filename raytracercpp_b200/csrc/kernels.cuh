@@ -1,17 +1,24 @@
-// kernels.cuh -- the wavefront pipeline's __global__ kernels (sm_100a).  One frame is
+// kernels.cuh -- the wavefront pipeline's __global__ kernels (sm_100a).  One frame (rt_render_device_begin, rtb200.cu):
 //
-//   k_primary   ray generation + closest-hit traversal by persistent warps whose idle lanes are refilled from an
-//               atomic ray counter; misses are shaded and written at once, hits are appended to the hit queue with
-//               one atomic per warp (ballot + popc), reflective hits also to the reflection queue
-//   k_compact   turns the per-ray-slot hit records into the hit queue, block by block in slot order, so that 32
-//               consecutive queue entries are 32 neighbouring pixels (coherent shadow rays); also the reflection queue
-//   k_reflect   (only if a material reflects) one thread per reflective hit walks its rough-reflection fan
-//   k_shade     one thread per queued hit: textures / Blinn-Phong, any-hit shadow ray, compose, quantise, store
-//   k_resolve   integer SSAA box filter of the quantised samples (imageUtils.h:98-147)
+//   host               tiles outside the screen-space bound of the scene's root box are set aside: they get no ray slots
+//   k_fill_miss        ... only the miss colour (background / skysphere / cube-map skybox)
+//   per chunk of the other tiles (two chunks in flight on two streams, RT_OPT_LANES):
+//     k_primary_packet ray generation + closest hit, 32 rays (an 8x4 pixel block) per warp in ONE traversal with a
+//                      shared-memory stack; misses are shaded and stored at once, hit records go to dense per-slot arrays
+//     k_primary_items  x6, k_primary_finish: the packets that ran out of rounds, split into work items (short launches)
+//     k_compact        turns the per-slot hit records into the hit queue, block by block in slot order, so that 32
+//                      consecutive queue entries are 32 neighbouring pixels (coherent shadow packets); also the
+//                      reflection queue
+//     k_reflect        (only if a material reflects) one thread per reflective hit walks its rough-reflection fan
+//     k_shade_packet   32 queued hits per warp: textures / Blinn-Phong, any-hit shadow packet, compose, quantise, store
+//     k_shade_items    x6, k_shade_finish: the shadow packets that ran out of rounds, split into work items
+//   k_resolve          integer SSAA box filter of the quantised samples (imageUtils.h:98-147)
 //
-// plus the batch kernels behind rt_intersect / rt_occluded / rt_generate_primary_rays and tile pack/unpack.
-// Nothing here is a dense contraction, so no tensor-core path; the roofline that bounds these kernels is the
-// node/triangle fetch bandwidth.
+// plus the single-ray kernels k_primary / k_shade (RT_OPT_PACKETS 0: one traversal state machine per lane with lane
+// refill; they count the reference-shaped work for the roofline), the batch kernels behind rt_intersect / rt_occluded /
+// rt_generate_primary_rays and the tile pack / unpack of the framebuffer gather.
+// Nothing here is a dense contraction, so no tensor-core path; the kernels are bound by fp32 issue and L2 latency on
+// node/triangle fetches.
 #pragma once
 
 #include <cuda_runtime.h>

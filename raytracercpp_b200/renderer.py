@@ -3,7 +3,7 @@
 one C-ABI call each (include/rtb200.h).  The C++ twin is include/rtb200_renderer.hpp; this Python one exists so
 that tests and bench.py read like the reference's own harness (utils/mainUtils.cpp:6-21).
 
-Members that belong to the rasterizer / SSAO / analytic shapes / cube-map skybox are not on the path and are
+Members that belong to the rasterizer / SSAO / analytic shapes are not on the path and are
 absent on purpose (the reference GUI keeps calling its own code for those).
 """
 from __future__ import annotations
