@@ -157,6 +157,8 @@ struct RtContext {
     Tuning tune{16, 16, 8, 1, -256, -64, -256};
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
+    uint32_t* h_frame = nullptr;         // pinned staging buffer of rt_render
+    size_t h_frame_cap = 0;
     int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
     bool opt_screen_cull = true;
     bool opt_lanes = true;
@@ -479,6 +481,7 @@ void rt_destroy(RtContext* ctx)
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
     if (ctx->pending.host_cnt) cudaFreeHost(ctx->pending.host_cnt);
+    if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1032,10 +1035,30 @@ int rt_render(RtContext* ctx, const RtSettings* s, uint32_t* argb_out, RtRenderS
     if (!argb_out) return fail(ctx, RT_ERR_INVALID, "argb_out is NULL");
     const size_t n = (size_t)s->image_width * s->image_height;
     RT_CUDA(ctx, ctx->d_frame.ensure(n));
-    int r = rt_render_device(ctx, s, ctx->d_frame.p, 64, 1, 0, stats);
-    if (r) return r;
-    RT_CUDA(ctx, cudaMemcpyAsync(argb_out, ctx->d_frame.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // The caller's buffer is ordinary pageable memory (the adapter hands a std::vector, the GUI a QImage): a device-to-host
+    // copy straight into it is staged by the driver in small pieces.  Frames of a megapixel and more go through a pinned
+    // buffer of the context instead -- the copy is enqueued behind the frame's kernels, one host wait covers both -- and
+    // are moved to the caller's buffer by all host threads.
+    const bool staged = n >= ((size_t)1 << 20);
+    if (staged && n > ctx->h_frame_cap) {
+        if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+        ctx->h_frame = nullptr; ctx->h_frame_cap = 0;
+        if (cudaHostAlloc((void**)&ctx->h_frame, n * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess) ctx->h_frame_cap = n;
+        else { ctx->h_frame = nullptr; (void)cudaGetLastError(); }             // no pinned memory to be had: copy directly
+    }
+    if (int r = rt_render_device_begin(ctx, s, ctx->d_frame.p, 64, 1, 0)) return r;
+    uint32_t* dst = (staged && ctx->h_frame) ? ctx->h_frame : argb_out;
+    cudaError_t ce = cudaMemcpyAsync(dst, ctx->d_frame.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (int r = rt_render_device_end(ctx, stats)) return r;                       // waits for the stream: kernels and copy
+    if (ce != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "cudaMemcpyAsync(frame): %s", cudaGetErrorString(ce));
+    if (dst != argb_out) {
+        const long long chunks = (long long)((n + 65535) / 65536);
+#pragma omp parallel for schedule(static)
+        for (long long c = 0; c < chunks; c++) {
+            const size_t b = (size_t)c * 65536, e = std::min(n, b + 65536);
+            memcpy(argb_out + b, ctx->h_frame + b, (e - b) * sizeof(uint32_t));
+        }
+    }
     return RT_OK;
 }
 
