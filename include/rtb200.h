@@ -211,6 +211,16 @@ int rt_transform_triangles(RtContext* ctx, const float m[16], int max_depth, int
 /* Renderer::set_materials / get_materials().materials -- renderer.cpp:150-152. */
 int rt_set_materials(RtContext* ctx, const RtMaterial* mats, size_t n);
 
+/* Renderer::add_analytic_shape(Sphere(center, radius, mat_index)) / (Plane(point, normal, mat_index)) -- renderer.cpp:146,
+ * analyticShape.h:22-55; rt_clear_analytic_shapes: the shapes half of Renderer::clear_geometry (renderer.cpp:182-186).
+ * Shapes are tested after the BVH, in the order they were added, by trace_ray (renderer.cpp:1029-1037) and is_shadowed
+ * (:376-397).  A frame with shapes refuses the texture-mapping switches and the barycentric / AO debug modes: the
+ * reference reads HitInfo::triangle there, which a shape hit leaves stale or null.  `normal` is used as given
+ * (the reference expects it normalised). */
+int rt_add_sphere(RtContext* ctx, const float center[3], float radius, int32_t mat_index);
+int rt_add_plane(RtContext* ctx, const float point[3], const float normal[3], int32_t mat_index);
+int rt_clear_analytic_shapes(RtContext* ctx);
+
 /* Renderer::set_*_map(const Image&) / set_skysphere -- renderer.cpp:194-201.  Texels are RGBA, row 0 first
  * (no Y flip, QT/mainwindow.cpp:285).  f32 is the reference's `Image` storage; u8 is the on-disk form,
  * decoded on the device as u8 * (1/255.f) exactly like read_image (image_io.cpp:115-121). */

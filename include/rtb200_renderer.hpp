@@ -9,7 +9,7 @@
 //   ImageT      : .width() .height() .data() -> const float* RGBA                                      (image.h:99-118)
 //   TransformT  : .m[4][4] row-major                                                                   (mat.h)
 //   PointT      : .x .y .z
-// Members of the reference class that belong to the rasterizer, SSAO or analytic shapes are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
+// Members of the reference class that belong to the rasterizer or SSAO are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
 #pragma once
 
 #include <cstdint>
@@ -103,6 +103,20 @@ public:
 
     void change_camera_fov(float fov) { _fov = fov; push_camera(); }                                      // renderer.cpp:189
     void change_camera_aspect_ratio(float aspect) { _aspect = aspect; push_camera(); }                    // renderer.cpp:190
+    // Renderer::add_analytic_shape(const AnalyticShapesTypes&) -- renderer.cpp:146.  Sphere and Plane keep their members
+    // private (analyticShape.h:33-55), so the adapter takes what their constructors take.
+    template <class PointT> void add_sphere(const PointT& center, float radius, int mat_index)
+    {
+        const float c[3] = {center.x, center.y, center.z};
+        check(rt_add_sphere(_ctx, c, radius, mat_index));
+    }
+    template <class PointT, class VectorT> void add_plane(const PointT& point, const VectorT& normal, int mat_index)
+    {
+        const float p[3] = {point.x, point.y, point.z}, n[3] = {normal.x, normal.y, normal.z};
+        check(rt_add_plane(_ctx, p, n, mat_index));
+    }
+    void clear_analytic_shapes() { check(rt_clear_analytic_shapes(_ctx)); }
+
     template <class PointT> void set_light_position(const PointT& p)                                      // renderer.cpp:191
     {
         float l[3] = {p.x, p.y, p.z};

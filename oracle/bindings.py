@@ -140,6 +140,8 @@ class CpuTracer:
         f("renderer_set_texture_u8").argtypes = [C.c_void_p, C.c_int, BP, C.c_int, C.c_int]
         f("renderer_set_camera_transform").argtypes = [C.c_void_p, FP]
         f("renderer_set_light").argtypes = [C.c_void_p, FP]
+        f("renderer_add_sphere").argtypes = [C.c_void_p, FP, C.c_float, C.c_int]
+        f("renderer_add_plane").argtypes = [C.c_void_p, FP, FP, C.c_int]
         f("camera_matrices").argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, FP, FP]
         f("transform_inverse").argtypes = [FP, FP]
         f("renderer_render").restype = C.c_double
@@ -304,6 +306,14 @@ class CpuRenderer:
     def set_camera_transform(self, m):
         self.cam_to_world = _f32(m).reshape(4, 4).copy()
         self.tr._fn("renderer_set_camera_transform")(self.h, _ptr(self.cam_to_world, C.c_float))
+
+    def add_sphere(self, center, radius, mat_index):
+        c = _f32(center)
+        self.tr._fn("renderer_add_sphere")(self.h, _ptr(c, C.c_float), float(radius), int(mat_index))
+
+    def add_plane(self, point, normal, mat_index):
+        p, n = _f32(point), _f32(normal)
+        self.tr._fn("renderer_add_plane")(self.h, _ptr(p, C.c_float), _ptr(n, C.c_float), int(mat_index))
 
     def set_light(self, p):
         p = _f32(p)

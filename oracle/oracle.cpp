@@ -562,7 +562,52 @@ struct Renderer {
     V3 cam_pos = {0, 0, 0};
     M4 cam_to_world = identity();
 
+    // Renderer::_analytic_shapes (renderer.h:331), in the order of add_analytic_shape
+    struct Shape {
+        int kind;            // 0 = Sphere, 1 = Plane
+        V3 a;                // centre / point
+        V3 n;                // plane normal
+        float radius2;       // Sphere::_radius2 = radius * radius (analyticShape.cpp:7)
+        int mat;
+    };
+    std::vector<Shape> shapes;
+
     ~Renderer() { delete bvh; }
+
+    // Sphere::intersect / Plane::intersect -- analyticShape.cpp:9-76.  hit is the record the caller hands in (the reference
+    // writes t into it even when it then returns false); only t, normal, mat of a successful test are read afterwards.
+    static bool shape_intersect(const Shape& sh, const RayT& ray, Hit& hit)
+    {
+        if (sh.kind == 0) {
+            V3 L = sub(ray.o, sh.a);
+            constexpr float a = 1;
+            float b = 2 * dot(ray.d, L);
+            float c = dot(L, L) - sh.radius2;
+            float delta = b * b - 4 * a * c;
+            if (delta < 0) return false;
+            constexpr float a2 = 2 * a;
+            if (delta == 0.0) hit.t = -b / a2;
+            else {
+                float sqrt_delta = std::sqrt(delta);
+                float t1 = (-b - sqrt_delta) / a2;
+                float t2 = (-b + sqrt_delta) / a2;
+                if (t1 < t2) {
+                    hit.t = t1;
+                    if (hit.t < 0) hit.t = t2;
+                }
+            }
+            if (hit.t < 0) return false;
+            hit.normal = normalize(sub(add(ray.o, scale(hit.t, ray.d)), sh.a));
+            hit.mat = sh.mat;
+            return true;
+        }
+        float t = dot(sub(sh.a, ray.o), sh.n) / dot(ray.d, sh.n);
+        if (t < 0) return false;
+        hit.t = t;
+        hit.mat = sh.mat;
+        hit.normal = sh.n;
+        return true;
+    }
 
     static constexpr float EPSILON = 1.0e-4f;                                       // renderer.h:23
     static constexpr float SHADOW_INTENSITY = 0.5f;                                 // renderer.h:24
@@ -589,7 +634,7 @@ struct Renderer {
         return normalize(p);
     }
 
-    // Renderer::is_shadowed -- renderer.cpp:340-402 (BVH branch; analytic shapes are outside the path)
+    // Renderer::is_shadowed -- renderer.cpp:340-402 (BVH branch, then the analytic shapes)
     bool is_shadowed(V3 p, V3 n, RenderCounters* rc, bool secondary) const
     {
         if (!s.compute_shadows) return false;
@@ -604,6 +649,11 @@ struct Renderer {
             V3 q = add(ray.o, scale(h.t, ray.d));
             if (length2(sub(p, q)) < length2(sub(p, light))) return true;
         }
+        for (const Shape& sh : shapes)                                               // :376-397, the same HitInfo all along
+            if (shape_intersect(sh, ray, h)) {
+                V3 q = add(ray.o, scale(h.t, ray.d));
+                if (length2(sub(p, q)) < length2(sub(p, light))) return true;
+            }
         return false;
     }
 
@@ -770,7 +820,7 @@ struct Renderer {
         return tex[RT_TEX_SKYBOX_RIGHT + face_index].texture_bilinear(u, v);
     }
 
-    // Renderer::trace_ray -- renderer.cpp:1008-1066 (BVH branch; analytic shapes are outside the path)
+    // Renderer::trace_ray -- renderer.cpp:1008-1066 (BVH branch, then the analytic shapes)
     Col trace_ray(const RayT& ray, Hit& final_hit, int depth, bool& found, XorShift& rng, RenderCounters* rc, bool secondary) const
     {
         Hit local;
@@ -782,6 +832,9 @@ struct Renderer {
         }
         if (bvh->intersect(ray, local, c))
             if (local.t < final_hit.t || final_hit.t == -1) final_hit = local;
+        for (const Shape& sh : shapes)                                               // :1029-1037
+            if (shape_intersect(sh, ray, local))
+                if (local.t < final_hit.t || final_hit.t == -1) final_hit = local;
         float min_t = 0.1;
         if (final_hit.t > min_t) {
             found = true;
@@ -1013,6 +1066,16 @@ void orc_renderer_set_camera_transform(void* h, const float m[16])
 }
 
 void orc_renderer_set_light(void* h, const float p[3]) { ((Renderer*)h)->light = v3(p[0], p[1], p[2]); }
+
+// Renderer::add_analytic_shape(Sphere(center, radius, mat)) / (Plane(point, normal, mat)) -- renderer.cpp:146
+void orc_renderer_add_sphere(void* h, const float c[3], float radius, int mat)
+{
+    ((Renderer*)h)->shapes.push_back(Renderer::Shape{0, v3(c[0], c[1], c[2]), v3(0, 0, 0), radius * radius, mat});
+}
+void orc_renderer_add_plane(void* h, const float p[3], const float n[3], int mat)
+{
+    ((Renderer*)h)->shapes.push_back(Renderer::Shape{1, v3(p[0], p[1], p[2]), v3(n[0], n[1], n[2]), 0.0f, mat});
+}
 
 void orc_camera_matrices(float fov, float aspect, float znear, float zfar, float* proj16, float* proj_inv16)
 {

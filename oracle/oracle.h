@@ -28,6 +28,8 @@ void orc_renderer_set_texture_f32(void* h, int slot, const float* rgba, int w, i
 void orc_renderer_set_texture_u8(void* h, int slot, const uint8_t* rgba, int w, int hgt);
 void orc_renderer_set_camera_transform(void* h, const float m[16]);
 void orc_renderer_set_light(void* h, const float p[3]);
+void orc_renderer_add_sphere(void* h, const float c[3], float radius, int mat);
+void orc_renderer_add_plane(void* h, const float p[3], const float n[3], int mat);
 void orc_camera_matrices(float fov, float aspect, float znear, float zfar, float* proj16, float* proj_inv16);
 void orc_transform_inverse(const float m[16], float* out16);
 double orc_renderer_render(void* h, uint32_t* argb_out, int threads);

@@ -292,6 +292,16 @@ void ref_renderer_set_camera_transform(void* handle, const float m[16])
     ((RefRenderer*)handle)->renderer.set_camera_transform(transform_from(m));
 }
 
+// Renderer::add_analytic_shape -- renderer.cpp:146
+void ref_renderer_add_sphere(void* handle, const float c[3], float radius, int mat)
+{
+    ((RefRenderer*)handle)->renderer.add_analytic_shape(Sphere(Point(c[0], c[1], c[2]), radius, mat));
+}
+void ref_renderer_add_plane(void* handle, const float p[3], const float n[3], int mat)
+{
+    ((RefRenderer*)handle)->renderer.add_analytic_shape(Plane(Point(p[0], p[1], p[2]), Vector(n[0], n[1], n[2]), mat));
+}
+
 void ref_renderer_set_light(void* handle, const float p[3])
 {
     ((RefRenderer*)handle)->renderer.set_light_position(Point(p[0], p[1], p[2]));

@@ -114,6 +114,9 @@ ABI = {
     "rt_invert_transform": (None, [FP, FP]),
     "rt_transform_point": (None, [FP, FP, FP]),
     "rt_set_light": (C.c_int, [C.c_void_p, FP]),
+    "rt_add_sphere": (C.c_int, [C.c_void_p, FP, C.c_float, C.c_int32]),
+    "rt_add_plane": (C.c_int, [C.c_void_p, FP, FP, C.c_int32]),
+    "rt_clear_analytic_shapes": (C.c_int, [C.c_void_p]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), UP, C.POINTER(RtRenderStats)]),
     "rt_render_device": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(RtRenderStats)]),
     "rt_render_device_begin": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -260,6 +263,17 @@ class Context:
     def set_light(self, p):
         p = _f32(p).reshape(3)
         self._check(self.lib.rt_set_light(self.h, _p(p, C.c_float)))
+
+    def add_sphere(self, center, radius, mat_index):
+        c = _f32(center).reshape(3)
+        self._check(self.lib.rt_add_sphere(self.h, _p(c, C.c_float), float(radius), int(mat_index)))
+
+    def add_plane(self, point, normal, mat_index):
+        p, n = _f32(point).reshape(3), _f32(normal).reshape(3)
+        self._check(self.lib.rt_add_plane(self.h, _p(p, C.c_float), _p(n, C.c_float), int(mat_index)))
+
+    def clear_analytic_shapes(self):
+        self._check(self.lib.rt_clear_analytic_shapes(self.h))
 
     # ---- host helpers -----------------------------------------------------------------------------------
     def perspective_inverse(self, fov, aspect, znear=0.1, zfar=1000.0):

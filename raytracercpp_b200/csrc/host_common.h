@@ -114,7 +114,37 @@ struct SceneFacts {
     uint32_t n_tris;
     int n_mats, min_mat_index, max_mat_index;
     int tex_format[RT_TEX_COUNT];
+    int n_shapes = 0, shape_min_mat = 0, shape_max_mat = -1;     // analytic shapes (rt_add_sphere / rt_add_plane)
 };
+
+// One analytic shape as the device reads it: 2 x float4 (rt_device.h, shape_intersect).
+struct HostShape {
+    float a[3];          // centre / point
+    float radius2;       // Sphere::_radius2 = radius * radius (analyticShape.cpp:7), in float
+    float n[3];          // plane normal
+    uint32_t bits;       // material index | kind << 31 (0 = sphere, 1 = plane)
+};
+static_assert(sizeof(HostShape) == 32, "two float4 per shape");
+
+inline HostShape make_sphere(const float c[3], float radius, int32_t mat)
+{
+    HostShape s;
+    s.a[0] = c[0]; s.a[1] = c[1]; s.a[2] = c[2];
+    s.radius2 = radius * radius;
+    s.n[0] = s.n[1] = s.n[2] = 0.0f;
+    s.bits = (uint32_t)mat & 0x7fffffffu;
+    return s;
+}
+
+inline HostShape make_plane(const float p[3], const float n[3], int32_t mat)
+{
+    HostShape s;
+    s.a[0] = p[0]; s.a[1] = p[1]; s.a[2] = p[2];
+    s.radius2 = 0.0f;
+    s.n[0] = n[0]; s.n[1] = n[1]; s.n[2] = n[2];
+    s.bits = ((uint32_t)mat & 0x7fffffffu) | 0x80000000u;
+    return s;
+}
 
 inline int check_scene_for_render(const SceneFacts& f, const RtSettings* s, std::string& why)
 {
@@ -126,6 +156,17 @@ inline int check_scene_for_render(const SceneFacts& f, const RtSettings* s, std:
         // the reference asserts on a bad material index (materials.h:117); here it is an error return
         if (f.n_mats == 0) return bad(RT_ERR_STATE, "RT_SHADING needs materials (rt_set_materials)");
         if (f.min_mat_index < 0 || f.max_mat_index >= f.n_mats) return bad(RT_ERR_STATE, "triangle material index out of range");
+    }
+    if (f.n_shapes > 0) {
+        // a shape hit leaves HitInfo::triangle / u / v stale or null in the reference (analyticShape.cpp:9-76): everything
+        // that would read them is undefined there and refused here
+        if (s->enable_ao_mapping || s->enable_diffuse_mapping || s->enable_normal_mapping || s->enable_roughness_mapping ||
+            s->enable_displacement_mapping)
+            return bad(RT_ERR_UNSUPPORTED, "texture mapping with analytic shapes reads a stale HitInfo::triangle in the reference");
+        if (s->shading_method == RT_BARYCENTRIC_COORDINATES_SHADING || s->shading_method == RT_VISUALIZE_AO)
+            return bad(RT_ERR_UNSUPPORTED, "this debug shading mode reads stale HitInfo fields for analytic shapes in the reference");
+        if (rt && (f.n_mats == 0 || f.shape_min_mat < 0 || f.shape_max_mat >= f.n_mats))
+            return bad(RT_ERR_STATE, "analytic shape material index out of range");
     }
     struct { int on; int slot; const char* msg; } need[] = {
         {(rt || s->shading_method == RT_VISUALIZE_AO) && s->enable_ao_mapping, RT_TEX_AO, "ao mapping enabled but no ao map set"},

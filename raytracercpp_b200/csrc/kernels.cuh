@@ -225,6 +225,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
                 q.slot_tri[slot] = S.best.tri; q.slot_t[slot] = S.best.t; q.slot_u[slot] = S.best.u; q.slot_v[slot] = S.best.v;
             } else {
                 q.slot_tri[slot] = -1;
+                if (sc.n_shapes > 0) q.slot_t[slot] = closest_found(S) ? S.best.t : -1.0f;   // see k_primary_shapes
                 super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, dir));
             }
         }
@@ -490,7 +491,10 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
                 const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
                 q.slot_tri[slot] = hit ? best.tri : -1;
                 if (hit) { q.slot_t[slot] = best.t; q.slot_u[slot] = best.u; q.slot_v[slot] = best.v; }
-                else if (active) super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+                else if (active) {
+                    if (sc.n_shapes > 0) q.slot_t[slot] = (best.tri >= 0 && best.t > 0.0f) ? best.t : -1.0f;   // see k_primary_shapes
+                    super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+                }
             }
         }
     }
@@ -571,22 +575,56 @@ k_primary_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
             slot_pixel(wk, fr, slot, px, py);
             primary_ray(fr, px, py, o, d);
             bool hit = false;
+            float gated_t = -1.0f;                                             // a BVH hit with 0 < t <= min_t, see k_primary_shapes
             if (key != kNoHitKey) {
                 const uint32_t tri = (uint32_t)sc.leaf_of[(uint32_t)key];
                 const rt_f4* tp = sc.tris + 3 * (size_t)tri;
                 float t, u, v;
-                if (tri_test(RT_LDG4(tp), RT_LDG4(tp + 1), RT_LDG4(tp + 2), o, -d, t, u, v) && t > 0.1f) {   // min_t, renderer.cpp:1039
-                    hit = true;
-                    q.slot_tri[slot] = (int32_t)tri; q.slot_t[slot] = t; q.slot_u[slot] = u; q.slot_v[slot] = v;
+                if (tri_test(RT_LDG4(tp), RT_LDG4(tp + 1), RT_LDG4(tp + 2), o, -d, t, u, v)) {
+                    if (t > 0.1f) {                                            // min_t, renderer.cpp:1039
+                        hit = true;
+                        q.slot_tri[slot] = (int32_t)tri; q.slot_t[slot] = t; q.slot_u[slot] = u; q.slot_v[slot] = v;
+                    } else if (t > 0.0f)
+                        gated_t = t;
                 }
             }
             if (!hit) {
                 q.slot_tri[slot] = -1;
+                if (sc.n_shapes > 0) q.slot_t[slot] = gated_t;
                 super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
             }
         } else {
             const uint32_t pps = (uint32_t)wk.patches_per_side;
             if (slot < (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch)) q.slot_tri[slot] = -1;   // slot without a ray
+        }
+    }
+}
+
+// trace_ray's loop over the analytic shapes (renderer.cpp:1029-1037), after the BVH part of the primary rays: a shape
+// replaces the closest hit so far when it is strictly closer (or when there is none), in the order the shapes were added;
+// then the min_t gate (:1039) decides between hit and miss.  The "closest hit so far" of a slot is slot_t: the BVH hit's
+// t, also when that hit is below min_t and the slot therefore counts as a miss (the primary kernels keep it then), else -1.
+// One thread per ray slot.  A shape hit is recorded as slot_tri = -2 - shape.
+__global__ void k_primary_shapes(SceneView sc, FrameView fr, WorkView wk, QueueView q, uint32_t total, uint32_t* super)
+{
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+        int px, py;
+        if (!slot_pixel(wk, fr, slot, px, py)) continue;
+        V3 o, d;
+        primary_ray(fr, px, py, o, d);
+        float final_t = q.slot_t[slot];
+        int best = -1;
+        for (int i = 0; i < sc.n_shapes; i++) {
+            float t;
+            V3 n;
+            int32_t m;
+            if (shape_intersect(sc, i, o, d, t, n, m) && (t < final_t || final_t == -1.0f)) { final_t = t; best = i; }
+        }
+        if (best < 0) continue;
+        if (final_t > 0.1f) { q.slot_tri[slot] = -2 - best; q.slot_t[slot] = final_t; }
+        else {
+            q.slot_tri[slot] = -1;
+            super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
         }
     }
 }
@@ -614,9 +652,10 @@ k_compact(SceneView sc, QueueView q, ChunkCounters* cnt, uint32_t total, int any
             const uint32_t slot = first + (uint32_t)j;
             if (slot < total) {
                 const int32_t tri = q.slot_tri[slot];
-                if (tri >= 0) {
+                if (tri != -1) {                             // a triangle (>= 0) or analytic shape -2 - tri
                     hits |= 1u << j;
-                    if (any_reflective && load_material(sc, load_tri_shade(sc, tri).mat).reflection > 0.0f) refl |= 1u << j;
+                    const int32_t mat = tri >= 0 ? load_tri_shade(sc, tri).mat : shape_material(sc, -2 - tri);
+                    if (any_reflective && load_material(sc, mat).reflection > 0.0f) refl |= 1u << j;
                 }
             }
         }
@@ -677,7 +716,7 @@ k_reflect(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
         HitRec hr;
         uint32_t pix;
         queue_ray(fr, wk, q, i, o, d, hr, pix);
-        Hit hit = complete_hit(sc, hr);
+        Hit hit = make_hit(sc, hr, o, d);
         V3 p;
         MatView m;
         shade_direct(sc, fr, o, d, hit, p, m);                             // updates hit.normal (normal mapping)
@@ -731,7 +770,7 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
                 V3 o, d;
                 HitRec hr;
                 queue_ray(fr, wk, q, entry, o, d, hr, pix);
-                Hit hit = complete_hit(sc, hr);
+                Hit hit = make_hit(sc, hr, o, d);
                 if (fr.s.shading_method != RT_SHADING)
                     super[pix] = quantise_argb(shade_debug(sc, fr, hit));
                 else {
@@ -763,7 +802,9 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
                 fan.refl_shadow_rays += (uint32_t)(packed >> 32);
                 if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
             }
-            super[pix] = quantise_argb(shade_compose(fr, m, direct, S.occluded, refl));
+            bool occluded = S.occluded;
+            if (sc.n_shapes > 0 && fr.s.compute_shadows && !occluded) occluded = shapes_occlude_ray(sc, S.o, -S.md, S.p, S.dist2);
+            super[pix] = quantise_argb(shade_compose(fr, m, direct, occluded, refl));
         }
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
@@ -791,7 +832,7 @@ RT_DEV ShadeLane shade_prepare(const SceneView& sc, const FrameView& fr, const W
     V3 o, d;
     HitRec hr;
     queue_ray(fr, wk, q, entry, o, d, hr, L.pix);
-    Hit hit = complete_hit(sc, hr);
+    Hit hit = make_hit(sc, hr, o, d);
     L.mat = hit.mat;
     L.rt = fr.s.shading_method == RT_SHADING;
     if (!L.rt) { L.direct = shade_debug(sc, fr, hit); L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1); }
@@ -808,6 +849,7 @@ RT_DEV void shade_store(const SceneView& sc, const FrameView& fr, const QueueVie
                         TraceCounters& fan, uint32_t* super)
 {
     if (!L.rt) { super[L.pix] = quantise_argb(L.direct); return; }
+    if (sc.n_shapes > 0 && fr.s.compute_shadows && !occluded) occluded = shapes_occlude(sc, L.p, L.nrm, fr.light);   // renderer.cpp:376-397
     const MatView m = load_material(sc, L.mat);
     Col refl = col(0.0f);
     if (m.reflection > 0.0f) {

@@ -51,6 +51,8 @@ struct SceneView {
     const rt_f4* mats;      // 4 per material (RtMaterial = 16 floats)
     const int32_t* orig;    // leaf order -> index in the caller's array (tie-break + reported ids)
     const int32_t* leaf_of; // the inverse: index in the caller's array -> leaf order (split primary packets)
+    const rt_f4* shapes;    // 2 per analytic shape, in the order they were added: (a.xyz, radius^2) (n.xyz, bits(mat | kind << 31))
+    int32_t n_shapes;       // kind 0 = Sphere (a = centre), 1 = Plane (a = point, n = normal)
     int32_t n_mats;
     uint32_t n_tris;
     TexView tex[RT_TEX_COUNT];
@@ -470,6 +472,68 @@ RT_DEV void tri_texcoords(const TriShade& ts, float u, float v, float& tex_u, fl
     tex_v = (1 - u - v) * ts.tv.x + u * ts.tv.y + v * ts.tv.z;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Analytic shapes: Sphere::intersect / Plane::intersect -- analyticShape.cpp:9-76, every operation as written there
+// (a sphere assumes a unit direction: a = 1, also for the un-normalised rays of rough reflections).  A hit record names
+// shape i as tri = -2 - i.  Only t, normal and material of a shape hit are ever read: frames with shapes refuse the
+// switches that would read the rest of the reference's HitInfo (host_common.h).
+RT_DEV bool shape_intersect(const SceneView& sc, int i, V3 o, V3 d, float& t_out, V3& n_out, int32_t& mat_out)
+{
+    const rt_f4 s0 = RT_LDG4(sc.shapes + 2 * (size_t)i), s1 = RT_LDG4(sc.shapes + 2 * (size_t)i + 1);
+    const uint32_t bits = f4_bits(s1.w);
+    const V3 a = v3(s0.x, s0.y, s0.z);
+    float t;
+    if (!(bits & 0x80000000u)) {
+        V3 L = o - a;
+        float b = 2 * dot(d, L);
+        float c = dot(L, L) - s0.w;
+        float delta = b * b - 4 * c;                             // a = 1: 4 * a * c
+        if (delta < 0) return false;
+        if (delta == 0.0f) t = -b / 2;
+        else {
+            float sq = sqrtf(delta);
+            float t1 = (-b - sq) / 2;
+            float t2 = (-b + sq) / 2;
+            if (!(t1 < t2)) return false;                        // only with NaN / inf input; the reference then reads a stale t
+            t = t1;
+            if (t < 0) t = t2;
+        }
+        if (t < 0) return false;
+        n_out = normalize((o + t * d) - a);
+    } else {
+        const V3 n = v3(s1.x, s1.y, s1.z);
+        t = dot(a - o, n) / dot(d, n);
+        if (t < 0) return false;
+        n_out = n;
+    }
+    t_out = t;
+    mat_out = (int32_t)(bits & 0x7fffffffu);
+    return true;
+}
+
+RT_DEV int32_t shape_material(const SceneView& sc, int i) { return (int32_t)(f4_bits(RT_LDG4(sc.shapes + 2 * (size_t)i + 1).w) & 0x7fffffffu); }
+
+// The shapes half of Renderer::is_shadowed -- renderer.cpp:376-397, for the shadow ray (o, d) of the shaded point p.
+RT_DEV bool shapes_occlude_ray(const SceneView& sc, V3 o, V3 d, V3 p, float dist2)
+{
+    for (int i = 0; i < sc.n_shapes; i++) {
+        float t;
+        V3 sn;
+        int32_t sm;
+        if (shape_intersect(sc, i, o, d, t, sn, sm)) {
+            V3 q = o + t * d;
+            if (length2(p - q) < dist2) return true;
+        }
+    }
+    return false;
+}
+
+RT_DEV bool shapes_occlude(const SceneView& sc, V3 p, V3 n, V3 light)
+{
+    // ray origin p + n * EPSILON (renderer.h:23), direction normalize(light - p) -- renderer.cpp:344
+    return shapes_occlude_ray(sc, p + 1.0e-4f * n, normalize(light - p), p, length2(p - light));
+}
+
 // Fills the HitInfo fields Triangle::intersect sets on a hit (triangle.cpp:81-88): material, normalised normal,
 // tangent (Triangle::get_tangent, triangle.cpp:134-153).
 RT_DEV Hit complete_hit(const SceneView& sc, const HitRec& hr)
@@ -488,6 +552,18 @@ RT_DEV Hit complete_hit(const SceneView& sc, const HitRec& hr)
     h.tangent = v3(f * (dv2 * ab.x - dv1 * ac.x), f * (dv2 * ab.y - dv1 * ac.y), f * (dv2 * ab.z - dv1 * ac.z));
     h.mat = ts.mat;
     h.normal = normalize(v3(p0.w, p1.w, p2.w));
+    return h;
+}
+
+// The hit record of a ray (origin o, direction d) as a Hit: a triangle (complete_hit) or analytic shape -2 - tri, whose
+// normal is recomputed from the ray exactly as Sphere::intersect / Plane::intersect computed it.
+RT_DEV Hit make_hit(const SceneView& sc, const HitRec& hr, V3 o, V3 d)
+{
+    if (hr.tri >= 0) return complete_hit(sc, hr);
+    Hit h = fresh_hit();
+    h.tri = hr.tri; h.t = hr.t;
+    float t;
+    shape_intersect(sc, -2 - hr.tri, o, d, t, h.normal, h.mat);
     return h;
 }
 
@@ -730,6 +806,14 @@ RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr
     if (trace_closest<COUNT>(sc, ro, rd, hr, tc)) {
         if (hr.t < final_hit.t || final_hit.t == -1.0f) final_hit = complete_hit(sc, hr);
     }
+    for (int i = 0; i < sc.n_shapes; i++) {                                          // renderer.cpp:1029-1037
+        float t;
+        V3 sn;
+        int32_t sm;
+        if (shape_intersect(sc, i, ro, rd, t, sn, sm) && (t < final_hit.t || final_hit.t == -1.0f)) {
+            final_hit.tri = -2 - i; final_hit.t = t; final_hit.normal = sn; final_hit.mat = sm;
+        }
+    }
     if (final_hit.t > 0.1f) {                                                        // min_t, renderer.cpp:1039
         if (fr.s.shading_method != RT_SHADING) return shade_debug(sc, fr, final_hit);
         V3 p;
@@ -738,7 +822,7 @@ RT_DEV_NOINLINE Col trace_ray_secondary(const SceneView& sc, const FrameView& fr
         bool shadowed = false;
         if (fr.s.compute_shadows) {
             if (tc) tc->refl_shadow_rays++;
-            shadowed = trace_occluded<COUNT>(sc, p, final_hit.normal, fr.light, tc);
+            shadowed = trace_occluded<COUNT>(sc, p, final_hit.normal, fr.light, tc) || (sc.n_shapes > 0 && shapes_occlude(sc, p, final_hit.normal, fr.light));
         }
         Col refl = col(0.0f);
         if (m.reflection > 0.0f) refl = compute_reflection<COUNT>(sc, fr, rd, p, final_hit, m, depth, rng, tc);

@@ -130,6 +130,8 @@ struct RtContext {
     RtBvhInfo info{};
     DevBuf<float4> d_recs, d_tris, d_shade, d_mats;
     DevBuf<int32_t> d_orig, d_leaf_of;
+    std::vector<HostShape> shapes;       // analytic shapes, in the order they were added
+    DevBuf<float4> d_shapes;
     uint32_t n_tris = 0;
     int n_mats = 0;
     bool any_reflective = false;
@@ -234,6 +236,8 @@ SceneView scene_view(const RtContext* ctx)
     sc.mats = ctx->d_mats.p;
     sc.orig = ctx->d_orig.p;
     sc.leaf_of = ctx->d_leaf_of.p;
+    sc.shapes = ctx->d_shapes.p;
+    sc.n_shapes = (int32_t)ctx->shapes.size();
     sc.n_mats = ctx->n_mats;
     sc.n_tris = ctx->n_tris;
     for (int i = 0; i < RT_TEX_COUNT; i++) {
@@ -258,6 +262,12 @@ int validate_scene_for_render(RtContext* ctx, const RtSettings* s)
     f.bvh_valid = ctx->bvh_valid; f.camera_set = ctx->camera_set; f.n_tris = ctx->n_tris; f.n_mats = ctx->n_mats;
     f.min_mat_index = ctx->min_mat_index; f.max_mat_index = ctx->max_mat_index;
     for (int i = 0; i < RT_TEX_COUNT; i++) f.tex_format[i] = ctx->tex[i].format;
+    f.n_shapes = (int)ctx->shapes.size();
+    for (const HostShape& sh : ctx->shapes) {
+        const int m = (int)(sh.bits & 0x7fffffffu);
+        f.shape_min_mat = std::min(f.shape_min_mat, m);
+        f.shape_max_mat = std::max(f.shape_max_mat, m);
+    }
     std::string why;
     int r = check_scene_for_render(f, s, why);
     return r ? fail(ctx, r, "%s", why.c_str()) : RT_OK;
@@ -470,7 +480,7 @@ void rt_destroy(RtContext* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release();
+    ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
@@ -646,6 +656,39 @@ int rt_set_materials(RtContext* ctx, const RtMaterial* mats, size_t n)
     return RT_OK;
 }
 
+static int upload_shapes(RtContext* ctx)
+{
+    if (int r = bind(ctx)) return r;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, ctx->d_shapes.ensure(2 * ctx->shapes.size()));
+    if (!ctx->shapes.empty())
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_shapes.p, ctx->shapes.data(), ctx->shapes.size() * sizeof(HostShape), cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+int rt_add_sphere(RtContext* ctx, const float center[3], float radius, int32_t mat_index)
+{
+    if (!ctx || !center) return RT_ERR_INVALID;
+    if (mat_index < 0) return fail(ctx, RT_ERR_INVALID, "material index %d", mat_index);
+    ctx->shapes.push_back(make_sphere(center, radius, mat_index));
+    return upload_shapes(ctx);
+}
+
+int rt_add_plane(RtContext* ctx, const float point[3], const float normal[3], int32_t mat_index)
+{
+    if (!ctx || !point || !normal) return RT_ERR_INVALID;
+    if (mat_index < 0) return fail(ctx, RT_ERR_INVALID, "material index %d", mat_index);
+    ctx->shapes.push_back(make_plane(point, normal, mat_index));
+    return upload_shapes(ctx);
+}
+
+int rt_clear_analytic_shapes(RtContext* ctx)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    ctx->shapes.clear();
+    return RT_OK;
+}
+
 static int set_texture(RtContext* ctx, int slot, const void* data, int width, int height, int format)
 {
     if (!ctx) return RT_ERR_INVALID;
@@ -727,7 +770,9 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     screen_cull_rect(ctx, fr, wk);
     // Tiles outside the screen-space bound of the scene cannot contain a hit: they get no ray slots, no queue entries and
     // no traversal, only the miss colour (k_fill_miss).  The wavefront below runs over the other tiles.
-    const bool classify = ctx->opt_screen_cull && ctx->tune.packets && tl->count > 0;
+    const bool has_shapes = !ctx->shapes.empty();                             // planes are unbounded: no screen-space bound
+    if (has_shapes) { wk.cull_x0 = 0; wk.cull_y0 = 0; wk.cull_x1 = fr.rw - 1; wk.cull_y1 = fr.rh - 1; }
+    const bool classify = ctx->opt_screen_cull && ctx->tune.packets && tl->count > 0 && !has_shapes;
     if (classify) {
         const int32_t rect[4] = {wk.cull_x0, wk.cull_y0, wk.cull_x1, wk.cull_y1};
         if (!tl->split_valid || memcmp(rect, tl->split_rect, sizeof(rect)) != 0 || tl->split_tile_px != wk.tile_px) {
@@ -864,6 +909,11 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
                 }
                 k_primary_finish<<<grid_pfinish, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
                 launches += kItemPasses + 1;
+            }
+            if (has_shapes) {                                                  // trace_ray's loop over the analytic shapes
+                const uint32_t slots = (wk.tile_end - wk.tile_begin) * (uint32_t)px_per_tile;
+                k_primary_shapes<<<ctx->sm_count * 8, 256, 0, st>>>(sc, fr, wk, q, slots, super);
+                launches++;
             }
         }
         {

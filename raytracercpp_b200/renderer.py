@@ -3,7 +3,7 @@
 one C-ABI call each (include/rtb200.h).  The C++ twin is include/rtb200_renderer.hpp; this Python one exists so
 that tests and bench.py read like the reference's own harness (utils/mainUtils.cpp:6-21).
 
-Members that belong to the rasterizer / SSAO / analytic shapes are not on the path and are
+Members that belong to the rasterizer / SSAO are not on the path and are
 absent on purpose (the reference GUI keeps calling its own code for those).
 """
 from __future__ import annotations
@@ -134,6 +134,16 @@ class Renderer:
 
     def set_light_position(self, position):
         self.ctx.set_light(position)
+
+    def add_analytic_shape(self, shape):
+        """Renderer::add_analytic_shape -- renderer.cpp:146.  shape = ("sphere", center, radius, mat_index) like
+        Sphere(center, radius, mat_index), or ("plane", point, normal, mat_index) like Plane(point, normal, mat_index)."""
+        if shape[0] == "sphere":
+            self.ctx.add_sphere(shape[1], shape[2], shape[3])
+        elif shape[0] == "plane":
+            self.ctx.add_plane(shape[1], shape[2], shape[3])
+        else:
+            raise ValueError(shape[0])
 
     def _push_camera(self):
         proj_inv = self.ctx.perspective_inverse(self._fov, self._aspect, self._near, self._far)

@@ -59,6 +59,9 @@ def configs(mats):
     mats3[1].update(reflection=0.5, roughness=0.4)
     mats3 = precompute_materials(mats3)
     tex3 = {3: tex2[3], 4: scenes.sky_texture((128, 256))}
+    mats_shapes = mats3 + precompute_materials([
+        dict(ambient_coeff=(1, 1, 1), diffuse=(0.2, 0.6, 0.3), specular=(0.4, 0.4, 0.4), emission=(0, 0, 0), reflection=0.0, roughness=0.0, ns=30.0),
+        dict(ambient_coeff=(1, 1, 1), diffuse=(0.7, 0.7, 0.8), specular=(0.6, 0.6, 0.6), emission=(0, 0, 0), reflection=0.6, roughness=0.3, ns=80.0)])
     return {
         "cfg1": (dict(image_width=320, image_height=180, compute_shadows=1), mats, {}),
         "cfg2": (dict(image_width=160, image_height=90, compute_shadows=1, enable_ssaa=1, ssaa_factor=2, enable_ao_mapping=1,
@@ -70,6 +73,11 @@ def configs(mats):
         "cfg2_pom": (dict(image_width=160, image_height=90, compute_shadows=1, enable_ao_mapping=1, enable_diffuse_mapping=1, enable_normal_mapping=1,
                           enable_displacement_mapping=1, displacement_mapping_strength=0.05, parallax_mapping_steps=16), mats,
                      {**tex2, 11: scenes.noise_texture((96, 96), 9)}),
+        # analytic shapes of the GUI (QT/mainwindow.cpp:828,883,914,930): a ground plane, a mirror sphere, a matte sphere, with the
+        # robot's own mirror materials; materials len(mats3) and len(mats3)+1 are appended for them
+        "cfg3_shapes": (dict(image_width=200, image_height=112, compute_shadows=1, max_recursion_depth=2, enable_skysphere=1), mats_shapes,
+                        {4: tex3[4], "shapes": [("plane", (0, -2, 0), (0, 1, 0), len(mats3)), ("sphere", (1.4, -1.2, -3.5), 0.5, len(mats3) + 1),
+                                                ("sphere", (-1.6, -1.5, -3.0), 0.4, len(mats3))]}),
         # the GUI's default miss shader (QT/mainwindow.cpp:45-46): cube-map skybox, seen directly and in mirror reflections
         "cfg3_skybox": (dict(image_width=200, image_height=112, compute_shadows=1, max_recursion_depth=2, enable_skybox=1), mats3,
                        {5 + i: scenes.noise_texture((48 + 8 * i, 40 + 4 * i), 20 + i, "rgb") for i in range(6)}),
@@ -84,7 +92,11 @@ def render_with(tracer, scene, kw, mats, tex, fov=80.0, seeded=False):
     r.set_materials(mats)
     r.set_light([3, 3, 2])
     for slot, img in tex.items():
-        r.set_texture(slot, img)
+        if slot == "shapes":
+            for sh in img:
+                (r.add_sphere if sh[0] == "sphere" else r.add_plane)(sh[1], sh[2], sh[3])
+        else:
+            r.set_texture(slot, img)
     if seeded:
         sup, _ = r.trace_rows()
         f = s.ssaa_factor if s.enable_ssaa else 1

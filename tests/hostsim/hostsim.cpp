@@ -39,6 +39,7 @@ struct RtContext {
     M4 proj_inv{}, cam_to_world{};
     V3 cam_pos{0, 0, 0}, light{3, 3, 2};
     int leaf_split = 8;
+    std::vector<HostShape> shapes;
 };
 
 static int fail(RtContext* c, int code, const std::string& msg)
@@ -58,6 +59,8 @@ static SceneView scene_view(const RtContext* c)
     sc.orig = c->flat.orig.data();
     sc.n_mats = c->n_mats;
     sc.n_tris = (uint32_t)(c->xyz9.size() / 9);
+    sc.shapes = reinterpret_cast<const F4*>(c->shapes.data());
+    sc.n_shapes = (int32_t)c->shapes.size();
     for (int i = 0; i < RT_TEX_COUNT; i++) {
         sc.tex[i].data = c->tex[i].bytes.data();
         sc.tex[i].w = c->tex[i].w;
@@ -196,6 +199,27 @@ static int set_tex(RtContext* c, int slot, const void* data, int w, int h, int f
     c->tex[slot].w = w; c->tex[slot].h = h; c->tex[slot].format = format;
     return RT_OK;
 }
+int rt_add_sphere(RtContext* c, const float center[3], float radius, int32_t mat)
+{
+    if (!c || !center) return RT_ERR_INVALID;
+    if (mat < 0) return fail(c, RT_ERR_INVALID, "material index");
+    c->shapes.push_back(make_sphere(center, radius, mat));
+    return RT_OK;
+}
+int rt_add_plane(RtContext* c, const float point[3], const float normal[3], int32_t mat)
+{
+    if (!c || !point || !normal) return RT_ERR_INVALID;
+    if (mat < 0) return fail(c, RT_ERR_INVALID, "material index");
+    c->shapes.push_back(make_plane(point, normal, mat));
+    return RT_OK;
+}
+int rt_clear_analytic_shapes(RtContext* c)
+{
+    if (!c) return RT_ERR_INVALID;
+    c->shapes.clear();
+    return RT_OK;
+}
+
 int rt_set_texture_f32(RtContext* c, int slot, const float* rgba, int w, int h) { return set_tex(c, slot, rgba, w, h, 2); }
 int rt_set_texture_u8(RtContext* c, int slot, const uint8_t* rgba, int w, int h) { return set_tex(c, slot, rgba, w, h, 1); }
 int rt_clear_texture(RtContext* c, int slot)
@@ -230,6 +254,12 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
     f.bvh_valid = c->bvh_valid; f.camera_set = c->camera_set; f.n_tris = (uint32_t)(c->xyz9.size() / 9); f.n_mats = c->n_mats;
     f.min_mat_index = c->min_mat; f.max_mat_index = c->max_mat;
     for (int i = 0; i < RT_TEX_COUNT; i++) f.tex_format[i] = c->tex[i].format;
+    f.n_shapes = (int)c->shapes.size();
+    for (const HostShape& sh : c->shapes) {
+        const int m = (int)(sh.bits & 0x7fffffffu);
+        f.shape_min_mat = std::min(f.shape_min_mat, m);
+        f.shape_max_mat = std::max(f.shape_max_mat, m);
+    }
     if (int r = check_scene_for_render(f, s, why)) return fail(c, r, why);
     if (tile_size <= 0 || tile_mod <= 0 || tile_rem < 0 || tile_rem >= tile_mod) return fail(c, RT_ERR_INVALID, "tile args");
 
@@ -266,11 +296,19 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
                 bool found = trace_closest<true>(sc, o, d, hr, &tc);
                 rs.primary_volume_tests += tc.vol_tests; rs.primary_triangle_tests += tc.tri_tests;
                 if (tc.stack_overflow) return fail(c, RT_ERR_STATE, "traversal stack overflow");
+                // trace_ray's loop over the analytic shapes (renderer.cpp:1029-1037), then the min_t gate (:1039)
+                float final_t = found ? hr.t : -1.0f;
+                for (int i = 0; i < sc.n_shapes; i++) {
+                    float t;
+                    V3 sn;
+                    int32_t sm;
+                    if (shape_intersect(sc, i, o, d, t, sn, sm) && (t < final_t || final_t == -1.0f)) { final_t = t; hr.tri = -2 - i; hr.t = t; found = true; }
+                }
                 bool hit = found && hr.t > 0.1f;
                 if (!hit) { super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d)); continue; }
                 if (reflect) {
-                    TriShade ts = load_tri_shade(sc, hr.tri);
-                    if (load_material(sc, ts.mat).reflection > 0.0f) refl_idx.push_back((uint32_t)queue.size());
+                    const int32_t mat = hr.tri >= 0 ? load_tri_shade(sc, hr.tri).mat : shape_material(sc, -2 - hr.tri);
+                    if (load_material(sc, mat).reflection > 0.0f) refl_idx.push_back((uint32_t)queue.size());
                 }
                 queue.push_back(QEntry{(uint32_t)py * (uint32_t)fr.rw + (uint32_t)px, hr});
             }
@@ -284,7 +322,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
         const QEntry& e = queue[refl_idx[r]];
         V3 o, d;
         primary_ray(fr, (int)(e.pix % (uint32_t)fr.rw), (int)(e.pix / (uint32_t)fr.rw), o, d);
-        Hit hit = complete_hit(sc, e.hr);
+        Hit hit = make_hit(sc, e.hr, o, d);
         V3 p;
         MatView m;
         shade_direct(sc, fr, o, d, hit, p, m);
@@ -305,7 +343,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
         const QEntry& e = queue[i];
         V3 o, d;
         primary_ray(fr, (int)(e.pix % (uint32_t)fr.rw), (int)(e.pix / (uint32_t)fr.rw), o, d);
-        Hit hit = complete_hit(sc, e.hr);
+        Hit hit = make_hit(sc, e.hr, o, d);
         Col cc;
         if (fr.s.shading_method != RT_SHADING) cc = shade_debug(sc, fr, hit);
         else {
@@ -314,7 +352,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
             Col direct = shade_direct(sc, fr, o, d, hit, p, m);
             bool shadowed = false;
             TraceCounters tc = zero_counters();
-            if (fr.s.compute_shadows) shadowed = trace_occluded<true>(sc, p, hit.normal, fr.light, &tc);
+            if (fr.s.compute_shadows) shadowed = trace_occluded<true>(sc, p, hit.normal, fr.light, &tc) || (sc.n_shapes > 0 && shapes_occlude(sc, p, hit.normal, fr.light));
             sv += tc.vol_tests; stt += tc.tri_tests;
             Col refl = m.reflection > 0.0f ? refl_rgb[i] : col(0.0f);
             cc = shade_compose(fr, m, direct, shadowed, refl);

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import raytracercpp_b200 as rt
-from raytracercpp_b200 import api
+from raytracercpp_b200 import api, scenes
 from tests import common
 
 
@@ -99,7 +99,7 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
         r.ray_trace()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_pom", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_pom", "cfg3", "cfg3_mirror5", "cfg3_skybox", "cfg3_shapes"])
 def test_frames_bit_exact(hostsim_lib, oracle, robot, golden_images, name):
     kw, mats, tex = common.config_table(robot["materials"])[name]
     img, stats = common.product_image(hostsim_lib, robot, kw, mats, tex)
@@ -298,3 +298,41 @@ def test_parallel_build_of_a_large_mesh(hostsim_lib, oracle, split):
         assert np.array_equal(g, w)
     assert (want[0] >= 0).sum() > 5000
     ctx.close()
+
+
+def test_analytic_shapes_gate_order_and_refusals(hostsim_lib, oracle, robot):
+    """trace_ray takes the CLOSEST of the BVH hit and the analytic shapes and only then applies min_t (renderer.cpp:
+    1029-1040): a plane 0.05 in front of the camera hides the robot AND is itself rejected, so the frame is background; a
+    far plane behind the robot changes only the background pixels.  Texture mapping and the barycentric / AO debug modes
+    are refused while shapes exist (the reference reads a stale HitInfo::triangle there)."""
+    mats = list(robot["materials"])
+    kw = dict(image_width=96, image_height=54, compute_shadows=1)
+    bg = 0xff000000 | (135 << 16) | (206 << 8) | 235
+    near = {"shapes": [("plane", (0, 0, -0.05), (0, 0, 1), 0)]}
+    img, st = common.product_image(hostsim_lib, robot, kw, mats, near)
+    assert (img == bg).all() and st.primary_hits == 0
+    assert np.array_equal(img, common.oracle_image(oracle, robot, kw, mats, near))
+    far = {"shapes": [("plane", (0, 0, -9), (0, 0, 1), 1), ("sphere", (0, 0, 0), 0.08, 0)]}     # the sphere around the camera: t = 0.08, rejected too
+    img2, st2 = common.product_image(hostsim_lib, robot, kw, mats, far)
+    want2 = common.oracle_image(oracle, robot, kw, mats, far)
+    assert np.array_equal(img2, want2)
+    plain, _ = common.product_image(hostsim_lib, robot, kw, mats, {})
+    assert (img2 == bg).all() and (plain != bg).any()        # the rejected sphere is the closest hit of every ray
+    r = common.product_renderer(hostsim_lib, robot, dict(kw, enable_ao_mapping=1), mats, {0: scenes.noise_texture((32, 32), 2), "shapes": far["shapes"][:1]})
+    with pytest.raises(api.RtError) as e:
+        r.ray_trace()
+    assert e.value.code == api.RT_ERR_UNSUPPORTED
+    r.render_settings().enable_ao_mapping = 0
+    r.render_settings().shading_method = api.RT_BARYCENTRIC_COORDINATES_SHADING
+    with pytest.raises(api.RtError) as e:
+        r.ray_trace()
+    assert e.value.code == api.RT_ERR_UNSUPPORTED
+    r.render_settings().shading_method = api.RT_ABS_NORMALS_SHADING
+    r.ray_trace()
+    want3 = common.oracle_image(oracle, robot, dict(kw, shading_method=api.RT_ABS_NORMALS_SHADING), mats, {"shapes": far["shapes"][:1]})
+    assert np.array_equal(r.get_image(), want3)
+    r.ctx.clear_analytic_shapes()
+    r.render_settings().shading_method = api.RT_SHADING
+    r.ray_trace()
+    assert np.array_equal(r.get_image(), plain)
+    r.close()

@@ -32,7 +32,7 @@ def test_reference_kats(oracle, golden_images):
     assert list(g["kat_hit"][:4]) == [False] * 4
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_pom", "cfg3", "cfg3_mirror5", "cfg3_skybox"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_pom", "cfg3", "cfg3_mirror5", "cfg3_skybox", "cfg3_shapes"])
 def test_images_match_reference(oracle, robot, golden_images, name):
     kw, mats, tex = common.config_table(robot["materials"])[name]
     img = common.oracle_image(oracle, robot, kw, mats, tex)
