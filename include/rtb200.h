@@ -284,7 +284,8 @@ int rt_intersect(RtContext* ctx, const float* o3, const float* d3, size_t n,
                  int32_t* tri_id, float* t, float* u, float* v);
 
 /* Batched Renderer::is_shadowed -- renderer.cpp:340-402.  p3 = inter_point, n3 = shading normal,
- * light = the context's light.  occluded[i] = 1 iff the reference returns true. */
+ * light = the context's light.  occluded[i] = 1 iff the reference returns true (BVH, then the analytic shapes).
+ * rt_intersect above is BVH::intersect alone: the shapes are Renderer state, not part of the BVH. */
 int rt_occluded(RtContext* ctx, const float* p3, const float* n3, size_t n, uint8_t* occluded);
 
 /* Primary-ray generation only (renderer.cpp:1083-1098) for the supersampled frame of `settings`:

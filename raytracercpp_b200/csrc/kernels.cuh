@@ -1146,7 +1146,7 @@ k_occluded(SceneView sc, V3 light, const float* p3, const float* n3, size_t n, u
         V3 p = v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]);
         V3 nn = v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]);
         TraceCounters tc = zero_counters();
-        occluded[i] = trace_occluded<false>(sc, p, nn, light, &tc) ? 1 : 0;
+        occluded[i] = (trace_occluded<false>(sc, p, nn, light, &tc) || (sc.n_shapes > 0 && shapes_occlude(sc, p, nn, light))) ? 1 : 0;
         if (tc.stack_overflow) atomicOr(overflow, 1u);
     }
 }

@@ -466,7 +466,7 @@ int rt_occluded(RtContext* c, const float* p3, const float* n3, size_t n, uint8_
     const SceneView sc = scene_view(c);
 #pragma omp parallel for schedule(dynamic, 256)
     for (long long i = 0; i < (long long)n; i++)
-        { TraceCounters tcs = zero_counters(); occluded[i] = trace_occluded<false>(sc, v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]), c->light, &tcs) ? 1 : 0; }
+        { TraceCounters tcs = zero_counters(); const V3 pp = v3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]), nn = v3(n3[3 * i], n3[3 * i + 1], n3[3 * i + 2]); occluded[i] = (trace_occluded<false>(sc, pp, nn, c->light, &tcs) || (sc.n_shapes > 0 && shapes_occlude(sc, pp, nn, c->light))) ? 1 : 0; }
     return RT_OK;
 }
 

@@ -336,3 +336,21 @@ def test_analytic_shapes_gate_order_and_refusals(hostsim_lib, oracle, robot):
     r.ray_trace()
     assert np.array_equal(r.get_image(), plain)
     r.close()
+
+
+def test_batched_is_shadowed_sees_the_shapes(hostsim_lib, robot):
+    """rt_occluded = Renderer::is_shadowed: a big sphere between the points and the light shadows points the robot alone does not."""
+    ctx = api.Context(0, hostsim_lib)
+    ctx.set_triangles(robot["xyz9"], robot["uv6"], robot["mat"])
+    ctx.build_bvh(12, 40)
+    ctx.set_light(common.LIGHT)
+    rng = np.random.default_rng(3)
+    p = (rng.uniform(-1, 1, size=(500, 3)) * np.float32([2, 0.2, 1]) + np.float32([0, -3.5, -4])).astype(np.float32)   # below the robot
+    n = np.tile(np.float32([0, 1, 0]), (500, 1))
+    before = ctx.occluded(p, n)
+    ctx.add_sphere((1.5, 0.0, -1.0), 2.5, 0)             # swallows the way to the light at (3, 3, 2)
+    after = ctx.occluded(p, n)
+    assert after.all() and not before.all() and (after >= before).all()
+    ctx.clear_analytic_shapes()
+    assert np.array_equal(ctx.occluded(p, n), before)
+    ctx.close()
