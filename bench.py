@@ -29,11 +29,28 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
     # name: (triangles, width, height, ssaa, bvh_max_depth, bvh_leaf_object_count)
-    "cfg4_sphere10M_4k_16spp": (10_000_000, 3840, 2160, 4, 12, 40),
+    "cfg4_sphere10M_4k_16spp": (10_000_000, 3840, 2160, 4, 12, 40),    # BASELINE.json configs[3]: the headline configuration (default)
+    # the same mesh and frame with the camera 0.2 in front of the surface: 96 % of the samples hit, so traversal throughput is
+    # not averaged with samples that never get a ray (cfg4 proper: the sphere covers 8 % of the frame)
+    "cfg4_fill_sphere10M_4k_16spp": (10_000_000, 3840, 2160, 4, 12, 40),
     "sphere1M_1080p_4spp": (1_000_000, 1920, 1080, 2, 12, 40),         # for quick local checks only
     "cfg5_hair1M_4k": (1_000_000, 3840, 2160, 1, 12, 40),              # BASELINE.json configs[4]: ~1 M thin strand triangles, 4K, shadows
+    # BASELINE.json configs[0..2] on the robot mesh (tests/golden/robot_scene.npz, cut from tp2/data/Robot/robot.obj)
+    "cfg1_robot_720p": (3238, 1280, 720, 1, 12, 40),
+    "cfg2_robot_textured_720p_4spp": (3238, 1280, 720, 2, 12, 40),
+    "cfg3_robot_reflect16_1080p": (3238, 1920, 1080, 1, 12, 40),
 }
 FOV, LIGHT = 80.0, (3.0, 3.0, 2.0)
+REFERENCE_BUILD = ("unmodified reference sources, g++ -O3 -mfma -fopenmp -march=x86-64-v3 (oracle/Makefile; the reference's own CMake uses "
+                   "-march=native, which would not run on another host's CPU)")
+CAMERA_Z = {"cfg4_fill_sphere10M_4k_16spp": -1.8}                       # camera_to_world = Translation(0, 0, z); identity elsewhere
+
+
+def host_cpus() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def log(*a):
@@ -63,14 +80,32 @@ def make_scene(name):
     from raytracercpp_b200 import scenes
     from raytracercpp_b200.renderer import precompute_materials
     tris, w, h, f, depth, leaf = WORKLOADS[name]
-    if "hair" in name:
-        xyz9, uv6, mat = scenes.hair_ball(n_strands=tris // 64, segments=16)
-    else:
-        xyz9, uv6, mat = scenes.displaced_sphere(*scenes.sphere_grid_for(tris))
-    mats = precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
     kw = dict(image_width=w, image_height=h, enable_ssaa=int(f > 1), ssaa_factor=f, compute_shadows=1, bvh_max_depth=depth,
               bvh_leaf_object_count=leaf)
-    return dict(xyz9=xyz9, uv6=uv6, mat=mat, mats=mats, kw=kw, name=name)
+    tex = {}
+    if "robot" in name:
+        z = np.load(ROOT / "tests" / "golden" / "robot_scene.npz")
+        xyz9, uv6, mat = z["xyz9"], z["uv6"], z["mat"]
+        mats = [dict(ambient_coeff=tuple(r[0:3]), diffuse=tuple(r[3:6]), specular=tuple(r[6:9]), emission=tuple(r[9:12]),
+                     reflection=float(r[12]), roughness=float(r[13]), ns=float(r[14]), specular_threshold=float(r[15])) for r in z["materials"]]
+        if name.startswith("cfg2"):                        # 2048^2 u8 maps: AO, diffuse, normal (SURVEY.md 8(d) input 2)
+            tex = {0: scenes.noise_texture((2048, 2048), 2), 1: scenes.noise_texture((2048, 2048), 1, "rgb"), 2: scenes.normal_map_texture((2048, 2048), 4)}
+            kw.update(enable_ao_mapping=1, enable_diffuse_mapping=1, enable_normal_mapping=1)
+        if name.startswith("cfg3"):                        # 16-ray rough fan, depth 1, roughness map, 4096x2048 sky (input 3)
+            mats[0].update(reflection=0.9, roughness=0.0, specular=(0.2, 0.2, 0.2), diffuse=(0.5, 0.5, 0.5))
+            mats[1].update(reflection=0.5, roughness=0.4)
+            mats = precompute_materials(mats)
+            tex = {3: scenes.noise_texture((2048, 2048), 3), 4: scenes.sky_texture((2048, 4096))}
+            kw.update(rough_reflections_sample_count=16, max_recursion_depth=1, enable_roughness_mapping=1, enable_skysphere=1, rng_seed=7)
+    else:
+        if "hair" in name:
+            xyz9, uv6, mat = scenes.hair_ball(n_strands=tris // 64, segments=16)
+        else:
+            xyz9, uv6, mat = scenes.displaced_sphere(*scenes.sphere_grid_for(tris))
+        mats = precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
+    cam = np.eye(4, dtype=np.float32)
+    cam[2, 3] = CAMERA_Z.get(name, 0.0)
+    return dict(xyz9=xyz9, uv6=uv6, mat=mat, mats=mats, kw=kw, name=name, tex=tex, cam=cam)
 
 
 class ClockSampler:
@@ -112,7 +147,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def reference_sample(scene, row_step, threads=0, renderer=None, tracer=None):
+def reference_sample(scene, row_step, threads=None, renderer=None, tracer=None):
     """Times the compiled reference (oracle/_ref/libref.so, or the oracle port if that was never built) on every
     `row_step`-th row of the supersampled frame, driving the reference's public trace_ray per pixel exactly as its
     ray_trace() loop does.  Returns (renderer, rays, ms, kind, cores)."""
@@ -121,6 +156,9 @@ def reference_sample(scene, row_step, threads=0, renderer=None, tracer=None):
         kind = "reference" if bindings.available("ref") else "port"
         tracer = bindings.CpuTracer("ref" if kind == "reference" else "oracle")
     kind = "reference" if tracer.kind == "ref" else "port"
+    # every host core this process may run on, stated explicitly: a launcher's OMP_NUM_THREADS (torchrun exports 1 for
+    # every rank when nproc-per-node > 1) must not starve the CPU arm
+    threads = host_cpus() if not threads or threads <= 0 else threads
     if renderer is None:
         s = bindings.default_settings(**scene["kw"])
         renderer = tracer.renderer()
@@ -130,15 +168,35 @@ def reference_sample(scene, row_step, threads=0, renderer=None, tracer=None):
         log(f"[reference] BVH::BVH over {len(scene['xyz9'])} triangles: {time.time() - t0:.1f} s")
         renderer.set_materials(scene["mats"])
         renderer.set_light(LIGHT)
+        if not np.array_equal(scene["cam"], np.eye(4, dtype=np.float32)):
+            renderer.set_camera_transform(scene["cam"])
+        for slot, img in scene["tex"].items():
+            renderer.set_texture(slot, img)
     rw, rh = renderer._super_dims()
     _, ms = renderer.trace_rows(row_begin=row_step // 2, row_end=rh, row_step=row_step, reseed=False, threads=threads, want_image=False)
     rows = len(range(row_step // 2, rh, row_step))
-    if kind == "reference":
-        hits = renderer.last_hit_count()
+    if kind == "reference" and not scene["kw"].get("rough_reflections_sample_count"):
+        rays = rows * rw + renderer.last_hit_count()
     else:
-        hits = renderer.count_rows(row_begin=row_step // 2, row_end=rh, row_step=row_step)["shadow_rays"]
-    rays = rows * rw + hits
-    return renderer, tracer, rays, ms, kind, tracer.max_threads() if threads <= 0 else threads
+        # fan rays are not visible through the reference's public interface: counted (untimed) by the oracle port, whose
+        # ray tree is the reference's (tests/test_oracle_vs_reference.py)
+        counter = renderer if kind == "port" else scene.setdefault("_oracle_counter", _oracle_counter(scene))
+        c = counter.count_rows(row_begin=row_step // 2, row_end=rh, row_step=row_step)
+        rays = c["primary_rays"] + c["shadow_rays"] + c["reflection_rays"] + c["reflection_shadow_rays"]
+    return renderer, tracer, rays, ms, kind, threads
+
+
+def _oracle_counter(scene):
+    from oracle import bindings
+    r = bindings.CpuTracer("oracle").renderer()
+    r.configure(bindings.default_settings(**scene["kw"]), FOV)
+    r.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
+    r.set_materials(scene["mats"])
+    r.set_light(LIGHT)
+    r.set_camera_transform(scene["cam"])
+    for slot, img in scene["tex"].items():
+        r.set_texture(slot, img)
+    return r
 
 
 def run_reference(args, scene):
@@ -171,7 +229,8 @@ def run_reference(args, scene):
         "impl": "reference", "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(scene, args.gpus, args.tile),
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample,
+                         "build": REFERENCE_BUILD if kind == "reference" else "oracle/oracle.cpp (port)"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -188,6 +247,27 @@ def workload_config(scene, n_gpus, tile=64):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def setup_context(ctx, api, scene, args, leaf_split=None):
+    kw = scene["kw"]
+    if leaf_split is not None:
+        ctx.set_option(api.RT_OPT_LEAF_SPLIT, leaf_split)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(int(k), int(v))
+    info = ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
+    ctx.set_materials(scene["mats"])
+    ctx.set_light(LIGHT)
+    for slot, img in scene["tex"].items():
+        ctx.set_texture(slot, img)
+    f = kw["ssaa_factor"] if kw["enable_ssaa"] else 1
+    aspect = float(np.float32(kw["image_width"] * f) / np.float32(kw["image_height"] * f))
+    proj_inv = ctx.perspective_inverse(FOV, aspect)
+    cam = scene["cam"]
+    pos = ctx.transform_point(cam, (0, 0, 0))
+    ctx.set_camera(proj_inv, cam, pos)
+    return info, (proj_inv, cam, pos)
+
+
 def run_ours(args, scene):
     import torch
     import torch.distributed as dist
@@ -196,62 +276,47 @@ def run_ours(args, scene):
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = api.load_library(args.lib)
+    # host threads of the library's own loops (octree build, copy into the caller's frame): this rank's share of the
+    # box's cores, whatever OMP_NUM_THREADS the launcher exported (torchrun: 1)
+    host_threads = max(1, host_cpus() // max(local_world, 1))
+    lib.rt_set_host_threads(host_threads)
     ctx = api.Context(local, lib)
     kw = scene["kw"]
     s = api.default_settings(lib, **kw)
-    t0 = time.time()
-    if args.leaf_split is not None:
-        ctx.set_option(api.RT_OPT_LEAF_SPLIT, args.leaf_split)
-    for kv in args.opt:
-        k, v = kv.split("=")
-        ctx.set_option(int(k), int(v))
     ctx.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
+    lanes_on = not any(kv.split("=")[0] == str(api.RT_OPT_LANES) and int(kv.split("=")[1]) == 0 for kv in args.opt)
     ref_work = None
     if not args.no_ref_work:
         # Work of the REFERENCE-SHAPED traversal: the reference's own cells and leaves
         # (RT_OPT_LEAF_SPLIT 0), one ordered early-exit traversal per ray (RT_OPT_PACKETS 0), instrumented kernels.
         # Outside every timed region; the product tree is built afterwards.
-        ctx.set_option(api.RT_OPT_LEAF_SPLIT, 0)
-        ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
-        ctx.set_materials(scene["mats"])
-        ctx.set_light(LIGHT)
-        f0 = kw["ssaa_factor"]
-        ctx.set_camera(ctx.perspective_inverse(FOV, float(np.float32(kw["image_width"] * f0) / np.float32(kw["image_height"] * f0))),
-                       np.eye(4, dtype=np.float32), (0, 0, 0))
+        setup_context(ctx, api, scene, args, leaf_split=0)
         ctx.set_option(api.RT_OPT_PACKETS, 0)
         ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
-        ref_frame = ShardedFrame(ctx, s, rank, world, tile_size=args.tile)
+        ref_frame = ShardedFrame(ctx, s, rank, world, tile_size=args.tile, gather="nccl")
         ref_work = ref_frame.render().as_dict()
         del ref_frame
         ctx.set_option(api.RT_OPT_COUNT_WORK, 0)
         ctx.set_option(api.RT_OPT_PACKETS, 1)
-        ctx.set_option(api.RT_OPT_LEAF_SPLIT, args.leaf_split if args.leaf_split is not None else 8)
-        for kv in args.opt:
-            k, v = kv.split("=")
-            ctx.set_option(int(k), int(v))
         if rank == 0:
             log(f"[ours] reference-shaped traversal: {ref_work['primary_volume_tests']} + {ref_work['shadow_volume_tests']} volume tests, "
                 f"{ref_work['primary_triangle_tests']} + {ref_work['shadow_triangle_tests']} triangle tests (primary + shadow)")
-    info = ctx.build_bvh(kw["bvh_max_depth"], kw["bvh_leaf_object_count"])
+    info, (proj_inv, cam, pos) = setup_context(ctx, api, scene, args, leaf_split=args.leaf_split if args.leaf_split is not None else 8)
     if rank == 0:
-        log(f"[ours] octree build {info['build_ms']:.0f} ms + upload {info['upload_ms']:.0f} ms, {info['child_records']} records, "
-            f"{info['device_bytes'] / 1e6:.0f} MB resident, max leaf {info['max_leaf_size']}")
-    ctx.set_materials(scene["mats"])
-    ctx.set_light(LIGHT)
-    f = kw["ssaa_factor"]
-    aspect = float(np.float32(kw["image_width"] * f) / np.float32(kw["image_height"] * f))
-    proj_inv = ctx.perspective_inverse(FOV, aspect)
-    cam = np.eye(4, dtype=np.float32)
-    ctx.set_camera(proj_inv, cam, (0, 0, 0))
+        log(f"[ours] octree build {info['build_ms']:.0f} ms ({host_threads} host threads) + upload {info['upload_ms']:.0f} ms, "
+            f"{info['child_records']} records, {info['device_bytes'] / 1e6:.0f} MB resident, max leaf {info['max_leaf_size']}")
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    frame = ShardedFrame(ctx, s, rank, world, tile_size=args.tile)
+    frame = ShardedFrame(ctx, s, rank, world, tile_size=args.tile, gather=args.gather)
+    if rank == 0 and world > 1:
+        log(f"[ours] frame gather mode: {frame.mode}" + (f" (peer refused: {frame.why_not_peer})" if frame.why_not_peer else ""))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -274,15 +339,15 @@ def run_ours(args, scene):
         stage = {"k_primary": 0.0, "k_compact": 0.0, "k_shade": 0.0, "k_reflect": 0.0, "k_resolve": 0.0}
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
-        rays_rank = 0
+        st = None
         ev0.record(stream)
         for _ in range(args.steps):
             st = frame.render_and_gather()
-            launches += st.kernel_launches + (2 if world > 1 else 0)           # + the pack and unpack kernels of the gather
-            rays_rank = st.total_rays
+            launches += st.kernel_launches + (2 if frame.mode == "nccl" else 0)   # + the pack and unpack kernels of the nccl-mode gather
         ev1.record(stream)
         sync_all()
         dev_ms = ev0.elapsed_time(ev1)
+        rays_rank, traced_rank = st.total_rays, st.traced_rays
         # Per-kernel durations for the roofline: the SAME K frames once more, still inside the clock sampling, with the two
         # chunk lanes turned off (RT_OPT_LANES 0) -- with two lanes the kernels of the two chunks overlap on purpose and a
         # CUDA-event pair around one of them also measures the time it waits for SMs.
@@ -297,40 +362,46 @@ def run_ours(args, scene):
         serial1.record(stream)
         sync_all()
         serial_ms = serial0.elapsed_time(serial1) / args.steps
-        ctx.set_option(api.RT_OPT_LANES, 0 if "9=0" in args.opt else 1)
+        ctx.set_option(api.RT_OPT_LANES, 1 if lanes_on else 0)
         clocks = sampler.stop()
 
-        # --- end to end: host framebuffer, copies inside the timed region
-        host = torch.empty((kw["image_height"], kw["image_width"]), dtype=torch.int32).pin_memory()
-        for _ in range(min(args.warmup, 2)):
-            frame.render_and_gather()
-            if rank == 0:
-                host.copy_(frame.frame, non_blocking=True)
-            stream.synchronize()
+        # --- end to end through the public call: the frame ends up in an ordinary (pageable) host array of the caller.
+        # N = 1: rt_render(ctx, settings, argb_out).  N > 1: the sharded counterpart (ShardedFrame.render_to_host: every rank
+        # renders its tiles into rank 0's frame, rank 0 copies it out with rt_frame_to_host).  Inputs of a step: camera and
+        # settings (host structs -> kernel arguments); result: the ARGB32 frame.  All copies are inside the timed region.
+        host = np.empty((kw["image_height"], kw["image_width"]), np.uint32)
+        host.fill(0)                                                             # touch the pages once, as a GUI's frame buffer would be
+
+        def e2e_step():
+            ctx.set_camera(proj_inv, cam, pos)
+            if world == 1:
+                ctx.render(s, host)
+            else:
+                frame.render_to_host(host)
+
+        for _ in range(min(args.warmup, 3)):
+            e2e_step()
         sync_all()
         t_e2e = time.perf_counter()
         for _ in range(args.steps):
-            ctx.set_camera(proj_inv, cam, (0, 0, 0))                             # the step's inputs: camera + settings (kernel arguments)
-            frame.ctx.render_device_begin(s, frame.frame.data_ptr(), frame.tile, world, rank)
-            frame.gather()
-            if rank == 0:                                                        # the caller's host framebuffer lives with rank 0
-                host.copy_(frame.frame, non_blocking=True)
-            frame.ctx.render_device_end()                                        # waits for the stream: frame, gather and copy
+            e2e_step()
+        stream.synchronize()
         e2e_ms = (time.perf_counter() - t_e2e) * 1e3
 
-    # --- the gathered frame of the sharded run must be the 1-GPU frame (rank 0 renders every tile once more, untimed)
+    # --- the frame of the sharded run must be the 1-GPU frame, on the device and in the caller's host array
+    # (rank 0 renders every tile once more, untimed)
     frame_check = None
     if world > 1:
         with torch.cuda.stream(stream):
             frame.render_and_gather()
             stream.synchronize()
-            gathered = frame.frame.clone()
             if rank == 0:
+                gathered = frame.frame.clone()
                 whole = ShardedFrame(ctx, s, 0, 1, tile_size=args.tile)
                 whole.render()
                 stream.synchronize()
-                same = bool(torch.equal(whole.frame, gathered))
-                frame_check = "identical to the 1-GPU frame" if same else "DIFFERS from the 1-GPU frame"
+                same = bool(torch.equal(whole.frame, gathered)) and bool(np.array_equal(host, whole.frame.cpu().numpy().view(np.uint32)))
+                frame_check = "identical to the 1-GPU frame (device frame and host array)" if same else "DIFFERS from the 1-GPU frame"
                 if not same:
                     raise SystemExit("bench.py: the gathered frame differs from the 1-GPU frame")
 
@@ -351,6 +422,8 @@ def run_ours(args, scene):
     dev_ms = reduce(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
     e2e_ms = reduce(e2e_ms, dist.ReduceOp.MAX if world > 1 else None)
     rays_total = reduce(float(rays_rank), dist.ReduceOp.SUM if world > 1 else None)
+    traced_total = reduce(float(traced_rank), dist.ReduceOp.SUM if world > 1 else None)
+    launches_total = reduce(float(launches), dist.ReduceOp.SUM if world > 1 else None)
     ms_step = dev_ms / args.steps
     value = rays_total / ms_step / 1e3
 
@@ -360,56 +433,82 @@ def run_ours(args, scene):
         if peaks_file.exists():
             peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
         dom = max(("k_primary", "k_shade", "k_reflect"), key=lambda k: stage[k])
-        keys = {"k_primary": ("primary_volume_tests", "primary_triangle_tests"), "k_shade": ("shadow_volume_tests", "shadow_triangle_tests"),
-                "k_reflect": ("reflection_volume_tests", "reflection_triangle_tests")}[dom]
         own = work.as_dict()
-        src = ref_work if ref_work is not None else own
-        dom_bytes = 56 * src[keys[0]] + 36 * src[keys[1]]                         # per launch set (one per step)
-        own_bytes = 56 * own[keys[0]] + 36 * own[keys[1]]
+        pre = {"k_primary": "primary", "k_shade": "shadow", "k_reflect": "reflection"}[dom]
+        fetched = own[pre + "_fetched_bytes"]                                     # rank 0's tiles, one launch set (= one step)
         dom_ms = stage[dom] / args.steps
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        traffic = None
-        tf = ROOT / "profiles" / "traffic.json"                                   # dram bytes per launch from the committed ncu --set full capture
-        if tf.exists():
-            traffic = json.loads(tf.read_text()).get(scene["name"], {}).get(dom)
+        achieved = fetched / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        ref_bytes = None if ref_work is None else 56 * ref_work[pre + "_volume_tests"] + 36 * ref_work[pre + "_triangle_tests"]
+        # ncu figures of the SAME kernel set, from the committed capture of this workload at N = 1 (scripts/make_profiles.py
+        # writes profiles/traffic.json from the .ncu-rep; it names the commit it was taken at).  At N > 1 the launch covers
+        # another set of tiles, so nothing is quoted there.
+        prof = {}
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists() and world == 1:
+            prof = json.loads(tf.read_text()).get(scene["name"], {}).get(dom, {})
+            if not isinstance(prof, dict):
+                prof = {}
+        traffic = prof.get("dram_bytes")
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        issue_peak = n_sm * 4 * sm_mhz * 1e6                                      # warp instructions per second: 4 schedulers per SM, 1 per clock
+        warp_inst = prof.get("warp_inst")
+        issue = None
+        if warp_inst and dom_ms > 0:
+            issue = {"bound": "issue", "kernel": dom, "achieved": warp_inst / (dom_ms * 1e-3) / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                     "frac": warp_inst / (dom_ms * 1e-3) / issue_peak, "warp_inst_per_launch": warp_inst,
+                     "warp_inst_per_traced_ray": warp_inst / max(1, {"k_primary": st.traced_primary_rays, "k_shade": st.shadow_rays,
+                                                                   "k_reflect": st.reflection_rays + st.reflection_shadow_rays}[dom]),
+                     "source": prof.get("source"), "peak_definition": f"{n_sm} SMs x 4 schedulers x {sm_mhz:.0f} MHz (median SM clock of the timed region)"}
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic,
-                    "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_step": dom_ms,
-                    "definition": ("56 B per 7-slab volume test + 36 B per triangle test of the REFERENCE-SHAPED traversal of the kernel's rays (rank 0's tiles): "
-                                   "the reference's own octree cells and leaves, one ordered early-exit traversal per ray, counted on the GPU by the "
-                                   "instrumented single-ray kernels (SURVEY.md 8(d))") if ref_work is not None else
-                                  "56 B per volume test + 36 B per triangle test performed by the kernel's own traversal (rank 0's tiles)",
-                    "kernel_traversal_bytes_per_launch": own_bytes,
+                    "algorithmic_bytes_per_launch": fetched, "kernel_ms_per_step": dom_ms,
+                    "definition": ("node + triangle bytes the kernel FETCHES per launch: 64 B per child record and 48 B per triangle, once per warp "
+                                   "and test (a 32-ray packet shares each fetch), counted by the instrumented instantiation of the same kernels "
+                                   "(RT_OPT_COUNT_WORK) outside the timed region; divided by the kernel's CUDA-event time in the timed run. "
+                                   "`traffic` = DRAM bytes of the same launch set under ncu (the rest is served by the 126 MB L2). "
+                                   "The kernel is ISSUE-bound, not HBM-bound: see roofline_issue"),
                     "dram_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if (traffic and dom_ms > 0) else None,
-                    "note": ("frac > 1 is real: the device tree refines the reference's leaves (7.7x fewer triangle tests) and 32 rays share each "
-                             "fetch, so the kernel ends sooner than the reference-shaped traversal could stream its bytes from HBM; physical DRAM "
-                             "traffic (`traffic`, ncu) is ~0.2 % of the algorithmic bytes (L2 hit rate 86 %) and the kernel is issue-bound "
-                             "(79 % issue-active, ALU pipe 68 %), see DESIGN.md section 5"),
+                    "reference_shaped_bytes": ref_bytes,
+                    "reference_shaped_definition": "SURVEY.md 8(d): 56 B per volume test + 36 B per triangle test of one ordered early-exit traversal per "
+                                                   "ray over the reference's own cells and leaves; a property of the reference algorithm, not bytes this kernel moves",
                     "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
                     "stage_timing": "K more frames with RT_OPT_LANES 0 (the chunks' kernels back to back on one stream; with the two lanes of "
                                     "the timed run they overlap on purpose), %.3f ms per frame that way" % serial_ms}
+        cfg = workload_config(scene, world, args.tile)
+        cfg["gather"] = {"peer": "every rank's resolve kernel stores its tiles into rank 0's frame over NVLink (CUDA IPC), one 4-byte all-reduce per frame as the barrier",
+                         "nccl": "pack kernel -> all_gather_into_tensor -> unpack kernel", "single": "none (one GPU)"}[frame.mode]
         out = {
             "metric": "Mrays/s (primary+shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(scene, world, args.tile), "rays_per_step": int(rays_total), "clocks": clocks,
+            "config": cfg, "rays_per_step": int(rays_total), "traced_rays_per_step": int(traced_total),
+            "traced_mrays_s": traced_total / ms_step / 1e3,
+            "rays_note": ("`value` counts every sample of the frame plus the shadow (and fan) rays, as the reference arm does for the same frame; "
+                          "`traced_*` leaves out the primary samples that the screen-space bound of the scene writes as misses without a ray"),
+            "clocks": clocks,
             "e2e": {"value": rays_total / (e2e_ms / args.steps) / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": 2 * 64 + 12 + 12 + 100, "d2h_bytes_per_step": int(host.numel() * 4)},
-            "gpu_launches": int(launches), "roofline": roofline,
-            "work": {k: getattr(work, k) for k in ("primary_volume_tests", "primary_triangle_tests", "shadow_volume_tests", "shadow_triangle_tests",
-                                                   "primary_hits")},
+                    "h2d_bytes_per_step": 2 * 64 + 12 + 12 + 108, "d2h_bytes_per_step": int(host.size * 4),
+                    "call": "rt_render into a pageable host array" if world == 1 else
+                            "ShardedFrame.render_to_host: rt_render_device_begin on every rank (stores into rank 0's frame), barrier, rt_frame_to_host into a pageable host array on rank 0"},
+            "gpu_launches": int(launches_total), "roofline": roofline, "roofline_issue": issue,
+            "work": {k: own[k] for k in ("primary_volume_tests", "primary_triangle_tests", "shadow_volume_tests", "shadow_triangle_tests",
+                                         "primary_hits", "primary_fetched_bytes", "shadow_fetched_bytes", "reflection_fetched_bytes")},
             "reference_work": None if ref_work is None else {k: ref_work[k] for k in ("primary_volume_tests", "primary_triangle_tests",
                                                                                       "shadow_volume_tests", "shadow_triangle_tests")},
             "per_rank_stage_ms": per_rank, "frame_check": frame_check,
-            "bvh": {k: info[k] for k in ("nodes", "interior", "leaves", "empty_leaves", "max_leaf_size", "child_records", "device_bytes", "build_ms", "upload_ms")},
+            "bvh": dict({k: info[k] for k in ("nodes", "interior", "leaves", "empty_leaves", "max_leaf_size", "child_records", "device_bytes", "build_ms", "upload_ms")},
+                        host_threads=host_threads),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
                 _, _, rays, ms, kind, cores = reference_sample(scene, row_step=args.cpu_row_step)
                 out["cpu_baseline"] = {"value": rays / ms / 1e3, "unit": "Mrays/s", "cores": cores, "kind": kind,
+                                       "build": REFERENCE_BUILD if kind == "reference" else "oracle/oracle.cpp (port)",
                                        "sample": f"every {args.cpu_row_step}th row of the supersampled frame, {rays} rays in {ms / 1e3:.1f} s"}
             except Exception as e:  # the checker is optional for the GPU number, never the other way round
                 out["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         emit(out)
+    frame.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -428,6 +527,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option override id=value (experiments), e.g. --opt 3=4")
     ap.add_argument("--tile", type=int, default=None, help="side of the screen tiles dealt over the ranks (final-resolution pixels); "
                     "default 64 on one GPU, 32 on several (finer interleaving balances the ranks better, measured at N=8)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how the frame gets to rank 0 (raytracercpp_b200/distributed.py)")
     ap.add_argument("--lib", default=None, help="another build of librtb200 (kernel A/B experiments)")
     ap.add_argument("--leaf-split", type=int, default=None, help="RT_OPT_LEAF_SPLIT override (experiments); default = library default")
     args = ap.parse_args()

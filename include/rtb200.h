@@ -132,6 +132,13 @@ typedef struct RtRenderStats {
     uint64_t primary_volume_tests, primary_triangle_tests;
     uint64_t shadow_volume_tests, shadow_triangle_tests;
     uint64_t reflection_volume_tests, reflection_triangle_tests;
+    /* Primary rays that were really traced: `primary_rays` counts every sample of the frame, also those of tiles and
+     * packets outside the screen-space bound of the scene, which are written as misses without a ray (RT_OPT_SCREEN_CULL).
+     * Always filled. */
+    uint64_t traced_primary_rays;
+    /* RT_OPT_COUNT_WORK only: bytes of child records (64 each) and triangles (48 each) the kernels fetched for the tests
+     * above.  A 32-ray packet fetches a record once per warp and tests it in every lane; a single ray fetches per test. */
+    uint64_t primary_fetched_bytes, shadow_fetched_bytes, reflection_fetched_bytes;
 } RtRenderStats;
 
 /* Flattened-tree facts, for tests and DESIGN.md (the reference tree has the same node/leaf counts). */
@@ -178,15 +185,20 @@ enum {
     RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -64; 0 is invalid)                 */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
-    RT_OPT_LANES = 9,         /* 1 (default): two wavefront chunks are in flight at a time on two streams, so one chunk's
-                                 kernels fill the SMs the other's leave idle while their longest packets finish; the
-                                 per-stage times of RtRenderStats then overlap.  Results do not depend on it           */
+    RT_OPT_LANES = 9,         /* wavefront chunks in flight at a time, each on its own stream with its own queues, so one
+                                 chunk's kernels fill the SMs the others leave idle while their longest packets finish; the
+                                 per-stage times of RtRenderStats then overlap.  0: one chunk at a time; 1 (default): 2 chunks;
+                                 n in [2,6]: n chunks.  Results do not depend on it                                     */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.
                                  Results do not depend on it (tests/test_gpu_parity.py)                               */
 };
 int rt_set_option(RtContext* ctx, int option, int64_t value);
+/* Threads the library's host-side loops may use (octree build, the copy into the caller's frame buffer): OpenMP's
+ * omp_set_num_threads for this process.  A launcher that exports OMP_NUM_THREADS=1 for every rank (torchrun does) would
+ * otherwise serialise rt_build_bvh.  n <= 0: all the cores this process may run on. */
+int rt_set_host_threads(int n);
 /* Run all of the context's work on the caller's CUDA stream (a cudaStream_t; NULL = back to the context's own
  * non-blocking stream), so a host that already orders work on a stream -- or times it with events -- can do so. */
 int rt_set_stream(RtContext* ctx, void* cuda_stream);
@@ -261,6 +273,25 @@ int rt_render_device(RtContext* ctx, const RtSettings* settings, uint32_t* d_arg
 int rt_render_device_begin(RtContext* ctx, const RtSettings* settings, uint32_t* d_argb_out,
                            int tile_size, int tile_mod, int tile_rem);
 int rt_render_device_end(RtContext* ctx, RtRenderStats* stats);
+
+/* ---- Frame buffers shared between the ranks of one box (one process per GPU) -------------------------------------------
+ * The gather of the sharded frame is fused into the kernels that produce the pixels: rank 0 allocates the frame with
+ * rt_frame_alloc and hands the 64-byte handle to its peers (any byte transport: the Python side uses torch.distributed);
+ * a peer maps it with rt_frame_open and passes the mapped pointer as `d_argb_out` of rt_render_device_begin -- its resolve
+ * (or shading) kernel then stores the final pixels of its tiles straight into rank 0's memory over NVLink.  No pack, no
+ * collective, no unpack; the only cross-rank step left is one barrier per frame, which the host enqueues.
+ * (CUDA IPC: cudaIpcGetMemHandle / cudaIpcOpenMemHandle with peer access.)  rt_frame_close unmaps, rt_frame_free frees. */
+#define RT_FRAME_HANDLE_BYTES 64
+int rt_frame_alloc(RtContext* ctx, size_t bytes, void** d_ptr_out, unsigned char handle_out[RT_FRAME_HANDLE_BYTES]);
+int rt_frame_open(RtContext* ctx, const unsigned char handle[RT_FRAME_HANDLE_BYTES], void** d_ptr_out);
+int rt_frame_close(RtContext* ctx, void* d_ptr);
+int rt_frame_free(RtContext* ctx, void* d_ptr);
+
+/* The last step of rt_render for a frame that already is (or is about to be, in stream order) in device memory: copies
+ * n_pixels ARGB32 words from d_frame to the caller's ordinary (pageable) host buffer, behind everything enqueued on the
+ * context's stream so far, and returns when host_out is complete.  The copy runs in slices through a pinned staging
+ * buffer; while one slice crosses PCIe the previous one is moved into host_out by the host threads. */
+int rt_frame_to_host(RtContext* ctx, const uint32_t* d_frame, uint32_t* host_out, size_t n_pixels);
 
 /* Pack / unpack the tiles owned by (tile_mod, tile_rem) between the row-major frame and a tile-major
  * staging buffer -- the operand of the framebuffer all-gather.  rt_tile_count gives how many tiles the

@@ -63,7 +63,9 @@ class RtRenderStats(C.Structure):
                 ("reflect_ms", C.c_float), ("compact_ms", C.c_float), ("resolve_ms", C.c_float),
                 ("primary_volume_tests", C.c_uint64), ("primary_triangle_tests", C.c_uint64),
                 ("shadow_volume_tests", C.c_uint64), ("shadow_triangle_tests", C.c_uint64),
-                ("reflection_volume_tests", C.c_uint64), ("reflection_triangle_tests", C.c_uint64)]
+                ("reflection_volume_tests", C.c_uint64), ("reflection_triangle_tests", C.c_uint64),
+                ("traced_primary_rays", C.c_uint64), ("primary_fetched_bytes", C.c_uint64), ("shadow_fetched_bytes", C.c_uint64),
+                ("reflection_fetched_bytes", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -71,6 +73,11 @@ class RtRenderStats(C.Structure):
     @property
     def total_rays(self) -> int:
         return self.primary_rays + self.shadow_rays + self.reflection_rays + self.reflection_shadow_rays
+
+    @property
+    def traced_rays(self) -> int:
+        """Rays that were really traced: `total_rays` minus the samples written as misses without a ray (screen cull)."""
+        return self.traced_primary_rays + self.shadow_rays + self.reflection_rays + self.reflection_shadow_rays
 
     @property
     def work_bytes(self) -> int:
@@ -101,6 +108,12 @@ ABI = {
     "rt_last_error": (C.c_char_p, [C.c_void_p]),
     "rt_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "rt_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_set_host_threads": (C.c_int, [C.c_int]),
+    "rt_frame_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "rt_frame_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "rt_frame_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_frame_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rt_frame_to_host": (C.c_int, [C.c_void_p, C.c_void_p, UP, C.c_size_t]),
     "rt_set_triangles": (C.c_int, [C.c_void_p, FP, FP, IP, C.c_size_t]),
     "rt_build_bvh": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "rt_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(RtBvhInfo)]),
@@ -330,6 +343,30 @@ class Context:
 
     def unpack_tiles(self, settings, d_frame: int, d_staging: int, tile_size, tile_mod, tile_rem):
         self._check(self.lib.rt_unpack_tiles(self.h, C.byref(settings), C.c_void_p(d_frame), C.c_void_p(d_staging), tile_size, tile_mod, tile_rem))
+
+    # ---- frames shared between the ranks of a box (rt_frame_*: CUDA IPC) ---------------------------------
+    def frame_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte handle) of a frame other ranks can map with frame_open."""
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._check(self.lib.rt_frame_alloc(self.h, nbytes, C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def frame_open(self, handle: bytes) -> int:
+        ptr, buf = C.c_void_p(), (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.rt_frame_open(self.h, buf, C.byref(ptr)))
+        return ptr.value
+
+    def frame_close(self, d_ptr: int):
+        self._check(self.lib.rt_frame_close(self.h, C.c_void_p(d_ptr)))
+
+    def frame_free(self, d_ptr: int):
+        self._check(self.lib.rt_frame_free(self.h, C.c_void_p(d_ptr)))
+
+    def frame_to_host(self, d_ptr: int, out: np.ndarray):
+        """Device frame -> the (pageable) host array `out`, behind everything enqueued on the context's stream."""
+        assert out.dtype == np.uint32 and out.flags.c_contiguous
+        self._check(self.lib.rt_frame_to_host(self.h, C.c_void_p(d_ptr), _p(out, C.c_uint32), out.size))
+        return out
 
     # ---- batch queries ----------------------------------------------------------------------------------
     def intersect(self, o3, d3):

@@ -51,6 +51,8 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
     unsigned long long primary_vol, primary_tri, shadow_vol, shadow_tri, refl_vol, refl_tri;
+    unsigned long long primary_fetch, shadow_fetch, refl_fetch;   // bytes fetched for those tests: 64 per child record, 48 per triangle
+    unsigned long long traced_primary;                            // primary rays that really were traced (always maintained)
     // COUNT instantiations of the packet kernels only: cell/leaf rounds per packet, [0] primary, [1] shadow
     unsigned int rounds_hist[2][16]; // bucket b: packets with 2^b <= rounds < 2^(b+1) (bucket 0 also holds 0 rounds)
     unsigned int max_rounds[2];
@@ -74,18 +76,20 @@ RT_DEV void note_packet(ChunkCounters* cnt, int which, unsigned rounds, unsigned
     atomicAdd(&cnt->sum_packet_ns[which], ns);
 }
 
-RT_DEV void flush_work(TraceCounters& tc, unsigned long long* vol, unsigned long long* tri)
+RT_DEV void flush_work(TraceCounters& tc, unsigned long long* vol, unsigned long long* tri, unsigned long long* fetch)
 {
-    // warp-aggregated: one atomic pair per warp
-    unsigned long long v = tc.vol_tests, t = tc.tri_tests;
+    // warp-aggregated: one atomic triple per warp
+    unsigned long long v = tc.vol_tests, t = tc.tri_tests, f = 64ull * tc.rec_fetch + 48ull * tc.tri_fetch;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         v += __shfl_xor_sync(0xffffffffu, v, o);
         t += __shfl_xor_sync(0xffffffffu, t, o);
+        f += __shfl_xor_sync(0xffffffffu, f, o);
     }
     if ((threadIdx.x & 31u) == 0) {
         if (v) atomicAdd(vol, v);
         if (t) atomicAdd(tri, t);
+        if (f) atomicAdd(fetch, f);
     }
 }
 
@@ -186,7 +190,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
     S.mode = RT_MODE_DONE;
     bool alive = false, exhausted = false;
     int px = 0, py = 0;
-    uint32_t slot = 0;
+    uint32_t slot = 0, traced = 0;
     V3 dir = v3(0, 0, 0);
     for (;;) {
         // ---- refill the idle lanes
@@ -206,6 +210,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
                     primary_ray(fr, px, py, o, dir);
                     closest_begin<COUNT>(sc, o, dir, S, &tc);
                     alive = true;
+                    ++traced;
                 } else
                     q.slot_tri[slot] = -1;
             }
@@ -231,7 +236,9 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
         }
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
+    traced = __reduce_add_sync(0xffffffffu, traced);
+    if (lane == 0 && traced) atomicAdd(&cnt->traced_primary, (unsigned long long)traced);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri, &cnt->primary_fetch);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -314,6 +321,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
         const rt_f4* r = sc.recs;
         rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
         if (COUNT && active) tc.vol_tests++;
+        if (COUNT && lane == 0) tc.rec_fetch++;
         const float tn = active ? slab_entry(q0, q1, q2, q3, sr, t_max) : INFINITY;
         link = f4_bits(q3.z); meta = f4_bits(q3.w);
         if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return true;
@@ -332,6 +340,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
             // child record (broadcast LDS) for its own ray
             const int base = sp;
             if (lane < 4u * meta) K.stage[lane] = RT_LDG4(sc.recs + 4 * (size_t)link + lane);
+            if (COUNT && lane == 0) tc.rec_fetch += meta;
             __syncwarp();
             for (uint32_t k = 0; k < meta; k++) {
                 const float4 c0 = K.stage[4 * k], c1 = K.stage[4 * k + 1], c2 = K.stage[4 * k + 2], c3 = K.stage[4 * k + 3];
@@ -357,6 +366,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
             for (uint32_t first = 0; first < cnt; first += 10u) {
                 const uint32_t m = min(10u, cnt - first);
                 if (lane < 3u * m) K.stage[lane] = RT_LDG4(sc.tris + 3 * (size_t)(link + first) + lane);
+                if (COUNT && lane == 0) tc.tri_fetch += m;
                 __syncwarp();
                 for (uint32_t i = 0; i < m; i++) {
                     const float4 p0 = K.stage[3 * i], p1 = K.stage[3 * i + 1], p2 = K.stage[3 * i + 2];
@@ -435,6 +445,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
     const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);
     TraceCounters tc = zero_counters();
     unsigned overflow = 0;
+    uint32_t traced = 0;                                                        // lane 0: rays of the packets this warp traced
     // Work fetch: kPrimaryFetch packets per atomic, and the atomic for the NEXT batch is issued before the current
     // batch is traced, so its round trip (11 % of the stall samples when it was waited for) is hidden.
     uint32_t nxt = 0;
@@ -464,6 +475,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
                 continue;
             }
             if (active) primary_ray(fr, px, py, o, d);
+            traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, active));
             HitRec best;
             bool occ, live = active;
             unsigned rounds = 0;
@@ -499,7 +511,8 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
         }
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
+    if (lane == 0 && traced) atomicAdd(&cnt->traced_primary, (unsigned long long)traced);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri, &cnt->primary_fetch);
 }
 
 // Item pass of the split primary packets: a warp takes one unvisited cell of a split packet, rebuilds the packet's 32
@@ -553,7 +566,7 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
         }
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri, &cnt->primary_fetch);
 }
 
 // After the item passes: the slot records (or miss colours) of the split primary packets.  The merged key names the
@@ -800,7 +813,10 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
                 const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
                 fan.refl_rays += (uint32_t)packed;
                 fan.refl_shadow_rays += (uint32_t)(packed >> 32);
-                if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
+                if (COUNT) {                                   // fan rays are single rays: one fetch per test
+                    fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2];
+                    fan.rec_fetch += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_fetch += q.refl_cnt[3 * (size_t)entry + 2];
+                }
             }
             bool occluded = S.occluded;
             if (sc.n_shapes > 0 && fr.s.compute_shadows && !occluded) occluded = shapes_occlude_ray(sc, S.o, -S.md, S.p, S.dist2);
@@ -808,13 +824,13 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
         }
     }
     if (tc.stack_overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri, &cnt->shadow_fetch);
     const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
     if ((threadIdx.x & 31u) == 0) {
         if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
         if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
     }
-    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
+    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri, &cnt->refl_fetch);
 }
 
 // What a lane of the shading kernels knows about its hit-queue entry before the shadow ray is traced.
@@ -857,7 +873,10 @@ RT_DEV void shade_store(const SceneView& sc, const FrameView& fr, const QueueVie
         const unsigned long long packed = q.refl_cnt[3 * (size_t)entry];
         fan.refl_rays += (uint32_t)packed;
         fan.refl_shadow_rays += (uint32_t)(packed >> 32);
-        if (COUNT) { fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2]; }
+        if (COUNT) {                                   // fan rays are single rays: one fetch per test
+                    fan.vol_tests += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_tests += q.refl_cnt[3 * (size_t)entry + 2];
+                    fan.rec_fetch += q.refl_cnt[3 * (size_t)entry + 1]; fan.tri_fetch += q.refl_cnt[3 * (size_t)entry + 2];
+                }
     }
     super[L.pix] = quantise_argb(shade_compose(fr, m, L.direct, occluded, refl));
 }
@@ -866,13 +885,13 @@ template <bool COUNT>
 RT_DEV void shade_epilogue(ChunkCounters* cnt, TraceCounters& tc, TraceCounters& fan, unsigned overflow)
 {
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri, &cnt->shadow_fetch);
     const unsigned rr = __reduce_add_sync(0xffffffffu, fan.refl_rays), rs = __reduce_add_sync(0xffffffffu, fan.refl_shadow_rays);
     if ((threadIdx.x & 31u) == 0) {
         if (rr) atomicAdd(&cnt->refl_rays, (unsigned long long)rr);
         if (rs) atomicAdd(&cnt->refl_shadow_rays, (unsigned long long)rs);
     }
-    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri);
+    if (COUNT) flush_work(fan, &cnt->refl_vol, &cnt->refl_tri, &cnt->refl_fetch);
 }
 
 // Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
@@ -987,7 +1006,7 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         if (om != 0u && lane == 0) atomicOr(&q.split_occ[sidx], om);
     }
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
-    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri);
+    if (COUNT) flush_work(tc, &cnt->shadow_vol, &cnt->shadow_tri, &cnt->shadow_fetch);
 }
 
 // After the item passes: composes and stores the pixels of the split packets' unanswered lanes with the merged answers.
@@ -1052,16 +1071,22 @@ __global__ void k_fill_miss(SceneView sc, FrameView fr, WorkView wk, uint32_t* s
 
 // ImageUtils::downscale_image_qt_ARGB32 -- imageUtils.h:98-147: per channel, sum of the factor^2 quantised samples
 // divided (integer, truncating) by factor^2.  One thread per final pixel of the owned tiles.
-__global__ void k_resolve(const uint32_t* super, uint32_t* out, WorkView wk, int tile_size, int factor, int width, int height)
+// Tiles at list positions >= n_box were not traced (they lie outside the screen-space bound of the scene) and their miss
+// colour does not depend on the ray: every one of their samples would be `fill`, whose box filter is `fill` again, so
+// the final pixel is written directly and the samples never exist (no 0.5 GB constant round trip through HBM).
+__global__ void k_resolve(const uint32_t* super, uint32_t* out, WorkView wk, int tile_size, int factor, int width, int height, uint32_t n_box,
+                          uint32_t fill)
 {
     const uint32_t per_tile = (uint32_t)tile_size * (uint32_t)tile_size;
     const uint64_t total = (uint64_t)(wk.tile_end - wk.tile_begin) * per_tile;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t tile = wk.tiles[wk.tile_begin + (uint32_t)(g / per_tile)];
+        const uint32_t tpos = wk.tile_begin + (uint32_t)(g / per_tile);
+        const uint32_t tile = wk.tiles[tpos];
         const uint32_t in = (uint32_t)(g % per_tile);
         const int x = (int)(tile % (uint32_t)wk.tiles_x) * tile_size + (int)(in % (uint32_t)tile_size);
         const int y = (int)(tile / (uint32_t)wk.tiles_x) * tile_size + (int)(in / (uint32_t)tile_size);
         if (x >= width || y >= height) continue;
+        if (tpos >= n_box) { out[(size_t)y * width + x] = fill; continue; }
         const int rw = width * factor;
         int ar = 0, ag = 0, ab = 0;
         for (int i = 0; i < factor; i++) {

@@ -94,12 +94,15 @@ struct TraceCounters {      // per-thread tallies, reduced by the kernels
     // work actually done by the traversal (only maintained by the COUNT instantiations): 7-slab volume tests and
     // ray/triangle tests, the V and T of the bytes-per-ray metric (56 V + 36 T)
     unsigned long long vol_tests, tri_tests;
+    // what the kernel FETCHED for those tests (COUNT only): 64-byte child records and 48-byte triangles.  A single ray
+    // fetches one per test; a 32-ray packet fetches one per warp and tests it in every lane (counted by lane 0).
+    unsigned long long rec_fetch, tri_fetch;
 };
 
 RT_DEV TraceCounters zero_counters()
 {
     TraceCounters tc;
-    tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0; tc.vol_tests = 0; tc.tri_tests = 0;
+    tc.refl_rays = 0; tc.refl_shadow_rays = 0; tc.stack_overflow = 0; tc.vol_tests = 0; tc.tri_tests = 0; tc.rec_fetch = 0; tc.tri_fetch = 0;
     return tc;
 }
 
@@ -270,7 +273,7 @@ RT_DEV void ray_begin(const SceneView& sc, V3 o, V3 d, float t_max, RayState& S,
     S.mode = RT_MODE_DONE;
     const rt_f4* r = sc.recs;
     rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
-    if (COUNT) tc->vol_tests++;
+    if (COUNT) { tc->vol_tests++; tc->rec_fetch++; }
     const uint32_t meta = f4_bits(q3.w);
     if (slab_entry(q0, q1, q2, q3, S.sr, S.t_max) != INFINITY && (meta & ~RT_LEAF_BIT) != 0u) ray_enter(S, f4_bits(q3.z), meta);
 }
@@ -297,7 +300,7 @@ RT_DEV void ray_child_step(const SceneView& sc, RayState& S, RayStack& K, TraceC
 {
     const rt_f4* r = sc.recs + 4 * (size_t)S.next;
     rt_f4 c0 = RT_LDG4(r), c1 = RT_LDG4(r + 1), c2 = RT_LDG4(r + 2), c3 = RT_LDG4(r + 3);
-    if (COUNT) tc->vol_tests++;
+    if (COUNT) { tc->vol_tests++; tc->rec_fetch++; }
     const float tn = slab_entry(c0, c1, c2, c3, S.sr, S.t_max);
     if (tn != INFINITY) {
         if (S.sp >= RT_STACK_SIZE) { tc->stack_overflow = 1; S.mode = RT_MODE_DONE; return; }
@@ -322,7 +325,7 @@ RT_DEV void ray_triangle_step(const SceneView& sc, RayState& S, const RayStack& 
 {
     const rt_f4* tp = sc.tris + 3 * (size_t)S.next;
     rt_f4 p0 = RT_LDG4(tp), p1 = RT_LDG4(tp + 1), p2 = RT_LDG4(tp + 2);
-    if (COUNT) tc->tri_tests++;
+    if (COUNT) { tc->tri_tests++; tc->tri_fetch++; }
     float t, u, v;
     if (tri_test(p0, p1, p2, S.o, S.md, t, u, v)) {
         if (ANY) {

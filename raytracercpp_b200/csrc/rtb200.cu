@@ -3,6 +3,8 @@
 #include "../../include/rtb200.h"
 
 #include <cuda_runtime.h>
+#include <omp.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <chrono>
@@ -87,7 +89,8 @@ typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile
 
 } // namespace
 
-constexpr int kLanes = 2;
+constexpr int kLanes = 2;        // chunks in flight by default
+constexpr int kMaxLanes = 6;     // ... at most (RT_OPT_LANES)
 
 // The per-frame work buffers of ONE wavefront chunk in flight.
 struct QueueSet {
@@ -145,9 +148,9 @@ struct RtContext {
     // per-frame work buffers
     DevBuf<uint32_t> d_super, d_frame;
     std::map<TileKey, TileList> tile_lists;
-    QueueSet qs[kLanes];                 // ray queues of the wavefront chunks in flight (one per lane, see rt_render_device_begin)
-    cudaStream_t lane_stream = nullptr;  // the second lane's stream (created on first use)
-    cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
+    QueueSet qs[kMaxLanes];              // ray queues of the wavefront chunks in flight (one per lane, see rt_render_device_begin)
+    cudaStream_t lane_stream[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // streams of lanes 1.. (created on first use; lane 0 = the context's stream)
+    cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<ChunkCounters> d_counters;
     DevBuf<unsigned int> d_flag;
     std::vector<cudaEvent_t> event_pool;
@@ -159,11 +162,13 @@ struct RtContext {
     Tuning tune{16, 16, 8, 1, -256, -64, -256};
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
-    uint32_t* h_frame = nullptr;         // pinned staging buffer of rt_render
+    uint32_t* h_frame = nullptr;         // pinned staging buffer of rt_frame_to_host / rt_render
     size_t h_frame_cap = 0;
+    cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per slice of that copy
     int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
+    int grid_intersect = 0, grid_occluded = 0;           // the same for the batch kernels (per context: its device's occupancy)
     bool opt_screen_cull = true;
-    bool opt_lanes = true;
+    int opt_lanes = kLanes;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -362,8 +367,23 @@ void screen_cull_rect(const RtContext* ctx, const FrameView& fr, WorkView& wk)
         if (!std::isfinite(nx) || !std::isfinite(ny)) return;
         xmin = std::min(xmin, nx); xmax = std::max(xmax, nx); ymin = std::min(ymin, ny); ymax = std::max(ymax, ny);
     }
-    // the projection must map depth monotonically for "in front" to mean what it says: check with the near-plane point
-    // that primary_ray uses (NDC z = -1 -> a view-space point with negative z for the reference's Perspective)
+    // The bound only means something if the rays primary_ray shoots are the projection's own lines of sight: the ray of
+    // NDC (x, y) runs from the view-space origin through proj_inv * (x, y, -1), so every point of it must project back to
+    // (x, y) with positive clip w.  That holds for the reference's Perspective; rt_set_camera accepts any matrix
+    // (orthographic, off-centre, ...), so it is checked on the frame's corners and centre, at two depths each.
+    for (int k = 0; k < 5; k++) {
+        const double nx = k == 4 ? 0.0 : (k & 1 ? 1.0 : -1.0), ny = k == 4 ? 0.0 : (k & 2 ? 1.0 : -1.0);
+        double v[4];
+        for (int i = 0; i < 4; i++) v[i] = pinv[4 * i] * nx + pinv[4 * i + 1] * ny - pinv[4 * i + 2] + pinv[4 * i + 3];
+        if (!(std::fabs(v[3]) > 1e-12)) return;
+        for (int i = 0; i < 3; i++) v[i] /= v[3];
+        for (const double along : {1.0, 7.5}) {
+            const double q[4] = {v[0] * along, v[1] * along, v[2] * along, 1.0};
+            double c[4];
+            for (int i = 0; i < 4; i++) c[i] = proj[4 * i] * q[0] + proj[4 * i + 1] * q[1] + proj[4 * i + 2] * q[2] + proj[4 * i + 3] * q[3];
+            if (!(c[3] > 0.0) || !(std::fabs(c[0] / c[3] - nx) < 1e-4) || !(std::fabs(c[1] / c[3] - ny) < 1e-4)) return;
+        }
+    }
     const double px0 = (xmin + 1.0) * 0.5 * fr.rw, px1 = (xmax + 1.0) * 0.5 * fr.rw;
     const double py0 = (ymin + 1.0) * 0.5 * fr.rh, py1 = (ymax + 1.0) * 0.5 * fr.rh;
     const double lim = 1e9;
@@ -485,13 +505,14 @@ void rt_destroy(RtContext* ctx)
     ctx->d_super.release(); ctx->d_frame.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
     for (auto& qs : ctx->qs) qs.release();
-    if (ctx->lane_stream) cudaStreamDestroy(ctx->lane_stream);
+    for (auto st : ctx->lane_stream) if (st) cudaStreamDestroy(st);
     if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
-    if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
+    for (auto e : ctx->lane_join) if (e) cudaEventDestroy(e);
     ctx->d_counters.release(); ctx->d_flag.release();
     ctx->b_a.release(); ctx->b_b.release(); ctx->b_t.release(); ctx->b_u.release(); ctx->b_v.release(); ctx->b_id.release(); ctx->b_occ.release();
     if (ctx->pending.host_cnt) cudaFreeHost(ctx->pending.host_cnt);
     if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+    for (auto e : ctx->copy_ev) if (e) cudaEventDestroy(e);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -534,9 +555,12 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
-    case RT_OPT_LANES: ctx->opt_lanes = value != 0; return RT_OK;
+    case RT_OPT_LANES:
+        if (value < 0 || value > kMaxLanes) return fail(ctx, RT_ERR_INVALID, "lanes %lld outside [0,%d]", (long long)value, kMaxLanes);
+        ctx->opt_lanes = value == 1 ? kLanes : (int)std::max<int64_t>(value, 1);   // 0: one chunk at a time; 1: the default (2); n: n chunks in flight
+        return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
-        if (value < 256) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels", (long long)value);
+        if (value < 256 || value > (1ll << 31)) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels outside [256, 2^31] (ray slots are 32-bit)", (long long)value);
         ctx->opt_chunk_pixels = (uint64_t)value;
         return RT_OK;
     default: return fail(ctx, RT_ERR_INVALID, "unknown option %d", option);
@@ -575,11 +599,13 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     if (max_depth < 0 || max_depth > RT_MAX_TREE_DEPTH) return fail(ctx, RT_ERR_INVALID, "max_depth %d outside [0,%d]", max_depth, RT_MAX_TREE_DEPTH);
     if (leaf_max_obj_count < 0) return fail(ctx, RT_ERR_INVALID, "leaf_max_obj_count %d", leaf_max_obj_count);
     const size_t n = ctx->xyz9.size() / 9;
+    ctx->bvh_valid = false;                              // whatever happens below, the previous tree is gone
     double t0 = now_ms();
     FlatScene flat;
     build_flat_scene(ctx->xyz9.data(), ctx->has_uv ? ctx->uv6.data() : nullptr, ctx->has_mat ? ctx->mat.data() : nullptr, n,
                      max_depth, leaf_max_obj_count, ctx->opt_leaf_split, flat);
     double t1 = now_ms();
+    if (flat.n_records >= (1ull << 28)) return fail(ctx, RT_ERR_INVALID, "scene needs %llu child records (limit 2^28)", (unsigned long long)flat.n_records);
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RT_CUDA(ctx, ctx->d_recs.ensure(flat.recs.size()));
     RT_CUDA(ctx, ctx->d_tris.ensure(flat.tris.size()));
@@ -609,7 +635,6 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     bi.nodes = flat.nodes; bi.leaves = flat.leaves; bi.empty_leaves = flat.empty_leaves; bi.interior = flat.interior;
     bi.max_depth_reached = flat.max_depth_reached; bi.max_leaf_size = flat.max_leaf_size;
     bi.child_records = flat.n_records;
-    if (flat.n_records >= (1ull << 28)) return fail(ctx, RT_ERR_INVALID, "scene needs %llu child records (limit 2^28)", (unsigned long long)flat.n_records);
     bi.device_bytes = (flat.recs.size() + flat.tris.size() + flat.shade.size()) * sizeof(F4) + flat.orig.size() * sizeof(int32_t);
     bi.build_ms = t1 - t0;
     bi.upload_ms = t2 - t1;
@@ -695,12 +720,16 @@ static int set_texture(RtContext* ctx, int slot, const void* data, int width, in
     if (int r = bind(ctx)) return r;
     if (slot < 0 || slot >= RT_TEX_COUNT) return fail(ctx, RT_ERR_INVALID, "texture slot %d", slot);
     if (!data || width <= 0 || height <= 0) return fail(ctx, RT_ERR_INVALID, "texture %dx%d", width, height);
-    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));                      // a frame in flight may still read the old texels
     Texture& t = ctx->tex[slot];
-    if (t.d) cudaFree(t.d);
-    t = Texture();
-    size_t bytes = (size_t)width * height * (format == 1 ? 4 : 16);
-    RT_CUDA(ctx, cudaMalloc(&t.d, bytes));
+    const size_t bytes = (size_t)width * height * (format == 1 ? 4 : 16);
+    const size_t had = (size_t)t.w * t.h * (t.format == 1 ? 4 : 16);
+    if (!t.d || had != bytes) {                                            // a map of the same size is replaced in place
+        if (t.d) cudaFree(t.d);
+        t = Texture();
+        RT_CUDA(ctx, cudaMalloc(&t.d, bytes));
+    }
+    t.w = 0; t.h = 0; t.format = 0;
     RT_CUDA(ctx, cudaMemcpy(t.d, data, bytes, cudaMemcpyHostToDevice));
     t.w = width; t.h = height; t.format = format;
     return RT_OK;
@@ -803,8 +832,8 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     // one chunk fill the SMs that the other chunk's kernels leave idle while their last, longest packets finish (within
     // one stream a kernel cannot start before the previous one has ended completely).  A frame that fits one chunk is cut
     // in two for that purpose.
-    const int n_lanes = (ctx->opt_lanes && tune_packets_hint(ctx) && tiles.size() >= 2) ? kLanes : 1;
-    if (n_lanes > 1 && tiles.size() <= tiles_per_chunk) tiles_per_chunk = (uint32_t)((tiles.size() + 1) / 2);
+    const int n_lanes = (ctx->opt_lanes > 1 && tune_packets_hint(ctx)) ? (int)std::min<size_t>((size_t)ctx->opt_lanes, std::max<size_t>(tiles.size(), 1)) : 1;
+    if (n_lanes > 1 && tiles.size() <= (size_t)tiles_per_chunk * (n_lanes - 1)) tiles_per_chunk = (uint32_t)((tiles.size() + n_lanes - 1) / n_lanes);
     const uint32_t n_chunks = (uint32_t)((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk);
     const size_t qcap = (size_t)std::min<uint64_t>((uint64_t)tiles_per_chunk, tiles.size()) * px_per_tile;
 
@@ -843,7 +872,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         super = ctx->d_super.p;
     }
     wk.tiles = classify ? tl->d_split : tl->d;
-    QueueView qv[kLanes];
+    QueueView qv[kMaxLanes];
     for (int l = 0; l < n_lanes; l++) {
         QueueSet& Q = ctx->qs[l];
         QueueView& q = qv[l];
@@ -853,11 +882,12 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         q.items = Q.items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
         q.refl_idx = Q.refl_idx.p; q.refl_rgb = Q.refl_rgb.p; q.refl_cnt = Q.refl_cnt.p; q.capacity = (uint32_t)qcap;
     }
-    if (n_lanes > 1 && !ctx->lane_stream) {
-        RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream, cudaStreamNonBlocking));
-        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
-        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join, cudaEventDisableTiming));
+    for (int l = 1; l < n_lanes; l++) {
+        if (ctx->lane_stream[l]) continue;
+        RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join[l], cudaEventDisableTiming));
     }
+    if (n_lanes > 1 && !ctx->lane_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
 
     const cudaStream_t main_stream = ctx->stream;
     cudaStream_t st = main_stream;
@@ -883,16 +913,16 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
     const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_items = grids[count][5], grid_finish = grids[count][6], grid_pitems = grids[count][7], grid_pfinish = grids[count][8];
-    if (n_lanes > 1) {                                                         // the second lane starts after everything enqueued so far
+    if (n_lanes > 1) {                                                         // the other lanes start after everything enqueued so far
         RT_CUDA(ctx, cudaEventRecord(ctx->lane_fork, main_stream));
-        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream, ctx->lane_fork, 0));
+        for (int l = 1; l < n_lanes; l++) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
     }
     for (uint32_t c = 0; c < n_chunks; c++) {
         wk.tile_begin = c * tiles_per_chunk;
         wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
         ChunkCounters* cnt = ctx->d_counters.p + c;
         const int lane = (int)(c % (uint32_t)n_lanes);
-        st = lane ? ctx->lane_stream : main_stream;
+        st = lane ? ctx->lane_stream[lane] : main_stream;
         const QueueView& q = qv[lane];
         {
             ScopedTimer tm(ctx, ST_PRIMARY, st);
@@ -949,12 +979,14 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         }
     }
     st = main_stream;
-    if (n_lanes > 1) {                                                         // the frame continues when both lanes are done
-        RT_CUDA(ctx, cudaEventRecord(ctx->lane_join, ctx->lane_stream));
-        RT_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->lane_join, 0));
+    for (int l = 1; l < n_lanes; l++) {                                        // the frame continues when all lanes are done
+        RT_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
+        RT_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->lane_join[l], 0));
     }
-    if (classify && n_traced < tl->count) {
-        // the tiles that cannot contain a hit: miss colour only
+    // the tiles that cannot contain a hit: miss colour only.  With a ray-independent miss colour and a resolve pass the
+    // resolved pixel IS that colour: k_resolve writes it and the samples of those tiles are never produced.
+    const bool const_fill = resolve && !(s->enable_skysphere || s->enable_skybox);
+    if (classify && n_traced < tl->count && !const_fill) {
         wk.tile_begin = n_traced;
         wk.tile_end = tl->count;
         ScopedTimer tm(ctx, ST_PRIMARY);
@@ -964,8 +996,10 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     if (resolve && !owned.empty()) {
         wk.tile_begin = 0;
         wk.tile_end = tl->count;                                               // all owned tiles, traced or not
+        const uint32_t background = quantise_argb(col(135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f));   // renderer.cpp:19, as shade_miss
         ScopedTimer tm(ctx, ST_RESOLVE);
-        k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(super, d_argb_out, wk, tile_size, fr.factor, s->image_width, s->image_height);
+        k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(super, d_argb_out, wk, tile_size, fr.factor, s->image_width, s->image_height,
+                                                     (classify && const_fill) ? n_traced : tl->count, background);
         launches++;
     }
     RT_CUDA(ctx, cudaEventRecord(ev_end, st));
@@ -1019,6 +1053,9 @@ int rt_render_device_end(RtContext* ctx, RtRenderStats* stats)
         rs.primary_volume_tests += host_cnt[c].primary_vol; rs.primary_triangle_tests += host_cnt[c].primary_tri;
         rs.shadow_volume_tests += host_cnt[c].shadow_vol; rs.shadow_triangle_tests += host_cnt[c].shadow_tri;
         rs.reflection_volume_tests += host_cnt[c].refl_vol; rs.reflection_triangle_tests += host_cnt[c].refl_tri;
+        rs.primary_fetched_bytes += host_cnt[c].primary_fetch; rs.shadow_fetched_bytes += host_cnt[c].shadow_fetch;
+        rs.reflection_fetched_bytes += host_cnt[c].refl_fetch;
+        rs.traced_primary_rays += host_cnt[c].traced_primary;
         overflow |= host_cnt[c].stack_overflow != 0;
     }
     rs.primary_rays = pd.primary_rays;
@@ -1077,6 +1114,55 @@ int rt_render_device(RtContext* ctx, const RtSettings* s, uint32_t* d_argb_out, 
     return rt_render_device_end(ctx, stats);
 }
 
+// Device frame -> the caller's pageable buffer.  The caller's buffer is ordinary memory (the adapter hands a std::vector,
+// the GUI a QImage): a device-to-host copy straight into it is staged by the driver in small pieces.  Frames of a
+// megapixel and more go through a pinned buffer of the context instead, in up to 8 slices: every slice's copy is enqueued
+// behind the frame's kernels with an event, and while slice i+1 crosses PCIe the host threads move slice i into the
+// caller's buffer.
+static int frame_to_host(RtContext* ctx, const uint32_t* d_frame, uint32_t* host_out, size_t n)
+{
+    if (n == 0) return RT_OK;
+    const bool staged = n >= ((size_t)1 << 20);
+    if (staged && n > ctx->h_frame_cap) {
+        if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+        ctx->h_frame = nullptr; ctx->h_frame_cap = 0;
+        if (cudaHostAlloc((void**)&ctx->h_frame, n * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess) ctx->h_frame_cap = n;
+        else { ctx->h_frame = nullptr; (void)cudaGetLastError(); }             // no pinned memory to be had: copy directly
+    }
+    if (!staged || !ctx->h_frame) {
+        RT_CUDA(ctx, cudaMemcpyAsync(host_out, d_frame, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RT_OK;
+    }
+    const int n_slices = (int)std::min<size_t>(8, std::max<size_t>(1, n >> 20));
+    const size_t per = ((n + n_slices - 1) / n_slices + 1023) & ~(size_t)1023;
+    for (int i = 0; i < n_slices; i++) {
+        const size_t b = std::min(n, per * i), e = std::min(n, b + per);
+        if (!ctx->copy_ev[i]) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+        if (e > b) RT_CUDA(ctx, cudaMemcpyAsync(ctx->h_frame + b, d_frame + b, (e - b) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        RT_CUDA(ctx, cudaEventRecord(ctx->copy_ev[i], ctx->stream));
+    }
+    for (int i = 0; i < n_slices; i++) {
+        const size_t b = std::min(n, per * i), e = std::min(n, b + per);
+        RT_CUDA(ctx, cudaEventSynchronize(ctx->copy_ev[i]));
+        const long long chunks = (long long)((e - b + 65535) / 65536);
+#pragma omp parallel for schedule(static)
+        for (long long c = 0; c < chunks; c++) {
+            const size_t cb = b + (size_t)c * 65536, ce = std::min(e, cb + 65536);
+            memcpy(host_out + cb, ctx->h_frame + cb, (ce - cb) * sizeof(uint32_t));
+        }
+    }
+    return RT_OK;
+}
+
+int rt_frame_to_host(RtContext* ctx, const uint32_t* d_frame, uint32_t* host_out, size_t n_pixels)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (n_pixels && (!d_frame || !host_out)) return fail(ctx, RT_ERR_INVALID, "NULL buffer");
+    return frame_to_host(ctx, d_frame, host_out, n_pixels);
+}
+
 int rt_render(RtContext* ctx, const RtSettings* s, uint32_t* argb_out, RtRenderStats* stats)
 {
     if (!ctx) return RT_ERR_INVALID;
@@ -1085,30 +1171,75 @@ int rt_render(RtContext* ctx, const RtSettings* s, uint32_t* argb_out, RtRenderS
     if (!argb_out) return fail(ctx, RT_ERR_INVALID, "argb_out is NULL");
     const size_t n = (size_t)s->image_width * s->image_height;
     RT_CUDA(ctx, ctx->d_frame.ensure(n));
-    // The caller's buffer is ordinary pageable memory (the adapter hands a std::vector, the GUI a QImage): a device-to-host
-    // copy straight into it is staged by the driver in small pieces.  Frames of a megapixel and more go through a pinned
-    // buffer of the context instead -- the copy is enqueued behind the frame's kernels, one host wait covers both -- and
-    // are moved to the caller's buffer by all host threads.
-    const bool staged = n >= ((size_t)1 << 20);
-    if (staged && n > ctx->h_frame_cap) {
-        if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
-        ctx->h_frame = nullptr; ctx->h_frame_cap = 0;
-        if (cudaHostAlloc((void**)&ctx->h_frame, n * sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess) ctx->h_frame_cap = n;
-        else { ctx->h_frame = nullptr; (void)cudaGetLastError(); }             // no pinned memory to be had: copy directly
-    }
     if (int r = rt_render_device_begin(ctx, s, ctx->d_frame.p, 64, 1, 0)) return r;
-    uint32_t* dst = (staged && ctx->h_frame) ? ctx->h_frame : argb_out;
-    cudaError_t ce = cudaMemcpyAsync(dst, ctx->d_frame.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (int r = rt_render_device_end(ctx, stats)) return r;                       // waits for the stream: kernels and copy
-    if (ce != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "cudaMemcpyAsync(frame): %s", cudaGetErrorString(ce));
-    if (dst != argb_out) {
-        const long long chunks = (long long)((n + 65535) / 65536);
-#pragma omp parallel for schedule(static)
-        for (long long c = 0; c < chunks; c++) {
-            const size_t b = (size_t)c * 65536, e = std::min(n, b + 65536);
-            memcpy(argb_out + b, ctx->h_frame + b, (e - b) * sizeof(uint32_t));
-        }
+    const int rc = frame_to_host(ctx, ctx->d_frame.p, argb_out, n);           // enqueued behind the kernels; returns when argb_out is complete
+    if (int r = rt_render_device_end(ctx, stats)) return r;
+    return rc;
+}
+
+int rt_set_host_threads(int n)
+{
+    if (n <= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : omp_get_num_procs();
     }
+    omp_set_num_threads(std::max(1, n));
+    return RT_OK;
+}
+
+// ---- frame buffers shared between the ranks of a box (CUDA IPC; see rtb200.h) ----------------------------------------
+int rt_frame_alloc(RtContext* ctx, size_t bytes, void** d_ptr_out, unsigned char handle_out[RT_FRAME_HANDLE_BYTES])
+{
+    if (!ctx || !d_ptr_out || !handle_out) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    static_assert(sizeof(cudaIpcMemHandle_t) == RT_FRAME_HANDLE_BYTES, "handle size");
+    void* p = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(bytes, 4)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(ctx, RT_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *d_ptr_out = p;
+    return RT_OK;
+}
+
+int rt_frame_open(RtContext* ctx, const unsigned char handle[RT_FRAME_HANDLE_BYTES], void** d_ptr_out)
+{
+    if (!ctx || !handle || !d_ptr_out) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ctx, RT_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    *d_ptr_out = p;
+    return RT_OK;
+}
+
+int rt_frame_close(RtContext* ctx, void* d_ptr)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (!d_ptr) return RT_OK;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return RT_OK;
+}
+
+int rt_frame_free(RtContext* ctx, void* d_ptr)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
+    if (!d_ptr) return RT_OK;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, cudaFree(d_ptr));
     return RT_OK;
 }
 
@@ -1172,9 +1303,8 @@ int rt_intersect(RtContext* ctx, const float* o3, const float* d3, size_t n, int
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_a.p, o3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_b.p, d3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(unsigned int), st));
-    static int grid = 0;
-    if (!grid) grid = grid_for(ctx, (const void*)k_intersect, kQueueThreads);
-    int blocks = (int)std::min<size_t>((size_t)grid, (n + kQueueThreads - 1) / kQueueThreads);
+    if (!ctx->grid_intersect) ctx->grid_intersect = grid_for(ctx, (const void*)k_intersect, kQueueThreads);
+    int blocks = (int)std::min<size_t>((size_t)ctx->grid_intersect, (n + kQueueThreads - 1) / kQueueThreads);
     k_intersect<<<blocks, kQueueThreads, 0, st>>>(scene_view(ctx), ctx->b_a.p, ctx->b_b.p, n, ctx->d_orig.p, ctx->b_id.p, ctx->b_t.p, ctx->b_u.p,
                                                  ctx->b_v.p, ctx->d_flag.p);
     RT_CUDA(ctx, cudaGetLastError());
@@ -1202,9 +1332,8 @@ int rt_occluded(RtContext* ctx, const float* p3, const float* n3, size_t n, uint
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_a.p, p3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->b_b.p, n3, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(unsigned int), st));
-    static int grid = 0;
-    if (!grid) grid = grid_for(ctx, (const void*)k_occluded, kQueueThreads);
-    int blocks = (int)std::min<size_t>((size_t)grid, (n + kQueueThreads - 1) / kQueueThreads);
+    if (!ctx->grid_occluded) ctx->grid_occluded = grid_for(ctx, (const void*)k_occluded, kQueueThreads);
+    int blocks = (int)std::min<size_t>((size_t)ctx->grid_occluded, (n + kQueueThreads - 1) / kQueueThreads);
     k_occluded<<<blocks, kQueueThreads, 0, st>>>(scene_view(ctx), ctx->light, ctx->b_a.p, ctx->b_b.p, n, ctx->b_occ.p, ctx->d_flag.p);
     RT_CUDA(ctx, cudaGetLastError());
     unsigned int flag = 0;
@@ -1252,7 +1381,7 @@ int rt_resolve_ssaa(RtContext* ctx, const uint32_t* argb_in, int width, int heig
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_super.p, argb_in, (size_t)width * height * 4, cudaMemcpyHostToDevice, st));
     WorkView wk = {};
     wk.tiles = tl->d; wk.tile_begin = 0; wk.tile_end = tl->count; wk.tiles_x = tl->tiles_x;
-    k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_super.p, ctx->d_frame.p, wk, tile, factor, w, h);
+    k_resolve<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_super.p, ctx->d_frame.p, wk, tile, factor, w, h, tl->count, 0u);
     RT_CUDA(ctx, cudaGetLastError());
     RT_CUDA(ctx, cudaMemcpyAsync(argb_out, ctx->d_frame.p, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));
     RT_CUDA(ctx, cudaStreamSynchronize(st));

@@ -146,3 +146,36 @@ def triangle_soup(n, seed, size=0.2, center=(0, 0, -4), spread=1.5):
     rng = np.random.default_rng(seed)
     c = rng.uniform(-spread, spread, size=(n, 1, 3)) + np.asarray(center)
     return (c + rng.normal(scale=size, size=(n, 3, 3))).reshape(n, 9).astype(np.float32)
+
+
+# ---- BASELINE.json configs at their FULL sizes (SURVEY.md section 8(d) inputs 1, 2, 3 and 5) ---------------------------
+_FULL_CACHE = {}
+
+
+def fullsize_table(mats):
+    """cfg1 1280x720; cfg2 1280x720 x ssaa 2 with 2048^2 u8 maps; cfg3 1920x1080 with the 16-ray fan, recursion depth 1,
+    seeded, roughness map and a 4096x2048 equirect sky.  Must stay in sync with tests/golden/make_golden_fullsize.py
+    (which imports this function)."""
+    if "tex" not in _FULL_CACHE:
+        n = 2048
+        _FULL_CACHE["tex"] = {0: scenes.noise_texture((n, n), 2), 1: scenes.noise_texture((n, n), 1, "rgb"),
+                              2: scenes.normal_map_texture((n, n), 4), 3: scenes.noise_texture((n, n), 3),
+                              4: scenes.sky_texture((2048, 4096))}
+    t = _FULL_CACHE["tex"]
+    mats3 = [dict(m) for m in mats]
+    mats3[0].update(reflection=0.9, roughness=0.0, specular=(0.2, 0.2, 0.2), diffuse=(0.5, 0.5, 0.5))   # load_obj override, QT/mainwindow.cpp:259-262
+    mats3[1].update(reflection=0.5, roughness=0.4)
+    mats3 = precompute_materials(mats3)
+    return {
+        "cfg1_full": (dict(image_width=1280, image_height=720, compute_shadows=1), mats, {}),
+        "cfg2_full": (dict(image_width=1280, image_height=720, compute_shadows=1, enable_ssaa=1, ssaa_factor=2, enable_ao_mapping=1,
+                           enable_diffuse_mapping=1, enable_normal_mapping=1), mats, {k: t[k] for k in (0, 1, 2, 3)}),
+        "cfg3_full": (dict(image_width=1920, image_height=1080, compute_shadows=1, rough_reflections_sample_count=16, max_recursion_depth=1,
+                           enable_roughness_mapping=1, enable_skysphere=1, rng_seed=7), mats3, {3: t[3], 4: t[4]}),
+    }
+
+
+FULL_ROW_STEP = 24                       # the committed goldens keep every 24th row of the reference's frame
+HAIR_FULL = dict(n_strands=15625, segments=16)        # 15 625 strands x 16 segments x 2 triangles x 2 sides = 1 000 000 triangles
+HAIR_KW = dict(image_width=3840, image_height=2160, compute_shadows=1)
+HAIR_BAND = (960, 1216, 16)              # rows of the 4K hair frame that the oracle / reference trace (row_begin, row_end, row_step)

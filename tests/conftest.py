@@ -93,3 +93,8 @@ def golden_rays():
 @pytest.fixture(scope="session")
 def golden_images():
     return dict(np.load(GOLDEN / "golden_images.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_fullsize():
+    return dict(np.load(GOLDEN / "golden_fullsize.npz"))

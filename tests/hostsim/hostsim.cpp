@@ -11,6 +11,9 @@
 #include <string>
 #include <vector>
 #include <omp.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include "../../raytracercpp_b200/csrc/rt_device.h"
 #include "../../raytracercpp_b200/csrc/host_common.h"
@@ -382,6 +385,10 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
         }
     }
     rs.kernel_launches = 0;
+    rs.traced_primary_rays = rs.primary_rays;                 // the emulation has no screen cull: every sample gets a ray
+    rs.primary_fetched_bytes = 64 * rs.primary_volume_tests + 48 * rs.primary_triangle_tests;   // single rays: one fetch per test
+    rs.shadow_fetched_bytes = 64 * rs.shadow_volume_tests + 48 * rs.shadow_triangle_tests;
+    rs.reflection_fetched_bytes = 64 * rs.reflection_volume_tests + 48 * rs.reflection_triangle_tests;
     if (stats) *stats = rs;
     return RT_OK;
 }
@@ -401,6 +408,74 @@ int rt_render_device_end(RtContext*, RtRenderStats* stats)
 int rt_render(RtContext* c, const RtSettings* s, uint32_t* argb_out, RtRenderStats* stats)
 {
     return rt_render_device(c, s, argb_out, 64, 1, 0, stats);
+}
+
+int rt_set_host_threads(int n)
+{
+    omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+    return RT_OK;
+}
+
+// Frames shared between the ranks of a box: where the CUDA library hands out CUDA IPC handles, the emulation hands out
+// the name of a POSIX shared-memory object, so the world_size-2 gloo test exercises the same "peers store straight into
+// rank 0's frame" protocol with real processes.
+struct SharedFrame { void* p; size_t bytes; bool owner; char name[RT_FRAME_HANDLE_BYTES]; };
+static std::vector<SharedFrame> g_frames;
+
+int rt_frame_alloc(RtContext* c, size_t bytes, void** d_ptr_out, unsigned char handle_out[RT_FRAME_HANDLE_BYTES])
+{
+    static int serial = 0;
+    SharedFrame f;
+    memset(&f, 0, sizeof(f));
+    f.bytes = std::max<size_t>(bytes, 4);
+    f.owner = true;
+    snprintf(f.name, sizeof(f.name) - 8, "/rtb200_hostsim_%d_%d", (int)getpid(), serial++);
+    int fd = shm_open(f.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)f.bytes) != 0) return fail(c, RT_ERR_CUDA, "shm_open");
+    f.p = mmap(nullptr, f.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (f.p == MAP_FAILED) return fail(c, RT_ERR_CUDA, "mmap");
+    memcpy(f.name + RT_FRAME_HANDLE_BYTES - 8, &f.bytes, 8);               // the size travels in the handle's last 8 bytes
+    memcpy(handle_out, f.name, RT_FRAME_HANDLE_BYTES);
+    g_frames.push_back(f);
+    *d_ptr_out = f.p;
+    return RT_OK;
+}
+
+int rt_frame_open(RtContext* c, const unsigned char handle[RT_FRAME_HANDLE_BYTES], void** d_ptr_out)
+{
+    SharedFrame f;
+    memset(&f, 0, sizeof(f));
+    memcpy(f.name, handle, RT_FRAME_HANDLE_BYTES);
+    memcpy(&f.bytes, handle + RT_FRAME_HANDLE_BYTES - 8, 8);
+    int fd = shm_open(f.name, O_RDWR, 0600);
+    if (fd < 0) return fail(c, RT_ERR_CUDA, "shm_open (peer)");
+    f.p = mmap(nullptr, f.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (f.p == MAP_FAILED) return fail(c, RT_ERR_CUDA, "mmap (peer)");
+    g_frames.push_back(f);
+    *d_ptr_out = f.p;
+    return RT_OK;
+}
+
+static int frame_release(void* p, bool unlink_it)
+{
+    for (size_t i = 0; i < g_frames.size(); i++)
+        if (g_frames[i].p == p) {
+            munmap(p, g_frames[i].bytes);
+            if (unlink_it && g_frames[i].owner) { char n[RT_FRAME_HANDLE_BYTES]; memcpy(n, g_frames[i].name, sizeof(n)); n[RT_FRAME_HANDLE_BYTES - 8] = 0; shm_unlink(n); }
+            g_frames.erase(g_frames.begin() + (long)i);
+            return RT_OK;
+        }
+    return RT_ERR_INVALID;
+}
+int rt_frame_close(RtContext*, void* p) { return p ? frame_release(p, false) : RT_OK; }
+int rt_frame_free(RtContext*, void* p) { return p ? frame_release(p, true) : RT_OK; }
+
+int rt_frame_to_host(RtContext*, const uint32_t* d_frame, uint32_t* host_out, size_t n_pixels)
+{
+    memcpy(host_out, d_frame, n_pixels * sizeof(uint32_t));
+    return RT_OK;
 }
 
 static void tile_copy(const RtSettings* s, const uint32_t* frame_in, uint32_t* frame_out, uint32_t* staging, int tile_size, int mod, int rem, int unpack)

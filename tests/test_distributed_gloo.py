@@ -1,5 +1,7 @@
-"""The N>1 host logic (tile ownership, equal-size staging slots, all-gather, unpack) on the CPU: two gloo ranks,
-CPU tensors, the host kernel emulation standing in for the device.  The same ShardedFrame runs on NCCL in bench.py."""
+"""The N>1 host logic on the CPU: gloo ranks, CPU tensors, the host kernel emulation standing in for the device.  Both
+gather modes of ShardedFrame: "peer" (every rank stores its tiles straight into rank 0's shared frame -- CUDA IPC on the
+GPU, POSIX shared memory here -- plus one barrier per frame) and "nccl" (pack -> all-gather -> unpack).  The same class
+runs on NCCL in bench.py."""
 import ctypes
 import os
 import socket
@@ -37,14 +39,31 @@ def _worker(rank, world, port, out_dir):
     kw, m, tex = common.config_table(mats)["cfg2"]
     kw = dict(kw, image_width=150, image_height=84)            # not a multiple of the tile size: ragged edge tiles
     r = common.product_renderer(lib, robot, kw, m, tex)
-    frame = ShardedFrame(r.ctx, r.render_settings(), rank, world, tile_size=16, device=torch.device("cpu"))
+    # round-1 path, kept as the fallback: pack -> all_gather -> unpack, every rank ends up with the frame
+    frame = ShardedFrame(r.ctx, r.render_settings(), rank, world, tile_size=16, device=torch.device("cpu"), gather="nccl")
     stats = frame.render()
     full = frame.gather().numpy().view(np.uint32).copy()
     frame.frame.zero_()
-    stats2 = frame.render_and_gather()                       # the begin / gather / end form used by bench.py
+    stats2 = frame.render_and_gather()                       # the begin / cross-rank step / end form used by bench.py
     assert np.array_equal(frame.frame.numpy().view(np.uint32), full) and stats2.primary_hits == stats.primary_hits
     np.save(Path(out_dir) / f"frame_{rank}.npy", full)
-    np.save(Path(out_dir) / f"rays_{rank}.npy", np.array([stats.primary_rays, stats.primary_hits]))
+    np.save(Path(out_dir) / f"rays_{rank}.npy", np.array([stats.primary_rays, stats.primary_hits, stats.traced_primary_rays]))
+    # the fused path: every rank stores its tiles straight into rank 0's (shared) frame, one barrier per frame, two
+    # frames used alternately; rank 0 ends up with the complete frame, through render_to_host in a pageable array
+    peer = ShardedFrame(r.ctx, r.render_settings(), rank, world, tile_size=16, device=torch.device("cpu"), gather="peer")
+    assert peer.mode == "peer", peer.why_not_peer
+    host = np.zeros((84, 150), np.uint32)
+    for it in range(3):                                      # three frames: both buffers, and the first one again
+        if rank == 0:
+            peer.views[peer.flip].zero_()
+        dist.barrier()
+        st3 = peer.render_to_host(host)
+        assert st3.primary_hits == stats.primary_hits
+        if rank == 0:
+            assert np.array_equal(host, full), f"peer-store frame {it} differs"
+            assert np.array_equal(peer.frame.numpy().view(np.uint32), full)
+        dist.barrier()
+    peer.close()
     if rank == 0:
         r.ray_trace()
         np.save(Path(out_dir) / "single.npy", r.get_image())

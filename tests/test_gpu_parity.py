@@ -448,11 +448,72 @@ def test_cpp_adapter_example(cuda_lib, tmp_path):
     assert "adapter ok" in out
 
 
+# ---- BASELINE.json configs[0..2] and [4] at their FULL sizes ----------------------------------------------------------
+def check_fullsize_frame(lib, oracle, robot, golden_fullsize, name):
+    kw, mats, tex = common.fullsize_table(robot["materials"])[name]
+    img, stats = common.product_image(lib, robot, kw, mats, tex)
+    assert img.shape == (kw["image_height"], kw["image_width"])
+    want = common.oracle_image(oracle, robot, kw, mats, tex)                     # live oracle, the whole frame
+    common.assert_image_close(img, want, what=name + " vs oracle")
+    assert (img == want).mean() >= 0.999
+    rows = golden_fullsize[name + "_rows"]                                       # committed rows of the compiled reference's frame
+    common.assert_image_close(img[::common.FULL_ROW_STEP], rows, what=name + " vs reference rows")
+    assert (img[::common.FULL_ROW_STEP] == rows).mean() >= 0.999
+    f = kw.get("ssaa_factor", 1) if kw.get("enable_ssaa") else 1
+    assert stats.primary_rays == kw["image_width"] * kw["image_height"] * f * f
+    assert stats.primary_hits == int(golden_fullsize[name + "_hits"]) and stats.shadow_rays == stats.primary_hits
+    cnt = common.oracle_renderer(oracle, robot, kw, mats, tex).count_rows()
+    assert stats.reflection_rays == cnt["reflection_rays"] and stats.reflection_shadow_rays == cnt["reflection_shadow_rays"]
+    return stats
+
+
+@pytest.mark.parametrize("name", ["cfg1_full", "cfg2_full", "cfg3_full"])
+def test_fullsize_frames_vs_oracle_and_reference_rows(cuda_lib, oracle, robot, golden_fullsize, name):
+    """cfg1 at 1280x720, cfg2 at 1280x720 x ssaa 2 with 2048^2 u8 maps, cfg3 at 1920x1080 with the seeded 16-ray fan
+    (renderer.cpp:1068-1116, :283-338): the whole frame against the live oracle and against the committed rows of the
+    compiled reference's frame; hit / shadow / fan ray counts exact."""
+    stats = check_fullsize_frame(cuda_lib, oracle, robot, golden_fullsize, name)
+    if name == "cfg3_full":
+        assert stats.reflection_rays > 1_000_000
+
+
+def test_hair_fullsize_band(cuda_lib, oracle, golden_fullsize):
+    """BASELINE.json configs[4] at its size: 1 000 000 thin strand triangles, 3840x2160, hard shadows.  The whole frame is
+    rendered; a band of rows is compared with the live oracle and with the committed rows of the compiled reference
+    (incoherent packets, deep tree: the worst case of the packet traversal)."""
+    xyz9, uv6, mat = scenes.hair_ball(**common.HAIR_FULL)
+    scene = dict(xyz9=xyz9, uv6=uv6, mat=mat)
+    mats = rt.precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
+    r = common.product_renderer(cuda_lib, scene, common.HAIR_KW, mats, {})
+    assert r.bvh_info["triangles"] == 1_000_000
+    r.ray_trace()
+    img, st = r.get_image().copy(), r.last_stats()
+    assert st.primary_rays == 3840 * 2160 and st.shadow_rays == st.primary_hits and st.primary_hits > 500_000
+    b0, b1, bs = common.HAIR_BAND
+    band = img[b0:b1:bs]
+    rows = golden_fullsize["cfg5_band_rows"]
+    common.assert_image_close(band, rows, what="hair band vs reference rows")
+    assert (band == rows).mean() >= 0.999
+    orc = common.oracle_renderer(oracle, scene, common.HAIR_KW, mats, {})
+    sup, _ = orc.trace_rows(row_begin=b0, row_end=b1, row_step=bs)
+    assert np.array_equal(sup[b0:b1:bs], rows)                                   # the oracle is bit-exact on the band
+    # closest hits of an incoherent ray batch, bit-exact against the oracle's octree
+    o, d = common.random_rays(50_000, 29, (-1, -1, -4), (1, 1, -2))
+    for g, w in zip(r.ctx.intersect(o, d), oracle.bvh(xyz9, 12, 40).intersect(o, d)):
+        assert np.array_equal(g, w)
+    # scheduling knobs leave the 4K frame bit-identical
+    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1)):
+        r.ctx.set_option(opt, val)
+        r.ray_trace()
+        assert np.array_equal(r.get_image(), img), opt
+        r.ctx.set_option(opt, back)
+    r.close()
+
+
 # ---- full BASELINE.json size: 10 M triangles, 3840x2160, 16 spp, shadows --------------------------------------------
 @pytest.fixture(scope="module")
 def big_sphere():
-    n = int(os.environ.get("RT_TEST_TRIANGLES", 10_000_000))
-    return scenes.displaced_sphere(*scenes.sphere_grid_for(n))
+    return scenes.displaced_sphere(*scenes.sphere_grid_for(10_000_000))
 
 
 def test_full_size_properties(cuda_lib, oracle, big_sphere):

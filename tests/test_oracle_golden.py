@@ -50,3 +50,32 @@ def test_camera_matrices_and_inverse(oracle, golden_images):
 @pytest.mark.parametrize("factor", [2, 3, 4])
 def test_ssaa_resolve(oracle, golden_images, factor):
     assert np.array_equal(oracle.downscale(golden_images["resolve_in"], factor), golden_images[f"resolve_out_{factor}"])
+
+
+# ---- BASELINE.json configs at their FULL sizes: the oracle is bit-exact against the compiled reference there too ------
+@pytest.mark.parametrize("name", ["cfg1_full", "cfg2_full", "cfg3_full"])
+def test_fullsize_frames_match_reference_crc(oracle, robot, golden_fullsize, name):
+    import zlib
+    kw, mats, tex = common.fullsize_table(robot["materials"])[name]
+    img = common.oracle_image(oracle, robot, kw, mats, tex)
+    assert img.shape == (kw["image_height"], kw["image_width"])
+    assert zlib.crc32(np.ascontiguousarray(img, np.uint32).tobytes()) == int(golden_fullsize[name + "_crc"])
+    assert np.array_equal(img[::common.FULL_ROW_STEP], golden_fullsize[name + "_rows"])
+    r = common.oracle_renderer(oracle, robot, kw, mats, tex)
+    assert r.count_rows()["shadow_rays"] == int(golden_fullsize[name + "_hits"])
+
+
+def test_hair_band_matches_reference(oracle, golden_fullsize):
+    """cfg5 at its BASELINE size (1 M strand triangles, 3840x2160, shadows): a band of rows, bit-exact."""
+    import zlib
+    import raytracercpp_b200 as rt
+    from raytracercpp_b200 import scenes
+    xyz9, uv6, mat = scenes.hair_ball(**common.HAIR_FULL)
+    assert len(xyz9) == 1_000_000
+    r = common.oracle_renderer(oracle, dict(xyz9=xyz9, uv6=uv6, mat=mat), common.HAIR_KW, rt.precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL]), {})
+    b0, b1, bs = common.HAIR_BAND
+    sup, _ = r.trace_rows(row_begin=b0, row_end=b1, row_step=bs)
+    band = sup[b0:b1:bs]
+    assert np.array_equal(band, golden_fullsize["cfg5_band_rows"])
+    assert zlib.crc32(np.ascontiguousarray(band, np.uint32).tobytes()) == int(golden_fullsize["cfg5_band_crc"])
+    assert r.count_rows(row_begin=b0, row_end=b1, row_step=bs)["shadow_rays"] == int(golden_fullsize["cfg5_band_hits"])
