@@ -183,6 +183,11 @@ enum {
     RT_OPT_PACKET_ROUNDS = 7, /* shadow packets (default -256)                                                           */
     RT_OPT_PRIMARY_ROUNDS = 11,/* primary packets (default -256; negative additionally means: not split in long launches) */
     RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -64; 0 is invalid)                 */
+    RT_OPT_FUSED_ITEMS = 12,  /* 0 (default): the work items of split packets are traced generation by generation in separate
+                                 launches (six item passes and a finish kernel per stage); 1: the packet kernels consume the
+                                 items themselves through 32 ticket queues, the last item of a record stores its pixels -- one
+                                 launch per stage, but items of a record run concurrently and prune each other less: measured
+                                 slower on B200, kept for experiments.  Results do not depend on it             */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
     RT_OPT_LANES = 9,         /* wavefront chunks in flight at a time, each on its own stream with its own queues, so one

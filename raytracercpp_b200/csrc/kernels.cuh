@@ -31,11 +31,31 @@ constexpr int kPrimaryThreads = 128;
 constexpr int kQueueThreads = 128;
 constexpr int kPrimaryFetch = 1;     // 32-ray packets a warp of k_primary_packet takes per atomic (4: -4 %, coarser load balance)
 constexpr int kStepsPerCheck = 4;    // single-test steps between two refill / completion checks of a persistent single-ray warp
+constexpr unsigned kParkCtas = 296;  // fused item scheduling: the warps of this many CTAs (the first waves: about two CTAs per SM) stay to serve late items
+constexpr unsigned kFusedGenerations = 12;   // ... an item of this generation is traced to the end (no round budget)
 constexpr int kItemPasses = 6;       // generations of work items of a split packet = launches of k_*_items; the last has no round
                                      // budget (3 left a straggler in the unlimited pass: k_shade 8.9 ms against 8.0 with 6; 10: same)
 #ifndef RTB_SHADE_MINB
 #define RTB_SHADE_MINB 7   /* resident CTAs per SM the compiler must allow for k_shade_packet; measured on cfg4: 7 -> 8.9 ms, 6: 9.4, 8: 9.6 */
 #endif
+
+// Fused item scheduling: the item queue of a stage is kSubQueues independent ticket queues, each with its counters on a
+// 128-byte line of its own (= an L2 slice of its own).  One queue polled and compare-and-swapped by every warp of the grid
+// after every packet is a single hot address: the L2 serves a few hundred million operations per second on one line, the
+// grid asks for billions, and the launch slows down tenfold (measured).  A warp emits into and polls its HOME queue;
+// only a warp that has run out of packets looks at all of them (one load per lane, in parallel).
+constexpr int kSubQueues = 32;
+struct alignas(128) SubQueue {
+    unsigned int n;                  // tickets reserved in this sub-queue
+    unsigned int next;               // tickets handed out
+    unsigned int pad[30];
+};
+struct alignas(16) FusedTotals {     // termination: read packets_done, then done, then reserved
+    unsigned int reserved;           // real items published, all sub-queues
+    unsigned int done;               // items completed
+    unsigned int packets_done;       // packets completed (reported per warp when it runs out of packets)
+    unsigned int pad;
+};
 
 struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int next_patch;         // next ray slot of k_primary
@@ -47,6 +67,9 @@ struct ChunkCounters {               // one per chunk, zeroed before the frame
     unsigned int items_n[kItemPasses];    // work items written for item pass p (each: one unvisited cell of a split packet)
     unsigned int items_next[kItemPasses]; // next item of pass p to take
     unsigned int p_split, p_items_n[kItemPasses], p_items_next[kItemPasses];   // the same for split PRIMARY packets
+    // fused item scheduling (Tuning::fused): [0] primary stage, [1] shade stage
+    SubQueue sq[2][kSubQueues];
+    FusedTotals ft[2];
     unsigned long long refl_rays;
     unsigned long long refl_shadow_rays;
     // COUNT instantiations only: volume / triangle tests done by the traversal, per ray class
@@ -119,6 +142,12 @@ struct QueueView {
     uint32_t* split_occ;             // lanes found occluded since (atomicOr by the items)
     uint4* items;                    // kItemPasses regions of item_capacity: (split index, link, meta, -)
     uint32_t split_capacity, item_capacity;
+    // fused item scheduling: items[] is one queue of kItemPasses * item_capacity slots; slot i is valid once item_ready[i] == tag
+    // (tag differs per frame and stage, so the flags never need clearing); split_pending[sidx] counts the record's items that
+    // have not completed yet -- the warp that brings it to zero stores the record's pixels / slot records
+    uint32_t* item_ready;
+    uint32_t* split_pending;
+    uint32_t tag;
     // split primary packets (k_primary_packet -> k_primary_items -> k_primary_finish); item regions are shared with the
     // shadow packets (the two never run at the same time), split_base / split_active too
     unsigned long long* split_best;  // 32 per split record: bits(t) << 32 | original triangle index of the closest hit so far (atomicMin)
@@ -156,6 +185,8 @@ struct Tuning {
     int32_t packet_rounds;    // a shadow packet that needs more cell/leaf rounds than this is split into work items (0: never)
     int32_t item_rounds;      // the same for the items of all passes but the last
     int32_t primary_rounds;   // round budget of a primary packet (0: never split)
+    int32_t fused;            // 1: the packet kernels consume the work items of their split packets themselves (one launch per stage);
+                              // 0: item passes and a finish kernel are separate launches (k_*_items x kItemPasses, k_*_finish)
 };
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
@@ -296,6 +327,8 @@ RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4&
     return ok ? tn - sr.slack : INFINITY;
 }
 
+RT_DEV uint32_t ld_vol(const unsigned int* p) { return *((const volatile unsigned int*)p); }
+
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
 // occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
 // The traversal starts at the root cell, or (start_meta != 0) at the cell / leaf (start_link, start_meta).
@@ -308,7 +341,8 @@ RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4&
 template <bool ANY, bool COUNT>
 RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
                          HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds,
-                         uint32_t start_link = 0u, uint32_t start_meta = 0u, int32_t best_orig = 0x7fffffff)
+                         uint32_t start_link = 0u, uint32_t start_meta = 0u, int32_t best_orig = 0x7fffffff,
+                         const unsigned int* poll_occ = nullptr, const unsigned long long* poll_best = nullptr)
 {
     const unsigned lane = threadIdx.x & 31u;
     SlabRay sr;
@@ -334,6 +368,26 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
             return false;
         }
         ++rounds;
+        // An item of a split packet that runs concurrently with the record's other items (fused scheduling) looks at what
+        // they have found every fourth round: an answered shadow ray is dropped (and the item ends when all are), a closer
+        // primary hit lowers this lane's limit.  Pure pruning: the merged answer is an OR / a minimum either way.
+        if ((rounds & 3u) == 0u) {
+            if (ANY && poll_occ != nullptr) {
+                uint32_t w = 0;
+                if (lane == 0) w = ld_vol(poll_occ);
+                w = __shfl_sync(0xffffffffu, w, 0);
+                if ((w >> lane) & 1u) active = false;
+                if (__ballot_sync(0xffffffffu, active) == 0u) return true;
+            }
+            if (!ANY && poll_best != nullptr) {
+                const unsigned long long key = *((const volatile unsigned long long*)(poll_best + lane));
+                if (key != ~0ull) {
+                    const float te = __uint_as_float((uint32_t)(key >> 32));
+                    const int32_t oe = (int32_t)(uint32_t)key;
+                    if (te < t_max || (te == t_max && oe < best_orig)) { t_max = te; best_orig = oe; }
+                }
+            }
+        }
         if (!(meta & RT_LEAF_BIT)) {
             // ---- one cell: the warp fetches the cell's records with ONE coalesced 128-bit load per lane and stages
             // them in shared memory (one memory latency per cell instead of one per child); then every lane tests every
@@ -1028,6 +1082,454 @@ k_shade_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         }
     }
     shade_epilogue<COUNT>(cnt, tc, fan, 0u);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused item scheduling (Tuning::fused, the default).  The item passes above are separate launches: six per stage, each
+// with its own ramp-up and tail, which is a third of the frame time of a short launch (one of 8 tile shards of a 4K frame:
+// 0.6 of 2.4 ms, measured).  Here the packet kernel's own persistent warps consume the work items while the launch is
+// still running: one queue per stage (kSubQueues ticket queues), a warp looks for an item before it takes the next
+// packet (items belong to the longest packets: starting them early shortens the critical path), and the warp that
+// completes the last item of a split record stores that record's pixels.  One launch per stage, no item generations to
+// wait for; the price is that items of one record run concurrently and prune each other less (an item reads the answers
+// found so far when it starts).  Results cannot differ from the pass-by-pass schedule: any-hit answers are OR-ed, closest
+// hits merged with the same 64-bit atomicMin.
+//
+// Protocol.  Producer (a packet or item that ran out of rounds): reserve n tickets in its home sub-queue (atomicAdd n),
+// raise the record's pending count and the stage's reserved total by n, write the n slots nearest cell first, fence, set
+// each slot's ready flag to this launch's tag.  Consumer: if next < n take ticket t = next by compare-and-swap, wait for
+// slot t's flag, run the item, OR / min its
+// answers into the record, fence, lower the record's pending count -- whoever reaches zero finishes the record -- and count
+// the item as done.  A warp that finds neither a packet nor an item leaves -- except the PARKED warps (the CTAs with the
+// lowest indices, about one per SM), which stay and poll with back-off until every packet has completed and
+// done == reserved (read in that order: nothing that could still emit is running then); late items are served by them
+// and by the warps that are still at work.  Nobody ever waits for a warp that is not running.
+RT_DEV uint2 sq_snapshot(const SubQueue* sq)                                   // (n, next) in one 8-byte load
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(sq));
+    return v;
+}
+
+RT_DEV bool fq_all_done(const FusedTotals* ft, uint32_t total_packets)
+{
+    // ordered reads: packets, then items done, then items reserved (an item's children are reserved before it is counted
+    // as done: with every packet complete and done == reserved read in that order, nothing that could still emit is running)
+    const uint32_t pd = ld_vol(&ft->packets_done);
+    if (pd != total_packets) return false;
+    __threadfence();
+    const uint32_t done = ld_vol(&ft->done);
+    __threadfence();
+    const uint32_t n = ld_vol(&ft->reserved);
+    return done == n;
+}
+
+// Round budget of a packet claimed when `rem` more packets per resident warp are still unclaimed, and of the items
+// emitted around that time (guided self-scheduling): early in the launch a packet may run long -- there is plenty of other
+// work to keep the SMs busy meanwhile --, near the end it is cut after a few rounds so that its cells spread over the
+// warps that are running out of packets.  The launch's tail is about one budget long instead of one whole packet.
+RT_DEV int fq_budget(int max_rounds, uint32_t rem) { return max_rounds > 0 ? (int)min((uint32_t)max_rounds, 8u + 8u * rem) : 0; }
+
+RT_DEV uint32_t fq_home() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % (uint32_t)kSubQueues; }
+RT_DEV uint32_t fq_sub_capacity(const QueueView& q) { return q.item_capacity * (uint32_t)kItemPasses / (uint32_t)kSubQueues; }
+
+// The unvisited cells K.link/meta[0, K.saved) of split record `sidx` become items of generation `gen` in the emitting
+// warp's home sub-queue.  `first`: the emitter is the packet itself (sets the record's pending count) rather than one of
+// its items (raises it).  The caller has written the split record and fenced.  Returns false when the sub-queue is full:
+// nothing was published and the caller finishes its rays in place (slots it was handed below the capacity get null items).
+RT_DEV bool fq_emit(const QueueView& q, ChunkCounters* cnt, int stage, const PacketStack& K, uint32_t sidx, uint32_t gen, bool first)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = (uint32_t)K.saved, cap = fq_sub_capacity(q), home = fq_home();
+    uint32_t at = 0;
+    if (lane == 0) at = atomicAdd(&cnt->sq[stage][home].n, n);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    const bool ok = at + n <= cap;
+    if (ok && lane == 0) {
+        if (first) atomicExch(&q.split_pending[sidx], n);
+        else atomicAdd(&q.split_pending[sidx], n);
+        atomicAdd(&cnt->ft[stage].reserved, n);
+        __threadfence();
+    }
+    __syncwarp();
+    const size_t region = (size_t)home * cap;
+    for (uint32_t i = lane; i < n && at + i < cap; i += 32u) {
+        const uint32_t j = n - 1u - i;                                          // the stack's top is the nearest cell: it goes first
+        q.items[region + at + i] = ok ? make_uint4(sidx, K.link[j], K.meta[j], gen) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+        __threadfence();
+        *((volatile uint32_t*)&q.item_ready[region + at + i]) = q.tag;
+    }
+    __syncwarp();
+    return ok;
+}
+
+// Takes one item if there is one: from the warp's home sub-queue (`scan` false: one 8-byte load) or from any sub-queue,
+// nearest to home first (`scan` true: every lane looks at one).  0: nothing queued (where it looked); 1: `item` holds one;
+// 2: something was queued but another warp took it first.  A ticket is claimed with compare-and-swap on the value just
+// read, so a warp never holds a ticket for an item that does not exist yet.
+RT_DEV int fq_take(const QueueView& q, ChunkCounters* cnt, int stage, bool scan, uint4& item)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t cap = fq_sub_capacity(q), home = fq_home();
+    const uint32_t mine_q = (home + lane) % (uint32_t)kSubQueues;
+    uint2 v = make_uint2(0u, 0u);
+    if (scan || lane == 0) v = sq_snapshot(&cnt->sq[stage][mine_q]);
+    const bool avail = v.y < v.x && v.y < cap;                                  // tickets beyond the capacity are void: nothing behind them
+    const unsigned am = __ballot_sync(0xffffffffu, avail);
+    if (am == 0u) return 0;
+    const int src = __ffs(am) - 1;
+    const uint32_t sub = (home + (uint32_t)src) % (uint32_t)kSubQueues;
+    const uint32_t t = __shfl_sync(0xffffffffu, v.y, src);
+    int won = 0;
+    if (lane == 0) won = atomicCAS(&cnt->sq[stage][sub].next, t, t + 1u) == t;
+    if (!__shfl_sync(0xffffffffu, won, 0)) return 2;
+    const size_t slot = (size_t)sub * cap + t;
+    if (lane == 0) {
+        while (ld_vol(&q.item_ready[slot]) != q.tag) __nanosleep(40);           // its producer is between reserving and publishing
+        __threadfence();
+    }
+    __syncwarp();
+    item = __ldcg(&q.items[slot]);
+    return 1;
+}
+
+// One shadow item: the packet's 32 shadow rays from one unvisited cell (as k_shade_items), then completion.
+template <bool COUNT>
+RT_DEV void shade_item_fused(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, ChunkCounters* cnt, uint32_t* super,
+                             int item_budget, PacketStack& K, const uint4 item, uint32_t n_hits, TraceCounters& tc, TraceCounters& fan, unsigned& overflow)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t sidx = item.x;
+    if (sidx == 0xffffffffu) return;                                           // a null item (its emission found the sub-queue full): nothing to do
+    const uint32_t base = __ldcg(&q.split_base[sidx]), am = __ldcg(&q.split_active[sidx]);   // written by another SM during this launch: not through L1
+    const uint32_t live = am & ~ld_vol(&q.split_occ[sidx]);
+    const uint32_t entry = base + lane;
+    bool active = entry < n_hits && ((live >> lane) & 1u) != 0u;
+    if (__ballot_sync(0xffffffffu, active) != 0u) {                            // else: every ray has been answered meanwhile
+        ShadeLane L;
+        L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
+        if (active) L = shade_prepare(sc, fr, wk, q, entry);
+        const V3 so = L.p + 1.0e-4f * L.nrm;
+        const V3 sd = active ? normalize(fr.light - L.p) : v3(0, 0, 1);
+        const float dist2 = length2(L.p - fr.light);
+        const float t_lim = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
+        HitRec unused;
+        bool occluded = false;
+        unsigned rounds = 0;
+        const int budget = item.w + 1u < kFusedGenerations ? item_budget : 0;
+        const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds, item.y, item.z,
+                                                        0x7fffffff, &q.split_occ[sidx]);
+        __syncwarp();
+        if (!finished && !fq_emit(q, cnt, 1, K, sidx, item.w + 1u, false)) {
+            const bool before = occluded;                                      // no room: finish the item here
+            packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z, 0x7fffffff,
+                                      &q.split_occ[sidx]);
+            occluded = occluded || before;
+            __syncwarp();
+        }
+        const unsigned om = __ballot_sync(0xffffffffu, occluded);
+        if (om != 0u && lane == 0) atomicOr(&q.split_occ[sidx], om);
+    }
+    // completion: the record's last item stores its pixels
+    uint32_t left = 0;
+    if (lane == 0) {
+        __threadfence();
+        left = atomicSub(&q.split_pending[sidx], 1u);
+    }
+    left = __shfl_sync(0xffffffffu, left, 0);
+    if (left == 1u) {
+        uint32_t occ = 0;
+        if (lane == 0) { __threadfence(); occ = atomicOr(&q.split_occ[sidx], 0u); }
+        occ = __shfl_sync(0xffffffffu, occ, 0);
+        if (entry < n_hits && ((am >> lane) & 1u) != 0u) {
+            const ShadeLane L = shade_prepare(sc, fr, wk, q, entry);
+            shade_store<COUNT>(sc, fr, q, entry, L, ((occ >> lane) & 1u) != 0u, fan, super);
+        }
+    }
+    if (lane == 0) { __threadfence(); atomicAdd(&cnt->ft[1].done, 1u); }
+}
+
+// k_shade_packet with fused item scheduling: one launch shades, traces and stores every queued hit.
+template <bool COUNT>
+__global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
+k_shade_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
+{
+    __shared__ PacketStack stacks[kQueueThreads / 32];
+    PacketStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n = cnt->n_hits;
+    const uint32_t total_packets = (n + 31u) >> 5;
+    const bool shadows = fr.s.compute_shadows && fr.s.shading_method == RT_SHADING;
+    TraceCounters tc = zero_counters();
+    TraceCounters fan = zero_counters();
+    unsigned overflow = 0;
+    bool more = true;
+    uint32_t my_packets = 0;                                                    // packets this warp completed, reported once (one hot atomic less per packet)
+    unsigned backoff = 250u;
+    const uint32_t per_round = 32u * gridDim.x * (kQueueThreads / 32);          // queue entries the grid's warps claim in one round of claims
+    uint32_t rem = n / per_round;                                               // packets per warp still unclaimed, as of this warp's last claim
+    for (;;) {
+        uint4 item;
+        const int got = (shadows && tune.packet_rounds > 0) ? fq_take(q, cnt, 1, !more, item) : 0;
+        if (got == 1) {
+            shade_item_fused<COUNT>(sc, fr, wk, q, cnt, super, fq_budget(tune.item_rounds, more ? rem : 0u), K, item, n, tc, fan, overflow);
+            backoff = 250u;
+            continue;
+        }
+        if (!more) {
+            if (got == 2) continue;                                             // items are queued, other warps were faster: try again
+            // no packet left to claim and no item queued right now.  Most warps leave: late items (emitted by the packets
+            // and items still running) are served by those running warps themselves and by the PARKED warps -- the CTAs
+            // with the lowest indices, about one per SM -- which poll the queue, backing off, until everything is complete.
+            if (!(shadows && tune.packet_rounds > 0) || blockIdx.x >= kParkCtas) break;
+            bool done = false;
+            if (lane == 0) done = fq_all_done(&cnt->ft[1], total_packets);
+            if (__shfl_sync(0xffffffffu, done ? 1 : 0, 0)) break;
+            __nanosleep(backoff);
+            backoff = min(backoff * 2u, 4000u);
+            continue;
+        }
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cnt->next_shade, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) {
+            more = false;
+            if (lane == 0 && my_packets) { __threadfence(); atomicAdd(&cnt->ft[1].packets_done, my_packets); }
+            continue;
+        }
+        const uint32_t entry = base + lane;
+        const bool valid = entry < n;
+        rem = (n - base) / per_round;
+        ShadeLane L;
+        L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
+        if (valid) L = shade_prepare(sc, fr, wk, q, entry);
+        bool occluded = false, deferred = false;
+        if (shadows) {
+            bool active = valid && L.rt;
+            const V3 so = L.p + 1.0e-4f * L.nrm;                               // Renderer::EPSILON, renderer.h:23
+            const V3 sd = active ? normalize(fr.light - L.p) : v3(0, 0, 1);
+            const float dist2 = length2(L.p - fr.light);
+            const float t_lim = (sqrtf(dist2) + 4.0e-4f) * 1.0001f;
+            HitRec unused;
+            unsigned rounds = 0;
+            const unsigned long long t0 = COUNT ? global_ns() : 0ull;
+            const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
+                                                            fq_budget(tune.packet_rounds, rem), rounds);
+            __syncwarp();
+            if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
+            if (!finished) {
+                const unsigned dm = __ballot_sync(0xffffffffu, active);
+                uint32_t sidx = 0xffffffffu;
+                if (lane == 0) {
+                    sidx = atomicAdd(&cnt->n_split, 1u);
+                    if (sidx < q.split_capacity) { q.split_base[sidx] = base; q.split_active[sidx] = dm; q.split_occ[sidx] = 0u; __threadfence(); }
+                }
+                sidx = __shfl_sync(0xffffffffu, sidx, 0);
+                if (sidx < q.split_capacity && fq_emit(q, cnt, 1, K, sidx, 0u, true)) deferred = active;   // the record's last item stores these pixels
+                else {
+                    const bool before = occluded;                              // no room: finish here, from the root
+                    packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds);
+                    occluded = occluded || before;
+                    __syncwarp();
+                }
+            }
+        }
+        if (valid && !deferred) shade_store<COUNT>(sc, fr, q, entry, L, occluded, fan, super);
+        ++my_packets;
+    }
+    shade_epilogue<COUNT>(cnt, tc, fan, overflow);
+}
+
+// The slot records (or miss colour) of one split primary record once all its items have completed (as k_primary_finish).
+RT_DEV void primary_finish_record(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, uint32_t* super, uint32_t sidx,
+                                  uint32_t total)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t am = __ldcg(&q.split_active[sidx]);                        // written by another SM during this launch: not through L1
+    const uint32_t slot = __ldcg(&q.split_base[sidx]) + lane;
+    if ((am >> lane) & 1u) {
+        const unsigned long long key = atomicMin(q.split_best + (size_t)sidx * 32u + lane, kNoHitKey);   // a coherent read
+        int px = 0, py = 0;
+        V3 o, d;
+        slot_pixel(wk, fr, slot, px, py);
+        primary_ray(fr, px, py, o, d);
+        bool hit = false;
+        float gated_t = -1.0f;                                                 // a BVH hit with 0 < t <= min_t, see k_primary_shapes
+        if (key != kNoHitKey) {
+            const uint32_t tri = (uint32_t)sc.leaf_of[(uint32_t)key];
+            const rt_f4* tp = sc.tris + 3 * (size_t)tri;
+            float t, u, v;
+            if (tri_test(RT_LDG4(tp), RT_LDG4(tp + 1), RT_LDG4(tp + 2), o, -d, t, u, v)) {
+                if (t > 0.1f) {                                                // min_t, renderer.cpp:1039
+                    hit = true;
+                    q.slot_tri[slot] = (int32_t)tri; q.slot_t[slot] = t; q.slot_u[slot] = u; q.slot_v[slot] = v;
+                } else if (t > 0.0f)
+                    gated_t = t;
+            }
+        }
+        if (!hit) {
+            q.slot_tri[slot] = -1;
+            if (sc.n_shapes > 0) q.slot_t[slot] = gated_t;
+            super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+        }
+    } else if (slot < total)
+        q.slot_tri[slot] = -1;                                                 // slot without a ray
+}
+
+template <bool COUNT>
+RT_DEV void primary_item_fused(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, ChunkCounters* cnt, uint32_t* super,
+                               int item_budget, PacketStack& K, const uint4 item, uint32_t total, TraceCounters& tc, unsigned& overflow)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t sidx = item.x;
+    if (sidx == 0xffffffffu) return;                                           // a null item (its emission found the sub-queue full): nothing to do
+    const uint32_t base = __ldcg(&q.split_base[sidx]);
+    const uint32_t slot = base + lane;
+    const bool active = ((__ldcg(&q.split_active[sidx]) >> lane) & 1u) != 0u;
+    int px = 0, py = 0;
+    V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
+    if (active) { slot_pixel(wk, fr, slot, px, py); primary_ray(fr, px, py, o, d); }
+    unsigned long long* mine = q.split_best + (size_t)sidx * 32u + lane;
+    const unsigned long long seen = *((volatile unsigned long long*)mine);
+    const float t_start = seen == kNoHitKey ? INFINITY : __uint_as_float((uint32_t)(seen >> 32));
+    const int32_t orig_start = seen == kNoHitKey ? 0x7fffffff : (int32_t)(uint32_t)seen;
+    HitRec best;
+    bool occ, live = active;
+    unsigned rounds = 0;
+    const int budget = item.w + 1u < kFusedGenerations ? item_budget : 0;
+    const bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start,
+                                                     nullptr, q.split_best + (size_t)sidx * 32u);
+    __syncwarp();
+    if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
+    if (!finished && !fq_emit(q, cnt, 0, K, sidx, item.w + 1u, false)) {
+        // no room: finish the item here (from its cell again, now pruned by what it has just found)
+        const unsigned long long now = *((volatile unsigned long long*)mine);
+        const float t2 = now == kNoHitKey ? INFINITY : __uint_as_float((uint32_t)(now >> 32));
+        const int32_t o2 = now == kNoHitKey ? 0x7fffffff : (int32_t)(uint32_t)now;
+        live = active;
+        packet_trace<false, COUNT>(sc, K, live, o, d, t2, o, 0.0f, best, occ, tc, overflow, 0, rounds, item.y, item.z, o2, nullptr,
+                                   q.split_best + (size_t)sidx * 32u);
+        __syncwarp();
+        if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
+    }
+    __threadfence();                                                           // this lane's atomicMin before the pending count drops
+    __syncwarp();
+    uint32_t left = 0;
+    if (lane == 0) left = atomicSub(&q.split_pending[sidx], 1u);
+    left = __shfl_sync(0xffffffffu, left, 0);
+    if (left == 1u) {
+        __threadfence();
+        primary_finish_record(sc, fr, wk, q, super, sidx, total);
+    }
+    if (lane == 0) { __threadfence(); atomicAdd(&cnt->ft[0].done, 1u); }
+}
+
+// k_primary_packet with fused item scheduling.
+template <bool COUNT>
+__global__ void RTB_PRIMARY_BOUNDS
+k_primary_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
+{
+    __shared__ PacketStack stacks[kPrimaryThreads / 32];
+    PacketStack& K = stacks[threadIdx.x >> 5];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t pps = (uint32_t)wk.patches_per_side;
+    const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);
+    const uint32_t total_packets = total >> 5;                                  // a tile's slots are a multiple of 64
+    TraceCounters tc = zero_counters();
+    unsigned overflow = 0;
+    uint32_t traced = 0;                                                        // lane 0: rays of the packets this warp traced
+    uint32_t nxt = 0;                                                           // the packet claimed for the NEXT iteration (its atomic's round trip is hidden)
+    if (lane == 0) nxt = atomicAdd(&cnt->next_patch, 32u);
+    bool more = true;
+    uint32_t my_packets = 0;                                                    // packets this warp completed, reported once
+    unsigned backoff = 250u;
+    const uint32_t per_round = 32u * gridDim.x * (kPrimaryThreads / 32);        // ray slots the grid's warps claim in one round of claims
+    uint32_t rem = total / per_round;                                           // packets per warp still unclaimed, as of this warp's last claim
+    for (;;) {
+        uint4 item;
+        const int got = tune.primary_rounds > 0 ? fq_take(q, cnt, 0, !more, item) : 0;
+        if (got == 1) {
+            primary_item_fused<COUNT>(sc, fr, wk, q, cnt, super, fq_budget(tune.item_rounds, more ? rem : 0u), K, item, total, tc, overflow);
+            backoff = 250u;
+            continue;
+        }
+        if (!more) {
+            if (got == 2) continue;                                             // items are queued, other warps were faster: try again
+            if (tune.primary_rounds <= 0 || blockIdx.x >= kParkCtas) break;     // see k_shade_fused: only the parked warps wait for late items
+            bool done = false;
+            if (lane == 0) done = fq_all_done(&cnt->ft[0], total_packets);
+            if (__shfl_sync(0xffffffffu, done ? 1 : 0, 0)) break;
+            __nanosleep(backoff);
+            backoff = min(backoff * 2u, 4000u);
+            continue;
+        }
+        const uint32_t base = __shfl_sync(0xffffffffu, nxt, 0);
+        if (base >= total) {
+            more = false;
+            if (lane == 0 && my_packets && tune.primary_rounds > 0) { __threadfence(); atomicAdd(&cnt->ft[0].packets_done, my_packets); }
+            continue;
+        }
+        if (lane == 0) nxt = atomicAdd(&cnt->next_patch, 32u);
+        rem = (total - base) / per_round;
+        const uint32_t slot = base + lane;
+        int px = 0, py = 0;
+        const bool active = slot_pixel(wk, fr, slot, px, py);
+        V3 o = v3(0, 0, 0), d = v3(0, 0, 1);
+        // a block that lies outside the screen-space bound of the scene misses without a ray being set up
+        const bool inside = active && px >= wk.cull_x0 && px <= wk.cull_x1 && py >= wk.cull_y0 && py <= wk.cull_y1;
+        bool deferred = false;
+        if (__ballot_sync(0xffffffffu, inside) == 0u) {
+            q.slot_tri[slot] = -1;
+            if (active) {
+                if (miss_needs_ray(fr)) primary_ray(fr, px, py, o, d);
+                super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+            }
+        } else {
+            if (active) primary_ray(fr, px, py, o, d);
+            traced += (uint32_t)__popc(__ballot_sync(0xffffffffu, active));
+            HitRec best;
+            bool occ, live = active;
+            unsigned rounds = 0;
+            const unsigned long long t0 = COUNT ? global_ns() : 0ull;
+            const bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow,
+                                                             fq_budget(tune.primary_rounds, rem), rounds);
+            __syncwarp();
+            if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
+            if (!finished) {
+                // out of rounds: the closest hits so far go to a split record, every unvisited cell becomes a work item
+                const unsigned am = __ballot_sync(0xffffffffu, active);
+                uint32_t sidx = 0xffffffffu;
+                if (lane == 0) sidx = atomicAdd(&cnt->p_split, 1u);
+                sidx = __shfl_sync(0xffffffffu, sidx, 0);
+                if (sidx < q.split_capacity) {
+                    if (lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = am; }
+                    q.split_best[(size_t)sidx * 32u + lane] = (active && best.tri >= 0) ? closest_key(best.t, sc.orig[best.tri]) : kNoHitKey;
+                    __threadfence();
+                    __syncwarp();
+                    deferred = fq_emit(q, cnt, 0, K, sidx, 0u, true);           // the record's last item writes these slots
+                }
+                if (!deferred) {
+                    live = active;                                             // no room: trace it here, from the root
+                    packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
+                    __syncwarp();
+                }
+            }
+            if (!deferred) {
+                const bool hit = active && best.tri >= 0 && best.t > 0.1f;        // t > 0 (bvh.h:247) and min_t (renderer.cpp:1039)
+                q.slot_tri[slot] = hit ? best.tri : -1;
+                if (hit) { q.slot_t[slot] = best.t; q.slot_u[slot] = best.u; q.slot_v[slot] = best.v; }
+                else if (active) {
+                    if (sc.n_shapes > 0) q.slot_t[slot] = (best.tri >= 0 && best.t > 0.0f) ? best.t : -1.0f;   // see k_primary_shapes
+                    super[(size_t)py * fr.rw + px] = quantise_argb(shade_miss(sc, fr, d));
+                }
+            }
+        }
+        ++my_packets;
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+    if (lane == 0 && traced) atomicAdd(&cnt->traced_primary, (unsigned long long)traced);
+    if (COUNT) flush_work(tc, &cnt->primary_vol, &cnt->primary_tri, &cnt->primary_fetch);
 }
 
 // The tiles that lie outside the screen-space bound of the scene (WorkView::cull_*): every sample is a miss

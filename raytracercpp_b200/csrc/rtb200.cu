@@ -68,6 +68,7 @@ enum Stage { ST_PRIMARY = 0, ST_COMPACT, ST_REFLECT, ST_SHADE, ST_RESOLVE, ST_CO
 struct TimedLaunch {
     int stage;
     cudaEvent_t a, b;
+    const char* label;      // non-null: a single launch timed for RTB200_TRACE only (not added to the stage sums)
 };
 
 // Device copy of a shard's tile list (owned_tiles), uploaded once per (frame size, tile size, shard) and kept.
@@ -94,7 +95,7 @@ constexpr int kMaxLanes = 6;     // ... at most (RT_OPT_LANES)
 
 // The per-frame work buffers of ONE wavefront chunk in flight.
 struct QueueSet {
-    DevBuf<uint32_t> hit_slot, refl_idx, split_base, split_active, split_occ;
+    DevBuf<uint32_t> hit_slot, refl_idx, split_base, split_active, split_occ, item_ready, split_pending;
     DevBuf<unsigned long long> split_best, refl_cnt;
     DevBuf<uint4> items;
     DevBuf<int32_t> tri;
@@ -102,6 +103,7 @@ struct QueueSet {
     void release()
     {
         hit_slot.release(); refl_idx.release(); split_base.release(); split_active.release(); split_occ.release(); split_best.release();
+        item_ready.release(); split_pending.release();
         refl_cnt.release(); items.release(); tri.release(); t.release(); u.release(); v.release(); refl_rgb.release();
     }
 };
@@ -159,13 +161,14 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, -256, -64, -256};
+    Tuning tune{16, 16, 8, 1, -256, -64, -256, 0};
+    uint32_t frame_serial = 0;           // tags the ready flags of the fused item queues: (serial << 2) | stage
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
     uint32_t* h_frame = nullptr;         // pinned staging buffer of rt_frame_to_host / rt_render
     size_t h_frame_cap = 0;
     cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per slice of that copy
-    int grids[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
+    int grids[2][11] = {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
     int grid_intersect = 0, grid_occluded = 0;           // the same for the batch kernels (per context: its device's occupancy)
     bool opt_screen_cull = true;
     int opt_lanes = kLanes;
@@ -217,15 +220,21 @@ struct ScopedTimer {
     RtContext* ctx;
     TimedLaunch tl;
     cudaStream_t stream;
-    ScopedTimer(RtContext* c, int stage, cudaStream_t st = nullptr) : ctx(c), stream(st ? st : c->stream)
+    bool on;
+    ScopedTimer(RtContext* c, int stage, cudaStream_t st = nullptr, const char* label = nullptr) : ctx(c), stream(st ? st : c->stream)
     {
+        static const bool trace = getenv("RTB200_TRACE") != nullptr;
+        on = label == nullptr || trace;
+        if (!on) return;
         tl.stage = stage;
+        tl.label = label;
         tl.a = next_event(c);
         tl.b = next_event(c);
         cudaEventRecord(tl.a, stream);
     }
     ~ScopedTimer()
     {
+        if (!on) return;
         cudaEventRecord(tl.b, stream);
         ctx->timed.push_back(tl);
     }
@@ -554,6 +563,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         if (value == 0 || value < -(1 << 30) || value > (1 << 30)) return fail(ctx, RT_ERR_INVALID, "item rounds %lld", (long long)value);
         ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
+    case RT_OPT_FUSED_ITEMS: ctx->tune.fused = value != 0; return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
     case RT_OPT_LANES:
         if (value < 0 || value > kMaxLanes) return fail(ctx, RT_ERR_INVALID, "lanes %lld outside [0,%d]", (long long)value, kMaxLanes);
@@ -849,6 +859,14 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     tune.packet_rounds = budget(ctx->tune.packet_rounds);
     tune.item_rounds = budget(ctx->tune.item_rounds);
     tune.primary_rounds = ctx->tune.primary_rounds >= 0 ? ctx->tune.primary_rounds : (short_launch ? std::max(1, -ctx->tune.primary_rounds / 2) : 0);
+    if (tune.fused && tune.packets) {
+        // fused item scheduling: the values are the LARGEST budgets -- a packet's own budget shrinks as the launch runs out
+        // of packets (fq_budget, kernels.cuh) --, so nothing depends on the length of the launch
+        auto largest = [](int32_t v) { return v >= 0 ? v : -v; };
+        tune.packet_rounds = largest(ctx->tune.packet_rounds);
+        tune.item_rounds = largest(ctx->tune.item_rounds);
+        tune.primary_rounds = largest(ctx->tune.primary_rounds);
+    }
     const bool tail = tune.packets && tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
     const bool psplit = tune.packets && tune.primary_rounds > 0;
     // split records and work items of the packets that run out of rounds; a packet that finds them full is finished in
@@ -860,6 +878,13 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         if (tail || psplit) {
             RT_CUDA(ctx, Q.split_base.ensure(split_cap)); RT_CUDA(ctx, Q.split_active.ensure(split_cap)); RT_CUDA(ctx, Q.split_occ.ensure(split_cap));
             RT_CUDA(ctx, Q.items.ensure(item_cap * kItemPasses));
+            if (tune.fused) {
+                if (Q.item_ready.n < item_cap * kItemPasses) {                   // fresh flags must not look like a tag
+                    RT_CUDA(ctx, Q.item_ready.ensure(item_cap * kItemPasses));
+                    RT_CUDA(ctx, cudaMemsetAsync(Q.item_ready.p, 0, Q.item_ready.n * sizeof(uint32_t), ctx->stream));
+                }
+                RT_CUDA(ctx, Q.split_pending.ensure(split_cap));
+            }
         }
         if (psplit) RT_CUDA(ctx, Q.split_best.ensure(split_cap * 32));
         RT_CUDA(ctx, Q.hit_slot.ensure(qcap)); RT_CUDA(ctx, Q.tri.ensure(qcap)); RT_CUDA(ctx, Q.t.ensure(qcap));
@@ -880,6 +905,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         q.split_base = Q.split_base.p; q.split_active = Q.split_active.p; q.split_occ = Q.split_occ.p;
         q.split_best = Q.split_best.p;
         q.items = Q.items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
+        q.item_ready = Q.item_ready.p; q.split_pending = Q.split_pending.p; q.tag = 0;
         q.refl_idx = Q.refl_idx.p; q.refl_rgb = Q.refl_rgb.p; q.refl_cnt = Q.refl_cnt.p; q.capacity = (uint32_t)qcap;
     }
     for (int l = 1; l < n_lanes; l++) {
@@ -899,7 +925,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
 
     const bool count = ctx->opt_count_work;
-    int (&grids)[2][9] = ctx->grids;                                           // per context: its device's occupancy
+    int (&grids)[2][11] = ctx->grids;                                           // per context: its device's occupancy
     if (!grids[count][0]) {
         grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
         grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
@@ -907,12 +933,17 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         grids[count][7] = grid_for(ctx, count ? (const void*)k_primary_items<true> : (const void*)k_primary_items<false>, kPrimaryThreads);
         grids[count][8] = grid_for(ctx, (const void*)k_primary_finish, kPrimaryThreads);
         grids[count][6] = grid_for(ctx, count ? (const void*)k_shade_finish<true> : (const void*)k_shade_finish<false>, kQueueThreads);
+        grids[count][9] = grid_for(ctx, count ? (const void*)k_primary_fused<true> : (const void*)k_primary_fused<false>, kPrimaryThreads);
+        grids[count][10] = grid_for(ctx, count ? (const void*)k_shade_fused<true> : (const void*)k_shade_fused<false>, kQueueThreads);
         grids[count][0] = grid_for(ctx, count ? (const void*)k_primary<true> : (const void*)k_primary<false>, kPrimaryThreads);
         grids[count][1] = grid_for(ctx, count ? (const void*)k_reflect<true> : (const void*)k_reflect<false>, kQueueThreads);
         grids[count][2] = grid_for(ctx, count ? (const void*)k_shade<true> : (const void*)k_shade<false>, kQueueThreads);
     }
     const int grid_primary = grids[count][0], grid_reflect = grids[count][1], grid_shade = grids[count][2];
     const int grid_pp = grids[count][3], grid_sp = grids[count][4], grid_items = grids[count][5], grid_finish = grids[count][6], grid_pitems = grids[count][7], grid_pfinish = grids[count][8];
+    // A fused kernel's CTAs all stay until the launch's last work item has completed, so two lanes' kernels only run side by
+    // side if each takes its share of the SMs' CTA slots from the start: the persistent grid is divided among the lanes.
+    const int grid_pf = std::max(ctx->sm_count, grids[count][9] / n_lanes), grid_sf = std::max(ctx->sm_count, grids[count][10] / n_lanes);
     if (n_lanes > 1) {                                                         // the other lanes start after everything enqueued so far
         RT_CUDA(ctx, cudaEventRecord(ctx->lane_fork, main_stream));
         for (int l = 1; l < n_lanes; l++) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
@@ -926,7 +957,18 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         const QueueView& q = qv[lane];
         {
             ScopedTimer tm(ctx, ST_PRIMARY, st);
+            auto next_tag = [&]() { if (++ctx->frame_serial == 0u) ctx->frame_serial = 1u; return ctx->frame_serial; };
+            if (tune.packets && tune.fused) {
+                // one launch: the packet kernel's warps also consume the work items of the packets they split
+                QueueView qf = q;
+                qf.tag = next_tag();
+                ScopedTimer t1(ctx, ST_PRIMARY, st, "  k_primary_fused");
+                if (count) k_primary_fused<true><<<grid_pf, kPrimaryThreads, 0, st>>>(sc, fr, wk, qf, cnt, super, tune);
+                else k_primary_fused<false><<<grid_pf, kPrimaryThreads, 0, st>>>(sc, fr, wk, qf, cnt, super, tune);
+                launches++;
+            } else {
             if (tune.packets) {
+                ScopedTimer t1(ctx, ST_PRIMARY, st, "  k_primary_packet");
                 if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
                 else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
@@ -934,11 +976,13 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             launches++;
             if (psplit) {
                 for (int pass = 0; pass < kItemPasses; pass++) {
+                    ScopedTimer t1(ctx, ST_PRIMARY, st, "  k_primary_items");
                     if (count) k_primary_items<true><<<grid_pitems, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                     else k_primary_items<false><<<grid_pitems, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                 }
                 k_primary_finish<<<grid_pfinish, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
                 launches += kItemPasses + 1;
+            }
             }
             if (has_shapes) {                                                  // trace_ray's loop over the analytic shapes
                 const uint32_t slots = (wk.tile_end - wk.tile_begin) * (uint32_t)px_per_tile;
@@ -961,7 +1005,17 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         }
         {
             ScopedTimer tm(ctx, ST_SHADE, st);
+            if (tune.packets && tune.fused) {
+                QueueView qf = q;
+                if (++ctx->frame_serial == 0u) ctx->frame_serial = 1u;
+                qf.tag = ctx->frame_serial;
+                ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_fused");
+                if (count) k_shade_fused<true><<<grid_sf, kQueueThreads, 0, st>>>(sc, fr, wk, qf, cnt, super, tune);
+                else k_shade_fused<false><<<grid_sf, kQueueThreads, 0, st>>>(sc, fr, wk, qf, cnt, super, tune);
+                launches++;
+            } else {
             if (tune.packets) {
+                ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_packet");
                 if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
                 else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
@@ -969,12 +1023,14 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             launches++;
             if (tail) {
                 for (int pass = 0; pass < kItemPasses; pass++) {
+                    ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_items");
                     if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                     else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                 }
                 if (count) k_shade_finish<true><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
                 else k_shade_finish<false><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
                 launches += kItemPasses + 1;
+            }
             }
         }
     }
@@ -1066,7 +1122,8 @@ int rt_render_device_end(RtContext* ctx, RtRenderStats* stats)
     for (const TimedLaunch& tl : ctx->timed) {
         float ms = 0;
         cudaEventElapsedTime(&ms, tl.a, tl.b);
-        if (trace) fprintf(stderr, "[rtb200] %s %.3f ms\n", tl.stage == ST_PRIMARY ? "k_primary" : tl.stage == ST_COMPACT ? "k_compact" : tl.stage == ST_REFLECT ? "k_reflect" : tl.stage == ST_SHADE ? "k_shade" : "k_resolve", ms);
+        if (trace) fprintf(stderr, "[rtb200] %s %.3f ms\n", tl.label ? tl.label : tl.stage == ST_PRIMARY ? "k_primary" : tl.stage == ST_COMPACT ? "k_compact" : tl.stage == ST_REFLECT ? "k_reflect" : tl.stage == ST_SHADE ? "k_shade" : "k_resolve", ms);
+        if (tl.label) continue;
         if (tl.stage == ST_PRIMARY) rs.trace_primary_ms += ms;
         else if (tl.stage == ST_COMPACT) rs.compact_ms += ms;
         else if (tl.stage == ST_REFLECT) rs.reflect_ms += ms;

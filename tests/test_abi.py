@@ -74,3 +74,23 @@ def test_tile_ownership_is_a_partition(lib):
             counts = [lib.rt_tile_count(ctypes.byref(s), tile, mod, r) for r in range(mod)]
             assert sum(counts) == total and max(counts) - min(counts) <= 2
     assert lib.rt_tile_count(ctypes.byref(s), 64, 2, 2) == api.RT_ERR_INVALID
+
+
+def test_adapter_compiles_against_the_reference_headers(tmp_path):
+    """include/rtb200_renderer.hpp with the reference's REAL Triangle / Materials / Image / Transform / Point / Vector
+    (headers included from /root/reference/tp2 where they lie; Qt's QImage from the oracle's shim): every templated
+    member is instantiated with them.  CPU-only object file; needs the mounted reference (this container)."""
+    import subprocess
+    ref = Path("/root/reference/tp2")
+    if not (ref / "projets" / "triangle.h").exists():
+        pytest.skip("/root/reference is not mounted here")
+    obj = tmp_path / "adapter_reference_types.o"
+    inc = [ROOT / "include", ROOT / "oracle" / "qt_shim", ref / "src", ref / "projets", ref / "projets" / "utils", ref / "projets" / "renderer",
+           ref / "projets" / "scene"]
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-c", "-o", str(obj), str(ROOT / "tests" / "adapter_reference_types.cpp")] + [f"-I{p}" for p in inc]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    syms = subprocess.run(["nm", "-C", str(obj)], capture_output=True, text=True, check=True).stdout
+    for member in ("set_triangles<Triangle>", "set_materials<Materials>", "set_ao_map<Image>", "set_skybox<Image>", "set_camera_transform<Transform>",
+                   "set_object_transform<Transform>", "set_light_position<Point>", "add_plane<Point, Vector>", "copy_to<QImage>"):
+        assert f"rtb200::Renderer::{member}" in syms, member

@@ -274,16 +274,20 @@ def test_packet_and_single_ray_kernels_agree(cuda_lib, oracle, robot, name):
     common.assert_image_close(out[0][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name)
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
-def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name):
+def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name, fused):
     """RT_OPT_PACKET_ROUNDS / RT_OPT_ITEM_ROUNDS split shadow packets that run out of rounds into work items (one per
     unvisited cell) that other warps trace for the same rays; answers are merged and the pixels stored by k_shade_finish.
     With budgets of 1..20 rounds nearly every packet is split, items are split again, and on the larger frames the item
-    regions overflow (finish-in-place path): the frames must equal the unlimited-packet frame bit for bit."""
+    regions overflow (finish-in-place path): the frames must equal the unlimited-packet frame bit for bit.
+    fused = 0 (the default): six item passes and a finish kernel per stage; fused = 1 (RT_OPT_FUSED_ITEMS): the packet kernel's own
+    warps consume the items through ticket queues and the last item of a record stores its pixels."""
     kw, mats, tex = common.config_table(robot["materials"])[name]
     frames = {}
     for rounds, item_rounds in ((0, 64), (1, 1), (3, 2), (20, 5), (2, 64)):
         r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+        r.ctx.set_option(api.RT_OPT_FUSED_ITEMS, fused)
         r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, rounds)
         r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, rounds)                 # primary packets: closest hit merged with atomicMin
         r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, item_rounds)
@@ -297,7 +301,10 @@ def test_split_shadow_packets_never_change_a_frame(cuda_lib, oracle, robot, name
         assert np.array_equal(img, base[0]), key
         for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
             assert st[k] == base[1][k]
-        assert st["kernel_launches"] >= base[1]["kernel_launches"] + 14     # (6 item passes + finish) for primary and for shadow packets, per chunk
+        if fused:
+            assert st["kernel_launches"] == base[1]["kernel_launches"]         # one launch per stage whatever is split
+        else:
+            assert st["kernel_launches"] >= base[1]["kernel_launches"] + 14     # (6 item passes + finish) for primary and for shadow packets, per chunk
     common.assert_image_close(frames[(1, 1)][0], common.oracle_image(oracle, robot, kw, mats, tex), what=name + " through split packets")
 
 
@@ -312,8 +319,9 @@ def test_split_primary_packets_keep_ids_and_ties(cuda_lib, oracle):
     scene = dict(xyz9=soup, uv6=None, mat=np.repeat(perm, 40).astype(np.int32))
     kw = dict(image_width=128, image_height=72, compute_shadows=0)
     out = []
-    for rounds in (0, 1, 2):
+    for rounds, fused in ((0, 1), (1, 1), (2, 1), (1, 0), (2, 0)):
         r = common.product_renderer(cuda_lib, scene, kw, mats, {})
+        r.ctx.set_option(api.RT_OPT_FUSED_ITEMS, fused)
         r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, rounds)
         r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, 1)
         r.ray_trace()
@@ -373,6 +381,7 @@ def test_hair_scene_vs_oracle(cuda_lib, oracle):
     for g, w in zip(got, ref):
         assert np.array_equal(g, w)
     for opts in ({api.RT_OPT_PACKETS: 0}, {api.RT_OPT_PACKET_ROUNDS: 8, api.RT_OPT_PRIMARY_ROUNDS: 8, api.RT_OPT_ITEM_ROUNDS: 4},
+                 {api.RT_OPT_PACKET_ROUNDS: 8, api.RT_OPT_PRIMARY_ROUNDS: 8, api.RT_OPT_ITEM_ROUNDS: 4, api.RT_OPT_FUSED_ITEMS: 1},
                  {api.RT_OPT_SCREEN_CULL: 0}):
         for k, v in opts.items():
             r.ctx.set_option(k, v)
@@ -381,6 +390,7 @@ def test_hair_scene_vs_oracle(cuda_lib, oracle):
         r.ctx.set_option(api.RT_OPT_PACKETS, 1)
         r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -64)
         r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1)
+        r.ctx.set_option(api.RT_OPT_FUSED_ITEMS, 0)
     r.close()
 
 
@@ -502,7 +512,7 @@ def test_hair_fullsize_band(cuda_lib, oracle, golden_fullsize):
     for g, w in zip(r.ctx.intersect(o, d), oracle.bvh(xyz9, 12, 40).intersect(o, d)):
         assert np.array_equal(g, w)
     # scheduling knobs leave the 4K frame bit-identical
-    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1)):
+    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1), (api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(r.get_image(), img), opt
@@ -556,9 +566,14 @@ def test_full_size_properties(cuda_lib, oracle, big_sphere):
     assert np.array_equal(frame.cpu().numpy().view(np.uint32), full) and total_hits == st.primary_hits
     bg = 0xff000000 | (135 << 16) | (206 << 8) | 235
     assert full[0, 0] == bg and full[1080, 1920] != bg
-    # (3) idempotence: same frame twice
+    # (3) idempotence: same frame twice; and the scheduling knobs at full size (item passes as separate launches, 4 chunks in flight)
     r.ray_trace()
     assert np.array_equal(full, r.get_image())
+    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1)):
+        r.ctx.set_option(opt, val)
+        r.ray_trace()
+        assert np.array_equal(full, r.get_image()), opt
+        r.ctx.set_option(opt, back)
     # (4) a band of the frame against the oracle (the oracle needs ~10 s for these rows at this size)
     orc = common.oracle_renderer(oracle, scene, kw, mats, {})
     rows = list(range(4000, 4640, 64))
