@@ -182,7 +182,7 @@ enum {
        one long packet shows in the launch time.  Results do not depend on any of them. */
     RT_OPT_PACKET_ROUNDS = 7, /* shadow packets (default -256)                                                           */
     RT_OPT_PRIMARY_ROUNDS = 11,/* primary packets (default -256; negative additionally means: not split in long launches) */
-    RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -64; 0 is invalid)                 */
+    RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -16; 0 is invalid)                 */
     RT_OPT_FUSED_ITEMS = 12,  /* 0 (default): the work items of split packets are traced generation by generation in separate
                                  launches (six item passes and a finish kernel per stage); 1: the packet kernels consume the
                                  items themselves through 32 ticket queues, the last item of a record stores its pixels -- one

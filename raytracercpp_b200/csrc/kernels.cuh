@@ -1129,7 +1129,9 @@ RT_DEV bool fq_all_done(const FusedTotals* ft, uint32_t total_packets)
 // emitted around that time (guided self-scheduling): early in the launch a packet may run long -- there is plenty of other
 // work to keep the SMs busy meanwhile --, near the end it is cut after a few rounds so that its cells spread over the
 // warps that are running out of packets.  The launch's tail is about one budget long instead of one whole packet.
-RT_DEV int fq_budget(int max_rounds, uint32_t rem) { return max_rounds > 0 ? (int)min((uint32_t)max_rounds, 8u + 8u * rem) : 0; }
+// (A budget that shrinks steadily over the launch -- 8 + 8 * rem -- split half of all packets and made the launch 5x slower:
+// an item re-does the shading set-up of its 32 rays for a few rounds of traversal.  Only the last round of claims is cut short.)
+RT_DEV int fq_budget(int max_rounds, uint32_t rem) { return max_rounds > 0 ? (rem == 0u ? max(8, max_rounds / 4) : max_rounds) : 0; }
 
 RT_DEV uint32_t fq_home() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % (uint32_t)kSubQueues; }
 RT_DEV uint32_t fq_sub_capacity(const QueueView& q) { return q.item_capacity * (uint32_t)kItemPasses / (uint32_t)kSubQueues; }

@@ -161,7 +161,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, -256, -64, -256, 0};
+    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0};
     uint32_t frame_serial = 0;           // tags the ready flags of the fused item queues: (serial << 2) | stage
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
@@ -844,8 +844,14 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     // in two for that purpose.
     const int n_lanes = (ctx->opt_lanes > 1 && tune_packets_hint(ctx)) ? (int)std::min<size_t>((size_t)ctx->opt_lanes, std::max<size_t>(tiles.size(), 1)) : 1;
     if (n_lanes > 1 && tiles.size() <= (size_t)tiles_per_chunk * (n_lanes - 1)) tiles_per_chunk = (uint32_t)((tiles.size() + n_lanes - 1) / n_lanes);
-    const uint32_t n_chunks = (uint32_t)((tiles.size() + tiles_per_chunk - 1) / tiles_per_chunk);
-    const size_t qcap = (size_t)std::min<uint64_t>((uint64_t)tiles_per_chunk, tiles.size()) * px_per_tile;
+    // chunk c covers tiles [bounds[c], bounds[c + 1])
+    std::vector<uint32_t> bounds;
+    for (size_t b = 0; b < tiles.size(); b += tiles_per_chunk) bounds.push_back((uint32_t)b);
+    bounds.push_back((uint32_t)tiles.size());
+    const uint32_t n_chunks = (uint32_t)bounds.size() - 1u;
+    uint32_t largest_chunk = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) largest_chunk = std::max(largest_chunk, bounds[c + 1] - bounds[c]);
+    const size_t qcap = (size_t)largest_chunk * px_per_tile;
 
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
     // Round budgets.  A launch is SHORT when it has fewer than 256 packets per resident warp: one long packet then shows in
@@ -949,8 +955,8 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         for (int l = 1; l < n_lanes; l++) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
     }
     for (uint32_t c = 0; c < n_chunks; c++) {
-        wk.tile_begin = c * tiles_per_chunk;
-        wk.tile_end = (uint32_t)std::min<size_t>(tiles.size(), (size_t)(c + 1) * tiles_per_chunk);
+        wk.tile_begin = bounds[c];
+        wk.tile_end = bounds[c + 1];
         ChunkCounters* cnt = ctx->d_counters.p + c;
         const int lane = (int)(c % (uint32_t)n_lanes);
         st = lane ? ctx->lane_stream[lane] : main_stream;

@@ -388,7 +388,7 @@ def test_hair_scene_vs_oracle(cuda_lib, oracle):
         r.ray_trace()
         assert np.array_equal(r.get_image(), img), opts
         r.ctx.set_option(api.RT_OPT_PACKETS, 1)
-        r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -64)
+        r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -16)
         r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1)
         r.ctx.set_option(api.RT_OPT_FUSED_ITEMS, 0)
     r.close()
