@@ -188,6 +188,11 @@ enum {
                                  items themselves through 32 ticket queues, the last item of a record stores its pixels -- one
                                  launch per stage, but items of a record run concurrently and prune each other less: measured
                                  slower on B200, kept for experiments.  Results do not depend on it             */
+    RT_OPT_TOP_TABLE = 13,    /* 1: every CTA of the packet kernels loads the child blocks of the first tree levels (<= 72 records,
+                                 4.6 KB) into shared memory with one bulk asynchronous copy (cp.async.bulk + mbarrier) and takes
+                                 those cells from there instead of fetching them; 0 (default): they are fetched like any other
+                                 cell -- they never leave the L1, and the extra address select costs 2 % of the frame on B200
+                                 (measured).  Results do not depend on it                                       */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
     RT_OPT_LANES = 9,         /* wavefront chunks in flight at a time, each on its own stream with its own queues, so one

@@ -301,36 +301,116 @@ RT_DEV float warp_min(float x)
 // slab_entry (rt_device.h) for packets, with a warp-uniform exit between the axis slabs and the diagonal slabs: the
 // rays of a packet mostly agree, so when NO lane survives the three axis slabs the record is dropped without the
 // divergent region a per-lane early return costs.  Same arithmetic, same conservative acceptance.
-RT_DEV float slab_entry_packet(const float4& q0, const float4& q1, const float4& q2, const float4& q3, const SlabRay& sr, float t_limit,
-                               bool active)
+// ORDERED: the staged record holds, per slab, (entry bound, exit bound) for THIS packet -- the lane that staged the
+// float4 swapped the (near, far) pairs of the slabs whose denominator is negative for every ray of the packet -- so the
+// per-slab min/max of the two quotients is not needed: 14 FMA + 2 x 7 running max/min instead of + 14 more min/max.
+template <bool ORDERED>
+RT_DEV float slab_entry_packet(const float4* rec, const SlabRay& sr, float t_limit, bool active, uint32_t& link, uint32_t& meta)
 {
     float tn = -INFINITY, tf = INFINITY;
 #define RT_SLAB(i, NEAR, FAR)                                   \
     {                                                           \
         float a = RT_FMA((NEAR), sr.inv[i], -sr.c[i]);          \
         float b = RT_FMA((FAR), sr.inv[i], -sr.c[i]);           \
-        tn = fmaxf(tn, fminf(a, b));                            \
-        tf = fminf(tf, fmaxf(a, b));                            \
+        if (ORDERED) { tn = fmaxf(tn, a); tf = fminf(tf, b); }  \
+        else { tn = fmaxf(tn, fminf(a, b)); tf = fminf(tf, fmaxf(a, b)); } \
     }
-    RT_SLAB(0, q0.x, q1.w)
-    RT_SLAB(1, q0.y, q2.x)
-    RT_SLAB(2, q0.z, q2.y)
+    const float4 q0 = rec[0];
+    const float2 q1a = *reinterpret_cast<const float2*>(rec + 1);
+    RT_SLAB(0, q0.x, q0.y)
+    RT_SLAB(1, q0.z, q0.w)
+    RT_SLAB(2, q1a.x, q1a.y)
     const float lim = fminf(t_limit, tf) + 2.0f * sr.slack;
     const bool pass = active && (tn <= lim) && !(tf + sr.slack < 0.0f);
     if (__ballot_sync(0xffffffffu, pass) == 0u) return INFINITY;
-    RT_SLAB(3, q0.w, q2.z)
-    RT_SLAB(4, q1.x, q2.w)
-    RT_SLAB(5, q1.y, q3.x)
-    RT_SLAB(6, q1.z, q3.y)
+    const float2 q1b = *(reinterpret_cast<const float2*>(rec + 1) + 1);
+    const float4 q2 = rec[2], q3 = rec[3];
+    RT_SLAB(3, q1b.x, q1b.y)
+    RT_SLAB(4, q2.x, q2.y)
+    RT_SLAB(5, q2.z, q2.w)
+    RT_SLAB(6, q3.x, q3.y)
 #undef RT_SLAB
+    link = f4_bits(q3.z); meta = f4_bits(q3.w);
     const bool ok = pass && (tn <= tf + 2.0f * sr.slack) && (tf + sr.slack >= 0.0f) && (tn - sr.slack <= t_limit);
     return ok ? tn - sr.slack : INFINITY;
 }
 
 RT_DEV uint32_t ld_vol(const unsigned int* p) { return *((const volatile unsigned int*)p); }
 
+// One cell round of a packet: the (<= 8) staged or top-table records at `rec` are tested by every lane for its own ray; a
+// child is entered if ANY lane hits it, with the smallest entry distance of the warp as its sort key (one redux.sync);
+// lane 0 keeps the cell's entries [base, sp) of the shared-memory stack sorted by descending distance, so the nearest is
+// popped first.  (Tried instead: the accepted children kept in registers, one per lane, ranked with a shuffle sweep, stored
+// in parallel and the nearest entered without going through the stack -- +6 % frame time on cfg4: the sweep runs on every
+// cell whereas the insertion costs one short loop per ACCEPTED child, mostly 1-3 per cell.)
+template <bool ORDERED, bool COUNT>
+RT_DEV bool packet_cell(const float4* rec, uint32_t count, const SlabRay& sr, float t_max, bool active, PacketStack& K, int& sp, TraceCounters& tc)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const int base = sp;
+    for (uint32_t k = 0; k < count; k++) {
+        if (COUNT && active) tc.vol_tests++;
+        uint32_t cl = 0u, cm = 0u;
+        const float tn = slab_entry_packet<ORDERED>(rec + 4 * k, sr, t_max, active, cl, cm);
+        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
+        const float tmin = warp_min(tn);
+        if (sp >= RT_STACK_SIZE) return false;
+        if (lane == 0) {                                     // keep [base, sp) sorted by descending entry distance
+            int j = sp;
+            while (j > base && K.t[j - 1] < tmin) {
+                K.t[j] = K.t[j - 1]; K.link[j] = K.link[j - 1]; K.meta[j] = K.meta[j - 1];
+                --j;
+            }
+            K.t[j] = tmin; K.link[j] = cl; K.meta[j] = cm;
+        }
+        ++sp;
+    }
+    return true;
+}
+
+// The top table in shared memory: loaded once per CTA at kernel start with ONE bulk asynchronous copy (cp.async.bulk, the
+// 1-D form of TMA) that completes on an mbarrier; every thread of the CTA waits for it before its first packet.
+struct TopTable {
+    float4 rec[4 * RT_TOP_RECORDS];
+    unsigned long long bar;
+};
+struct NoTopTable {                     // what a kernel instantiated without the top table keeps in shared memory instead
+    unsigned long long bar;
+};
+template <bool TOP> struct TopStorage { typedef TopTable type; };
+template <> struct TopStorage<false> { typedef NoTopTable type; };
+RT_DEV const float4* top_pointer(TopTable& T) { return T.rec; }
+RT_DEV const float4* top_pointer(NoTopTable&) { return nullptr; }
+RT_DEV void load_top_table(const SceneView&, NoTopTable&) {}
+
+RT_DEV void load_top_table(const SceneView& sc, TopTable& T)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&T.bar), dst = (uint32_t)__cvta_generic_to_shared(&T.rec[0]);
+    const uint32_t bytes = (uint32_t)sc.top_n * 64u;
+    if (bytes == 0u) return;                                 // warp-uniform: a kernel argument
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(sc.top), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TOP_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@!p bra TOP_WAIT;\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
+
 // Per-lane inputs: `active`, ray (o, d), t_max (closest: INFINITY; any: light limit).  Outputs: best (closest) or
-// occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory.
+// occluded (any).  For ANY: p / dist2 of the reference predicate.  K points to this warp's stack in shared memory, `top`
+// to the CTA's copy of the top table (null: none).
 // The traversal starts at the root cell, or (start_meta != 0) at the cell / leaf (start_link, start_meta).
 // Returns false when the packet used up `max_rounds` cell/leaf rounds without finishing (max_rounds 0: no limit); the
 // lanes whose `active` is still set then have no result yet, and K.link/meta[0, K.saved) are the cells the packet has
@@ -339,7 +419,7 @@ RT_DEV uint32_t ld_vol(const unsigned int* p) { return *((const volatile unsigne
 // 11 ms of a 17 ms kernel) is SPLIT: each unvisited cell becomes a work item that another warp traces for the same 32
 // rays (k_shade_items), and the answers are merged (any-hit: OR).
 template <bool ANY, bool COUNT>
-RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
+RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, const float4* top, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
                          HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds,
                          uint32_t start_link = 0u, uint32_t start_meta = 0u, int32_t best_orig = 0x7fffffff,
                          const unsigned int* poll_occ = nullptr, const unsigned long long* poll_best = nullptr)
@@ -350,6 +430,26 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
     const V3 md = -d;
     best.tri = -1; best.t = -1.0f; best.u = 1.0f; best.v = 0.0f;
     occluded = false;
+    // Do the packet's rays agree, slab by slab, on the sign of the denominator?  (A zero denominator agrees with both: its
+    // quotients are NaN and drop out of the running max / min.)  If so the staged records are swapped into (entry, exit)
+    // order for this packet and the ordered slab test is used; a packet that disagrees on any slab uses the general one.
+    unsigned neg_mask = 0u;
+#ifdef RTB_NO_ORDERED
+    bool ordered = false;
+#else
+    bool ordered = true;
+#endif
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        const bool nz = active && sr.inv[i] != 0.0f;
+        const unsigned bn = __ballot_sync(0xffffffffu, nz && sr.inv[i] < 0.0f), bp = __ballot_sync(0xffffffffu, nz && sr.inv[i] > 0.0f);
+        if (bn != 0u && bp != 0u) ordered = false;
+        if (bn != 0u) neg_mask |= 1u << i;
+    }
+    // the pair(s) this lane swaps when it stages float4 number (lane & 3) of a record: slabs 2f and 2f + 1 (float4 3: slab 6 only)
+    const unsigned f = lane & 3u;
+    const bool swap_lo = ordered && ((neg_mask >> (2u * f)) & 1u) != 0u;
+    const bool swap_hi = ordered && f < 3u && ((neg_mask >> (2u * f + 1u)) & 1u) != 0u;
     uint32_t link = start_link, meta = start_meta;
     if (start_meta == 0u) {
         const rt_f4* r = sc.recs;
@@ -358,7 +458,7 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
         if (COUNT && lane == 0) tc.rec_fetch++;
         const float tn = active ? slab_entry(q0, q1, q2, q3, sr, t_max) : INFINITY;
         link = f4_bits(q3.z); meta = f4_bits(q3.w);
-        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~RT_LEAF_BIT) == 0u) return true;
+        if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u || (meta & ~(RT_LEAF_BIT | RT_META_TOP)) == 0u) return true;
     }
     int sp = 0;
     for (;;) {
@@ -389,30 +489,23 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, bool& active, V3 o
             }
         }
         if (!(meta & RT_LEAF_BIT)) {
-            // ---- one cell: the warp fetches the cell's records with ONE coalesced 128-bit load per lane and stages
-            // them in shared memory (one memory latency per cell instead of one per child); then every lane tests every
-            // child record (broadcast LDS) for its own ray
-            const int base = sp;
-            if (lane < 4u * meta) K.stage[lane] = RT_LDG4(sc.recs + 4 * (size_t)link + lane);
-            if (COUNT && lane == 0) tc.rec_fetch += meta;
-            __syncwarp();
-            for (uint32_t k = 0; k < meta; k++) {
-                const float4 c0 = K.stage[4 * k], c1 = K.stage[4 * k + 1], c2 = K.stage[4 * k + 2], c3 = K.stage[4 * k + 3];
-                if (COUNT && active) tc.vol_tests++;
-                const float tn = slab_entry_packet(c0, c1, c2, c3, sr, t_max, active);
-                if (__ballot_sync(0xffffffffu, tn != INFINITY) == 0u) continue;
-                const float tmin = warp_min(tn);
-                if (sp >= RT_STACK_SIZE) { overflow = 1u; return true; }
-                if (lane == 0) {                             // keep [base, sp) sorted by descending entry distance
-                    int j = sp;
-                    while (j > base && K.t[j - 1] < tmin) {
-                        K.t[j] = K.t[j - 1]; K.link[j] = K.link[j - 1]; K.meta[j] = K.meta[j - 1];
-                        --j;
-                    }
-                    K.t[j] = tmin; K.link[j] = f4_bits(c3.z); K.meta[j] = f4_bits(c3.w);
-                }
-                ++sp;
+            // ---- one cell.  Its records come from the CTA's top table (the first levels of the tree: no global fetch), or
+            // the warp fetches them with ONE coalesced 128-bit load per lane; either way they are staged in this warp's
+            // shared memory -- swapped into (entry, exit) order when the packet's rays agree on the signs -- and every lane
+            // then tests every child record (broadcast LDS) for its own ray.
+            const uint32_t count = meta & RT_META_COUNT_MASK;
+            const bool in_top = top != nullptr && (meta & RT_META_TOP) != 0u;
+            if (lane < 4u * count) {
+                float4 v = in_top ? top[4u * ((meta >> RT_META_TOP_SHIFT) & 0xffu) + lane] : RT_LDG4(sc.recs + 4 * (size_t)link + lane);
+                if (swap_lo) { const float t = v.x; v.x = v.y; v.y = t; }
+                if (swap_hi) { const float t = v.z; v.z = v.w; v.w = t; }
+                K.stage[lane] = v;
             }
+            if (COUNT && lane == 0 && !in_top) tc.rec_fetch += count;
+            __syncwarp();
+            const bool fits = ordered ? packet_cell<true, COUNT>(K.stage, count, sr, t_max, active, K, sp, tc)
+                                      : packet_cell<false, COUNT>(K.stage, count, sr, t_max, active, K, sp, tc);
+            if (!fits) { overflow = 1u; return true; }
             __syncwarp();
         } else {
             // ---- one leaf: triangles staged the same way, 10 per round; every lane tests every triangle for its own ray
@@ -488,12 +581,15 @@ constexpr unsigned long long kNoHitKey = ~0ull;
 #define RTB_PRIMARY_MINB 8   /* measured on cfg4: 8 CTAs/SM (64 registers, some spills) 7.5 ms, 7: 7.6, 6 (80, none): 8.0, 5: 8.6 -- latency-bound */
 #endif
 #define RTB_PRIMARY_BOUNDS __launch_bounds__(kPrimaryThreads, RTB_PRIMARY_MINB)
-template <bool COUNT>
+template <bool COUNT, bool TOP>
 __global__ void RTB_PRIMARY_BOUNDS
 k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     __shared__ PacketStack stacks[kPrimaryThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
+    __shared__ typename TopStorage<TOP>::type top_table;        // TOP: the first levels of the tree, one bulk asynchronous copy per CTA
+    load_top_table(sc, top_table);
+    const float4* top = top_pointer(top_table);
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t pps = (uint32_t)wk.patches_per_side;
     const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);
@@ -534,7 +630,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
             bool occ, live = active;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds);
+            const bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds);
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
             if (!finished) {
@@ -550,7 +646,7 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
                 }
                 if (sidx < q.split_capacity && lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = 0u; }
                 live = active;                                                 // no room: trace it here, from the root
-                packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
+                packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
                 __syncwarp();
             }
             if (slot < total) {
@@ -578,6 +674,7 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
 {
     __shared__ PacketStack stacks[kPrimaryThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
+    const float4* top = nullptr;                       // items start deep in the tree: no use for the top table
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n = min(cnt->p_items_n[pass], q.item_capacity);
     const uint4* region = q.items + (size_t)pass * q.item_capacity;
@@ -605,7 +702,7 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
         HitRec best;
         bool occ, live = active;
         unsigned rounds = 0;
-        bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start);
+        bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start);
         __syncwarp();
         if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
         if (!finished && !emit_items(q, cnt->p_items_n, K, pass + 1, sidx)) {
@@ -614,7 +711,7 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
             const float t2 = now == kNoHitKey ? INFINITY : __uint_as_float((uint32_t)(now >> 32));
             const int32_t o2 = now == kNoHitKey ? 0x7fffffff : (int32_t)(uint32_t)now;
             live = active;
-            packet_trace<false, COUNT>(sc, K, live, o, d, t2, o, 0.0f, best, occ, tc, overflow, 0, rounds, item.y, item.z, o2);
+            packet_trace<false, COUNT>(sc, K, top, live, o, d, t2, o, 0.0f, best, occ, tc, overflow, 0, rounds, item.y, item.z, o2);
             __syncwarp();
             if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
         }
@@ -951,12 +1048,15 @@ RT_DEV void shade_epilogue(ChunkCounters* cnt, TraceCounters& tc, TraceCounters&
 // Packet version of k_shade: a warp takes 32 consecutive hit-queue entries (neighbouring pixels, k_compact), shades
 // them, traces their 32 shadow rays as one packet, composes and stores.  A packet that runs out of rounds
 // (RT_OPT_PACKET_ROUNDS) stores the pixels it has an answer for and is split into work items for the rest.
-template <bool COUNT>
+template <bool COUNT, bool TOP>
 __global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
 k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
+    __shared__ typename TopStorage<TOP>::type top_table;        // TOP: the first levels of the tree, one bulk asynchronous copy per CTA
+    load_top_table(sc, top_table);
+    const float4* top = top_pointer(top_table);
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n = cnt->n_hits;
     TraceCounters tc = zero_counters();
@@ -982,7 +1082,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
             HitRec unused;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
+            const bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
                                                             tune.packet_rounds, rounds);
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
@@ -997,7 +1097,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
                 } else {
                     if (sidx < q.split_capacity && lane == 0) { q.split_base[sidx] = base; q.split_active[sidx] = 0u; q.split_occ[sidx] = 0u; }
                     const bool before = occluded;                              // no room: finish here, from the root
-                    packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds);
+                    packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds);
                     occluded = occluded || before;
                     __syncwarp();
                 }
@@ -1017,6 +1117,7 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
 {
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
+    const float4* top = nullptr;                       // items start deep in the tree: no use for the top table
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n_hits = cnt->n_hits;
     const uint32_t n = min(cnt->items_n[pass], q.item_capacity);
@@ -1047,12 +1148,12 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         HitRec unused;
         bool occluded = false;
         unsigned rounds = 0;
-        bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
+        bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
                                                   item.y, item.z);
         __syncwarp();
         if (!finished && !emit_items(q, cnt->items_n, K, pass + 1, sidx)) {
             const bool before = occluded;                                      // no room: finish the item here
-            packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z);
+            packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z);
             occluded = occluded || before;
             __syncwarp();
         }
@@ -1199,7 +1300,8 @@ RT_DEV int fq_take(const QueueView& q, ChunkCounters* cnt, int stage, bool scan,
 // One shadow item: the packet's 32 shadow rays from one unvisited cell (as k_shade_items), then completion.
 template <bool COUNT>
 RT_DEV void shade_item_fused(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, ChunkCounters* cnt, uint32_t* super,
-                             int item_budget, PacketStack& K, const uint4 item, uint32_t n_hits, TraceCounters& tc, TraceCounters& fan, unsigned& overflow)
+                             int item_budget, PacketStack& K, const float4* top, const uint4 item, uint32_t n_hits, TraceCounters& tc, TraceCounters& fan,
+                             unsigned& overflow)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t sidx = item.x;
@@ -1220,12 +1322,12 @@ RT_DEV void shade_item_fused(const SceneView& sc, const FrameView& fr, const Wor
         bool occluded = false;
         unsigned rounds = 0;
         const int budget = item.w + 1u < kFusedGenerations ? item_budget : 0;
-        const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds, item.y, item.z,
+        const bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds, item.y, item.z,
                                                         0x7fffffff, &q.split_occ[sidx]);
         __syncwarp();
         if (!finished && !fq_emit(q, cnt, 1, K, sidx, item.w + 1u, false)) {
             const bool before = occluded;                                      // no room: finish the item here
-            packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z, 0x7fffffff,
+            packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds, item.y, item.z, 0x7fffffff,
                                       &q.split_occ[sidx]);
             occluded = occluded || before;
             __syncwarp();
@@ -1259,6 +1361,7 @@ k_shade_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
 {
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
+    const float4* top = nullptr;                       // (the fused experiment runs without the top table)
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n = cnt->n_hits;
     const uint32_t total_packets = (n + 31u) >> 5;
@@ -1275,7 +1378,7 @@ k_shade_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         uint4 item;
         const int got = (shadows && tune.packet_rounds > 0) ? fq_take(q, cnt, 1, !more, item) : 0;
         if (got == 1) {
-            shade_item_fused<COUNT>(sc, fr, wk, q, cnt, super, fq_budget(tune.item_rounds, more ? rem : 0u), K, item, n, tc, fan, overflow);
+            shade_item_fused<COUNT>(sc, fr, wk, q, cnt, super, fq_budget(tune.item_rounds, more ? rem : 0u), K, top, item, n, tc, fan, overflow);
             backoff = 250u;
             continue;
         }
@@ -1316,7 +1419,7 @@ k_shade_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
             HitRec unused;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
+            const bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
                                                             fq_budget(tune.packet_rounds, rem), rounds);
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
@@ -1331,7 +1434,7 @@ k_shade_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
                 if (sidx < q.split_capacity && fq_emit(q, cnt, 1, K, sidx, 0u, true)) deferred = active;   // the record's last item stores these pixels
                 else {
                     const bool before = occluded;                              // no room: finish here, from the root
-                    packet_trace<true, COUNT>(sc, K, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds);
+                    packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, 0, rounds);
                     occluded = occluded || before;
                     __syncwarp();
                 }
@@ -1381,7 +1484,7 @@ RT_DEV void primary_finish_record(const SceneView& sc, const FrameView& fr, cons
 
 template <bool COUNT>
 RT_DEV void primary_item_fused(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, ChunkCounters* cnt, uint32_t* super,
-                               int item_budget, PacketStack& K, const uint4 item, uint32_t total, TraceCounters& tc, unsigned& overflow)
+                               int item_budget, PacketStack& K, const float4* top, const uint4 item, uint32_t total, TraceCounters& tc, unsigned& overflow)
 {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t sidx = item.x;
@@ -1400,7 +1503,7 @@ RT_DEV void primary_item_fused(const SceneView& sc, const FrameView& fr, const W
     bool occ, live = active;
     unsigned rounds = 0;
     const int budget = item.w + 1u < kFusedGenerations ? item_budget : 0;
-    const bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start,
+    const bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start,
                                                      nullptr, q.split_best + (size_t)sidx * 32u);
     __syncwarp();
     if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
@@ -1410,7 +1513,7 @@ RT_DEV void primary_item_fused(const SceneView& sc, const FrameView& fr, const W
         const float t2 = now == kNoHitKey ? INFINITY : __uint_as_float((uint32_t)(now >> 32));
         const int32_t o2 = now == kNoHitKey ? 0x7fffffff : (int32_t)(uint32_t)now;
         live = active;
-        packet_trace<false, COUNT>(sc, K, live, o, d, t2, o, 0.0f, best, occ, tc, overflow, 0, rounds, item.y, item.z, o2, nullptr,
+        packet_trace<false, COUNT>(sc, K, top, live, o, d, t2, o, 0.0f, best, occ, tc, overflow, 0, rounds, item.y, item.z, o2, nullptr,
                                    q.split_best + (size_t)sidx * 32u);
         __syncwarp();
         if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
@@ -1434,6 +1537,7 @@ k_primary_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
 {
     __shared__ PacketStack stacks[kPrimaryThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
+    const float4* top = nullptr;                       // (the fused experiment runs without the top table)
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t pps = (uint32_t)wk.patches_per_side;
     const uint32_t total = (wk.tile_end - wk.tile_begin) * pps * pps * (uint32_t)(kPatch * kPatch);
@@ -1452,7 +1556,7 @@ k_primary_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
         uint4 item;
         const int got = tune.primary_rounds > 0 ? fq_take(q, cnt, 0, !more, item) : 0;
         if (got == 1) {
-            primary_item_fused<COUNT>(sc, fr, wk, q, cnt, super, fq_budget(tune.item_rounds, more ? rem : 0u), K, item, total, tc, overflow);
+            primary_item_fused<COUNT>(sc, fr, wk, q, cnt, super, fq_budget(tune.item_rounds, more ? rem : 0u), K, top, item, total, tc, overflow);
             backoff = 250u;
             continue;
         }
@@ -1494,7 +1598,7 @@ k_primary_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
             bool occ, live = active;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow,
+            const bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow,
                                                              fq_budget(tune.primary_rounds, rem), rounds);
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
@@ -1513,7 +1617,7 @@ k_primary_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
                 }
                 if (!deferred) {
                     live = active;                                             // no room: trace it here, from the root
-                    packet_trace<false, COUNT>(sc, K, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
+                    packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, 0, rounds);
                     __syncwarp();
                 }
             }

@@ -241,11 +241,11 @@ struct Builder {
     {
         float nr[PLANES], fr[PLANES];
         for (int i = 0; i < PLANES; i++) { nr[i] = pad_down(nr_in[i]); fr[i] = pad_up(fr_in[i]); }
-        F4* q = &out->recs[(size_t)rec * 4];
-        q[0] = F4{nr[0], nr[1], nr[2], nr[3]};
-        q[1] = F4{nr[4], nr[5], nr[6], fr[0]};
-        q[2] = F4{fr[1], fr[2], fr[3], fr[4]};
-        q[3] = F4{fr[5], fr[6], u2f(link), u2f(meta)};
+        F4* q = &out->recs[(size_t)rec * 4];                                     // (near, far) pairs, slab by slab: scene_layout.h
+        q[0] = F4{nr[0], fr[0], nr[1], fr[1]};
+        q[1] = F4{nr[2], fr[2], nr[3], fr[3]};
+        q[2] = F4{nr[4], fr[4], nr[5], fr[5]};
+        q[3] = F4{nr[6], fr[6], u2f(link), u2f(meta)};
     }
 
     // Appends triangles `ids` (sorted ascending = the reference's order inside a leaf) as one leaf; returns link.
@@ -383,6 +383,35 @@ struct Builder {
 
 } // namespace
 
+// The top of the tree as one small contiguous table (scene_layout.h): breadth-first from the root cell, whole child
+// blocks, while they fit RT_TOP_RECORDS records.  The parent record of a block that made it gets RT_META_TOP and the
+// block's offset in the table written into its meta word -- in recs[] and, when the parent is itself in the table, in its
+// copy there.
+static void build_top_table(FlatScene& out)
+{
+    out.top.clear();
+    if (out.recs.size() < 4) return;
+    struct Ref { size_t rec; long top_at; };                  // a record of recs[] and where its copy sits in the table (-1: the root, not copied)
+    std::vector<Ref> queue;
+    queue.push_back(Ref{0, -1});
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        const Ref r = queue[qi];
+        F4* q3 = &out.recs[r.rec * 4 + 3];
+        const uint32_t link = f2u(q3->z), meta = f2u(q3->w);
+        if ((meta & RT_META_LEAF) || meta == 0) continue;
+        const uint32_t count = meta & RT_META_COUNT_MASK;
+        const size_t at = out.top.size() / 4;
+        if (at + count > RT_TOP_RECORDS) continue;
+        for (uint32_t k = 0; k < count; k++) {
+            for (int j = 0; j < 4; j++) out.top.push_back(out.recs[((size_t)link + k) * 4 + j]);
+            queue.push_back(Ref{(size_t)link + k, (long)(at + k)});
+        }
+        const uint32_t tagged = meta | RT_META_TOP | ((uint32_t)at << RT_META_TOP_SHIFT);
+        q3->w = u2f(tagged);
+        if (r.top_at >= 0) out.top[(size_t)r.top_at * 4 + 3].w = u2f(tagged);
+    }
+}
+
 void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, size_t n, int max_depth,
                       int leaf_max, int leaf_split, FlatScene& out)
 {
@@ -506,6 +535,7 @@ void build_flat_scene(const float* xyz9, const float* uv6, const int32_t* mat, s
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = relocate(src[3], j);
     }
     out.n_records = out.recs.size() / 4;
+    build_top_table(out);
     if (getenv("RTB200_TRACE"))
         fprintf(stderr, "[rtb200] octree: top %.0f ms, %zu jobs %.0f ms, assemble %.0f ms\n", t1 - t0, jobs.size(), t2 - t1, now() - t2);
 }

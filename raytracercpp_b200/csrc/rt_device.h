@@ -27,6 +27,14 @@ typedef rtb::F4 rt_f4;
 
 #define RT_STACK_SIZE 160              /* 7 * RT_MAX_TREE_DEPTH + root, rounded up */
 #define RT_LEAF_BIT 0x80000000u
+#ifndef RT_META_TOP                    /* the meta word of an interior record, see scene_layout.h */
+#define RT_META_TOP 0x40000000u
+#define RT_META_TOP_SHIFT 8
+#define RT_META_COUNT_MASK 0xffu
+#ifndef RT_TOP_RECORDS
+#define RT_TOP_RECORDS 72
+#endif
+#endif
 
 namespace rtb {
 
@@ -46,6 +54,8 @@ struct TexView {
 // Everything a ray needs, by value in kernel parameter space.
 struct SceneView {
     const rt_f4* recs;      // 4 per child record (scene_layout.h)
+    const rt_f4* top;       // the top table: copies of the first levels' child blocks, top_n records (<= RT_TOP_RECORDS)
+    int32_t top_n;
     const rt_f4* tris;      // 3 per triangle, leaf order
     const rt_f4* shade;     // 2 per triangle, leaf order
     const rt_f4* mats;      // 4 per material (RtMaterial = 16 floats)
@@ -160,15 +170,15 @@ RT_DEV float slab_entry(const rt_f4& q0, const rt_f4& q1, const rt_f4& q2, const
         tn = fmaxf(tn, fminf(a, b));                            \
         tf = fminf(tf, fmaxf(a, b));                            \
     }
-    RT_SLAB(0, q0.x, q1.w)
-    RT_SLAB(1, q0.y, q2.x)
-    RT_SLAB(2, q0.z, q2.y)
+    RT_SLAB(0, q0.x, q0.y)
+    RT_SLAB(1, q0.z, q0.w)
+    RT_SLAB(2, q1.x, q1.y)
     const float lim = fminf(t_limit, tf) + 2.0f * sr.slack;
     if (!(tn <= lim) || tf + sr.slack < 0.0f) return INFINITY;
-    RT_SLAB(3, q0.w, q2.z)
-    RT_SLAB(4, q1.x, q2.w)
-    RT_SLAB(5, q1.y, q3.x)
-    RT_SLAB(6, q1.z, q3.y)
+    RT_SLAB(3, q1.z, q1.w)
+    RT_SLAB(4, q2.x, q2.y)
+    RT_SLAB(5, q2.z, q2.w)
+    RT_SLAB(6, q3.x, q3.y)
 #undef RT_SLAB
     bool ok = (tn <= tf + 2.0f * sr.slack) && (tf + sr.slack >= 0.0f) && (tn - sr.slack <= t_limit);
     return ok ? tn - sr.slack : INFINITY;
@@ -246,7 +256,7 @@ RT_DEV void ray_enter(RayState& S, uint32_t link, uint32_t meta)
     S.next = link;
     S.base = S.sp;
     if (meta & RT_LEAF_BIT) { S.mode = RT_MODE_TRIANGLES; S.left = meta & ~RT_LEAF_BIT; }
-    else { S.mode = RT_MODE_CHILDREN; S.left = meta; }
+    else { S.mode = RT_MODE_CHILDREN; S.left = meta & RT_META_COUNT_MASK; }
 }
 
 RT_DEV void ray_pop(RayState& S, const RayStack& K)
@@ -275,7 +285,7 @@ RT_DEV void ray_begin(const SceneView& sc, V3 o, V3 d, float t_max, RayState& S,
     rt_f4 q0 = RT_LDG4(r), q1 = RT_LDG4(r + 1), q2 = RT_LDG4(r + 2), q3 = RT_LDG4(r + 3);
     if (COUNT) { tc->vol_tests++; tc->rec_fetch++; }
     const uint32_t meta = f4_bits(q3.w);
-    if (slab_entry(q0, q1, q2, q3, S.sr, S.t_max) != INFINITY && (meta & ~RT_LEAF_BIT) != 0u) ray_enter(S, f4_bits(q3.z), meta);
+    if (slab_entry(q0, q1, q2, q3, S.sr, S.t_max) != INFINITY && (meta & ~(RT_LEAF_BIT | RT_META_TOP)) != 0u) ray_enter(S, f4_bits(q3.z), meta);
 }
 
 template <bool COUNT>

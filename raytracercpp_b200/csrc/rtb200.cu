@@ -133,7 +133,8 @@ struct RtContext {
 
     bool bvh_valid = false;
     RtBvhInfo info{};
-    DevBuf<float4> d_recs, d_tris, d_shade, d_mats;
+    DevBuf<float4> d_recs, d_tris, d_shade, d_mats, d_top;
+    int top_n = 0;
     DevBuf<int32_t> d_orig, d_leaf_of;
     std::vector<HostShape> shapes;       // analytic shapes, in the order they were added
     DevBuf<float4> d_shapes;
@@ -172,6 +173,7 @@ struct RtContext {
     int grid_intersect = 0, grid_occluded = 0;           // the same for the batch kernels (per context: its device's occupancy)
     bool opt_screen_cull = true;
     int opt_lanes = kLanes;
+    bool opt_top_table = false;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -245,6 +247,8 @@ SceneView scene_view(const RtContext* ctx)
     SceneView sc;
     memset(&sc, 0, sizeof(sc));
     sc.recs = ctx->d_recs.p;
+    sc.top = ctx->d_top.p;
+    sc.top_n = ctx->top_n;
     sc.tris = ctx->d_tris.p;
     sc.shade = ctx->d_shade.p;
     sc.mats = ctx->d_mats.p;
@@ -509,7 +513,7 @@ void rt_destroy(RtContext* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->d_recs.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
+    ctx->d_recs.release(); ctx->d_top.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
@@ -564,6 +568,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->tune.item_rounds = (int32_t)value;
         return RT_OK;
     case RT_OPT_FUSED_ITEMS: ctx->tune.fused = value != 0; return RT_OK;
+    case RT_OPT_TOP_TABLE: ctx->opt_top_table = value != 0; return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
     case RT_OPT_LANES:
         if (value < 0 || value > kMaxLanes) return fail(ctx, RT_ERR_INVALID, "lanes %lld outside [0,%d]", (long long)value, kMaxLanes);
@@ -626,6 +631,9 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < (long long)flat.orig.size(); i++) leaf_of[(size_t)flat.orig[i]] = (int32_t)i;
     RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_recs.p, flat.recs.data(), flat.recs.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, ctx->d_top.ensure(4 * RT_TOP_RECORDS));
+    if (!flat.top.empty()) RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_top.p, flat.top.data(), flat.top.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->top_n = (int)(flat.top.size() / 4);
     if (n) {
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris.p, flat.tris.data(), flat.tris.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(ctx->d_shade.p, flat.shade.data(), flat.shade.size() * sizeof(F4), cudaMemcpyHostToDevice, ctx->stream));
@@ -636,9 +644,9 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     double t2 = now_ms();
     ctx->n_tris = (uint32_t)n;
     {
-        const F4 *q0 = &flat.recs[0], *q1 = &flat.recs[1], *q2 = &flat.recs[2];
-        ctx->root_lo[0] = q0->x; ctx->root_lo[1] = q0->y; ctx->root_lo[2] = q0->z;
-        ctx->root_hi[0] = q1->w; ctx->root_hi[1] = q2->x; ctx->root_hi[2] = q2->y;
+        const F4 *q0 = &flat.recs[0], *q1 = &flat.recs[1];                       // (near, far) pairs of the three axis slabs
+        ctx->root_lo[0] = q0->x; ctx->root_lo[1] = q0->z; ctx->root_lo[2] = q1->x;
+        ctx->root_hi[0] = q0->y; ctx->root_hi[1] = q0->w; ctx->root_hi[2] = q1->y;
     }
     RtBvhInfo& bi = ctx->info;
     bi.triangles = n;
@@ -858,7 +866,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     // the launch time (a whole 4K 16-spp frame on one GPU has ~1000 and hides its stragglers; one of 8 tile shards does
     // not).  Positive option values are taken as they are; negative ones (the defaults) mean: |n| rounds for a long launch
     // and |n| / 2 for a short one -- and for primary packets: no splitting at all in a long launch.
-    const int pw = grid_for(ctx, (const void*)k_primary_packet<false>, kPrimaryThreads) * (kPrimaryThreads / 32);
+    const int pw = grid_for(ctx, (const void*)k_primary_packet<false, false>, kPrimaryThreads) * (kPrimaryThreads / 32);
     const bool short_launch = (uint64_t)owned.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
     auto budget = [&](int32_t v) { return v >= 0 ? v : (short_launch ? std::max(1, -v / 2) : -v); };
     Tuning tune = ctx->tune;
@@ -933,8 +941,8 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     const bool count = ctx->opt_count_work;
     int (&grids)[2][11] = ctx->grids;                                           // per context: its device's occupancy
     if (!grids[count][0]) {
-        grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true> : (const void*)k_primary_packet<false>, kPrimaryThreads);
-        grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true> : (const void*)k_shade_packet<false>, kQueueThreads);
+        grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true, true> : (const void*)k_primary_packet<false, true>, kPrimaryThreads);
+        grids[count][4] = grid_for(ctx, count ? (const void*)k_shade_packet<true, true> : (const void*)k_shade_packet<false, true>, kQueueThreads);
         grids[count][5] = grid_for(ctx, count ? (const void*)k_shade_items<true> : (const void*)k_shade_items<false>, kQueueThreads);
         grids[count][7] = grid_for(ctx, count ? (const void*)k_primary_items<true> : (const void*)k_primary_items<false>, kPrimaryThreads);
         grids[count][8] = grid_for(ctx, (const void*)k_primary_finish, kPrimaryThreads);
@@ -975,8 +983,12 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             } else {
             if (tune.packets) {
                 ScopedTimer t1(ctx, ST_PRIMARY, st, "  k_primary_packet");
-                if (count) k_primary_packet<true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-                else k_primary_packet<false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                const bool use_top = ctx->opt_top_table && sc.top_n > 0;
+                if (count) {
+                    if (use_top) k_primary_packet<true, true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                    else k_primary_packet<true, false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                } else if (use_top) k_primary_packet<false, true><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                else k_primary_packet<false, false><<<grid_pp, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             } else if (count) k_primary<true><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             launches++;
@@ -1022,8 +1034,12 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             } else {
             if (tune.packets) {
                 ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_packet");
-                if (count) k_shade_packet<true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-                else k_shade_packet<false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                const bool use_top = ctx->opt_top_table && sc.top_n > 0;
+                if (count) {
+                    if (use_top) k_shade_packet<true, true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                    else k_shade_packet<true, false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                } else if (use_top) k_shade_packet<false, true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                else k_shade_packet<false, false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             launches++;

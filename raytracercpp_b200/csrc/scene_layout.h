@@ -3,10 +3,14 @@
 // Reference layout (per node, 176 B + heap): 8 child pointers, std::vector<Triangle*>, AABB, 7 near + 7 far floats.
 // B200 layout (SoA, read with 128-bit loads):
 //
-//   recs[]  : one 64-byte "child record" per NON-EMPTY octree cell = 4 x float4
-//               q0 = near[0..3]      q1 = near[4..6], far[0]      q2 = far[1..4]
-//               q3 = far[5], far[6], bits(link), bits(meta)
-//             meta bit 31 = leaf; low bits = triangle count (leaf) or number of child records (interior, 1..8)
+//   recs[]  : one 64-byte "child record" per NON-EMPTY octree cell = 4 x float4, the 7 slabs as (near, far) pairs:
+//               q0 = near[0], far[0], near[1], far[1]      q1 = near[2], far[2], near[3], far[3]
+//               q2 = near[4], far[4], near[5], far[5]      q3 = near[6], far[6], bits(link), bits(meta)
+//             (pairs, so that the lane that stages a float4 for a 32-ray packet whose rays agree on the sign of a slab's
+//             denominator can swap that pair in place: the packet's slab test then needs no min/max per slab, kernels.cuh;
+//             the three axis slabs are q0 and half of q1)
+//             meta bit 31 = leaf; low 8 bits = number of child records (interior, 1..8); leaf: low 31 bits = triangle count
+//             meta bit 30 (interior only) = the children block is also in the TOP TABLE, at record offset (meta >> 8) & 0xff
 //             link        = first triangle (leaf) or first child record (interior)
 //             The (<= 8) records of one interior cell are contiguous and start on a 128-byte boundary, so a cell
 //             is 1..4 full cache lines.  Record 0 is the root cell itself.  Cells are laid out depth-first, so a
@@ -14,6 +18,9 @@
 //             have near=+inf/far=-inf, can never pass the slab test (bvh.h:101) and are dropped.
 //             Bounds are widened by RT_SLAB_PAD_ULPS ulps: the slab test multiplies by a reciprocal where the
 //             reference divides (bvh.h:92-93), so the widening keeps it conservative; it can only add visits.
+//   top[]   : copies of the child blocks of the first levels, breadth-first from the root, at most RT_TOP_RECORDS records
+//             (root's block + its children's blocks: 8 + 64 when all are full) = 4.6 KB that every CTA of the packet kernels
+//             loads into shared memory once, with one bulk asynchronous copy (cp.async.bulk), and traverses from there.
 //   tris[]  : 48 bytes per triangle in LEAF order = 3 x float4: (a.xyz, n.x) (b.xyz, n.y) (c.xyz, n.z) with
 //             n = cross(b-a, c-a), the un-normalised normal the reference caches (triangle.cpp:9-10).
 //   shade[] : 32 bytes per triangle in leaf order, read by shading only = 2 x float4:
@@ -31,6 +38,14 @@
 #define RT_SLAB_PAD_ULPS 4
 #define RT_MAX_TREE_DEPTH 20
 #define RT_META_LEAF 0x80000000u
+#ifndef RT_META_TOP
+#define RT_META_TOP 0x40000000u
+#define RT_META_TOP_SHIFT 8
+#define RT_META_COUNT_MASK 0xffu       /* interior records */
+#ifndef RT_TOP_RECORDS
+#define RT_TOP_RECORDS 72
+#endif
+#endif
 
 namespace rtb {
 
@@ -53,6 +68,7 @@ struct FlatScene {
     RawVector<F4> tris;          // 3 per triangle, leaf order
     RawVector<F4> shade;         // 2 per triangle, leaf order
     RawVector<int32_t> orig;     // leaf order -> index in the caller's array
+    RawVector<F4> top;           // 4 per record of the top table (<= RT_TOP_RECORDS records)
     // statistics of the (reference-shaped) octree
     uint64_t nodes = 0, leaves = 0, empty_leaves = 0, interior = 0;
     uint32_t max_depth_reached = 0, max_leaf_size = 0;

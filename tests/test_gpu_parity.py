@@ -394,6 +394,25 @@ def test_hair_scene_vs_oracle(cuda_lib, oracle):
     r.close()
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+def test_top_table_never_changes_a_frame(cuda_lib, robot, name):
+    """RT_OPT_TOP_TABLE: the packet kernels take the first tree levels from a per-CTA shared-memory copy that one
+    cp.async.bulk loads (instead of fetching those cells): same frame, same counts -- also on a tree so small that the
+    whole of it is in the table (depth 1) and on one whose root is a leaf."""
+    kw, mats, tex = common.config_table(robot["materials"])[name]
+    out = []
+    for top, depth, leaf in ((0, 12, 40), (1, 12, 40), (1, 1, 40), (1, 0, 5)):
+        r = common.product_renderer(cuda_lib, robot, dict(kw, bvh_max_depth=depth, bvh_leaf_object_count=leaf), mats, tex)
+        r.ctx.set_option(api.RT_OPT_TOP_TABLE, top)
+        r.ray_trace()
+        out.append((r.get_image().copy(), r.last_stats().as_dict()))
+        r.close()
+    for img, st in out[1:]:
+        assert np.array_equal(img, out[0][0])
+        for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
+            assert st[k] == out[0][1][k]
+
+
 def test_two_lanes_never_change_a_frame(cuda_lib, robot):
     """RT_OPT_LANES runs two wavefront chunks at a time on two streams with their own queues: same frame, same counts."""
     kw, mats, tex = common.config_table(robot["materials"])["cfg3"]
@@ -512,7 +531,7 @@ def test_hair_fullsize_band(cuda_lib, oracle, golden_fullsize):
     for g, w in zip(r.ctx.intersect(o, d), oracle.bvh(xyz9, 12, 40).intersect(o, d)):
         assert np.array_equal(g, w)
     # scheduling knobs leave the 4K frame bit-identical
-    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1), (api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1)):
+    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1), (api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(r.get_image(), img), opt
@@ -569,7 +588,7 @@ def test_full_size_properties(cuda_lib, oracle, big_sphere):
     # (3) idempotence: same frame twice; and the scheduling knobs at full size (item passes as separate launches, 4 chunks in flight)
     r.ray_trace()
     assert np.array_equal(full, r.get_image())
-    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1)):
+    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(full, r.get_image()), opt
