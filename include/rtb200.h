@@ -177,11 +177,13 @@ enum {
     /* Round budgets of the 32-ray packets.  A packet that needs more cell/leaf rounds than its budget is SPLIT: each cell
        it has not visited becomes a work item that another warp traces for the same 32 rays (items can be split again, 6
        generations deep, the last without a limit); answers are merged (shadow: OR, primary: 64-bit atomicMin on
-       (t, original index)).  n > 0: n rounds; 0: never split; n < 0 (the defaults): |n| rounds for a long launch, |n| / 2
-       for a short one (fewer than 256 packets per resident warp, e.g. one of 8 tile shards of a 4K 16-spp frame), where
-       one long packet shows in the launch time.  Results do not depend on any of them. */
+       (t, original index)).  n > 0: n rounds; 0: never split; n < 0 (the defaults): adaptive -- split after 8 |n| rounds
+       at the latest, and after |n| / 4 rounds (items: |n|) as soon as the launch's queue has been handed out completely,
+       i.e. when the packet has become the tail of its launch and other warps are free to take its cells.  Results do not
+       depend on any of them. */
     RT_OPT_PACKET_ROUNDS = 7, /* shadow packets (default -256)                                                           */
-    RT_OPT_PRIMARY_ROUNDS = 11,/* primary packets (default -256; negative additionally means: not split in long launches) */
+    RT_OPT_PRIMARY_ROUNDS = 11,/* primary packets (default -256; negative additionally means: not split in long launches,
+                                 256 and more packets per resident warp)                                                  */
     RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -16; 0 is invalid)                 */
     RT_OPT_FUSED_ITEMS = 12,  /* 0 (default): the work items of split packets are traced generation by generation in separate
                                  launches (six item passes and a finish kernel per stage); 1: the packet kernels consume the
@@ -193,6 +195,14 @@ enum {
                                  those cells from there instead of fetching them; 0 (default): they are fetched like any other
                                  cell -- they never leave the L1, and the extra address select costs 2 % of the frame on B200
                                  (measured).  Results do not depend on it                                       */
+    RT_OPT_SHADOW_SORT = 14,  /* before the shadow packets are formed the hit queue is put in LIGHT-SPACE order (Morton code of
+                                 the hit point's direction from the light, one counting sort), so a packet's 32 shadow rays run
+                                 through the same cells whatever the depth of their hits.  0: never (queue order = pixel order);
+                                 1: always; 2 (default): when fewer than a quarter of a chunk's ray slots are hits -- sparse
+                                 hits (thin strands) lie at unrelated depths, whereas the neighbouring pixels of a closed
+                                 surface already are neighbours from the light (measured: hair scene shadow stage 18.0 ->
+                                 6.8 ms with it, 10 M-triangle sphere 7.3 -> 9.6 ms).  Not used with reflection fans.
+                                 Results do not depend on it                                                              */
     RT_OPT_SCREEN_CULL = 8,   /* 1 (default): primary packets outside the screen-space bound of the scene's root box are
                                  written as misses without tracing.  Results do not depend on it                        */
     RT_OPT_LANES = 9,         /* wavefront chunks in flight at a time, each on its own stream with its own queues, so one

@@ -136,6 +136,10 @@ struct QueueView {
     float* slot_v;
     // compacted by k_compact
     uint32_t* hit_slot;              // hit queue: ray slots of the hits
+    // light-space order of the hit queue (k_sort_*): sort_mode 0 = off, 1 = always, 2 = when fewer than a quarter of the
+    // chunk's sort_slots ray slots are hits (sparse hits = hits at unrelated depths); the shade stage reads hit_sorted then
+    uint32_t* hit_sorted;
+    uint32_t sort_mode, sort_slots;
     // split shadow packets (k_shade_packet -> k_shade_items -> k_shade_finish)
     uint32_t* split_base;            // first hit-queue entry of the packet
     uint32_t* split_active;          // lanes that had no answer when the packet was split
@@ -187,7 +191,24 @@ struct Tuning {
     int32_t primary_rounds;   // round budget of a primary packet (0: never split)
     int32_t fused;            // 1: the packet kernels consume the work items of their split packets themselves (one launch per stage);
                               // 0: item passes and a finish kernel are separate launches (k_*_items x kItemPasses, k_*_finish)
+    // adaptive budgets (the defaults): a packet / item that has done at least *_min rounds is also split as soon as its
+    // launch's work queue has been handed out completely -- from then on it would only lengthen the launch's tail, whereas its
+    // unvisited cells can be traced by the warps that have nothing left to do.  0: the budgets above are all there is.
+    int32_t packet_min, item_min, primary_min;
 };
+
+// When a packet should give up before its round budget: the launch's queue (`counter` = tickets handed out, `total` =
+// tickets there are) is drained and the packet has done `min_rounds` rounds.  Looked at every 16th round.
+struct Drain {
+    const unsigned int* counter;
+    uint32_t total;
+    int min_rounds;
+};
+RT_DEV Drain no_drain() { Drain d; d.counter = nullptr; d.total = 0u; d.min_rounds = 0; return d; }
+RT_DEV Drain make_drain(const unsigned int* counter, uint32_t total, int min_rounds)
+{
+    Drain d; d.counter = min_rounds > 0 ? counter : nullptr; d.total = total; d.min_rounds = min_rounds; return d;
+}
 
 // One scheduling round of a persistent warp: either every lane that sits in a cell tests one child record, or every
 // lane that sits in a leaf tests one triangle.  Triangle tests are postponed until `tri_batch` lanes want one.
@@ -422,7 +443,7 @@ template <bool ANY, bool COUNT>
 RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, const float4* top, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
                          HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds,
                          uint32_t start_link = 0u, uint32_t start_meta = 0u, int32_t best_orig = 0x7fffffff,
-                         const unsigned int* poll_occ = nullptr, const unsigned long long* poll_best = nullptr)
+                         const unsigned int* poll_occ = nullptr, const unsigned long long* poll_best = nullptr, Drain drain = no_drain())
 {
     const unsigned lane = threadIdx.x & 31u;
     SlabRay sr;
@@ -462,10 +483,18 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, const float4* top,
     }
     int sp = 0;
     for (;;) {
-        if (max_rounds > 0 && (int)rounds >= max_rounds && sp < RT_STACK_SIZE) {
-            if (lane == 0) { K.t[sp] = 0.0f; K.link[sp] = link; K.meta[sp] = meta; K.saved = sp + 1; }
-            __syncwarp();
-            return false;
+        if (max_rounds > 0 && sp < RT_STACK_SIZE) {
+            bool stop = (int)rounds >= max_rounds;
+            if (!stop && drain.counter != nullptr && (int)rounds >= drain.min_rounds && (rounds & 15u) == 0u) {
+                uint32_t handed = 0;
+                if (lane == 0) handed = ld_vol(drain.counter);
+                stop = __shfl_sync(0xffffffffu, handed, 0) >= drain.total;     // nothing left to fetch: the other warps are idle or about to be
+            }
+            if (stop) {
+                if (lane == 0) { K.t[sp] = 0.0f; K.link[sp] = link; K.meta[sp] = meta; K.saved = sp + 1; }
+                __syncwarp();
+                return false;
+            }
         }
         ++rounds;
         // An item of a split packet that runs concurrently with the record's other items (fused scheduling) looks at what
@@ -630,7 +659,8 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
             bool occ, live = active;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds);
+            const bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds,
+                                                             0u, 0u, 0x7fffffff, nullptr, nullptr, make_drain(&cnt->next_patch, total, tune.primary_min));
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
             if (!finished) {
@@ -702,7 +732,8 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
         HitRec best;
         bool occ, live = active;
         unsigned rounds = 0;
-        bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start);
+        bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start,
+                                                   nullptr, nullptr, make_drain(&cnt->p_items_next[pass], n, tune.item_min));
         __syncwarp();
         if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
         if (!finished && !emit_items(q, cnt->p_items_n, K, pass + 1, sidx)) {
@@ -854,6 +885,143 @@ k_compact(SceneView sc, QueueView q, ChunkCounters* cnt, uint32_t total, int any
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Light-space ordering of the hit queue (RT_OPT_SHADOW_SORT).  The shadow rays of one point light are the rays FROM the
+// light: two hits seen from the light in nearly the same direction have shadow rays through the same cells, whatever
+// their depth, whereas 32 neighbouring PIXELS of a thin-strand scene hit strands at unrelated depths (cfg5: a packet of
+// queue-order neighbours does 8x the slab tests of its rays traced one by one).  So the queue is reordered before
+// k_shade_packet forms its packets: key = Morton code of the hit point's direction from the light on a kSortGrid^2 grid
+// (gnomonic map of the cone that holds the scene when the light is outside the scene's bounding sphere, octahedral map of
+// the whole sphere otherwise), one counting sort: histogram -> scan of the bins -> scatter.  Which 32 rays share a packet
+// never changes a ray's answer (any-hit is decided per ray), so frames stay bit-identical.
+constexpr int kSortGrid = 512;
+constexpr int kSortBins = kSortGrid * kSortGrid;
+constexpr int kSortScanThreads = 1024;                       // bins per block of the two scan kernels
+constexpr int kSortScanBlocks = kSortBins / kSortScanThreads;
+
+RT_DEV bool queue_sorted(const QueueView& q, const ChunkCounters* cnt)
+{
+    return q.sort_mode == 1u || (q.sort_mode == 2u && (unsigned long long)cnt->n_hits * 4ull < (unsigned long long)q.sort_slots);
+}
+// for the kernels of the shade stage: read the hit queue in the order the sort kernels left it (if they ran)
+RT_DEV void pick_hit_queue(QueueView& q, const ChunkCounters* cnt)
+{
+    if (queue_sorted(q, cnt)) q.hit_slot = q.hit_sorted;
+}
+
+struct LightMap {
+    V3 ex, ey, ez;          // orthonormal; ez points from the light to the centre of the scene's bounding sphere
+    float scale;            // gnomonic: 1 / tan(half angle of the cone); 0: octahedral map
+};
+
+RT_DEV uint32_t morton_spread(uint32_t x)                    // 16 bits -> every other bit
+{
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+RT_DEV uint32_t light_key(const LightMap& lm, V3 light, V3 p)
+{
+    const V3 w = p - light;
+    const float x = dot(w, lm.ex), y = dot(w, lm.ey), z = dot(w, lm.ez);
+    float a, b;
+    if (lm.scale > 0.0f) {
+        const float iz = lm.scale / fmaxf(z, 1.0e-30f);
+        a = x * iz; b = y * iz;
+    } else {
+        const float s = 1.0f / fmaxf(fabsf(x) + fabsf(y) + fabsf(z), 1.0e-30f);
+        a = x * s; b = y * s;
+        if (z < 0.0f) {
+            const float fa = (1.0f - fabsf(b)) * (a < 0.0f ? -1.0f : 1.0f), fb = (1.0f - fabsf(a)) * (b < 0.0f ? -1.0f : 1.0f);
+            a = fa; b = fb;
+        }
+    }
+    // fminf / fmaxf drop a NaN operand: every input lands on the grid
+    const uint32_t ia = (uint32_t)fminf(fmaxf((a * 0.5f + 0.5f) * (float)kSortGrid, 0.0f), (float)(kSortGrid - 1));
+    const uint32_t ib = (uint32_t)fminf(fmaxf((b * 0.5f + 0.5f) * (float)kSortGrid, 0.0f), (float)(kSortGrid - 1));
+    return morton_spread(ia) | (morton_spread(ib) << 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_keys(FrameView fr, WorkView wk, QueueView q, const ChunkCounters* cnt, LightMap lm, uint32_t* keys, uint32_t* bins)
+{
+    if (!queue_sorted(q, cnt)) return;
+    const uint32_t n = cnt->n_hits;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = q.hit_slot[i];
+        int px, py;
+        slot_pixel(wk, fr, slot, px, py);
+        V3 o, d;
+        primary_ray(fr, px, py, o, d);
+        const uint32_t key = light_key(lm, fr.light, o + q.slot_t[slot] * d);
+        keys[i] = key;
+        atomicAdd(&bins[key], 1u);
+    }
+}
+
+RT_DEV uint32_t block_sum_1024(uint32_t v, uint32_t* warp_part)       // sum over a 1024-thread block, returned to every thread
+{
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t w = __reduce_add_sync(0xffffffffu, v);
+    __syncthreads();
+    if (lane == 0) warp_part[warp] = w;
+    __syncthreads();
+    const uint32_t t = __reduce_add_sync(0xffffffffu, warp_part[lane]);
+    return t;
+}
+
+__global__ void __launch_bounds__(kSortScanThreads)
+k_sort_partial(QueueView q, const ChunkCounters* cnt, const uint32_t* bins, uint32_t* partial)
+{
+    __shared__ uint32_t warp_part[32];
+    if (!queue_sorted(q, cnt)) return;
+    const uint32_t total = block_sum_1024(bins[blockIdx.x * kSortScanThreads + threadIdx.x], warp_part);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+// bins[] (counts) -> exclusive prefix sums over all kSortBins, in place: a block adds up the partial sums of the blocks
+// before it and scans its own 1024 bins.
+__global__ void __launch_bounds__(kSortScanThreads)
+k_sort_scan(QueueView q, const ChunkCounters* cnt, uint32_t* bins, const uint32_t* partial)
+{
+    __shared__ uint32_t warp_part[32];
+    if (!queue_sorted(q, cnt)) return;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t before = block_sum_1024(threadIdx.x < blockIdx.x ? partial[threadIdx.x] : 0u, warp_part);
+    static_assert(kSortScanBlocks <= kSortScanThreads, "one thread per preceding block");
+    const uint32_t c = bins[blockIdx.x * kSortScanThreads + threadIdx.x];
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += a;
+    }
+    __syncthreads();
+    if (lane == 31) warp_part[warp] = inc;
+    __syncthreads();
+    uint32_t wsum = warp_part[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, wsum, o);
+        if ((int)lane >= o) wsum += a;
+    }
+    const uint32_t warps_before = __shfl_sync(0xffffffffu, wsum - warp_part[lane], warp);
+    bins[blockIdx.x * kSortScanThreads + threadIdx.x] = before + warps_before + inc - c;
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_scatter(QueueView q, const ChunkCounters* cnt, const uint32_t* keys, uint32_t* bins)
+{
+    if (!queue_sorted(q, cnt)) return;
+    uint32_t* sorted = q.hit_sorted;
+    const uint32_t n = cnt->n_hits;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        sorted[atomicAdd(&bins[keys[i]], 1u)] = q.hit_slot[i];
+}
+
 // The primary ray and hit record of hit-queue entry i.
 RT_DEV void queue_ray(const FrameView& fr, const WorkView& wk, const QueueView& q, uint32_t i, V3& o, V3& d, HitRec& hr, uint32_t& pix)
 {
@@ -906,6 +1074,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
 k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
+    pick_hit_queue(q, cnt);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t n = cnt->n_hits;
@@ -1052,6 +1221,7 @@ template <bool COUNT, bool TOP>
 __global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
 k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super, Tuning tune)
 {
+    pick_hit_queue(q, cnt);
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
     __shared__ typename TopStorage<TOP>::type top_table;        // TOP: the first levels of the tree, one bulk asynchronous copy per CTA
@@ -1083,7 +1253,8 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
             const bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
-                                                            tune.packet_rounds, rounds);
+                                                            tune.packet_rounds, rounds, 0u, 0u, 0x7fffffff, nullptr, nullptr,
+                                                            make_drain(&cnt->next_shade, n, tune.packet_min));
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
             if (!finished) {
@@ -1115,6 +1286,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads, RTB_SHADE_MINB)
 k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, Tuning tune, int pass)
 {
+    pick_hit_queue(q, cnt);
     __shared__ PacketStack stacks[kQueueThreads / 32];
     PacketStack& K = stacks[threadIdx.x >> 5];
     const float4* top = nullptr;                       // items start deep in the tree: no use for the top table
@@ -1149,7 +1321,7 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         bool occluded = false;
         unsigned rounds = 0;
         bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
-                                                  item.y, item.z);
+                                                  item.y, item.z, 0x7fffffff, nullptr, nullptr, make_drain(&cnt->items_next[pass], n, tune.item_min));
         __syncwarp();
         if (!finished && !emit_items(q, cnt->items_n, K, pass + 1, sidx)) {
             const bool before = occluded;                                      // no room: finish the item here
@@ -1169,6 +1341,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kQueueThreads)
 k_shade_finish(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt, uint32_t* super)
 {
+    pick_hit_queue(q, cnt);
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n_hits = cnt->n_hits;
     const uint32_t n = min(cnt->n_split, q.split_capacity);

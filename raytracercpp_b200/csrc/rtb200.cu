@@ -96,6 +96,7 @@ constexpr int kMaxLanes = 6;     // ... at most (RT_OPT_LANES)
 // The per-frame work buffers of ONE wavefront chunk in flight.
 struct QueueSet {
     DevBuf<uint32_t> hit_slot, refl_idx, split_base, split_active, split_occ, item_ready, split_pending;
+    DevBuf<uint32_t> hit_sorted, sort_keys, sort_bins;       // light-space ordering of the hit queue (RT_OPT_SHADOW_SORT)
     DevBuf<unsigned long long> split_best, refl_cnt;
     DevBuf<uint4> items;
     DevBuf<int32_t> tri;
@@ -103,7 +104,7 @@ struct QueueSet {
     void release()
     {
         hit_slot.release(); refl_idx.release(); split_base.release(); split_active.release(); split_occ.release(); split_best.release();
-        item_ready.release(); split_pending.release();
+        item_ready.release(); split_pending.release(); hit_sorted.release(); sort_keys.release(); sort_bins.release();
         refl_cnt.release(); items.release(); tri.release(); t.release(); u.release(); v.release(); refl_rgb.release();
     }
 };
@@ -162,7 +163,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0};
+    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0, 0, 0, 0};
     uint32_t frame_serial = 0;           // tags the ready flags of the fused item queues: (serial << 2) | stage
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
@@ -174,6 +175,7 @@ struct RtContext {
     bool opt_screen_cull = true;
     int opt_lanes = kLanes;
     bool opt_top_table = false;
+    int opt_shadow_sort = 2;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -436,6 +438,33 @@ int get_tile_list(RtContext* ctx, const RtSettings* s, int tile_size, int tile_m
     return RT_OK;
 }
 
+// The frame of reference of the light-space queue order (kernels.cuh, LightMap): ez from the light to the centre of the
+// root cell's box; a gnomonic map of the cone around the box's bounding sphere when the light is outside it.
+LightMap make_light_map(const RtContext* ctx)
+{
+    LightMap lm;
+    const V3 c = v3(0.5f * (ctx->root_lo[0] + ctx->root_hi[0]), 0.5f * (ctx->root_lo[1] + ctx->root_hi[1]), 0.5f * (ctx->root_lo[2] + ctx->root_hi[2]));
+    const V3 h = v3(0.5f * (ctx->root_hi[0] - ctx->root_lo[0]), 0.5f * (ctx->root_hi[1] - ctx->root_lo[1]), 0.5f * (ctx->root_hi[2] - ctx->root_lo[2]));
+    const float radius = std::sqrt(h.x * h.x + h.y * h.y + h.z * h.z);
+    V3 z = c - ctx->light;
+    const float dist = std::sqrt(z.x * z.x + z.y * z.y + z.z * z.z);
+    if (!(dist > 1.0e-20f) || !std::isfinite(dist)) { z = v3(0, 0, 1); }
+    else z = v3(z.x / dist, z.y / dist, z.z / dist);
+    const V3 up = std::fabs(z.y) < 0.9f ? v3(0, 1, 0) : v3(1, 0, 0);
+    V3 x = v3(up.y * z.z - up.z * z.y, up.z * z.x - up.x * z.z, up.x * z.y - up.y * z.x);
+    const float xl = std::sqrt(x.x * x.x + x.y * x.y + x.z * x.z);
+    x = v3(x.x / xl, x.y / xl, x.z / xl);
+    lm.ex = x;
+    lm.ey = v3(z.y * x.z - z.z * x.y, z.z * x.x - z.x * x.z, z.x * x.y - z.y * x.x);
+    lm.ez = z;
+    lm.scale = 0.0f;
+    if (std::isfinite(dist) && std::isfinite(radius) && dist > radius * 1.05f && radius > 0.0f) {
+        const float tan_half = radius / std::sqrt(dist * dist - radius * radius);
+        lm.scale = 1.0f / tan_half;
+    }
+    return lm;
+}
+
 bool tune_packets_hint(const RtContext* ctx) { return ctx->tune.packets != 0; }
 
 int ensure_stack(RtContext* ctx, const RtSettings* s)
@@ -569,6 +598,10 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         return RT_OK;
     case RT_OPT_FUSED_ITEMS: ctx->tune.fused = value != 0; return RT_OK;
     case RT_OPT_TOP_TABLE: ctx->opt_top_table = value != 0; return RT_OK;
+    case RT_OPT_SHADOW_SORT:
+        if (value < 0 || value > 2) return fail(ctx, RT_ERR_INVALID, "shadow sort %lld outside [0,2]", (long long)value);
+        ctx->opt_shadow_sort = (int)value;
+        return RT_OK;
     case RT_OPT_SCREEN_CULL: ctx->opt_screen_cull = value != 0; return RT_OK;
     case RT_OPT_LANES:
         if (value < 0 || value > kMaxLanes) return fail(ctx, RT_ERR_INVALID, "lanes %lld outside [0,%d]", (long long)value, kMaxLanes);
@@ -862,27 +895,36 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     const size_t qcap = (size_t)largest_chunk * px_per_tile;
 
     RT_CUDA(ctx, ctx->d_counters.ensure(std::max<uint32_t>(n_chunks, 1)));
-    // Round budgets.  A launch is SHORT when it has fewer than 256 packets per resident warp: one long packet then shows in
-    // the launch time (a whole 4K 16-spp frame on one GPU has ~1000 and hides its stragglers; one of 8 tile shards does
-    // not).  Positive option values are taken as they are; negative ones (the defaults) mean: |n| rounds for a long launch
-    // and |n| / 2 for a short one -- and for primary packets: no splitting at all in a long launch.
+    // Round budgets.  Positive option values are fixed budgets.  Negative ones (the defaults) are adaptive: a packet is
+    // split after 8 |n| rounds at the latest, and after |n| / 4 rounds as soon as its launch has no unfetched packets left
+    // (Drain, kernels.cuh) -- a packet is only worth splitting when it would otherwise be the tail of its launch.  The same
+    // for the work items of a pass, with |n| rounds as the minimum.  Primary packets are only split in SHORT launches (fewer
+    // than 256 packets per resident warp, e.g. one of 8 tile shards of a 4K frame): a long launch hides its stragglers,
+    // and the item passes of a stage that splits nothing still cost their launches (measured: +0.3 ms on a whole 4K frame).
     const int pw = grid_for(ctx, (const void*)k_primary_packet<false, false>, kPrimaryThreads) * (kPrimaryThreads / 32);
     const bool short_launch = (uint64_t)owned.size() * px_per_tile / 32 < (uint64_t)256 * (uint64_t)pw;
-    auto budget = [&](int32_t v) { return v >= 0 ? v : (short_launch ? std::max(1, -v / 2) : -v); };
+    auto largest = [](int32_t v) { return v >= 0 ? v : std::min<int32_t>(-v, 1 << 27) * 8; };
+    auto least = [](int32_t v, int div) { return v >= 0 ? 0 : std::max<int32_t>(1, -v / div); };
     Tuning tune = ctx->tune;
-    tune.packet_rounds = budget(ctx->tune.packet_rounds);
-    tune.item_rounds = budget(ctx->tune.item_rounds);
-    tune.primary_rounds = ctx->tune.primary_rounds >= 0 ? ctx->tune.primary_rounds : (short_launch ? std::max(1, -ctx->tune.primary_rounds / 2) : 0);
+    tune.packet_rounds = largest(ctx->tune.packet_rounds); tune.packet_min = least(ctx->tune.packet_rounds, 4);
+    tune.item_rounds = largest(ctx->tune.item_rounds); tune.item_min = least(ctx->tune.item_rounds, 1);
+    tune.primary_rounds = largest(ctx->tune.primary_rounds); tune.primary_min = least(ctx->tune.primary_rounds, 4);
+    if (ctx->tune.primary_rounds < 0 && !short_launch) tune.primary_rounds = tune.primary_min = 0;
     if (tune.fused && tune.packets) {
         // fused item scheduling: the values are the LARGEST budgets -- a packet's own budget shrinks as the launch runs out
         // of packets (fq_budget, kernels.cuh) --, so nothing depends on the length of the launch
-        auto largest = [](int32_t v) { return v >= 0 ? v : -v; };
-        tune.packet_rounds = largest(ctx->tune.packet_rounds);
-        tune.item_rounds = largest(ctx->tune.item_rounds);
-        tune.primary_rounds = largest(ctx->tune.primary_rounds);
+        auto magnitude = [](int32_t v) { return v >= 0 ? v : -v; };
+        tune.packet_rounds = magnitude(ctx->tune.packet_rounds);
+        tune.item_rounds = magnitude(ctx->tune.item_rounds);
+        tune.primary_rounds = magnitude(ctx->tune.primary_rounds);
+        tune.packet_min = tune.item_min = tune.primary_min = 0;
     }
     const bool tail = tune.packets && tune.packet_rounds > 0 && s->compute_shadows && s->shading_method == RT_SHADING;
     const bool psplit = tune.packets && tune.primary_rounds > 0;
+    // light-space ordering of the hit queue before the shadow packets are formed (kernels.cuh).  Not with reflection fans:
+    // their queue indexes the hit queue in compaction order.
+    const bool sort_hits = ctx->opt_shadow_sort && tune.packets && !tune.fused && !reflect && s->compute_shadows && s->shading_method == RT_SHADING;
+    const LightMap light_map = sort_hits ? make_light_map(ctx) : LightMap{};
     // split records and work items of the packets that run out of rounds; a packet that finds them full is finished in
     // place.  Primary and shadow packets never run at the same time and share the storage.
     const size_t split_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
@@ -904,6 +946,10 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         RT_CUDA(ctx, Q.hit_slot.ensure(qcap)); RT_CUDA(ctx, Q.tri.ensure(qcap)); RT_CUDA(ctx, Q.t.ensure(qcap));
         RT_CUDA(ctx, Q.u.ensure(qcap)); RT_CUDA(ctx, Q.v.ensure(qcap));
         if (reflect) { RT_CUDA(ctx, Q.refl_idx.ensure(qcap)); RT_CUDA(ctx, Q.refl_rgb.ensure(3 * qcap)); RT_CUDA(ctx, Q.refl_cnt.ensure(3 * qcap)); }
+        if (sort_hits) {
+            RT_CUDA(ctx, Q.hit_sorted.ensure(qcap)); RT_CUDA(ctx, Q.sort_keys.ensure(qcap));
+            RT_CUDA(ctx, Q.sort_bins.ensure((size_t)kSortBins + kSortScanBlocks));
+        }
     }
     uint32_t* super = d_argb_out;
     if (resolve) {
@@ -921,6 +967,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         q.items = Q.items.p; q.split_capacity = (uint32_t)split_cap; q.item_capacity = (uint32_t)item_cap;
         q.item_ready = Q.item_ready.p; q.split_pending = Q.split_pending.p; q.tag = 0;
         q.refl_idx = Q.refl_idx.p; q.refl_rgb = Q.refl_rgb.p; q.refl_cnt = Q.refl_cnt.p; q.capacity = (uint32_t)qcap;
+        q.hit_sorted = nullptr; q.sort_mode = 0u; q.sort_slots = 0u;
     }
     for (int l = 1; l < n_lanes; l++) {
         if (ctx->lane_stream[l]) continue;
@@ -1015,6 +1062,22 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             k_compact<<<blocks, kCompactThreads, 0, st>>>(sc, q, cnt, slots, reflect ? 1 : 0);
             launches++;
         }
+        QueueView qsorted = q;                                                 // the shade stage's view of the queues
+        if (sort_hits) {
+            ScopedTimer tm(ctx, ST_COMPACT, st);
+            QueueSet& Q = ctx->qs[lane];
+            uint32_t* bins = Q.sort_bins.p;
+            uint32_t* partial = bins + kSortBins;
+            qsorted.hit_sorted = Q.hit_sorted.p;
+            qsorted.sort_mode = (uint32_t)ctx->opt_shadow_sort;
+            qsorted.sort_slots = (wk.tile_end - wk.tile_begin) * (uint32_t)px_per_tile;
+            RT_CUDA(ctx, cudaMemsetAsync(bins, 0, sizeof(uint32_t) * kSortBins, st));
+            k_sort_keys<<<ctx->sm_count * 4, 256, 0, st>>>(fr, wk, qsorted, cnt, light_map, Q.sort_keys.p, bins);
+            k_sort_partial<<<kSortScanBlocks, kSortScanThreads, 0, st>>>(qsorted, cnt, bins, partial);
+            k_sort_scan<<<kSortScanBlocks, kSortScanThreads, 0, st>>>(qsorted, cnt, bins, partial);
+            k_sort_scatter<<<ctx->sm_count * 4, 256, 0, st>>>(qsorted, cnt, Q.sort_keys.p, bins);
+            launches += 4;
+        }
         if (reflect) {
             ScopedTimer tm(ctx, ST_REFLECT, st);
             if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
@@ -1036,21 +1099,21 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
                 ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_packet");
                 const bool use_top = ctx->opt_top_table && sc.top_n > 0;
                 if (count) {
-                    if (use_top) k_shade_packet<true, true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-                    else k_shade_packet<true, false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-                } else if (use_top) k_shade_packet<false, true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-                else k_shade_packet<false, false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-            } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
-            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
+                    if (use_top) k_shade_packet<true, true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
+                    else k_shade_packet<true, false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
+                } else if (use_top) k_shade_packet<false, true><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
+                else k_shade_packet<false, false><<<grid_sp, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
+            } else if (count) k_shade<true><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
+            else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
             launches++;
             if (tail) {
                 for (int pass = 0; pass < kItemPasses; pass++) {
                     ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_items");
-                    if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
-                    else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
+                    if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, tune, pass);
+                    else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, tune, pass);
                 }
-                if (count) k_shade_finish<true><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
-                else k_shade_finish<false><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
+                if (count) k_shade_finish<true><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super);
+                else k_shade_finish<false><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super);
                 launches += kItemPasses + 1;
             }
             }

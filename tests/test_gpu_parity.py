@@ -382,14 +382,14 @@ def test_hair_scene_vs_oracle(cuda_lib, oracle):
         assert np.array_equal(g, w)
     for opts in ({api.RT_OPT_PACKETS: 0}, {api.RT_OPT_PACKET_ROUNDS: 8, api.RT_OPT_PRIMARY_ROUNDS: 8, api.RT_OPT_ITEM_ROUNDS: 4},
                  {api.RT_OPT_PACKET_ROUNDS: 8, api.RT_OPT_PRIMARY_ROUNDS: 8, api.RT_OPT_ITEM_ROUNDS: 4, api.RT_OPT_FUSED_ITEMS: 1},
-                 {api.RT_OPT_SCREEN_CULL: 0}):
+                 {api.RT_OPT_SCREEN_CULL: 0}, {api.RT_OPT_SHADOW_SORT: 0}):
         for k, v in opts.items():
             r.ctx.set_option(k, v)
         r.ray_trace()
         assert np.array_equal(r.get_image(), img), opts
         r.ctx.set_option(api.RT_OPT_PACKETS, 1)
         r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -16)
-        r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1)
+        r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1); r.ctx.set_option(api.RT_OPT_SHADOW_SORT, 1)
         r.ctx.set_option(api.RT_OPT_FUSED_ITEMS, 0)
     r.close()
 
@@ -411,6 +411,27 @@ def test_top_table_never_changes_a_frame(cuda_lib, robot, name):
         assert np.array_equal(img, out[0][0])
         for k in ("primary_rays", "shadow_rays", "primary_hits", "reflection_rays", "reflection_shadow_rays"):
             assert st[k] == out[0][1][k]
+
+
+@pytest.mark.parametrize("light", [(3.0, 3.0, 2.0), (0.0, 0.4, -4.0), (40.0, 60.0, 10.0)])
+def test_light_space_queue_order_never_changes_a_frame(cuda_lib, robot, light):
+    """RT_OPT_SHADOW_SORT reorders the hit queue by the direction of the hits from the light before the shadow packets are
+    formed: same frame, same counts -- with the light outside the scene's bounding sphere (gnomonic map), inside it
+    (octahedral map) and far away (a narrow cone)."""
+    kw, mats, tex = common.config_table(robot["materials"])["cfg2"]
+    out = []
+    for sort in (1, 0):
+        r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+        r.ctx.set_light(light)
+        r.ctx.set_option(api.RT_OPT_SHADOW_SORT, sort)
+        for _ in range(2):
+            r.ray_trace()
+        out.append((r.get_image().copy(), r.last_stats().as_dict()))
+        r.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("primary_rays", "shadow_rays", "primary_hits"):
+        assert out[0][1][k] == out[1][1][k]
+    assert out[0][1]["kernel_launches"] > out[1][1]["kernel_launches"]
 
 
 def test_two_lanes_never_change_a_frame(cuda_lib, robot):
@@ -531,7 +552,8 @@ def test_hair_fullsize_band(cuda_lib, oracle, golden_fullsize):
     for g, w in zip(r.ctx.intersect(o, d), oracle.bvh(xyz9, 12, 40).intersect(o, d)):
         assert np.array_equal(g, w)
     # scheduling knobs leave the 4K frame bit-identical
-    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1), (api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0)):
+    for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1), (api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0),
+                           (api.RT_OPT_SHADOW_SORT, 0, 1)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(r.get_image(), img), opt
@@ -588,7 +610,7 @@ def test_full_size_properties(cuda_lib, oracle, big_sphere):
     # (3) idempotence: same frame twice; and the scheduling knobs at full size (item passes as separate launches, 4 chunks in flight)
     r.ray_trace()
     assert np.array_equal(full, r.get_image())
-    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0)):
+    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0), (api.RT_OPT_SHADOW_SORT, 0, 1)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(full, r.get_image()), opt
