@@ -195,6 +195,11 @@ enum {
                                  those cells from there instead of fetching them; 0 (default): they are fetched like any other
                                  cell -- they never leave the L1, and the extra address select costs 2 % of the frame on B200
                                  (measured).  Results do not depend on it                                       */
+    RT_OPT_DEVICE_BUILD = 15, /* 1 (default): rt_build_bvh / rt_transform_triangles build the octree ON THE GPU (per-triangle path
+                                 through the reference's subdivision -> stable radix sort -> cells level by level): same cells,
+                                 leaf contents and order, slab extents and rt_bvh_info statistics as the host builder, hence as
+                                 the reference's BVH::BVH; the caller's arrays stay resident, so a transform + rebuild moves no
+                                 triangle data.  0: the host builder (C++/OpenMP) + upload.  Results do not depend on it  */
     RT_OPT_SHADOW_SORT = 14,  /* before the shadow packets are formed the hit queue is put in LIGHT-SPACE order (Morton code of
                                  the hit point's direction from the light, one counting sort), so a packet's 32 shadow rays run
                                  through the same cells whatever the depth of their hits.  0: never (queue order = pixel order);

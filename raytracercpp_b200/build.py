@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librtb200.so"
 SOURCES = [CSRC / "rtb200.cu", CSRC / "octree_build.cpp"]
-HEADERS = [CSRC / "kernels.cuh", CSRC / "host_common.h", CSRC / "rt_device.h", CSRC / "rt_math.h", CSRC / "scene_layout.h",
+HEADERS = [CSRC / "kernels.cuh", CSRC / "octree_device.cuh", CSRC / "host_common.h", CSRC / "rt_device.h", CSRC / "rt_math.h", CSRC / "scene_layout.h",
            PKG.parent / "include" / "rtb200.h"]
 
 NVCC_FLAGS = [

@@ -20,6 +20,7 @@
 
 #include "kernels.cuh"
 #include "scene_layout.h"
+#include "octree_device.cuh"
 #include "host_common.h"
 
 using namespace rtb;
@@ -119,6 +120,24 @@ struct Pending {                          // a frame that has been enqueued (rt_
     uint64_t primary_rays = 0;
 };
 
+// Device copies of the caller's triangle arrays and the temporaries of the device octree build (octree_device.cuh); kept
+// between builds: set_object_transform rebuilds the tree again and again (renderer.cpp:214-224).
+struct DeviceBuild {
+    DevBuf<float> xyz9, uv6, centroid, c_nr, c_fr;
+    DevBuf<int32_t> mat;
+    DevBuf<unsigned long long> keys[2];
+    DevBuf<uint32_t> idx[2], hist, sums, counts, c_begin, c_end, c_first, c_info, c_size, c_rec, c_block;
+    DevBuf<devbuild::Stats> stats;
+    bool tris_on_device = false;             // xyz9 / uv6 / mat above hold the caller's current triangles
+    std::vector<M4> host_pending;            // transforms applied to the device copy but not yet to RtContext::xyz9
+    void release()
+    {
+        xyz9.release(); uv6.release(); centroid.release(); c_nr.release(); c_fr.release(); mat.release(); keys[0].release(); keys[1].release();
+        idx[0].release(); idx[1].release(); hist.release(); sums.release(); counts.release(); c_begin.release(); c_end.release(); c_first.release();
+        c_info.release(); c_size.release(); c_rec.release(); c_block.release(); stats.release();
+    }
+};
+
 struct RtContext {
     int device = 0;
     int sm_count = 0;
@@ -176,6 +195,8 @@ struct RtContext {
     int opt_lanes = kLanes;
     bool opt_top_table = false;
     int opt_shadow_sort = 2;
+    bool opt_device_build = true;
+    DeviceBuild db;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -465,6 +486,208 @@ LightMap make_light_map(const RtContext* ctx)
     return lm;
 }
 
+
+void transform_host_vertices(RtContext* ctx, const M4& t)
+{
+    const long long n = (long long)(ctx->xyz9.size() / 3);
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; i++) {                                            // Transform::operator()(Triangle), mat.cpp:133-140
+        V3 p = xform_point(t, v3(ctx->xyz9[3 * i], ctx->xyz9[3 * i + 1], ctx->xyz9[3 * i + 2]));
+        ctx->xyz9[3 * i] = p.x; ctx->xyz9[3 * i + 1] = p.y; ctx->xyz9[3 * i + 2] = p.z;
+    }
+}
+
+void apply_pending_host_transforms(RtContext* ctx)
+{
+    for (const M4& t : ctx->db.host_pending) transform_host_vertices(ctx, t);
+    ctx->db.host_pending.clear();
+}
+
+// keeps the first `keep` elements
+template <typename T>
+cudaError_t grow_keep(DevBuf<T>& b, size_t count, size_t keep, cudaStream_t st)
+{
+    if (count <= b.n) return cudaSuccess;
+    T* fresh = nullptr;
+    cudaError_t e = cudaMalloc((void**)&fresh, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (b.p && keep) e = cudaMemcpyAsync(fresh, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (b.p) cudaFree(b.p);
+    b.p = fresh;
+    b.n = count;
+    return e;
+}
+
+// rt_build_bvh on the device (octree_device.cuh).  n > 0.
+int build_bvh_device(RtContext* ctx, int max_depth, int leaf_max)
+{
+    using namespace devbuild;
+    DeviceBuild& D = ctx->db;
+    const size_t n = ctx->xyz9.size() / 9;
+    const cudaStream_t st = ctx->stream;
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    const double t0 = now_ms();
+    if (!D.tris_on_device) {
+        apply_pending_host_transforms(ctx);
+        RT_CUDA(ctx, D.xyz9.ensure(9 * n));
+        RT_CUDA(ctx, cudaMemcpyAsync(D.xyz9.p, ctx->xyz9.data(), 9 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (ctx->has_uv) { RT_CUDA(ctx, D.uv6.ensure(6 * n)); RT_CUDA(ctx, cudaMemcpyAsync(D.uv6.p, ctx->uv6.data(), 6 * n * sizeof(float), cudaMemcpyHostToDevice, st)); }
+        if (ctx->has_mat) { RT_CUDA(ctx, D.mat.ensure(n)); RT_CUDA(ctx, cudaMemcpyAsync(D.mat.p, ctx->mat.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st)); }
+        RT_CUDA(ctx, cudaStreamSynchronize(st));
+        D.tris_on_device = true;
+    }
+    const double t1 = now_ms();
+
+    Params P;
+    P.max_depth = max_depth; P.leaf_max = leaf_max; P.leaf_split = ctx->opt_leaf_split;
+    P.total_depth = std::min(kMaxKeyLevels, max_depth + (ctx->opt_leaf_split > 0 ? kExtraLevels : 0));
+    P.s3 = std::sqrt(3.0f) / 3;
+    const uint32_t n32 = (uint32_t)n;
+    const int wide = ctx->sm_count * 8;
+    static const bool trace = getenv("RTB200_TRACE") != nullptr;
+    double t_phase = t1;
+    auto trace_phase = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        const double t = now_ms();
+        fprintf(stderr, "[rtb200]   device octree: %s %.2f ms\n", what, t - t_phase);
+        t_phase = t;
+    };
+    RT_CUDA(ctx, D.stats.ensure(1)); RT_CUDA(ctx, D.centroid.ensure(3 * n));
+    for (int k = 0; k < 2; k++) { RT_CUDA(ctx, D.keys[k].ensure(n)); RT_CUDA(ctx, D.idx[k].ensure(n)); }
+    k_ob_init<<<1, 1, 0, st>>>(D.stats.p);
+    k_ob_centroids<<<wide, 256, 0, st>>>(D.xyz9.p, n32, D.centroid.p, D.stats.p);
+    k_ob_keys<<<wide, 256, 0, st>>>(D.centroid.p, n32, D.stats.p, P, D.keys[0].p, D.idx[0].p);
+
+    // ---- stable radix sort of (key, index), 8 bits per pass over the 3 * total_depth bits in use
+    const uint32_t n_units = (n32 + kSortUnit - 1) / kSortUnit;
+    const size_t n_hist = (size_t)256 * n_units;
+    const uint32_t hist_blocks = (uint32_t)((n_hist + kScanBlock - 1) / kScanBlock);
+    RT_CUDA(ctx, D.hist.ensure(n_hist));
+    int cur = 0;
+    const int passes = (3 * P.total_depth + 7) / 8;
+    auto scan = [&](uint32_t* data, size_t count, uint32_t* total) -> int {
+        const uint32_t blocks = (uint32_t)((count + kScanBlock - 1) / kScanBlock);
+        RT_CUDA(ctx, D.sums.ensure(std::max<uint32_t>(blocks, 1)));
+        k_scan_sums<<<blocks, 1024, 0, st>>>(data, count, D.sums.p);
+        k_scan_top<<<1, 1024, 0, st>>>(D.sums.p, blocks, total);
+        k_scan_apply<<<blocks, 1024, 0, st>>>(data, count, D.sums.p);
+        return RT_OK;
+    };
+    (void)hist_blocks;
+    for (int pass = 0; pass < passes; pass++) {
+        k_rs_count<<<(n_units + 3) / 4, 128, 0, st>>>(D.keys[cur].p, n32, 8 * pass, n_units, D.hist.p);
+        if (int r = scan(D.hist.p, n_hist, nullptr)) return r;
+        k_rs_scatter<<<(n_units + 3) / 4, 128, 0, st>>>(D.keys[cur].p, D.idx[cur].p, n32, 8 * pass, n_units, D.hist.p, D.keys[cur ^ 1].p, D.idx[cur ^ 1].p);
+        cur ^= 1;
+    }
+    const unsigned long long* keys = D.keys[cur].p;
+    const uint32_t* idx = D.idx[cur].p;                                         // (k_ob_refine reorders ranges of it in place)
+    trace_phase("keys + sort");
+
+    // ---- cells, level by level
+    size_t cap = 0;
+    auto cells_view = [&]() {
+        Cells C;
+        C.begin = D.c_begin.p; C.end = D.c_end.p; C.first_child = D.c_first.p; C.info = D.c_info.p; C.nr = D.c_nr.p; C.fr = D.c_fr.p;
+        C.size = D.c_size.p; C.rec = D.c_rec.p; C.block = D.c_block.p;
+        return C;
+    };
+    auto reserve_cells = [&](size_t want, size_t keep) -> int {
+        if (want <= cap) return RT_OK;
+        const size_t c = std::max(want, cap * 2);
+        RT_CUDA(ctx, grow_keep(D.c_begin, c, keep, st)); RT_CUDA(ctx, grow_keep(D.c_end, c, keep, st)); RT_CUDA(ctx, grow_keep(D.c_first, c, keep, st));
+        RT_CUDA(ctx, grow_keep(D.c_info, c, keep, st)); RT_CUDA(ctx, grow_keep(D.c_size, c, keep, st)); RT_CUDA(ctx, grow_keep(D.c_rec, c, keep, st));
+        RT_CUDA(ctx, grow_keep(D.c_block, c, keep, st)); RT_CUDA(ctx, grow_keep(D.c_nr, 7 * c, 7 * keep, st)); RT_CUDA(ctx, grow_keep(D.c_fr, 7 * c, 7 * keep, st));
+        cap = std::min({D.c_begin.n, D.c_end.n, D.c_first.n, D.c_info.n, D.c_size.n, D.c_rec.n, D.c_block.n, D.c_nr.n / 7, D.c_fr.n / 7});
+        return RT_OK;
+    };
+    cap = std::min({D.c_begin.n, D.c_end.n, D.c_first.n, D.c_info.n, D.c_size.n, D.c_rec.n, D.c_block.n, D.c_nr.n / 7, D.c_fr.n / 7});
+    if (int r = reserve_cells(n / 2 + 4096, 0)) return r;
+    {
+        const uint32_t root[4] = {0u, n32, 0u, 1u << 6};                        // begin, end, first child, info: a reference cell
+        RT_CUDA(ctx, cudaMemcpyAsync(D.c_begin.p, &root[0], 4, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(D.c_end.p, &root[1], 4, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(D.c_info.p, &root[3], 4, cudaMemcpyHostToDevice, st));
+        const uint32_t place[2] = {0u, 2u};                                     // the root's record and its children's block
+        RT_CUDA(ctx, cudaMemcpyAsync(D.c_rec.p, &place[0], 4, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaMemcpyAsync(D.c_block.p, &place[1], 4, cudaMemcpyHostToDevice, st));
+        RT_CUDA(ctx, cudaStreamSynchronize(st));                                // the sources are on this stack frame
+    }
+    std::vector<uint32_t> level_first, level_count;
+    level_first.push_back(0); level_count.push_back(1);
+    uint32_t* d_total = (uint32_t*)&D.stats.p->top_n;                           // borrowed until the top table is built
+    for (int depth = 0; depth <= P.max_depth + 16; depth++) {
+        const uint32_t lf = level_first.back(), lc = level_count.back();
+        RT_CUDA(ctx, D.counts.ensure(lc));
+        k_ob_split<<<(lc + 255) / 256, 256, 0, st>>>(keys, cells_view(), lf, lc, depth, P, D.counts.p, D.stats.p);
+        if (int r = scan(D.counts.p, lc, d_total)) return r;
+        uint32_t total = 0;
+        RT_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
+        RT_CUDA(ctx, cudaStreamSynchronize(st));
+        if (total == 0) break;
+        if ((size_t)lf + lc + total >= (size_t)0xffffffffu) return fail(ctx, RT_ERR_INVALID, "too many octree cells");
+        if (P.leaf_split > 0)
+            k_ob_refine<<<std::min<uint32_t>((lc + 7) / 8, (uint32_t)wide), 256, 0, st>>>(cells_view(), lf, lc, P, D.centroid.p, D.idx[cur].p, D.idx[cur ^ 1].p);
+        if (int r = reserve_cells((size_t)lf + lc + total, (size_t)lf + lc)) return r;
+        k_ob_children<<<(lc + 255) / 256, 256, 0, st>>>(keys, cells_view(), lf, lc, depth, P, D.counts.p, lf + lc);
+        level_first.push_back(lf + lc); level_count.push_back(total);
+    }
+    const uint32_t n_cells = level_first.back() + level_count.back();
+    const Cells C = cells_view();
+    trace_phase("cells");
+    // ---- leaf-order triangle arrays
+    k_ob_leaf_order<<<wide, 256, 0, st>>>(C, n_cells, idx, D.idx[cur ^ 1].p);
+    idx = D.idx[cur ^ 1].p;
+    RT_CUDA(ctx, ctx->d_tris.ensure(3 * n)); RT_CUDA(ctx, ctx->d_shade.ensure(2 * n)); RT_CUDA(ctx, ctx->d_orig.ensure(n)); RT_CUDA(ctx, ctx->d_leaf_of.ensure(n));
+    k_ob_triangles<<<wide, 256, 0, st>>>(D.xyz9.p, ctx->has_uv ? D.uv6.p : nullptr, ctx->has_mat ? D.mat.p : nullptr, idx, n32,
+                                         (float4*)ctx->d_tris.p, (float4*)ctx->d_shade.p, ctx->d_orig.p, ctx->d_leaf_of.p);
+    for (int l = (int)level_first.size() - 1; l >= 0; l--)
+        k_ob_bounds<<<(level_count[l] + 127) / 128, 128, 0, st>>>((const float4*)ctx->d_tris.p, C, level_first[l], level_count[l], P);
+    trace_phase("triangles + bounds");
+    uint32_t root_size = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&root_size, D.c_size.p, 4, cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    const uint64_t n_records = 2ull + root_size;
+    if (n_records >= (1ull << 28)) return fail(ctx, RT_ERR_INVALID, "scene needs %llu child records (limit 2^28)", (unsigned long long)n_records);
+    RT_CUDA(ctx, ctx->d_recs.ensure(4 * n_records));
+    RT_CUDA(ctx, ctx->d_top.ensure(4 * RT_TOP_RECORDS));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_recs.p, 0, 4 * n_records * sizeof(float4), st));
+    for (size_t l = 0; l < level_first.size(); l++)
+        k_ob_place<<<(level_count[l] + 255) / 256, 256, 0, st>>>(C, level_first[l], level_count[l], P);
+    k_ob_records<<<(n_cells + 255) / 256, 256, 0, st>>>(C, n_cells, P, (float4*)ctx->d_recs.p);
+    k_ob_top_table<<<1, 32, 0, st>>>((float4*)ctx->d_recs.p, (float4*)ctx->d_top.p, D.stats.p);
+    Stats hs;
+    F4 root_rec[2];
+    RT_CUDA(ctx, cudaMemcpyAsync(&hs, D.stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaMemcpyAsync(root_rec, ctx->d_recs.p, sizeof(root_rec), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(ctx, cudaStreamSynchronize(st));
+    RT_CUDA(ctx, cudaGetLastError());
+    const double t2 = now_ms();
+
+    ctx->top_n = (int)hs.top_n;
+    ctx->n_tris = n32;
+    ctx->root_lo[0] = root_rec[0].x; ctx->root_lo[1] = root_rec[0].z; ctx->root_lo[2] = root_rec[1].x;
+    ctx->root_hi[0] = root_rec[0].y; ctx->root_hi[1] = root_rec[0].w; ctx->root_hi[2] = root_rec[1].y;
+    RtBvhInfo& bi = ctx->info;
+    bi.triangles = n;
+    bi.interior = hs.interior;
+    bi.nodes = 1 + 8 * hs.interior;                                             // every split allocates all 8 children (bvh.h:159-166)
+    bi.leaves = bi.nodes - bi.interior;
+    bi.empty_leaves = 8 * hs.interior - hs.nonempty_children;
+    bi.max_depth_reached = hs.max_depth; bi.max_leaf_size = hs.max_leaf;
+    bi.child_records = n_records;
+    bi.device_bytes = (4 * n_records + 3 * n + 2 * n) * sizeof(F4) + n * sizeof(int32_t);
+    bi.build_ms = t2 - t1;
+    bi.upload_ms = t1 - t0;
+    ctx->bvh_valid = true;
+    if (getenv("RTB200_TRACE"))
+        fprintf(stderr, "[rtb200] device octree: %u cells on %zu levels, %llu records, upload %.1f ms, build %.1f ms\n", n_cells, level_first.size(),
+                (unsigned long long)n_records, t1 - t0, t2 - t1);
+    return RT_OK;
+}
+
 bool tune_packets_hint(const RtContext* ctx) { return ctx->tune.packets != 0; }
 
 int ensure_stack(RtContext* ctx, const RtSettings* s)
@@ -544,7 +767,7 @@ void rt_destroy(RtContext* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_recs.release(); ctx->d_top.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
-    ctx->d_super.release(); ctx->d_frame.release();
+    ctx->d_super.release(); ctx->d_frame.release(); ctx->db.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
     for (auto& qs : ctx->qs) qs.release();
     for (auto st : ctx->lane_stream) if (st) cudaStreamDestroy(st);
@@ -598,6 +821,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         return RT_OK;
     case RT_OPT_FUSED_ITEMS: ctx->tune.fused = value != 0; return RT_OK;
     case RT_OPT_TOP_TABLE: ctx->opt_top_table = value != 0; return RT_OK;
+    case RT_OPT_DEVICE_BUILD: ctx->opt_device_build = value != 0; return RT_OK;
     case RT_OPT_SHADOW_SORT:
         if (value < 0 || value > 2) return fail(ctx, RT_ERR_INVALID, "shadow sort %lld outside [0,2]", (long long)value);
         ctx->opt_shadow_sort = (int)value;
@@ -637,6 +861,8 @@ int rt_set_triangles(RtContext* ctx, const float* xyz9, const float* uv6, const 
     ctx->min_mat_index = n ? (mat ? *std::min_element(mat, mat + n) : -1) : 0;
     ctx->max_mat_index = n ? (mat ? *std::max_element(mat, mat + n) : -1) : -1;
     ctx->bvh_valid = false;
+    ctx->db.tris_on_device = false;
+    ctx->db.host_pending.clear();
     return RT_OK;
 }
 
@@ -648,6 +874,8 @@ int rt_build_bvh(RtContext* ctx, int max_depth, int leaf_max_obj_count)
     if (leaf_max_obj_count < 0) return fail(ctx, RT_ERR_INVALID, "leaf_max_obj_count %d", leaf_max_obj_count);
     const size_t n = ctx->xyz9.size() / 9;
     ctx->bvh_valid = false;                              // whatever happens below, the previous tree is gone
+    if (ctx->opt_device_build && n > 0) return build_bvh_device(ctx, max_depth, leaf_max_obj_count);
+    apply_pending_host_transforms(ctx);
     double t0 = now_ms();
     FlatScene flat;
     build_flat_scene(ctx->xyz9.data(), ctx->has_uv ? ctx->uv6.data() : nullptr, ctx->has_mat ? ctx->mat.data() : nullptr, n,
@@ -704,15 +932,20 @@ int rt_bvh_info(const RtContext* ctx, RtBvhInfo* out)
 int rt_transform_triangles(RtContext* ctx, const float m[16], int max_depth, int leaf_max_obj_count)
 {
     if (!ctx || !m) return RT_ERR_INVALID;
+    if (int r = bind(ctx)) return r;
     M4 t;
     memcpy(t.m, m, sizeof(t.m));
-    const long long n = (long long)(ctx->xyz9.size() / 3);
-#pragma omp parallel for schedule(static)
-    for (long long i = 0; i < n; i++) {                                            // Transform::operator()(Triangle), mat.cpp:133-140
-        V3 p = xform_point(t, v3(ctx->xyz9[3 * i], ctx->xyz9[3 * i + 1], ctx->xyz9[3 * i + 2]));
-        ctx->xyz9[3 * i] = p.x; ctx->xyz9[3 * i + 1] = p.y; ctx->xyz9[3 * i + 2] = p.z;
-    }
     ctx->bvh_valid = false;
+    if (ctx->opt_device_build && ctx->db.tris_on_device && !ctx->xyz9.empty()) {
+        // the vertices are transformed where the builder reads them; the host copy catches up only if it is ever needed
+        devbuild::k_ob_transform<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->db.xyz9.p, ctx->xyz9.size() / 3, t);
+        RT_CUDA(ctx, cudaGetLastError());
+        ctx->db.host_pending.push_back(t);
+    } else {
+        apply_pending_host_transforms(ctx);
+        transform_host_vertices(ctx, t);
+        ctx->db.tris_on_device = false;
+    }
     return rt_build_bvh(ctx, max_depth, leaf_max_obj_count);
 }
 

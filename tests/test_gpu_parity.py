@@ -389,7 +389,7 @@ def test_hair_scene_vs_oracle(cuda_lib, oracle):
         assert np.array_equal(r.get_image(), img), opts
         r.ctx.set_option(api.RT_OPT_PACKETS, 1)
         r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -16)
-        r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1); r.ctx.set_option(api.RT_OPT_SHADOW_SORT, 1)
+        r.ctx.set_option(api.RT_OPT_SCREEN_CULL, 1); r.ctx.set_option(api.RT_OPT_SHADOW_SORT, 2)
         r.ctx.set_option(api.RT_OPT_FUSED_ITEMS, 0)
     r.close()
 
@@ -432,6 +432,102 @@ def test_light_space_queue_order_never_changes_a_frame(cuda_lib, robot, light):
     for k in ("primary_rays", "shadow_rays", "primary_hits"):
         assert out[0][1][k] == out[1][1][k]
     assert out[0][1]["kernel_launches"] > out[1][1]["kernel_launches"]
+
+
+STAT_KEYS = ("triangles", "nodes", "interior", "leaves", "empty_leaves", "max_depth_reached", "max_leaf_size")
+
+
+@pytest.mark.parametrize("params", [(12, 40), (10, 8), (3, 2), (0, 5), (20, 1)])
+@pytest.mark.parametrize("leaf_split", [8, 0])
+def test_device_build_is_the_host_build(cuda_lib, oracle, robot, golden_rays, params, leaf_split):
+    """RT_OPT_DEVICE_BUILD: the octree built on the GPU (octree_device.cuh) against the host builder (octree_build.cpp)
+    and the oracle's BVH::BVH restatement: the statistics of the reference-shaped tree, closest hits (ids, t, u, v
+    bit-exact), a frame, and the tallies of the single-ray traversal (same cells, same leaves in the same order, same
+    refinement groups below oversized leaves)."""
+    depth, leaf = params
+    kw, mats, tex = common.config_table(robot["materials"])["cfg1"]
+    kw = dict(kw, bvh_max_depth=depth, bvh_leaf_object_count=leaf)
+    o, d = golden_rays["o"], golden_rays["d"]
+    out = []
+    for device in (1, 0):
+        r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+        r.ctx.set_option(api.RT_OPT_DEVICE_BUILD, device)
+        r.ctx.set_option(api.RT_OPT_LEAF_SPLIT, leaf_split)
+        r.reconstruct_bvh_new()
+        info = dict(r.bvh_info)
+        hits = r.ctx.intersect(o, d)
+        r.ctx.set_option(api.RT_OPT_COUNT_WORK, 1)
+        r.ctx.set_option(api.RT_OPT_PACKETS, 0)
+        r.ray_trace()
+        out.append((info, hits, r.get_image().copy(), r.last_stats().as_dict()))
+        r.close()
+    (di, dh, dimg, dst), (hi, hh, himg, hst) = out
+    for k in STAT_KEYS:
+        assert di[k] == hi[k], (k, di[k], hi[k])
+    want = oracle.bvh(robot["xyz9"], depth, leaf).intersect(o, d)
+    for g, h, w in zip(dh, hh, want):
+        assert np.array_equal(g, h) and np.array_equal(g, w)
+    assert np.array_equal(dimg, himg)
+    assert di["child_records"] >= hi["child_records"]             # same records; the device layout pads every block to an even size
+    for k in ("primary_volume_tests", "primary_triangle_tests", "shadow_volume_tests", "shadow_triangle_tests"):
+        assert dst[k] == hst[k], (k, dst[k], hst[k])
+
+
+def test_device_build_edge_cases(cuda_lib, oracle):
+    """One triangle, 60 coincident triangles (a chain of single-child cells, then a leaf that cannot be refined), a
+    degenerate triangle among others, and all centroids on one plane: device build == host build."""
+    rng = np.random.default_rng(5)
+    one = np.float32([[0, 0, -3, 1, 0, -3, 0, 1, -3]])
+    many = rng.uniform(-1, 1, (500, 9)).astype(np.float32) + np.float32([0, 0, -3] * 3)
+    flat = many.copy(); flat[:, 2::3] = -3.0
+    scenes_ = {"one": one, "coincident": np.repeat(one, 60, 0), "degenerate": np.concatenate([many, np.float32([[0.2, 0.2, -3] * 3])]), "flat": flat}
+    o, d = common.random_rays(4000, 3, (-1, -1, 0), (1, 1, 0.5))
+    d = (np.float32([0, 0, -3]) + rng.uniform(-1, 1, (4000, 3)).astype(np.float32) - o).astype(np.float32)
+    for name, xyz9 in scenes_.items():
+        res = []
+        for device in (1, 0):
+            ctx = api.Context(0, cuda_lib)
+            ctx.set_option(api.RT_OPT_DEVICE_BUILD, device)
+            ctx.set_triangles(xyz9, None, None)
+            info = ctx.build_bvh(12, 4)
+            res.append((info, ctx.intersect(o, d)))
+            ctx.close()
+        for k in STAT_KEYS:
+            assert res[0][0][k] == res[1][0][k], (name, k)
+        # (overlapping coplanar triangles tie on t across leaves; the reference keeps the first in traversal order there, this
+        # library the lowest index -- "flat" is compared between the two builders only)
+        want = res[1][1] if name == "flat" else oracle.bvh(xyz9, 12, 4).intersect(o, d)
+        for g, h, w in zip(res[0][1], res[1][1], want):
+            assert np.array_equal(g, h) and np.array_equal(g, w), name
+
+
+def test_device_transform_and_rebuild(cuda_lib, oracle, robot):
+    """Renderer::set_object_transform (renderer.cpp:214-224) with the triangles resident on the device: two successive
+    transforms, each followed by a device rebuild, give the frame of a host transform + host build; switching to the host
+    builder afterwards sees the transformed vertices."""
+    kw = dict(image_width=160, image_height=90, compute_shadows=1)
+    m1, m2 = np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)
+    m1[0, 3], m1[2, 3] = 0.5, -1.0
+    c, s_ = np.float32(np.cos(0.3)), np.float32(np.sin(0.3))
+    m2[0, 0], m2[0, 2], m2[2, 0], m2[2, 2], m2[1, 3] = c, s_, -s_, c, 0.25
+    imgs, infos = [], []
+    for device in (1, 0):
+        r = common.product_renderer(cuda_lib, robot, kw, robot["materials"], {})
+        r.ctx.set_option(api.RT_OPT_DEVICE_BUILD, device)
+        r.reconstruct_bvh_new()
+        r.set_object_transform(m1)
+        r.set_object_transform(m2)
+        r.ray_trace()
+        imgs.append(r.get_image().copy()); infos.append(dict(r.bvh_info))
+        if device:
+            r.ctx.set_option(api.RT_OPT_DEVICE_BUILD, 0)       # the host copy of the vertices catches up with the device copy
+            r.reconstruct_bvh_new()
+            r.ray_trace()
+            assert np.array_equal(r.get_image(), imgs[0])
+        r.close()
+    assert np.array_equal(imgs[0], imgs[1]) and (imgs[0] != imgs[0][0, 0]).any()
+    for k in STAT_KEYS:
+        assert infos[0][k] == infos[1][k], k
 
 
 def test_two_lanes_never_change_a_frame(cuda_lib, robot):
@@ -553,7 +649,7 @@ def test_hair_fullsize_band(cuda_lib, oracle, golden_fullsize):
         assert np.array_equal(g, w)
     # scheduling knobs leave the 4K frame bit-identical
     for opt, val, back in ((api.RT_OPT_PACKETS, 0, 1), (api.RT_OPT_SCREEN_CULL, 0, 1), (api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0),
-                           (api.RT_OPT_SHADOW_SORT, 0, 1)):
+                           (api.RT_OPT_SHADOW_SORT, 0, 2)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(r.get_image(), img), opt
@@ -610,11 +706,26 @@ def test_full_size_properties(cuda_lib, oracle, big_sphere):
     # (3) idempotence: same frame twice; and the scheduling knobs at full size (item passes as separate launches, 4 chunks in flight)
     r.ray_trace()
     assert np.array_equal(full, r.get_image())
-    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0), (api.RT_OPT_SHADOW_SORT, 0, 1)):
+    for opt, val, back in ((api.RT_OPT_FUSED_ITEMS, 1, 0), (api.RT_OPT_LANES, 4, 1), (api.RT_OPT_TOP_TABLE, 1, 0), (api.RT_OPT_SHADOW_SORT, 0, 2)):
         r.ctx.set_option(opt, val)
         r.ray_trace()
         assert np.array_equal(full, r.get_image()), opt
         r.ctx.set_option(opt, back)
+    # (3b) the tree was built on the device (the default); the host builder gives the same statistics, hits and frame
+    dev_info = dict(info)
+    r.reconstruct_bvh_new()                                    # once more with the builder's buffers allocated: what a transform + rebuild costs
+    assert r.bvh_info["build_ms"] < 50.0 and r.bvh_info["upload_ms"] < 1.0, (r.bvh_info["build_ms"], r.bvh_info["upload_ms"])
+    for k in STAT_KEYS + ("child_records",):
+        assert r.bvh_info[k] == dev_info[k]
+    r.ctx.set_option(api.RT_OPT_DEVICE_BUILD, 0)
+    r.reconstruct_bvh_new()
+    for k in STAT_KEYS:
+        assert r.bvh_info[k] == dev_info[k], (k, r.bvh_info[k], dev_info[k])
+    for g, w in zip(r.ctx.intersect(o, d), a):
+        assert np.array_equal(g, w)
+    r.ray_trace()
+    assert np.array_equal(full, r.get_image())
+    r.ctx.set_option(api.RT_OPT_DEVICE_BUILD, 1)
     # (4) a band of the frame against the oracle (the oracle needs ~10 s for these rows at this size)
     orc = common.oracle_renderer(oracle, scene, kw, mats, {})
     rows = list(range(4000, 4640, 64))
