@@ -57,8 +57,8 @@ enum {
 };
 
 /* POD mirror of `RenderSettings` (tp2/projets/renderer/rendererSettings.h:6-105), same defaults via
- * rt_default_settings().  Switches that leave the path (rasterizer, SSAO)
- * are carried so a caller can pass its struct through; rt_render() refuses them (RT_ERR_UNSUPPORTED). */
+ * rt_default_settings().  The switch that leaves the path (hybrid rasterizer) is carried so a caller can pass its
+ * struct through; rt_render() refuses it (RT_ERR_UNSUPPORTED). */
 typedef struct RtSettings {
     int32_t image_width;
     int32_t image_height;
@@ -71,7 +71,7 @@ typedef struct RtSettings {
     int32_t enable_bvh;                   /* must be 1 */
     int32_t bvh_max_depth;
     int32_t bvh_leaf_object_count;
-    int32_t enable_ssao;                  /* must be 0 */
+    int32_t enable_ssao;                  /* screen-space ambient occlusion post-process (renderer.cpp:1229-1434), see rt_set_projection */
     int32_t enable_ambient;
     int32_t enable_diffuse;
     int32_t enable_specular;
@@ -91,6 +91,10 @@ typedef struct RtSettings {
     /* RenderSettings::displacement_mapping_strength / parallax_mapping_steps, rendererSettings.h:94-95 (0.02, 32). */
     float displacement_mapping_strength;
     int32_t parallax_mapping_steps;
+    /* RenderSettings::ssao_sample_count / ssao_radius / ssao_amount, rendererSettings.h:69-73 (64, 0.5, 1.0). */
+    int32_t ssao_sample_count;
+    float ssao_radius;
+    float ssao_amount;
 } RtSettings;
 
 /* Texture slots: Renderer::set_{ao,diffuse,normal,roughness}_map / set_skysphere / set_skybox, renderer.cpp:194-201.
@@ -276,6 +280,11 @@ void rt_perspective_inverse(float fov, float aspect, float znear, float zfar, fl
 void rt_invert_transform(const float m[16], float out[16]);
 /* Transform::operator()(const Point&) -- mat.cpp:83-100 (e.g. Camera::_position = transform(Point(0,0,0))). */
 void rt_transform_point(const float m[16], const float p[3], float out[3]);
+
+/* Camera::_perspective_proj_mat, _fov, _aspect_ratio (scene/camera.cpp:5-19): what Renderer::post_process_ssao_SIMD reads
+ * (renderer.cpp:1249,1283-1326).  Needed only with RtSettings::enable_ssao; the matrix is Perspective(fov, aspect, znear,
+ * zfar) in the reference's float arithmetic (mat.cpp:307-319).  fov in degrees. */
+int rt_set_projection(RtContext* ctx, float fov, float aspect, float znear, float zfar);
 
 /* Renderer::set_light_position -- renderer.cpp:191. */
 int rt_set_light(RtContext* ctx, const float position[3]);

@@ -170,10 +170,8 @@ public:
         _image.resize((size_t)_settings.image_width * _settings.image_height);
         check(rt_render(_ctx, &_settings, _image.data(), &_stats));
     }
-    void post_process()                                                                                    // renderer.cpp:1118-1124
-    {
-        if (_settings.enable_ssao) throw Error(RT_ERR_UNSUPPORTED, "SSAO stays on the host");
-    }
+    // renderer.cpp:1118-1124: SSAO (enable_ssao) and the SSAA resolve have already run on the device, inside ray_trace()
+    void post_process() {}
 
     // Renderer::get_image(): ARGB32, row 0 = bottom row (renderer.cpp:1086); copy_to() fills a QImage-like object.
     const std::vector<uint32_t>& get_image() const { return _image; }
@@ -199,6 +197,7 @@ private:
         float proj_inv[16];
         rt_perspective_inverse(_fov, _aspect, 0.1f, 1000.0f, proj_inv);                                    // Camera(), scene/camera.h:11
         check(rt_set_camera(_ctx, proj_inv, _camera_to_world, _position));
+        check(rt_set_projection(_ctx, _fov, _aspect, 0.1f, 1000.0f));                                      // read by the SSAO pass only
     }
 
     RtContext* _ctx = nullptr;

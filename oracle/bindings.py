@@ -45,7 +45,8 @@ SETTINGS_FIELDS = [
 
 class RtSettings(C.Structure):
     _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32), ("displacement_mapping_strength", C.c_float),
-                                                              ("parallax_mapping_steps", C.c_int32)]
+                                                              ("parallax_mapping_steps", C.c_int32),
+                                                              ("ssao_sample_count", C.c_int32), ("ssao_radius", C.c_float), ("ssao_amount", C.c_float)]
 
 
 def default_settings(**kw) -> RtSettings:
@@ -66,10 +67,11 @@ def default_settings(**kw) -> RtSettings:
     s.rng_seed = 0
     s.displacement_mapping_strength = 0.02
     s.parallax_mapping_steps = 32
+    s.ssao_sample_count, s.ssao_radius, s.ssao_amount = 64, 0.5, 1.0          # rendererSettings.h:69-73
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
-        setattr(s, k, float(v) if k == "displacement_mapping_strength" else int(v))
+        setattr(s, k, float(v) if k in ("displacement_mapping_strength", "ssao_radius", "ssao_amount") else int(v))
     return s
 
 
@@ -152,9 +154,12 @@ class CpuTracer:
         f("omp_max_threads").restype = C.c_int
         if kind != "oracle":
             f("last_hit_count").restype = C.c_longlong
+            f("renderer_render_ssao").restype = C.c_double
+            f("renderer_render_ssao").argtypes = [C.c_void_p, UP, C.c_uint, UP, C.c_int]
             f("load_obj").restype = C.c_int
             f("load_obj").argtypes = [C.c_char_p, FP, FP, FP, IP, C.POINTER(RtMaterial), C.c_int, IP]
         else:
+            f("renderer_render_ssao").argtypes = [C.c_void_p, UP, C.c_int, C.c_int, UP]
             f("bvh_count").restype = C.c_double
             f("bvh_count").argtypes = [C.c_void_p, FP, FP, C.c_size_t, C.POINTER(C.c_uint64), C.c_int]
             f("renderer_count_rows").argtypes = [C.c_void_p, FP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int]
@@ -330,6 +335,22 @@ class CpuRenderer:
         out = np.zeros((s.image_height, s.image_width), np.uint32)
         ms = self.tr._fn("renderer_render")(self.h, _ptr(out, C.c_uint32), threads)
         return out, ms
+
+    def render_ssao(self, srand_seed=None, ref_seeds9=None, n_rand=64, threads=0):
+        """ray_trace() with the G-buffers + post_process() with enable_ssao (renderer.cpp:1229-1434).
+        Compiled reference: the SSAO pass runs on one thread after srand(srand_seed); returns (argb, rand_values) where
+        rand_values are the first n_rand values std::rand() gives after that srand.
+        Oracle: ref_seeds9 = None -> the per-pixel stream (settings.rng_seed); else the 9 generator seeds of a
+        single-threaded reference run (8 lanes + scalar), reference order; returns (argb, None)."""
+        s = self.settings
+        out = np.zeros((s.image_height, s.image_width), np.uint32)
+        if self.tr.kind != "oracle":
+            rv = np.zeros(n_rand, np.uint32)
+            self.tr._fn("renderer_render_ssao")(self.h, _ptr(out, C.c_uint32), int(srand_seed), _ptr(rv, C.c_uint32), n_rand)
+            return out, rv
+        seeds = None if ref_seeds9 is None else np.ascontiguousarray(ref_seeds9, dtype=np.uint32)
+        self.tr._fn("renderer_render_ssao")(self.h, _ptr(out, C.c_uint32), threads, 0 if seeds is None else 1, _ptr(seeds, C.c_uint32))
+        return out, None
 
     def trace_rows(self, row_begin=0, row_end=None, row_step=1, reseed=True, threads=0, want_image=True):
         """Seeded pixel loop on the supersampled frame; returns (argb_super[H',W'], ms)."""

@@ -870,7 +870,7 @@ inline uint32_t quantise(Col c)
 
 // Pixel loop of Renderer::ray_trace -- renderer.cpp:1082-1115
 double trace_rows(const Renderer& r, const M4& c2w, uint32_t* argb_super, int row_begin, int row_end, int row_step,
-                  int threads, RenderCounters* total)
+                  int threads, RenderCounters* total, float* zbuf = nullptr, V3* nbuf = nullptr)
 {
     int rw, rh;
     r.super_dims(rw, rh);
@@ -894,6 +894,10 @@ double trace_rows(const Renderer& r, const M4& c2w, uint32_t* argb_super, int ro
                 bool found = false;
                 Hit hit;
                 Col c = r.trace_ray(ray, hit, 0, found, rng, total ? &local : nullptr, false);
+                if (found && zbuf) {                                                 // renderer.cpp:1104-1111
+                    zbuf[(size_t)py * rw + px] = -(ray.o.z + ray.d.z * hit.t);
+                    nbuf[(size_t)py * rw + px] = hit.normal;
+                }
                 if (argb_super) argb_super[(size_t)py * rw + px] = quantise(c);
             }
         }
@@ -925,6 +929,217 @@ void downscale(const uint32_t* in, int w, int h, int factor, uint32_t* out)
             ab = ab / (factor * factor);
             out[(size_t)y * dw + x] = 0xff000000u | ((uint32_t)(ar & 0xff) << 16) | ((uint32_t)(ag & 0xff) << 8) | (uint32_t)(ab & 0xff);
         }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Renderer::post_process_ssao_SIMD -- renderer.cpp:1229-1434, with its helpers SIMD/m256Vector.cpp:81-110,
+// SIMD/m256Point.cpp:3-31 and renderer/xorshift.h:8-65.  The reference processes 8 pixels per AVX2 register; every
+// lane's arithmetic is restated here as scalar float operations in the same order (one explicit fmaf per _mm256_fmadd_ps),
+// so one pixel costs one call of ssao_simd_pixel.  The columns the last partial group of a row leaves over go through
+// the reference's scalar loop (renderer.cpp:1358-1407), which uses other formulas (double arithmetic and truncation for
+// the sampled pixel, unsigned random numbers): ssao_scalar_pixel.
+//
+// Random numbers.  The reference seeds one 8-lane generator and one scalar generator per OpenMP thread from std::rand()
+// and the thread number (renderer.cpp:1254-1266) and draws from them in processing order, which is not reproducible.
+// Two disciplines are offered here:
+//   SSAO_RNG_REFERENCE_ORDER  one 8-lane generator + one scalar generator with caller-given seeds, rows and 8-pixel groups
+//                             in the order of a single-threaded run, groups without geometry skipped (renderer.cpp:1277)
+//                             -- what the reference does with OMP_NUM_THREADS=1 after srand(); pins the arithmetic against
+//                             the compiled reference (tests/test_oracle_vs_reference.py);
+//   SSAO_RNG_PER_PIXEL        every pixel owns a generator seeded pixel_seed(py * W' + px, rng_seed + kSsaoSeedOffset):
+//                             the shared stream of the CUDA path (same arithmetic, order-independent).
+constexpr uint32_t kSsaoSeedOffset = 0x9e3779b9u;
+enum { SSAO_RNG_PER_PIXEL = 0, SSAO_RNG_REFERENCE_ORDER = 1 };
+
+inline uint32_t xs_next(uint32_t& st)                                                 // xorshift.h:13-22,43-52
+{
+    uint32_t x = st;
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 5;
+    return st = x;
+}
+// __m256_XorShiftGenerator::get_rand_bilateral / get_rand_lateral -- xorshift.h:24-32 (_mm256_cvtepi32_ps is SIGNED)
+inline float simd_bilateral(uint32_t& st) { return (float)(int32_t)xs_next(st) / (float)std::numeric_limits<int32_t>::max(); }
+inline float simd_lateral(uint32_t& st) { return ((float)(int32_t)xs_next(st) / (float)std::numeric_limits<int32_t>::max() + 1.0f) * 0.5f; }
+// XorShiftGenerator::get_rand_bilateral / get_rand_lateral -- xorshift.h:54-62
+inline float scalar_bilateral(uint32_t& st) { return xs_next(st) / (float)std::numeric_limits<uint32_t>::max() * 2 - 1; }
+inline float scalar_lateral(uint32_t& st) { return xs_next(st) / (float)std::numeric_limits<uint32_t>::max(); }
+
+// _mm256_cvtps_epi32: round to nearest even; NaN and out-of-range give the "integer indefinite" 0x80000000
+inline int32_t cvtps_epi32(float f)
+{
+    if (!(f >= -2147483648.0f && f < 2147483648.0f)) return std::numeric_limits<int32_t>::min();
+    return (int32_t)std::nearbyintf(f);
+}
+// (int) of a double as x86 does it (cvttsd2si): truncation, indefinite when out of range
+inline int32_t cvttsd_epi32(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return std::numeric_limits<int32_t>::min();
+    return (int32_t)v;
+}
+
+struct SsaoFrame {
+    int rw, rh;
+    const float* z;
+    const V3* n;
+    M4 proj;                     // Camera::_perspective_proj_mat
+    float aspect;
+    float fov_mult_simd;         // (float)std::tan(fov / 2 / 180 * M_PI), renderer.cpp:1249
+    float fov_mult_scalar;       // std::tan(radians(fov / 2)) in float, renderer.cpp:1369
+    int samples;
+    float radius;
+};
+
+// One lane of the AVX2 loop body, renderer.cpp:1283-1355.  Returns the lane's pixel_occlusion.
+int ssao_simd_pixel(const SsaoFrame& f, int x, int y, uint32_t& rng)
+{
+    const float view_z = f.z[(size_t)y * f.rw + x];
+    const bool has_geometry = view_z != INFINITY;                                   // infinity_mask (_CMP_NEQ_OQ)
+    float y_ndc = (float)y / (float)f.rh;
+    y_ndc = y_ndc * 2.0f;
+    y_ndc = y_ndc - 1.0f;
+    const float xs = (float)(x & 7) + (float)(x & ~7);
+    float x_ndc = xs / (float)f.rw;
+    x_ndc = x_ndc * 2.0f;
+    x_ndc = x_ndc - 1.0f;
+    const float view_ray_x = x_ndc * (f.fov_mult_simd * f.aspect);
+    const float view_ray_y = y_ndc * f.fov_mult_simd;
+    const V3 P = v3(view_z * view_ray_x, view_z * view_ray_y, view_z * -1.0f);
+    const V3 nb = f.n[(size_t)y * f.rw + x];
+    const float n_len = std::sqrt(nb.x * nb.x + (nb.y * nb.y + nb.z * nb.z));      // _mm256_length: x + (y + z)
+    const float n_inv = 1.0f / n_len;
+    const V3 normal = v3(nb.x * n_inv, nb.y * n_inv, nb.z * n_inv);
+    int occlusion = 0;
+    for (int i = 0; i < f.samples; i++) {
+        const float rx = simd_bilateral(rng), ry = simd_bilateral(rng), rz = simd_bilateral(rng);
+        const float r_inv = 1.0f / std::sqrt(rx * rx + (ry * ry + rz * rz));
+        V3 rs = v3(rx * r_inv, ry * r_inv, rz * r_inv);
+        const float k = simd_lateral(rng) + 0.0001f;
+        rs = v3(rs.x * k, rs.y * k, rs.z * k);
+        rs = v3(rs.x * f.radius, rs.y * f.radius, rs.z * f.radius);
+        rs = v3(rs.x + P.x, rs.y + P.y, rs.z + P.z);
+        const V3 vd = v3(rs.x - P.x, rs.y - P.y, rs.z - P.z);
+        const float d = vd.x * normal.x + (vd.y * normal.y + vd.z * normal.z);       // _mm256_dot_product: x + (y + z)
+        const float flip = d < 0.0f ? 1.0f : 0.0f;                                   // _CMP_LT_OQ & ones
+        const V3 back = v3((P.x - rs.x) * 2.0f, (P.y - rs.y) * 2.0f, (P.z - rs.z) * 2.0f);
+        rs = v3(rs.x + back.x * flip, rs.y + back.y * flip, rs.z + back.z * flip);
+        const float (*m)[4] = f.proj.m;                                              // __m256Point::transform
+        const float xt = std::fmaf(m[0][0], rs.x, std::fmaf(m[0][1], rs.y, std::fmaf(m[0][2], rs.z, m[0][3])));
+        const float yt = std::fmaf(m[1][0], rs.x, std::fmaf(m[1][1], rs.y, std::fmaf(m[1][2], rs.z, m[1][3])));
+        const float wt = std::fmaf(m[3][0], rs.x, std::fmaf(m[3][1], rs.y, std::fmaf(m[3][2], rs.z, m[3][3])));
+        const float w = 1.0f / wt;
+        const float ndc_x = xt * w, ndc_y = yt * w;
+        int32_t px = cvtps_epi32(((ndc_x + 1.0f) * 0.5f) * (float)f.rw);
+        int32_t py = cvtps_epi32(((ndc_y + 1.0f) * 0.5f) * (float)f.rh);
+        px = std::max(std::min(px, cvtps_epi32((float)f.rw - 1.0f)), 0);
+        py = std::max(std::min(py, cvtps_epi32((float)f.rh - 1.0f)), 0);
+        const float sample_geometry_depth = -1.0f * f.z[(size_t)px + (size_t)py * f.rw];
+        const bool in_range = std::fabs(sample_geometry_depth - P.z) <= f.radius;   // _CMP_LE_OQ
+        const bool behind = rs.z < sample_geometry_depth;                            // _CMP_LT_OQ
+        if (in_range && behind && has_geometry) occlusion++;
+    }
+    return occlusion;
+}
+
+// The scalar loop for the left-over columns, renderer.cpp:1358-1407 (called for pixels with geometry only).
+int ssao_scalar_pixel(const SsaoFrame& f, int x, int y, uint32_t& rng)
+{
+    float x_ndc = (float)x / f.rw * 2 - 1;
+    float y_ndc = (float)y / f.rh * 2 - 1;
+    float view_z = f.z[(size_t)y * f.rw + x];
+    float view_ray_x = x_ndc * f.aspect * f.fov_mult_scalar;
+    float view_ray_y = y_ndc * f.fov_mult_scalar;
+    V3 P = v3(view_ray_x * view_z, view_ray_y * view_z, -view_z);
+    V3 normal = normalize(f.n[(size_t)y * f.rw + x]);
+    int occlusion = 0;
+    for (int i = 0; i < f.samples; i++) {
+        float rx = scalar_bilateral(rng);
+        float ry = scalar_bilateral(rng);
+        float rz = scalar_bilateral(rng);
+        V3 rs = normalize(v3(rx, ry, rz));
+        rs = scale(scalar_lateral(rng) + 0.0001f, rs);
+        rs = scale(f.radius, rs);
+        rs = add(rs, P);
+        if (dot(sub(rs, P), normal) < 0) rs = add(rs, scale(2, sub(P, rs)));
+        V3 ndc = xform_point(f.proj, rs);
+        int px = cvttsd_epi32((ndc.x + 1) * 0.5 * f.rw);
+        int py = cvttsd_epi32((ndc.y + 1) * 0.5 * f.rh);
+        px = std::min(std::max(0, px), f.rw - 1);
+        py = std::min(std::max(0, py), f.rh - 1);
+        float sample_geometry_depth = -f.z[(size_t)py * f.rw + px];
+        if (std::abs(sample_geometry_depth - P.z) > f.radius) continue;
+        if (rs.z < sample_geometry_depth) occlusion++;
+    }
+    return occlusion;
+}
+
+// ao[] for the whole frame, then the 7x7 blur applied to the image (renderer.cpp:1411-1431).
+void ssao_post_process(const SsaoFrame& f, uint32_t* argb_super, uint32_t rng_seed, float amount, int rng_mode, const uint32_t* ref_seeds9)
+{
+    std::vector<int> ao((size_t)f.rw * f.rh, 0);
+    const int leftover = f.rw % 8;
+    if (rng_mode == SSAO_RNG_REFERENCE_ORDER) {
+        uint32_t lanes[8], scalar = ref_seeds9[8];
+        for (int l = 0; l < 8; l++) lanes[l] = ref_seeds9[l];
+        for (int y = 0; y < f.rh; y++) {
+            for (int x = 0; x + 8 <= f.rw; x += 8) {                                 // (the reference's partial group reads past the row)
+                bool any = false;
+                for (int l = 0; l < 8; l++) any |= f.z[(size_t)y * f.rw + x + l] != INFINITY;
+                if (!any) continue;                                                  // renderer.cpp:1276-1278
+                // the 8 lanes draw in lockstep, each from its own state: lane by lane is the same sequence per lane
+                for (int l = 0; l < 8; l++) ao[(size_t)y * f.rw + x + l] = ssao_simd_pixel(f, x + l, y, lanes[l]);
+            }
+            for (int x = f.rw - leftover; x < f.rw; x++) {
+                if (f.z[(size_t)y * f.rw + x] == INFINITY) continue;
+                ao[(size_t)y * f.rw + x] = ssao_scalar_pixel(f, x, y, scalar);
+            }
+        }
+    } else {
+#pragma omp parallel for schedule(dynamic)
+        for (int y = 0; y < f.rh; y++)
+            for (int x = 0; x < f.rw; x++) {
+                if (f.z[(size_t)y * f.rw + x] == INFINITY) continue;
+                uint32_t st = pixel_seed((uint32_t)(y * f.rw + x), rng_seed + kSsaoSeedOffset);
+                ao[(size_t)y * f.rw + x] = x < f.rw - leftover ? ssao_simd_pixel(f, x, y, st) : ssao_scalar_pixel(f, x, y, st);
+            }
+    }
+    const int blur_size = 7, half = blur_size / 2;
+    for (int y = half; y < f.rh - half; y++)
+        for (int x = half; x < f.rw - half; x++) {
+            if (f.z[(size_t)y * f.rw + x] == INFINITY) continue;
+            int sum = 0;
+            for (int oy = -half; oy <= half; oy++)
+                for (int ox = -half; ox <= half; ox++) sum += ao[(size_t)(y + oy) * f.rw + x + ox];
+            float mult = 1 - ((float)sum / (float)(blur_size * blur_size) / (float)f.samples * (float)amount);
+            uint32_t c = argb_super[(size_t)y * f.rw + x];
+            int r = (c >> 16) & 0xff, g = (c >> 8) & 0xff, b = c & 0xff;
+            // QColor(int, int, int) from float expressions: truncation (renderer.cpp:1429)
+            int nr = (int)(r * mult), ng = (int)(g * mult), nb = (int)(b * mult);
+            argb_super[(size_t)y * f.rw + x] = 0xff000000u | (((uint32_t)nr & 0xffu) << 16) | (((uint32_t)ng & 0xffu) << 8) | ((uint32_t)nb & 0xffu);
+        }
+}
+
+// ray_trace() with the G-buffers, post_process_ssao_SIMD(), apply_ssaa() -- renderer.cpp:1068-1135
+void render_with_ssao(const Renderer& r, uint32_t* argb_out, int threads, int rng_mode, const uint32_t* ref_seeds9)
+{
+    int rw, rh;
+    r.super_dims(rw, rh);
+    std::vector<uint32_t> super((size_t)rw * rh);
+    std::vector<float> z((size_t)rw * rh, INFINITY);                                 // clear_z_buffer, renderer.cpp:165-168
+    std::vector<V3> n((size_t)rw * rh, v3(0, 0, 0));                                 // clear_normal_buffer, :170-173
+    trace_rows(r, r.cam_to_world, super.data(), 0, rh, 1, threads, nullptr, z.data(), n.data());
+    SsaoFrame f;
+    f.rw = rw; f.rh = rh; f.z = z.data(); f.n = n.data();
+    f.aspect = (float)rw / rh;                                                       // renderer.cpp:250-261
+    f.proj = perspective(r.fov, f.aspect, 0.1f, 1000.0f);
+    f.fov_mult_simd = (float)std::tan(r.fov / 2 / 180 * M_PI);
+    f.fov_mult_scalar = std::tan(((float)M_PI / 180) * (r.fov / 2));                 // radians(), mat.cpp:13-16; std::tan(float)
+    f.samples = r.s.ssao_sample_count; f.radius = r.s.ssao_radius;
+    ssao_post_process(f, super.data(), r.s.rng_seed, r.s.ssao_amount, rng_mode, ref_seeds9);
+    if (r.s.enable_ssaa) downscale(super.data(), rw, rh, r.s.ssaa_factor, argb_out);
+    else memcpy(argb_out, super.data(), super.size() * sizeof(uint32_t));
 }
 
 struct BvhHandle {
@@ -1132,6 +1347,12 @@ double orc_renderer_render(void* h, uint32_t* argb_out, int threads)
     else memcpy(argb_out, super.data(), super.size() * sizeof(uint32_t));
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double, std::milli>(t1 - t0).count();
+}
+
+// The same with enable_ssao: rng_mode 0 = per-pixel stream (rng_seed), 1 = reference order with the 9 given generator seeds
+void orc_renderer_render_ssao(void* h, uint32_t* argb_out, int threads, int rng_mode, const uint32_t* ref_seeds9)
+{
+    render_with_ssao(*(Renderer*)h, argb_out, threads, rng_mode, ref_seeds9);
 }
 
 void orc_downscale(const uint32_t* in, int w, int hgt, int factor, uint32_t* out) { downscale(in, w, hgt, factor, out); }

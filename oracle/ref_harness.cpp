@@ -75,6 +75,9 @@ void apply_settings(RenderSettings& rs, const RtSettings& s)
     rs.enable_skybox = s.enable_skybox != 0;
     rs.displacement_mapping_strength = s.displacement_mapping_strength;
     rs.parallax_mapping_steps = s.parallax_mapping_steps;
+    rs.ssao_sample_count = s.ssao_sample_count;
+    rs.ssao_radius = s.ssao_radius;
+    rs.ssao_amount = s.ssao_amount;
 }
 
 struct RefBvh {
@@ -336,6 +339,37 @@ double ref_renderer_render(void* handle, uint32_t* argb_out, int threads)
     auto t0 = std::chrono::steady_clock::now();
     h->renderer.ray_trace();
     h->renderer.post_process();
+    auto t1 = std::chrono::steady_clock::now();
+    if (argb_out) {
+        QImage* img = h->renderer.get_image();
+        memcpy(argb_out, img->raw(), sizeof(uint32_t) * (size_t)img->width() * img->height());
+    }
+    return std::chrono::duration<double, std::milli>(t1 - t0).count();
+}
+
+// SSAO (enable_ssao in the settings): the GUI's sequence -- prepare_ssao_buffers / clear_z_buffer / clear_normal_buffer
+// (QT/mainwindow.cpp:174-185), ray_trace(), post_process() -- with the SSAO pass on ONE thread after srand(seed): its
+// generators are seeded from std::rand() and the thread number (renderer.cpp:1254-1266), so this is the reproducible run.
+// rand_values (may be NULL) receives the first n_rand values of std::rand() after srand(seed): the caller works out which of
+// them became generator seeds (the default-constructed generators of renderer.cpp:1252-1253 and the private copy of the
+// parallel region consume some first; the evaluation order of _mm256_set_epi32's arguments decides which lane gets which).
+double ref_renderer_render_ssao(void* handle, uint32_t* argb_out, unsigned seed, uint32_t* rand_values, int n_rand)
+{
+    RefRenderer* h = (RefRenderer*)handle;
+    h->renderer.prepare_ssao_buffers();
+    h->renderer.clear_z_buffer();
+    h->renderer.clear_normal_buffer();
+    auto t0 = std::chrono::steady_clock::now();
+    h->renderer.ray_trace();
+    const int threads = omp_get_max_threads();
+    if (rand_values) {
+        srand(seed);
+        for (int i = 0; i < n_rand; i++) rand_values[i] = (uint32_t)rand();
+    }
+    srand(seed);
+    omp_set_num_threads(1);
+    h->renderer.post_process();
+    omp_set_num_threads(threads);
     auto t1 = std::chrono::steady_clock::now();
     if (argb_out) {
         QImage* img = h->renderer.get_image();

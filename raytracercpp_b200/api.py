@@ -48,7 +48,8 @@ SETTINGS_FIELDS = [
 
 class RtSettings(C.Structure):
     _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32), ("displacement_mapping_strength", C.c_float),
-                                                              ("parallax_mapping_steps", C.c_int32)]
+                                                              ("parallax_mapping_steps", C.c_int32),
+                                                              ("ssao_sample_count", C.c_int32), ("ssao_radius", C.c_float), ("ssao_amount", C.c_float)]
 
     def copy(self) -> "RtSettings":
         out = RtSettings()
@@ -123,6 +124,7 @@ ABI = {
     "rt_set_texture_u8": (C.c_int, [C.c_void_p, C.c_int, BP, C.c_int, C.c_int]),
     "rt_clear_texture": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_set_camera": (C.c_int, [C.c_void_p, FP, FP, FP]),
+    "rt_set_projection": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]),
     "rt_perspective_inverse": (None, [C.c_float, C.c_float, C.c_float, C.c_float, FP]),
     "rt_invert_transform": (None, [FP, FP]),
     "rt_transform_point": (None, [FP, FP, FP]),
@@ -177,7 +179,7 @@ def default_settings(lib=None, **kw) -> RtSettings:
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
-        setattr(s, k, float(v) if k == "displacement_mapping_strength" else int(v))
+        setattr(s, k, float(v) if k in ("displacement_mapping_strength", "ssao_radius", "ssao_amount") else int(v))
     return s
 
 
@@ -272,6 +274,10 @@ class Context:
     def set_camera(self, proj_inv, cam_to_world, position):
         a, b, c = _f32(proj_inv).reshape(16), _f32(cam_to_world).reshape(16), _f32(position).reshape(3)
         self._check(self.lib.rt_set_camera(self.h, _p(a, C.c_float), _p(b, C.c_float), _p(c, C.c_float)))
+
+    def set_projection(self, fov, aspect, znear=0.1, zfar=1000.0):
+        """Camera::_perspective_proj_mat / _fov / _aspect_ratio for the SSAO post-process (RtSettings.enable_ssao)."""
+        self._check(self.lib.rt_set_projection(self.h, float(fov), float(aspect), float(znear), float(zfar)))
 
     def set_light(self, p):
         p = _f32(p).reshape(3)

@@ -140,6 +140,9 @@ struct QueueView {
     // chunk's sort_slots ray slots are hits (sparse hits = hits at unrelated depths); the shade stage reads hit_sorted then
     uint32_t* hit_sorted;
     uint32_t sort_mode, sort_slots;
+    // G-buffers of the SSAO post-process (ssao.cuh), one entry per supersampled pixel; null when SSAO is off
+    float* g_z;
+    V3* g_n;
     // split shadow packets (k_shade_packet -> k_shade_items -> k_shade_finish)
     uint32_t* split_base;            // first hit-queue entry of the packet
     uint32_t* split_active;          // lanes that had no answer when the packet was split
@@ -1104,12 +1107,14 @@ k_shade(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt
                 HitRec hr;
                 queue_ray(fr, wk, q, entry, o, d, hr, pix);
                 Hit hit = make_hit(sc, hr, o, d);
-                if (fr.s.shading_method != RT_SHADING)
+                if (fr.s.shading_method != RT_SHADING) {
                     super[pix] = quantise_argb(shade_debug(sc, fr, hit));
-                else {
+                    if (q.g_z != nullptr) { q.g_z[pix] = -(o.z + d.z * hr.t); q.g_n[pix] = hit.normal; }
+                } else {
                     V3 p;
                     MatView m;
                     direct = shade_direct(sc, fr, o, d, hit, p, m);
+                    if (q.g_z != nullptr) { q.g_z[pix] = -(o.z + d.z * hr.t); q.g_n[pix] = hit.normal; }
                     mat = hit.mat;
                     S.occluded = false;
                     S.mode = RT_MODE_DONE;
@@ -1162,7 +1167,10 @@ struct ShadeLane {
     bool rt;                // RT_SHADING (false: one of the debug shading modes, no further rays)
 };
 
-RT_DEV ShadeLane shade_prepare(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, uint32_t entry)
+// gbuffer: also store what Renderer::ray_trace keeps for the SSAO pass (renderer.cpp:1104-1111): the z of the hit point and
+// the hit's normal as shading left it (normal-mapped when normal mapping is on).  Only the kernel that sees every queue
+// entry exactly once asks for it.
+RT_DEV ShadeLane shade_prepare(const SceneView& sc, const FrameView& fr, const WorkView& wk, const QueueView& q, uint32_t entry, bool gbuffer = false)
 {
     ShadeLane L;
     V3 o, d;
@@ -1176,6 +1184,10 @@ RT_DEV ShadeLane shade_prepare(const SceneView& sc, const FrameView& fr, const W
         MatView m;
         L.direct = shade_direct(sc, fr, o, d, hit, L.p, m);
         L.nrm = hit.normal;
+    }
+    if (gbuffer && q.g_z != nullptr) {
+        q.g_z[L.pix] = -(o.z + d.z * hr.t);
+        q.g_n[L.pix] = hit.normal;
     }
     return L;
 }
@@ -1241,7 +1253,7 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
         const bool valid = entry < n;
         ShadeLane L;
         L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
-        if (valid) L = shade_prepare(sc, fr, wk, q, entry);
+        if (valid) L = shade_prepare(sc, fr, wk, q, entry, true);
         bool occluded = false, deferred = false;
         if (fr.s.compute_shadows && fr.s.shading_method == RT_SHADING) {
             bool active = valid && L.rt;
@@ -1581,7 +1593,7 @@ k_shade_fused(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         rem = (n - base) / per_round;
         ShadeLane L;
         L.rt = false; L.p = v3(0, 0, 0); L.nrm = v3(0, 0, 1);
-        if (valid) L = shade_prepare(sc, fr, wk, q, entry);
+        if (valid) L = shade_prepare(sc, fr, wk, q, entry, true);
         bool occluded = false, deferred = false;
         if (shadows) {
             bool active = valid && L.rt;

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "scene_layout.h"
 #include "octree_device.cuh"
+#include "ssao.cuh"
 #include "host_common.h"
 
 using namespace rtb;
@@ -197,6 +198,13 @@ struct RtContext {
     int opt_shadow_sort = 2;
     bool opt_device_build = true;
     DeviceBuild db;
+    // SSAO post-process (ssao.cuh): G-buffers, counts, and the camera's forward projection (rt_set_projection)
+    DevBuf<float> d_gz;
+    DevBuf<V3> d_gn;
+    DevBuf<int> d_ao;
+    M4 proj{};
+    float proj_fov = 45.0f, proj_aspect = 1.0f;
+    bool proj_set = false;
     float root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0};   // the root cell's axis-aligned box (first three slabs)
 
     // batch query staging
@@ -767,7 +775,7 @@ void rt_destroy(RtContext* ctx)
     cudaStreamSynchronize(ctx->stream);
     ctx->d_recs.release(); ctx->d_top.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
-    ctx->d_super.release(); ctx->d_frame.release(); ctx->db.release();
+    ctx->d_super.release(); ctx->d_frame.release(); ctx->db.release(); ctx->d_gz.release(); ctx->d_gn.release(); ctx->d_ao.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
     for (auto& qs : ctx->qs) qs.release();
     for (auto st : ctx->lane_stream) if (st) cudaStreamDestroy(st);
@@ -1043,6 +1051,17 @@ int rt_set_camera(RtContext* ctx, const float proj_inv[16], const float cam_to_w
     return RT_OK;
 }
 
+int rt_set_projection(RtContext* ctx, float fov, float aspect, float znear, float zfar)
+{
+    if (!ctx) return RT_ERR_INVALID;
+    if (!(aspect > 0.0f) || !(zfar > znear)) return fail(ctx, RT_ERR_INVALID, "projection: aspect %g, znear %g, zfar %g", aspect, znear, zfar);
+    ctx->proj = perspective_matrix(fov, aspect, znear, zfar);                     // Camera::_perspective_proj_mat, scene/camera.cpp:5-19
+    ctx->proj_fov = fov;
+    ctx->proj_aspect = aspect;
+    ctx->proj_set = true;
+    return RT_OK;
+}
+
 int rt_set_light(RtContext* ctx, const float position[3])
 {
     if (!ctx || !position) return RT_ERR_INVALID;
@@ -1065,6 +1084,9 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     if (int r = validate_scene_for_render(ctx, s)) return r;
     if (int r = check_tile_args(ctx, tile_size, tile_mod, tile_rem)) return r;
     if (!d_argb_out) return fail(ctx, RT_ERR_INVALID, "d_argb_out is NULL");
+    const bool ssao = s->enable_ssao != 0;
+    if (ssao && tile_mod != 1) return fail(ctx, RT_ERR_UNSUPPORTED, "enable_ssao needs the whole frame on one GPU: its samples read the z-buffer of neighbouring tiles");
+    if (ssao && !ctx->proj_set) return fail(ctx, RT_ERR_STATE, "enable_ssao: the projection has not been set (rt_set_projection)");
 
     const FrameView fr = frame_view(ctx, s);
     const SceneView sc = scene_view(ctx);
@@ -1189,6 +1211,10 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         RT_CUDA(ctx, ctx->d_super.ensure((size_t)fr.rw * fr.rh));
         super = ctx->d_super.p;
     }
+    if (ssao) {
+        const size_t px = (size_t)fr.rw * fr.rh;
+        RT_CUDA(ctx, ctx->d_gz.ensure(px)); RT_CUDA(ctx, ctx->d_gn.ensure(px)); RT_CUDA(ctx, ctx->d_ao.ensure(px));
+    }
     wk.tiles = classify ? tl->d_split : tl->d;
     QueueView qv[kMaxLanes];
     for (int l = 0; l < n_lanes; l++) {
@@ -1201,6 +1227,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         q.item_ready = Q.item_ready.p; q.split_pending = Q.split_pending.p; q.tag = 0;
         q.refl_idx = Q.refl_idx.p; q.refl_rgb = Q.refl_rgb.p; q.refl_cnt = Q.refl_cnt.p; q.capacity = (uint32_t)qcap;
         q.hit_sorted = nullptr; q.sort_mode = 0u; q.sort_slots = 0u;
+        q.g_z = ssao ? ctx->d_gz.p : nullptr; q.g_n = ssao ? ctx->d_gn.p : nullptr;
     }
     for (int l = 1; l < n_lanes; l++) {
         if (ctx->lane_stream[l]) continue;
@@ -1217,6 +1244,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
     RT_CUDA(ctx, cudaEventRecord(ev_begin, st));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
+    if (ssao) { k_gbuffer_clear<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_gz.p, ctx->d_gn.p, (size_t)fr.rw * fr.rh); launches++; }
 
     const bool count = ctx->opt_count_work;
     int (&grids)[2][11] = ctx->grids;                                           // per context: its device's occupancy
@@ -1366,6 +1394,21 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         ScopedTimer tm(ctx, ST_PRIMARY);
         k_fill_miss<<<ctx->sm_count * 8, 256, 0, st>>>(sc, fr, wk, super);
         launches++;
+    }
+    if (ssao && !owned.empty()) {
+        // Renderer::post_process: SSAO on the supersampled image, then the SSAA resolve (renderer.cpp:1118-1124)
+        SsaoView sv;
+        sv.rw = fr.rw; sv.rh = fr.rh; sv.z = ctx->d_gz.p; sv.n = ctx->d_gn.p;
+        sv.proj = ctx->proj;
+        sv.aspect = ctx->proj_aspect;
+        sv.fov_mult_simd = (float)std::tan(ctx->proj_fov / 2 / 180 * M_PI);                  // renderer.cpp:1249
+        sv.fov_mult_scalar = std::tan(((float)M_PI / 180) * (ctx->proj_fov / 2));            // radians(), mat.cpp:13-16, std::tan(float)
+        sv.samples = s->ssao_sample_count; sv.radius = s->ssao_radius; sv.amount = s->ssao_amount;
+        sv.rng_seed = s->rng_seed;
+        ScopedTimer tm(ctx, ST_RESOLVE);
+        k_ssao_occlusion<<<ctx->sm_count * 16, 128, 0, st>>>(sv, ctx->d_ao.p);
+        k_ssao_apply<<<ctx->sm_count * 8, 256, 0, st>>>(sv, ctx->d_ao.p, super);
+        launches += 2;
     }
     if (resolve && !owned.empty()) {
         wk.tile_begin = 0;

@@ -148,19 +148,20 @@ class Renderer:
     def _push_camera(self):
         proj_inv = self.ctx.perspective_inverse(self._fov, self._aspect, self._near, self._far)
         self.ctx.set_camera(proj_inv, self._camera_to_world, self._position)
+        self.ctx.set_projection(self._fov, self._aspect, self._near, self._far)       # read by the SSAO pass only
 
     # -- rendering ------------------------------------------------------------------------------------------------
     def ray_trace(self):
         """Renderer::ray_trace() + the SSAA half of post_process() (renderer.cpp:1068-1135).  The resolve runs on the
-        device in the same call, so post_process() has nothing left to do for this path."""
+        device in the same call -- and, with enable_ssao, the SSAO pass before it (renderer.cpp:1229-1434) -- so post_process() has
+        nothing left to do for this path."""
         rw, rh = self.get_render_width_height()
         self._aspect = float(np.float32(rw) / np.float32(rh))
         self._push_camera()
         self._image, self._stats = self.ctx.render(self._settings)
 
     def post_process(self):
-        if self._settings.enable_ssao:
-            raise api.RtError(api.RT_ERR_UNSUPPORTED, "SSAO is a host post-process of the reference")
+        """Renderer::post_process (renderer.cpp:1118-1124): SSAO and the SSAA resolve ran on the device inside ray_trace()."""
 
     def get_image(self):
         """ARGB32 [H, W], row 0 = bottom row like the reference's QImage (renderer.cpp:1086)."""

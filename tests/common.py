@@ -64,6 +64,27 @@ def config_table(mats):
     }
 
 
+def ssao_table(mats):
+    """SSAO set-ups (renderer.cpp:1229-1434): name -> (settings, materials, textures).  The supersampled width of the
+    cases that are pinned against the compiled reference is a multiple of 8: its AVX2 loop runs its last partial
+    8-pixel group past the end of the row (and of the buffers at the last row)."""
+    tex2 = config_table(mats)["cfg2"][2]
+    return {
+        "ssao_ssaa2": (dict(image_width=160, image_height=96, enable_ssaa=1, ssaa_factor=2, compute_shadows=1, enable_ssao=1, ssao_sample_count=16,
+                            ssao_radius=0.5, ssao_amount=1.0, rng_seed=3), mats, {}),
+        "ssao_normal_mapped": (dict(image_width=192, image_height=108, compute_shadows=1, enable_ssao=1, ssao_sample_count=24, ssao_radius=0.3,
+                                    ssao_amount=0.8, enable_ao_mapping=1, enable_diffuse_mapping=1, enable_normal_mapping=1, rng_seed=5), mats, tex2),
+    }
+
+
+def ssao_reference_seeds(rand_values):
+    """The nine generator seeds of a single-threaded Renderer::post_process_ssao_SIMD run after srand(): the two
+    default-constructed generators (renderer.cpp:1252-1253; xorshift.h:10,39) and the private copy of the parallel region
+    consume 8 + 1 + 8 values of std::rand() first; _mm256_set_epi32's arguments are evaluated right to left, so lane 0 gets
+    the next value, ..., lane 7 the eighth, and the scalar generator the ninth (pinned by tests/test_oracle_vs_reference.py)."""
+    return np.asarray(rand_values[17:26], np.uint32)
+
+
 def oracle_renderer(tracer, scene, kw, mats, tex, fov=FOV, light=LIGHT, cam=None):
     s = ob.default_settings(**kw)
     r = tracer.renderer()
@@ -104,7 +125,7 @@ def product_renderer(lib, scene, kw, mats, tex, fov=FOV, light=LIGHT, cam=None, 
     r = rt.Renderer(device, lib)
     s = r.render_settings()
     for k, v in kw.items():
-        setattr(s, k, float(v) if k == "displacement_mapping_strength" else int(v))
+        setattr(s, k, float(v) if k in ("displacement_mapping_strength", "ssao_radius", "ssao_amount") else int(v))
     r.change_render_size(s.image_width, s.image_height)
     r.change_camera_fov(fov)
     if cam is not None:

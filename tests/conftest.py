@@ -86,6 +86,11 @@ def robot():
 
 
 @pytest.fixture(scope="session")
+def golden_ssao():
+    return dict(np.load(GOLDEN / "golden_ssao.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_rays():
     return dict(np.load(GOLDEN / "golden_rays.npz"))
 

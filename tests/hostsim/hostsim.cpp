@@ -129,7 +129,7 @@ const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""
 int rt_set_option(RtContext* c, int option, int64_t value)
 {
     if (option == RT_OPT_LEAF_SPLIT) { c->leaf_split = (int)value; c->bvh_valid = false; return RT_OK; }
-    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_LANES || option == RT_OPT_ITEM_ROUNDS || option == RT_OPT_PRIMARY_ROUNDS || option == RT_OPT_FUSED_ITEMS || option == RT_OPT_TOP_TABLE) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
+    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_LANES || option == RT_OPT_ITEM_ROUNDS || option == RT_OPT_PRIMARY_ROUNDS || option == RT_OPT_FUSED_ITEMS || option == RT_OPT_TOP_TABLE || option == RT_OPT_SHADOW_SORT || option == RT_OPT_DEVICE_BUILD) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
 }
 
 int rt_set_stream(RtContext*, void*) { return RT_OK; }
@@ -241,6 +241,7 @@ int rt_set_camera(RtContext* c, const float proj_inv[16], const float cam_to_wor
     return RT_OK;
 }
 int rt_set_light(RtContext* c, const float p[3]) { c->light = v3(p[0], p[1], p[2]); return RT_OK; }
+int rt_set_projection(RtContext*, float, float, float, float) { return RT_OK; }     // SSAO is not emulated here (ssao.cuh is CUDA only)
 
 int rt_tile_count(const RtSettings* s, int tile_size, int tile_mod, int tile_rem)
 {
@@ -253,6 +254,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
 {
     std::string why;
     if (int r = check_settings(s, why)) return fail(c, r, why);
+    if (s->enable_ssao) return fail(c, RT_ERR_UNSUPPORTED, "the host emulation has no SSAO pass");
     SceneFacts f;
     f.bvh_valid = c->bvh_valid; f.camera_set = c->camera_set; f.n_tris = (uint32_t)(c->xyz9.size() / 9); f.n_mats = c->n_mats;
     f.min_mat_index = c->min_mat; f.max_mat_index = c->max_mat;

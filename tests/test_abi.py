@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_sizes(lib):
     assert ctypes.sizeof(api.RtMaterial) == 64
-    assert ctypes.sizeof(api.RtSettings) == 27 * 4
+    assert ctypes.sizeof(api.RtSettings) == 30 * 4
 
 
 def test_defaults_mirror_render_settings(lib):
@@ -44,6 +44,7 @@ def test_defaults_mirror_render_settings(lib):
     assert (s.image_width, s.image_height, s.ssaa_factor, s.max_recursion_depth) == (1024, 1024, 2, 5)
     assert (s.enable_bvh, s.bvh_max_depth, s.bvh_leaf_object_count, s.rough_reflections_sample_count) == (1, 12, 40, 3)
     assert abs(s.displacement_mapping_strength - 0.02) < 1e-9 and s.parallax_mapping_steps == 32      # rendererSettings.h:94-95
+    assert (s.ssao_sample_count, s.ssao_radius, s.ssao_amount) == (64, 0.5, 1.0) and not s.enable_ssao    # rendererSettings.h:66-73
     assert s.enable_ambient and s.enable_diffuse and s.enable_specular and s.enable_emissive
     assert not (s.enable_ssaa or s.compute_shadows or s.enable_skysphere or s.enable_ao_mapping)
 

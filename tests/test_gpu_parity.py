@@ -166,7 +166,7 @@ def test_primary_rays_resolve_and_call_order(cuda_lib, golden_images, robot):
         r.ray_trace()                                          # RT_SHADING without materials
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao", "hybrid_rasterization_tracing"):
+    for field in ("hybrid_rasterization_tracing",):
         setattr(st, field, 1)
         with pytest.raises(api.RtError) as e:
             r.ray_trace()
@@ -432,6 +432,51 @@ def test_light_space_queue_order_never_changes_a_frame(cuda_lib, robot, light):
     for k in ("primary_rays", "shadow_rays", "primary_hits"):
         assert out[0][1][k] == out[1][1][k]
     assert out[0][1]["kernel_launches"] > out[1][1]["kernel_launches"]
+
+
+@pytest.mark.parametrize("name", ["ssao_ssaa2", "ssao_normal_mapped", "ssao_leftover_columns", "ssao_debug_shading"])
+def test_ssao_vs_oracle(cuda_lib, oracle, robot, golden_ssao, name):
+    """Renderer::post_process_ssao_SIMD (renderer.cpp:1229-1434) on the GPU: G-buffers from the shade stage, per-pixel
+    occlusion counts, 7x7 blur applied before the SSAA resolve -- against the oracle's restatement with the same per-pixel
+    random stream (whose arithmetic is pinned bit-exactly to the compiled reference, tests/test_oracle_vs_reference.py)
+    and against the frame stored with the reference's golden.  Also a frame width that is not a multiple of 8 (the
+    reference's scalar loop for the left-over columns) and a debug shading mode (geometric normals in the G-buffer)."""
+    table = common.ssao_table(robot["materials"])
+    if name == "ssao_leftover_columns":
+        kw, mats, tex = table["ssao_ssaa2"]
+        kw = dict(kw, image_width=99, image_height=57, enable_ssaa=0)
+    elif name == "ssao_debug_shading":
+        kw, mats, tex = table["ssao_ssaa2"]
+        kw = dict(kw, shading_method=api.RT_ABS_NORMALS_SHADING)
+    else:
+        kw, mats, tex = table[name]
+    r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+    r.ray_trace()
+    r.post_process()
+    img = r.get_image().copy()
+    want, _ = common.oracle_renderer(oracle, robot, kw, mats, tex).render_ssao()
+    common.assert_image_close(img, want, what=name)
+    assert (img == want).mean() >= 0.999
+    if name in table:
+        assert (img == golden_ssao[name + "_per_pixel"]).mean() >= 0.999
+        # against the reference's own frame the two differ as two samplings of the same estimator do
+        assert common.image_error(img, golden_ssao[name + "_reference"])[0] < 0.5
+    plain = common.product_renderer(cuda_lib, robot, dict(kw, enable_ssao=0), mats, tex)
+    plain.ray_trace()
+    assert (plain.get_image() != img).mean() > 0.05
+    plain.close()
+    # the single-ray kernels fill the same G-buffers; the stream does not depend on the schedule
+    r.ctx.set_option(api.RT_OPT_PACKETS, 0)
+    r.ray_trace()
+    assert np.array_equal(r.get_image(), img)
+    r.ctx.set_option(api.RT_OPT_PACKETS, 1)
+    # a tile shard cannot run the pass: its samples read the z-buffer of neighbouring tiles
+    import torch
+    frame = torch.zeros((kw["image_height"], kw["image_width"]), dtype=torch.int32, device="cuda")
+    with pytest.raises(api.RtError) as e:
+        r.ctx.render_device(r.render_settings(), frame.data_ptr(), 32, 2, 0)
+    assert e.value.code == api.RT_ERR_UNSUPPORTED
+    r.close()
 
 
 STAT_KEYS = ("triangles", "nodes", "interior", "leaves", "empty_leaves", "max_depth_reached", "max_leaf_size")

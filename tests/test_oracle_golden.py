@@ -79,3 +79,16 @@ def test_hair_band_matches_reference(oracle, golden_fullsize):
     assert np.array_equal(band, golden_fullsize["cfg5_band_rows"])
     assert zlib.crc32(np.ascontiguousarray(band, np.uint32).tobytes()) == int(golden_fullsize["cfg5_band_crc"])
     assert r.count_rows(row_begin=b0, row_end=b1, row_step=bs)["shadow_rays"] == int(golden_fullsize["cfg5_band_hits"])
+
+
+@pytest.mark.parametrize("name", ["ssao_ssaa2", "ssao_normal_mapped"])
+def test_ssao_matches_reference(oracle, robot, golden_ssao, name):
+    """SSAO frames cut from the compiled reference (tests/golden/make_golden_ssao.py): the oracle in reference order, from the
+    generator seeds stored with the frame, is bit-exact; its per-pixel stream (what the CUDA path is compared with) is
+    stored too, so a change of that discipline shows up here."""
+    kw, mats, tex = common.ssao_table(robot["materials"])[name]
+    orc = common.oracle_renderer(oracle, robot, kw, mats, tex)
+    got, _ = orc.render_ssao(ref_seeds9=golden_ssao[name + "_seeds9"])
+    assert np.array_equal(got, golden_ssao[name + "_reference"])
+    per_pixel, _ = orc.render_ssao()
+    assert np.array_equal(per_pixel, golden_ssao[name + "_per_pixel"])

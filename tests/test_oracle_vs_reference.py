@@ -39,3 +39,21 @@ def test_rough_reflection_depth2_and_normal_mapping(oracle, ref_strict, robot):
     tex[2] = common.scenes.normal_map_texture((64, 64), 8)
     kw = dict(kw, image_width=96, image_height=54, max_recursion_depth=2, rough_reflections_sample_count=5, enable_normal_mapping=1)
     assert np.array_equal(common.oracle_image(oracle, robot, kw, mats, tex), common.oracle_image(ref_strict, robot, kw, mats, tex))
+
+
+@pytest.mark.parametrize("name", ["ssao_ssaa2", "ssao_normal_mapped"])
+@pytest.mark.parametrize("seed", [1234, 77])
+def test_ssao_reference_order(oracle, ref_strict, robot, name, seed):
+    """Renderer::post_process_ssao_SIMD (renderer.cpp:1229-1434) on one thread after srand(seed) against the oracle's
+    restatement drawing from the same nine generator seeds in the same order: bit-exact, G-buffers (z, normal-mapped
+    normals) included.  The per-pixel stream differs from it only as two samplings of the same estimator do."""
+    kw, mats, tex = common.ssao_table(robot["materials"])[name]
+    want, rand_values = common.oracle_renderer(ref_strict, robot, kw, mats, tex).render_ssao(srand_seed=seed)
+    plain, _ = common.oracle_renderer(ref_strict, robot, dict(kw, enable_ssao=0), mats, tex).render()
+    assert (want != plain).mean() > 0.05                                  # the pass really darkens a good part of the frame
+    orc = common.oracle_renderer(oracle, robot, kw, mats, tex)
+    got, _ = orc.render_ssao(ref_seeds9=common.ssao_reference_seeds(rand_values))
+    assert np.array_equal(got, want)
+    per_pixel, _ = orc.render_ssao()
+    diff = np.abs(common.channels(per_pixel).astype(int) - common.channels(want).astype(int))
+    assert diff.mean() < 0.5 and (per_pixel != plain).mean() > 0.05
