@@ -189,6 +189,7 @@ enum {
     RT_OPT_PRIMARY_ROUNDS = 11,/* primary packets (default -256; negative additionally means: not split in long launches,
                                  256 and more packets per resident warp)                                                  */
     RT_OPT_ITEM_ROUNDS = 10,  /* work items of all generations but the last (default -16; 0 is invalid)                 */
+    RT_OPT_ITEM_PASSES = 16,  /* generations of work items per stage = launches of the item kernels (1..6, default 6)        */
     RT_OPT_FUSED_ITEMS = 12,  /* 0 (default): the work items of split packets are traced generation by generation in separate
                                  launches (six item passes and a finish kernel per stage); 1: the packet kernels consume the
                                  items themselves through 32 ticket queues, the last item of a record stores its pixels -- one

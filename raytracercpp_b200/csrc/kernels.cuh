@@ -198,6 +198,7 @@ struct Tuning {
     // launch's work queue has been handed out completely -- from then on it would only lengthen the launch's tail, whereas its
     // unvisited cells can be traced by the warps that have nothing left to do.  0: the budgets above are all there is.
     int32_t packet_min, item_min, primary_min;
+    int32_t item_passes;      // generations of work items actually launched (<= kItemPasses); the last has no budget
 };
 
 // When a packet should give up before its round budget: the launch's queue (`counter` = tickets handed out, `total` =
@@ -711,7 +712,7 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n = min(cnt->p_items_n[pass], q.item_capacity);
     const uint4* region = q.items + (size_t)pass * q.item_capacity;
-    const int budget = pass + 1 < kItemPasses ? tune.item_rounds : 0;
+    const int budget = pass + 1 < tune.item_passes ? tune.item_rounds : 0;
     TraceCounters tc = zero_counters();
     unsigned overflow = 0;
     for (;;) {
@@ -1306,7 +1307,7 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
     const uint32_t n_hits = cnt->n_hits;
     const uint32_t n = min(cnt->items_n[pass], q.item_capacity);
     const uint4* region = q.items + (size_t)pass * q.item_capacity;
-    const int budget = pass + 1 < kItemPasses ? tune.item_rounds : 0;
+    const int budget = pass + 1 < tune.item_passes ? tune.item_rounds : 0;
     TraceCounters tc = zero_counters();
     unsigned overflow = 0;
     for (;;) {

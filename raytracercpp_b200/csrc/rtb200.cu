@@ -87,6 +87,7 @@ struct TileList {
     int32_t split_rect[4] = {0, 0, -1, -1};
     int32_t split_tile_px = 0;
     bool split_valid = false;
+    float last_hit_fraction = -1.0f;     // hits per traced ray slot of the last frame rendered with this list (-1: none yet)
 };
 typedef std::tuple<int, int, int, int, int> TileKey;      // width, height, tile_size, tile_mod, tile_rem (-1: all shards, padded)
 
@@ -119,6 +120,9 @@ struct Pending {                          // a frame that has been enqueued (rt_
     bool count = false, shadow = false;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     uint64_t primary_rays = 0;
+    bool has_key = false;                 // the tile list of the frame and its traced ray slots (for TileList::last_hit_fraction)
+    int key[5] = {0, 0, 0, 0, 0};
+    uint64_t traced_slots = 0;
 };
 
 // Device copies of the caller's triangle arrays and the temporaries of the device octree build (octree_device.cuh); kept
@@ -183,7 +187,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0, 0, 0, 0};
+    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0, 0, 0, 0, kItemPasses};
     uint32_t frame_serial = 0;           // tags the ready flags of the fused item queues: (serial << 2) | stage
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
@@ -829,6 +833,10 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         return RT_OK;
     case RT_OPT_FUSED_ITEMS: ctx->tune.fused = value != 0; return RT_OK;
     case RT_OPT_TOP_TABLE: ctx->opt_top_table = value != 0; return RT_OK;
+    case RT_OPT_ITEM_PASSES:
+        if (value < 1 || value > kItemPasses) return fail(ctx, RT_ERR_INVALID, "item passes %lld outside [1,%d]", (long long)value, kItemPasses);
+        ctx->tune.item_passes = (int32_t)value;
+        return RT_OK;
     case RT_OPT_DEVICE_BUILD: ctx->opt_device_build = value != 0; return RT_OK;
     case RT_OPT_SHADOW_SORT:
         if (value < 0 || value > 2) return fail(ctx, RT_ERR_INVALID, "shadow sort %lld outside [0,2]", (long long)value);
@@ -1178,7 +1186,10 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     const bool psplit = tune.packets && tune.primary_rounds > 0;
     // light-space ordering of the hit queue before the shadow packets are formed (kernels.cuh).  Not with reflection fans:
     // their queue indexes the hit queue in compaction order.
-    const bool sort_hits = ctx->opt_shadow_sort && tune.packets && !tune.fused && !reflect && s->compute_shadows && s->shading_method == RT_SHADING;
+    // In the adaptive mode the kernels decide on the device (sparse hits: fewer than 1 in 4 ray slots); when the last frame of
+    // the same tile list was clearly dense, the five launches are not even enqueued (they matter to a short launch).
+    const bool sort_hits = ctx->opt_shadow_sort && tune.packets && !tune.fused && !reflect && s->compute_shadows && s->shading_method == RT_SHADING &&
+                           !(ctx->opt_shadow_sort == 2 && tl->last_hit_fraction >= 0.3f);
     const LightMap light_map = sort_hits ? make_light_map(ctx) : LightMap{};
     // split records and work items of the packets that run out of rounds; a packet that finds them full is finished in
     // place.  Primary and shadow packets never run at the same time and share the storage.
@@ -1301,13 +1312,13 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             else k_primary<false><<<grid_primary, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super, tune);
             launches++;
             if (psplit) {
-                for (int pass = 0; pass < kItemPasses; pass++) {
+                for (int pass = 0; pass < tune.item_passes; pass++) {
                     ScopedTimer t1(ctx, ST_PRIMARY, st, "  k_primary_items");
                     if (count) k_primary_items<true><<<grid_pitems, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                     else k_primary_items<false><<<grid_pitems, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, tune, pass);
                 }
                 k_primary_finish<<<grid_pfinish, kPrimaryThreads, 0, st>>>(sc, fr, wk, q, cnt, super);
-                launches += kItemPasses + 1;
+                launches += tune.item_passes + 1;
             }
             }
             if (has_shapes) {                                                  // trace_ray's loop over the analytic shapes
@@ -1368,14 +1379,14 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             else k_shade<false><<<grid_shade, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super, tune);
             launches++;
             if (tail) {
-                for (int pass = 0; pass < kItemPasses; pass++) {
+                for (int pass = 0; pass < tune.item_passes; pass++) {
                     ScopedTimer t1(ctx, ST_SHADE, st, "  k_shade_items");
                     if (count) k_shade_items<true><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, tune, pass);
                     else k_shade_items<false><<<grid_items, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, tune, pass);
                 }
                 if (count) k_shade_finish<true><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super);
                 else k_shade_finish<false><<<grid_finish, kQueueThreads, 0, st>>>(sc, fr, wk, qsorted, cnt, super);
-                launches += kItemPasses + 1;
+                launches += tune.item_passes + 1;
             }
             }
         }
@@ -1437,6 +1448,9 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     pd.count = count;
     pd.ev_begin = ev_begin; pd.ev_end = ev_end;
     pd.shadow = s->shading_method == RT_SHADING && s->compute_shadows;
+    pd.has_key = true;
+    pd.key[0] = s->image_width; pd.key[1] = s->image_height; pd.key[2] = tile_size; pd.key[3] = tile_mod; pd.key[4] = tile_rem;
+    pd.traced_slots = (uint64_t)n_traced * px_per_tile;
     pd.primary_rays = 0;                                  // supersampled pixels of the owned tiles that lie inside the frame
     for (uint32_t tile : owned) {
         int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
@@ -1474,6 +1488,10 @@ int rt_render_device_end(RtContext* ctx, RtRenderStats* stats)
         rs.reflection_fetched_bytes += host_cnt[c].refl_fetch;
         rs.traced_primary_rays += host_cnt[c].traced_primary;
         overflow |= host_cnt[c].stack_overflow != 0;
+    }
+    if (pd.has_key) {
+        auto it = ctx->tile_lists.find(TileKey(pd.key[0], pd.key[1], pd.key[2], pd.key[3], pd.key[4]));
+        if (it != ctx->tile_lists.end()) it->second.last_hit_fraction = pd.traced_slots ? (float)((double)rs.primary_hits / (double)pd.traced_slots) : 0.0f;
     }
     rs.primary_rays = pd.primary_rays;
     rs.shadow_rays = pd.shadow ? rs.primary_hits : 0;

@@ -9,6 +9,7 @@ echo "== ncu launch list"
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BCMD > $OUT/ncu_launches.log 2>&1
 echo "rc=$?"; tail -2 $OUT/ncu_launches.log | cut -c1-300
 echo "== ncu full"
-timeout -k 10 1500 ncu --set full --clock-control none --import-source on -k regex:"k_primary_packet|k_shade_packet" -s 8 -c 2 -o $OUT/${TAG}_prof $BCMD > $OUT/ncu_full.log 2>&1
+# the packet kernels of ONE timed frame: the instrumented frame (4 launches: 2 chunks x 2 stages) and the 3 warm-up frames are skipped
+timeout -k 10 1500 ncu --set full --clock-control none --import-source on -k regex:"k_primary_packet|k_shade_packet" -s 16 -c 4 -o $OUT/${TAG}_prof $BCMD > $OUT/ncu_full.log 2>&1
 echo "rc=$?"; tail -2 $OUT/ncu_full.log | cut -c1-300
 ls -la $OUT | grep $TAG

@@ -57,7 +57,7 @@ if rep.exists():
     txt = subprocess.run(['ncu', '-i', str(rep), '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
-    lines, traffic = [], {}
+    lines, traffic = [], {}                      # traffic: per kernel family, summed over the captured launches (= one frame)
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         kname = d['Kernel Name'].split("(")[0].replace("void ", "")
@@ -76,7 +76,11 @@ if rep.exists():
         try:
             b = sum(float(d[m].replace(",", "")) * UNIT[units[hdr.index(m)]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
             short = "k_primary" if "k_primary" in kname else "k_shade" if "k_shade" in kname else "k_reflect" if "k_reflect" in kname else kname
-            traffic[short] = traffic.get(short, 0) + int(b)
+            t = traffic.setdefault(short, {"dram_bytes": 0, "warp_inst": 0, "launches": 0, "kernel_ms": 0.0})
+            t["dram_bytes"] += int(b)
+            t["warp_inst"] += int(float(d['smsp__inst_executed.sum'].replace(",", "")))
+            t["launches"] += 1
+            t["kernel_ms"] += float(d['gpu__time_duration.sum'].replace(",", "")) * {"msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6, "second": 1e3}.get(units[hdr.index('gpu__time_duration.sum')], 1.0)
         except Exception:
             pass
     # hottest SASS lines per kernel
@@ -97,6 +101,9 @@ if rep.exists():
     print("\n".join(lines[:70]))
     tf = out / "traffic.json"
     cur = json.loads(tf.read_text()) if tf.exists() else {}
+    for t in traffic.values():
+        t["source"] = (f"profiles/{tag}_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of the {t['launches']} packet-kernel "
+                       "launches of one frame (the item passes and finish kernels of the stage are not in the capture)")
     cur["cfg4_sphere10M_4k_16spp"] = traffic
-    cur["_source"] = f"profiles/{tag}_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    cur["_source"] = f"profiles/{tag}_ncu_full.txt"
     tf.write_text(json.dumps(cur, indent=1) + "\n")
