@@ -172,6 +172,12 @@ public:
     }
     // renderer.cpp:1118-1124: SSAO (enable_ssao) and the SSAA resolve have already run on the device, inside ray_trace()
     void post_process() {}
+    // renderer.cpp:152-173 (called by QT/mainwindow.cpp:174-185): the z and normal buffers of the SSAO pass live on the device,
+    // are sized by the frame and cleared at the start of every frame that uses them
+    void prepare_ssao_buffers() {}
+    void destroy_ssao_buffers() {}
+    void clear_z_buffer() {}
+    void clear_normal_buffer() {}
 
     // Renderer::get_image(): ARGB32, row 0 = bottom row (renderer.cpp:1086); copy_to() fills a QImage-like object.
     const std::vector<uint32_t>& get_image() const { return _image; }
