@@ -57,14 +57,15 @@ enum {
 };
 
 /* POD mirror of `RenderSettings` (tp2/projets/renderer/rendererSettings.h:6-105), same defaults via
- * rt_default_settings().  The switch that leaves the path (hybrid rasterizer) is carried so a caller can pass its
- * struct through; rt_render() refuses it (RT_ERR_UNSUPPORTED). */
+ * rt_default_settings(). */
 typedef struct RtSettings {
     int32_t image_width;
     int32_t image_height;
     int32_t enable_ssaa;
     int32_t ssaa_factor;
-    int32_t hybrid_rasterization_tracing; /* must be 0 */
+    int32_t hybrid_rasterization_tracing; /* 1: Renderer::raster_trace() instead of ray_trace() (renderer.cpp:869-1006): primary
+                                             visibility by rasterisation + z-buffer, shading / shadow / reflection rays as before;
+                                             needs rt_set_projection; whole frame on one GPU */
     int32_t shading_method;
     int32_t compute_shadows;
     int32_t max_recursion_depth;
@@ -95,6 +96,9 @@ typedef struct RtSettings {
     int32_t ssao_sample_count;
     float ssao_radius;
     float ssao_amount;
+    /* RenderSettings::enable_clipping, rendererSettings.h:40 (true): hybrid_rasterization_tracing clips every triangle against
+     * the six planes of the view volume in clip space (renderer.cpp:837-853) before it is rasterised. */
+    int32_t enable_clipping;
 } RtSettings;
 
 /* Texture slots: Renderer::set_{ao,diffuse,normal,roughness}_map / set_skysphere / set_skybox, renderer.cpp:194-201.
@@ -219,6 +223,8 @@ enum {
                                  chunk's kernels fill the SMs the others leave idle while their longest packets finish; the
                                  per-stage times of RtRenderStats then overlap.  0: one chunk at a time; 1 (default): 2 chunks;
                                  n in [2,6]: n chunks.  Results do not depend on it                                     */
+    RT_OPT_RASTER_UNITS = 17, /* hybrid raster path: first size of the list of work units (row bands of the pieces too large for one
+                                 thread); a frame that needs more grows the list and repeats its depth pass.  Default 2^18       */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a
                                  device-side median-split sub-hierarchy of groups of <= n triangles; 0 = flatten the
                                  reference's cells and leaves exactly as they are.  Applies to the next rt_build_bvh.

@@ -9,7 +9,7 @@
 //   ImageT      : .width() .height() .data() -> const float* RGBA                                      (image.h:99-118)
 //   TransformT  : .m[4][4] row-major                                                                   (mat.h)
 //   PointT      : .x .y .z
-// Members of the reference class that belong to the rasterizer or SSAO are not on this path and are intentionally absent; see INTEGRATION.md for how the GUI keeps them.
+// raster_trace() (the hybrid rasterizer) and the SSAO pass run on the device too; see INTEGRATION.md.
 #pragma once
 
 #include <cstdint>
@@ -161,15 +161,12 @@ public:
     }
 
     // Renderer::ray_trace() (renderer.cpp:1068-1116); the SSAA resolve of post_process() happens in the same call.
-    void ray_trace()
-    {
-        int rw, rh;
-        get_render_width_height(_settings, rw, rh);
-        _aspect = (float)rw / rh;
-        push_camera();
-        _image.resize((size_t)_settings.image_width * _settings.image_height);
-        check(rt_render(_ctx, &_settings, _image.data(), &_stats));
-    }
+    void ray_trace() { render_frame(0); }
+    // Renderer::raster_trace() (renderer.cpp:869-1006), what RenderThread::run calls when hybrid_rasterization_tracing is set
+    // (QT/mainWindowThreads.cpp:46-49): clipping, rasterisation and the z-buffer on the device, every visible fragment shaded with
+    // shadow rays and reflection fans as in ray_trace().  Uncovered pixels are the colour of clear_image() (renderer.cpp:175-180).
+    void raster_trace() { render_frame(1); }
+    void clear_image() {}
     // renderer.cpp:1118-1124: SSAO (enable_ssao) and the SSAA resolve have already run on the device, inside ray_trace()
     void post_process() {}
     // renderer.cpp:152-173 (called by QT/mainwindow.cpp:174-185): the z and normal buffers of the SSAO pass live on the device,
@@ -203,7 +200,19 @@ private:
         float proj_inv[16];
         rt_perspective_inverse(_fov, _aspect, 0.1f, 1000.0f, proj_inv);                                    // Camera(), scene/camera.h:11
         check(rt_set_camera(_ctx, proj_inv, _camera_to_world, _position));
-        check(rt_set_projection(_ctx, _fov, _aspect, 0.1f, 1000.0f));                                      // read by the SSAO pass only
+        check(rt_set_projection(_ctx, _fov, _aspect, 0.1f, 1000.0f));                                      // read by the SSAO pass and by raster_trace
+    }
+
+    void render_frame(int hybrid)
+    {
+        int rw, rh;
+        get_render_width_height(_settings, rw, rh);
+        _aspect = (float)rw / rh;
+        push_camera();
+        _image.resize((size_t)_settings.image_width * _settings.image_height);
+        RtSettings s = _settings;
+        s.hybrid_rasterization_tracing = hybrid;
+        check(rt_render(_ctx, &s, _image.data(), &_stats));
     }
 
     RtContext* _ctx = nullptr;

@@ -46,7 +46,8 @@ SETTINGS_FIELDS = [
 class RtSettings(C.Structure):
     _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32), ("displacement_mapping_strength", C.c_float),
                                                               ("parallax_mapping_steps", C.c_int32),
-                                                              ("ssao_sample_count", C.c_int32), ("ssao_radius", C.c_float), ("ssao_amount", C.c_float)]
+                                                              ("ssao_sample_count", C.c_int32), ("ssao_radius", C.c_float), ("ssao_amount", C.c_float),
+                                                             ("enable_clipping", C.c_int32)]
 
 
 def default_settings(**kw) -> RtSettings:
@@ -68,6 +69,7 @@ def default_settings(**kw) -> RtSettings:
     s.displacement_mapping_strength = 0.02
     s.parallax_mapping_steps = 32
     s.ssao_sample_count, s.ssao_radius, s.ssao_amount = 64, 0.5, 1.0          # rendererSettings.h:69-73
+    s.enable_clipping = 1                                                     # rendererSettings.h:40
     for k, v in kw.items():
         if not hasattr(s, k):
             raise AttributeError(k)
@@ -156,10 +158,13 @@ class CpuTracer:
             f("last_hit_count").restype = C.c_longlong
             f("renderer_render_ssao").restype = C.c_double
             f("renderer_render_ssao").argtypes = [C.c_void_p, UP, C.c_uint, UP, C.c_int]
+            f("renderer_raster").restype = C.c_double
+            f("renderer_raster").argtypes = [C.c_void_p, UP, C.c_uint, UP, C.c_int]
             f("load_obj").restype = C.c_int
             f("load_obj").argtypes = [C.c_char_p, FP, FP, FP, IP, C.POINTER(RtMaterial), C.c_int, IP]
         else:
             f("renderer_render_ssao").argtypes = [C.c_void_p, UP, C.c_int, C.c_int, UP]
+            f("renderer_raster").argtypes = [C.c_void_p, UP, C.c_int, UP, C.POINTER(C.c_uint64)]
             f("bvh_count").restype = C.c_double
             f("bvh_count").argtypes = [C.c_void_p, FP, FP, C.c_size_t, C.POINTER(C.c_uint64), C.c_int]
             f("renderer_count_rows").argtypes = [C.c_void_p, FP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int]
@@ -351,6 +356,21 @@ class CpuRenderer:
         seeds = None if ref_seeds9 is None else np.ascontiguousarray(ref_seeds9, dtype=np.uint32)
         self.tr._fn("renderer_render_ssao")(self.h, _ptr(out, C.c_uint32), threads, 0 if seeds is None else 1, _ptr(seeds, C.c_uint32))
         return out, None
+
+    def raster(self, srand_seed=1, ref_seeds9=None, n_rand=64):
+        """raster_trace() + post_process() with hybrid_rasterization_tracing (renderer.cpp:869-1006) in sequential triangle
+        order (the compiled reference runs it on one thread).  Returns (argb, extra): extra = rand_values for the compiled
+        reference (see render_ssao), the dict of ray counters for the oracle."""
+        s = self.settings
+        out = np.zeros((s.image_height, s.image_width), np.uint32)
+        if self.tr.kind != "oracle":
+            rv = np.zeros(n_rand, np.uint32)
+            self.tr._fn("renderer_raster")(self.h, _ptr(out, C.c_uint32), int(srand_seed), _ptr(rv, C.c_uint32), n_rand)
+            return out, rv
+        seeds = None if ref_seeds9 is None else np.ascontiguousarray(ref_seeds9, dtype=np.uint32)
+        cnt = (C.c_uint64 * 5)()
+        self.tr._fn("renderer_raster")(self.h, _ptr(out, C.c_uint32), 0 if seeds is None else 1, _ptr(seeds, C.c_uint32), cnt)
+        return out, dict(zip(("fragments", "fragment_hits", "shadow_rays", "reflection_rays", "reflection_shadow_rays"), [int(x) for x in cnt]))
 
     def trace_rows(self, row_begin=0, row_end=None, row_step=1, reseed=True, threads=0, want_image=True):
         """Seeded pixel loop on the supersampled frame; returns (argb_super[H',W'], ms)."""

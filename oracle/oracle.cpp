@@ -159,6 +159,7 @@ struct Hit {       // hitInfo.h:8-29
     int mat = -1;
     V3 normal = {0, 0, 0};
     V3 tangent = {0, 0, 0};
+    const struct Tri* frag = nullptr;  // HitInfo::triangle when it points at raster_trace's temporary (renderer.cpp:619-628), not into _triangles
 };
 
 struct RayT { V3 o, d; };
@@ -614,7 +615,8 @@ struct Renderer {
 
     void tex_coords(const Hit& h, float u, float v, float& tu, float& tv) const     // renderer.cpp:436-445
     {
-        if (h.tri >= 0) tri_texcoords(tris[h.tri], u, v, tu, tv);
+        if (h.frag) tri_texcoords(*h.frag, u, v, tu, tv);
+        else if (h.tri >= 0) tri_texcoords(tris[h.tri], u, v, tu, tv);
         else { tu = u; tv = v; }
     }
 
@@ -781,7 +783,7 @@ struct Renderer {
             c = Col{0.9f, 0.9f, 0.9f};
             if (s.enable_ao_mapping) {
                 float tu, tv;
-                tri_texcoords(tris[hit.tri], hit.u, hit.v, tu, tv);
+                tri_texcoords(hit.frag ? *hit.frag : tris[hit.tri], hit.u, hit.v, tu, tv);
                 c = cmul(c, col(tex[RT_TEX_AO].texture_floor(tu, tv).r));
             }
         }
@@ -1142,6 +1144,257 @@ void render_with_ssao(const Renderer& r, uint32_t* argb_out, int threads, int rn
     else memcpy(argb_out, super.data(), super.size() * sizeof(uint32_t));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Renderer::raster_trace -- renderer.cpp:869-1006, with clip_triangle / clip_triangles_to_plane (:630-853),
+// matrix_transform_z (:855-867) and trace_triangle (:619-628).  The reference walks the triangles under
+// `omp parallel for` with an unsynchronised z-buffer; the restatement is the sequential order (what one thread does):
+// a fragment replaces the pixel iff its depth is STRICTLY smaller, so the pixel ends up with the first fragment, in
+// (triangle, clipped piece) order, of the smallest depth.
+struct V4 { float x, y, z, w; };
+inline V4 v4(float x, float y, float z, float w) { return V4{x, y, z, w}; }
+inline V4 add4(V4 u, V4 v) { return v4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w); }  // vec.cpp:123-126
+inline V4 sub4(V4 u, V4 v) { return v4(u.x - v.x, u.y - v.y, u.z - v.z, u.w - v.w); }  // vec.cpp:128-131
+inline V4 scale4(float t, V4 u) { return v4(u.x * t, u.y * t, u.z * t, u.w * t); }     // vec.cpp:133-141
+inline float comp4(const V4& v, int i) { return (&v.x)[i]; }
+
+// Transform::operator()(const vec4&) -- mat.cpp:119-132
+V4 xform_v4(const M4& t, V4 v)
+{
+    float x = v.x, y = v.y, z = v.z, w = v.w;
+    float xt = t.m[0][0] * x + t.m[0][1] * y + t.m[0][2] * z + t.m[0][3] * w;
+    float yt = t.m[1][0] * x + t.m[1][1] * y + t.m[1][2] * z + t.m[1][3] * w;
+    float zt = t.m[2][0] * x + t.m[2][1] * y + t.m[2][2] * z + t.m[2][3] * w;
+    float wt = t.m[3][0] * x + t.m[3][1] * y + t.m[3][2] * z + t.m[3][3] * w;
+    return v4(xt, yt, zt, wt);
+}
+
+struct Tri4 {                                                                       // Triangle4, triangle.h:24-40
+    V4 a, b, c;
+    V3 tu, tv;
+};
+constexpr int kClipMax = 12;                                                        // std::array<Triangle4, 12>, renderer.cpp:881-882
+
+// is_inside<plane_index, plane_sign> -- renderer.cpp:630-670
+inline bool is_inside(int plane_index, int plane_sign, const V4& v)
+{
+    return plane_sign > 0 ? comp4(v, plane_index) < v.w : comp4(v, plane_index) > -v.w;
+}
+
+// Renderer::clip_triangles_to_plane<plane_index, plane_sign> -- renderer.cpp:672-835 (CLIPPING_EPSILON = 0).  `in` and
+// `out` may be the same array (the first stage of clip_triangle, one triangle): every triangle is read before it is written.
+int clip_to_plane(int plane_index, int plane_sign, const Tri4* in, int n, Tri4* out)
+{
+    int added = 0;
+    for (int i = 0; i < n; i++) {
+        const Tri4 t = in[i];
+        const bool ai = is_inside(plane_index, plane_sign, t.a), bi = is_inside(plane_index, plane_sign, t.b), ci = is_inside(plane_index, plane_sign, t.c);
+        const int sum = ai + bi + ci;
+        const float sign = (float)plane_sign;
+        if (sum == 3) {
+            if (added < kClipMax) out[added++] = t;
+        } else if (sum == 1) {
+            V4 in_v, o1, o2;
+            float u[3], v[3];                                                       // { inside, outside_1, outside_2 }
+            if (ai) { in_v = t.a; o1 = t.b; o2 = t.c; u[0] = t.tu.x; u[1] = t.tu.y; u[2] = t.tu.z; v[0] = t.tv.x; v[1] = t.tv.y; v[2] = t.tv.z; }
+            else if (bi) { in_v = t.b; o1 = t.c; o2 = t.a; u[0] = t.tu.y; u[1] = t.tu.z; u[2] = t.tu.x; v[0] = t.tv.y; v[1] = t.tv.z; v[2] = t.tv.x; }
+            else { in_v = t.c; o1 = t.a; o2 = t.b; u[0] = t.tu.z; u[1] = t.tu.x; u[2] = t.tu.y; v[0] = t.tv.z; v[1] = t.tv.x; v[2] = t.tv.y; }
+            float din = comp4(in_v, plane_index) - in_v.w * sign;
+            float d1 = comp4(o1, plane_index) - o1.w * sign;
+            float d2 = comp4(o2, plane_index) - o2.w * sign;
+            float tp1 = d1 / (d1 - din);
+            float tp2 = d2 / (d2 - din);
+            V4 p1 = add4(o1, scale4(tp1 - 0.0f, sub4(in_v, o1)));
+            V4 p2 = add4(o2, scale4(tp2 - 0.0f, sub4(in_v, o2)));
+            Tri4 nt;
+            nt.a = in_v; nt.b = p1; nt.c = p2;
+            nt.tu = v3(u[0], u[1] + (tp1 - 0.0f) * (u[0] - u[1]), u[2] + (tp2 - 0.0f) * (u[0] - u[2]));
+            nt.tv = v3(v[0], v[1] + (tp1 - 0.0f) * (v[0] - v[1]), v[2] + (tp2 - 0.0f) * (v[0] - v[2]));
+            if (added < kClipMax) out[added++] = nt;
+        } else if (sum == 2) {
+            V4 i1, i2, ov;
+            float u[3], v[3];                                                       // { inside_1, inside_2, outside }
+            if (!ai) { ov = t.a; i1 = t.b; i2 = t.c; u[0] = t.tu.y; u[1] = t.tu.z; u[2] = t.tu.x; v[0] = t.tv.y; v[1] = t.tv.z; v[2] = t.tv.x; }
+            else if (!bi) { ov = t.b; i1 = t.c; i2 = t.a; u[0] = t.tu.z; u[1] = t.tu.x; u[2] = t.tu.y; v[0] = t.tv.z; v[1] = t.tv.x; v[2] = t.tv.y; }
+            else { ov = t.c; i1 = t.a; i2 = t.b; u[0] = t.tu.x; u[1] = t.tu.y; u[2] = t.tu.z; v[0] = t.tv.x; v[1] = t.tv.y; v[2] = t.tv.z; }
+            float d1 = comp4(i1, plane_index) - i1.w * sign;
+            float d2 = comp4(i2, plane_index) - i2.w * sign;
+            float dout = comp4(ov, plane_index) - ov.w * sign;
+            float tp1 = dout / (dout - d1);
+            float tp2 = dout / (dout - d2);
+            V4 p1 = add4(ov, scale4(tp1 - 0.0f, sub4(i1, ov)));
+            V4 p2 = add4(ov, scale4(tp2 - 0.0f, sub4(i2, ov)));
+            Tri4 t1, t2;
+            t1.a = i1; t1.b = i2; t1.c = p2;
+            t1.tu = v3(u[0], u[1], u[2] + (tp2 - 0.0f) * (u[1] - u[2]));
+            t1.tv = v3(v[0], v[1], v[2] + (tp2 - 0.0f) * (v[1] - v[2]));
+            t2.a = i1; t2.b = p2; t2.c = p1;
+            t2.tu = v3(u[0], u[2] + (tp2 - 0.0f) * (u[1] - u[2]), u[2] + (tp1 - 0.0f) * (u[0] - u[2]));
+            t2.tv = v3(v[0], v[2] + (tp2 - 0.0f) * (v[1] - v[2]), v[2] + (tp1 - 0.0f) * (v[0] - v[2]));
+            if (added < kClipMax) out[added++] = t1;                                // (the reference's arrays hold 12 and are not checked)
+            if (added < kClipMax) out[added++] = t2;
+        }
+    }
+    return added;
+}
+
+// Renderer::clip_triangle -- renderer.cpp:837-853: right, left, top, bottom, far, near, ping-ponging between the two arrays.
+int clip_triangle(bool enable_clipping, Tri4* to_clip, Tri4* clipped)
+{
+    int n = 1;
+    if (enable_clipping) {
+        n = clip_to_plane(0, 1, to_clip, n, to_clip);
+        n = clip_to_plane(0, -1, to_clip, n, clipped);
+        n = clip_to_plane(1, 1, clipped, n, to_clip);
+        n = clip_to_plane(1, -1, to_clip, n, clipped);
+        n = clip_to_plane(2, 1, clipped, n, to_clip);
+        n = clip_to_plane(2, -1, to_clip, n, clipped);
+    } else
+        clipped[0] = to_clip[0];
+    return n;
+}
+
+// Renderer::matrix_transform_z -- renderer.cpp:855-867
+inline float matrix_transform_z(const M4& m, V3 p)
+{
+    float zt = m.m[2][0] * p.x + m.m[2][1] * p.y + m.m[2][2] * p.z + m.m[2][3];
+    float wt = m.m[3][0] * p.x + m.m[3][1] * p.y + m.m[3][2] * p.z + m.m[3][3];
+    if (wt == 1.0f) return zt;
+    return zt / wt;
+}
+
+// Triangle::edge_function -- triangle.h:65-68
+inline float edge_function(V3 p, V3 a, V3 b) { return (b.x - a.x) * (p.y - a.y) - (b.y - a.y) * (p.x - a.x); }
+
+// Transform::operator()(const Triangle&) -- mat.cpp:133-140: the three points, then Triangle(a, b, c, ...) recomputes the normal
+inline Tri xform_tri(const M4& m, const Tri& t)
+{
+    Tri r;
+    r.a = xform_point(m, t.a); r.b = xform_point(m, t.b); r.c = xform_point(m, t.c);
+    r.normal = cross(sub(r.b, r.a), sub(r.c, r.a));
+    r.mat = t.mat; r.tu = t.tu; r.tv = t.tv;
+    return r;
+}
+
+// argb_super: the supersampled image as clear_image() left it; zbuf: +inf; nbuf (may be null): the SSAO normal buffer.
+void raster_trace(const Renderer& r, uint32_t* argb_super, float* zbuf, V3* nbuf, RenderCounters* rc)
+{
+    int rw, rh;
+    r.super_dims(rw, rh);
+    const M4 proj = perspective(r.fov, (float)rw / rh, 0.1f, 1000.0f);              // scene/camera.cpp:5-11
+    const M4 proj_inv = inverse(proj);
+    const M4 world_to_cam = inverse(r.cam_to_world);                                // renderer.cpp:229
+    const float height_scaling = 1.0f / rh * 2;
+    const float width_scaling = 1.0f / rw * 2;
+    Tri4 to_clip[kClipMax], clipped[kClipMax];
+    for (size_t ti = 0; ti < r.tris.size(); ti++) {
+        const Tri& orig = r.tris[ti];
+        const Tri cam = xform_tri(world_to_cam, orig);
+        to_clip[0].a = xform_v4(proj, v4(cam.a.x, cam.a.y, cam.a.z, 1));
+        to_clip[0].b = xform_v4(proj, v4(cam.b.x, cam.b.y, cam.b.z, 1));
+        to_clip[0].c = xform_v4(proj, v4(cam.c.x, cam.c.y, cam.c.z, 1));
+        to_clip[0].tu = cam.tu; to_clip[0].tv = cam.tv;
+        const int nb = clip_triangle(r.s.enable_clipping != 0, to_clip, clipped);
+        for (int ci = 0; ci < nb; ci++) {
+            const Tri4& c4 = clipped[ci];
+            Tri ndc;                                                                // Triangle(const Triangle4&, ...), triangle.cpp:12-23
+            {
+                float iaw = 1.0f / c4.a.w, ibw = 1.0f / c4.b.w, icw = 1.0f / c4.c.w;
+                ndc.a = v3(c4.a.x * iaw, c4.a.y * iaw, c4.a.z * iaw);
+                ndc.b = v3(c4.b.x * ibw, c4.b.y * ibw, c4.b.z * ibw);
+                ndc.c = v3(c4.c.x * icw, c4.c.y * icw, c4.c.z * icw);
+                ndc.normal = v3(0, 0, 0);                                           // left uninitialised by the reference, never read
+                ndc.mat = orig.mat; ndc.tu = c4.tu; ndc.tv = c4.tv;
+            }
+            const Tri cam_space = xform_tri(proj_inv, ndc);
+            const V3 a = ndc.a, b = ndc.b, c = ndc.c;
+            float inv_area = 1 / ((b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x));
+            float bminx = std::min(a.x, std::min(b.x, c.x)), bminy = std::min(a.y, std::min(b.y, c.y));
+            float bmaxx = std::max(a.x, std::max(b.x, c.x)), bmaxy = std::max(a.y, std::max(b.y, c.y));
+            int min_x = (int)((bminx + 1) * 0.5 * rw), min_y = (int)((bminy + 1) * 0.5 * rh);
+            int max_x = (int)((bmaxx + 1) * 0.5 * rw), max_y = (int)((bmaxy + 1) * 0.5 * rh);
+            min_x = std::max(min_x, 0); min_y = std::max(min_y, 0);
+            max_x = std::min(rw - 1, max_x); max_y = std::min(rh - 1, max_y);
+            float image_y = min_y * height_scaling - 1;
+            for (int py = min_y; py <= max_y; py++, image_y += height_scaling) {
+                float image_x = min_x * width_scaling - 1;
+                for (int px = min_x; px <= max_x; px++, image_x += width_scaling) {
+                    V3 pp = v3(image_x + width_scaling * 0.5f, image_y + height_scaling * 0.5f, -1);
+                    float u = edge_function(pp, c, a);
+                    if (u < 0) continue;
+                    float v = edge_function(pp, a, b);
+                    if (v < 0) continue;
+                    float w = edge_function(pp, b, c);
+                    if (w < 0) continue;
+                    u *= inv_area; v *= inv_area; w *= inv_area;
+                    float za = matrix_transform_z(r.cam_to_world, xform_point(proj_inv, a));
+                    float zb = matrix_transform_z(r.cam_to_world, xform_point(proj_inv, b));
+                    float zc = matrix_transform_z(r.cam_to_world, xform_point(proj_inv, c));
+                    float z_tri = -1 / (1 / za * w + 1 / zb * u + 1 / zc * v);
+                    const size_t pix = (size_t)py * rw + px;
+                    if (!(z_tri < zbuf[pix])) continue;
+                    zbuf[pix] = z_tri;
+                    if (nbuf) nbuf[pix] = orig.normal;
+                    Col color = col(0.0f);
+                    if (r.s.shading_method == RT_SHADING) {
+                        RayT ray{r.cam_pos, normalize(sub(xform_point(r.cam_to_world, xform_point(proj_inv, pp)), r.cam_pos))};
+                        const Tri world = xform_tri(r.cam_to_world, cam_space);
+                        Hit hit;                                                    // trace_triangle, renderer.cpp:619-628
+                        if (rc) rc->primary_rays++;
+                        if (tri_intersect(world, (int)ti, ray, hit)) {
+                            hit.frag = &world;
+                            XorShift rng;
+                            rng.state = pixel_seed((uint32_t)(py * rw + px), r.s.rng_seed);
+                            if (rc) rc->primary_hits++;
+                            color = r.shade(ray, hit, 0, rng, rc, false);
+                        }
+                    } else if (r.s.shading_method == RT_ABS_NORMALS_SHADING) {
+                        V3 n = normalize(orig.normal);
+                        color = Col{std::abs(n.x), std::abs(n.y), std::abs(n.z)};
+                    } else if (r.s.shading_method == RT_PASTEL_NORMALS_SHADING) {
+                        V3 n = normalize(orig.normal);
+                        color = cscale(cadd(Col{n.x, n.y, n.z}, col(1.0f)), 0.5f);
+                    } else if (r.s.shading_method == RT_BARYCENTRIC_COORDINATES_SHADING) {
+                        color = cadd(cadd(cscale(Col{1, 0, 0}, u), cscale(Col{0, 1, 0}, v)), cscale(Col{0, 0, 1}, 1 - u - v));
+                    } else if (r.s.shading_method == RT_VISUALIZE_AO) {             // shade_visualize_ao(proj_inv(ndc), u, v), :419-434
+                        color = Col{0.9f, 0.9f, 0.9f};
+                        if (r.s.enable_ao_mapping) {
+                            float tu, tv;
+                            tri_texcoords(cam_space, u, v, tu, tv);
+                            color = cmul(color, col(r.tex[RT_TEX_AO].texture_floor(tu, tv).r));
+                        }
+                    }
+                    argb_super[pix] = quantise(color);
+                }
+            }
+        }
+    }
+}
+
+// clear_z_buffer / clear_normal_buffer / clear_image (QT/mainwindow.cpp:184-190), raster_trace(), post_process()
+void render_raster(const Renderer& r, uint32_t* argb_out, int rng_mode, const uint32_t* ref_seeds9, RenderCounters* rc)
+{
+    int rw, rh;
+    r.super_dims(rw, rh);
+    const uint32_t background = quantise(Col{135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f});   // renderer.cpp:19,175-180
+    std::vector<uint32_t> super((size_t)rw * rh, background);
+    std::vector<float> z((size_t)rw * rh, INFINITY);
+    std::vector<V3> n;
+    if (r.s.enable_ssao) n.assign((size_t)rw * rh, v3(0, 0, 0));
+    raster_trace(r, super.data(), z.data(), r.s.enable_ssao ? n.data() : nullptr, rc);
+    if (r.s.enable_ssao) {
+        SsaoFrame f;
+        f.rw = rw; f.rh = rh; f.z = z.data(); f.n = n.data();
+        f.aspect = (float)rw / rh;
+        f.proj = perspective(r.fov, f.aspect, 0.1f, 1000.0f);
+        f.fov_mult_simd = (float)std::tan(r.fov / 2 / 180 * M_PI);
+        f.fov_mult_scalar = std::tan(((float)M_PI / 180) * (r.fov / 2));
+        f.samples = r.s.ssao_sample_count; f.radius = r.s.ssao_radius;
+        ssao_post_process(f, super.data(), r.s.rng_seed, r.s.ssao_amount, rng_mode, ref_seeds9);
+    }
+    if (r.s.enable_ssaa) downscale(super.data(), rw, rh, r.s.ssaa_factor, argb_out);
+    else memcpy(argb_out, super.data(), super.size() * sizeof(uint32_t));
+}
+
 struct BvhHandle {
     std::vector<Tri> tris;
     Octree tree;
@@ -1355,6 +1608,16 @@ void orc_renderer_render_ssao(void* h, uint32_t* argb_out, int threads, int rng_
     render_with_ssao(*(Renderer*)h, argb_out, threads, rng_mode, ref_seeds9);
 }
 
+// Renderer::raster_trace + post_process (hybrid_rasterization_tracing) -- renderer.cpp:869-1006,1118-1124, in sequential
+// triangle order.  out5 (may be NULL): fragments shaded with RT_SHADING, of which hit their triangle, shadow rays,
+// reflection rays, reflection shadow rays.
+void orc_renderer_raster(void* h, uint32_t* argb_out, int rng_mode, const uint32_t* ref_seeds9, uint64_t* out5)
+{
+    RenderCounters rc;
+    render_raster(*(Renderer*)h, argb_out, rng_mode, ref_seeds9, out5 ? &rc : nullptr);
+    if (out5) { out5[0] = rc.primary_rays; out5[1] = rc.primary_hits; out5[2] = rc.shadow_rays; out5[3] = rc.reflection_rays; out5[4] = rc.reflection_shadow_rays; }
+}
+
 void orc_downscale(const uint32_t* in, int w, int hgt, int factor, uint32_t* out) { downscale(in, w, hgt, factor, out); }
 
 int orc_omp_max_threads(void) { return omp_get_max_threads(); }
@@ -1370,5 +1633,6 @@ void default_settings(RtSettings* s)
     s->enable_bvh = 1; s->bvh_max_depth = 12; s->bvh_leaf_object_count = 40;
     s->enable_ambient = s->enable_diffuse = s->enable_specular = s->enable_emissive = 1;
     s->rough_reflections_sample_count = 3;
+    s->enable_clipping = 1;                                                          // rendererSettings.h:40
 }
 } // namespace

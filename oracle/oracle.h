@@ -39,6 +39,9 @@ double orc_renderer_trace_rows(void* h, const float cam_to_world[16], uint32_t* 
 // primary V, primary T, shadow V, shadow T, reflection(+its shadows) V, reflection(+its shadows) T.
 void orc_renderer_count_rows(void* h, const float cam_to_world[16], int row_begin, int row_end, int row_step,
                              uint64_t* out16, int threads);
+// hybrid_rasterization_tracing: Renderer::raster_trace + post_process in sequential triangle order; rng_mode / ref_seeds9 as in
+// orc_renderer_render_ssao; out5 (may be NULL) = shaded fragments, of which hit, shadow / reflection / reflection-shadow rays.
+void orc_renderer_raster(void* h, uint32_t* argb_out, int rng_mode, const uint32_t* ref_seeds9, uint64_t* out5);
 void orc_downscale(const uint32_t* in, int w, int hgt, int factor, uint32_t* out);
 int orc_omp_max_threads(void);
 

@@ -78,6 +78,7 @@ void apply_settings(RenderSettings& rs, const RtSettings& s)
     rs.ssao_sample_count = s.ssao_sample_count;
     rs.ssao_radius = s.ssao_radius;
     rs.ssao_amount = s.ssao_amount;
+    rs.enable_clipping = s.enable_clipping != 0;
 }
 
 struct RefBvh {
@@ -371,6 +372,39 @@ double ref_renderer_render_ssao(void* handle, uint32_t* argb_out, unsigned seed,
     h->renderer.post_process();
     omp_set_num_threads(threads);
     auto t1 = std::chrono::steady_clock::now();
+    if (argb_out) {
+        QImage* img = h->renderer.get_image();
+        memcpy(argb_out, img->raw(), sizeof(uint32_t) * (size_t)img->width() * img->height());
+    }
+    return std::chrono::duration<double, std::milli>(t1 - t0).count();
+}
+
+// Renderer::raster_trace() + post_process() (hybrid_rasterization_tracing in the settings given to ref_renderer_configure,
+// so that init_buffers allocated the z-buffer): the GUI's sequence clear_z_buffer / clear_normal_buffer / clear_image
+// (QT/mainwindow.cpp:184-190), raster_trace(), post_process() (QT/mainWindowThreads.cpp:46-57).  raster_trace() walks the
+// triangles under `omp parallel for` with an unsynchronised z-buffer: ONE thread is the reproducible run (sequential
+// triangle order), and with enable_ssao the SSAO pass runs after srand(seed) as in ref_renderer_render_ssao.
+double ref_renderer_raster(void* handle, uint32_t* argb_out, unsigned seed, uint32_t* rand_values, int n_rand)
+{
+    RefRenderer* h = (RefRenderer*)handle;
+    const int threads = omp_get_max_threads();
+    if (h->settings.enable_ssao) {
+        h->renderer.prepare_ssao_buffers();
+        h->renderer.clear_normal_buffer();
+    }
+    h->renderer.clear_z_buffer();
+    h->renderer.clear_image();
+    omp_set_num_threads(1);
+    auto t0 = std::chrono::steady_clock::now();
+    h->renderer.raster_trace();
+    if (rand_values) {
+        srand(seed);
+        for (int i = 0; i < n_rand; i++) rand_values[i] = (uint32_t)rand();
+    }
+    srand(seed);
+    h->renderer.post_process();
+    auto t1 = std::chrono::steady_clock::now();
+    omp_set_num_threads(threads);
     if (argb_out) {
         QImage* img = h->renderer.get_image();
         memcpy(argb_out, img->raw(), sizeof(uint32_t) * (size_t)img->width() * img->height());

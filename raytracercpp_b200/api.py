@@ -22,6 +22,7 @@ RT_TEX_SKYBOX_RIGHT, RT_TEX_SKYBOX_LEFT, RT_TEX_SKYBOX_TOP, RT_TEX_SKYBOX_BOTTOM
 RT_TEX_DISPLACEMENT = 11
 RT_OPT_COUNT_WORK, RT_OPT_CHUNK_PIXELS, RT_OPT_LEAF_SPLIT, RT_OPT_REFILL_PRIMARY, RT_OPT_REFILL_SHADE, RT_OPT_TRI_BATCH, RT_OPT_PACKETS = 0, 1, 2, 3, 4, 5, 6
 RT_OPT_PACKET_ROUNDS, RT_OPT_SCREEN_CULL, RT_OPT_LANES, RT_OPT_ITEM_ROUNDS, RT_OPT_PRIMARY_ROUNDS, RT_OPT_FUSED_ITEMS, RT_OPT_TOP_TABLE, RT_OPT_SHADOW_SORT, RT_OPT_DEVICE_BUILD, RT_OPT_ITEM_PASSES = 7, 8, 9, 10, 11, 12, 13, 14, 15, 16
+RT_OPT_RASTER_UNITS = 17
 
 
 class RtError(RuntimeError):
@@ -49,7 +50,8 @@ SETTINGS_FIELDS = [
 class RtSettings(C.Structure):
     _fields_ = [(n, C.c_int32) for n in SETTINGS_FIELDS] + [("rng_seed", C.c_uint32), ("displacement_mapping_strength", C.c_float),
                                                               ("parallax_mapping_steps", C.c_int32),
-                                                              ("ssao_sample_count", C.c_int32), ("ssao_radius", C.c_float), ("ssao_amount", C.c_float)]
+                                                              ("ssao_sample_count", C.c_int32), ("ssao_radius", C.c_float), ("ssao_amount", C.c_float),
+                                                             ("enable_clipping", C.c_int32)]
 
     def copy(self) -> "RtSettings":
         out = RtSettings()

@@ -89,6 +89,7 @@ inline void default_settings(RtSettings* s)
     s->ssao_sample_count = 64;                    // rendererSettings.h:69-73
     s->ssao_radius = 0.5f;
     s->ssao_amount = 1.0f;
+    s->enable_clipping = 1;                       // rendererSettings.h:40
 }
 
 // Returns RT_OK or an error code with a message in `why`.
@@ -102,7 +103,6 @@ inline int check_settings(const RtSettings* s, std::string& why)
         return bad(RT_ERR_INVALID, buf);
     }
     if (s->enable_ssaa && s->ssaa_factor < 1) return bad(RT_ERR_INVALID, "ssaa_factor < 1");
-    if (s->hybrid_rasterization_tracing) return bad(RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing stays on the host (renderer.cpp:869-1006)");
     if (s->enable_ssao && s->ssao_sample_count < 0) return bad(RT_ERR_INVALID, "ssao_sample_count < 0");
     if (s->enable_displacement_mapping && s->parallax_mapping_steps < 1) return bad(RT_ERR_INVALID, "parallax_mapping_steps < 1");
     if (!s->enable_bvh) return bad(RT_ERR_UNSUPPORTED, "enable_bvh = false (brute force) is not offered");

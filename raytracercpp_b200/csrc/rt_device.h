@@ -65,6 +65,8 @@ struct SceneView {
     int32_t n_shapes;       // kind 0 = Sphere (a = centre), 1 = Plane (a = point, n = normal)
     int32_t n_mats;
     uint32_t n_tris;
+    const rt_f4* frag_shade; // hybrid raster path only (raster_device.h): shading records of the clipped pieces being shaded, one per
+                             // thread; triangle index n_tris + i means record i here (their texture coordinates are the clipped ones)
     TexView tex[RT_TEX_COUNT];
 };
 
@@ -468,8 +470,15 @@ struct TriShade {       // shading-side triangle data
 
 RT_DEV TriShade load_tri_shade(const SceneView& sc, int32_t tri)
 {
-    const rt_f4* s = sc.shade + 2 * (size_t)tri;
-    rt_f4 a = RT_LDG4(s), b = RT_LDG4(s + 1);
+    rt_f4 a, b;
+    if ((uint32_t)tri >= sc.n_tris) {
+        // a clipped piece of raster_trace: written by this very thread a moment ago, so an ordinary (coherent) load
+        const rt_f4* s = sc.frag_shade + 2 * (size_t)((uint32_t)tri - sc.n_tris);
+        a = s[0]; b = s[1];
+    } else {
+        const rt_f4* s = sc.shade + 2 * (size_t)tri;
+        a = RT_LDG4(s); b = RT_LDG4(s + 1);
+    }
     TriShade ts;
     ts.tu = v3(a.x, a.y, a.z);
     ts.tv = v3(a.w, b.x, b.y);

@@ -22,6 +22,7 @@
 #include "scene_layout.h"
 #include "octree_device.cuh"
 #include "ssao.cuh"
+#include "raster.cuh"
 #include "host_common.h"
 
 using namespace rtb;
@@ -118,6 +119,7 @@ struct Pending {                          // a frame that has been enqueued (rt_
     size_t host_cap = 0;
     uint32_t n_chunks = 0, launches = 0;
     bool count = false, shadow = false;
+    bool raster = false;                  // a raster_trace frame: `primary_rays` = the fragments whose ray was tested against their piece
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     uint64_t primary_rays = 0;
     bool has_key = false;                 // the tile list of the frame and its traced ray slots (for TileList::last_hit_fraction)
@@ -206,6 +208,15 @@ struct RtContext {
     DevBuf<float> d_gz;
     DevBuf<V3> d_gn;
     DevBuf<int> d_ao;
+    // hybrid raster path (raster.cuh): z-keys and pixel points per supersampled pixel, work units of the large pieces,
+    // per-thread shading records of the pieces being shaded
+    DevBuf<unsigned long long> d_rkeys;
+    DevBuf<float2> d_rxy;
+    DevBuf<RasterUnit> d_runits;
+    DevBuf<unsigned int> d_rcount;
+    DevBuf<float4> d_rfrag;
+    size_t raster_smem_set = 0;
+    size_t raster_units0 = (size_t)1 << 18;   // first size of the unit list (RT_OPT_RASTER_UNITS); grown when a frame needs more
     M4 proj{};
     float proj_fov = 45.0f, proj_aspect = 1.0f;
     bool proj_set = false;
@@ -780,6 +791,7 @@ void rt_destroy(RtContext* ctx)
     ctx->d_recs.release(); ctx->d_top.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release(); ctx->db.release(); ctx->d_gz.release(); ctx->d_gn.release(); ctx->d_ao.release();
+    ctx->d_rkeys.release(); ctx->d_rxy.release(); ctx->d_runits.release(); ctx->d_rcount.release(); ctx->d_rfrag.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
     for (auto& qs : ctx->qs) qs.release();
     for (auto st : ctx->lane_stream) if (st) cudaStreamDestroy(st);
@@ -846,6 +858,11 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
     case RT_OPT_LANES:
         if (value < 0 || value > kMaxLanes) return fail(ctx, RT_ERR_INVALID, "lanes %lld outside [0,%d]", (long long)value, kMaxLanes);
         ctx->opt_lanes = value == 1 ? kLanes : (int)std::max<int64_t>(value, 1);   // 0: one chunk at a time; 1: the default (2); n: n chunks in flight
+        return RT_OK;
+    case RT_OPT_RASTER_UNITS:
+        if (value < 1 || value > (1ll << 28)) return fail(ctx, RT_ERR_INVALID, "raster unit list of %lld entries outside [1, 2^28]", (long long)value);
+        ctx->d_runits.release();
+        ctx->raster_units0 = (size_t)value;
         return RT_OK;
     case RT_OPT_CHUNK_PIXELS:
         if (value < 256 || value > (1ll << 31)) return fail(ctx, RT_ERR_INVALID, "chunk of %lld pixels outside [256, 2^31] (ray slots are 32-bit)", (long long)value);
@@ -1093,6 +1110,9 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     if (int r = check_tile_args(ctx, tile_size, tile_mod, tile_rem)) return r;
     if (!d_argb_out) return fail(ctx, RT_ERR_INVALID, "d_argb_out is NULL");
     const bool ssao = s->enable_ssao != 0;
+    const bool raster = s->hybrid_rasterization_tracing != 0;
+    if (raster && tile_mod != 1) return fail(ctx, RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing renders the whole frame on one GPU (one z-buffer)");
+    if (raster && !ctx->proj_set) return fail(ctx, RT_ERR_STATE, "hybrid_rasterization_tracing: the projection has not been set (rt_set_projection)");
     if (ssao && tile_mod != 1) return fail(ctx, RT_ERR_UNSUPPORTED, "enable_ssao needs the whole frame on one GPU: its samples read the z-buffer of neighbouring tiles");
     if (ssao && !ctx->proj_set) return fail(ctx, RT_ERR_STATE, "enable_ssao: the projection has not been set (rt_set_projection)");
 
@@ -1115,7 +1135,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     // no traversal, only the miss colour (k_fill_miss).  The wavefront below runs over the other tiles.
     const bool has_shapes = !ctx->shapes.empty();                             // planes are unbounded: no screen-space bound
     if (has_shapes) { wk.cull_x0 = 0; wk.cull_y0 = 0; wk.cull_x1 = fr.rw - 1; wk.cull_y1 = fr.rh - 1; }
-    const bool classify = ctx->opt_screen_cull && ctx->tune.packets && tl->count > 0 && !has_shapes;
+    const bool classify = ctx->opt_screen_cull && ctx->tune.packets && tl->count > 0 && !has_shapes && !raster;
     if (classify) {
         const int32_t rect[4] = {wk.cull_x0, wk.cull_y0, wk.cull_x1, wk.cull_y1};
         if (!tl->split_valid || memcmp(rect, tl->split_rect, sizeof(rect)) != 0 || tl->split_tile_px != wk.tile_px) {
@@ -1136,7 +1156,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
             tl->split_valid = true;
         }
     }
-    const uint32_t n_traced = classify ? tl->n_traced : tl->count;
+    const uint32_t n_traced = raster ? 0u : (classify ? tl->n_traced : tl->count);   // raster_trace: no primary rays, the wavefront below has no chunks
     const std::vector<uint32_t> tiles(classify ? tl->split_host.begin() : owned.begin(), (classify ? tl->split_host.begin() : owned.begin()) + n_traced);
     const uint64_t px_per_tile = (uint64_t)wk.patches_per_side * wk.patches_per_side * kPatch * kPatch;
     uint32_t tiles_per_chunk = (uint32_t)std::max<uint64_t>(1, ctx->opt_chunk_pixels / px_per_tile);
@@ -1392,6 +1412,56 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         }
     }
     st = main_stream;
+    if (raster && !owned.empty()) {
+        // Renderer::raster_trace (renderer.cpp:869-1006): depth pass, emit pass, shade pass (raster.cuh)
+        const size_t npx = (size_t)fr.rw * fr.rh;
+        RasterView rv;
+        rv.world_to_cam = invert_matrix(ctx->cam_to_world);                    // Camera::_world_to_camera_mat, renderer.cpp:229
+        rv.proj = ctx->proj;
+        rv.clipping = s->enable_clipping;
+        const size_t smem = ((size_t)fr.rw + kRasterBandRows) * sizeof(float);
+        if (smem > 200 * 1024) return fail(ctx, RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing: frame wider than 51 000 supersampled pixels");
+        if (smem > 48 * 1024 && smem > ctx->raster_smem_set) {
+            RT_CUDA(ctx, cudaFuncSetAttribute(k_raster_units<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RT_CUDA(ctx, cudaFuncSetAttribute(k_raster_units<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->raster_smem_set = smem;
+        }
+        const int shade_grid = ctx->sm_count * 8, shade_threads = 128;
+        RT_CUDA(ctx, ctx->d_rkeys.ensure(npx)); RT_CUDA(ctx, ctx->d_rxy.ensure(npx)); RT_CUDA(ctx, ctx->d_rcount.ensure(1));
+        RT_CUDA(ctx, ctx->d_rfrag.ensure((size_t)2 * shade_grid * shade_threads));
+        if (ctx->d_runits.n == 0) RT_CUDA(ctx, ctx->d_runits.ensure(ctx->raster_units0));
+        SceneView scf = sc;
+        scf.frag_shade = ctx->d_rfrag.p;
+        const int tri_grid = (int)std::min<uint64_t>(((uint64_t)ctx->n_tris + 127) / 128, (uint64_t)ctx->sm_count * 16), unit_grid = ctx->sm_count * 4;
+        RasterBuffers rb;
+        rb.keys = ctx->d_rkeys.p; rb.frag_xy = ctx->d_rxy.p; rb.n_units = ctx->d_rcount.p;
+        {
+            ScopedTimer tm(ctx, ST_PRIMARY, st);
+            unsigned int n_units = 0;
+            for (;;) {                                                         // depth pass; repeated once if the unit list was too short
+                rb.units = ctx->d_runits.p;
+                rb.unit_cap = (uint32_t)std::min<size_t>(ctx->d_runits.n, 0xffffffffu);
+                RT_CUDA(ctx, cudaMemsetAsync(rb.keys, 0xff, npx * sizeof(unsigned long long), st));     // RT_RASTER_EMPTY = clear_z_buffer()
+                RT_CUDA(ctx, cudaMemsetAsync(rb.n_units, 0, sizeof(unsigned int), st));
+                if (ctx->n_tris) { k_raster_tris<false><<<tri_grid, 128, 0, st>>>(sc, fr, rv, rb); launches++; }
+                // the number of work units says whether the list was long enough: a raster_trace frame waits for it here
+                RT_CUDA(ctx, cudaMemcpyAsync(&n_units, rb.n_units, sizeof(n_units), cudaMemcpyDeviceToHost, st));
+                RT_CUDA(ctx, cudaStreamSynchronize(st));
+                if (n_units <= rb.unit_cap) break;
+                RT_CUDA(ctx, ctx->d_runits.ensure((size_t)n_units + n_units / 4));
+            }
+            if (n_units) { k_raster_units<false><<<unit_grid, kRasterUnitThreads, smem, st>>>(sc, fr, rv, rb); launches++; }
+            if (ctx->n_tris) { k_raster_tris<true><<<tri_grid, 128, 0, st>>>(sc, fr, rv, rb); launches++; }
+            if (n_units) { k_raster_units<true><<<unit_grid, kRasterUnitThreads, smem, st>>>(sc, fr, rv, rb); launches++; }
+        }
+        {
+            const uint32_t background = quantise_argb(col(135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f));   // clear_image(), renderer.cpp:19,175-180
+            ScopedTimer ts(ctx, ST_SHADE, st);
+            if (count) k_raster_shade<true><<<shade_grid, shade_threads, 0, st>>>(scf, fr, rv, rb, ctx->d_rfrag.p, super, ssao ? ctx->d_gz.p : nullptr, ssao ? ctx->d_gn.p : nullptr, background, ctx->d_counters.p);
+            else k_raster_shade<false><<<shade_grid, shade_threads, 0, st>>>(scf, fr, rv, rb, ctx->d_rfrag.p, super, ssao ? ctx->d_gz.p : nullptr, ssao ? ctx->d_gn.p : nullptr, background, ctx->d_counters.p);
+            launches++;
+        }
+    }
     for (int l = 1; l < n_lanes; l++) {                                        // the frame continues when all lanes are done
         RT_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
         RT_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->lane_join[l], 0));
@@ -1443,12 +1513,13 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         pd.host_cap = n_cnt;
     }
     RT_CUDA(ctx, cudaMemcpyAsync(pd.host_cnt, ctx->d_counters.p, sizeof(ChunkCounters) * n_cnt, cudaMemcpyDeviceToHost, st));
-    pd.n_chunks = n_chunks;
+    pd.n_chunks = raster ? 1u : n_chunks;
+    pd.raster = raster;
     pd.launches = launches;
     pd.count = count;
     pd.ev_begin = ev_begin; pd.ev_end = ev_end;
     pd.shadow = s->shading_method == RT_SHADING && s->compute_shadows;
-    pd.has_key = true;
+    pd.has_key = !raster;
     pd.key[0] = s->image_width; pd.key[1] = s->image_height; pd.key[2] = tile_size; pd.key[3] = tile_mod; pd.key[4] = tile_rem;
     pd.traced_slots = (uint64_t)n_traced * px_per_tile;
     pd.primary_rays = 0;                                  // supersampled pixels of the owned tiles that lie inside the frame
@@ -1493,7 +1564,7 @@ int rt_render_device_end(RtContext* ctx, RtRenderStats* stats)
         auto it = ctx->tile_lists.find(TileKey(pd.key[0], pd.key[1], pd.key[2], pd.key[3], pd.key[4]));
         if (it != ctx->tile_lists.end()) it->second.last_hit_fraction = pd.traced_slots ? (float)((double)rs.primary_hits / (double)pd.traced_slots) : 0.0f;
     }
-    rs.primary_rays = pd.primary_rays;
+    rs.primary_rays = pd.raster ? rs.traced_primary_rays : pd.primary_rays;
     rs.shadow_rays = pd.shadow ? rs.primary_hits : 0;
     rs.kernel_launches = pd.launches;
     cudaEventElapsedTime(&rs.device_ms, ev_begin, ev_end);

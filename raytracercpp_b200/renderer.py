@@ -148,17 +148,32 @@ class Renderer:
     def _push_camera(self):
         proj_inv = self.ctx.perspective_inverse(self._fov, self._aspect, self._near, self._far)
         self.ctx.set_camera(proj_inv, self._camera_to_world, self._position)
-        self.ctx.set_projection(self._fov, self._aspect, self._near, self._far)       # read by the SSAO pass only
+        self.ctx.set_projection(self._fov, self._aspect, self._near, self._far)       # read by the SSAO pass and by raster_trace
 
     # -- rendering ------------------------------------------------------------------------------------------------
     def ray_trace(self):
         """Renderer::ray_trace() + the SSAA half of post_process() (renderer.cpp:1068-1135).  The resolve runs on the
         device in the same call -- and, with enable_ssao, the SSAO pass before it (renderer.cpp:1229-1434) -- so post_process() has
         nothing left to do for this path."""
+        self._render(0)
+
+    def raster_trace(self):
+        """Renderer::raster_trace() (renderer.cpp:869-1006), what RenderThread::run calls instead of ray_trace() when
+        render_settings().hybrid_rasterization_tracing is set (QT/mainWindowThreads.cpp:46-49): primary visibility by
+        clipping + rasterisation + z-buffer on the device, shading with shadow rays and reflection fans as in ray_trace().
+        The image starts from clear_image() (QT/mainwindow.cpp:186-190): uncovered pixels are the background colour."""
+        self._render(1)
+
+    def _render(self, hybrid: int):
         rw, rh = self.get_render_width_height()
         self._aspect = float(np.float32(rw) / np.float32(rh))
         self._push_camera()
-        self._image, self._stats = self.ctx.render(self._settings)
+        keep = self._settings.hybrid_rasterization_tracing
+        self._settings.hybrid_rasterization_tracing = hybrid
+        try:
+            self._image, self._stats = self.ctx.render(self._settings)
+        finally:
+            self._settings.hybrid_rasterization_tracing = keep
 
     def post_process(self):
         """Renderer::post_process (renderer.cpp:1118-1124): SSAO and the SSAA resolve ran on the device inside ray_trace()."""
@@ -191,6 +206,9 @@ def _compose(a, b):
 def render(renderer: Renderer) -> float:
     """The reference's timed harness entry `render(Renderer&)` (utils/mainUtils.cpp:6-21): trace + post-process, ms."""
     t0 = time.perf_counter()
-    renderer.ray_trace()
+    if renderer.render_settings().hybrid_rasterization_tracing:
+        renderer.raster_trace()
+    else:
+        renderer.ray_trace()
     renderer.post_process()
     return (time.perf_counter() - t0) * 1e3

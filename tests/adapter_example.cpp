@@ -41,6 +41,17 @@ int main()
         std::printf("rays %llu hits %llu launches %u lit %zu\n", (unsigned long long)st.primary_rays,
                     (unsigned long long)st.primary_hits, st.kernel_launches, lit);
         if (st.primary_rays != 160u * 90u * 4u || st.primary_hits == 0 || lit == 0) return 1;
+        // the hybrid path: RenderThread::run calls raster_trace() when hybrid_rasterization_tracing is set (QT/mainWindowThreads.cpp:46-49)
+        renderer.clear_z_buffer();
+        renderer.clear_image();
+        renderer.raster_trace();
+        renderer.post_process();
+        const RtRenderStats& rs = renderer.last_stats();
+        size_t lit2 = 0;
+        for (uint32_t c : renderer.get_image()) lit2 += (c != 0xff87ceebu);
+        std::printf("raster: fragments %llu hits %llu launches %u lit %zu\n", (unsigned long long)rs.primary_rays,
+                    (unsigned long long)rs.primary_hits, rs.kernel_launches, lit2);
+        if (rs.primary_hits == 0 || lit2 == 0 || lit2 > lit + lit / 4 || lit2 + lit / 4 < lit) return 1;
         std::puts("adapter ok");
         return 0;
     } catch (const rtb200::Error& e) {

@@ -77,6 +77,47 @@ def ssao_table(mats):
     }
 
 
+CAM_INSIDE = np.float32([[1, 0, 0, 0], [0, 1, 0, -1.0], [0, 0, 1, -2.6], [0, 0, 0, 1]])   # camera inside the robot's bounding box
+
+
+def raster_table(robot):
+    """hybrid_rasterization_tracing set-ups (Renderer::raster_trace, renderer.cpp:869-1006):
+    name -> (scene, settings, materials, textures, camera).  The reference shades its rough-reflection fans from
+    per-thread generators that cannot be reseeded per pixel, so the cases pinned against the compiled reference have no
+    ROUGH reflections (mirror reflections draw no random numbers); `r_rough` is compared between oracle and product only.
+    `r_big`: the robot in front of two wall triangles that cover the frame (the banded work units of raster.cuh) with the
+    camera inside the scene's box, so that every clip plane cuts something."""
+    mats = robot["materials"]
+    tab = config_table(mats)
+    tex2 = tab["cfg2"][2]
+    mirror = [dict(m, roughness=0.0) for m in tab["cfg3_mirror5"][1]]
+    hy = dict(hybrid_rasterization_tracing=1)
+    wall = np.float32([[-30, -12, -9, 30, -12, -9, 30, 20, -7], [-30, -12, -9, 30, 20, -7, -30, 20, -7],
+                       [-40, -2.5, 6, 40, -2.5, 6, 40, -2.5, -30], [-40, -2.5, 6, 40, -2.5, -30, -40, -2.5, -30]])
+    wall_uv = np.float32([[0, 4, 4, 0, 0, 3], [0, 4, 0, 0, 3, 3], [0, 6, 6, 0, 0, 5], [0, 6, 0, 0, 5, 5]])
+    big = dict(xyz9=np.concatenate([wall[:2], robot["xyz9"], wall[2:]]), uv6=np.concatenate([wall_uv[:2], robot["uv6"], wall_uv[2:]]),
+               mat=np.concatenate([np.int32([1, 1]), robot["mat"], np.int32([0, 0])]))
+    out = {
+        "r_cfg1": (robot, dict(tab["cfg1"][0], **hy), mats, {}, None),
+        "r_cfg2": (robot, dict(tab["cfg2"][0], **hy), mats, tex2, None),
+        "r_inside": (robot, dict(tab["cfg2"][0], **hy), mats, tex2, CAM_INSIDE),
+        "r_inside_noclip": (robot, dict(tab["cfg2"][0], enable_clipping=0, **hy), mats, tex2, CAM_INSIDE),
+        "r_mirror": (robot, dict(tab["cfg3_mirror5"][0], **hy), mirror, tab["cfg3_mirror5"][2], None),
+        "r_big": (big, dict(image_width=256, image_height=144, compute_shadows=1, enable_ssaa=1, ssaa_factor=3, enable_diffuse_mapping=1,
+                            enable_normal_mapping=1, **hy), mats, tex2, CAM_INSIDE),
+        "r_ssao": (robot, dict(ssao_table(mats)["ssao_ssaa2"][0], **hy), mats, {}, None),
+        "r_rough": (robot, dict(tab["cfg3"][0], **hy), tab["cfg3"][1], tab["cfg3"][2], None),
+    }
+    for mode in (1, 2, 3, 4):
+        out[f"r_debug{mode}"] = (robot, dict(image_width=200, image_height=120, shading_method=mode, enable_ao_mapping=1, **hy), mats,
+                                 {0: tex2[0]}, CAM_INSIDE if mode > 2 else None)
+    return out
+
+
+RASTER_PINNED = ["r_cfg1", "r_cfg2", "r_inside", "r_inside_noclip", "r_mirror", "r_big", "r_ssao", "r_debug1", "r_debug2", "r_debug3", "r_debug4"]
+RASTER_SRAND = 20261019
+
+
 def ssao_reference_seeds(rand_values):
     """The nine generator seeds of a single-threaded Renderer::post_process_ssao_SIMD run after srand(): the two
     default-constructed generators (renderer.cpp:1252-1253; xorshift.h:10,39) and the private copy of the parallel region
@@ -113,6 +154,8 @@ def add_shapes(renderer, shapes):
 
 def oracle_image(tracer, scene, kw, mats, tex, **k):
     r = oracle_renderer(tracer, scene, kw, mats, tex, **k)
+    if kw.get("hybrid_rasterization_tracing"):
+        return r.raster()[0]                   # raster_trace() + post_process() in sequential triangle order
     if tracer.kind == "oracle":
         return r.render()[0]
     sup, _ = r.trace_rows()            # compiled reference: seeded pixel loop, then its own downscale
@@ -143,7 +186,10 @@ def product_renderer(lib, scene, kw, mats, tex, fov=FOV, light=LIGHT, cam=None, 
 
 def product_image(lib, scene, kw, mats, tex, **k):
     r = product_renderer(lib, scene, kw, mats, tex, **k)
-    r.ray_trace()
+    if kw.get("hybrid_rasterization_tracing"):
+        r.raster_trace()                       # what RenderThread::run calls for this setting (QT/mainWindowThreads.cpp:46-49)
+    else:
+        r.ray_trace()
     r.post_process()
     img, stats = r.get_image(), r.last_stats()
     r.close()

@@ -91,6 +91,11 @@ def golden_ssao():
 
 
 @pytest.fixture(scope="session")
+def golden_raster():
+    return dict(np.load(GOLDEN / "golden_raster.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_rays():
     return dict(np.load(GOLDEN / "golden_rays.npz"))
 

@@ -16,6 +16,7 @@
 #include <unistd.h>
 
 #include "../../raytracercpp_b200/csrc/rt_device.h"
+#include "../../raytracercpp_b200/csrc/raster_device.h"
 #include "../../raytracercpp_b200/csrc/host_common.h"
 #include "../../raytracercpp_b200/csrc/scene_layout.h"
 
@@ -41,6 +42,8 @@ struct RtContext {
     HostTexture tex[RT_TEX_COUNT];
     M4 proj_inv{}, cam_to_world{};
     V3 cam_pos{0, 0, 0}, light{3, 3, 2};
+    M4 proj{};
+    bool proj_set = false;
     int leaf_split = 8;
     std::vector<HostShape> shapes;
 };
@@ -129,7 +132,7 @@ const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""
 int rt_set_option(RtContext* c, int option, int64_t value)
 {
     if (option == RT_OPT_LEAF_SPLIT) { c->leaf_split = (int)value; c->bvh_valid = false; return RT_OK; }
-    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_LANES || option == RT_OPT_ITEM_ROUNDS || option == RT_OPT_PRIMARY_ROUNDS || option == RT_OPT_FUSED_ITEMS || option == RT_OPT_TOP_TABLE || option == RT_OPT_SHADOW_SORT || option == RT_OPT_DEVICE_BUILD || option == RT_OPT_ITEM_PASSES) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
+    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_LANES || option == RT_OPT_ITEM_ROUNDS || option == RT_OPT_PRIMARY_ROUNDS || option == RT_OPT_FUSED_ITEMS || option == RT_OPT_TOP_TABLE || option == RT_OPT_SHADOW_SORT || option == RT_OPT_DEVICE_BUILD || option == RT_OPT_ITEM_PASSES || option == RT_OPT_RASTER_UNITS) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
 }
 
 int rt_set_stream(RtContext*, void*) { return RT_OK; }
@@ -241,7 +244,12 @@ int rt_set_camera(RtContext* c, const float proj_inv[16], const float cam_to_wor
     return RT_OK;
 }
 int rt_set_light(RtContext* c, const float p[3]) { c->light = v3(p[0], p[1], p[2]); return RT_OK; }
-int rt_set_projection(RtContext*, float, float, float, float) { return RT_OK; }     // SSAO is not emulated here (ssao.cuh is CUDA only)
+int rt_set_projection(RtContext* c, float fov, float aspect, float znear, float zfar)      // SSAO is not emulated here (ssao.cuh is CUDA only)
+{
+    c->proj = perspective_matrix(fov, aspect, znear, zfar);                                // raster_trace reads Camera::_perspective_proj_mat
+    c->proj_set = true;
+    return RT_OK;
+}
 
 int rt_tile_count(const RtSettings* s, int tile_size, int tile_mod, int tile_rem)
 {
@@ -283,11 +291,68 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
     RtRenderStats rs;
     memset(&rs, 0, sizeof(rs));
 
+
+    if (s->hybrid_rasterization_tracing) {
+        // Renderer::raster_trace (raster_device.h): the three passes of the CUDA path (cover, emit, shade), sequentially
+        if (tile_mod != 1) return fail(c, RT_ERR_UNSUPPORTED, "hybrid_rasterization_tracing renders the whole frame on one device");
+        if (!c->proj_set) return fail(c, RT_ERR_STATE, "hybrid_rasterization_tracing: the projection has not been set (rt_set_projection)");
+        RasterView rv;
+        rv.world_to_cam = invert_matrix(c->cam_to_world);
+        rv.proj = c->proj;
+        rv.clipping = s->enable_clipping;
+        const size_t npx = (size_t)fr.rw * fr.rh;
+        std::vector<unsigned long long> keys(npx, RT_RASTER_EMPTY);
+        std::vector<float> fx(npx), fy(npx);
+        const float sx = raster_scale(fr.rw), sy = raster_scale(fr.rh);
+        for (int pass = 0; pass < 2; pass++)
+            for (uint32_t tri = 0; tri < sc.n_tris; tri++) {
+                const RasterSource src = raster_source(sc, tri);
+                Tri4 scratch[RT_CLIP_MAX], clipped[RT_CLIP_MAX];
+                const int np = raster_clip(rv, src.a, src.b, src.c, src.tu, src.tv, scratch, clipped);
+                for (int pi = 0; pi < np; pi++) {
+                    const RasterPiece pc = raster_piece(fr, clipped[pi]);
+                    float image_y = raster_start(pc.min_y, sy);
+                    for (int py = pc.min_y; py <= pc.max_y; py++, image_y += sy) {
+                        float image_x = raster_start(pc.min_x, sx);
+                        for (int px = pc.min_x; px <= pc.max_x; px++, image_x += sx) {
+                            float ppx, ppy, u, v, w, z;
+                            if (!raster_fragment(pc, image_x, image_y, sx, sy, ppx, ppy, u, v, w, z)) continue;
+                            unsigned long long key;
+                            if (!raster_key(z, (uint32_t)src.orig * 16u + (uint32_t)pi, key)) continue;
+                            const size_t pix = (size_t)py * fr.rw + px;
+                            if (pass == 0) keys[pix] = std::min(keys[pix], key);
+                            else if (keys[pix] == key) { fx[pix] = ppx; fy[pix] = ppy; }
+                        }
+                    }
+                }
+            }
+        std::vector<int32_t> leaf_of(sc.n_tris);
+        for (uint32_t i = 0; i < sc.n_tris; i++) leaf_of[(size_t)sc.orig[i]] = (int32_t)i;
+        const uint32_t background = quantise_argb(col(135.0f / 255.0f, 206.0f / 255.0f, 235.0f / 255.0f));   // clear_image, renderer.cpp:175-180
+        F4 frag_slot[2];
+        SceneView scf = sc;
+        scf.frag_shade = frag_slot;
+        uint64_t sv2 = 0, st2 = 0;
+        for (size_t pix = 0; pix < npx; pix++) {
+            if (keys[pix] == RT_RASTER_EMPTY) { super[pix] = background; continue; }
+            const uint32_t order = (uint32_t)(keys[pix] & 0xffffffffull);
+            TraceCounters tc = zero_counters();
+            const RasterShadeOut o = raster_shade<true>(scf, fr, rv, (uint32_t)leaf_of[order >> 4], (int)(order & 15u), (uint32_t)pix, fx[pix], fy[pix], frag_slot, 0u, &tc);
+            if (tc.stack_overflow) return fail(c, RT_ERR_STATE, "traversal stack overflow");
+            super[pix] = quantise_argb(o.colour);
+            rs.primary_rays += o.shaded; rs.primary_hits += o.hit; rs.shadow_rays += o.shadow_ray;
+            rs.reflection_rays += tc.refl_rays; rs.reflection_shadow_rays += tc.refl_shadow_rays;
+            sv2 += tc.vol_tests; st2 += tc.tri_tests;
+        }
+        rs.shadow_volume_tests = sv2; rs.shadow_triangle_tests = st2;
+    }
+    const bool raster = s->hybrid_rasterization_tracing != 0;
+    const std::vector<uint32_t> no_tiles;
     // k_primary
     struct QEntry { uint32_t pix; HitRec hr; };
     std::vector<QEntry> queue;
     std::vector<uint32_t> refl_idx;
-    for (uint32_t tile : tiles) {
+    for (uint32_t tile : (raster ? no_tiles : tiles)) {
         int tx = (int)(tile % (uint32_t)tiles_x), ty = (int)(tile / (uint32_t)tiles_x);
         for (int ly = 0; ly < tile_px; ly++)
             for (int lx = 0; lx < tile_px; lx++) {
@@ -318,7 +383,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
                 queue.push_back(QEntry{(uint32_t)py * (uint32_t)fr.rw + (uint32_t)px, hr});
             }
     }
-    rs.primary_hits = queue.size();
+    if (!raster) rs.primary_hits = queue.size();
     // k_reflect
     std::vector<Col> refl_rgb(queue.size(), col(0.0f));
     uint64_t refl_rays = 0, refl_shadow = 0, rv = 0, rtt = 0, sv = 0, stt = 0;
@@ -340,8 +405,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
         rv += tc.vol_tests; rtt += tc.tri_tests;
     }
     rs.reflection_volume_tests = rv; rs.reflection_triangle_tests = rtt;
-    rs.reflection_rays = refl_rays;
-    rs.reflection_shadow_rays = refl_shadow;
+    if (!raster) { rs.reflection_rays = refl_rays; rs.reflection_shadow_rays = refl_shadow; }
     // k_shade
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : sv, stt)
     for (long long i = 0; i < (long long)queue.size(); i++) {
@@ -364,8 +428,10 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
         }
         super[e.pix] = quantise_argb(cc);
     }
-    rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
-    rs.shadow_volume_tests = sv; rs.shadow_triangle_tests = stt;
+    if (!raster) {
+        rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
+        rs.shadow_volume_tests = sv; rs.shadow_triangle_tests = stt;
+    }
     // k_resolve
     if (fr.factor > 1) {
         const int ff = fr.factor * fr.factor;

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_sizes(lib):
     assert ctypes.sizeof(api.RtMaterial) == 64
-    assert ctypes.sizeof(api.RtSettings) == 30 * 4
+    assert ctypes.sizeof(api.RtSettings) == 31 * 4
 
 
 def test_defaults_mirror_render_settings(lib):
@@ -46,6 +46,7 @@ def test_defaults_mirror_render_settings(lib):
     assert abs(s.displacement_mapping_strength - 0.02) < 1e-9 and s.parallax_mapping_steps == 32      # rendererSettings.h:94-95
     assert (s.ssao_sample_count, s.ssao_radius, s.ssao_amount) == (64, 0.5, 1.0) and not s.enable_ssao    # rendererSettings.h:66-73
     assert s.enable_ambient and s.enable_diffuse and s.enable_specular and s.enable_emissive
+    assert s.enable_clipping and not s.hybrid_rasterization_tracing                                     # rendererSettings.h:40,46
     assert not (s.enable_ssaa or s.compute_shadows or s.enable_skysphere or s.enable_ao_mapping)
 
 

@@ -166,12 +166,6 @@ def test_primary_rays_resolve_and_call_order(cuda_lib, golden_images, robot):
         r.ray_trace()                                          # RT_SHADING without materials
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("hybrid_rasterization_tracing",):
-        setattr(st, field, 1)
-        with pytest.raises(api.RtError) as e:
-            r.ray_trace()
-        assert e.value.code == api.RT_ERR_UNSUPPORTED
-        setattr(st, field, 0)
     r.close()
 
 
@@ -808,3 +802,77 @@ def test_leaf_refinement_never_changes_a_result(cuda_lib, oracle, robot, golden_
     r.ray_trace()
     common.assert_image_close(r.get_image(), common.oracle_image(oracle, robot, dict(kw, image_width=96, image_height=54), mats, tex), what="split")
     r.close()
+
+
+# ---- hybrid path: Renderer::raster_trace (renderer.cpp:869-1006), SURVEY.md section 8(f)4 -------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["r_cfg1", "r_cfg2", "r_inside", "r_inside_noclip", "r_mirror", "r_big", "r_ssao", "r_rough",
+                                  "r_debug1", "r_debug2", "r_debug3", "r_debug4"])
+def test_raster_trace_vs_oracle(cuda_lib, oracle, robot, golden_raster, name):
+    """hybrid_rasterization_tracing on the GPU (csrc/raster.cuh: depth pass with 64-bit z-keys, emit pass, shade pass) through
+    the C ABI, against the oracle's restatement and against the frames of the compiled reference run on one thread.
+    Coverage, depth order and the shaded hit are integer / bit-exact work: every pixel must have the oracle's WINNER; only
+    powf of the specular term can move a channel by one unit."""
+    scene, kw, mats, tex, cam = common.raster_table(robot)[name]
+    img, st = common.product_image(cuda_lib, scene, kw, mats, tex, cam=cam)
+    want = common.oracle_image(oracle, scene, kw, mats, tex, cam=cam)
+    common.assert_image_close(img, want, what=name)
+    assert (img == want).mean() >= 0.999
+    if name in common.RASTER_PINNED:
+        ref = golden_raster[name + ("_per_pixel" if kw.get("enable_ssao") else "_reference")]
+        common.assert_image_close(img, ref, what=name + " vs the compiled reference")
+        assert (img == ref).mean() >= 0.999
+    if kw.get("shading_method", 0) == 0:
+        assert st.primary_rays > 0 and st.shadow_rays == st.primary_hits and st.kernel_launches >= 3
+    if kw.get("shading_method", 0) in (1, 2, 3):
+        assert np.array_equal(img, want)                   # no libm call on these paths: bit-exact
+
+
+@pytest.mark.gpu
+def test_raster_trace_schedule_independent(cuda_lib, oracle, robot):
+    """The frame does not depend on how the pieces are scheduled: a unit list that is too short at first (the depth pass is
+    repeated with a longer one), the host-built tree (another leaf order), a second frame from the same context; and
+    ray_trace() after raster_trace() is the ray-traced frame again."""
+    scene, kw, mats, tex, cam = common.raster_table(robot)["r_big"]
+    base, _ = common.product_image(cuda_lib, scene, kw, mats, tex, cam=cam)
+    r = common.product_renderer(cuda_lib, scene, kw, mats, tex, cam=cam)
+    r.ctx.set_option(api.RT_OPT_RASTER_UNITS, 3)
+    r.raster_trace()
+    assert np.array_equal(r.get_image(), base)
+    r.raster_trace()
+    assert np.array_equal(r.get_image(), base)
+    r.ctx.set_option(api.RT_OPT_DEVICE_BUILD, 0)
+    r.reconstruct_bvh_new()
+    r.raster_trace()
+    assert np.array_equal(r.get_image(), base)
+    r.ray_trace()
+    traced = r.get_image().copy()
+    r.close()
+    plain, _ = common.product_image(cuda_lib, scene, dict(kw, hybrid_rasterization_tracing=0), mats, tex, cam=cam)
+    assert np.array_equal(traced, plain)
+    # the rasterised and the ray-traced frame show the same scene: they differ at silhouettes and where the two
+    # paths' hit points differ by rounding, not wholesale
+    assert (traced == base).mean() > 0.8
+    # a tile shard cannot own a z-buffer of its own
+    import torch
+    frame = torch.zeros((kw["image_height"], kw["image_width"]), dtype=torch.int32, device="cuda")
+    r2 = common.product_renderer(cuda_lib, scene, kw, mats, tex, cam=cam)
+    with pytest.raises(api.RtError) as e:
+        r2.ctx.render_device(r2.render_settings(), frame.data_ptr(), 32, 2, 0)
+    assert e.value.code == api.RT_ERR_UNSUPPORTED
+    r2.close()
+
+
+@pytest.mark.gpu
+def test_raster_trace_full_size(cuda_lib, oracle, robot):
+    """BASELINE configs[0] and [1] at their sizes through the hybrid path: cfg1 1280x720, cfg2 1280x720 x ssaa 2 with the
+    2048^2 u8 maps, against the oracle live."""
+    table = common.fullsize_table(robot["materials"])
+    for name in ("cfg1_full", "cfg2_full"):
+        kw, mats, tex = table[name]
+        kw = dict(kw, hybrid_rasterization_tracing=1)
+        img, st = common.product_image(cuda_lib, robot, kw, mats, tex)
+        want = common.oracle_image(oracle, robot, kw, mats, tex)
+        common.assert_image_close(img, want, what=name + " raster")
+        assert (img == want).mean() >= 0.999
+        assert st.primary_hits > 100_000

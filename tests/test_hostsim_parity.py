@@ -80,7 +80,7 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
         r.ray_trace()                                     # RT_SHADING without materials (reference: assert, materials.h:117)
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao", "hybrid_rasterization_tracing"):
+    for field in ("enable_ssao",):
         setattr(s, field, 1)
         with pytest.raises(api.RtError) as e:
             r.ray_trace()
@@ -354,3 +354,18 @@ def test_batched_is_shadowed_sees_the_shapes(hostsim_lib, robot):
     ctx.clear_analytic_shapes()
     assert np.array_equal(ctx.occluded(p, n), before)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["r_cfg1", "r_cfg2", "r_inside", "r_inside_noclip", "r_mirror", "r_big", "r_rough", "r_debug1", "r_debug2", "r_debug3", "r_debug4"])
+def test_raster_trace_vs_oracle(hostsim_lib, oracle, robot, golden_raster, name):
+    """The device source of the hybrid path (csrc/raster_device.h: clipping, piece set-up, fragment test, z-keys, shading of
+    the winning piece) compiled for the host, through the C ABI (RtSettings::hybrid_rasterization_tracing) -- bit-exact
+    against the oracle and against the frames of the compiled reference."""
+    scene, kw, mats, tex, cam = common.raster_table(robot)[name]
+    img, st = common.product_image(hostsim_lib, scene, kw, mats, tex, cam=cam)
+    want = common.oracle_image(oracle, scene, kw, mats, tex, cam=cam)
+    assert np.array_equal(img, want)
+    if name in common.RASTER_PINNED:
+        assert np.array_equal(img, golden_raster[name + "_reference"])
+    if kw.get("shading_method", 0) == 0:
+        assert st.primary_rays > 0 and st.shadow_rays == st.primary_hits

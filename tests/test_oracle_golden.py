@@ -92,3 +92,19 @@ def test_ssao_matches_reference(oracle, robot, golden_ssao, name):
     assert np.array_equal(got, golden_ssao[name + "_reference"])
     per_pixel, _ = orc.render_ssao()
     assert np.array_equal(per_pixel, golden_ssao[name + "_per_pixel"])
+
+
+@pytest.mark.parametrize("name", common.RASTER_PINNED)
+def test_raster_trace_matches_reference(oracle, robot, golden_raster, name):
+    """Renderer::raster_trace + post_process (hybrid_rasterization_tracing, renderer.cpp:869-1006): frames cut from the
+    compiled reference run on one thread (tests/golden/make_golden_raster.py) -- clipping on and off, the camera inside the
+    scene (every clip plane cuts), frame-filling triangles, textures + SSAA, mirror reflections, the four debug modes,
+    SSAO on the rasterizer's z-buffer.  Bit-exact."""
+    scene, kw, mats, tex, cam = common.raster_table(robot)[name]
+    r = common.oracle_renderer(oracle, scene, kw, mats, tex, cam=cam)
+    img, counters = r.raster(ref_seeds9=golden_raster[name + "_seeds9"] if kw.get("enable_ssao") else None)
+    assert np.array_equal(img, golden_raster[name + "_reference"])
+    if kw.get("enable_ssao"):
+        assert np.array_equal(r.raster()[0], golden_raster[name + "_per_pixel"])
+    if kw.get("shading_method", 0) == 0:
+        assert counters["fragments"] > 0 and counters["shadow_rays"] == counters["fragment_hits"]

@@ -57,3 +57,14 @@ def test_ssao_reference_order(oracle, ref_strict, robot, name, seed):
     per_pixel, _ = orc.render_ssao()
     diff = np.abs(common.channels(per_pixel).astype(int) - common.channels(want).astype(int))
     assert diff.mean() < 0.5 and (per_pixel != plain).mean() > 0.05
+
+
+@pytest.mark.parametrize("name", ["r_inside", "r_big", "r_ssao"])
+def test_raster_trace_live(oracle, ref_strict, robot, name):
+    """The oracle's restatement of Renderer::raster_trace (clipping, rasterisation, z-buffer, trace_triangle) against the
+    compiled reference run here on one thread: bit-exact, also with SSAO on the rasterizer's G-buffers."""
+    scene, kw, mats, tex, cam = common.raster_table(robot)[name]
+    ref_img, rand_values = common.oracle_renderer(ref_strict, scene, kw, mats, tex, cam=cam).raster(srand_seed=7)
+    seeds = common.ssao_reference_seeds(rand_values) if kw.get("enable_ssao") else None
+    img, _ = common.oracle_renderer(oracle, scene, kw, mats, tex, cam=cam).raster(ref_seeds9=seeds)
+    assert np.array_equal(img, ref_img)
