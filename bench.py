@@ -272,7 +272,7 @@ def run_ours(args, scene):
     import torch
     import torch.distributed as dist
     from raytracercpp_b200 import api
-    from raytracercpp_b200.distributed import ShardedFrame
+    from raytracercpp_b200.distributed import FramePipeline, ShardedFrame
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -292,6 +292,7 @@ def run_ours(args, scene):
     s = api.default_settings(lib, **kw)
     ctx.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
     lanes_on = not any(kv.split("=")[0] == str(api.RT_OPT_LANES) and int(kv.split("=")[1]) == 0 for kv in args.opt)
+    graph_on = not any(kv.split("=")[0] == str(api.RT_OPT_GRAPH) and int(kv.split("=")[1]) == 0 for kv in args.opt)
     ref_work = None
     if not args.no_ref_work:
         # Work of the REFERENCE-SHAPED traversal: the reference's own cells and leaves
@@ -318,6 +319,20 @@ def run_ours(args, scene):
     if rank == 0 and world > 1:
         log(f"[ours] frame gather mode: {frame.mode}" + (f" (peer refused: {frame.why_not_peer})" if frame.why_not_peer else ""))
 
+    # More frames in flight (--frames-in-flight F, default 2): F - 1 further contexts with the same scene, each on its own
+    # stream with its own frame buffers; the timed loop enqueues frame k+1 before it waits for frame k (FramePipeline).
+    in_flight = max(1, args.frames_in_flight)
+    frames, streams, ctxs = [frame], [stream], [ctx]
+    for _ in range(1, in_flight):
+        c2 = api.Context(local, lib)
+        c2.set_triangles(scene["xyz9"], scene["uv6"], scene["mat"])
+        setup_context(c2, api, scene, args, leaf_split=args.leaf_split if args.leaf_split is not None else 8)
+        st2 = torch.cuda.Stream()
+        c2.set_stream(st2.cuda_stream)
+        ctxs.append(c2); streams.append(st2)
+        frames.append(ShardedFrame(c2, s, rank, world, tile_size=args.tile, gather=args.gather))
+    pipe = FramePipeline(frames, streams)
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -331,8 +346,9 @@ def run_ours(args, scene):
     ctx.set_option(api.RT_OPT_COUNT_WORK, 0)
 
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            frame.render_and_gather()
+        for _ in range(max(args.warmup, 2 * in_flight)):                          # every context warms up (and captures its frame graphs)
+            pipe.submit()
+        pipe.drain()
         sync_all()
         sampler = ClockSampler(local)
         sampler.start()
@@ -340,18 +356,32 @@ def run_ours(args, scene):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
         st = None
+        # the timed region starts on every stream at ev0 and ends when the last stream is done: K frames, F in flight
         ev0.record(stream)
+        for other in streams[1:]:
+            other.wait_event(ev0)
+        done = []
         for _ in range(args.steps):
-            st = frame.render_and_gather()
-            launches += st.kernel_launches + (2 if frame.mode == "nccl" else 0)   # + the pack and unpack kernels of the nccl-mode gather
+            r = pipe.submit()
+            if r is not None:
+                done.append(r)
+        done += pipe.drain()
+        for other in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(other)
+            stream.wait_event(e)
         ev1.record(stream)
         sync_all()
+        assert len(done) == args.steps
+        st = done[-1]
+        launches = sum(d.kernel_launches + (2 if frame.mode == "nccl" else 0) for d in done)   # + the pack and unpack kernels of the nccl-mode gather
         dev_ms = ev0.elapsed_time(ev1)
         rays_rank, traced_rank = st.total_rays, st.traced_rays
         # Per-kernel durations for the roofline: the SAME K frames once more, still inside the clock sampling, with the two
         # chunk lanes turned off (RT_OPT_LANES 0) -- with two lanes the kernels of the two chunks overlap on purpose and a
         # CUDA-event pair around one of them also measures the time it waits for SMs.
         ctx.set_option(api.RT_OPT_LANES, 0)
+        ctx.set_option(api.RT_OPT_GRAPH, 0)                                       # a replayed frame graph has no per-stage events
         serial0, serial1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         frame.render_and_gather()
         serial0.record(stream)
@@ -363,6 +393,7 @@ def run_ours(args, scene):
         sync_all()
         serial_ms = serial0.elapsed_time(serial1) / args.steps
         ctx.set_option(api.RT_OPT_LANES, 1 if lanes_on else 0)
+        ctx.set_option(api.RT_OPT_GRAPH, 1 if graph_on else 0)
         clocks = sampler.stop()
 
         # --- end to end through the public call: the frame ends up in an ordinary (pageable) host array of the caller.
@@ -372,21 +403,27 @@ def run_ours(args, scene):
         host = np.empty((kw["image_height"], kw["image_width"]), np.uint32)
         host.fill(0)                                                             # touch the pages once, as a GUI's frame buffer would be
 
+        e2e_device_ms = []
+
         def e2e_step():
             ctx.set_camera(proj_inv, cam, pos)
             if world == 1:
-                ctx.render(s, host)
+                e2e_device_ms.append(ctx.render(s, host)[1].device_ms)
             else:
                 frame.render_to_host(host)
 
         for _ in range(min(args.warmup, 3)):
             e2e_step()
         sync_all()
+        e2e_steps_ms = []
         t_e2e = time.perf_counter()
         for _ in range(args.steps):
+            t_step = time.perf_counter()
             e2e_step()
+            e2e_steps_ms.append((time.perf_counter() - t_step) * 1e3)
         stream.synchronize()
         e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+        log("[ours] e2e steps (ms): " + " ".join(f"{x:.2f}" for x in e2e_steps_ms) + " | device part: " + " ".join(f"{x:.2f}" for x in e2e_device_ms[-args.steps:]))
 
     # --- the frame of the sharded run must be the 1-GPU frame, on the device and in the caller's host array
     # (rank 0 renders every tile once more, untimed)
@@ -476,6 +513,8 @@ def run_ours(args, scene):
                     "stage_timing": "K more frames with RT_OPT_LANES 0 (the chunks' kernels back to back on one stream; with the two lanes of "
                                     "the timed run they overlap on purpose), %.3f ms per frame that way" % serial_ms}
         cfg = workload_config(scene, world, args.tile)
+        cfg["frames_in_flight"] = (f"{in_flight}: frame k+1 is enqueued (own context, stream and frame buffers) before the host waits for frame k; "
+                                   "`ms_per_step` = time of the K frames / K" if in_flight > 1 else "1: each frame is waited for before the next is enqueued")
         cfg["gather"] = {"peer": "every rank's resolve kernel stores its tiles into rank 0's frame over NVLink (CUDA IPC), one 4-byte all-reduce per frame as the barrier",
                          "nccl": "pack kernel -> all_gather_into_tensor -> unpack kernel", "single": "none (one GPU)"}[frame.mode]
         out = {
@@ -508,7 +547,8 @@ def run_ours(args, scene):
             except Exception as e:  # the checker is optional for the GPU number, never the other way round
                 out["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         emit(out)
-    frame.close()
+    for f in frames:
+        f.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -521,6 +561,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4_sphere10M_4k_16spp", choices=list(WORKLOADS))
+    ap.add_argument("--frames-in-flight", type=int, default=2,
+                    help="frames enqueued before the host waits for the oldest (each on its own context and stream); 1 = one frame at a time")
     ap.add_argument("--cpu-row-step", type=int, default=6, help="cpu_baseline sample: every n-th supersampled row")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-work", action="store_true", help="skip the reference-shaped work count (roofline then uses the kernel's own tests)")

@@ -223,6 +223,10 @@ enum {
                                  chunk's kernels fill the SMs the others leave idle while their longest packets finish; the
                                  per-stage times of RtRenderStats then overlap.  0: one chunk at a time; 1 (default): 2 chunks;
                                  n in [2,6]: n chunks.  Results do not depend on it                                     */
+    RT_OPT_GRAPH = 18,        /* 1 (default): a frame whose launch sequence equals the previous frame's (same settings, camera, light,
+                                 buffers, options) is captured as a CUDA graph and replayed with one cudaGraphLaunch from then on;
+                                 the per-stage times of RtRenderStats are 0 for such frames.  0: every frame is enqueued launch by
+                                 launch.  Results do not depend on it                                                       */
     RT_OPT_RASTER_UNITS = 17, /* hybrid raster path: first size of the list of work units (row bands of the pieces too large for one
                                  thread); a frame that needs more grows the list and repeats its depth pass.  Default 2^18       */
     RT_OPT_LEAF_SPLIT = 2     /* n > 0 (default 8): when flattening, octree leaves with more than n triangles get a

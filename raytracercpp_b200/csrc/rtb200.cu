@@ -33,6 +33,7 @@ constexpr uint64_t kChunkPixels = 1ull << 28;     // supersampled pixels per wav
 constexpr int kMaxChunks = 256;
 
 thread_local std::string g_create_error;
+unsigned long long g_alloc_generation = 0;        // bumped whenever a device buffer moves: invalidates the captured frame graphs
 
 double now_ms()
 {
@@ -51,6 +52,7 @@ struct DevBuf {
         n = 0;
         cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
         if (e == cudaSuccess) n = count;
+        g_alloc_generation++;
         return e;
     }
     void release()
@@ -58,6 +60,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
+        g_alloc_generation++;
     }
 };
 
@@ -216,6 +219,13 @@ struct RtContext {
     DevBuf<unsigned int> d_rcount;
     DevBuf<float4> d_rfrag;
     size_t raster_smem_set = 0;
+    // The frame as a CUDA graph (RT_OPT_GRAPH): when a frame's launch sequence is byte for byte the one of the frame before
+    // (same settings, camera, light, buffers, options), it is captured once and replayed with one cudaGraphLaunch.
+    bool opt_graph = true;
+    bool capturing = false;              // stage timers are off while the launches are being captured
+    struct FrameGraph { std::string key; cudaGraphExec_t exec; uint32_t launches; };
+    std::vector<FrameGraph> graphs;      // the last few captured frames (a sharded frame alternates between two output buffers)
+    std::vector<std::string> seen_keys;  // serialised launch parameters of the last few frames that were enqueued the ordinary way
     size_t raster_units0 = (size_t)1 << 18;   // first size of the unit list (RT_OPT_RASTER_UNITS); grown when a frame needs more
     M4 proj{};
     float proj_fov = 45.0f, proj_aspect = 1.0f;
@@ -272,7 +282,7 @@ struct ScopedTimer {
     ScopedTimer(RtContext* c, int stage, cudaStream_t st = nullptr, const char* label = nullptr) : ctx(c), stream(st ? st : c->stream)
     {
         static const bool trace = getenv("RTB200_TRACE") != nullptr;
-        on = label == nullptr || trace;
+        on = (label == nullptr || trace) && !c->capturing;
         if (!on) return;
         tl.stage = stage;
         tl.label = label;
@@ -791,6 +801,7 @@ void rt_destroy(RtContext* ctx)
     ctx->d_recs.release(); ctx->d_top.release(); ctx->d_tris.release(); ctx->d_shade.release(); ctx->d_mats.release(); ctx->d_orig.release(); ctx->d_leaf_of.release(); ctx->d_shapes.release();
     for (auto& t : ctx->tex) if (t.d) cudaFree(t.d);
     ctx->d_super.release(); ctx->d_frame.release(); ctx->db.release(); ctx->d_gz.release(); ctx->d_gn.release(); ctx->d_ao.release();
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     ctx->d_rkeys.release(); ctx->d_rxy.release(); ctx->d_runits.release(); ctx->d_rcount.release(); ctx->d_rfrag.release();
     for (auto& kv : ctx->tile_lists) { cudaFree(kv.second.d); cudaFree(kv.second.d_split); }
     for (auto& qs : ctx->qs) qs.release();
@@ -859,6 +870,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         if (value < 0 || value > kMaxLanes) return fail(ctx, RT_ERR_INVALID, "lanes %lld outside [0,%d]", (long long)value, kMaxLanes);
         ctx->opt_lanes = value == 1 ? kLanes : (int)std::max<int64_t>(value, 1);   // 0: one chunk at a time; 1: the default (2); n: n chunks in flight
         return RT_OK;
+    case RT_OPT_GRAPH: ctx->opt_graph = value != 0; return RT_OK;
     case RT_OPT_RASTER_UNITS:
         if (value < 1 || value > (1ll << 28)) return fail(ctx, RT_ERR_INVALID, "raster unit list of %lld entries outside [1, 2^28]", (long long)value);
         ctx->d_runits.release();
@@ -1210,7 +1222,9 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     // the same tile list was clearly dense, the five launches are not even enqueued (they matter to a short launch).
     const bool sort_hits = ctx->opt_shadow_sort && tune.packets && !tune.fused && !reflect && s->compute_shadows && s->shading_method == RT_SHADING &&
                            !(ctx->opt_shadow_sort == 2 && tl->last_hit_fraction >= 0.3f);
-    const LightMap light_map = sort_hits ? make_light_map(ctx) : LightMap{};
+    LightMap light_map;
+    memset(&light_map, 0, sizeof(light_map));
+    if (sort_hits) light_map = make_light_map(ctx);
     // split records and work items of the packets that run out of rounds; a packet that finds them full is finished in
     // place.  Primary and shadow packets never run at the same time and share the storage.
     const size_t split_cap = (tail || psplit) ? std::min<size_t>(std::max<size_t>(qcap / 32, 1024), (size_t)1 << 20) : 0;
@@ -1248,6 +1262,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     }
     wk.tiles = classify ? tl->d_split : tl->d;
     QueueView qv[kMaxLanes];
+    memset(qv, 0, sizeof(qv));                                                 // padding too: the views are part of the frame-graph key
     for (int l = 0; l < n_lanes; l++) {
         QueueSet& Q = ctx->qs[l];
         QueueView& q = qv[l];
@@ -1272,12 +1287,55 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
     ctx->events_used = 0;
     ctx->timed.clear();
     uint32_t launches = 0;
+    const bool count = ctx->opt_count_work;
+    Pending& pd = ctx->pending;
+    const size_t n_cnt = std::max<uint32_t>(n_chunks, 1);
+    if (n_cnt > pd.host_cap) {
+        if (pd.host_cnt) cudaFreeHost(pd.host_cnt);
+        pd.host_cnt = nullptr; pd.host_cap = 0;
+        RT_CUDA(ctx, cudaHostAlloc((void**)&pd.host_cnt, n_cnt * sizeof(ChunkCounters), cudaHostAllocDefault));
+        pd.host_cap = n_cnt;
+    }
+
+    // ---- the frame as a graph.  Everything the launches below depend on is serialised into a key; a frame whose key
+    // equals the previous frame's is captured (stream capture, the lanes' streams join through their fork / join events),
+    // and from then on frames with that key are ONE cudaGraphLaunch: a tile shard's 40 short dependent launches otherwise
+    // cost more host and launch latency than their kernels run (a 1/8 shard of the 4K frame: 2.2 ms, 0.5 ms of it the chain).
+    static const bool trace_env = getenv("RTB200_TRACE") != nullptr;
+    const bool graph_ok = ctx->opt_graph && !raster && !(tune.fused && tune.packets) && !trace_env;
+    bool replay = false, capture = false;
+    size_t graph_at = 0;
+    std::string key;
+    if (graph_ok) {
+        auto put = [&](const void* ptr, size_t n) { key.append((const char*)ptr, n); };
+        auto put64 = [&](unsigned long long v) { put(&v, sizeof(v)); };
+        put(&sc, sizeof(sc)); put(&fr, sizeof(fr)); put(&wk, sizeof(wk)); put(qv, sizeof(QueueView) * (size_t)n_lanes); put(&tune, sizeof(tune));
+        put(&light_map, sizeof(light_map));
+        if (!bounds.empty()) put(bounds.data(), bounds.size() * sizeof(uint32_t));
+        put64((unsigned long long)tile_size); put64((unsigned long long)tile_mod); put64((unsigned long long)tile_rem); put64((unsigned long long)n_lanes);
+        put64(n_chunks); put64(classify); put64(n_traced); put64(tl->count); put64((unsigned long long)(uintptr_t)tl->d); put64((unsigned long long)(uintptr_t)tl->d_split);
+        put64(sort_hits); put64((unsigned long long)ctx->opt_shadow_sort); put64(tail); put64(psplit); put64(reflect); put64(ssao); put64(resolve); put64(count); put64(has_shapes);
+        put64(ctx->opt_top_table); put64((unsigned long long)(uintptr_t)d_argb_out); put64((unsigned long long)(uintptr_t)super);
+        put64((unsigned long long)(uintptr_t)ctx->d_counters.p); put64((unsigned long long)(uintptr_t)pd.host_cnt); put64(g_alloc_generation);
+        put64((unsigned long long)(uintptr_t)main_stream); put64((unsigned long long)split_cap); put64((unsigned long long)item_cap); put64(px_per_tile);
+        put64((unsigned long long)ctx->stack_limit_set);
+        if (ssao) { put(&ctx->proj, sizeof(ctx->proj)); put(&ctx->proj_fov, sizeof(float)); put(&ctx->proj_aspect, sizeof(float)); }
+        for (size_t i = 0; i < ctx->graphs.size() && !replay; i++)
+            if (ctx->graphs[i].key == key) { replay = true; graph_at = i; }
+        if (!replay) {
+            for (const std::string& k : ctx->seen_keys) capture |= (k == key);
+            if (!capture) {
+                if (ctx->seen_keys.size() >= 4) ctx->seen_keys.erase(ctx->seen_keys.begin());
+                ctx->seen_keys.push_back(key);
+            }
+        }
+    }
     cudaEvent_t ev_begin = next_event(ctx), ev_end = next_event(ctx);
     RT_CUDA(ctx, cudaEventRecord(ev_begin, st));
+    auto enqueue = [&]() -> int {
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(ChunkCounters) * std::max<uint32_t>(n_chunks, 1), st));
     if (ssao) { k_gbuffer_clear<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->d_gz.p, ctx->d_gn.p, (size_t)fr.rw * fr.rh); launches++; }
 
-    const bool count = ctx->opt_count_work;
     int (&grids)[2][11] = ctx->grids;                                           // per context: its device's occupancy
     if (!grids[count][0]) {
         grids[count][3] = grid_for(ctx, count ? (const void*)k_primary_packet<true, true> : (const void*)k_primary_packet<false, true>, kPrimaryThreads);
@@ -1500,19 +1558,46 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
                                                      (classify && const_fill) ? n_traced : tl->count, background);
         launches++;
     }
+    // the counters come back in the same stream order and are read by rt_render_device_end
+    RT_CUDA(ctx, cudaMemcpyAsync(pd.host_cnt, ctx->d_counters.p, sizeof(ChunkCounters) * n_cnt, cudaMemcpyDeviceToHost, st));
+    return RT_OK;
+    };
+    if (replay) {
+        RT_CUDA(ctx, cudaGraphLaunch(ctx->graphs[graph_at].exec, main_stream));
+        launches = ctx->graphs[graph_at].launches;
+    } else if (capture) {
+        if (ctx->graphs.size() >= 4) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+        RT_CUDA(ctx, cudaStreamBeginCapture(main_stream, cudaStreamCaptureModeRelaxed));
+        ctx->capturing = true;
+        const int rc = enqueue();
+        ctx->capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(main_stream, &graph);
+        if (rc != RT_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || !graph) {
+            // the sequence cannot be captured: run this frame and the following ones the ordinary way
+            (void)cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            ctx->opt_graph = false;
+            launches = 0;
+            st = main_stream;
+            if (int r = enqueue()) return r;
+        } else {
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie));
+            RtContext::FrameGraph fg;
+            fg.key = key; fg.exec = exec; fg.launches = launches;
+            ctx->graphs.push_back(fg);
+            RT_CUDA(ctx, cudaGraphLaunch(exec, main_stream));
+        }
+    } else if (int r = enqueue()) return r;
+    st = main_stream;
     RT_CUDA(ctx, cudaEventRecord(ev_end, st));
     RT_CUDA(ctx, cudaGetLastError());
 
-    // everything is enqueued; the counters come back with the same stream order and are read by rt_render_device_end
-    Pending& pd = ctx->pending;
-    const size_t n_cnt = std::max<uint32_t>(n_chunks, 1);
-    if (n_cnt > pd.host_cap) {
-        if (pd.host_cnt) cudaFreeHost(pd.host_cnt);
-        pd.host_cnt = nullptr; pd.host_cap = 0;
-        RT_CUDA(ctx, cudaHostAlloc((void**)&pd.host_cnt, n_cnt * sizeof(ChunkCounters), cudaHostAllocDefault));
-        pd.host_cap = n_cnt;
-    }
-    RT_CUDA(ctx, cudaMemcpyAsync(pd.host_cnt, ctx->d_counters.p, sizeof(ChunkCounters) * n_cnt, cudaMemcpyDeviceToHost, st));
+    // everything is enqueued
     pd.n_chunks = raster ? 1u : n_chunks;
     pd.raster = raster;
     pd.launches = launches;

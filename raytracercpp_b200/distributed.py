@@ -23,6 +23,7 @@ rt_frame_alloc hands out POSIX shared memory).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 
 import numpy as np
@@ -157,3 +158,35 @@ class ShardedFrame:
         # one launch scatters the peers' tiles; pack, collective and unpack are stream-ordered, no host synchronisation
         self.ctx.unpack_gathered(self.s, self.frame.data_ptr(), self.gathered.data_ptr(), self.tile, self.world, self.rank)
         return self.frame
+
+
+class FramePipeline:
+    """Several frames in flight on one GPU: each ShardedFrame has its own context (the scene is resident once per context) on
+    its own stream; frame k+1 is enqueued before the host waits for frame k, so the tail of one frame's launches -- a
+    persistent kernel's last, longest packets, the short item passes of split packets -- runs beside the next frame's first
+    kernels instead of leaving SMs idle.  Throughput of a sequence of frames (an animation, a turntable), not the latency of
+    one; the frames are complete and in order.  `streams` are torch streams, streams[i] the one frames[i].ctx runs on."""
+
+    def __init__(self, frames, streams):
+        assert len(frames) == len(streams) and frames
+        self.frames, self.streams = list(frames), list(streams)
+        self.inflight = []
+        self.next = 0
+
+    def submit(self):
+        """Enqueues the next frame; returns the stats of the frame that had to be waited for to make room (or None)."""
+        done = None
+        if len(self.inflight) == len(self.frames):
+            done = self.frames[self.inflight.pop(0)].end()
+        i = self.next
+        self.next = (self.next + 1) % len(self.frames)
+        with (torch.cuda.stream(self.streams[i]) if self.streams[i] is not None else contextlib.nullcontext()):   # None: CPU tests
+            self.frames[i].begin()
+        self.inflight.append(i)
+        return done
+
+    def drain(self):
+        """Waits for the frames still in flight; returns their stats in order."""
+        out = [self.frames[i].end() for i in self.inflight]
+        self.inflight = []
+        return out

@@ -42,7 +42,7 @@ def main():
     bench.setup_context(ctx, api, scene, A, leaf_split=8)
     frame = torch.zeros((s.image_height, s.image_width), dtype=torch.int32, device="cuda")
     results = []
-    defaults = {api.RT_OPT_LANES: 1, api.RT_OPT_PACKET_ROUNDS: -256, api.RT_OPT_ITEM_ROUNDS: -16, api.RT_OPT_PRIMARY_ROUNDS: -256, api.RT_OPT_ITEM_PASSES: 6}
+    defaults = {api.RT_OPT_LANES: 1, api.RT_OPT_PACKET_ROUNDS: -256, api.RT_OPT_ITEM_ROUNDS: -16, api.RT_OPT_PRIMARY_ROUNDS: -256, api.RT_OPT_ITEM_PASSES: 6, api.RT_OPT_GRAPH: 1}
     for optset in args.sets:
         for k, v in defaults.items():
             ctx.set_option(k, v)

@@ -64,6 +64,23 @@ def _worker(rank, world, port, out_dir):
             assert np.array_equal(peer.frame.numpy().view(np.uint32), full)
         dist.barrier()
     peer.close()
+    # two frames in flight (FramePipeline, as bench.py's timed loop): two contexts, each with its own shared frames; every
+    # frame that comes out is the complete frame
+    from raytracercpp_b200.distributed import FramePipeline
+    r2 = common.product_renderer(lib, robot, kw, m, tex)
+    fa = ShardedFrame(r.ctx, r.render_settings(), rank, world, tile_size=16, device=torch.device("cpu"), gather="peer")
+    fb = ShardedFrame(r2.ctx, r2.render_settings(), rank, world, tile_size=16, device=torch.device("cpu"), gather="peer")
+    pipe = FramePipeline([fa, fb], [None, None])
+    done = [x for x in (pipe.submit() for _ in range(5)) if x is not None] + pipe.drain()
+    assert len(done) == 5 and all(d.primary_hits == stats.primary_hits for d in done)
+    dist.barrier()
+    if rank == 0:
+        for f in (fa, fb):
+            for v in f.views:
+                assert np.array_equal(v.numpy().view(np.uint32), full)
+    dist.barrier()
+    fa.close(); fb.close()
+    r2.close()
     if rank == 0:
         r.ray_trace()
         np.save(Path(out_dir) / "single.npy", r.get_image())
