@@ -260,6 +260,27 @@ int rt_bvh_info(const RtContext* ctx, RtBvhInfo* out);
  * The caller composes object_transform * previous^-1 exactly as the reference does. */
 int rt_transform_triangles(RtContext* ctx, const float m[16], int max_depth, int leaf_max_obj_count);
 
+/* ---- load -> upload: Wavefront OBJ + MTL (host side, csrc/scene_io.cpp) --------------------------------------------------
+ * rt_obj_load = read_meshio_data(path) (tp2/src/mesh_io.cpp:426-591, with read_materials_mtl :213-304) followed by
+ * MeshIOUtils::create_triangles(data, current_material_count, transform) (tp2/projets/utils/meshIOUtils.cpp:4-33): what
+ * MainWindow::load_obj does before Renderer::set_triangles (QT/mainwindow.cpp:251-282).  The arrays of the returned mesh have
+ * the layout rt_set_triangles / rt_set_materials take: a maintainer's load_obj becomes rt_obj_load -> (edit the materials) ->
+ * rt_precompute_materials -> rt_set_triangles -> rt_set_materials.  transform: row-major 4x4 or NULL (identity).
+ * err (may be NULL): receives the message when the call fails (RT_ERR_INVALID: file missing, parse error, no geometry). */
+typedef struct RtObjMesh RtObjMesh;
+int rt_obj_load(const char* path, const float transform[16], int32_t current_material_count, RtObjMesh** out, char* err, size_t err_cap);
+void rt_obj_free(RtObjMesh* mesh);
+size_t rt_obj_triangle_count(const RtObjMesh* mesh);
+size_t rt_obj_material_count(const RtObjMesh* mesh);             /* materials of the .mtl (+ "default" when a face needed it)  */
+const float* rt_obj_xyz9(const RtObjMesh* mesh);
+const float* rt_obj_uv6(const RtObjMesh* mesh);                  /* NULL when the file has no texture coordinates              */
+const int32_t* rt_obj_material_indices(const RtObjMesh* mesh);   /* already offset by current_material_count                   */
+const RtMaterial* rt_obj_materials(const RtObjMesh* mesh);       /* specular_threshold = 0 until rt_precompute_materials       */
+const char* rt_obj_material_name(const RtObjMesh* mesh, size_t i);
+/* MainWindow::precompute_materials -- QT/mainwindow.cpp:240-249: specular_threshold = pow(1e-3 / luminance(specular), 1 / ns),
+ * in the reference's mixed float / double arithmetic. */
+void rt_precompute_materials(RtMaterial* mats, size_t n);
+
 /* Renderer::set_materials / get_materials().materials -- renderer.cpp:150-152. */
 int rt_set_materials(RtContext* ctx, const RtMaterial* mats, size_t n);
 

@@ -67,6 +67,31 @@ public:
 
     void reconstruct_bvh_new() { check(rt_build_bvh(_ctx, _settings.bvh_max_depth, _settings.bvh_leaf_object_count)); }  // :243-246
 
+    // MainWindow::load_obj (QT/mainwindow.cpp:251-282): read_meshio_data + MeshIOUtils::create_triangles with the native
+    // loader (rt_obj_load), the GUI's overrides of material 0 (:258-261), Renderer::set_triangles, the mesh's materials
+    // appended to the renderer's, precompute_materials, reset_previous_transform.  `transform`: row-major 4x4 or null.
+    void load_obj(const char* filepath, const float* transform16 = nullptr)
+    {
+        RtObjMesh* mesh = nullptr;
+        char err[512] = {0};
+        const int rc = rt_obj_load(filepath, transform16, (int32_t)_materials.size(), &mesh, err, sizeof(err));
+        if (rc != RT_OK) throw Error(rc, err);
+        std::vector<RtMaterial> loaded(rt_obj_materials(mesh), rt_obj_materials(mesh) + rt_obj_material_count(mesh));
+        if (!loaded.empty()) {
+            loaded[0].roughness = 0.0f;
+            loaded[0].reflection = 0.9f;
+            for (int k = 0; k < 3; k++) { loaded[0].specular[k] = 0.2f; loaded[0].diffuse[k] = 0.5f; }
+        }
+        const int set = rt_set_triangles(_ctx, rt_obj_xyz9(mesh), rt_obj_uv6(mesh), rt_obj_material_indices(mesh), rt_obj_triangle_count(mesh));
+        rt_obj_free(mesh);
+        check(set);
+        reconstruct_bvh_new();
+        _materials.insert(_materials.end(), loaded.begin(), loaded.end());
+        rt_precompute_materials(_materials.data(), _materials.size());
+        check(rt_set_materials(_ctx, _materials.data(), _materials.size()));
+        reset_previous_transform();
+    }
+
     template <class MaterialsT>
     void set_materials(const MaterialsT& ms)                                             // renderer.cpp:150-152
     {
@@ -81,6 +106,7 @@ public:
             o.reflection = m.reflection; o.roughness = m.roughness; o.ns = m.ns; o.specular_threshold = m.specular_threshold;
         }
         check(rt_set_materials(_ctx, out.data(), out.size()));
+        _materials = out;
     }
 
     template <class ImageT> void set_ao_map(const ImageT& im) { set_map(RT_TEX_AO, im); }                // renderer.cpp:194-201
@@ -216,6 +242,7 @@ private:
     }
 
     RtContext* _ctx = nullptr;
+    std::vector<RtMaterial> _materials;                                                  // Renderer::_materials (what load_obj appends to)
     RtSettings _settings;
     RtRenderStats _stats{};
     std::vector<uint32_t> _image;

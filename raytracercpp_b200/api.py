@@ -146,6 +146,16 @@ ABI = {
     "rt_occluded": (C.c_int, [C.c_void_p, FP, FP, C.c_size_t, BP]),
     "rt_generate_primary_rays": (C.c_int, [C.c_void_p, C.POINTER(RtSettings), FP, FP]),
     "rt_resolve_ssaa": (C.c_int, [C.c_void_p, UP, C.c_int, C.c_int, C.c_int, UP]),
+    "rt_obj_load": (C.c_int, [C.c_char_p, FP, C.c_int32, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
+    "rt_obj_free": (None, [C.c_void_p]),
+    "rt_obj_triangle_count": (C.c_size_t, [C.c_void_p]),
+    "rt_obj_material_count": (C.c_size_t, [C.c_void_p]),
+    "rt_obj_xyz9": (FP, [C.c_void_p]),
+    "rt_obj_uv6": (FP, [C.c_void_p]),
+    "rt_obj_material_indices": (IP, [C.c_void_p]),
+    "rt_obj_materials": (C.POINTER(RtMaterial), [C.c_void_p]),
+    "rt_obj_material_name": (C.c_char_p, [C.c_void_p, C.c_size_t]),
+    "rt_precompute_materials": (None, [C.POINTER(RtMaterial), C.c_size_t]),
 }
 
 
@@ -187,6 +197,30 @@ def default_settings(lib=None, **kw) -> RtSettings:
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def load_obj(path, transform=None, current_material_count=0, lib=None):
+    """rt_obj_load: read_meshio_data + MeshIOUtils::create_triangles (mesh_io.cpp:426-591, utils/meshIOUtils.cpp:4-33).
+    Returns (xyz9 [n, 9], uv6 [n, 6] or None, mat [n], materials as a list of dicts, material names)."""
+    lib = lib or load_library()
+    tr = _f32(transform).reshape(16) if transform is not None else None
+    mesh, err = C.c_void_p(), C.create_string_buffer(512)
+    rc = lib.rt_obj_load(str(path).encode(), tr.ctypes.data_as(FP) if tr is not None else None, int(current_material_count), C.byref(mesh), err, len(err))
+    if rc != RT_OK:
+        raise RtError(rc, err.value.decode(errors="replace"))
+    try:
+        n, nm = lib.rt_obj_triangle_count(mesh), lib.rt_obj_material_count(mesh)
+        xyz9 = np.ctypeslib.as_array(lib.rt_obj_xyz9(mesh), shape=(n, 9)).copy()
+        uvp = lib.rt_obj_uv6(mesh)
+        uv6 = np.ctypeslib.as_array(uvp, shape=(n, 6)).copy() if uvp else None
+        mat = np.ctypeslib.as_array(lib.rt_obj_material_indices(mesh), shape=(n,)).copy()
+        mp = lib.rt_obj_materials(mesh)
+        mats = [dict(ambient_coeff=tuple(mp[i].ambient_coeff), diffuse=tuple(mp[i].diffuse), specular=tuple(mp[i].specular),
+                     emission=tuple(mp[i].emission), reflection=mp[i].reflection, roughness=mp[i].roughness, ns=mp[i].ns) for i in range(nm)]
+        names = [lib.rt_obj_material_name(mesh, i).decode() for i in range(nm)]
+    finally:
+        lib.rt_obj_free(mesh)
+    return xyz9, uv6, mat, mats, names
 
 
 def _p(a, t):

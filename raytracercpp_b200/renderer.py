@@ -72,6 +72,17 @@ class Renderer:
         self._have_triangles = True
         self.reconstruct_bvh_new()
 
+    def load_obj(self, filepath, transform=None):
+        """MainWindow::load_obj (QT/mainwindow.cpp:251-282): the native loader (rt_obj_load = read_meshio_data +
+        MeshIOUtils::create_triangles), the GUI's overrides of material 0, set_triangles, the mesh's materials appended to
+        the renderer's, precompute_materials, reset_previous_transform."""
+        xyz9, uv6, mat, mats, _ = api.load_obj(filepath, transform, len(self._materials), self.ctx.lib)
+        if mats:
+            mats[0].update(roughness=0.0, reflection=0.9, specular=(0.2, 0.2, 0.2), diffuse=(0.5, 0.5, 0.5))
+        self.set_triangles(xyz9, uv6, mat)
+        self.set_materials(precompute_materials(self._materials + mats))
+        self.reset_previous_transform()
+
     def reconstruct_bvh_new(self):
         s = self._settings                                 # renderer.cpp:243-246
         self.bvh_info = self.ctx.build_bvh(s.bvh_max_depth, s.bvh_leaf_object_count)

@@ -35,6 +35,7 @@ void drive_with_reference_types(rtb200::Renderer& renderer, const std::vector<Tr
     renderer.change_camera_fov(80.0f);
     renderer.ray_trace();
     renderer.post_process();
+    renderer.load_obj("data/Robot/robot.obj", nullptr);
     renderer.clear_image();
     renderer.raster_trace();
     renderer.post_process();
