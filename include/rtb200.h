@@ -223,6 +223,11 @@ enum {
                                  chunk's kernels fill the SMs the others leave idle while their longest packets finish; the
                                  per-stage times of RtRenderStats then overlap.  0: one chunk at a time; 1 (default): 2 chunks;
                                  n in [2,6]: n chunks.  Results do not depend on it                                     */
+    RT_OPT_PACKET_CULL = 19,  /* bounding-pyramid cull of the packet kernels: the rays of a packet leave from (primary: the camera) or
+                                 arrive at (shadow: the point light) one point, so they lie in a thin pyramid; the children of a cell
+                                 whose boxes lie outside one of its four side planes are dropped in one pass, 4 lanes per child, before
+                                 the per-ray slab tests.  Bit 0: primary packets, bit 1: shadow packets (default 3).  Results do not
+                                 depend on it                                                                                 */
     RT_OPT_GRAPH = 18,        /* 1 (default): a frame whose launch sequence equals the previous frame's (same settings, camera, light,
                                  buffers, options) is captured as a CUDA graph and replayed with one cudaGraphLaunch from then on;
                                  the per-stage times of RtRenderStats are 0 for such frames.  0: every frame is enqueued launch by

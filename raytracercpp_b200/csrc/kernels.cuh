@@ -199,6 +199,7 @@ struct Tuning {
     // unvisited cells can be traced by the warps that have nothing left to do.  0: the budgets above are all there is.
     int32_t packet_min, item_min, primary_min;
     int32_t item_passes;      // generations of work items actually launched (<= kItemPasses); the last has no budget
+    int32_t cull;             // bounding-pyramid cull of a cell's children (packet_set_cull): bit 0 primary packets, bit 1 shadow packets
 };
 
 // When a packet should give up before its round budget: the launch's queue (`counter` = tickets handed out, `total` =
@@ -307,6 +308,7 @@ k_primary(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
 // Incoherent rays (reflection fans, arbitrary batches) keep the per-ray state machine above.
 struct PacketStack {
     int saved;                      // entries [0, saved) are the unvisited cells of a packet that ran out of rounds
+    float4 plane[4];                // the packet's bounding pyramid (packet_set_cull): inside = x * n.x + y * n.y + z * n.z - w >= 0
     float4 stage[32];               // the cell (<= 8 records) or leaf chunk (<= 10 triangles) being tested, 512 bytes
     float t[RT_STACK_SIZE];
     uint32_t link[RT_STACK_SIZE];
@@ -321,6 +323,59 @@ RT_DEV float warp_min(float x)
     const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
     const uint32_t m = __reduce_min_sync(0xffffffffu, key);
     return __uint_as_float(m ^ ((m & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+
+// The bounding pyramid of a packet whose rays all leave from (or arrive at) one point: the primary rays of a pixel block
+// from the camera, the shadow rays of neighbouring hits towards the point light.  Axis = the first active lane's direction
+// from the apex; every lane's direction in the tangent plane of that axis; the warp's min / max give a rectangle there,
+// its four sides four planes through the apex.  A cell's child whose axis-aligned box (its first three slabs) lies outside
+// one of them cannot be hit by any ray of the packet: packet_trace drops such children with ONE pass in which lane
+// 4 * child + plane tests the box's farthest corner -- all <= 8 children at once, before any per-ray slab arithmetic.
+// Pure pruning with margins on every rounding (the rectangle is widened, the plane test has a relative and an absolute
+// slack), so results cannot change.  Returns false (warp-uniform) when the packet has no pyramid: no active lane, or a
+// direction more than ~84 degrees off the axis.  `slack`: how far a ray may leave the segment (point -> apex); 0 for primary
+// rays, 2e-4 for shadow rays, which start EPSILON = 1e-4 off the hit point but aim from the hit point itself (renderer.cpp:344).
+RT_DEV bool packet_set_cull(PacketStack& K, bool active, V3 apex, V3 point, float slack)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned am = __ballot_sync(0xffffffffu, active);
+    if (am == 0u) return false;
+    const int lead = __ffs(am) - 1;
+    const V3 v = point - apex;
+    V3 ez = v3(__shfl_sync(0xffffffffu, v.x, lead), __shfl_sync(0xffffffffu, v.y, lead), __shfl_sync(0xffffffffu, v.z, lead));
+    const float len2 = length2(ez);
+    if (!(len2 > 1e-30f)) return false;
+    ez = normalize(ez);
+    const V3 helper = fabsf(ez.x) < 0.5f ? v3(1, 0, 0) : v3(0, 1, 0);
+    const V3 ex = normalize(cross(helper, ez));
+    const V3 ey = cross(ez, ex);
+    const float vz = dot(v, ez), vx = dot(v, ex), vy = dot(v, ey);
+    const bool good = !active || (vz > 0.0f && vz * vz > 0.01f * length2(v));
+    if (__ballot_sync(0xffffffffu, !good) != 0u) return false;
+    const float tx = active ? vx / vz : 0.0f, ty = active ? vy / vz : 0.0f;
+    float x0 = warp_min(active ? tx : INFINITY), x1 = -warp_min(active ? -tx : INFINITY);
+    float y0 = warp_min(active ? ty : INFINITY), y1 = -warp_min(active ? -ty : INFINITY);
+    const float wx = 1.0e-5f * (1.0f + fmaxf(fabsf(x0), fabsf(x1))), wy = 1.0e-5f * (1.0f + fmaxf(fabsf(y0), fabsf(y1)));
+    x0 -= wx; x1 += wx; y0 -= wy; y1 += wy;
+    if (lane < 4u) {
+        V3 n;
+        if (lane == 0u) n = ex - x0 * ez;
+        else if (lane == 1u) n = x1 * ez - ex;
+        else if (lane == 2u) n = ey - y0 * ez;
+        else n = y1 * ez - ey;
+        const float inv = 1.0f / sqrtf(length2(n));
+        n = inv * n;
+        K.plane[lane] = make_float4(n.x, n.y, n.z, dot(n, apex) - slack);
+    }
+    __syncwarp();
+    return true;
+}
+
+// planes no box is outside of
+RT_DEV void packet_no_cull(PacketStack& K)
+{
+    if ((threadIdx.x & 31u) < 4u) K.plane[threadIdx.x & 31u] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    __syncwarp();
 }
 
 // slab_entry (rt_device.h) for packets, with a warp-uniform exit between the axis slabs and the diagonal slabs: the
@@ -369,11 +424,14 @@ RT_DEV uint32_t ld_vol(const unsigned int* p) { return *((const volatile unsigne
 // in parallel and the nearest entered without going through the stack -- +6 % frame time on cfg4: the sweep runs on every
 // cell whereas the insertion costs one short loop per ACCEPTED child, mostly 1-3 per cell.)
 template <bool ORDERED, bool COUNT>
-RT_DEV bool packet_cell(const float4* rec, uint32_t count, const SlabRay& sr, float t_max, bool active, PacketStack& K, int& sp, TraceCounters& tc)
+RT_DEV bool packet_cell(const float4* rec, uint32_t count, const SlabRay& sr, float t_max, bool active, PacketStack& K, int& sp, TraceCounters& tc,
+                        uint32_t keep)
 {
     const unsigned lane = threadIdx.x & 31u;
     const int base = sp;
-    for (uint32_t k = 0; k < count; k++) {
+    // keep: bit k set = child k is to be tested (all `count` children, or those the bounding pyramid has not dropped)
+    for (uint32_t m = keep; m != 0u; m &= m - 1u) {
+        const uint32_t k = (uint32_t)__ffs((int)m) - 1u;
         if (COUNT && active) tc.vol_tests++;
         uint32_t cl = 0u, cm = 0u;
         const float tn = slab_entry_packet<ORDERED>(rec + 4 * k, sr, t_max, active, cl, cm);
@@ -443,7 +501,7 @@ RT_DEV void load_top_table(const SceneView& sc, TopTable& T)
 // needs thousands of them (measured: one shadow packet through the pole of the 10 M-triangle sphere, 8 000 rounds =
 // 11 ms of a 17 ms kernel) is SPLIT: each unvisited cell becomes a work item that another warp traces for the same 32
 // rays (k_shade_items), and the answers are merged (any-hit: OR).
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool CULL = false>
 RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, const float4* top, bool& active, V3 o, V3 d, float t_max, V3 p, float dist2,
                          HitRec& best, bool& occluded, TraceCounters& tc, unsigned& overflow, int max_rounds, unsigned& rounds,
                          uint32_t start_link = 0u, uint32_t start_meta = 0u, int32_t best_orig = 0x7fffffff,
@@ -536,8 +594,30 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, const float4* top,
             }
             if (COUNT && lane == 0 && !in_top) tc.rec_fetch += count;
             __syncwarp();
-            const bool fits = ordered ? packet_cell<true, COUNT>(K.stage, count, sr, t_max, active, K, sp, tc)
-                                      : packet_cell<false, COUNT>(K.stage, count, sr, t_max, active, K, sp, tc);
+            uint32_t keep = (1u << count) - 1u;
+            if (CULL) {
+                // lane 4 * child + plane: the corner of the child's box that lies farthest along the plane's inward normal
+                const uint32_t child = lane >> 2;
+                const float4 pl = K.plane[lane & 3u];
+                const float4 b0 = K.stage[4u * child];
+                const float2 b1 = *reinterpret_cast<const float2*>(&K.stage[4u * child + 1u]);
+                // (the staged pairs may have been swapped into entry / exit order; slots >= count hold stale records: masked below)
+                const float ax = pl.x * (pl.x > 0.0f ? fmaxf(b0.x, b0.y) : fminf(b0.x, b0.y));
+                const float ay = pl.y * (pl.y > 0.0f ? fmaxf(b0.z, b0.w) : fminf(b0.z, b0.w));
+                const float az = pl.z * (pl.z > 0.0f ? fmaxf(b1.x, b1.y) : fminf(b1.x, b1.y));
+                const bool outside = (ax + ay + az) - pl.w < -4.0e-6f * (fabsf(ax) + fabsf(ay) + fabsf(az) + fabsf(pl.w));
+                unsigned m = __ballot_sync(0xffffffffu, outside);
+                m |= m >> 1;
+                m |= m >> 2;                                 // bit 4k: some plane has child k outside
+                // gather bit 4k of ~m into bit k
+                unsigned in = ~m & 0x11111111u;
+                in = (in | (in >> 3)) & 0x03030303u;
+                in = (in | (in >> 6)) & 0x000f000fu;
+                in = (in | (in >> 12)) & 0xffu;
+                keep &= in;
+            }
+            const bool fits = ordered ? packet_cell<true, COUNT>(K.stage, count, sr, t_max, active, K, sp, tc, keep)
+                                      : packet_cell<false, COUNT>(K.stage, count, sr, t_max, active, K, sp, tc, keep);
             if (!fits) { overflow = 1u; return true; }
             __syncwarp();
         } else {
@@ -663,8 +743,9 @@ k_primary_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCoun
             bool occ, live = active;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds,
-                                                             0u, 0u, 0x7fffffff, nullptr, nullptr, make_drain(&cnt->next_patch, total, tune.primary_min));
+            if (!((tune.cull & 1) != 0 && packet_set_cull(K, active, o, o + d, 0.0f))) packet_no_cull(K);
+            const bool finished = packet_trace<false, COUNT, true>(sc, K, top, live, o, d, INFINITY, o, 0.0f, best, occ, tc, overflow, tune.primary_rounds, rounds,
+                                                                   0u, 0u, 0x7fffffff, nullptr, nullptr, make_drain(&cnt->next_patch, total, tune.primary_min));
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 0, rounds, global_ns() - t0);
             if (!finished) {
@@ -736,8 +817,9 @@ k_primary_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCount
         HitRec best;
         bool occ, live = active;
         unsigned rounds = 0;
-        bool finished = packet_trace<false, COUNT>(sc, K, top, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start,
-                                                   nullptr, nullptr, make_drain(&cnt->p_items_next[pass], n, tune.item_min));
+        if (!((tune.cull & 1) != 0 && packet_set_cull(K, active, o, o + d, 0.0f))) packet_no_cull(K);
+        bool finished = packet_trace<false, COUNT, true>(sc, K, top, live, o, d, t_start, o, 0.0f, best, occ, tc, overflow, budget, rounds, item.y, item.z, orig_start,
+                                                         nullptr, nullptr, make_drain(&cnt->p_items_next[pass], n, tune.item_min));
         __syncwarp();
         if (active && best.tri >= 0) atomicMin(mine, closest_key(best.t, sc.orig[best.tri]));
         if (!finished && !emit_items(q, cnt->p_items_n, K, pass + 1, sidx)) {
@@ -1265,9 +1347,10 @@ k_shade_packet(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounte
             HitRec unused;
             unsigned rounds = 0;
             const unsigned long long t0 = COUNT ? global_ns() : 0ull;
-            const bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
-                                                            tune.packet_rounds, rounds, 0u, 0u, 0x7fffffff, nullptr, nullptr,
-                                                            make_drain(&cnt->next_shade, n, tune.packet_min));
+            if (!((tune.cull & 2) != 0 && packet_set_cull(K, active, fr.light, so, 2.0e-4f))) packet_no_cull(K);
+            const bool finished = packet_trace<true, COUNT, true>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow,
+                                                                  tune.packet_rounds, rounds, 0u, 0u, 0x7fffffff, nullptr, nullptr,
+                                                                  make_drain(&cnt->next_shade, n, tune.packet_min));
             __syncwarp();
             if (COUNT && lane == 0) note_packet(cnt, 1, rounds, global_ns() - t0);
             if (!finished) {
@@ -1333,8 +1416,9 @@ k_shade_items(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounter
         HitRec unused;
         bool occluded = false;
         unsigned rounds = 0;
-        bool finished = packet_trace<true, COUNT>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
-                                                  item.y, item.z, 0x7fffffff, nullptr, nullptr, make_drain(&cnt->items_next[pass], n, tune.item_min));
+        if (!((tune.cull & 2) != 0 && packet_set_cull(K, active, fr.light, so, 2.0e-4f))) packet_no_cull(K);
+        bool finished = packet_trace<true, COUNT, true>(sc, K, top, active, so, sd, t_lim, L.p, dist2, unused, occluded, tc, overflow, budget, rounds,
+                                                        item.y, item.z, 0x7fffffff, nullptr, nullptr, make_drain(&cnt->items_next[pass], n, tune.item_min));
         __syncwarp();
         if (!finished && !emit_items(q, cnt->items_n, K, pass + 1, sidx)) {
             const bool before = occluded;                                      // no room: finish the item here

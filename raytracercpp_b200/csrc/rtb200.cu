@@ -192,7 +192,7 @@ struct RtContext {
     size_t stack_limit_set = 0;
     bool opt_count_work = false;
     int opt_leaf_split = 8;
-    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0, 0, 0, 0, kItemPasses};
+    Tuning tune{16, 16, 8, 1, -256, -16, -256, 0, 0, 0, 0, kItemPasses, 3};
     uint32_t frame_serial = 0;           // tags the ready flags of the fused item queues: (serial << 2) | stage
     uint64_t opt_chunk_pixels = kChunkPixels;
     Pending pending;
@@ -871,6 +871,10 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->opt_lanes = value == 1 ? kLanes : (int)std::max<int64_t>(value, 1);   // 0: one chunk at a time; 1: the default (2); n: n chunks in flight
         return RT_OK;
     case RT_OPT_GRAPH: ctx->opt_graph = value != 0; return RT_OK;
+    case RT_OPT_PACKET_CULL:
+        if (value < 0 || value > 3) return fail(ctx, RT_ERR_INVALID, "packet cull %lld outside [0,3]", (long long)value);
+        ctx->tune.cull = (int32_t)value;
+        return RT_OK;
     case RT_OPT_RASTER_UNITS:
         if (value < 1 || value > (1ll << 28)) return fail(ctx, RT_ERR_INVALID, "raster unit list of %lld entries outside [1, 2^28]", (long long)value);
         ctx->d_runits.release();
