@@ -621,14 +621,39 @@ RT_DEV bool packet_trace(const SceneView& sc, PacketStack& K, const float4* top,
             if (!fits) { overflow = 1u; return true; }
             __syncwarp();
         } else {
-            // ---- one leaf: triangles staged the same way, 10 per round; every lane tests every triangle for its own ray
+            // ---- one leaf: triangles staged the same way, 10 per round (8 with the bounding pyramid); every lane tests every
+            // triangle for its own ray.  With the pyramid, lane 4 * triangle + plane first looks whether the triangle's three
+            // vertices all lie outside its plane: no ray of the packet can hit such a triangle, and the per-ray loop runs over
+            // the others only.
             const uint32_t cnt = meta & ~RT_LEAF_BIT;
-            for (uint32_t first = 0; first < cnt; first += 10u) {
-                const uint32_t m = min(10u, cnt - first);
+            const uint32_t per_round = CULL ? 8u : 10u;
+            for (uint32_t first = 0; first < cnt; first += per_round) {
+                const uint32_t m = min(per_round, cnt - first);
                 if (lane < 3u * m) K.stage[lane] = RT_LDG4(sc.tris + 3 * (size_t)(link + first) + lane);
                 if (COUNT && lane == 0) tc.tri_fetch += m;
                 __syncwarp();
-                for (uint32_t i = 0; i < m; i++) {
+                uint32_t keep = (1u << m) - 1u;
+                if (CULL) {
+                    const uint32_t tri = lane >> 2;
+                    const float4 pl = K.plane[lane & 3u];
+                    const float4 va = K.stage[3u * tri], vb = K.stage[3u * tri + 1u], vc = K.stage[3u * tri + 2u];   // slots >= m: stale, masked below
+                    const float da = (pl.x * va.x + pl.y * va.y + pl.z * va.z) - pl.w;
+                    const float db = (pl.x * vb.x + pl.y * vb.y + pl.z * vb.z) - pl.w;
+                    const float dc = (pl.x * vc.x + pl.y * vc.y + pl.z * vc.z) - pl.w;
+                    const float mag = fabsf(pl.w) + fmaxf(fabsf(va.x), fmaxf(fabsf(vb.x), fabsf(vc.x))) + fmaxf(fabsf(va.y), fmaxf(fabsf(vb.y), fabsf(vc.y))) +
+                                      fmaxf(fabsf(va.z), fmaxf(fabsf(vb.z), fabsf(vc.z)));
+                    const bool outside = fmaxf(da, fmaxf(db, dc)) < -4.0e-6f * mag;
+                    unsigned om = __ballot_sync(0xffffffffu, outside);
+                    om |= om >> 1;
+                    om |= om >> 2;
+                    unsigned in = ~om & 0x11111111u;
+                    in = (in | (in >> 3)) & 0x03030303u;
+                    in = (in | (in >> 6)) & 0x000f000fu;
+                    in = (in | (in >> 12)) & 0xffu;
+                    keep &= in;
+                }
+                for (uint32_t km = keep; km != 0u; km &= km - 1u) {
+                    const uint32_t i = (uint32_t)__ffs((int)km) - 1u;
                     const float4 p0 = K.stage[3 * i], p1 = K.stage[3 * i + 1], p2 = K.stage[3 * i + 2];
                     if (COUNT && active) tc.tri_tests++;
                     float t, u, v;

@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
 TAG=${1:-r2}
-BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-work"
+BCMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ref-work --frames-in-flight 1 --opt 18=0"
 $BCMD > $OUT/ncu_plain.json 2> $OUT/ncu_plain.err || { tail -20 $OUT/ncu_plain.err; exit 1; }
 echo "== ncu launch list"
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $BCMD > $OUT/ncu_launches.log 2>&1
