@@ -228,6 +228,9 @@ enum {
                                  whose boxes lie outside one of its four side planes are dropped in one pass, 4 lanes per child, before
                                  the per-ray slab tests.  Bit 0: primary packets, bit 1: shadow packets (default 3).  Results do not
                                  depend on it                                                                                 */
+    RT_OPT_FAN_LANES = 20,    /* 1 (default): with max_recursion_depth 1 and no normal mapping a rough-reflection fan runs with one LANE
+                                 per fan ray (k_reflect_fan: the stream offsets and the stale hit record of the reference's sequential
+                                 walk are found as a fixed point); 0: one thread walks the fan (k_reflect).  Results do not depend on it */
     RT_OPT_GRAPH = 18,        /* 1 (default): a frame whose launch sequence equals the previous frame's (same settings, camera, light,
                                  buffers, options) is captured as a CUDA graph and replayed with one cudaGraphLaunch from then on;
                                  the per-stage times of RtRenderStats are 0 for such frames.  0: every frame is enqueued launch by

@@ -1177,6 +1177,200 @@ k_reflect(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* c
     if (overflow) atomicOr(&cnt->stack_overflow, 1u);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_reflect_fan: the rough-reflection fan of a hit with one LANE per fan ray (recursion limit 1, the stated setting of
+// BASELINE.json's configs[2]).  compute_reflection (rt_device.h) walks a fan sequentially because the reference does and
+// two things chain its samples together:
+//   (1) the random stream: sample i draws 3 numbers, and when the hit it is SHADED with has a rough reflective material, the
+//       nested fan of that hit draws 3 * sample_count more before it finds out that the recursion limit cuts it off
+//       (renderer.cpp:283-338 under :1008-1015) -- so where sample i starts in the stream depends on samples 0 .. i-1;
+//   (2) the stale hit record: reflection_hit_info lives across the samples (:286), so sample i is shaded with the closest
+//       hit seen by samples 0 .. i (a prefix minimum over t, first wins).
+// Both are functions of the samples' own closest hits, so the fan is a fixed point: every lane assumes a start offset
+// (3 i at first), draws its direction, traces its ray; a segmented scan gives every lane its prefix-minimum hit, from its
+// material the draws its nested fan consumes, a prefix sum the true offsets.  Lanes whose offset moved trace again; sample 0
+// is right after the first round, sample i after at most i + 1, in practice after one or two (most fan rays hit the sky or
+// a material that does not reflect).  Then every lane shades its sample, and lane 0 adds the colours in sample order.
+// Same arithmetic as the sequential walk, so the same bits.  Left to k_reflect: recursion limits other than 1 (nested fans
+// really trace), normal mapping (shading rewrites the shared record's normal, a third chain), more than 32 samples, the
+// instrumented instantiation.
+RT_DEV Hit shfl_hit(const Hit& h, int src, int width)
+{
+    Hit r;
+    r.tri = __shfl_sync(0xffffffffu, h.tri, src, width); r.t = __shfl_sync(0xffffffffu, h.t, src, width);
+    r.u = __shfl_sync(0xffffffffu, h.u, src, width); r.v = __shfl_sync(0xffffffffu, h.v, src, width);
+    r.mat = __shfl_sync(0xffffffffu, h.mat, src, width);
+    r.normal = v3(__shfl_sync(0xffffffffu, h.normal.x, src, width), __shfl_sync(0xffffffffu, h.normal.y, src, width), __shfl_sync(0xffffffffu, h.normal.z, src, width));
+    r.tangent = v3(__shfl_sync(0xffffffffu, h.tangent.x, src, width), __shfl_sync(0xffffffffu, h.tangent.y, src, width), __shfl_sync(0xffffffffu, h.tangent.z, src, width));
+    return r;
+}
+
+#ifndef RTB_FAN_MINB
+#define RTB_FAN_MINB 6     /* resident CTAs per SM the compiler must allow for k_reflect_fan; measured on cfg3 at 1080p: 3 (168 registers) 4.99 ms, 4: 4.21, 5: 4.04, 6 (80): 3.99 */
+#endif
+__global__ void __launch_bounds__(kQueueThreads, RTB_FAN_MINB)
+k_reflect_fan(SceneView sc, FrameView fr, WorkView wk, QueueView q, ChunkCounters* cnt)
+{
+    const uint32_t n = cnt->n_refl;
+    const int S = fr.s.rough_reflections_sample_count;
+    const int G = S <= 16 ? 16 : 32;                          // lanes per fan: two fans per warp up to 16 samples
+    const unsigned lane = threadIdx.x & 31u;
+    const int sub = (int)(lane & (unsigned)(G - 1));          // this lane's sample
+    const uint32_t group = lane / (unsigned)G, per_warp = 32u / (unsigned)G;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned overflow = 0;
+    for (uint32_t first = warp_id * per_warp; first < n; first += n_warps * per_warp) {       // warp-uniform trip count
+        const uint32_t r = first + group;
+        const bool fan = r < n;
+        const uint32_t entry = fan ? q.refl_idx[r] : 0u;
+        TraceCounters tc = zero_counters();
+        V3 o = v3(0, 0, 0), d = v3(0, 0, 1), p = v3(0, 0, 0);
+        HitRec hr;
+        hr.tri = -1; hr.t = -1.0f; hr.u = 1.0f; hr.v = 0.0f;
+        uint32_t pix = 0;
+        Hit hit = fresh_hit();
+        MatView m = {};
+        float roughness = 0.0f;
+        if (fan) {
+            queue_ray(fr, wk, q, entry, o, d, hr, pix);
+            hit = make_hit(sc, hr, o, d);
+            shade_direct(sc, fr, o, d, hit, p, m);            // (no normal mapping on this path: hit.normal is the geometric one)
+            if (fr.s.enable_roughness_mapping) {
+                float tu, tv;
+                hit_texcoords(sc, hit, hit.u, hit.v, tu, tv);
+                roughness = tex_floor(sc.tex[RT_TEX_ROUGHNESS], tu, tv).r;
+            } else
+                roughness = m.roughness;
+        }
+        const bool rough = fan && roughness > 0.0f;
+        // a mirror hit is one sample without a random number: the sequential code, on the fan's first lane
+        if (fan && !rough && sub == 0) {
+            XorShift32 rng;
+            rng.state = pixel_seed(pix, fr.s.rng_seed);
+            const Col c = compute_reflection<false>(sc, fr, d, p, hit, m, 0, rng, &tc);
+            q.refl_rgb[3 * (size_t)entry + 0] = c.r; q.refl_rgb[3 * (size_t)entry + 1] = c.g; q.refl_rgb[3 * (size_t)entry + 2] = c.b;
+            q.refl_cnt[3 * (size_t)entry + 0] = (unsigned long long)tc.refl_rays | ((unsigned long long)tc.refl_shadow_rays << 32);
+            q.refl_cnt[3 * (size_t)entry + 1] = 0ull; q.refl_cnt[3 * (size_t)entry + 2] = 0ull;
+            overflow |= tc.stack_overflow;
+        }
+        const bool mine = rough && sub < S;                   // this lane owns a sample of a rough fan
+        const V3 nrm = hit.normal;
+        const V3 origin = p + 0.01f * nrm;                    // renderer.cpp:291
+        const V3 mirror = d - (2 * dot(d, nrm)) * nrm;
+        const uint32_t seed = pixel_seed(pix, fr.s.rng_seed);
+        int my_off = 3 * sub, traced_off = -1;
+        V3 dir = v3(0, 0, 1);
+        Hit own = fresh_hit();                                // this sample's own closest hit (triangles, then the shapes)
+        bool found = false;
+        Hit fh = fresh_hit();                                 // the record this sample is shaded with
+        for (int round = 0; round <= S; round++) {
+            if (mine && my_off != traced_off) {
+                XorShift32 rng;
+                rng.state = seed;
+                for (int k = 0; k < my_off; k++) rng.next();
+                const float rz = rng.bilateral();             // Vector(rand, rand, rand), renderer.cpp:313: evaluated right to left
+                const float ry = rng.bilateral();
+                const float rx = rng.bilateral();
+                V3 rv = normalize(v3(rx, ry, rz));
+                if (dot(rv, nrm) < 0) rv = -rv;
+                dir = roughness * rv + (1 - roughness) * mirror;
+                own = fresh_hit();
+                HitRec h2;
+                found = trace_closest<false>(sc, origin, dir, h2, &tc);
+                if (found) own = complete_hit(sc, h2);
+                for (int i = 0; i < sc.n_shapes; i++) {       // renderer.cpp:1029-1037
+                    float t;
+                    V3 sn;
+                    int32_t sm;
+                    if (shape_intersect(sc, i, origin, dir, t, sn, sm) && (t < own.t || own.t == -1.0f)) {
+                        own.tri = -2 - i; own.t = t; own.normal = sn; own.mat = sm;
+                        found = true;
+                    }
+                }
+                traced_off = my_off;
+            }
+            // prefix minimum over the samples so far, first wins: which sample's record is each sample shaded with
+            float bt = (mine && found) ? own.t : INFINITY;
+            int bi = sub;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const float ot = __shfl_up_sync(0xffffffffu, bt, k, G);
+                const int oi = __shfl_up_sync(0xffffffffu, bi, k, G);
+                if (k < G && sub >= k && !(bt < ot)) { bt = ot; bi = oi; }      // the earlier one stays unless the later is strictly closer
+            }
+            const bool have = bt != INFINITY;
+            const Hit src = shfl_hit(own, bi, G);
+            fh = have ? src : fresh_hit();
+            // draws the nested fan of that record consumes (the recursion limit stops its rays, not its random numbers)
+            int consume = 0;
+            if (mine && fr.s.shading_method == RT_SHADING && fh.t > 0.1f) {
+                const MatView m2 = load_material(sc, fh.mat);
+                if (m2.reflection > 0.0f) {
+                    float r2 = m2.roughness;
+                    if (fr.s.enable_roughness_mapping) {
+                        float tu, tv;
+                        hit_texcoords(sc, fh, fh.u, fh.v, tu, tv);
+                        r2 = tex_floor(sc.tex[RT_TEX_ROUGHNESS], tu, tv).r;
+                    }
+                    if (r2 > 0.0f) consume = 3 * S;
+                }
+            }
+            int before = consume;                             // exclusive prefix sum over the fan's lanes
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const int a = __shfl_up_sync(0xffffffffu, before, k, G);
+                if (k < G && sub >= k) before += a;
+            }
+            before -= consume;
+            const int new_off = 3 * sub + before;
+            const bool moved = mine && new_off != my_off;
+            my_off = new_off;
+            if (__ballot_sync(0xffffffffu, moved) == 0u) break;
+        }
+        // every sample's colour: trace_ray_secondary from the gate on (renderer.cpp:1039-1065), with the record above
+        Col c = col(0.0f);
+        if (mine) {
+            tc.refl_rays++;
+            if (fh.t > 0.1f) {
+                if (fr.s.shading_method != RT_SHADING) c = shade_debug(sc, fr, fh);
+                else {
+                    V3 p2;
+                    MatView m2;
+                    const Col direct = shade_direct(sc, fr, origin, dir, fh, p2, m2);
+                    bool shadowed = false;
+                    if (fr.s.compute_shadows) {
+                        tc.refl_shadow_rays++;
+                        shadowed = trace_occluded<false>(sc, p2, fh.normal, fr.light, &tc) || (sc.n_shapes > 0 && shapes_occlude(sc, p2, fh.normal, fr.light));
+                    }
+                    // the nested fan returns (0 / samples) * reflection: its rays are beyond the recursion limit
+                    c = shade_compose(fr, m2, direct, shadowed, col(0.0f));
+                }
+            } else
+                c = shade_miss(sc, fr, dir);
+        }
+        overflow |= tc.stack_overflow;
+        // the sum in sample order, on the fan's first lane (renderer.cpp:315-337)
+        Col total = col(0.0f);
+        for (int i = 0; i < S; i++) {
+            const Col ci = col(__shfl_sync(0xffffffffu, c.r, i, G), __shfl_sync(0xffffffffu, c.g, i, G), __shfl_sync(0xffffffffu, c.b, i, G));
+            total = total + ci;
+        }
+        unsigned rays = tc.refl_rays, shadow_rays = tc.refl_shadow_rays;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const unsigned a = __shfl_down_sync(0xffffffffu, rays, k, G), b = __shfl_down_sync(0xffffffffu, shadow_rays, k, G);
+            if (k < G && sub + k < G) { rays += a; shadow_rays += b; }
+        }
+        if (rough && sub == 0) {
+            const Col res = total / col((float)S) * col(m.reflection);
+            q.refl_rgb[3 * (size_t)entry + 0] = res.r; q.refl_rgb[3 * (size_t)entry + 1] = res.g; q.refl_rgb[3 * (size_t)entry + 2] = res.b;
+            q.refl_cnt[3 * (size_t)entry + 0] = (unsigned long long)rays | ((unsigned long long)shadow_rays << 32);
+            q.refl_cnt[3 * (size_t)entry + 1] = 0ull; q.refl_cnt[3 * (size_t)entry + 2] = 0ull;
+        }
+    }
+    if (overflow) atomicOr(&cnt->stack_overflow, 1u);
+}
+
 // Shade + hard shadow + compose + quantise for the queued hits.  Same persistent / refill scheme as k_primary over
 // the hit queue: a refilled lane shades its hit (textures, Blinn-Phong) and starts the any-hit state machine of its
 // shadow ray; when that ends the lane composes the pixel (with the fan colour k_reflect left, if the material

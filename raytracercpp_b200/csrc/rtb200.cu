@@ -200,7 +200,7 @@ struct RtContext {
     size_t h_frame_cap = 0;
     cudaEvent_t copy_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per slice of that copy
     int grids[2][11] = {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};   // persistent-grid sizes of the kernels, by COUNT flag
-    int grid_intersect = 0, grid_occluded = 0;           // the same for the batch kernels (per context: its device's occupancy)
+    int grid_intersect = 0, grid_occluded = 0, grid_fan = 0;           // the same for the batch kernels (per context: its device's occupancy)
     bool opt_screen_cull = true;
     int opt_lanes = kLanes;
     bool opt_top_table = false;
@@ -222,6 +222,7 @@ struct RtContext {
     // The frame as a CUDA graph (RT_OPT_GRAPH): when a frame's launch sequence is byte for byte the one of the frame before
     // (same settings, camera, light, buffers, options), it is captured once and replayed with one cudaGraphLaunch.
     bool opt_graph = true;
+    bool opt_fan_lanes = true;           // RT_OPT_FAN_LANES
     bool capturing = false;              // stage timers are off while the launches are being captured
     struct FrameGraph { std::string key; cudaGraphExec_t exec; uint32_t launches; };
     std::vector<FrameGraph> graphs;      // the last few captured frames (a sharded frame alternates between two output buffers)
@@ -871,6 +872,7 @@ int rt_set_option(RtContext* ctx, int option, int64_t value)
         ctx->opt_lanes = value == 1 ? kLanes : (int)std::max<int64_t>(value, 1);   // 0: one chunk at a time; 1: the default (2); n: n chunks in flight
         return RT_OK;
     case RT_OPT_GRAPH: ctx->opt_graph = value != 0; return RT_OK;
+    case RT_OPT_FAN_LANES: ctx->opt_fan_lanes = value != 0; return RT_OK;
     case RT_OPT_PACKET_CULL:
         if (value < 0 || value > 3) return fail(ctx, RT_ERR_INVALID, "packet cull %lld outside [0,3]", (long long)value);
         ctx->tune.cull = (int32_t)value;
@@ -1322,7 +1324,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         put64(ctx->opt_top_table); put64((unsigned long long)(uintptr_t)d_argb_out); put64((unsigned long long)(uintptr_t)super);
         put64((unsigned long long)(uintptr_t)ctx->d_counters.p); put64((unsigned long long)(uintptr_t)pd.host_cnt); put64(g_alloc_generation);
         put64((unsigned long long)(uintptr_t)main_stream); put64((unsigned long long)split_cap); put64((unsigned long long)item_cap); put64(px_per_tile);
-        put64((unsigned long long)ctx->stack_limit_set);
+        put64((unsigned long long)ctx->stack_limit_set); put64(ctx->opt_fan_lanes);
         if (ssao) { put(&ctx->proj, sizeof(ctx->proj)); put(&ctx->proj_fov, sizeof(float)); put(&ctx->proj_aspect, sizeof(float)); }
         for (size_t i = 0; i < ctx->graphs.size() && !replay; i++)
             if (ctx->graphs[i].key == key) { replay = true; graph_at = i; }
@@ -1434,7 +1436,13 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         }
         if (reflect) {
             ScopedTimer tm(ctx, ST_REFLECT, st);
-            if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
+            // one lane per fan ray where the fan is a fixed point of its own hits (k_reflect_fan); else one thread per fan
+            const bool fan_lanes = ctx->opt_fan_lanes && !count && s->max_recursion_depth == 1 && !s->enable_normal_mapping &&
+                                   s->rough_reflections_sample_count >= 1 && s->rough_reflections_sample_count <= 32;
+            if (fan_lanes) {
+                if (!ctx->grid_fan) ctx->grid_fan = grid_for(ctx, (const void*)k_reflect_fan, kQueueThreads);
+                k_reflect_fan<<<ctx->grid_fan, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
+            } else if (count) k_reflect<true><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
             else k_reflect<false><<<grid_reflect, kQueueThreads, 0, st>>>(sc, fr, wk, q, cnt);
             launches++;
         }

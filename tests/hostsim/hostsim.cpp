@@ -132,7 +132,7 @@ const char* rt_last_error(const RtContext* c) { return c ? c->error.c_str() : ""
 int rt_set_option(RtContext* c, int option, int64_t value)
 {
     if (option == RT_OPT_LEAF_SPLIT) { c->leaf_split = (int)value; c->bvh_valid = false; return RT_OK; }
-    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_LANES || option == RT_OPT_ITEM_ROUNDS || option == RT_OPT_PRIMARY_ROUNDS || option == RT_OPT_FUSED_ITEMS || option == RT_OPT_TOP_TABLE || option == RT_OPT_SHADOW_SORT || option == RT_OPT_DEVICE_BUILD || option == RT_OPT_ITEM_PASSES || option == RT_OPT_RASTER_UNITS || option == RT_OPT_GRAPH || option == RT_OPT_PACKET_CULL) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
+    return (option == RT_OPT_COUNT_WORK || option == RT_OPT_CHUNK_PIXELS || option == RT_OPT_REFILL_PRIMARY || option == RT_OPT_REFILL_SHADE || option == RT_OPT_TRI_BATCH || option == RT_OPT_PACKETS || option == RT_OPT_PACKET_ROUNDS || option == RT_OPT_SCREEN_CULL || option == RT_OPT_LANES || option == RT_OPT_ITEM_ROUNDS || option == RT_OPT_PRIMARY_ROUNDS || option == RT_OPT_FUSED_ITEMS || option == RT_OPT_TOP_TABLE || option == RT_OPT_SHADOW_SORT || option == RT_OPT_DEVICE_BUILD || option == RT_OPT_ITEM_PASSES || option == RT_OPT_RASTER_UNITS || option == RT_OPT_GRAPH || option == RT_OPT_PACKET_CULL || option == RT_OPT_FAN_LANES) ? RT_OK : fail(c, RT_ERR_INVALID, "unknown option");
 }
 
 int rt_set_stream(RtContext*, void*) { return RT_OK; }

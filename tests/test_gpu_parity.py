@@ -876,3 +876,36 @@ def test_raster_trace_full_size(cuda_lib, oracle, robot):
         common.assert_image_close(img, want, what=name + " raster")
         assert (img == want).mean() >= 0.999
         assert st.primary_hits > 100_000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["cfg3", "samples5", "samples20", "samples1", "no_roughness_map", "shapes"])
+def test_fan_lanes_equal_sequential_fans(cuda_lib, oracle, robot, variant):
+    """k_reflect_fan (one lane per fan ray: the reference's sequential stream offsets and stale hit record found as a fixed
+    point) against k_reflect (one thread walks the fan): same frame bit for bit, same ray counts; and against the oracle."""
+    table = common.config_table(robot["materials"])
+    kw, mats, tex = table["cfg3"]
+    if variant == "samples5":
+        kw = dict(kw, rough_reflections_sample_count=5)
+    elif variant == "samples20":
+        kw = dict(kw, rough_reflections_sample_count=20, image_width=160, image_height=90)
+    elif variant == "samples1":
+        kw = dict(kw, rough_reflections_sample_count=1)
+    elif variant == "no_roughness_map":
+        kw = dict(kw, enable_roughness_mapping=0)
+    elif variant == "shapes":
+        kw, mats, tex = table["cfg3_shapes"]
+        kw = dict(kw, max_recursion_depth=1, rough_reflections_sample_count=8, rng_seed=11)
+    r = common.product_renderer(cuda_lib, robot, kw, mats, tex)
+    r.ctx.set_option(api.RT_OPT_GRAPH, 0)
+    r.ray_trace()
+    lanes, st_lanes = r.get_image().copy(), r.last_stats()
+    r.ctx.set_option(api.RT_OPT_FAN_LANES, 0)
+    r.ray_trace()
+    seq, st_seq = r.get_image().copy(), r.last_stats()
+    r.close()
+    assert np.array_equal(lanes, seq)
+    assert st_lanes.reflection_rays == st_seq.reflection_rays > 0 and st_lanes.reflection_shadow_rays == st_seq.reflection_shadow_rays
+    want = common.oracle_image(oracle, robot, kw, mats, tex)
+    common.assert_image_close(lanes, want, what="fan lanes " + variant)
+    assert (lanes == want).mean() >= 0.999
