@@ -7,6 +7,7 @@
 #include <sched.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -33,7 +34,7 @@ constexpr uint64_t kChunkPixels = 1ull << 28;     // supersampled pixels per wav
 constexpr int kMaxChunks = 256;
 
 thread_local std::string g_create_error;
-unsigned long long g_alloc_generation = 0;        // bumped whenever a device buffer moves: invalidates the captured frame graphs
+std::atomic<unsigned long long> g_alloc_generation{0};   // bumped whenever a device buffer moves: invalidates the captured frame graphs
 
 double now_ms()
 {
@@ -1322,7 +1323,7 @@ int rt_render_device_begin(RtContext* ctx, const RtSettings* s, uint32_t* d_argb
         put64(n_chunks); put64(classify); put64(n_traced); put64(tl->count); put64((unsigned long long)(uintptr_t)tl->d); put64((unsigned long long)(uintptr_t)tl->d_split);
         put64(sort_hits); put64((unsigned long long)ctx->opt_shadow_sort); put64(tail); put64(psplit); put64(reflect); put64(ssao); put64(resolve); put64(count); put64(has_shapes);
         put64(ctx->opt_top_table); put64((unsigned long long)(uintptr_t)d_argb_out); put64((unsigned long long)(uintptr_t)super);
-        put64((unsigned long long)(uintptr_t)ctx->d_counters.p); put64((unsigned long long)(uintptr_t)pd.host_cnt); put64(g_alloc_generation);
+        put64((unsigned long long)(uintptr_t)ctx->d_counters.p); put64((unsigned long long)(uintptr_t)pd.host_cnt); put64(g_alloc_generation.load());
         put64((unsigned long long)(uintptr_t)main_stream); put64((unsigned long long)split_cap); put64((unsigned long long)item_cap); put64(px_per_tile);
         put64((unsigned long long)ctx->stack_limit_set); put64(ctx->opt_fan_lanes);
         if (ssao) { put(&ctx->proj, sizeof(ctx->proj)); put(&ctx->proj_fov, sizeof(float)); put(&ctx->proj_aspect, sizeof(float)); }
