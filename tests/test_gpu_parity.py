@@ -909,3 +909,60 @@ def test_fan_lanes_equal_sequential_fans(cuda_lib, oracle, robot, variant):
     want = common.oracle_image(oracle, robot, kw, mats, tex)
     common.assert_image_close(lanes, want, what="fan lanes " + variant)
     assert (lanes == want).mean() >= 0.999
+
+
+@pytest.mark.gpu
+def test_pyramid_cull_and_frame_graphs_never_change_a_frame(cuda_lib, oracle, robot):
+    """RT_OPT_PACKET_CULL (the bounding-pyramid cull of a cell's children and a leaf's triangles, primary and shadow packets)
+    and RT_OPT_GRAPH (a repeated frame replayed as a CUDA graph) are pure scheduling: frames, hits and ray counts equal the
+    frame without them bit for bit -- from outside the scene, from INSIDE it (the pyramids' apex inside cells, every direction
+    of the frame's packets against the clip of the boxes), with the light inside the scene's box (shadow pyramids with their
+    apex among the occluders), with split packets and items, on a hair ball (thin, incoherent), and with SSAA."""
+    from raytracercpp_b200 import scenes
+    mats = robot["materials"]
+    tab = common.config_table(mats)
+    hx, huv, hmat = scenes.hair_ball(n_strands=1500, segments=8)
+    hair = dict(xyz9=hx, uv6=huv, mat=hmat)
+    hair_mats = rt.precompute_materials([scenes.DEFAULT_SPHERE_MATERIAL])
+    cases = [
+        ("outside", robot, tab["cfg1"][0], mats, {}, None, common.LIGHT),
+        ("inside", robot, tab["cfg2"][0], mats, tab["cfg2"][2], common.CAM_INSIDE, common.LIGHT),
+        ("light_inside", robot, dict(tab["cfg1"][0], enable_ssaa=1, ssaa_factor=3), mats, {}, None, (0.1, -1.2, -3.9)),
+        ("hair", hair, dict(image_width=320, image_height=180, compute_shadows=1), hair_mats, {}, None, common.LIGHT),
+    ]
+    for name, scene, kw, m, tex, cam, light in cases:
+        r = common.product_renderer(cuda_lib, scene, kw, m, tex, cam=cam, light=light)
+        r.ctx.set_option(api.RT_OPT_GRAPH, 0)
+        r.ctx.set_option(api.RT_OPT_PACKET_CULL, 0)
+        r.ray_trace()
+        base, st0 = r.get_image().copy(), r.last_stats().as_dict()
+        assert st0["primary_hits"] > 500, name
+        for cull, budgets in ((1, None), (2, None), (3, None), (3, (3, 2))):
+            r.ctx.set_option(api.RT_OPT_PACKET_CULL, cull)
+            if budgets:
+                r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, budgets[0]); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, budgets[0])
+                r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, budgets[1])
+            r.ray_trace()
+            st = r.last_stats().as_dict()
+            assert np.array_equal(r.get_image(), base), (name, cull, budgets)
+            for k in ("primary_rays", "shadow_rays", "primary_hits", "traced_primary_rays"):
+                assert st[k] == st0[k], (name, k)
+        r.ctx.set_option(api.RT_OPT_PACKET_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_PRIMARY_ROUNDS, -256); r.ctx.set_option(api.RT_OPT_ITEM_ROUNDS, -16)
+        # the same frame three more times with graphs on: the second is captured, the third replayed; then a moved light
+        # (another key: enqueued the ordinary way) and back (the captured graph again)
+        r.ctx.set_option(api.RT_OPT_GRAPH, 1)
+        launches = []
+        for _ in range(3):
+            r.ray_trace()
+            assert np.array_equal(r.get_image(), base), name
+            launches.append(r.last_stats().kernel_launches)
+        assert launches[0] == launches[1] == launches[2]
+        r.set_light_position((light[0] + 0.5, light[1], light[2]))
+        r.ray_trace()
+        moved = r.get_image().copy()
+        assert not np.array_equal(moved, base), name
+        r.set_light_position(light)
+        r.ray_trace()
+        assert np.array_equal(r.get_image(), base), name
+        r.close()
+        common.assert_image_close(base, common.oracle_image(oracle, scene, kw, m, tex, cam=cam, light=light), what="cull test " + name)
