@@ -17,6 +17,7 @@
 
 #include "../../raytracercpp_b200/csrc/rt_device.h"
 #include "../../raytracercpp_b200/csrc/raster_device.h"
+#include "../../raytracercpp_b200/csrc/ssao_device.h"
 #include "../../raytracercpp_b200/csrc/host_common.h"
 #include "../../raytracercpp_b200/csrc/scene_layout.h"
 
@@ -43,6 +44,7 @@ struct RtContext {
     M4 proj_inv{}, cam_to_world{};
     V3 cam_pos{0, 0, 0}, light{3, 3, 2};
     M4 proj{};
+    float proj_fov = 45.0f, proj_aspect = 1.0f;
     bool proj_set = false;
     int leaf_split = 8;
     std::vector<HostShape> shapes;
@@ -244,9 +246,10 @@ int rt_set_camera(RtContext* c, const float proj_inv[16], const float cam_to_wor
     return RT_OK;
 }
 int rt_set_light(RtContext* c, const float p[3]) { c->light = v3(p[0], p[1], p[2]); return RT_OK; }
-int rt_set_projection(RtContext* c, float fov, float aspect, float znear, float zfar)      // SSAO is not emulated here (ssao.cuh is CUDA only)
+int rt_set_projection(RtContext* c, float fov, float aspect, float znear, float zfar)
 {
-    c->proj = perspective_matrix(fov, aspect, znear, zfar);                                // raster_trace reads Camera::_perspective_proj_mat
+    c->proj = perspective_matrix(fov, aspect, znear, zfar);                                // raster_trace and the SSAO pass read Camera::_perspective_proj_mat
+    c->proj_fov = fov; c->proj_aspect = aspect;
     c->proj_set = true;
     return RT_OK;
 }
@@ -262,7 +265,9 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
 {
     std::string why;
     if (int r = check_settings(s, why)) return fail(c, r, why);
-    if (s->enable_ssao) return fail(c, RT_ERR_UNSUPPORTED, "the host emulation has no SSAO pass");
+    const bool ssao = s->enable_ssao != 0;
+    if (ssao && tile_mod != 1) return fail(c, RT_ERR_UNSUPPORTED, "enable_ssao needs the whole frame on one device");
+    if (ssao && !c->proj_set) return fail(c, RT_ERR_STATE, "enable_ssao: the projection has not been set (rt_set_projection)");
     SceneFacts f;
     f.bvh_valid = c->bvh_valid; f.camera_set = c->camera_set; f.n_tris = (uint32_t)(c->xyz9.size() / 9); f.n_mats = c->n_mats;
     f.min_mat_index = c->min_mat; f.max_mat_index = c->max_mat;
@@ -290,6 +295,10 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
     }
     RtRenderStats rs;
     memset(&rs, 0, sizeof(rs));
+    // G-buffers of the SSAO pass (clear_z_buffer / clear_normal_buffer, renderer.cpp:165-173)
+    std::vector<float> gz;
+    std::vector<V3> gn;
+    if (ssao) { gz.assign((size_t)fr.rw * fr.rh, INFINITY); gn.assign((size_t)fr.rw * fr.rh, v3(0, 0, 0)); }
 
 
     if (s->hybrid_rasterization_tracing) {
@@ -340,6 +349,7 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
             const RasterShadeOut o = raster_shade<true>(scf, fr, rv, (uint32_t)leaf_of[order >> 4], (int)(order & 15u), (uint32_t)pix, fx[pix], fy[pix], frag_slot, 0u, &tc);
             if (tc.stack_overflow) return fail(c, RT_ERR_STATE, "traversal stack overflow");
             super[pix] = quantise_argb(o.colour);
+            if (ssao) { gz[pix] = raster_key_depth(keys[pix]); gn[pix] = o.normal; }     // renderer.cpp:976-979
             rs.primary_rays += o.shaded; rs.primary_hits += o.hit; rs.shadow_rays += o.shadow_ray;
             rs.reflection_rays += tc.refl_rays; rs.reflection_shadow_rays += tc.refl_shadow_rays;
             sv2 += tc.vol_tests; st2 += tc.tri_tests;
@@ -426,11 +436,28 @@ int rt_render_device(RtContext* c, const RtSettings* s, uint32_t* out, int tile_
             Col refl = m.reflection > 0.0f ? refl_rgb[i] : col(0.0f);
             cc = shade_compose(fr, m, direct, shadowed, refl);
         }
+        if (ssao) { gz[e.pix] = -(o.z + d.z * e.hr.t); gn[e.pix] = hit.normal; }         // renderer.cpp:1104-1111, after the normal-map update
         super[e.pix] = quantise_argb(cc);
     }
     if (!raster) {
         rs.shadow_rays = (s->shading_method == RT_SHADING && s->compute_shadows) ? rs.primary_hits : 0;
         rs.shadow_volume_tests = sv; rs.shadow_triangle_tests = stt;
+    }
+    // k_ssao_occlusion, k_ssao_apply (ssao_device.h): Renderer::post_process runs SSAO before the SSAA resolve
+    if (ssao) {
+        SsaoView sv;
+        sv.rw = fr.rw; sv.rh = fr.rh; sv.z = gz.data(); sv.n = gn.data();
+        sv.proj = c->proj;
+        sv.aspect = c->proj_aspect;
+        sv.fov_mult_simd = (float)std::tan(c->proj_fov / 2 / 180 * M_PI);                    // renderer.cpp:1249
+        sv.fov_mult_scalar = std::tan(((float)M_PI / 180) * (c->proj_fov / 2));              // radians(), mat.cpp:13-16, std::tan(float)
+        sv.samples = s->ssao_sample_count; sv.radius = s->ssao_radius; sv.amount = s->ssao_amount;
+        sv.rng_seed = s->rng_seed;
+        const size_t npx = (size_t)fr.rw * fr.rh;
+        std::vector<int> ao(npx);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long long i = 0; i < (long long)npx; i++) ao[(size_t)i] = ssao_count_pixel(sv, (size_t)i);
+        for (size_t i = 0; i < npx; i++) ssao_apply_pixel(sv, ao.data(), super, i);
     }
     // k_resolve
     if (fr.factor > 1) {

@@ -80,12 +80,11 @@ def test_call_order_and_unsupported_switches(hostsim_lib, robot):
         r.ray_trace()                                     # RT_SHADING without materials (reference: assert, materials.h:117)
     r.set_materials(robot["materials"])
     r.ray_trace()
-    for field in ("enable_ssao",):
-        setattr(s, field, 1)
-        with pytest.raises(api.RtError) as e:
-            r.ray_trace()
-        assert e.value.code == api.RT_ERR_UNSUPPORTED
-        setattr(s, field, 0)
+    s.enable_ssao = 1                                      # whole frames only: a tile shard's samples would read its neighbours' z-buffer
+    with pytest.raises(api.RtError) as e:
+        r.ctx.render_device(s, r.get_image().ctypes.data, 16, 2, 0)
+    assert e.value.code == api.RT_ERR_UNSUPPORTED
+    s.enable_ssao = 0
     s.enable_ao_mapping = 1
     with pytest.raises(api.RtError):
         r.ray_trace()                                     # mapping enabled, no map
@@ -369,3 +368,34 @@ def test_raster_trace_vs_oracle(hostsim_lib, oracle, robot, golden_raster, name)
         assert np.array_equal(img, golden_raster[name + "_reference"])
     if kw.get("shading_method", 0) == 0:
         assert st.primary_rays > 0 and st.shadow_rays == st.primary_hits
+
+
+@pytest.mark.parametrize("name", ["ssao_ssaa2", "ssao_normal_mapped", "ssao_leftover_columns", "ssao_debug_shading", "r_ssao"])
+def test_ssao_vs_oracle(hostsim_lib, oracle, robot, golden_ssao, golden_raster, name):
+    """The device source of the SSAO pass (csrc/ssao_device.h: one lane of the reference's AVX2 loop, its scalar loop for the
+    left-over columns, the 7x7 blur) compiled for the host, on the G-buffers the emulated shade stage / rasterizer writes:
+    bit-exact against the oracle's per-pixel stream and against the frames stored with the reference's goldens."""
+    table = common.ssao_table(robot["materials"])
+    cam = None
+    scene = robot
+    if name == "ssao_leftover_columns":
+        kw, mats, tex = table["ssao_ssaa2"]
+        kw = dict(kw, image_width=99, image_height=57, enable_ssaa=0)
+    elif name == "ssao_debug_shading":
+        kw, mats, tex = table["ssao_ssaa2"]
+        kw = dict(kw, shading_method=api.RT_ABS_NORMALS_SHADING)
+    elif name == "r_ssao":
+        scene, kw, mats, tex, cam = common.raster_table(robot)[name]
+    else:
+        kw, mats, tex = table[name]
+    img, _ = common.product_image(hostsim_lib, scene, kw, mats, tex, cam=cam)
+    if name == "r_ssao":
+        want = common.oracle_renderer(oracle, scene, kw, mats, tex, cam=cam).raster()[0]
+        assert np.array_equal(img, golden_raster[name + "_per_pixel"])
+    else:
+        want, _ = common.oracle_renderer(oracle, scene, kw, mats, tex).render_ssao()
+        if name in table:
+            assert np.array_equal(img, golden_ssao[name + "_per_pixel"])
+    assert np.array_equal(img, want)
+    plain, _ = common.product_image(hostsim_lib, scene, dict(kw, enable_ssao=0), mats, tex, cam=cam)
+    assert (plain != img).mean() > 0.02
