@@ -2,7 +2,8 @@
  * rtb200.h -- C ABI of the B200-native ray-tracing hot path (librtb200.so).
  *
  * This is the drop-in boundary for ONE path of TomClabault/RayTracerCPP: everything that sits behind
- * `Renderer::ray_trace()` + `Renderer::post_process()` (SSAA only) and `BVH::intersect()`.
+ * `Renderer::ray_trace()` / `Renderer::raster_trace()` + `Renderer::post_process()` (SSAO, SSAA), `BVH::BVH` and
+ * `BVH::intersect()`, plus the OBJ / MTL loader that feeds it.
  * The reference has no FFI of its own; the seam is the public section of `class Renderer`
  * (tp2/projets/renderer/renderer.h:38-169) and `class BVH` (tp2/projets/bvh.h:302,307).  Each entry
  * point below names the reference member it replaces.  A header-only C++ adapter with the reference's
@@ -32,7 +33,7 @@ typedef enum RtStatus {
     RT_ERR_INVALID = -1,      /* bad argument / unsupported setting            */
     RT_ERR_CUDA = -2,         /* CUDA runtime error (message in rt_last_error) */
     RT_ERR_STATE = -3,        /* call order (e.g. render before set_triangles) */
-    RT_ERR_UNSUPPORTED = -4   /* a RenderSettings switch outside the path      */
+    RT_ERR_UNSUPPORTED = -4   /* a combination the path cannot serve (see rt_render) */
 } RtStatus;
 
 /* Blinn-Phong material: the fields of `Material` (tp2/src/materials.h:14-38) that the path reads. */
