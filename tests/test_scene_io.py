@@ -125,3 +125,74 @@ def test_adapter_load_obj(hostsim_lib):
     r.ray_trace()
     assert (r.get_image() != first).any()
     r.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_obj_files_live(lib, ref_strict, tmp_path, seed):
+    """Randomly written OBJ + MTL files (polygons of 3-7 vertices, the four vertex forms, negative indices, CRLF lines,
+    comments, materials switched back and forth, faces before any usemtl, unknown material names, several mtllib lines)
+    through the native loader and through the compiled reference's loader: the same triangles, texture coordinates,
+    material indices and material table.  Files either carry texture coordinates on every face vertex or on none -- the
+    reference reads past its texcoord array when a file mixes the two."""
+    rng = np.random.default_rng(seed)
+    with_uv = bool(seed % 2)
+    n_pos, n_tex, n_nrm = int(rng.integers(8, 40)), int(rng.integers(4, 20)), int(rng.integers(1, 6))
+    eol = "\r\n" if seed % 3 == 0 else "\n"
+    names = ["alpha", "beta gamma", "delta"]
+    mtl = ["# materials" + eol]
+    for k, nm in enumerate(names):
+        mtl.append(f"newmtl {nm}{eol}")
+        for key in ("Ka", "Kd", "Ks", "Ke")[: int(rng.integers(1, 5))]:
+            mtl.append(f"  {key} " + " ".join(f"{x:.6f}" for x in rng.uniform(0, 1, 3)) + eol)
+        if k != 1:
+            mtl.append(f"Ns {rng.uniform(1, 400):.3f}{eol}")
+        mtl.append(f"Ni 1.45{eol}d 1.0{eol}illum 2{eol}map_Kd tex_{k}.png{eol}")
+    (tmp_path / "m.mtl").write_text("".join(mtl))
+    lines = ["# random mesh" + eol]
+    if seed != 4:
+        lines.append("mtllib m.mtl" + eol)                     # seed 4: no material library at all
+    pos_written = tex_written = nrm_written = 0
+
+    def emit_vertices(count):
+        nonlocal pos_written, tex_written, nrm_written
+        for _ in range(count):
+            lines.append("v " + " ".join(f"{x:.5f}" for x in rng.uniform(-2, 2, 3)) + eol)
+            pos_written += 1
+        for _ in range(max(1, count // 2)):
+            lines.append("vt " + " ".join(f"{x:.5f}" for x in rng.uniform(0, 1, 2)) + eol)
+            tex_written += 1
+        lines.append("vn " + " ".join(f"{x:.5f}" for x in rng.normal(size=3)) + eol)
+        nrm_written += 1
+
+    emit_vertices(n_pos)
+    for f in range(int(rng.integers(10, 40))):
+        if rng.random() < 0.25:
+            lines.append(f"usemtl {names[int(rng.integers(0, 3))] if rng.random() < 0.85 else 'nobody'}{eol}")
+        if rng.random() < 0.2:
+            emit_vertices(int(rng.integers(1, 5)))
+        if rng.random() < 0.1:
+            lines.append("# a comment" + eol + eol)
+        verts = []
+        for _ in range(int(rng.integers(3, 8))):
+            p = int(rng.integers(1, pos_written + 1))
+            t = int(rng.integers(1, tex_written + 1))
+            n = int(rng.integers(1, nrm_written + 1))
+            if rng.random() < 0.3:
+                p, t, n = p - pos_written - 1, t - tex_written - 1, n - nrm_written - 1     # the same vertices, counted from the end
+            form = int(rng.integers(0, 2))
+            if with_uv:
+                verts.append(f"{p}/{t}/{n}" if form else f"{p}/{t}")
+            else:
+                verts.append(f"{p}//{n}" if form else f"{p}")
+        lines.append(("f " if rng.random() < 0.8 else "f   ") + " ".join(verts) + ("  " if rng.random() < 0.3 else "") + eol)
+    path = tmp_path / "mesh.obj"
+    path.write_text("".join(lines))
+    tr = np.float32([[0.7, 0.1, 0, 0.3], [0, 1.1, 0.2, -1], [0.1, 0, 0.9, -5], [0, 0, 0, 1]])
+    xyz9, uv6, mat, mats, _ = api.load_obj(path, tr, current_material_count=2, lib=lib)
+    rx, ruv, rmat, rmats = ref_strict.load_obj(str(path), tr)
+    assert len(xyz9) == len(rx) > 10
+    assert np.array_equal(xyz9, rx) and np.array_equal(mat, rmat + 2)
+    assert (uv6 is not None) == with_uv
+    if with_uv:
+        assert np.array_equal(uv6, ruv)
+    assert np.array_equal(material_rows(mats), material_rows(rmats))
