@@ -966,3 +966,31 @@ def test_pyramid_cull_and_frame_graphs_never_change_a_frame(cuda_lib, oracle, ro
         assert np.array_equal(r.get_image(), base), name
         r.close()
         common.assert_image_close(base, common.oracle_image(oracle, scene, kw, m, tex, cam=cam, light=light), what="cull test " + name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_raster_trace_random_soups(cuda_lib, oracle, seed):
+    """The hybrid path on triangle soups that surround the camera (triangles behind it, through it, across every clip plane,
+    degenerate ones, coincident duplicates whose fragments tie on depth): the GPU's z-keys must pick the reference's winner
+    in every pixel, with clipping on and off.  (tests/test_hostsim_parity.py runs the same soups through the host build of
+    the device source, against the oracle and the compiled reference, bit for bit.)"""
+    rng = np.random.default_rng(seed)
+    n = 260
+    c = rng.uniform(-3, 3, size=(n, 1, 3)) + np.float32([0, 0, -1.0])
+    soup = (c + rng.normal(scale=rng.uniform(0.1, 2.5, size=(n, 1, 1)), size=(n, 3, 3))).reshape(n, 9).astype(np.float32)
+    soup[::17, 3:9] = np.tile(soup[::17, 0:3], 2)
+    dup = soup[5:45].copy()
+    xyz9 = np.concatenate([soup, dup]).astype(np.float32)
+    uv6 = rng.uniform(0, 1, size=(len(xyz9), 6)).astype(np.float32)
+    mat = np.concatenate([np.zeros(n, np.int32), np.ones(len(dup), np.int32)])
+    mats = rt.precompute_materials([dict(scenes.DEFAULT_SPHERE_MATERIAL, diffuse=(0.9, 0.2, 0.1)), dict(scenes.DEFAULT_SPHERE_MATERIAL, diffuse=(0.1, 0.3, 0.9))])
+    scene = dict(xyz9=xyz9, uv6=uv6, mat=mat)
+    for clipping in (1, 0):
+        kw = dict(image_width=136, image_height=88, compute_shadows=1, hybrid_rasterization_tracing=1, enable_clipping=clipping,
+                  enable_ssaa=int(seed == 2), ssaa_factor=2)
+        img, st = common.product_image(cuda_lib, scene, kw, mats, {})
+        want = common.oracle_image(oracle, scene, kw, mats, {})
+        common.assert_image_close(img, want, what=f"raster soup {seed} clipping {clipping}")
+        assert (img == want).mean() >= 0.999
+        assert st.primary_rays > 5000

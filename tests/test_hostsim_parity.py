@@ -399,3 +399,35 @@ def test_ssao_vs_oracle(hostsim_lib, oracle, robot, golden_ssao, golden_raster, 
     assert np.array_equal(img, want)
     plain, _ = common.product_image(hostsim_lib, scene, dict(kw, enable_ssao=0), mats, tex, cam=cam)
     assert (plain != img).mean() > 0.02
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_raster_trace_random_soups(hostsim_lib, oracle, seed):
+    """raster_trace on triangle soups that surround the camera: triangles behind it, through it, across every clip plane
+    (pieces up to the 12 the reference's arrays hold), degenerate ones, and coincident duplicates whose fragments tie on
+    depth -- the first in (triangle, piece) order must win, as in the reference's sequential loop.  The host build of the
+    device source against the oracle, and (where it is built) against the compiled reference on one thread, bit for bit."""
+    from oracle import bindings
+    rng = np.random.default_rng(seed)
+    n = 260
+    c = rng.uniform(-3, 3, size=(n, 1, 3)) + np.float32([0, 0, -1.0])
+    soup = (c + rng.normal(scale=rng.uniform(0.1, 2.5, size=(n, 1, 1)), size=(n, 3, 3))).reshape(n, 9).astype(np.float32)
+    soup[::17, 3:9] = np.tile(soup[::17, 0:3], 2)                    # degenerate
+    dup = soup[5:45].copy()                                          # coincident copies with other materials, later in the order
+    xyz9 = np.concatenate([soup, dup]).astype(np.float32)
+    uv6 = rng.uniform(0, 1, size=(len(xyz9), 6)).astype(np.float32)
+    mat = np.concatenate([np.zeros(n, np.int32), np.ones(len(dup), np.int32)])
+    mats = rt.precompute_materials([dict(scenes.DEFAULT_SPHERE_MATERIAL, diffuse=(0.9, 0.2, 0.1)), dict(scenes.DEFAULT_SPHERE_MATERIAL, diffuse=(0.1, 0.3, 0.9))])
+    scene = dict(xyz9=xyz9, uv6=uv6, mat=mat)
+    for clipping in (1, 0):
+        kw = dict(image_width=136, image_height=88, compute_shadows=1, hybrid_rasterization_tracing=1, enable_clipping=clipping,
+                  enable_ssaa=int(seed == 2), ssaa_factor=2)
+        img, st = common.product_image(hostsim_lib, scene, kw, mats, {})
+        want = common.oracle_image(oracle, scene, kw, mats, {})
+        assert np.array_equal(img, want), (seed, clipping)
+        # without clipping the triangles behind the camera project through w < 0 to negative depths, win their pixels and are
+        # then missed by the pixels' rays (black, as in the reference): only the clipped frame has hits to speak of
+        assert st.primary_rays > 5000 and (st.primary_hits > 1000 or not clipping)
+        if bindings.available("ref_strict"):
+            ref = common.oracle_image(bindings.CpuTracer("ref_strict"), scene, kw, mats, {})
+            assert np.array_equal(img, ref), (seed, clipping, "compiled reference")
